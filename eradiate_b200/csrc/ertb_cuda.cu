@@ -1,0 +1,744 @@
+// ertb_cuda.cu -- C ABI (include/eradiate_b200.h) of the sm_100a path tracer:
+// scene upload, parameter updates, render launches and the KAT entry points.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared
+//        -Xcompiler -fPIC  (see __graft_entry__.build()).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ertb_kernel.cuh"
+
+// ----------------------------------------------------------------------------
+// error handling
+// ----------------------------------------------------------------------------
+static thread_local std::string g_error;
+
+static int set_error(const std::string &msg) {
+    g_error = msg;
+    return 1;
+}
+#define CUDA_TRY(expr)                                                                    \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            return set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ----------------------------------------------------------------------------
+// scene object
+// ----------------------------------------------------------------------------
+struct HostPhase {
+    int type = 0;
+    float params[4] = { 0, 0, 0, 0 };
+    std::vector<float> values, nodes;
+};
+
+struct HostSensor {
+    ertb_sensor_desc desc;
+    std::vector<double> directions; // normalised
+    float *d_table = nullptr;       // device primary-ray table
+    double ray_offset = 0.0;
+    int use_table = 0;
+};
+
+struct ertb_scene {
+    int device = 0;
+    int geometry = 0;
+    double surface_z = 0, medium_bottom = 0, medium_top = 0;
+    double bs_center[3] = { 0, 0, 0 };
+    double bs_radius = 0;
+    int has_medium = 0, n_layers = 0, homogeneous = 0;
+    float scale = 1.f;
+    std::vector<float> sigma_t, albedo, phase_weight;
+    int n_phase = 0;
+    HostPhase phase[ERTB_MAX_PHASE];
+    int bsdf_type = 0;
+    float bsdf_params[ERTB_MAX_BSDF_PARAMS];
+    double emitter_dir[3];
+    float irradiance = 1.f;
+    int integrator = 0, rr_depth = 5;
+    long long max_depth = -1;
+    std::vector<HostSensor> sensors;
+
+    // derived / device state
+    bool dirty = true;
+    ErtbParams base;            // everything but the per-launch fields
+    std::vector<float> blob;    // host copy of the table blob
+    float *d_blob = nullptr;
+    size_t d_blob_capacity = 0;
+    unsigned long long *d_counter = nullptr; // work counter + stats (1 + 8)
+    double *d_accum = nullptr;
+    size_t d_accum_capacity = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+};
+
+static size_t align4(size_t n) { return (n + 3) & ~size_t(3); }
+
+// distr_1d.h:548-600 compute_cdf_scalar: trapezoid CDF accumulated in double
+static void build_tab_leaf(const HostPhase &hp, ErtbPhaseLeaf &L, std::vector<float> &blob) {
+    const int n = (int) hp.values.size();
+    const bool irregular = hp.type == ERTB_PHASE_TABULATED_IRREGULAR;
+    L.n_nodes = n;
+    L.inv_interval = (float) ((n - 1) / 2.0);
+    L.off_pdf = (int) blob.size();
+    blob.insert(blob.end(), hp.values.begin(), hp.values.end());
+    blob.resize(align4(blob.size()), 0.f);
+    L.off_cdf = (int) blob.size();
+    double integral = 0.0, interval = 2.0 / (n - 1);
+    int v0 = -1, v1 = -1;
+    std::vector<float> cdf(n - 1);
+    for (int i = 0; i < n - 1; ++i) {
+        double w = irregular ? ((double) hp.nodes[i + 1] - (double) hp.nodes[i]) : interval;
+        double value = 0.5 * w * ((double) hp.values[i] + (double) hp.values[i + 1]);
+        integral += value;
+        cdf[i] = (float) integral;
+        if (value > 0.0) {
+            if (v0 < 0) v0 = i;
+            v1 = i;
+        }
+    }
+    blob.insert(blob.end(), cdf.begin(), cdf.end());
+    blob.resize(align4(blob.size()), 0.f);
+    L.valid0 = v0;
+    L.valid1 = v1;
+    L.integral = cdf[v1];
+    L.normalization = 1.f / L.integral;
+    L.off_nodes = -1;
+    if (irregular) {
+        L.off_nodes = (int) blob.size();
+        blob.insert(blob.end(), hp.nodes.begin(), hp.nodes.end());
+        blob.resize(align4(blob.size()), 0.f);
+    }
+}
+
+static int validate_tab(const HostPhase &hp) {
+    const int n = (int) hp.values.size();
+    if (n < 2) return set_error("ContinuousDistribution: needs at least two entries!");
+    if (n > ERTB_MAX_PHASE_NODES) return set_error("tabulated phase function: too many nodes");
+    bool mass = false;
+    for (int i = 0; i < n; ++i) {
+        if (!(hp.values[i] >= 0.f)) return set_error("ContinuousDistribution: entries must be non-negative!");
+        if (hp.values[i] > 0.f) mass = true;
+    }
+    if (!mass) return set_error("ContinuousDistribution: no probability mass found!");
+    if (hp.type == ERTB_PHASE_TABULATED_IRREGULAR) {
+        if ((int) hp.nodes.size() != n) return set_error("'nodes' and 'values' must have the same length");
+        for (int i = 0; i < n - 1; ++i)
+            if (!(hp.nodes[i + 1] > hp.nodes[i]))
+                return set_error("IrregularContinuousDistribution: node positions must be strictly increasing!");
+        if (hp.nodes[0] != -1.f || hp.nodes[n - 1] != 1.f) return set_error("'nodes' bounds must be [-1, 1]");
+    }
+    return 0;
+}
+
+// Rebuild derived tables + base kernel parameters and upload them.
+static int scene_commit(ertb_scene *S) {
+    CUDA_TRY(cudaSetDevice(S->device));
+    ErtbParams &P = S->base;
+    memset(&P, 0, sizeof P);
+    const bool sph = S->geometry == ERTB_GEOM_SPHERICAL_SHELL;
+    P.spherical = sph;
+    P.R = (float) S->surface_z;
+    P.Rd = S->surface_z;
+    P.has_medium = S->has_medium;
+    P.H = S->has_medium ? (float) (S->medium_top - S->surface_z) : 0.f;
+    P.n_layers = S->has_medium ? S->n_layers : 1;
+    P.h_off = (float) (S->surface_z - S->medium_bottom);
+    P.inv_dz = S->has_medium ? (float) (S->n_layers / (S->medium_top - S->medium_bottom)) : 0.f;
+    P.n_phase = S->n_phase;
+    P.off_ocean = -1;
+
+    std::vector<float> &blob = S->blob;
+    blob.clear();
+    double majorant = 0.0;
+    if (S->has_medium) {
+        const int n = S->n_layers;
+        float mx = S->sigma_t[0];
+        for (int i = 1; i < n; ++i) mx = fmaxf(mx, S->sigma_t[i]);
+        majorant = (double) S->scale * (double) mx; // heterogeneous.cpp:163 / homogeneous.cpp:157
+        P.off_preal = (int) blob.size();
+        for (int i = 0; i < n; ++i) {
+            double st = (double) S->scale * (double) S->sigma_t[i];
+            double pr = majorant > 0.0 ? st / majorant : 0.0;
+            if (S->homogeneous) pr = majorant > 0.0 ? 1.0 : 0.0;
+            blob.push_back((float) fmin(fmax(pr, 0.0), 1.0));
+        }
+        blob.resize(align4(blob.size()), 0.f);
+        P.off_albedo = (int) blob.size();
+        blob.insert(blob.end(), S->albedo.begin(), S->albedo.end());
+        blob.resize(align4(blob.size()), 0.f);
+        P.off_cumw = (int) blob.size();
+        if (S->n_phase > 1) {
+            std::vector<double> cum(n, 0.0);
+            for (int k = 0; k < S->n_phase - 1; ++k)
+                for (int i = 0; i < n; ++i) {
+                    cum[i] += (double) S->phase_weight[(size_t) k * n + i];
+                    blob.push_back((float) cum[i]);
+                }
+            blob.resize(align4(blob.size()), 0.f);
+        }
+        for (int k = 0; k < S->n_phase; ++k) {
+            ErtbPhaseLeaf &L = P.leaf[k];
+            const HostPhase &hp = S->phase[k];
+            L.type = hp.type;
+            L.p0 = hp.params[0];
+            L.off_nodes = -1;
+            if (hp.type == ERTB_PHASE_TABULATED || hp.type == ERTB_PHASE_TABULATED_IRREGULAR) {
+                if (validate_tab(hp)) return 1;
+                build_tab_leaf(hp, L, blob);
+            }
+        }
+    }
+    P.majorant = (float) majorant;
+    P.inv_majorant = majorant > 0.0 ? (float) (1.0 / majorant) : INFINITY;
+
+    const size_t blob_bytes = blob.size() * sizeof(float);
+    if (blob_bytes > (size_t) S->max_smem_optin - 1024)
+        return set_error("scene tables do not fit in one SM's shared memory");
+    if (blob_bytes > S->d_blob_capacity) {
+        if (S->d_blob) cudaFree(S->d_blob);
+        CUDA_TRY(cudaMalloc(&S->d_blob, blob_bytes));
+        S->d_blob_capacity = blob_bytes;
+    }
+    if (blob_bytes) CUDA_TRY(cudaMemcpy(S->d_blob, blob.data(), blob_bytes, cudaMemcpyHostToDevice));
+    P.blob = S->d_blob;
+    P.blob_bytes = (int) blob_bytes;
+
+    P.bsdf_type = S->bsdf_type;
+    memcpy(P.bsdf, S->bsdf_params, sizeof P.bsdf);
+    double dn = sqrt(S->emitter_dir[0] * S->emitter_dir[0] + S->emitter_dir[1] * S->emitter_dir[1] +
+                     S->emitter_dir[2] * S->emitter_dir[2]);
+    for (int i = 0; i < 3; ++i) P.sun[i] = (float) (-S->emitter_dir[i] / dn);
+    P.irradiance = S->irradiance;
+    P.mis = S->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
+    P.rr_depth = (unsigned) S->rr_depth;
+    P.max_depth = S->max_depth < 0 ? 0xffffffffu : (unsigned) S->max_depth;
+    S->dirty = false;
+    return 0;
+}
+
+// mdistant.cpp:180-190: ray_offset default
+static double sensor_ray_offset(const ertb_scene *S, const ertb_sensor_desc &sd) {
+    if (sd.ray_offset >= 0.0) return sd.ray_offset;
+    const double eps = 1.1920929e-7 * 0.5 * 1500.0; // math::RayEpsilon<float>
+    double rad = fmax(eps, S->bs_radius * (1.0 + eps));
+    return sd.target_type == ERTB_TARGET_NONE ? rad : 2.0 * rad;
+}
+
+static int build_sensor(ertb_scene *S, HostSensor &hs) {
+    const ertb_sensor_desc &sd = hs.desc;
+    hs.ray_offset = sensor_ray_offset(S, sd);
+    const int npix = sd.width * sd.height;
+    const bool sph = S->geometry == ERTB_GEOM_SPHERICAL_SHELL;
+    if (sd.type == ERTB_SENSOR_MDISTANT) {
+        if (sd.n_directions != sd.width || sd.height != 1)
+            return set_error("Film size must be [sensor_count, 1]");
+        hs.use_table = (!sph) || sd.target_type == ERTB_TARGET_POINT;
+        std::vector<float> table((size_t) npix * 8, 0.f);
+        const double Rt = S->has_medium ? S->medium_top : S->surface_z;
+        for (int i = 0; i < npix; ++i) {
+            double dx = hs.directions[3 * i], dy = hs.directions[3 * i + 1], dz = hs.directions[3 * i + 2];
+            float *t = &table[(size_t) i * 8];
+            t[3] = (float) dx; t[4] = (float) dy; t[5] = (float) dz;
+            t[6] = 1.f;
+            t[2] = 1.f;
+            if (sph && sd.target_type == ERTB_TARGET_POINT) {
+                const double *T = sd.target;
+                double b = T[0] * dx + T[1] * dy + T[2] * dz;
+                double c = T[0] * T[0] + T[1] * T[1] + T[2] * T[2] - Rt * Rt;
+                double disc = b * b - c;
+                if (disc < 0.0) { t[6] = 0.f; continue; }
+                double t0 = -b - sqrt(disc);
+                t[0] = (float) ((T[0] + t0 * dx) / Rt);
+                t[1] = (float) ((T[1] + t0 * dy) / Rt);
+                t[2] = (float) ((T[2] + t0 * dz) / Rt);
+            }
+        }
+        CUDA_TRY(cudaMalloc(&hs.d_table, table.size() * sizeof(float)));
+        CUDA_TRY(cudaMemcpy(hs.d_table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+static void fill_sensor_params(const ertb_scene *S, const HostSensor &hs, ErtbSensor &o) {
+    const ertb_sensor_desc &sd = hs.desc;
+    memset(&o, 0, sizeof o);
+    o.type = sd.type;
+    o.width = sd.width;
+    o.height = sd.height;
+    o.target_type = sd.target_type;
+    o.use_table = hs.use_table;
+    o.table = hs.d_table;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o.to_world[3 * r + c] = (float) sd.to_world[4 * r + c];
+    for (int i = 0; i < 3; ++i) o.target[i] = sd.target[i];
+    for (int i = 0; i < 12; ++i) o.target_to_world[i] = sd.target_to_world[i];
+    for (int i = 0; i < 3; ++i) o.bs_center[i] = S->bs_center[i];
+    const double eps = 1.1920929e-7 * 0.5 * 1500.0;
+    o.bs_radius = fmax(eps, S->bs_radius * (1.0 + eps));
+    o.flux_norm = (float) (2.0 * M_PI / (double) (sd.width * sd.height));
+}
+
+// ----------------------------------------------------------------------------
+// C ABI
+// ----------------------------------------------------------------------------
+// (the header declares every entry point extern "C"; definitions inherit the linkage)
+
+int ertb_abi_version(void) { return ERTB_ABI_VERSION; }
+const char *ertb_last_error(void) { return g_error.c_str(); }
+
+int ertb_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error(std::string("no usable CUDA device (there is no CPU fallback): ") +
+                  (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+        return -1;
+    }
+    return n;
+}
+
+void ertb_scene_destroy(ertb_scene *S) {
+    if (!S) return;
+    cudaSetDevice(S->device);
+    for (auto &hs : S->sensors)
+        if (hs.d_table) cudaFree(hs.d_table);
+    if (S->d_blob) cudaFree(S->d_blob);
+    if (S->d_counter) cudaFree(S->d_counter);
+    if (S->d_accum) cudaFree(S->d_accum);
+    if (S->ev0) cudaEventDestroy(S->ev0);
+    if (S->ev1) cudaEventDestroy(S->ev1);
+    delete S;
+}
+
+int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
+    if (!D || !out) return set_error("null argument");
+    *out = nullptr;
+    if (D->abi_version != ERTB_ABI_VERSION) return set_error("ABI version mismatch");
+    int ndev = ertb_device_count();
+    if (ndev < 0) return 1;
+    if (device < 0 || device >= ndev) return set_error("invalid CUDA device index");
+    if (D->geometry != ERTB_GEOM_PLANE_PARALLEL && D->geometry != ERTB_GEOM_SPHERICAL_SHELL)
+        return set_error("unsupported geometry");
+    if (D->bsdf_type < 0 || D->bsdf_type > ERTB_BSDF_BLACK) return set_error("unsupported BSDF type");
+    if (D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) return set_error("ocean_legacy BSDF is not implemented on the device yet");
+    if (D->n_sensors < 1 || !D->sensors) return set_error("scene has no sensor");
+    if (D->rr_depth <= 0) return set_error("\"rr_depth\" must be set to a value greater than zero!");
+    if (D->has_medium) {
+        if (D->n_layers < 1 || D->n_layers > ERTB_MAX_LAYERS) return set_error("invalid number of layers");
+        if (!D->sigma_t || !D->albedo) return set_error("medium arrays missing");
+        if (D->n_phase < 1 || D->n_phase > ERTB_MAX_PHASE) return set_error("invalid number of phase leaves");
+        if (D->n_phase > 1 && !D->phase_weight) return set_error("phase_weight missing");
+        if (!(D->medium_top > D->medium_bottom)) return set_error("invalid medium extent");
+        if (D->medium_top < D->surface_z) return set_error("top of atmosphere below the surface");
+    }
+    ertb_scene *S = new ertb_scene();
+    S->device = device;
+    S->geometry = D->geometry;
+    S->surface_z = D->surface_z;
+    S->medium_bottom = D->medium_bottom;
+    S->medium_top = D->medium_top;
+    memcpy(S->bs_center, D->bsphere_center, sizeof S->bs_center);
+    S->bs_radius = D->bsphere_radius;
+    S->has_medium = D->has_medium;
+    S->n_layers = D->n_layers;
+    S->homogeneous = D->homogeneous;
+    S->scale = D->sigma_t_scale;
+    if (D->has_medium) {
+        S->sigma_t.assign(D->sigma_t, D->sigma_t + D->n_layers);
+        S->albedo.assign(D->albedo, D->albedo + D->n_layers);
+        S->n_phase = D->n_phase;
+        if (D->n_phase > 1)
+            S->phase_weight.assign(D->phase_weight, D->phase_weight + (size_t) D->n_phase * D->n_layers);
+        for (int k = 0; k < D->n_phase; ++k) {
+            const ertb_phase_desc &pd = D->phase[k];
+            HostPhase &hp = S->phase[k];
+            hp.type = pd.type;
+            memcpy(hp.params, pd.params, sizeof hp.params);
+            if (pd.type == ERTB_PHASE_TABULATED || pd.type == ERTB_PHASE_TABULATED_IRREGULAR) {
+                if (!pd.values || pd.n_nodes < 2) { delete S; return set_error("tabulated phase: values missing"); }
+                hp.values.assign(pd.values, pd.values + pd.n_nodes);
+                if (pd.type == ERTB_PHASE_TABULATED_IRREGULAR) {
+                    if (!pd.nodes) { delete S; return set_error("tabulated phase: nodes missing"); }
+                    hp.nodes.assign(pd.nodes, pd.nodes + pd.n_nodes);
+                }
+            } else if (pd.type < 0 || pd.type > ERTB_PHASE_TABULATED_IRREGULAR) {
+                delete S;
+                return set_error("unsupported phase function type");
+            }
+        }
+    }
+    S->bsdf_type = D->bsdf_type;
+    memcpy(S->bsdf_params, D->bsdf_params, sizeof S->bsdf_params);
+    memcpy(S->emitter_dir, D->emitter_direction, sizeof S->emitter_dir);
+    S->irradiance = D->irradiance;
+    S->integrator = D->integrator;
+    S->rr_depth = D->rr_depth;
+    S->max_depth = D->max_depth;
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete S; return set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
+    cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&S->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (cudaMalloc(&S->d_counter, 16 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaEventCreate(&S->ev0) != cudaSuccess || cudaEventCreate(&S->ev1) != cudaSuccess) {
+        ertb_scene_destroy(S);
+        return set_error("device allocation failed");
+    }
+    for (int i = 0; i < D->n_sensors; ++i) {
+        HostSensor hs;
+        hs.desc = D->sensors[i];
+        const ertb_sensor_desc &sd = hs.desc;
+        if (sd.width < 1 || sd.height < 1) { ertb_scene_destroy(S); return set_error("invalid film size"); }
+        if (sd.type == ERTB_SENSOR_MDISTANT) {
+            if (!sd.directions || sd.n_directions < 1) { ertb_scene_destroy(S); return set_error("mdistant: directions missing"); }
+            hs.directions.resize(3 * (size_t) sd.n_directions);
+            for (int k = 0; k < sd.n_directions; ++k) {
+                const double *v = sd.directions + 3 * k;
+                double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+                if (!(n > 0.0)) { ertb_scene_destroy(S); return set_error("mdistant: zero-length direction"); }
+                for (int c = 0; c < 3; ++c) hs.directions[3 * k + c] = v[c] / n;
+            }
+        } else if (sd.type != ERTB_SENSOR_HDISTANT && sd.type != ERTB_SENSOR_DISTANTFLUX) {
+            ertb_scene_destroy(S);
+            return set_error("unsupported sensor type");
+        }
+        hs.desc.directions = nullptr;
+        S->sensors.push_back(hs);
+        if (build_sensor(S, S->sensors.back())) { ertb_scene_destroy(S); return 1; }
+    }
+    if (scene_commit(S)) { ertb_scene_destroy(S); return 1; }
+    *out = S;
+    return 0;
+}
+
+int ertb_scene_update(ertb_scene *S, int param, int index, const float *data, size_t count) {
+    if (!S || !data) return set_error("null argument");
+    auto need = [&](size_t n) -> int {
+        return count == n ? 0 : set_error("ertb_scene_update: size mismatch for parameter " + std::to_string(param));
+    };
+    switch (param) {
+        case ERTB_PARAM_SIGMA_T:
+            if (!S->has_medium) return set_error("scene has no medium");
+            if (need(S->n_layers)) return 1;
+            S->sigma_t.assign(data, data + count);
+            break;
+        case ERTB_PARAM_ALBEDO:
+            if (!S->has_medium) return set_error("scene has no medium");
+            if (need(S->n_layers)) return 1;
+            S->albedo.assign(data, data + count);
+            break;
+        case ERTB_PARAM_PHASE_WEIGHT:
+            if (S->n_phase <= 1) break; // single leaf: weight is implicit
+            if (need((size_t) S->n_phase * S->n_layers)) return 1;
+            S->phase_weight.assign(data, data + count);
+            break;
+        case ERTB_PARAM_PHASE_VALUES:
+            if (index < 0 || index >= S->n_phase) return set_error("invalid phase leaf index");
+            if (need(S->phase[index].values.size())) return 1;
+            S->phase[index].values.assign(data, data + count);
+            break;
+        case ERTB_PARAM_PHASE_PARAMS:
+            if (index < 0 || index >= S->n_phase) return set_error("invalid phase leaf index");
+            if (need(4)) return 1;
+            memcpy(S->phase[index].params, data, 4 * sizeof(float));
+            break;
+        case ERTB_PARAM_BSDF_PARAMS:
+            if (need(ERTB_MAX_BSDF_PARAMS)) return 1;
+            memcpy(S->bsdf_params, data, sizeof S->bsdf_params);
+            break;
+        case ERTB_PARAM_IRRADIANCE:
+            if (need(1)) return 1;
+            S->irradiance = data[0];
+            break;
+        default:
+            return set_error("unknown parameter id");
+    }
+    S->dirty = true;
+    return 0;
+}
+
+int ertb_sensor_pixel_count(const ertb_scene *S, int sensor) {
+    if (!S || sensor < 0 || sensor >= (int) S->sensors.size()) return -1;
+    return S->sensors[sensor].desc.width * S->sensors[sensor].desc.height;
+}
+
+static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, uint64_t sample_offset,
+                         double *accum_dev, unsigned long long *stats_dev, cudaStream_t stream,
+                         bool with_stats) {
+    if (!S) return set_error("null scene");
+    if (sensor < 0 || sensor >= (int) S->sensors.size()) return set_error("invalid sensor index");
+    if (spp == 0) return set_error("spp must be > 0");
+    if (sample_offset + spp >= (1ULL << 40)) return set_error("sample index exceeds 2^40");
+    CUDA_TRY(cudaSetDevice(S->device));
+    if (S->dirty && scene_commit(S)) return 1;
+    ErtbParams P = S->base;
+    const HostSensor &hs = S->sensors[sensor];
+    fill_sensor_params(S, hs, P.sensor);
+    P.seed = seed;
+    P.spp = spp;
+    P.sample_offset = sample_offset;
+    P.n_pixels = (unsigned) (hs.desc.width * hs.desc.height);
+    // persistent grid: as many CTAs as can be resident (queried, not assumed)
+    const bool sph = P.spherical;
+    int blocks_per_sm = 0;
+    const size_t smem = (size_t) S->base.blob_bytes;
+#define ERTB_OCC(SPH, ST)                                                                             \
+    do {                                                                                              \
+        CUDA_TRY(cudaFuncSetAttribute(ertb_render_kernel<SPH, ST>,                                    \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));      \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                       \
+            &blocks_per_sm, ertb_render_kernel<SPH, ST>, ERTB_BLOCK, smem));                          \
+    } while (0)
+    if (sph) { if (with_stats) ERTB_OCC(true, true); else ERTB_OCC(true, false); }
+    else     { if (with_stats) ERTB_OCC(false, true); else ERTB_OCC(false, false); }
+#undef ERTB_OCC
+    if (blocks_per_sm < 1) return set_error("render kernel cannot be resident on this device");
+    // chunk: a few thousand paths, so that the queue hands out >> n_warps chunks
+    const unsigned long long total = (unsigned long long) P.n_pixels * spp;
+    const unsigned long long n_warps = (unsigned long long) S->sm_count * blocks_per_sm * (ERTB_BLOCK / 32);
+    unsigned long long chunk = total / (n_warps * 16ULL);
+    if (chunk > 4096) chunk = 4096;
+    if (chunk < 32) chunk = 32;
+    if (chunk > spp) chunk = spp;
+    P.chunk = (unsigned) chunk;
+    P.chunks_per_pixel = (unsigned) ((spp + chunk - 1) / chunk);
+    P.n_chunks = (unsigned long long) P.chunks_per_pixel * P.n_pixels;
+    P.work_counter = S->d_counter;
+    P.accum = accum_dev;
+    P.stats = stats_dev;
+    CUDA_TRY(cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned long long), stream));
+
+    unsigned long long want_blocks = (P.n_chunks * 32ULL + ERTB_BLOCK - 1) / ERTB_BLOCK; // >= 1 lane per path slot
+    unsigned long long grid = (unsigned long long) S->sm_count * blocks_per_sm;
+    if (want_blocks < grid) grid = want_blocks ? want_blocks : 1;
+#define ERTB_LAUNCH(SPH, ST)                                                                          \
+    do {                                                                                              \
+        ertb_render_kernel<SPH, ST><<<(unsigned) grid, ERTB_BLOCK, smem, stream>>>(P);                \
+    } while (0)
+    if (sph) { if (with_stats) ERTB_LAUNCH(true, true); else ERTB_LAUNCH(true, false); }
+    else     { if (with_stats) ERTB_LAUNCH(false, true); else ERTB_LAUNCH(false, false); }
+#undef ERTB_LAUNCH
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ertb_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, uint64_t sample_offset,
+                double *sum_wl, double *sum_l, double *sum_l2, ertb_render_stats *stats) {
+    if (!S) return set_error("null scene");
+    int npix = ertb_sensor_pixel_count(S, sensor);
+    if (npix <= 0) return set_error("invalid sensor index");
+    CUDA_TRY(cudaSetDevice(S->device));
+    size_t bytes = (size_t) 3 * npix * sizeof(double);
+    if (bytes > S->d_accum_capacity) {
+        if (S->d_accum) cudaFree(S->d_accum);
+        CUDA_TRY(cudaMalloc(&S->d_accum, bytes));
+        S->d_accum_capacity = bytes;
+    }
+    CUDA_TRY(cudaMemsetAsync(S->d_accum, 0, bytes, 0));
+    unsigned long long *d_stats = S->d_counter + 8;
+    CUDA_TRY(cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), 0));
+    CUDA_TRY(cudaEventRecord(S->ev0, 0));
+    if (launch_render(S, sensor, seed, spp, sample_offset, S->d_accum, d_stats, 0, stats != nullptr)) return 1;
+    CUDA_TRY(cudaEventRecord(S->ev1, 0));
+    std::vector<double> host((size_t) 3 * npix);
+    CUDA_TRY(cudaMemcpy(host.data(), S->d_accum, bytes, cudaMemcpyDeviceToHost));
+    if (sum_wl) memcpy(sum_wl, host.data(), npix * sizeof(double));
+    if (sum_l) memcpy(sum_l, host.data() + npix, npix * sizeof(double));
+    if (sum_l2) memcpy(sum_l2, host.data() + 2 * (size_t) npix, npix * sizeof(double));
+    if (stats) {
+        unsigned long long h[8];
+        CUDA_TRY(cudaMemcpy(h, d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, S->ev0, S->ev1));
+        memset(stats, 0, sizeof *stats);
+        stats->n_paths = h[0];
+        stats->trips_main = h[1];
+        stats->trips_nee = h[2];
+        stats->n_scatter = h[3];
+        stats->n_surface = h[4];
+        stats->device_ms = ms;
+        stats->n_launches = 1;
+    }
+    return 0;
+}
+
+int ertb_render_device(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, uint64_t sample_offset,
+                       void *accum_dev, void *stats_dev, void *stream) {
+    if (!accum_dev) return set_error("null accumulator buffer");
+    return launch_render(S, sensor, seed, spp, sample_offset, (double *) accum_dev,
+                         (unsigned long long *) stats_dev, (cudaStream_t) stream, stats_dev != nullptr);
+}
+
+// ----------------------------------------------------------------------------
+// KAT kernels: the same device functions the render kernel uses, one thread per query
+// ----------------------------------------------------------------------------
+__global__ void kat_bsdf_eval_kernel(ErtbParams P, size_t n, const float *wi, const float *wo, float *out) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 a = mk3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), b = mk3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+    float ci = a.z, co = b.z;
+    float v = 0.f;
+    if (ci > 0.f && co > 0.f) v = bsdf_f(P, ci, co, cos_dphi(ci, co, dot3(a, b))) * co;
+    out[i] = v;
+}
+__global__ void kat_bsdf_sample_kernel(ErtbParams P, size_t n, const float *wi, const float *u, float *wo, float *w) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 a = mk3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+    f3 o = cosine_hemisphere(u[2 * i], u[2 * i + 1]);
+    float weight = 0.f;
+    if (a.z > 0.f && o.z > 0.f) weight = bsdf_f(P, a.z, o.z, cos_dphi(a.z, o.z, dot3(a, o))) * ERTB_PI;
+    wo[3 * i] = o.x; wo[3 * i + 1] = o.y; wo[3 * i + 2] = o.z;
+    w[i] = weight;
+}
+__global__ void kat_phase_eval_kernel(ErtbParams P, int leaf, size_t n, const float *c, float *out) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = leaf_eval(P.blob, P.leaf[leaf], -c[i]); // graphics -> physics cosine
+}
+__global__ void kat_phase_sample_kernel(ErtbParams P, int leaf, size_t n, const float *u, float *ct, float *w, float *pdf) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float ww, pp;
+    ct[i] = leaf_sample(P.blob, P.leaf[leaf], u[2 * i], ww, pp);
+    w[i] = ww;
+    pdf[i] = pp;
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { return cudaMalloc(&p, n * sizeof(T)) == cudaSuccess ? 0 : 1; }
+};
+
+static int kat_prepare(ertb_scene *S) {
+    if (!S) return set_error("null scene");
+    CUDA_TRY(cudaSetDevice(S->device));
+    if (S->dirty && scene_commit(S)) return 1;
+    return 0;
+}
+#define KAT_GRID(n) (unsigned) (((n) + 127) / 128), 128
+
+int ertb_kat_bsdf_eval(ertb_scene *S, size_t n, const float *wi, const float *wo, float *out) {
+    if (kat_prepare(S)) return 1;
+    DevBuf<float> a, b, o;
+    if (a.alloc(3 * n) || b.alloc(3 * n) || o.alloc(n)) return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(a.p, wi, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.p, wo, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+    kat_bsdf_eval_kernel<<<KAT_GRID(n)>>>(S->base, n, a.p, b.p, o.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, o.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int ertb_kat_bsdf_sample(ertb_scene *S, size_t n, const float *wi, const float *u, float *wo, float *weight) {
+    if (kat_prepare(S)) return 1;
+    DevBuf<float> a, b, o, w;
+    if (a.alloc(3 * n) || b.alloc(2 * n) || o.alloc(3 * n) || w.alloc(n)) return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(a.p, wi, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.p, u, 2 * n * sizeof(float), cudaMemcpyHostToDevice));
+    kat_bsdf_sample_kernel<<<KAT_GRID(n)>>>(S->base, n, a.p, b.p, o.p, w.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(wo, o.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(weight, w.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int ertb_kat_phase_eval(ertb_scene *S, int leaf, size_t n, const float *c, float *out) {
+    if (kat_prepare(S)) return 1;
+    if (leaf < 0 || leaf >= S->n_phase) return set_error("invalid phase leaf index");
+    DevBuf<float> a, o;
+    if (a.alloc(n) || o.alloc(n)) return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(a.p, c, n * sizeof(float), cudaMemcpyHostToDevice));
+    kat_phase_eval_kernel<<<KAT_GRID(n)>>>(S->base, leaf, n, a.p, o.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, o.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int ertb_kat_phase_sample(ertb_scene *S, int leaf, size_t n, const float *u, float *ct, float *weight, float *pdf) {
+    if (kat_prepare(S)) return 1;
+    if (leaf < 0 || leaf >= S->n_phase) return set_error("invalid phase leaf index");
+    DevBuf<float> a, c, w, p;
+    if (a.alloc(2 * n) || c.alloc(n) || w.alloc(n) || p.alloc(n)) return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(a.p, u, 2 * n * sizeof(float), cudaMemcpyHostToDevice));
+    kat_phase_sample_kernel<<<KAT_GRID(n)>>>(S->base, leaf, n, a.p, c.p, w.p, p.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(ct, c.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(weight, w.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(pdf, p.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Sensor rays as the reference defines them (origin = target - d * ray_offset).
+__global__ void kat_sensor_ray_kernel(ErtbParams P, double ray_offset, size_t n, const float *fs_,
+                                      const float *as_, double *origin, double *dir, float *weight) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ErtbSensor &S = P.sensor;
+    float fx = fs_[2 * i], fy = fs_[2 * i + 1], ax = as_[2 * i], ay = as_[2 * i + 1];
+    f3 d, fs = mk3(1.f, 0.f, 0.f), ft = mk3(0.f, 1.f, 0.f);
+    float w = 1.f;
+    if (S.type == ERTB_SENSOR_MDISTANT) {
+        int idx = min((int) (fx * (float) S.width), S.width - 1);
+        const float *t = S.table + 8 * (size_t) idx;
+        d = mk3(t[3], t[4], t[5]);
+        onb(d, fs, ft);
+    } else {
+        f3 hv = uniform_hemisphere(fx, fy);
+        const float *M = S.to_world;
+        d = mk3(-(M[0] * hv.x + M[1] * hv.y + M[2] * hv.z), -(M[3] * hv.x + M[4] * hv.y + M[5] * hv.z),
+                -(M[6] * hv.x + M[7] * hv.y + M[8] * hv.z));
+        fs = mk3(M[0], M[3], M[6]);
+        ft = mk3(M[1], M[4], M[7]);
+        if (S.type == ERTB_SENSOR_DISTANTFLUX) w = hv.z * S.flux_norm;
+    }
+    double tx, ty, tz;
+    if (S.target_type == ERTB_TARGET_POINT) {
+        tx = S.target[0]; ty = S.target[1]; tz = S.target[2];
+    } else if (S.target_type == ERTB_TARGET_NONE) {
+        float ox, oy;
+        disk_concentric(ax, ay, ox, oy);
+        tx = S.bs_center[0] + ((double) fs.x * ox + (double) ft.x * oy) * S.bs_radius;
+        ty = S.bs_center[1] + ((double) fs.y * ox + (double) ft.y * oy) * S.bs_radius;
+        tz = S.bs_center[2] + ((double) fs.z * ox + (double) ft.z * oy) * S.bs_radius;
+    } else {
+        float lx, ly;
+        if (S.target_type == ERTB_TARGET_RECTANGLE) { lx = fmaf(2.f, ax, -1.f); ly = fmaf(2.f, ay, -1.f); }
+        else disk_concentric(ax, ay, lx, ly);
+        const double *T = S.target_to_world;
+        tx = T[0] * lx + T[1] * ly + T[3];
+        ty = T[4] * lx + T[5] * ly + T[7];
+        tz = T[8] * lx + T[9] * ly + T[11];
+    }
+    origin[3 * i] = tx - (double) d.x * ray_offset;
+    origin[3 * i + 1] = ty - (double) d.y * ray_offset;
+    origin[3 * i + 2] = tz - (double) d.z * ray_offset;
+    dir[3 * i] = d.x; dir[3 * i + 1] = d.y; dir[3 * i + 2] = d.z;
+    weight[i] = w;
+}
+
+int ertb_kat_sensor_ray(ertb_scene *S, int sensor, size_t n, const float *film_sample,
+                        const float *aperture_sample, double *origin, double *dir, float *weight) {
+    if (kat_prepare(S)) return 1;
+    if (sensor < 0 || sensor >= (int) S->sensors.size()) return set_error("invalid sensor index");
+    ErtbParams P = S->base;
+    fill_sensor_params(S, S->sensors[sensor], P.sensor);
+    DevBuf<float> a, b, w;
+    DevBuf<double> o, d;
+    if (a.alloc(2 * n) || b.alloc(2 * n) || w.alloc(n) || o.alloc(3 * n) || d.alloc(3 * n))
+        return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(a.p, film_sample, 2 * n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.p, aperture_sample, 2 * n * sizeof(float), cudaMemcpyHostToDevice));
+    kat_sensor_ray_kernel<<<KAT_GRID(n)>>>(P, S->sensors[sensor].ray_offset, n, a.p, b.p, o.p, d.p, w.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(origin, o.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(dir, d.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(weight, w.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+

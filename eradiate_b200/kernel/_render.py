@@ -1,0 +1,444 @@
+"""
+Drop-in replacements for ``eradiate.kernel.mi_load_dict / mi_traverse / mi_render``
+(``src/eradiate/kernel/_render.py:186, :212, :379``) backed by the sm_100a CUDA
+path tracer instead of Mitsuba.
+
+Same names, argument meaning, return structure and error behaviour
+(``RuntimeError`` on load failures, ``warnings.warn`` on unsuccessful parameter
+lookups).  The CUDA library is mandatory: there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import re
+import typing as t
+import warnings
+
+import numpy as np
+
+from .. import _abi, _lib
+from . import _scene
+from ._bitmap import Bitmap
+from ._kernel_dict import KernelSceneParameterMap, SceneParameter
+
+logger = logging.getLogger(__name__)
+
+# ------------------------------------------------------------------------------
+#                                seed state
+# ------------------------------------------------------------------------------
+
+
+class SeedState:
+    """``src/eradiate/rng.py``: numpy ``SeedSequence``-based seed generator."""
+
+    def __init__(self, seed=None):
+        self._seed = (
+            seed if isinstance(seed, np.random.SeedSequence) else np.random.SeedSequence(seed)
+        )
+
+    def reset(self, seed=None):
+        if seed is not None:
+            self._seed = (
+                seed if isinstance(seed, np.random.SeedSequence) else np.random.SeedSequence(seed)
+            )
+        else:
+            self._seed = np.random.SeedSequence(entropy=self._seed.entropy)
+
+    def next(self, n: int = 1) -> np.ndarray:
+        return self._seed.spawn(1)[0].generate_state(n)
+
+
+_root_seed_state = SeedState(0)  # src/eradiate/config/_defaults.py:50 rng_seed = 0
+
+
+def get_seed_state() -> SeedState:
+    return _root_seed_state
+
+
+# ------------------------------------------------------------------------------
+#                        device-side scene (C ABI handle)
+# ------------------------------------------------------------------------------
+
+
+class DeviceScene:
+    """Owns one ``ertb_scene`` handle and keeps it in sync with the host scene graph."""
+
+    def __init__(self, scene: _scene.Scene, device: int = 0):
+        self.scene = scene
+        self.device = device
+        self.lib = _lib.load()
+        self.flat = scene.flat
+        self.desc = self.flat.build_desc()
+        handle = C.c_void_p()
+        _lib.check(self.lib.ertb_scene_create(C.byref(self.desc), device, C.byref(handle)))
+        self.handle = handle
+        self._mark_clean()
+
+    def _nodes(self):
+        stack, seen = [self.scene], set()
+        while stack:
+            n = stack.pop()
+            if id(n) in seen:
+                continue
+            seen.add(id(n))
+            yield n
+            stack.extend(n.children.values())
+
+    def _mark_clean(self):
+        for n in self._nodes():
+            n.dirty = False
+
+    def sync(self) -> None:
+        """Push updated parameters (``parameters_changed`` equivalent)."""
+        if not any(n.dirty for n in self._nodes()):
+            return
+        flat, lib, h = self.flat, self.lib, self.handle
+
+        def push(param, index, arr):
+            arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)
+            _lib.check(
+                lib.ertb_scene_update(h, param, index, arr.ctypes.data_as(_abi.c_float_p), arr.size)
+            )
+
+        if flat.medium is not None:
+            n = flat.n_layers()
+            if n != self.desc.n_layers:
+                raise RuntimeError("the number of atmospheric layers cannot change after loading")
+            m = flat.medium
+            push(_abi.PARAM_SIGMA_T, 0, flat._profile(m.children["sigma_t"], n, "sigma_t"))
+            push(_abi.PARAM_ALBEDO, 0, flat._profile(m.children["albedo"], n, "albedo"))
+            leaves = flat.phase_leaves(n)
+            if len(leaves) != self.desc.n_phase:
+                raise RuntimeError("the phase function tree cannot change after loading")
+            push(_abi.PARAM_PHASE_WEIGHT, 0, np.stack([p for _, p in leaves]))
+            for i, (ph, _) in enumerate(leaves):
+                _, params, values, _ = _scene._phase_leaf_desc(ph)
+                push(_abi.PARAM_PHASE_PARAMS, i, np.asarray(params))
+                if values is not None:
+                    push(_abi.PARAM_PHASE_VALUES, i, values)
+        push(_abi.PARAM_BSDF_PARAMS, 0, flat.bsdf_params())
+        push(_abi.PARAM_IRRADIANCE, 0, [flat.emitter.children["irradiance"].values["value"]])
+        self._mark_clean()
+
+    def render(self, sensor: int, seed: int, spp: int, sample_offset: int = 0):
+        """One ``ertb_render`` call. Returns (sum_wl, sum_l, sum_l2, stats)."""
+        self.sync()
+        npix = self.lib.ertb_sensor_pixel_count(self.handle, sensor)
+        if npix <= 0:
+            raise RuntimeError(f"invalid sensor index {sensor}")
+        out = [np.zeros(npix, dtype=np.float64) for _ in range(3)]
+        stats = _abi.RenderStats()
+        _lib.check(
+            self.lib.ertb_render(
+                self.handle, sensor, seed, spp, sample_offset,
+                *[o.ctypes.data_as(_abi.c_double_p) for o in out], C.byref(stats),
+            )
+        )
+        return out[0], out[1], out[2], stats
+
+    def render_device(self, sensor, seed, spp, sample_offset, accum_ptr, stats_ptr=None, stream=None):
+        """Asynchronous render into a caller-owned device buffer (see the header)."""
+        self.sync()
+        _lib.check(
+            self.lib.ertb_render_device(
+                self.handle, sensor, seed, spp, sample_offset,
+                C.c_void_p(accum_ptr), C.c_void_p(stats_ptr or 0), C.c_void_p(stream or 0),
+            )
+        )
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ertb_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _device_scene(scene: _scene.Scene, device: int | None = None) -> DeviceScene:
+    dev = getattr(scene, "_device_scene", None)
+    want = 0 if device is None else device
+    if dev is None or (device is not None and dev.device != want):
+        if dev is not None:
+            dev.close()
+        dev = DeviceScene(scene, want)
+        scene._device_scene = dev
+    return dev
+
+
+# ------------------------------------------------------------------------------
+#                               scene parameters
+# ------------------------------------------------------------------------------
+
+
+class SceneParameters:
+    """``mitsuba.SceneParameters`` stand-in: dotted key -> (node, value name)."""
+
+    def __init__(self, properties: dict, scene=None, aliases: dict | None = None):
+        self.properties = properties
+        self.scene = scene
+        self.aliases = aliases or {}
+        self.update_candidates: dict = {}
+
+    def __contains__(self, key):
+        return self.aliases.get(key, key) in self.properties
+
+    def __getitem__(self, key):
+        node, name = self.properties[self.aliases.get(key, key)]
+        return node.values[name]
+
+    def __setitem__(self, key, value):
+        key = self.aliases.get(key, key)
+        if key not in self.properties:
+            raise KeyError(key)
+        self.update_candidates[key] = value
+
+    def __len__(self):
+        return len(self.properties)
+
+    def keys(self):
+        return self.properties.keys()
+
+    def items(self):
+        return ((k, self[k]) for k in self.properties)
+
+    def keep(self, keys) -> None:
+        if isinstance(keys, str):
+            regexps = [re.compile(keys).fullmatch]
+            keys = [k for k in self.properties if any(r(k) for r in regexps)]
+        keys = [self.aliases.get(k, k) for k in keys]
+        self.properties = {k: v for k, v in self.properties.items() if k in set(keys)}
+
+    def update(self, values: dict | None = None) -> list:
+        if values is not None:
+            for k, v in values.items():
+                if v is SceneParameter.UNUSED:
+                    continue
+                if k not in self:
+                    raise KeyError(f"scene parameter '{k}' not found")
+                self[k] = v
+        touched = []
+        for key, value in self.update_candidates.items():
+            node, name = self.properties[key]
+            node.set_value(name, value)
+            touched.append((node, {name}))
+        self.update_candidates = {}
+        return touched
+
+    def __repr__(self):
+        lines = "\n".join(f"  {k}" for k in self.properties)
+        return f"SceneParameters[\n{lines}\n]"
+
+
+class MitsubaObjectWrapper:
+    """``_render.py:74-140``: scene + parameter table + update-map template."""
+
+    def __init__(self, obj, parameters=None, umap_template=None):
+        self.obj = obj
+        self.parameters = parameters
+        self.umap_template = umap_template
+
+    def drop_parameters(self) -> None:
+        if self.umap_template is not None:
+            keys = []
+            for k, v in self.umap_template.items():
+                if getattr(v, "parameter_id", None) is not None:
+                    keys.append(v.parameter_id)
+                else:
+                    keys.append(k)
+            self.parameters.keep(keys)
+
+    def __repr__(self):
+        return "MitsubaObjectWrapper[obj=Scene[...], parameters=SceneParameters[...]]"
+
+
+# ------------------------------------------------------------------------------
+#                       mi_load_dict / mi_traverse / mi_render
+# ------------------------------------------------------------------------------
+
+
+def mi_load_dict(dict: dict, parallel: bool = True, optimize: bool = False) -> object:
+    """
+    Load a scene (or a single plugin) from a Mitsuba-style dictionary
+    (``_render.py:186-209``).  Unsupported plugins and malformed scenes raise
+    ``RuntimeError``.
+    """
+    return _scene.load_dict(dict)
+
+
+def mi_traverse(obj, umap_template=None, name_id_override=None) -> MitsubaObjectWrapper:
+    """
+    Traverse the scene graph and return the parameter table
+    (``_render.py:212-371``).  Parameter lookups registered in ``umap_template``
+    through ``search`` callables are resolved during traversal; unsuccessful
+    lookups emit a warning.
+    """
+    umap_template = (
+        KernelSceneParameterMap(data=dict(getattr(umap_template, "data", umap_template)))
+        if umap_template is not None
+        else KernelSceneParameterMap()
+    )
+    lookups = {
+        k: v
+        for k, v in umap_template.items()
+        if getattr(v, "parameter_id", None) is None and getattr(v, "search", None) is not None
+    }
+    if name_id_override is None or name_id_override is False:
+        name_id_override = []
+    if name_id_override is True:
+        name_id_override = [r".*"]
+    if not isinstance(name_id_override, list):
+        name_id_override = [name_id_override]
+    regexps = [re.compile(k).match for k in name_id_override]
+
+    properties: dict = {}
+    hierarchy: dict = {}
+    prefixes: set = set()
+    aliases: dict = {}
+
+    class SceneTraversal:
+        def __init__(self, node, parent=None, name=None, depth=0):
+            node_id = node.id()
+            if name_id_override and node_id:
+                for r in regexps:
+                    if r(node_id):
+                        if node_id != name:
+                            aliases[node_id] = name
+                        name = node_id
+                        break
+            if name is not None:
+                ctr, name_len = 1, len(name)
+                while name in prefixes:
+                    name = f"{name[:name_len]}_{ctr}"
+                    ctr += 1
+                prefixes.add(name)
+            self.name, self.node, self.depth = name, node, depth
+            hierarchy[id(node)] = (parent, depth)
+            for key, uparam in list(lookups.items()):
+                found = uparam.search(self.node, self.name)
+                if found is not None:
+                    uparam.parameter_id = found
+                    del lookups[key]
+
+        def put(self, name, value, flags=0, cpptype=None):
+            if isinstance(value, _scene.Object):
+                self.put_object(name, value, flags)
+            else:
+                self.put_value(name, value, flags, cpptype)
+
+        def put_value(self, name, value, flags=0, cpptype=None):
+            full = name if self.name is None else f"{self.name}.{name}"
+            properties[full] = (self.node, name)
+
+        def put_object(self, name, child, flags=0):
+            if child is None or id(child) in hierarchy:
+                return
+            cb = SceneTraversal(
+                child,
+                parent=self.node,
+                name=name if self.name is None else f"{self.name}.{name}",
+                depth=self.depth + 1,
+            )
+            child.traverse(cb)
+
+    cb = SceneTraversal(obj)
+    obj.traverse(cb)
+
+    if lookups:
+        warnings.warn(
+            "There were unsuccessful Mitsuba scene parameter lookups: " f"{list(lookups.keys())}"
+        )
+    return MitsubaObjectWrapper(
+        obj=obj,
+        parameters=SceneParameters(properties, obj, aliases),
+        umap_template=umap_template,
+    )
+
+
+def render(scene, sensor: int = 0, seed: int = 0, spp: int = 0, device: int | None = None):
+    """
+    ``mitsuba.render(scene, sensor=i, seed=seed, spp=spp)`` for scalar variants
+    (``MI/src/python/python/util.py:511-519``): renders, develops the film and
+    returns the bitmap (also available from ``sensor.film().bitmap()``).
+    """
+    if not isinstance(scene, _scene.Scene):
+        raise RuntimeError("render(): expected a scene loaded with mi_load_dict")
+    sensors = scene.sensors()
+    if isinstance(sensor, int):
+        if not 0 <= sensor < len(sensors):
+            raise RuntimeError(f"render(): sensor index {sensor} out of range")
+        i_sensor = sensor
+    else:
+        i_sensor = sensors.index(sensor)
+    s = sensors[i_sensor]
+    if spp <= 0:
+        spp = s.sampler().sample_count
+    dev = _device_scene(scene, device)
+    sum_wl, sum_l, sum_l2, stats = dev.render(i_sensor, int(seed) & 0xFFFFFFFFFFFFFFFF, int(spp))
+    bmp = develop(scene, i_sensor, sum_wl, sum_l, sum_l2, spp)
+    bmp.stats = stats.as_dict()
+    s.film()._bitmap = bmp
+    return bmp
+
+
+def develop(scene, i_sensor: int, sum_wl, sum_l, sum_l2, spp: int) -> Bitmap:
+    """``HDRFilm::develop`` (``hdrfilm.cpp:304-405``): sums / weight, channel naming."""
+    s = scene.sensors()[i_sensor]
+    film = s.film()
+    h, w = film.height, film.width
+    inv = 1.0 / float(spp)
+    chans = [np.asarray(sum_wl).reshape(h, w) * inv]
+    names = ["Y"]
+    if scene.integrator().moment:
+        m1 = np.asarray(sum_l).reshape(h, w) * inv
+        m2 = np.asarray(sum_l2).reshape(h, w) * inv
+        chans += [m1, m1, m1, m2, m2, m2]
+        names += ["nested.X", "nested.Y", "nested.Z", "m2_nested.X", "m2_nested.Y", "m2_nested.Z"]
+    data = np.stack(chans, axis=-1).astype(np.float32)
+    raw = {
+        "sum_wl": np.asarray(sum_wl, dtype=np.float64).reshape(h, w).copy(),
+        "sum_l": np.asarray(sum_l, dtype=np.float64).reshape(h, w).copy(),
+        "sum_l2": np.asarray(sum_l2, dtype=np.float64).reshape(h, w).copy(),
+        "spp": int(spp),
+    }
+    return Bitmap(data, None, names, raw=raw)
+
+
+def mi_render(
+    mi_scene: MitsubaObjectWrapper,
+    ctxs: list,
+    spp: int = 0,
+    seed_state: SeedState | None = None,
+) -> dict[t.Any, dict[str, Bitmap]]:
+    """
+    Render the scene for every context and active sensor (``_render.py:379-470``).
+    Returns ``{ctx.si.as_hashable: {sensor_id: Bitmap}}``.
+    """
+    if seed_state is None:
+        logger.debug("Using default RNG seed generator")
+        seed_state = get_seed_state()
+
+    results: dict = {}
+    for ctx in ctxs:
+        logger.debug("Updating scene parameters")
+        mi_scene.parameters.update(mi_scene.umap_template.render(ctx))
+
+        active_sensors = getattr(ctx, "active_sensors", None)
+        sensors = mi_scene.obj.sensors()
+        if active_sensors is None:
+            mi_sensors = list(enumerate(sensors))
+        else:
+            mi_sensors = [(i, sensors[i]) for i in active_sensors]
+
+        for i_sensor, mi_sensor in mi_sensors:
+            seed = int(np.asarray(seed_state.next()).squeeze())
+            logger.debug('Running kernel for sensor "%s" with seed value %s', mi_sensor.id(), seed)
+            render(mi_scene.obj, sensor=i_sensor, seed=seed, spp=spp)
+            siah = ctx.si.as_hashable
+            results.setdefault(siah, {})[mi_sensor.id()] = Bitmap(mi_sensor.film().bitmap())
+    return results

@@ -1,0 +1,901 @@
+"""
+Host-side scene graph and flattener.
+
+``load_dict`` walks the very same nested plugin dictionary Eradiate passes to
+``mitsuba.load_dict`` (``src/eradiate/kernel/_render.py:186-209``; the dict layout
+is restated in SURVEY.md section 3.5) and builds a small node tree that
+
+* exposes the parameter paths ``mi_traverse`` publishes (same dotted keys as
+  Mitsuba's ``traverse`` callbacks: ``<shape>.interior_medium.sigma_t.volume.data``,
+  ``<emitter>.irradiance.value``, ``<bsdf>.rho_0.value``, ``...phase_0.values`` ...),
+* flattens to the POD ``ertb_scene_desc`` consumed by the CUDA library
+  (``include/eradiate_b200.h``).
+
+Unsupported plugins raise ``RuntimeError`` -- the convention of
+``src/eradiate/experiments/_core.py:670-671``.  There is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import typing as t
+
+import numpy as np
+
+from .. import _abi
+from ._types import to_grid, to_matrix
+
+# ------------------------------------------------------------------------------
+#                               dict utilities
+# ------------------------------------------------------------------------------
+
+
+def unflatten(d: dict) -> dict:
+    """Expand dotted keys (``"film.width": 32``) into nested dicts, recursively."""
+    out: dict = {}
+    for k, v in d.items():
+        if isinstance(v, dict):
+            v = unflatten(v)
+        if isinstance(k, str) and "." in k and not _looks_like_id(k, v):
+            head, rest = k.split(".", 1)
+            node = out.setdefault(head, {})
+            if not isinstance(node, dict):
+                raise RuntimeError(f"conflicting dictionary entries for '{head}'")
+            _merge(node, unflatten({rest: v}))
+        else:
+            if k in out and isinstance(out[k], dict) and isinstance(v, dict):
+                _merge(out[k], v)
+            else:
+                out[k] = v
+    return out
+
+
+def _looks_like_id(key: str, value) -> bool:
+    # Top-level object ids never contain dots in Eradiate-emitted dicts.
+    return False
+
+
+def _merge(dst: dict, src: dict) -> None:
+    for k, v in src.items():
+        if k in dst and isinstance(dst[k], dict) and isinstance(v, dict):
+            _merge(dst[k], v)
+        else:
+            dst[k] = v
+
+
+def _parse_floats(value, what: str) -> np.ndarray:
+    """Comma/space separated float string (tabphase.cpp:45-62, mdistant.cpp:104-111)."""
+    if isinstance(value, str):
+        toks = value.replace(",", " ").split()
+        try:
+            return np.array([float(s) for s in toks], dtype=np.float64)
+        except ValueError as e:
+            raise RuntimeError(f"could not parse floating point value in '{what}': {e}") from e
+    return np.asarray(value, dtype=np.float64).ravel()
+
+
+def _scalar_spectrum(value, what: str) -> float:
+    """A mono-mode spectrum/texture: float or ``{"type": "uniform", "value": x}``."""
+    if isinstance(value, dict):
+        ty = value.get("type")
+        if ty != "uniform":
+            raise RuntimeError(f"unsupported spectrum type '{ty}' for '{what}' (only 'uniform')")
+        return float(value["value"])
+    return float(value)
+
+
+# ------------------------------------------------------------------------------
+#                                 node classes
+# ------------------------------------------------------------------------------
+
+
+class Object:
+    """Base scene-graph node (``mitsuba.Object`` stand-in)."""
+
+    plugin_kind = "object"
+
+    def __init__(self, type_: str, id_: str | None = None):
+        self.type = type_
+        self._id = id_ or ""
+        self.children: dict[str, Object] = {}
+        self.values: dict[str, t.Any] = {}
+        self.dirty = True
+
+    def id(self) -> str:
+        return self._id
+
+    def traverse(self, cb) -> None:
+        for name, value in self.values.items():
+            cb.put(name, value, 0)
+        for name, child in self.children.items():
+            cb.put(name, child, 0)
+
+    def set_value(self, name: str, value) -> None:
+        cur = self.values[name]
+        if isinstance(cur, np.ndarray):
+            new = np.asarray(value, dtype=cur.dtype)
+            if new.size != cur.size:
+                raise RuntimeError(
+                    f"parameter '{name}' of {self}: size mismatch ({new.size} != {cur.size})"
+                )
+            self.values[name] = new.reshape(cur.shape).copy()
+        else:
+            self.values[name] = type(cur)(np.asarray(value).reshape(-1)[0])
+        self.dirty = True
+
+    def __repr__(self):
+        return f"{type(self).__name__}[type={self.type}, id={self._id!r}]"
+
+
+class Texture(Object):
+    plugin_kind = "texture"
+
+
+class Volume(Object):
+    plugin_kind = "volume"
+
+    def layer_values(self) -> np.ndarray:
+        """1D profile carried by the volume (float32)."""
+        if self.type == "constvolume":
+            return np.array([self.values["value"]], dtype=np.float32)
+        if self.type == "sphericalcoordsvolume":
+            return self.children["volume"].layer_values()
+        data = self.values["data"]
+        return data.reshape(-1).astype(np.float32)
+
+
+class PhaseFunction(Object):
+    plugin_kind = "phase"
+
+
+class BSDF(Object):
+    plugin_kind = "bsdf"
+
+
+class Medium(Object):
+    plugin_kind = "medium"
+
+
+class Emitter(Object):
+    plugin_kind = "emitter"
+
+
+class Shape(Object):
+    plugin_kind = "shape"
+
+
+class Film(Object):
+    plugin_kind = "film"
+
+    def __init__(self, type_, id_=None):
+        super().__init__(type_, id_)
+        self._bitmap = None
+
+    def size(self):
+        return (self.width, self.height)
+
+    def bitmap(self, raw: bool = False):
+        if self._bitmap is None:
+            raise RuntimeError("film has not been rendered yet")
+        return self._bitmap
+
+
+class Sampler(Object):
+    plugin_kind = "sampler"
+
+
+class Sensor(Object):
+    plugin_kind = "sensor"
+
+    def film(self) -> Film:
+        return self.children["film"]
+
+    def sampler(self) -> Sampler:
+        return self.children["sampler"]
+
+
+class Integrator(Object):
+    plugin_kind = "integrator"
+
+
+class Scene(Object):
+    plugin_kind = "scene"
+
+    def __init__(self):
+        super().__init__("scene", "")
+        self._sensors: list[Sensor] = []
+        self._flat: FlatScene | None = None
+
+    def sensors(self) -> list[Sensor]:
+        return self._sensors
+
+    def integrator(self) -> Integrator:
+        return self.children[self._integrator_key]
+
+    @property
+    def flat(self) -> "FlatScene":
+        if self._flat is None:
+            self._flat = FlatScene(self)
+        return self._flat
+
+
+# ------------------------------------------------------------------------------
+#                                   loader
+# ------------------------------------------------------------------------------
+
+_SUPPORTED = {
+    "integrator": {"volpath", "volpathmis", "moment"},
+    "emitter": {"directional"},
+    "shape": {"sphere", "cube", "rectangle", "arectangle"},
+    "medium": {"heterogeneous", "homogeneous"},
+    "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "null"},
+    "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase"},
+    "sensor": {"mdistant", "hdistant", "distantflux"},
+    "volume": {"gridvolume", "sphericalcoordsvolume", "constvolume"},
+}
+_KIND_OF = {ty: kind for kind, types in _SUPPORTED.items() for ty in types}
+# plugins the reference ships for this slot but that this kernel does not (yet) implement
+_KNOWN_UNSUPPORTED = {
+    "piecewise_volpath": "the analytic piecewise integrator is a 'next' row (SURVEY 8f-1); "
+    "pass integrator={'type': 'volpath'} and atmosphere.force_majorant=True",
+    "piecewise": "the piecewise medium is a 'next' row (SURVEY 8f-1); use force_majorant=True",
+    "stokes": "polarized (Stokes) rendering is not implemented in this kernel yet",
+    "path": "surface-only integrators are out of scope",
+    "perspective": "perspective sensors (canopy scenes) are a 'next' row (SURVEY 8f-3)",
+}
+
+
+class _Loader:
+    def __init__(self, root: dict):
+        self.root = unflatten(root)
+        self.by_id: dict[str, Object] = {}
+        self.dict_by_id: dict[str, dict] = {}
+        self._index_ids(self.root, top=True)
+
+    def _index_ids(self, d: dict, top: bool = False) -> None:
+        for k, v in d.items():
+            if isinstance(v, dict) and "type" in v and v["type"] != "ref":
+                oid = v.get("id", k if top else None)
+                if oid is not None:
+                    self.dict_by_id[oid] = v
+                self._index_ids(v)
+
+    # -- generic -----------------------------------------------------------------
+    def resolve(self, value, default_id: str | None = None) -> Object:
+        """Instantiate a nested plugin dict or follow a ``ref``."""
+        if not isinstance(value, dict) or "type" not in value:
+            raise RuntimeError(f"expected a plugin dictionary, got {value!r}")
+        if value["type"] == "ref":
+            rid = value["id"]
+            if rid in self.by_id:
+                return self.by_id[rid]
+            if rid not in self.dict_by_id:
+                raise RuntimeError(f"reference to unknown object id '{rid}'")
+            return self.make(self.dict_by_id[rid], rid)
+        return self.make(value, value.get("id", default_id))
+
+    def make(self, d: dict, oid: str | None) -> Object:
+        if oid and oid in self.by_id:
+            return self.by_id[oid]
+        ty = d["type"]
+        if ty in _KNOWN_UNSUPPORTED:
+            raise RuntimeError(f"unsupported plugin '{ty}': {_KNOWN_UNSUPPORTED[ty]}")
+        kind = _KIND_OF.get(ty)
+        if kind is None:
+            raise RuntimeError(f"unsupported plugin type '{ty}' (no B200 kernel implementation)")
+        obj = getattr(self, f"make_{kind}")(d, oid)
+        if oid:
+            self.by_id[oid] = obj
+        return obj
+
+    # -- leaves ------------------------------------------------------------------
+    def make_texture(self, value, what: str) -> Texture:
+        tex = Texture("uniform")
+        tex.values["value"] = _scalar_spectrum(value, what)
+        return tex
+
+    def make_volume(self, d, oid) -> Volume:
+        if not isinstance(d, dict):  # bare float -> constvolume (Properties::get_volume)
+            vol = Volume("constvolume", oid)
+            vol.values["value"] = float(d)
+            return vol
+        ty = d["type"]
+        vol = Volume(ty, oid)
+        if ty == "constvolume":
+            vol.values["value"] = _scalar_spectrum(d.get("value", 1.0), "constvolume.value")
+        elif ty == "gridvolume":
+            if d.get("filter_type", "trilinear") != "nearest":
+                raise RuntimeError("gridvolume: only filter_type='nearest' is supported")
+            if "grid" in d:
+                data = to_grid(d["grid"])
+            elif "data" in d:
+                data = to_grid(d["data"])
+            else:
+                raise RuntimeError("gridvolume: needs a 'grid' (file loading is not supported)")
+            if data.shape[-1] != 1:
+                raise RuntimeError("gridvolume: only 1-channel grids are supported")
+            if sum(1 for s in data.shape[:3] if s > 1) > 1:
+                raise RuntimeError(
+                    f"gridvolume: only 1D profiles are supported, got shape {data.shape}"
+                )
+            vol.values["data"] = data.copy()
+            vol.to_world = to_matrix(d.get("to_world"))
+        elif ty == "sphericalcoordsvolume":
+            vol.rmin = float(d.get("rmin", 0.0))
+            vol.rmax = float(d.get("rmax", 1.0))
+            if d.get("fillmin", 0.0) != 0.0 or d.get("fillmax", 0.0) != 0.0:
+                raise RuntimeError("sphericalcoordsvolume: non-zero fill values are unsupported")
+            vol.to_world = to_matrix(d.get("to_world"))
+            vol.children["volume"] = self.make_volume(d.get("volume", 1.0), None)
+            inner = vol.children["volume"]
+            if inner.type == "gridvolume":
+                shp = inner.values["data"].shape
+                if shp[0] != 1 or shp[1] != 1:
+                    raise RuntimeError(
+                        "sphericalcoordsvolume: nested grid must vary along r only "
+                        f"(shape [1,1,N,1]), got {shp}"
+                    )
+        return vol
+
+    def make_phase(self, d, oid) -> PhaseFunction:
+        ty = d["type"]
+        ph = PhaseFunction(ty, oid)
+        if ty == "hg":
+            ph.values["g"] = float(d.get("g", 0.8))
+        elif ty == "rayleigh":
+            dep = d.get("depolarization", 0.0)
+            if isinstance(dep, dict):
+                vol = self.make_volume(dep, None)
+                vals = vol.layer_values()
+                if not np.all(vals == vals.flat[0]):
+                    raise RuntimeError("rayleigh: layer-dependent depolarization is unsupported")
+                ph.children["depolarization"] = vol
+            else:
+                ph.values["depolarization"] = float(dep)
+        elif ty == "tabphase":
+            ph.values["values"] = _parse_floats(d["values"], "tabphase.values").astype(np.float32)
+        elif ty == "tabphase_irregular":
+            ph.values["values"] = _parse_floats(d["values"], "values").astype(np.float32)
+            ph.values["nodes"] = _parse_floats(d["nodes"], "nodes").astype(np.float32)
+            n, v = ph.values["nodes"], ph.values["values"]
+            if n.size != v.size:
+                raise RuntimeError("'nodes' and 'values' must have the same length")
+            if n[0] != -1.0 or n[-1] != 1.0:
+                raise RuntimeError(f"'nodes' bounds must be [-1, 1], got [{n[0]}, {n[-1]}]")
+        elif ty == "blendphase":
+            nested = [v for k, v in d.items() if isinstance(v, dict) and k not in ("weight",)
+                      and _KIND_OF.get(v.get("type")) == "phase" or
+                      (isinstance(v, dict) and v.get("type") == "ref" and k != "weight")]
+            if len(nested) != 2:
+                raise RuntimeError("BlendPhase: Two child phase functions must be specified!")
+            ph.children["weight"] = self.make_volume(d.get("weight", 0.5), None)
+            ph.children["phase_0"] = self.resolve(nested[0])
+            ph.children["phase_1"] = self.resolve(nested[1])
+        return ph
+
+    def make_bsdf(self, d, oid) -> BSDF:
+        ty = d["type"]
+        b = BSDF(ty, oid)
+        tex = lambda name, default: self.make_texture(d.get(name, default), f"{ty}.{name}")  # noqa: E731
+        if ty == "diffuse":
+            b.children["reflectance"] = tex("reflectance", 0.5)
+        elif ty == "rpv":  # rpv.cpp:80-92
+            b.children["rho_0"] = tex("rho_0", 0.1)
+            b.children["g"] = tex("g", 0.0)
+            b.children["k"] = tex("k", 0.1)
+            b.children["rho_c"] = tex("rho_c", d.get("rho_0", 0.1))
+            b.rho_c_tied = "rho_c" not in d
+        elif ty == "rtls":  # rtls.cpp:63-78
+            b.children["f_iso"] = tex("f_iso", 0.209741)
+            b.children["f_vol"] = tex("f_vol", 0.081384)
+            b.children["f_geo"] = tex("f_geo", 0.004140)
+            b.h, b.r, b.b = float(d.get("h", 2.0)), float(d.get("r", 1.0)), float(d.get("b", 1.0))
+        elif ty == "hapke":
+            for name in ("w", "b", "c", "theta", "B_0", "h"):
+                if name not in d:
+                    raise RuntimeError(f"hapke: missing required parameter '{name}'")
+                b.children[name] = tex(name, 0.0)
+        elif ty == "ocean_legacy":
+            b.values["wavelength"] = float(d.get("wavelength", 550.0))
+            b.values["wind_speed"] = float(d.get("wind_speed", 0.1))
+            b.values["wind_direction"] = float(d.get("wind_direction", 0.0))
+            b.values["chlorinity"] = float(d.get("chlorinity", 19.0))
+            b.values["pigmentation"] = float(d.get("pigmentation", 0.3))
+            b.values["shadowing"] = bool(d.get("shadowing", True))
+            b.component = int(d.get("component", 0))
+        return b
+
+    def make_medium(self, d, oid) -> Medium:
+        ty = d["type"]
+        m = Medium(ty, oid)
+        if "phase" in d:
+            m.children["phase_function"] = self.resolve(d["phase"])
+        else:
+            cands = [v for v in d.values() if isinstance(v, dict)
+                     and (_KIND_OF.get(v.get("type")) == "phase")]
+            m.children["phase_function"] = (
+                self.resolve(cands[0]) if cands else PhaseFunction("isotropic")
+            )
+        m.children["albedo"] = self.make_volume(d.get("albedo", 0.75), None)
+        m.children["sigma_t"] = self.make_volume(d.get("sigma_t", 1.0), None)
+        m.values["scale"] = float(d.get("scale", 1.0))
+        if not d.get("has_spectral_extinction", True):
+            raise RuntimeError("has_spectral_extinction=False is not supported")
+        if not d.get("sample_emitters", True):
+            raise RuntimeError("sample_emitters=False is not supported")
+        return m
+
+    def make_emitter(self, d, oid) -> Emitter:
+        e = Emitter(d["type"], oid)
+        if "direction" in d:
+            direction = np.asarray(d["direction"], dtype=np.float64)
+        else:
+            direction = to_matrix(d.get("to_world"))[:3, :3] @ np.array([0.0, 0.0, 1.0])
+        e.direction = direction / np.linalg.norm(direction)
+        e.children["irradiance"] = self.make_texture(d.get("irradiance", 1.0), "irradiance")
+        return e
+
+    def make_shape(self, d, oid) -> Shape:
+        ty = d["type"]
+        s = Shape(ty, oid)
+        s.to_world = to_matrix(d.get("to_world"))
+        if ty == "sphere":
+            s.center = np.asarray(d.get("center", [0.0, 0.0, 0.0]), dtype=np.float64)
+            s.radius = float(d.get("radius", 1.0))
+            m = s.to_world
+            scale = np.linalg.norm(m[:3, :3], axis=0)
+            if not np.allclose(scale, scale[0], rtol=1e-9):
+                raise RuntimeError("sphere: non-uniform scaling is unsupported")
+            s.center = m[:3, :3] @ s.center + m[:3, 3]
+            s.radius *= scale[0]
+        bsdf = d.get("bsdf")
+        if bsdf is None:
+            cands = [v for v in d.values() if isinstance(v, dict)
+                     and (_KIND_OF.get(v.get("type")) == "bsdf" or
+                          (v.get("type") == "ref" and v.get("id") in self.dict_by_id and
+                           _KIND_OF.get(self.dict_by_id[v["id"]].get("type")) == "bsdf"))]
+            bsdf = cands[0] if cands else {"type": "diffuse"}
+        s.children["bsdf"] = self.resolve(bsdf)
+        if "interior" in d:
+            s.children["interior_medium"] = self.resolve(d["interior"])
+        if "exterior" in d:
+            raise RuntimeError("shapes with an exterior medium are unsupported")
+        return s
+
+    def make_sensor(self, d, oid) -> Sensor:
+        ty = d["type"]
+        s = Sensor(ty, oid)
+        film_d = d.get("film", {"type": "hdrfilm"})
+        if film_d.get("type", "hdrfilm") != "hdrfilm":
+            raise RuntimeError(f"unsupported film type '{film_d.get('type')}'")
+        rf = film_d.get("rfilter", {"type": "box"})
+        if isinstance(rf, dict) and rf.get("type", "box") != "box":
+            raise RuntimeError("only the box reconstruction filter is supported")
+        film = Film("hdrfilm")
+        film.width = int(film_d.get("width", 768))
+        film.height = int(film_d.get("height", 576))
+        film.pixel_format = film_d.get("pixel_format", "rgb")
+        s.children["film"] = film
+        samp_d = d.get("sampler", {"type": "independent"})
+        if samp_d.get("type", "independent") != "independent":
+            raise RuntimeError(f"unsupported sampler '{samp_d.get('type')}' (only 'independent')")
+        sampler = Sampler("independent")
+        sampler.sample_count = int(samp_d.get("sample_count", 4))
+        s.children["sampler"] = sampler
+        if "medium" in d:
+            raise RuntimeError("sensors inside a medium are unsupported")
+        s.ray_offset = float(d.get("ray_offset", -1.0))
+        s.to_world = to_matrix(d.get("to_world"))
+        if ty == "mdistant":
+            if "to_world" in d:
+                raise RuntimeError(
+                    "This sensor is specified through a set of origin and direction "
+                    "values and cannot use the to_world transform."
+                )
+            dirs = _parse_floats(d["directions"], "directions")
+            if dirs.size % 3 != 0:
+                raise RuntimeError(
+                    f"Invalid specification! Number of parameters {dirs.size}, is not a "
+                    "multiple of three."
+                )
+            s.directions = dirs.reshape(-1, 3)
+            if (film.width, film.height) != (s.directions.shape[0], 1):
+                raise RuntimeError(
+                    f"Film size must be [sensor_count, 1]. Expected "
+                    f"[{s.directions.shape[0]}, 1], got [{film.width}, {film.height}]"
+                )
+        tgt = d.get("target")
+        s.target_to_world = np.eye(4)
+        s.target_point = np.zeros(3)
+        if tgt is None:
+            s.target_type = _abi.TARGET_NONE
+        elif isinstance(tgt, dict):
+            if tgt.get("type") == "rectangle":
+                s.target_type = _abi.TARGET_RECTANGLE
+            elif tgt.get("type") == "disk":
+                s.target_type = _abi.TARGET_DISK
+            else:
+                raise RuntimeError(f"unsupported target shape '{tgt.get('type')}'")
+            s.target_to_world = to_matrix(tgt.get("to_world"))
+        else:
+            s.target_type = _abi.TARGET_POINT
+            s.target_point = np.asarray(tgt, dtype=np.float64).reshape(3)
+        return s
+
+    def make_integrator(self, d, oid) -> Integrator:
+        ty = d["type"]
+        it = Integrator(ty, oid)
+        it.moment = False
+        inner = d
+        if ty == "moment":
+            it.moment = True
+            nested = [v for v in d.values() if isinstance(v, dict) and "type" in v]
+            if len(nested) != 1:
+                raise RuntimeError("moment: exactly one nested integrator is supported")
+            inner = nested[0]
+            if inner["type"] in _KNOWN_UNSUPPORTED:
+                raise RuntimeError(
+                    f"unsupported plugin '{inner['type']}': {_KNOWN_UNSUPPORTED[inner['type']]}"
+                )
+            if inner["type"] not in ("volpath", "volpathmis"):
+                raise RuntimeError(f"unsupported nested integrator '{inner['type']}'")
+        it.kernel_type = inner["type"]
+        it.max_depth = int(inner.get("max_depth", -1))
+        it.rr_depth = int(inner.get("rr_depth", 5))
+        if it.max_depth < 0 and it.max_depth != -1:
+            raise RuntimeError(
+                '"max_depth" must be set to -1 (infinite) or a value >= 0'
+            )
+        if it.rr_depth <= 0:
+            raise RuntimeError('"rr_depth" must be set to a value greater than zero!')
+        return it
+
+    # -- scene ---------------------------------------------------------------------
+    def load(self) -> Object:
+        root = self.root
+        if root.get("type") != "scene":
+            return self.make(root, root.get("id"))
+        scene = Scene()
+        scene._integrator_key = None
+        for key, value in root.items():
+            if not isinstance(value, dict) or "type" not in value:
+                continue
+            if value["type"] == "ref":
+                continue
+            obj = self.make(value, value.get("id", key))
+            if obj._id == "":
+                obj._id = key
+            if obj.plugin_kind in ("integrator", "emitter", "shape", "sensor"):
+                scene.children[obj.id() or key] = obj
+            if obj.plugin_kind == "integrator":
+                scene._integrator_key = obj.id() or key
+            elif obj.plugin_kind == "sensor":
+                scene._sensors.append(obj)
+        if scene._integrator_key is None:
+            raise RuntimeError("scene has no integrator")
+        scene.flat  # validate eagerly: load errors surface at mi_load_dict time
+        return scene
+
+
+def load_dict(d: dict) -> Object:
+    return _Loader(d).load()
+
+
+# ------------------------------------------------------------------------------
+#                                  flattener
+# ------------------------------------------------------------------------------
+
+
+class FlatScene:
+    """Flat view of a :class:`Scene`; owns the numpy buffers the C ABI points to."""
+
+    def __init__(self, scene: Scene):
+        self.scene = scene
+        self._keepalive: list = []
+        self._extract()
+
+    # -- extraction ----------------------------------------------------------------
+    def _extract(self) -> None:
+        sc = self.scene
+        shapes = [o for o in sc.children.values() if isinstance(o, Shape)]
+        emitters = [o for o in sc.children.values() if isinstance(o, Emitter)]
+        if len(emitters) != 1:
+            raise RuntimeError(f"exactly one directional emitter is supported, got {len(emitters)}")
+        self.emitter = emitters[0]
+        self.integrator = sc.integrator()
+
+        atm = [s for s in shapes if "interior_medium" in s.children]
+        srf = [s for s in shapes if "interior_medium" not in s.children]
+        if len(atm) > 1:
+            raise RuntimeError("at most one medium-bearing shape is supported (1D atmospheres)")
+        if len(srf) != 1:
+            raise RuntimeError(f"exactly one surface shape is supported, got {len(srf)}")
+        self.surface_shape = srf[0]
+        self.atm_shape = atm[0] if atm else None
+        self.bsdf: BSDF = self.surface_shape.children["bsdf"]
+        if self.bsdf.type == "null":
+            raise RuntimeError("the surface shape must not carry a null BSDF")
+        if self.atm_shape is not None and self.atm_shape.children["bsdf"].type != "null":
+            raise RuntimeError("the atmosphere stencil shape must carry a null BSDF")
+
+        # geometry ------------------------------------------------------------------
+        s = self.surface_shape
+        if s.type == "sphere":
+            self.geometry = _abi.GEOM_SPHERICAL_SHELL
+            if not np.allclose(s.center, 0.0, atol=1e-6 * s.radius):
+                raise RuntimeError("spherical-shell scenes must be centred at the origin")
+            self.surface_z = s.radius
+        elif s.type in ("rectangle", "arectangle"):
+            self.geometry = _abi.GEOM_PLANE_PARALLEL
+            n = s.to_world[:3, :3] @ np.array([0.0, 0.0, 1.0])
+            if not np.allclose(n / np.linalg.norm(n), [0, 0, 1], atol=1e-9):
+                raise RuntimeError("the ground rectangle must be horizontal (normal +Z)")
+            self.surface_z = float(s.to_world[2, 3])
+        else:
+            raise RuntimeError(f"unsupported surface shape '{s.type}'")
+
+        bbox_lo, bbox_hi = _shape_bbox(s)
+        self.medium = None
+        self.medium_top = self.surface_z
+        self.medium_bottom = self.surface_z
+        if self.atm_shape is not None:
+            a = self.atm_shape
+            lo, hi = _shape_bbox(a)
+            bbox_lo, bbox_hi = np.minimum(bbox_lo, lo), np.maximum(bbox_hi, hi)
+            self.medium = a.children["interior_medium"]
+            if self.geometry == _abi.GEOM_SPHERICAL_SHELL:
+                if a.type != "sphere":
+                    raise RuntimeError("spherical-shell atmosphere must use a sphere stencil")
+                self.medium_top = a.radius
+            else:
+                if a.type != "cube":
+                    raise RuntimeError("plane-parallel atmosphere must use a cube stencil")
+                self.medium_top = float(hi[2])
+            self._extract_medium()
+        self.bsphere_center = 0.5 * (bbox_lo + bbox_hi)
+        self.bsphere_radius = float(0.5 * np.linalg.norm(bbox_hi - bbox_lo))
+        self.sensors = sc.sensors()
+        if not self.sensors:
+            raise RuntimeError("scene has no sensor")
+
+    def _extract_medium(self) -> None:
+        m = self.medium
+        st, al = m.children["sigma_t"], m.children["albedo"]
+        self.homogeneous = m.type == "homogeneous"
+        if self.homogeneous:
+            if st.type != "constvolume" or al.type != "constvolume":
+                raise RuntimeError("homogeneous medium expects constant sigma_t / albedo")
+            self.medium_bottom = self.surface_z
+            return
+        top_tol = 1e-6 * abs(self.medium_top)
+        if self.geometry == _abi.GEOM_SPHERICAL_SHELL:
+            for v in (st, al):
+                if v.type == "constvolume":
+                    continue
+                if v.type != "sphericalcoordsvolume":
+                    raise RuntimeError(
+                        "spherical-shell media must use sphericalcoordsvolume (or constant) volumes"
+                    )
+                scale = np.linalg.norm(v.to_world[:3, :3], axis=0)
+                if not np.allclose(scale, self.medium_top, atol=top_tol) or v.rmax != 1.0:
+                    raise RuntimeError("sphericalcoordsvolume extent must match the TOA sphere")
+            rmin = st.rmin if st.type == "sphericalcoordsvolume" else self.surface_z / self.medium_top
+            self.medium_bottom = float(rmin * self.medium_top)
+        else:
+            ref = next((v for v in (st, al) if v.type == "gridvolume"), None)
+            if ref is None:
+                self.medium_bottom = self.surface_z
+            else:
+                z0 = float((ref.to_world @ np.array([0.0, 0.0, 0.0, 1.0]))[2])
+                z1 = float((ref.to_world @ np.array([0.0, 0.0, 1.0, 1.0]))[2])
+                if abs(z1 - self.medium_top) > max(top_tol, 1e-6):
+                    raise RuntimeError("gridvolume z-extent must end at the top of the slab")
+                if ref.values["data"].shape[1] != 1 or ref.values["data"].shape[2] != 1:
+                    raise RuntimeError("plane-parallel grids must vary along z only ([N,1,1,1])")
+                self.medium_bottom = z0
+
+    # -- per-layer arrays ----------------------------------------------------------------
+    def n_layers(self) -> int:
+        if self.medium is None:
+            return 0
+        n = 1
+        for v in self._layer_volumes():
+            n = max(n, v.layer_values().size)
+        return n
+
+    def _layer_volumes(self) -> list[Volume]:
+        vols = [self.medium.children["sigma_t"], self.medium.children["albedo"]]
+
+        def walk(ph):
+            if ph.type == "blendphase":
+                vols.append(ph.children["weight"])
+                walk(ph.children["phase_0"])
+                walk(ph.children["phase_1"])
+
+        walk(self.medium.children["phase_function"])
+        return vols
+
+    def _profile(self, vol: Volume, n: int, what: str) -> np.ndarray:
+        v = vol.layer_values()
+        if v.size == 1:
+            return np.full(n, v[0], dtype=np.float32)
+        if v.size != n:
+            raise RuntimeError(
+                f"{what}: all per-layer volumes must share one vertical grid "
+                f"({v.size} != {n} layers)"
+            )
+        return v.astype(np.float32)
+
+    def phase_leaves(self, n: int):
+        """Flatten the blendphase tree: list of (leaf node, probability[n])."""
+        leaves: list[tuple[PhaseFunction, np.ndarray]] = []
+
+        def walk(ph: PhaseFunction, prob: np.ndarray):
+            if ph.type == "blendphase":
+                w = np.clip(self._profile(ph.children["weight"], n, "blendphase.weight"), 0.0, 1.0)
+                walk(ph.children["phase_0"], prob * (1.0 - w))
+                walk(ph.children["phase_1"], prob * w)
+            else:
+                leaves.append((ph, prob.astype(np.float32)))
+
+        walk(self.medium.children["phase_function"], np.ones(n, dtype=np.float32))
+        if len(leaves) > _abi.MAX_PHASE:
+            raise RuntimeError(
+                f"phase function tree has {len(leaves)} leaves; at most {_abi.MAX_PHASE} supported"
+            )
+        return leaves
+
+    def bsdf_params(self) -> np.ndarray:
+        b = self.bsdf
+        p = np.zeros(_abi.MAX_BSDF_PARAMS, dtype=np.float32)
+        tv = lambda name: b.children[name].values["value"]  # noqa: E731
+        if b.type == "diffuse":
+            p[0] = tv("reflectance")
+        elif b.type == "rpv":
+            p[0], p[1], p[2] = tv("rho_0"), tv("k"), tv("g")
+            p[3] = tv("rho_0") if getattr(b, "rho_c_tied", False) else tv("rho_c")
+        elif b.type == "rtls":
+            p[0], p[1], p[2] = tv("f_iso"), tv("f_vol"), tv("f_geo")
+            p[3], p[4], p[5] = b.h, b.r, b.b
+        elif b.type == "hapke":
+            for i, name in enumerate(("w", "b", "c", "theta", "B_0", "h")):
+                p[i] = tv(name)
+        elif b.type == "ocean_legacy":
+            v = b.values
+            p[0], p[1], p[2] = v["wavelength"], v["wind_speed"], v["wind_direction"]
+            p[3], p[4], p[5] = v["chlorinity"], v["pigmentation"], float(v["shadowing"])
+            p[6] = float(b.component)
+        return p
+
+    def bsdf_type(self) -> int:
+        return {
+            "diffuse": _abi.BSDF_DIFFUSE,
+            "rpv": _abi.BSDF_RPV,
+            "rtls": _abi.BSDF_RTLS,
+            "hapke": _abi.BSDF_HAPKE,
+            "ocean_legacy": _abi.BSDF_OCEAN_LEGACY,
+        }[self.bsdf.type]
+
+    # -- ctypes descriptor -----------------------------------------------------------------
+    def build_desc(self) -> _abi.SceneDesc:
+        """Build the POD descriptor.  Buffers stay alive as long as ``self``."""
+        keep: list = []
+        d = _abi.SceneDesc()
+        d.abi_version = _abi.ABI_VERSION
+        d.geometry = self.geometry
+        d.surface_z = self.surface_z
+        d.medium_bottom = self.medium_bottom
+        d.medium_top = self.medium_top
+        d.bsphere_center[:] = list(self.bsphere_center)
+        d.bsphere_radius = self.bsphere_radius
+
+        n = self.n_layers()
+        d.has_medium = int(self.medium is not None)
+        d.n_layers = n
+        d.n_phase = 0
+        d.sigma_t_scale = 1.0
+        if self.medium is not None:
+            if n > _abi.MAX_LAYERS:
+                raise RuntimeError(f"too many layers ({n} > {_abi.MAX_LAYERS})")
+            m = self.medium
+            sig = np.ascontiguousarray(self._profile(m.children["sigma_t"], n, "sigma_t"))
+            alb = np.ascontiguousarray(self._profile(m.children["albedo"], n, "albedo"))
+            keep += [sig, alb]
+            d.sigma_t = sig.ctypes.data_as(_abi.c_float_p)
+            d.albedo = alb.ctypes.data_as(_abi.c_float_p)
+            d.sigma_t_scale = m.values["scale"]
+            d.homogeneous = int(self.homogeneous)
+            leaves = self.phase_leaves(n)
+            d.n_phase = len(leaves)
+            w = np.ascontiguousarray(np.stack([p for _, p in leaves]).astype(np.float32))
+            keep.append(w)
+            d.phase_weight = w.ctypes.data_as(_abi.c_float_p)
+            for i, (ph, _) in enumerate(leaves):
+                pd = d.phase[i]
+                pd.type, params, values, nodes = _phase_leaf_desc(ph)
+                pd.params[:] = params
+                if values is not None:
+                    values = np.ascontiguousarray(values, dtype=np.float32)
+                    if values.size > _abi.MAX_PHASE_NODES:
+                        raise RuntimeError("tabulated phase function has too many nodes")
+                    keep.append(values)
+                    pd.n_nodes = values.size
+                    pd.values = values.ctypes.data_as(_abi.c_float_p)
+                if nodes is not None:
+                    nodes = np.ascontiguousarray(nodes, dtype=np.float32)
+                    keep.append(nodes)
+                    pd.nodes = nodes.ctypes.data_as(_abi.c_float_p)
+
+        d.bsdf_type = self.bsdf_type()
+        d.bsdf_params[:] = list(self.bsdf_params())
+        d.emitter_direction[:] = list(self.emitter.direction)
+        d.irradiance = self.emitter.children["irradiance"].values["value"]
+        it = self.integrator
+        d.integrator = (
+            _abi.INTEGRATOR_VOLPATHMIS if it.kernel_type == "volpathmis" else _abi.INTEGRATOR_VOLPATH
+        )
+        d.rr_depth = it.rr_depth
+        d.max_depth = it.max_depth
+
+        sens = (_abi.SensorDesc * len(self.sensors))()
+        for i, s in enumerate(self.sensors):
+            sd = sens[i]
+            sd.type = {
+                "mdistant": _abi.SENSOR_MDISTANT,
+                "hdistant": _abi.SENSOR_HDISTANT,
+                "distantflux": _abi.SENSOR_DISTANTFLUX,
+            }[s.type]
+            sd.width, sd.height = s.film().width, s.film().height
+            if s.type == "mdistant":
+                dirs = np.ascontiguousarray(s.directions, dtype=np.float64)
+                keep.append(dirs)
+                sd.n_directions = dirs.shape[0]
+                sd.directions = dirs.ctypes.data_as(_abi.c_double_p)
+            sd.to_world[:] = list(s.to_world.reshape(-1))
+            sd.target_type = s.target_type
+            sd.target[:] = list(s.target_point)
+            sd.target_to_world[:] = list(s.target_to_world.reshape(-1))
+            sd.ray_offset = s.ray_offset
+        keep.append(sens)
+        d.n_sensors = len(self.sensors)
+        d.sensors = C.cast(sens, C.POINTER(_abi.SensorDesc))
+        self._keepalive = keep
+        return d
+
+
+def _phase_leaf_desc(ph: PhaseFunction):
+    params = [0.0, 0.0, 0.0, 0.0]
+    if ph.type == "isotropic":
+        return _abi.PHASE_ISOTROPIC, params, None, None
+    if ph.type == "rayleigh":
+        if "depolarization" in ph.children:
+            params[0] = float(ph.children["depolarization"].layer_values().flat[0])
+        else:
+            params[0] = ph.values.get("depolarization", 0.0)
+        if params[0] >= 1.0:
+            raise RuntimeError("Depolarization factor must be in [0, 1[")
+        return _abi.PHASE_RAYLEIGH, params, None, None
+    if ph.type == "hg":
+        g = ph.values["g"]
+        if not (-1.0 < g < 1.0):
+            raise RuntimeError("The asymmetry parameter must lie in the interval (-1, 1)!")
+        params[0] = g
+        return _abi.PHASE_HG, params, None, None
+    if ph.type == "tabphase":
+        return _abi.PHASE_TABULATED, params, ph.values["values"], None
+    if ph.type == "tabphase_irregular":
+        return _abi.PHASE_TABULATED_IRREGULAR, params, ph.values["values"], ph.values["nodes"]
+    raise RuntimeError(f"unsupported phase function '{ph.type}'")
+
+
+def _shape_bbox(s: Shape):
+    if s.type == "sphere":
+        return s.center - s.radius, s.center + s.radius
+    if s.type == "cube":
+        corners = np.array(
+            [[x, y, z, 1.0] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], dtype=np.float64
+        )
+    else:  # rectangle / arectangle: [-1,1]^2 in the local XY plane
+        corners = np.array([[x, y, 0.0, 1.0] for x in (-1, 1) for y in (-1, 1)], dtype=np.float64)
+    w = (s.to_world @ corners.T).T[:, :3]
+    return w.min(axis=0), w.max(axis=0)

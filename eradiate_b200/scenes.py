@@ -1,0 +1,389 @@
+"""
+Synthetic scene dictionaries restating what Eradiate's scene compiler emits for
+its 1D atmosphere experiments (reference templates:
+``src/eradiate/scenes/atmosphere/_core.py:640-724``, ``shapes/_sphere.py``,
+``shapes/_cuboid.py:223-290``, ``shapes/_rectangle.py``, ``bsdfs/_rpv.py:104-125``,
+``illumination/_directional.py``, ``measure/_core.py:218-245``,
+``measure/_multi_distant.py:655-667``, ``integrators/_path_tracers.py:53-80``).
+
+Eradiate itself cannot be imported in the build environment (no pint / xarray /
+joseki / absorption databases), so the AFGL-1986-shaped radiative profile below is
+synthetic and deterministic.  The *dict layout* is the
+reference's; the kernel consumes it through ``mi_load_dict`` unchanged.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .kernel._kernel_dict import (
+    KernelSceneParameterFlags,
+    KernelSceneParameterMap,
+    SceneParameter,
+    SearchSceneParameter,
+)
+from .kernel._scene import Emitter, Medium
+from .kernel._types import ScalarTransform4f, VolumeGrid, map_cube, map_unit_cube
+
+EARTH_RADIUS = 6378.1e3  # m, src/eradiate/constants.py:8
+TOA = 120.0e3  # m, default z-grid top (src/eradiate/scenes/geometry.py:69-81)
+
+
+# ------------------------------------------------------------------------------
+#                         synthetic radiative profiles
+# ------------------------------------------------------------------------------
+
+
+def afgl_like_profile(n_layers: int = 1200, toa: float = TOA, w_nm: float = 550.0):
+    """
+    AFGL-1986-shaped molecular profile: Rayleigh scattering with an
+    8 km scale height, lambda^-4 scaling around 550 nm (magnitude from
+    ``src/eradiate/radprops/rayleigh.py:77-140`` at standard density) and an
+    ozone-like Chappuis absorber centred at 22 km.  Returned float32, exactly as
+    the reference stores its grids (``atmosphere/_core.py:659,674``).
+    """
+    dz = toa / n_layers
+    z = (np.arange(n_layers) + 0.5) * dz
+    sigma_s = 1.16e-5 * (550.0 / w_nm) ** 4 * np.exp(-z / 8000.0)
+    chappuis = np.exp(-(((w_nm - 600.0) / 120.0) ** 2)) / np.exp(-((50.0 / 120.0) ** 2))
+    sigma_a = 5.0e-7 * chappuis * np.exp(-(((z - 22000.0) / 5000.0) ** 2))
+    sigma_t = sigma_s + sigma_a
+    albedo = sigma_s / sigma_t
+    return z, sigma_t.astype(np.float32), albedo.astype(np.float32)
+
+
+def aerosol_layer(z, bottom=1000.0, top=2000.0, tau_ref=0.5, ssa=0.9):
+    """Uniform particle layer (``test_cases/atmospheres.py:71-77`` shape)."""
+    inside = (z >= bottom) & (z < top)
+    sigma_t = np.where(inside, tau_ref / (top - bottom), 0.0)
+    return sigma_t.astype(np.float64), np.full_like(sigma_t, ssa)
+
+
+def hg_table(g: float = 0.7, n: int = 181):
+    """HG phase function sampled on a regular cos(theta) grid, physics convention."""
+    mu = np.linspace(-1.0, 1.0, n)
+    p = (1.0 - g * g) / (4.0 * np.pi * (1.0 + g * g - 2.0 * g * mu) ** 1.5)
+    return mu, p
+
+
+# ------------------------------------------------------------------------------
+#                                direction helpers
+# ------------------------------------------------------------------------------
+
+
+def angles_to_direction(zenith_deg, azimuth_deg):
+    """Unit vector pointing *towards* (zenith, azimuth); +Z is local up."""
+    th, ph = np.deg2rad(zenith_deg), np.deg2rad(azimuth_deg)
+    return np.stack(
+        [np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], axis=-1
+    )
+
+
+def _look_at_direction(d):
+    """``to_world`` mapping +Z to ``d`` (illumination/_directional.py)."""
+    d = np.asarray(d, dtype=np.float64)
+    up = np.array([0.0, 0.0, 1.0]) if abs(d[2]) < 0.999 else np.array([1.0, 0.0, 0.0])
+    return ScalarTransform4f().look_at([0, 0, 0], d, up)
+
+
+# ------------------------------------------------------------------------------
+#                                  scene builder
+# ------------------------------------------------------------------------------
+
+
+def atmosphere_scene(
+    geometry: str = "spherical_shell",
+    atmosphere: str | None = "afgl",
+    n_layers: int = 1200,
+    aerosol: bool = False,
+    aerosol_phase: str = "tabphase",
+    surface: dict | None = None,
+    sza: float = 30.0,
+    saa: float = 0.0,
+    irradiance: float = 1.8,
+    sensor: dict | None = None,
+    spp: int = 1024,
+    integrator: str = "volpath",
+    moment: bool = True,
+    max_depth: int | None = None,
+    rr_depth: int | None = None,
+    w_nm: float = 550.0,
+    planet_radius: float = EARTH_RADIUS,
+    toa: float = TOA,
+    homogeneous_sigma_t: float = 1.16e-5,
+    homogeneous_albedo: float = 1.0,
+    phase: dict | None = None,
+) -> dict:
+    """Build the nested scene dict an ``AtmosphereExperiment`` would emit."""
+    if surface is None:
+        surface = {"type": "rpv", "rho_0": 0.027685, "k": 0.95, "g": -0.1}  # atmospheres.py:100
+    surface = _spectrumify(dict(surface))
+    surface["id"] = "surface_bsdf"
+    scene: dict = {"type": "scene"}
+
+    integ: dict = {"type": integrator}
+    if max_depth is not None:
+        integ["max_depth"] = max_depth
+    if rr_depth is not None:
+        integ["rr_depth"] = rr_depth
+    scene["integrator"] = {"type": "moment", "nested": integ} if moment else integ
+
+    sun = angles_to_direction(sza, saa)
+    scene["illumination"] = {
+        "type": "directional",
+        "to_world": _look_at_direction(-sun),
+        "irradiance": {"type": "uniform", "value": irradiance},
+    }
+
+    spherical = geometry == "spherical_shell"
+    if not spherical and geometry != "plane_parallel":
+        raise ValueError(f"unknown geometry '{geometry}'")
+
+    scene["surface_bsdf"] = surface
+    width = 1.0e9  # PlaneParallelGeometry.width default 1e6 km (geometry.py:182-189)
+    if spherical:
+        scene["surface_shape"] = {
+            "type": "sphere",
+            "center": [0.0, 0.0, 0.0],
+            "radius": planet_radius,
+            "bsdf": {"type": "ref", "id": "surface_bsdf"},
+        }
+        target = [0.0, 0.0, planet_radius]
+    else:
+        scene["surface_shape"] = {
+            "type": "rectangle",
+            "to_world": ScalarTransform4f().scale([0.5 * width, 0.5 * width, 1.0]),
+            "bsdf": {"type": "ref", "id": "surface_bsdf"},
+        }
+        target = [0.0, 0.0, 0.0]
+
+    if atmosphere is not None:
+        if atmosphere == "afgl":
+            z, sigma_t, albedo = afgl_like_profile(n_layers, toa, w_nm)
+            sigma_t = sigma_t.astype(np.float64)
+            albedo = albedo.astype(np.float64)
+            weight = None
+            if aerosol:
+                st_a, al_a = aerosol_layer(z)
+                ss_m, ss_a = sigma_t * albedo, st_a * al_a
+                tot = sigma_t + st_a
+                albedo = (ss_m + ss_a) / tot
+                sigma_t = tot
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    weight = np.where(ss_m + ss_a > 0, ss_a / (ss_m + ss_a), 0.0)
+            medium_type = "heterogeneous"
+        elif atmosphere == "homogeneous":
+            sigma_t = np.array([homogeneous_sigma_t])
+            albedo = np.array([homogeneous_albedo])
+            weight = None
+            medium_type = "homogeneous"
+        else:
+            raise ValueError(f"unknown atmosphere '{atmosphere}'")
+
+        if phase is None:
+            phase = {"type": "rayleigh"}
+        if aerosol and weight is not None:
+            if aerosol_phase == "tabphase":
+                _, p = hg_table()
+                aer_phase = {"type": "tabphase", "values": ",".join(map(str, p))}
+            elif aerosol_phase == "tabphase_irregular":
+                mu = np.concatenate([np.linspace(-1, 0.5, 40), np.linspace(0.5, 1.0, 121)[1:]])
+                g = 0.7
+                p = (1.0 - g * g) / (4.0 * np.pi * (1.0 + g * g - 2.0 * g * mu) ** 1.5)
+                aer_phase = {
+                    "type": "tabphase_irregular",
+                    "values": ",".join(map(str, p)),
+                    "nodes": ",".join(map(str, mu)),
+                }
+            else:
+                aer_phase = {"type": "hg", "g": 0.7}
+            phase_dict = {
+                "type": "blendphase",
+                "phase_0": phase,
+                "phase_1": aer_phase,
+                "weight": _volume(weight, spherical, planet_radius, toa, width),
+            }
+        else:
+            phase_dict = phase
+        phase_dict = dict(phase_dict)
+        phase_dict["id"] = "phase_atmosphere"
+        scene["phase_atmosphere"] = phase_dict
+
+        if medium_type == "homogeneous":
+            medium = {
+                "type": "homogeneous",
+                "sigma_t": float(sigma_t[0]),
+                "albedo": float(albedo[0]),
+            }
+        else:
+            medium = {
+                "type": "heterogeneous",
+                "sigma_t": _volume(sigma_t, spherical, planet_radius, toa, width),
+                "albedo": _volume(albedo, spherical, planet_radius, toa, width),
+            }
+        medium["phase"] = {"type": "ref", "id": "phase_atmosphere"}
+        medium["id"] = "medium_atmosphere"
+        scene["medium_atmosphere"] = medium
+
+        if spherical:
+            scene["shape_atmosphere"] = {
+                "type": "sphere",
+                "center": [0.0, 0.0, 0.0],
+                "radius": planet_radius + toa,
+                "bsdf": {"type": "null"},
+                "interior": {"type": "ref", "id": "medium_atmosphere"},
+            }
+        else:
+            bottom = -0.01 * toa  # shapes/_cuboid.py:288 (1 % below the ground)
+            scene["shape_atmosphere"] = {
+                "type": "cube",
+                "to_world": map_cube(-0.5 * width, 0.5 * width, -0.5 * width, 0.5 * width, bottom, toa),
+                "bsdf": {"type": "null"},
+                "interior": {"type": "ref", "id": "medium_atmosphere"},
+            }
+
+    if sensor is None:
+        sensor = {"type": "mdistant", "vza": np.linspace(-75.0, 75.0, 32), "vaa": 0.0}
+    scene["measure"] = _sensor_dict(dict(sensor), target, spp)
+    return scene
+
+
+def _spectrumify(bsdf: dict) -> dict:
+    """Wrap scalar BSDF parameters as uniform spectra, as Eradiate does."""
+    spectral = {
+        "diffuse": ("reflectance",),
+        "rpv": ("rho_0", "k", "g", "rho_c"),
+        "rtls": ("f_iso", "f_vol", "f_geo"),
+        "hapke": ("w", "b", "c", "theta", "B_0", "h"),
+    }.get(bsdf.get("type"), ())
+    for k in spectral:
+        if k in bsdf and not isinstance(bsdf[k], dict):
+            bsdf[k] = {"type": "uniform", "value": float(bsdf[k])}
+    return bsdf
+
+
+def _volume(values, spherical: bool, planet_radius: float, toa: float, width: float) -> dict:
+    values = np.asarray(values, dtype=np.float64)
+    if spherical:
+        rtoa = planet_radius + toa
+        return {
+            "type": "sphericalcoordsvolume",
+            "volume": {
+                "type": "gridvolume",
+                "grid": VolumeGrid(np.reshape(values, (1, 1, -1)).astype(np.float32)),
+                "filter_type": "nearest",
+            },
+            "to_world": map_cube(-rtoa, rtoa, -rtoa, rtoa, -rtoa, rtoa),
+            "rmin": planet_radius / rtoa,
+        }
+    return {
+        "type": "gridvolume",
+        "grid": VolumeGrid(np.reshape(values, (-1, 1, 1)).astype(np.float32)),
+        "to_world": map_unit_cube(-0.5 * width, 0.5 * width, -0.5 * width, 0.5 * width, 0.0, toa),
+        "filter_type": "nearest",
+    }
+
+
+def _sensor_dict(sensor: dict, target, spp: int) -> dict:
+    ty = sensor.pop("type")
+    out: dict = {"type": ty, "id": sensor.pop("id", "measure")}
+    if ty == "mdistant":
+        vza = np.atleast_1d(np.asarray(sensor.pop("vza"), dtype=np.float64))
+        vaa = float(sensor.pop("vaa", 0.0))
+        # hplane layout: negative zeniths point to azimuth + 180 deg
+        az = np.where(vza < 0, vaa + 180.0, vaa)
+        view = angles_to_direction(np.abs(vza), az)
+        out["directions"] = ",".join(map(str, (-view).ravel(order="C")))
+        width, height = vza.size, 1
+    else:
+        res = sensor.pop("film_resolution", (32, 32))
+        width, height = int(res[0]), int(res[1])
+        if "to_world" in sensor:
+            out["to_world"] = sensor.pop("to_world")
+    tgt = sensor.pop("target", target)
+    if tgt is not None:
+        out["target"] = tgt
+    if "ray_offset" in sensor:
+        out["ray_offset"] = sensor.pop("ray_offset")
+    out["film"] = {
+        "type": "hdrfilm",
+        "width": width,
+        "height": height,
+        "pixel_format": "luminance",
+        "component_format": "float32",
+        "rfilter": {"type": "box"},
+    }
+    out["sampler"] = {"type": "independent", "sample_count": int(spp)}
+    return out
+
+
+# ------------------------------------------------------------------------------
+#                         BASELINE.json configurations
+# ------------------------------------------------------------------------------
+
+
+def config_c1(spp: int = 4096) -> dict:
+    """C1: homogeneous molecular atmosphere, Lambertian rho=0.5, plane-parallel, 1 angle."""
+    return atmosphere_scene(
+        geometry="plane_parallel",
+        atmosphere="homogeneous",
+        surface={"type": "diffuse", "reflectance": 0.5},
+        sensor={"type": "mdistant", "vza": [0.0], "vaa": 0.0},
+        spp=spp,
+    )
+
+
+def config_c2(spp: int = 1 << 20, n_vza: int = 32) -> dict:
+    """C2: AFGL1986-shaped molecular atmosphere + RPV, spherical shell, mdistant 32 VZA."""
+    return atmosphere_scene(
+        geometry="spherical_shell",
+        atmosphere="afgl",
+        sensor={"type": "mdistant", "vza": np.linspace(-75.0, 75.0, n_vza), "vaa": 0.0},
+        spp=spp,
+    )
+
+
+def config_c3(spp: int = 1 << 22, res: int = 32, w_nm: float = 865.0) -> dict:
+    """C3: AFGL + aerosol layer (tab_phase), hdistant hemispherical film."""
+    return atmosphere_scene(
+        geometry="spherical_shell",
+        atmosphere="afgl",
+        aerosol=True,
+        w_nm=w_nm,
+        sensor={"type": "hdistant", "film_resolution": (res, res)},
+        spp=spp,
+    )
+
+
+def spectral_update_map(n_layers: int = 1200, spherical: bool = True) -> KernelSceneParameterMap:
+    """
+    Update map equivalent to ``atmosphere/_core.py:777-805`` +
+    ``illumination/_directional.py``: per-context sigma_t / albedo / irradiance.
+    """
+    rel = "volume.data" if spherical else "data"
+
+    def sigma_t(ctx):
+        return afgl_like_profile(n_layers, TOA, ctx.si.w)[1]
+
+    def albedo(ctx):
+        return afgl_like_profile(n_layers, TOA, ctx.si.w)[2]
+
+    return KernelSceneParameterMap(
+        {
+            "medium_atmosphere.sigma_t": SceneParameter(
+                sigma_t,
+                KernelSceneParameterFlags.SPECTRAL,
+                search=SearchSceneParameter(Medium, "medium_atmosphere", f"sigma_t.{rel}"),
+            ),
+            "medium_atmosphere.albedo": SceneParameter(
+                albedo,
+                KernelSceneParameterFlags.SPECTRAL,
+                search=SearchSceneParameter(Medium, "medium_atmosphere", f"albedo.{rel}"),
+            ),
+            "illumination.irradiance.value": SceneParameter(
+                lambda ctx: 1.8 * (550.0 / ctx.si.w),
+                KernelSceneParameterFlags.SPECTRAL,
+                search=SearchSceneParameter(Emitter, "illumination", "irradiance.value"),
+            ),
+        }
+    )

@@ -1,0 +1,242 @@
+/*
+ * eradiate_b200.h -- C ABI of the B200-native Monte Carlo volumetric path
+ * tracer that replaces the Mitsuba kernel behind eradiate.kernel.mi_render.
+ *
+ * Drop-in boundary (reference, read-only):
+ *   src/eradiate/kernel/_render.py:186  mi_load_dict   -> ertb_scene_create
+ *   src/eradiate/kernel/_render.py:212  mi_traverse    -> (host only; parameter
+ *                                                          keys map to ertb_scene_update_*)
+ *   src/eradiate/kernel/_render.py:440  parameters.update(...) -> ertb_scene_update_*
+ *   src/eradiate/kernel/_render.py:459  mi.render(scene, sensor, seed, spp)
+ *                                                      -> ertb_render / ertb_render_device
+ *   src/eradiate/kernel/_render.py:466  mi.Bitmap(film.bitmap()) -> the three
+ *                                       per-pixel accumulators written by ertb_render
+ *
+ * The scene arrives as a flat POD descriptor: the Python host
+ * (eradiate_b200/kernel/_scene.py) walks the very same nested Mitsuba dict
+ * Eradiate builds today and flattens it.  Every field cites the reference
+ * plugin parameter it carries.  No torch / C++ types cross this boundary.
+ *
+ * All functions return 0 on success, non-zero on failure; the message is
+ * available from ertb_last_error() (thread-local).  The host shim raises
+ * RuntimeError, mirroring src/eradiate/experiments/_core.py:670-671.
+ */
+#ifndef ERADIATE_B200_H
+#define ERADIATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ERTB_ABI_VERSION 3
+#define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
+#define ERTB_MAX_BSDF_PARAMS 16
+#define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
+#define ERTB_MAX_PHASE_NODES 2048
+
+/* Scene geometry: the three 1D stencils Eradiate emits
+ * (src/eradiate/scenes/geometry.py:176-266). */
+enum ertb_geometry {
+    ERTB_GEOM_PLANE_PARALLEL = 0, /* cube slab + (a)rectangle ground */
+    ERTB_GEOM_SPHERICAL_SHELL = 1 /* sphere (TOA, null BSDF) + sphere (ground) */
+};
+
+/* ERP/bsdfs + MI/src/bsdfs emitted by eradiate's bsdf_factory
+ * (src/eradiate/scenes/bsdfs/_core.py:13-29). */
+enum ertb_bsdf_type {
+    ERTB_BSDF_DIFFUSE = 0,      /* MI/src/bsdfs/diffuse.cpp:100-178; params: reflectance */
+    ERTB_BSDF_RPV = 1,          /* ERP/bsdfs/rpv.cpp:99-193;   params: rho_0, k, g, rho_c */
+    ERTB_BSDF_RTLS = 2,         /* ERP/bsdfs/rtls.cpp:86-293;  params: f_iso, f_vol, f_geo, h, r, b */
+    ERTB_BSDF_HAPKE = 3,        /* ERP/bsdfs/hapke.cpp:93-381; params: w, b, c, theta(deg), B_0, h */
+    ERTB_BSDF_OCEAN_LEGACY = 4, /* ERP/bsdfs/ocean_legacy.cpp; params: wavelength(nm), wind_speed,
+                                   wind_direction(deg), chlorinity, pigmentation, shadowing(0/1),
+                                   then 5 host-derived scalars, see _scene.py */
+    ERTB_BSDF_BLACK = 5         /* reflectance 0 (no surface contribution) */
+};
+
+enum ertb_phase_type {
+    ERTB_PHASE_ISOTROPIC = 0,  /* MI/src/phase/isotropic.cpp:39-60 */
+    ERTB_PHASE_RAYLEIGH = 1,   /* MI/src/phase/rayleigh.cpp:61-110; params[0] = depolarization */
+    ERTB_PHASE_HG = 2,         /* MI/src/phase/hg.cpp:64-100; params[0] = g */
+    ERTB_PHASE_TABULATED = 3,  /* MI/src/phase/tabphase.cpp:77-124 (regular cos-theta grid) */
+    ERTB_PHASE_TABULATED_IRREGULAR = 4 /* ERP/phase/tabphase_irregular.cpp:111-152 */
+};
+
+enum ertb_sensor_type {
+    ERTB_SENSOR_MDISTANT = 0,   /* ERP/sensors/mdistant.cpp:192-242 */
+    ERTB_SENSOR_HDISTANT = 1,   /* ERP/sensors/hdistant.cpp:232-275 */
+    ERTB_SENSOR_DISTANTFLUX = 2 /* ERP/sensors/distantflux.cpp:148-195 */
+};
+
+enum ertb_target_type {
+    ERTB_TARGET_NONE = 0,      /* bounding-sphere cross section */
+    ERTB_TARGET_POINT = 1,
+    ERTB_TARGET_RECTANGLE = 2, /* shape target: rectangle with a to_world */
+    ERTB_TARGET_DISK = 3
+};
+
+enum ertb_integrator_type {
+    ERTB_INTEGRATOR_VOLPATH = 0,   /* MI/src/integrators/volpath.cpp:93-572 */
+    ERTB_INTEGRATOR_VOLPATHMIS = 1 /* MI/src/integrators/volpathmis.cpp:124-669 (mono: 1x1 weights) */
+};
+
+/* One leaf of the (flattened) phase-function tree. */
+typedef struct ertb_phase_desc {
+    int32_t type;          /* enum ertb_phase_type */
+    int32_t n_nodes;       /* tabulated: number of entries of `values` (>= 2) */
+    float params[4];       /* see enum */
+    const float *values;   /* tabulated: pdf samples, physics convention, cos(theta) ascending */
+    const float *nodes;    /* tabulated_irregular: cos(theta) nodes in [-1,1]; NULL otherwise */
+} ertb_phase_desc;
+
+typedef struct ertb_sensor_desc {
+    int32_t type;          /* enum ertb_sensor_type */
+    int32_t width, height; /* film size; mdistant: width = n_directions, height = 1 */
+    int32_t n_directions;  /* mdistant */
+    const double *directions; /* mdistant: 3*n, ray propagation directions (as in the plugin's
+                                 `directions` string), need not be normalised */
+    double to_world[16];   /* hdistant / distantflux: row-major 4x4 */
+    int32_t target_type;   /* enum ertb_target_type */
+    int32_t _pad0;
+    double target[3];      /* point target */
+    double target_to_world[16]; /* rectangle/disk target: maps [-1,1]^2 x {0} (unit disk) to world */
+    double ray_offset;     /* < 0: derive from the scene bounding sphere (mdistant.cpp:180-190) */
+} ertb_sensor_desc;
+
+typedef struct ertb_scene_desc {
+    int32_t abi_version;   /* must be ERTB_ABI_VERSION */
+    int32_t geometry;      /* enum ertb_geometry */
+
+    /* Geometry, metres (kernel length unit, src/eradiate/units.py).
+     * plane-parallel : ground plane z = surface_z, slab top z = medium_top;
+     *                  the volume grid spans [medium_bottom, medium_top].
+     * spherical shell: ground sphere radius = surface_z (planet radius + ground
+     *                  altitude), TOA sphere radius = medium_top; the radial grid spans
+     *                  [medium_bottom, medium_top] (medium_bottom = rmin * medium_top,
+     *                  ERP/volumes/sphericalcoords.cpp:102-123). */
+    double surface_z;
+    double medium_bottom;
+    double medium_top;
+    double bsphere_center[3]; /* scene bounding sphere (sensor ray_offset, emitter distance) */
+    double bsphere_radius;
+
+    /* Medium: MI/src/media/heterogeneous.cpp:155-201 (homogeneous.cpp = 1 layer). */
+    int32_t has_medium;
+    int32_t n_layers;
+    const float *sigma_t;  /* n_layers, m^-1, float32 exactly as the reference stores it */
+    const float *albedo;   /* n_layers */
+    float sigma_t_scale;   /* heterogeneous `scale` */
+    int32_t homogeneous;   /* 1: homogeneous.cpp semantics (majorant = sigma_t, no null collisions) */
+
+    /* Phase function: flattened blendphase tree (MI/src/phase/blendphase.cpp:100-190).
+     * phase_weight[i*n_layers + l] = probability of leaf i in layer l (rows sum to 1);
+     * NULL when n_phase == 1. */
+    int32_t n_phase;
+    int32_t _pad1;
+    ertb_phase_desc phase[ERTB_MAX_PHASE];
+    const float *phase_weight;
+
+    /* Surface */
+    int32_t bsdf_type;     /* enum ertb_bsdf_type */
+    int32_t _pad2;
+    float bsdf_params[ERTB_MAX_BSDF_PARAMS];
+
+    /* Emitter: MI/src/emitters/directional.cpp:171-201 */
+    double emitter_direction[3]; /* direction light travels (to_world * (0,0,1)) */
+    float irradiance;
+    int32_t _pad3;
+
+    /* Integrator: MI/src/render/integrator.cpp:562-566 defaults */
+    int32_t integrator;    /* enum ertb_integrator_type */
+    int32_t rr_depth;      /* default 5 */
+    int64_t max_depth;     /* -1 = unbounded */
+
+    int32_t n_sensors;
+    int32_t _pad4;
+    const ertb_sensor_desc *sensors;
+} ertb_scene_desc;
+
+/* Named updatable parameters (KernelSceneParameterMap keys resolve to these;
+ * src/eradiate/scenes/atmosphere/_core.py:777-805, phase/_tabulated.py:273-281,
+ * phase/_blend.py:282-305, bsdfs/_rpv.py, illumination/_directional.py). */
+enum ertb_param {
+    ERTB_PARAM_SIGMA_T = 0,      /* float[n_layers] */
+    ERTB_PARAM_ALBEDO = 1,       /* float[n_layers] */
+    ERTB_PARAM_PHASE_WEIGHT = 2, /* float[n_phase*n_layers] (leaf probabilities) */
+    ERTB_PARAM_PHASE_VALUES = 3, /* index = leaf; float[n_nodes] */
+    ERTB_PARAM_BSDF_PARAMS = 4,  /* float[ERTB_MAX_BSDF_PARAMS] */
+    ERTB_PARAM_IRRADIANCE = 5,   /* float[1] */
+    ERTB_PARAM_PHASE_PARAMS = 6  /* index = leaf; float[4] */
+};
+
+typedef struct ertb_render_stats {
+    uint64_t n_paths;        /* samples traced by this call */
+    uint64_t trips_main;     /* iterations of hot loop #2 (volpath.cpp:170-393) */
+    uint64_t trips_nee;      /* iterations of hot loop #3 (volpath.cpp:454-551) */
+    uint64_t n_scatter;      /* real medium collisions */
+    uint64_t n_surface;      /* surface (non-null) interactions */
+    double device_ms;        /* kernel time measured with CUDA events on the launch stream */
+    int32_t n_launches;      /* kernels launched by this call */
+    int32_t _pad;
+} ertb_render_stats;
+
+typedef struct ertb_scene ertb_scene; /* opaque */
+
+/* Library / device probing.  ertb_device_count returns -1 (and sets the error)
+ * when no CUDA device is usable: there is NO CPU fallback. */
+int ertb_abi_version(void);
+const char *ertb_last_error(void);
+int ertb_device_count(void);
+
+/* mi_load_dict equivalent: validates the descriptor, uploads tables to `device`. */
+int ertb_scene_create(const ertb_scene_desc *desc, int device, ertb_scene **out);
+void ertb_scene_destroy(ertb_scene *scene);
+
+/* parameters.update(...) equivalent. */
+int ertb_scene_update(ertb_scene *scene, int param, int index, const float *data, size_t count);
+
+/* mi.render equivalent.  Renders samples [sample_offset, sample_offset+spp) of
+ * every pixel of `sensor` (sample sharding across GPUs = disjoint offsets with
+ * the same seed).  Outputs (host, n_pixels doubles each, row-major film):
+ *   sum_wl : sum of ray_weight * L   (root bitmap * spp, integrator.cpp:489)
+ *   sum_l  : sum of L                (moment.cpp:101, `nested`)
+ *   sum_l2 : sum of L^2              (moment.cpp:104, `m2_nested`)
+ * Any output pointer may be NULL. */
+int ertb_render(ertb_scene *scene, int sensor, uint64_t seed, uint64_t spp,
+                uint64_t sample_offset, double *sum_wl, double *sum_l, double *sum_l2,
+                ertb_render_stats *stats);
+
+/* Same, but accumulates into a caller-owned DEVICE buffer of 3*n_pixels doubles
+ * ([sum_wl | sum_l | sum_l2], zeroed by the caller) on `stream` (a cudaStream_t,
+ * NULL = default stream) and does not synchronise: used for the HBM-resident
+ * throughput number and for the NCCL all-reduce of the accumulators.
+ * `stats_dev` (optional) is a device buffer of 8 uint64 counters. */
+int ertb_render_device(ertb_scene *scene, int sensor, uint64_t seed, uint64_t spp,
+                       uint64_t sample_offset, void *accum_dev, void *stats_dev,
+                       void *stream);
+
+int ertb_sensor_pixel_count(const ertb_scene *scene, int sensor);
+
+/* Known-answer-test entry points: evaluate the device implementations of the
+ * plugins point-wise (one thread per query).  Host pointers.
+ *   bsdf_eval  : wi, wo local-frame unit vectors (3*n); out = f * cos(theta_o) (n)
+ *   bsdf_sample: wi (3*n), u (2*n) -> wo (3*n), weight (n)
+ *   phase_eval : leaf index, cos between wo and wi ("graphics" convention, n) -> out (n)
+ *   phase_sample: leaf index, u (2*n) -> cos_theta of wo w.r.t. propagation dir (n), weight (n), pdf (n)
+ *   sensor_ray : film sample (2*n) + aperture sample (2*n) -> origin (3*n) dir (3*n) weight (n) */
+int ertb_kat_bsdf_eval(ertb_scene *scene, size_t n, const float *wi, const float *wo, float *out);
+int ertb_kat_bsdf_sample(ertb_scene *scene, size_t n, const float *wi, const float *u,
+                         float *wo, float *weight);
+int ertb_kat_phase_eval(ertb_scene *scene, int leaf, size_t n, const float *cos_theta, float *out);
+int ertb_kat_phase_sample(ertb_scene *scene, int leaf, size_t n, const float *u,
+                          float *cos_theta, float *weight, float *pdf);
+int ertb_kat_sensor_ray(ertb_scene *scene, int sensor, size_t n, const float *film_sample,
+                        const float *aperture_sample, double *origin, double *dir, float *weight);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERADIATE_B200_H */

@@ -1,0 +1,1151 @@
+/*
+ * ertb_oracle.c -- CPU oracle: double-precision restatement of the reference's
+ * null-collision volumetric path tracer (Eradiate 1.1.0 / eradiate-mitsuba 0.4.3).
+ *
+ * TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library.  The product
+ * (eradiate_b200/) never does.
+ *
+ * Parity pinning: the plugin-level functions below are checked against every
+ * golden vector / numpy reference implementation the reference's own tests hold
+ * for this path (tests/test_oracle_golden.py lists them with file:line).  The
+ * reference itself (Mitsuba + Dr.Jit, cmake + generated config headers) cannot be
+ * built or imported in this environment, so the END-TO-END render of the oracle
+ * is pinned only through the reference's analytic system tests (BRF == rho,
+ * L = rho E / pi, RPV(k=1,g=0,rho_c=1) == Lambertian, transmittance KATs).
+ *
+ * "MI"  = /root/reference/ext/mitsuba, "ERP" = MI/src/eradiate_plugins.
+ * Nothing here is copied from the reference; each function restates the cited
+ * lines' arithmetic in plain scalar C.
+ */
+#include "ertb_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "ertb_oracle_ocean.h"
+
+#define PI 3.14159265358979323846
+#define INV_PI (1.0 / PI)
+#define INV_TWO_PI (0.5 / PI)
+#define INV_FOUR_PI (0.25 / PI)
+
+/* MI/include/mitsuba/core/math.h:18-23 (double variant) */
+#define RAY_EPS (DBL_EPSILON * 0.5 * 1500.0) /* dr::Epsilon<double> = 2^-53 */
+#define SHADOW_EPS (RAY_EPS * 10.0)
+
+static __thread char g_err[512];
+const char *ertbo_last_error(void) { return g_err; }
+static int fail(const char *msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return 1;
+}
+
+/* ------------------------------------------------------------------ vectors */
+typedef struct { double x, y, z; } v3;
+static inline v3 V(double x, double y, double z) { v3 r = { x, y, z }; return r; }
+static inline v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 vmul(v3 a, double s) { return V(a.x * s, a.y * s, a.z * s); }
+static inline v3 vfma(v3 a, double s, v3 b) { return V(a.x * s + b.x, a.y * s + b.y, a.z * s + b.z); }
+static inline double vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline double vnorm(v3 a) { return sqrt(vdot(a, a)); }
+static inline v3 vnormalize(v3 a) { return vmul(a, 1.0 / vnorm(a)); }
+static inline v3 vneg(v3 a) { return V(-a.x, -a.y, -a.z); }
+static inline double sqr(double x) { return x * x; }
+static inline double safe_sqrt(double x) { return sqrt(x > 0.0 ? x : 0.0); }
+static inline double safe_acos(double x) { return acos(x < -1.0 ? -1.0 : (x > 1.0 ? 1.0 : x)); }
+
+/* MI/include/mitsuba/core/vector.h:118-140  coordinate_system (Duff et al.) */
+static void coordinate_system(v3 n, v3 *s, v3 *t) {
+    double sign = copysign(1.0, n.z);
+    double a = -1.0 / (sign + n.z);
+    double b = n.x * n.y * a;
+    *s = V(sign * sqr(n.x) * a + 1.0, sign * b, -sign * n.x);
+    *t = V(b, sqr(n.y) * a + sign, -n.y);
+}
+typedef struct { v3 s, t, n; } frame_t;
+static frame_t make_frame(v3 n) { frame_t f; f.n = n; coordinate_system(n, &f.s, &f.t); return f; }
+static v3 to_local(const frame_t *f, v3 v) { return V(vdot(v, f->s), vdot(v, f->t), vdot(v, f->n)); }
+static v3 to_world(const frame_t *f, v3 v) {
+    return vadd(vadd(vmul(f->s, v.x), vmul(f->t, v.y)), vmul(f->n, v.z));
+}
+
+/* --------------------------------------------------------------------- RNG */
+/* MI/ext/drjit/include/drjit/random.h:108-195 : PCG32 (O'Neill).  One stream per
+ * path; the reference seeds one stream per pixel (integrator.cpp:418-421) -- same
+ * distribution, different realisation (parity is statistical, SURVEY 8b "Seeds"). */
+typedef struct { uint64_t state, inc; } pcg32;
+#define PCG_MULT 6364136223846793005ULL
+static inline uint32_t pcg_next(pcg32 *r) {
+    uint64_t old = r->state;
+    r->state = old * PCG_MULT + r->inc;
+    uint32_t xs = (uint32_t) (((old >> 18u) ^ old) >> 27u);
+    uint32_t rot = (uint32_t) (old >> 59u);
+    return (xs >> rot) | (xs << ((-rot) & 31));
+}
+static inline void pcg_seed(pcg32 *r, uint64_t initstate, uint64_t initseq) {
+    r->state = 0;
+    r->inc = (initseq << 1u) | 1u;
+    pcg_next(r);
+    r->state += initstate;
+    pcg_next(r);
+}
+/* MI/src/samplers/independent.cpp:77-86 next_1d (double variant: 53 random bits) */
+static inline double next_1d(pcg32 *r) {
+    uint64_t a = pcg_next(r) >> 5, b = pcg_next(r) >> 6;
+    return (double) (a * 67108864ULL + b) * (1.0 / 9007199254740992.0);
+}
+static inline uint64_t mix64(uint64_t z) { /* splitmix64 finaliser */
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+/* ------------------------------------------------------------------- warps */
+/* MI/include/mitsuba/core/warp.h:54-90 */
+void ertbo_square_to_uniform_disk_concentric(double u, double v, double *ox, double *oy) {
+    double x = 2.0 * u - 1.0, y = 2.0 * v - 1.0;
+    int is_zero = (x == 0.0 && y == 0.0);
+    int q13 = fabs(x) < fabs(y);
+    double r = q13 ? y : x, rp = q13 ? x : y;
+    double phi = 0.25 * PI * rp / r;
+    if (q13) phi = 0.5 * PI - phi;
+    if (is_zero) phi = 0.0;
+    *ox = r * cos(phi);
+    *oy = r * sin(phi);
+}
+/* warp.h:412-433 */
+void ertbo_square_to_cosine_hemisphere(double u, double v, double *o) {
+    double x, y;
+    ertbo_square_to_uniform_disk_concentric(u, v, &x, &y);
+    o[0] = x; o[1] = y; o[2] = safe_sqrt(1.0 - x * x - y * y);
+}
+/* warp.h:374-388 */
+void ertbo_square_to_uniform_hemisphere(double u, double v, double *o) {
+    double x, y;
+    ertbo_square_to_uniform_disk_concentric(u, v, &x, &y);
+    double z = 1.0 - (x * x + y * y);
+    double s = sqrt(z + 1.0);
+    o[0] = x * s; o[1] = y * s; o[2] = z;
+}
+
+/* ----------------------------------------------------- 1D distributions */
+/* MI/include/mitsuba/core/distr_1d.h: ContinuousDistribution (regular, :300-620)
+ * and IrregularContinuousDistribution (:628-1000).  Storage is float (the
+ * reference stores ScalarFloat pdf/cdf even though the CDF is accumulated in
+ * double, :548-600); in the double variant ScalarFloat = double, so the oracle
+ * keeps double storage and parity tests state a tolerance. */
+typedef struct {
+    int n;            /* nodes */
+    int irregular;
+    double *nodes;    /* irregular only */
+    double *pdf, *cdf;
+    double integral, normalization, interval_size, inv_interval_size, x0, x1;
+    int valid0, valid1;
+} distr_t;
+
+static void distr_free(distr_t *d) { free(d->nodes); free(d->pdf); free(d->cdf); memset(d, 0, sizeof *d); }
+
+static int distr_init(distr_t *d, const float *nodes, const float *pdf, int n) {
+    memset(d, 0, sizeof *d);
+    if (n < 2) return fail("distribution needs at least two entries");
+    d->n = n;
+    d->irregular = nodes != NULL;
+    d->pdf = malloc(sizeof(double) * n);
+    d->cdf = malloc(sizeof(double) * n);
+    if (nodes) d->nodes = malloc(sizeof(double) * n);
+    for (int i = 0; i < n; ++i) {
+        d->pdf[i] = pdf[i];
+        if (nodes) d->nodes[i] = nodes[i];
+    }
+    d->x0 = nodes ? nodes[0] : -1.0;
+    d->x1 = nodes ? nodes[n - 1] : 1.0;
+    d->interval_size = (d->x1 - d->x0) / (n - 1);
+    d->inv_interval_size = 1.0 / d->interval_size;
+    d->valid0 = d->valid1 = -1;
+    double integral = 0.0;
+    for (int i = 0; i < n - 1; ++i) {
+        double w = nodes ? ((double) nodes[i + 1] - (double) nodes[i]) : d->interval_size;
+        double y0 = pdf[i], y1 = pdf[i + 1];
+        if (nodes && !(w > 0.0)) return fail("node positions must be strictly increasing");
+        if (y0 < 0.0 || y1 < 0.0) return fail("entries must be non-negative");
+        double value = 0.5 * w * (y0 + y1);
+        integral += value;
+        d->cdf[i] = integral;
+        if (value > 0.0) {
+            if (d->valid0 < 0) d->valid0 = i;
+            d->valid1 = i;
+        }
+    }
+    if (d->valid0 < 0) return fail("no probability mass found");
+    d->integral = d->cdf[d->valid1];
+    d->normalization = 1.0 / d->integral;
+    return 0;
+}
+
+/* MI/ext/drjit/include/drjit/util.h:136-187 binary_search (scalar branch) */
+static int bsearch_pred_cdf(const distr_t *d, int start, int end, double sample) {
+    int iterations = 0;
+    if (start < end) { /* log2i(end-start)+1 */
+        unsigned v = (unsigned) (end - start);
+        int l = 0;
+        while (v >>= 1) ++l;
+        iterations = l + 1;
+    }
+    for (int i = 0; i < iterations; ++i) {
+        int middle = (start + end) >> 1;
+        if (d->cdf[middle] < sample) start = (middle + 1 < end) ? middle + 1 : end;
+        else end = middle;
+    }
+    return start;
+}
+static int bsearch_pred_nodes(const distr_t *d, double x) {
+    int start = 0, end = d->n, iterations = 0;
+    unsigned v = (unsigned) (end - start);
+    int l = 0;
+    while (v >>= 1) ++l;
+    iterations = l + 1;
+    for (int i = 0; i < iterations; ++i) {
+        int middle = (start + end) >> 1;
+        int cond = (middle < d->n) ? (d->nodes[middle] < x) : 0;
+        if (cond) start = (middle + 1 < end) ? middle + 1 : end;
+        else end = middle;
+    }
+    return start;
+}
+
+/* distr_1d.h:429-459 (regular) / :790-822 (irregular): sample */
+static double distr_sample(const distr_t *d, double sample) {
+    sample *= d->integral;
+    int index = bsearch_pred_cdf(d, d->valid0, d->valid1, sample);
+    double y0 = d->pdf[index], y1 = d->pdf[index + 1];
+    double c0 = index > 0 ? d->cdf[index - 1] : 0.0;
+    double w = d->irregular ? d->nodes[index + 1] - d->nodes[index] : d->interval_size;
+    sample = (sample - c0) / w;
+    double t_linear = (y0 - safe_sqrt(y0 * y0 + 2.0 * sample * (y1 - y0))) / (y0 - y1);
+    double t_const = sample / y0;
+    double t = (y0 == y1) ? t_const : t_linear;
+    if (d->irregular) return t * w + d->nodes[index];
+    return ((double) index + t) * d->interval_size + d->x0;
+}
+/* distr_1d.h:370-392 (regular) / :712-735 (irregular): eval_pdf (unnormalised) */
+static double distr_eval_pdf(const distr_t *d, double x) {
+    if (!(x >= d->x0 && x <= d->x1)) return 0.0;
+    if (d->irregular) {
+        int index = bsearch_pred_nodes(d, x);
+        if (index > d->n - 1) index = d->n - 1;
+        if (index < 1) index = 1;
+        index -= 1;
+        double xa = d->nodes[index], xb = d->nodes[index + 1];
+        double t = (x - xa) / (xb - xa);
+        return t * (d->pdf[index + 1] - d->pdf[index]) + d->pdf[index];
+    }
+    double xs = (x - d->x0) * d->inv_interval_size;
+    int index = (int) xs;
+    if (index < 0) index = 0;
+    if (index > d->n - 2) index = d->n - 2;
+    double w1 = xs - index, w0 = 1.0 - w1;
+    return w0 * d->pdf[index] + w1 * d->pdf[index + 1];
+}
+
+int ertbo_distr_regular(const float *pdf, int n, size_t nq, const double *u, double *xs,
+                        const double *xq, double *pe, double *integral) {
+    distr_t d;
+    if (distr_init(&d, NULL, pdf, n)) return 1;
+    for (size_t i = 0; i < nq; ++i) {
+        if (u && xs) xs[i] = distr_sample(&d, u[i]);
+        if (xq && pe) pe[i] = distr_eval_pdf(&d, xq[i]) * d.normalization;
+    }
+    if (integral) *integral = d.integral;
+    distr_free(&d);
+    return 0;
+}
+int ertbo_distr_irregular(const float *nodes, const float *pdf, int n, size_t nq, const double *u,
+                          double *xs, const double *xq, double *pe, double *integral) {
+    distr_t d;
+    if (distr_init(&d, nodes, pdf, n)) return 1;
+    for (size_t i = 0; i < nq; ++i) {
+        if (u && xs) xs[i] = distr_sample(&d, u[i]);
+        if (xq && pe) pe[i] = distr_eval_pdf(&d, xq[i]) * d.normalization;
+    }
+    if (integral) *integral = d.integral;
+    distr_free(&d);
+    return 0;
+}
+
+/* ------------------------------------------------------------ scene state */
+typedef struct {
+    const ertb_scene_desc *desc;
+    int spherical;
+    double majorant;            /* heterogeneous.cpp:163 m_scale * max(sigma_t) */
+    distr_t distr[ERTB_MAX_PHASE];
+    int has_distr[ERTB_MAX_PHASE];
+    v3 emitter_d;               /* normalised propagation direction */
+    ocean_state_t ocean;        /* ocean_legacy precomputed tables */
+} scene_t;
+
+static void scene_free(scene_t *S) {
+    for (int i = 0; i < ERTB_MAX_PHASE; ++i)
+        if (S->has_distr[i]) distr_free(&S->distr[i]);
+    ocean_free(&S->ocean);
+}
+
+static int scene_init(scene_t *S, const ertb_scene_desc *d) {
+    memset(S, 0, sizeof *S);
+    if (d->abi_version != ERTB_ABI_VERSION) return fail("ABI version mismatch");
+    S->desc = d;
+    S->spherical = d->geometry == ERTB_GEOM_SPHERICAL_SHELL;
+    if (d->has_medium) {
+        if (d->n_layers < 1 || !d->sigma_t || !d->albedo) return fail("medium arrays missing");
+        float m = d->sigma_t[0];
+        for (int i = 1; i < d->n_layers; ++i) if (d->sigma_t[i] > m) m = d->sigma_t[i];
+        /* scalar_mono_double: Float = double, grid data float32 */
+        S->majorant = (double) d->sigma_t_scale * (double) m;
+        if (d->n_phase < 1 || d->n_phase > ERTB_MAX_PHASE) return fail("invalid n_phase");
+        for (int i = 0; i < d->n_phase; ++i) {
+            const ertb_phase_desc *p = &d->phase[i];
+            if (p->type == ERTB_PHASE_TABULATED || p->type == ERTB_PHASE_TABULATED_IRREGULAR) {
+                const float *nodes = p->type == ERTB_PHASE_TABULATED_IRREGULAR ? p->nodes : NULL;
+                if (p->type == ERTB_PHASE_TABULATED_IRREGULAR && !nodes) return fail("nodes missing");
+                if (distr_init(&S->distr[i], nodes, p->values, p->n_nodes)) return 1;
+                S->has_distr[i] = 1;
+            }
+        }
+    }
+    S->emitter_d = vnormalize(V(d->emitter_direction[0], d->emitter_direction[1], d->emitter_direction[2]));
+    if (d->bsdf_type == ERTB_BSDF_OCEAN_LEGACY)
+        if (ocean_init(&S->ocean, d->bsdf_params)) return fail("ocean_legacy init failed");
+    return 0;
+}
+
+/* ------------------------------------------------------------- geometry */
+typedef struct { v3 o, d; double maxt; } ray_t;
+enum { SHAPE_GROUND = 0, SHAPE_TOA = 1 };
+typedef struct { double t; v3 p, n; int shape; } si_t; /* t = INFINITY when invalid */
+
+static inline v3 ray_at(const ray_t *r, double t) { return vfma(r->d, t, r->o); }
+
+/* MI/src/shapes/sphere.cpp:519-580: plane-shifted quadratic in double */
+static double sphere_intersect(const ray_t *ray, double radius) {
+    v3 l = ray->o; /* center = 0 */
+    v3 d = ray->d;
+    double plane_t = vdot(vneg(l), d) / vnorm(d);
+    v3 o = ray_at(ray, plane_t);
+    double A = vdot(d, d), B = 2.0 * vdot(o, d), C = vdot(o, o) - radius * radius;
+    /* math::solve_quadratic (MI/include/mitsuba/core/math.h) */
+    double disc = B * B - 4.0 * A * C;
+    if (disc < 0.0) return INFINITY;
+    double temp = -0.5 * (B + copysign(sqrt(disc), B));
+    double x0 = temp / A, x1 = C / temp;
+    if (temp == 0.0) { x0 = x1 = 0.0; }
+    double near_t = fmin(x0, x1) + plane_t, far_t = fmax(x0, x1) + plane_t;
+    if (!(near_t <= ray->maxt && far_t >= 0.0)) return INFINITY;
+    if (near_t < 0.0 && far_t > ray->maxt) return INFINITY;
+    return near_t < 0.0 ? far_t : near_t;
+}
+
+/* Scene::ray_intersect over the two stencil surfaces Eradiate emits
+ * (src/eradiate/scenes/geometry.py:191-266; ERP/shapes/arectangle.cpp; the slab
+ * `cube` top face; horizontal extent treated as unbounded: default width 1e6 km) */
+static si_t scene_intersect(const scene_t *S, const ray_t *ray) {
+    const ertb_scene_desc *d = S->desc;
+    si_t best; best.t = INFINITY; best.shape = -1; best.p = best.n = V(0, 0, 0);
+    double tg = INFINITY, tt = INFINITY;
+    if (S->spherical) {
+        tg = sphere_intersect(ray, d->surface_z);
+        if (d->has_medium) tt = sphere_intersect(ray, d->medium_top);
+    } else {
+        if (ray->d.z != 0.0) {
+            double t = (d->surface_z - ray->o.z) / ray->d.z;
+            if (t > 0.0 && t <= ray->maxt) tg = t;
+            if (d->has_medium) {
+                t = (d->medium_top - ray->o.z) / ray->d.z;
+                if (t > 0.0 && t <= ray->maxt) tt = t;
+            }
+        }
+    }
+    if (tg < tt) { best.t = tg; best.shape = SHAPE_GROUND; }
+    else if (tt < INFINITY) { best.t = tt; best.shape = SHAPE_TOA; }
+    if (best.t < INFINITY) {
+        best.p = ray_at(ray, best.t);
+        best.n = S->spherical ? vnormalize(best.p) : V(0, 0, 1);
+    }
+    return best;
+}
+
+/* MI/include/mitsuba/render/interaction.h:140-169 */
+static v3 offset_p(v3 p, v3 n, v3 d) {
+    double m = fmax(fabs(p.x), fmax(fabs(p.y), fabs(p.z)));
+    double mag = (1.0 + m) * RAY_EPS;
+    double dn = vdot(n, d);
+    if (dn < 0.0) mag = -mag; /* mulsign */
+    return vfma(n, mag, p);
+}
+static ray_t spawn_ray(v3 p, v3 n, v3 d) {
+    ray_t r; r.o = offset_p(p, n, d); r.d = d; r.maxt = DBL_MAX; return r;
+}
+static ray_t spawn_ray_to(v3 p, v3 n, v3 t) {
+    ray_t r;
+    r.o = offset_p(p, n, vsub(t, p));
+    v3 d = vsub(t, r.o);
+    double dist = vnorm(d);
+    r.d = vmul(d, 1.0 / dist);
+    r.maxt = dist * (1.0 - SHADOW_EPS);
+    return r;
+}
+
+/* --------------------------------------------------------------- medium */
+/* Layer index at a world-space point: GridVolume nearest lookup
+ * (MI/src/volumes/grid.cpp:548-562, MI/ext/drjit/include/drjit/texture.h:493-498,
+ * clamp wrap mode) behind either the slab to_world (plane-parallel,
+ * src/eradiate/scenes/geometry.py:197-210) or the radial remap of
+ * ERP/volumes/sphericalcoords.cpp:102-123.  Returns -1 for fill regions. */
+static int layer_index(const scene_t *S, v3 p) {
+    const ertb_scene_desc *d = S->desc;
+    double u;
+    if (S->spherical) {
+        /* to_local scales the TOA sphere to the unit sphere */
+        double r = vnorm(p) / d->medium_top;
+        double rmin = d->medium_bottom / d->medium_top;
+        if (r < rmin || r > 1.0) return -1; /* fillmin / fillmax = 0 */
+        u = (r - rmin) / (1.0 - rmin);
+    } else {
+        u = (p.z - d->medium_bottom) / (d->medium_top - d->medium_bottom);
+    }
+    int idx = (int) floor(u * d->n_layers);
+    if (idx < 0) idx = 0;
+    if (idx > d->n_layers - 1) idx = d->n_layers - 1;
+    return idx;
+}
+
+/* BoundingBox::ray_intersect of the sigma_t volume's bbox
+ * (heterogeneous.cpp:199; sphericalcoords.cpp update_bbox_sphere) */
+static int medium_aabb(const scene_t *S, const ray_t *ray, double *mint, double *maxt) {
+    const ertb_scene_desc *d = S->desc;
+    if (d->homogeneous) { *mint = 0.0; *maxt = INFINITY; return 1; } /* homogeneous.cpp:176-181 */
+    double lo[3], hi[3];
+    if (S->spherical) {
+        for (int i = 0; i < 3; ++i) { lo[i] = -d->medium_top; hi[i] = d->medium_top; }
+    } else {
+        lo[0] = lo[1] = -INFINITY; hi[0] = hi[1] = INFINITY;
+        lo[2] = d->medium_bottom; hi[2] = d->medium_top;
+    }
+    double o[3] = { ray->o.x, ray->o.y, ray->o.z }, dd[3] = { ray->d.x, ray->d.y, ray->d.z };
+    double tn = -INFINITY, tf = INFINITY;
+    int active = 1;
+    for (int i = 0; i < 3; ++i) {
+        if (!isfinite(lo[i])) continue;
+        if (dd[i] == 0.0) {
+            if (!(o[i] > lo[i] && o[i] < hi[i])) active = 0;
+            continue;
+        }
+        double t1 = (lo[i] - o[i]) / dd[i], t2 = (hi[i] - o[i]) / dd[i];
+        double a = fmin(t1, t2), b = fmax(t1, t2);
+        if (a > tn) tn = a;
+        if (b < tf) tf = b;
+    }
+    active = active && (tf >= tn);
+    *mint = tn; *maxt = tf;
+    return active;
+}
+
+typedef struct {
+    double t, mint, sigma_s, sigma_n, sigma_t, combined;
+    v3 p, wi;
+    int layer;
+} mei_t;
+
+/* MI/src/render/medium.cpp:42-82 + heterogeneous.cpp:185-196 / homogeneous.cpp:157-170 */
+static mei_t sample_interaction(const scene_t *S, const ray_t *ray, double sample) {
+    const ertb_scene_desc *d = S->desc;
+    mei_t mei; memset(&mei, 0, sizeof mei);
+    mei.wi = vneg(ray->d);
+    double mint, maxt;
+    int active = medium_aabb(S, ray, &mint, &maxt);
+    active = active && (isfinite(mint) || isfinite(maxt));
+    if (!active) { mint = 0.0; maxt = INFINITY; }
+    mint = fmax(0.0, mint);
+    maxt = fmin(ray->maxt, maxt);
+    double m = S->majorant;
+    double sampled_t = mint + (-log(1.0 - sample) / m);
+    int valid = active && (sampled_t <= maxt);
+    mei.t = valid ? sampled_t : INFINITY;
+    mei.p = ray_at(ray, sampled_t);
+    mei.mint = mint;
+    mei.combined = m;
+    mei.layer = -1;
+    if (valid) {
+        int l = layer_index(S, mei.p);
+        mei.layer = l;
+        double st = l >= 0 ? (double) d->sigma_t_scale * (double) d->sigma_t[l] : 0.0;
+        double al = l >= 0 ? (double) d->albedo[l] : 0.0;
+        mei.sigma_t = st;
+        mei.sigma_s = st * al;
+        mei.sigma_n = m - st;
+    }
+    return mei;
+}
+
+/* ---------------------------------------------------------------- phase */
+static double eval_rayleigh(double c, double rho) { /* rayleigh.cpp:61-67 */
+    double r1 = (1.0 - rho) / (1.0 + rho / 2.0), r2 = (1.0 + rho) / (1.0 - rho);
+    return (3.0 / 16.0) * INV_PI * r1 * (r2 + c * c);
+}
+static double eval_rayleigh_pdf(double c) { return (3.0 / 16.0) * INV_PI * (1.0 + c * c); }
+static double eval_hg(double g, double c) { /* hg.cpp:64-68 */
+    double temp = 1.0 + g * g + 2.0 * g * c;
+    return INV_FOUR_PI * (1.0 - g * g) / (temp * sqrt(temp));
+}
+
+/* eval_pdf of one leaf; `c` = dot(wo, wi) with wi = -ray.d (graphics convention) */
+static void leaf_eval_pdf(const scene_t *S, int leaf, double c, double *val, double *pdf) {
+    const ertb_phase_desc *p = &S->desc->phase[leaf];
+    switch (p->type) {
+        case ERTB_PHASE_ISOTROPIC: /* isotropic.cpp:39-60 */
+            *val = *pdf = INV_FOUR_PI; break;
+        case ERTB_PHASE_RAYLEIGH:  /* rayleigh.cpp:97-107 */
+            *val = eval_rayleigh(c, p->params[0]); *pdf = eval_rayleigh_pdf(c); break;
+        case ERTB_PHASE_HG:        /* hg.cpp:92-99 */
+            *val = *pdf = eval_hg(p->params[0], c); break;
+        default: {                 /* tabphase.cpp:107-118: data in physics convention */
+            double v = distr_eval_pdf(&S->distr[leaf], -c) * S->distr[leaf].normalization * INV_TWO_PI;
+            *val = *pdf = v; break;
+        }
+    }
+}
+
+/* sample of one leaf: returns local direction in the frame of wi (z = wi). */
+static void leaf_sample(const scene_t *S, int leaf, double u1, double u2, v3 *wo_local,
+                        double *weight, double *pdf) {
+    const ertb_phase_desc *p = &S->desc->phase[leaf];
+    double sphi = sin(2.0 * PI * u2), cphi = cos(2.0 * PI * u2);
+    switch (p->type) {
+        case ERTB_PHASE_ISOTROPIC: { /* warp::square_to_uniform_sphere */
+            double z = 1.0 - 2.0 * u2;
+            double r = safe_sqrt(1.0 - z * z);
+            double s2 = sin(2.0 * PI * u1), c2 = cos(2.0 * PI * u1);
+            *wo_local = V(r * c2, r * s2, z);
+            *weight = 1.0; *pdf = INV_FOUR_PI;
+            break;
+        }
+        case ERTB_PHASE_RAYLEIGH: { /* rayleigh.cpp:75-95 */
+            double z = 2.0 * (2.0 * u1 - 1.0);
+            double tmp = sqrt(z * z + 1.0);
+            double A = cbrt(z + tmp), B = cbrt(z - tmp);
+            double ct = A + B, st = safe_sqrt(1.0 - ct * ct);
+            *wo_local = V(st * cphi, st * sphi, ct);
+            *pdf = eval_rayleigh_pdf(-ct);
+            *weight = eval_rayleigh(-ct, p->params[0]) / *pdf;
+            break;
+        }
+        case ERTB_PHASE_HG: { /* hg.cpp:70-90 */
+            double g = p->params[0];
+            double sq = (1.0 - g * g) / (1.0 - g + 2.0 * g * u1);
+            double ct = (1.0 + g * g - sq * sq) / (2.0 * g);
+            if (fabs(g) < DBL_EPSILON * 0.5) ct = 1.0 - 2.0 * u1;
+            double st = safe_sqrt(1.0 - ct * ct);
+            *wo_local = V(st * cphi, st * sphi, -ct);
+            *weight = 1.0; *pdf = eval_hg(g, -ct);
+            break;
+        }
+        default: { /* tabphase.cpp:77-105: wo = -to_world(physics-convention dir) */
+            const distr_t *D = &S->distr[leaf];
+            double ctp = distr_sample(D, u1), stp = safe_sqrt(1.0 - ctp * ctp);
+            *wo_local = V(-stp * cphi, -stp * sphi, -ctp);
+            *pdf = distr_eval_pdf(D, ctp) * D->normalization * INV_TWO_PI;
+            *weight = 1.0;
+            break;
+        }
+    }
+}
+
+static double leaf_prob(const scene_t *S, int leaf, int layer) {
+    const ertb_scene_desc *d = S->desc;
+    if (d->n_phase == 1 || !d->phase_weight) return leaf == 0 ? 1.0 : 0.0;
+    if (layer < 0) return leaf == 0 ? 1.0 : 0.0;
+    return (double) d->phase_weight[(size_t) leaf * d->n_layers + layer];
+}
+
+/* blendphase.cpp:172-190 (nested lerp == sum of leaf probabilities) */
+static void phase_eval_pdf(const scene_t *S, int layer, v3 wi, v3 wo, double *val, double *pdf) {
+    double c = vdot(wo, wi), v = 0.0, p = 0.0;
+    for (int i = 0; i < S->desc->n_phase; ++i) {
+        double w = leaf_prob(S, i, layer);
+        if (w == 0.0) continue;
+        double vi, pi_;
+        leaf_eval_pdf(S, i, c, &vi, &pi_);
+        v += w * vi; p += w * pi_;
+    }
+    *val = v; *pdf = p;
+}
+
+/* blendphase.cpp:100-141: pick a component with sample1 (rescaled and forwarded
+ * as the nested sample1, unused by every leaf), return the component's own
+ * weight and pdf (no mixture MIS). */
+static void phase_sample(const scene_t *S, int layer, v3 wi, double s1, double u1, double u2,
+                         v3 *wo, double *weight, double *pdf) {
+    int n = S->desc->n_phase, leaf = 0;
+    if (n > 1) {
+        double acc = 0.0;
+        leaf = n - 1;
+        for (int i = 0; i < n; ++i) {
+            acc += leaf_prob(S, i, layer);
+            if (s1 < acc) { leaf = i; break; }
+        }
+    }
+    v3 wl;
+    leaf_sample(S, leaf, u1, u2, &wl, weight, pdf);
+    frame_t f = make_frame(wi); /* medium.cpp:51 sh_frame = Frame3f(wi) */
+    *wo = to_world(&f, wl);
+}
+
+/* ----------------------------------------------------------------- BSDFs */
+static double cos_theta(v3 v) { return v.z; }
+static double sin_theta(v3 v) { return safe_sqrt(1.0 - v.z * v.z); }
+static double tan_theta(v3 v) { return safe_sqrt(1.0 - v.z * v.z) / v.z; }
+/* Frame3f::sincos_phi (MI/include/mitsuba/core/frame.h) */
+static void sincos_phi(v3 v, double *s, double *c) {
+    double st2 = 1.0 - v.z * v.z;
+    if (st2 <= 0.0) { *s = 0.0; *c = 1.0; return; }
+    double inv = 1.0 / sqrt(st2);
+    *s = v.y * inv; *c = v.x * inv;
+    if (*s > 1.0) *s = 1.0; if (*s < -1.0) *s = -1.0;
+    if (*c > 1.0) *c = 1.0; if (*c < -1.0) *c = -1.0;
+}
+
+/* ERP/bsdfs/rpv.cpp:128-167 */
+static double eval_rpv(const float *P, v3 wi, v3 wo) {
+    double rho_0 = P[0], k = P[1], g = P[2], rho_c = P[3];
+    double spi, cpi, spo, cpo;
+    sincos_phi(wi, &spi, &cpi);
+    sincos_phi(wo, &spo, &cpo);
+    double cdphi = cpi * cpo + spi * spo;
+    double sti = sin_theta(wi), cti = cos_theta(wi), tti = tan_theta(wi);
+    double sto = sin_theta(wo), cto = cos_theta(wo), tto = tan_theta(wo);
+    double cT = cti * cto + sti * sto * cdphi;
+    double F = (1.0 - g * g) / pow(1.0 + g * g + 2.0 * g * cT, 1.5);
+    double G = safe_sqrt(tti * tti + tto * tto - 2.0 * tti * tto * cdphi);
+    double H = 1.0 + (1.0 - rho_c) / (1.0 + G);
+    double M = pow(cti * cto * (cti + cto), k - 1.0);
+    return rho_0 * M * F * H * INV_PI;
+}
+
+/* ERP/bsdfs/rtls.cpp:116-243 */
+static double eval_rtls(const float *P, v3 wi, v3 wo) {
+    double f_iso = P[0], f_vol = P[1], f_geo = P[2], h = P[3], r = P[4], b = P[5];
+    double spi, cpi, spo, cpo;
+    sincos_phi(wi, &spi, &cpi);
+    sincos_phi(wo, &spo, &cpo);
+    double sti = sin_theta(wi), cti = cos_theta(wi), tti = tan_theta(wi);
+    double sto = sin_theta(wo), cto = cos_theta(wo), tto = tan_theta(wo);
+    double cdphi = cpi * cpo + spi * spo, sdphi = spi * cpo - cpi * spo;
+    double cpsi = cti * cto + sti * sto * cdphi;
+    double spsi = sqrt(1.0 - cpsi * cpsi), psi = acos(cpsi);
+    double K_vol = ((PI / 2.0 - psi) * cpsi + spsi) / (cti + cto) - PI / 4.0;
+    double ci = cti, co = cto, ti = tti, to = tto, cp = cpsi;
+    if (fabs(r - b) > FLT_EPSILON * 0.5) { /* dr::Epsilon<ScalarFloat>; rtls.cpp:197-214 */
+        ti = b / r * tti; to = b / r * tto;
+        double thi = atan(ti), tho = atan(to);
+        ci = cos(thi); co = cos(tho);
+        cp = ci * co + sin(thi) * sin(tho) * cdphi;
+    }
+    double sec_i = 1.0 / ci, sec_o = 1.0 / co, sec_sum = sec_i + sec_o;
+    double D = sqrt(ti * ti + to * to - 2.0 * ti * to * cdphi);
+    double tsp = ti * to * sdphi;
+    double cos_t = (h / b) * sqrt(D * D + tsp * tsp) / sec_sum;
+    cos_t = fmax(fmin(cos_t, 1.0), -1.0);
+    double t = acos(cos_t), sin_t = sin(t);
+    double O = INV_PI * (t - sin_t * cos_t) * sec_sum;
+    double K_geo = O - sec_sum + 0.5 * (1.0 + cp) * sec_i * sec_o;
+    return (f_iso + f_vol * K_vol + f_geo * K_geo) * INV_PI;
+}
+
+/* ERP/bsdfs/hapke.cpp:120-332 */
+static double hapke_H(double w, double x) {
+    double gamma = sqrt(1.0 - w), ro = (1.0 - gamma) / (1.0 + gamma);
+    return 1.0 / (1.0 - w * x * (ro + (1.0 - 2.0 * ro * x) * 0.5 * log((1.0 + x) / x)));
+}
+static double hapke_E1(double tt, double x) { return exp(-2.0 * INV_PI / tt / tan(x)); }
+static double hapke_E2(double tt, double x) { return exp(-INV_PI / (tt * tt) / sqr(tan(x))); }
+static double hapke_mu(double tt, double e, double i, double cos_x, double sin_x, double phi,
+                       double opt_cos_phi, double sign) {
+    double chi = 1.0 / sqrt(1.0 + PI * tt * tt);
+    double E1e = hapke_E1(tt, e), E1i = hapke_E1(tt, i), E2e = hapke_E2(tt, e), E2i = hapke_E2(tt, i);
+    double s2 = sin(phi * 0.5);
+    return chi * (cos_x + sin_x * tt * (opt_cos_phi * E2e + sign * s2 * s2 * E2i) /
+                              (2.0 - E1e - phi * INV_PI * E1i));
+}
+static double eval_hapke(const float *P, v3 wi, v3 wo) {
+    double w = P[0], b = P[1], c = P[2], theta = P[3] * PI / 180.0, B0 = P[4], h = P[5];
+    double tt = tan(theta);
+    double spe, cpe, spi, cpi;
+    sincos_phi(wo, &spe, &cpe);
+    sincos_phi(wi, &spi, &cpi);
+    double cos_phi = cpe * cpi + spe * spi;
+    double sin_e = sin_theta(wo), mu = cos_theta(wo), tan_e = tan_theta(wo);
+    double sin_i = sin_theta(wi), mu_0 = cos_theta(wi), tan_i = tan_theta(wi);
+    double i = atan(tan_i), e = atan(tan_e);
+    double fr_phi = safe_acos(cos_phi);
+    double phi = fabs(fr_phi > PI ? 2.0 * PI - fr_phi : fr_phi);
+    /* eval_mu_0eG / eval_mu_eG (:207-235) */
+    double a_ = e <= i ? i : e, b_ = e <= i ? e : i;
+    double mu_0eG = hapke_mu(tt, a_, b_, cos(i), sin(i), phi, e <= i ? 1.0 : cos_phi, e <= i ? -1.0 : 1.0);
+    double mu_eG = hapke_mu(tt, a_, b_, cos(e), sin(e), phi, e <= i ? cos_phi : 1.0, e <= i ? 1.0 : -1.0);
+    double mu_ratio = mu_0eG / (mu_0eG + mu_eG) / mu_0;
+    double cos_g = mu_0 * mu + sin_i * sin_e * cos_phi;
+    double g = safe_acos(cos_g);
+    double num = 1.0 - b * b;
+    double Pf = (1.0 - c) * num / pow(1.0 + 2.0 * b * cos_g + b * b, 1.5) +
+                c * num / pow(1.0 - 2.0 * b * cos_g + b * b, 1.5);
+    double B = B0 / (1.0 + 1.0 / h * tan(g / 2.0));
+    double M = hapke_H(w, mu_0eG) * hapke_H(w, mu_eG) - 1.0;
+    /* eval_f (:134-138): clip uses dr::Epsilon<Float> of the variant */
+    double half = phi / 2.0, lim = PI / 2.0 - DBL_EPSILON * 0.5;
+    if (half < 0.0) half = 0.0; if (half > lim) half = lim;
+    double f = exp(-2.0 * tan(half));
+    double chi = 1.0 / sqrt(1.0 + PI * tt * tt);
+    double E1e = hapke_E1(tt, e), E1i = hapke_E1(tt, i), E2e = hapke_E2(tt, e), E2i = hapke_E2(tt, i);
+    double eta_0e = chi * (mu_0 + sin_i * tt * E2i / (2.0 - E1i));
+    double eta_e = chi * (mu + sin_e * tt * E2e / (2.0 - E1e));
+    double opt_mu = e < i ? mu : mu_0, opt_eta = e < i ? eta_e : eta_0e;
+    double Sf = (mu_eG * mu_0 * chi) / (eta_e * eta_0e * (1.0 - f + f * chi * opt_mu / opt_eta));
+    return w * 0.25 * INV_PI * mu_ratio * (Pf * (1.0 + B) + M) * Sf;
+}
+
+/* BSDF::eval (value * cos_theta_o), local frame */
+static double bsdf_eval(const scene_t *S, v3 wi, v3 wo) {
+    const ertb_scene_desc *d = S->desc;
+    double cti = wi.z, cto = wo.z;
+    if (!(cti > 0.0 && cto > 0.0)) return 0.0;
+    const float *P = d->bsdf_params;
+    switch (d->bsdf_type) {
+        case ERTB_BSDF_DIFFUSE: return (double) P[0] * INV_PI * cto;  /* diffuse.cpp:127-143 */
+        case ERTB_BSDF_RPV: return eval_rpv(P, wi, wo) * fabs(cto);   /* rpv.cpp:169-181 */
+        case ERTB_BSDF_RTLS: return eval_rtls(P, wi, wo) * fabs(cto); /* rtls.cpp:245-257 */
+        case ERTB_BSDF_HAPKE: return eval_hapke(P, wi, wo) * fabs(cto);
+        case ERTB_BSDF_OCEAN_LEGACY: return ocean_eval(&S->ocean, wi.x, wi.y, wi.z, wo.x, wo.y, wo.z);
+        default: return 0.0;
+    }
+}
+/* BSDF::sample -> wo (local), weight = eval / pdf */
+static double bsdf_sample(const scene_t *S, v3 wi, double s1, double u1, double u2, v3 *wo) {
+    const ertb_scene_desc *d = S->desc;
+    *wo = V(0, 0, 1);
+    if (!(wi.z > 0.0)) return 0.0;
+    if (d->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+        double o[3], w = ocean_sample(&S->ocean, wi.x, wi.y, wi.z, s1, u1, u2, o);
+        *wo = V(o[0], o[1], o[2]);
+        return w;
+    }
+    double o[3];
+    ertbo_square_to_cosine_hemisphere(u1, u2, o); /* rpv.cpp:113 etc. */
+    *wo = V(o[0], o[1], o[2]);
+    double pdf = INV_PI * o[2];
+    if (!(pdf > 0.0)) return 0.0;
+    const float *P = d->bsdf_params;
+    switch (d->bsdf_type) {
+        case ERTB_BSDF_DIFFUSE: return (double) P[0];               /* diffuse.cpp:121-123 */
+        case ERTB_BSDF_RPV: return eval_rpv(P, wi, *wo) * o[2] / pdf; /* rpv.cpp:119-122 */
+        case ERTB_BSDF_RTLS: return eval_rtls(P, wi, *wo) * o[2] / pdf;
+        case ERTB_BSDF_HAPKE: return eval_hapke(P, wi, *wo) * o[2] / pdf;
+        default: return 0.0;
+    }
+}
+
+/* -------------------------------------------------------------- sensors */
+static void mat_apply_vec(const double *m, v3 v, v3 *o) { /* row-major 4x4, direction */
+    *o = V(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z,
+           m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+static void mat_apply_pt(const double *m, v3 v, v3 *o) {
+    *o = V(m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3], m[4] * v.x + m[5] * v.y + m[6] * v.z + m[7],
+           m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11]);
+}
+
+static double sensor_ray_offset(const scene_t *S, const ertb_sensor_desc *sd) {
+    /* mdistant.cpp:180-190 / hdistant.cpp:219-229 / distantflux.cpp:136-146 */
+    if (sd->ray_offset >= 0.0) return sd->ray_offset;
+    double rad = fmax(RAY_EPS, S->desc->bsphere_radius * (1.0 + RAY_EPS));
+    return sd->target_type == ERTB_TARGET_NONE ? rad : 2.0 * rad;
+}
+
+/* sample_ray of the three distant sensors. film = adjusted film position in [0,1)^2 */
+static double sensor_sample_ray(const scene_t *S, const ertb_sensor_desc *sd, double fx, double fy,
+                                double ax, double ay, ray_t *ray) {
+    v3 d, frame_s = V(1, 0, 0), frame_t = V(0, 1, 0);
+    double weight = 1.0;
+    if (sd->type == ERTB_SENSOR_MDISTANT) { /* mdistant.cpp:192-242 */
+        int idx = (int) (fx * sd->n_directions);
+        if (idx > sd->n_directions - 1) idx = sd->n_directions - 1;
+        d = vnormalize(V(sd->directions[3 * idx], sd->directions[3 * idx + 1], sd->directions[3 * idx + 2]));
+        /* look_at(0, direction, up) : columns (left, new_up, dir) */
+        v3 up, tmp;
+        coordinate_system(d, &up, &tmp);
+        v3 left = vnormalize(V(up.y * d.z - up.z * d.y, up.z * d.x - up.x * d.z, up.x * d.y - up.y * d.x));
+        frame_s = left;
+        frame_t = V(d.y * left.z - d.z * left.y, d.z * left.x - d.x * left.z, d.x * left.y - d.y * left.x);
+    } else { /* hdistant.cpp:248-250, distantflux.cpp:163-170 */
+        double h[3];
+        ertbo_square_to_uniform_hemisphere(fx, fy, h);
+        mat_apply_vec(sd->to_world, V(-h[0], -h[1], -h[2]), &d);
+        mat_apply_vec(sd->to_world, V(1, 0, 0), &frame_s);
+        mat_apply_vec(sd->to_world, V(0, 1, 0), &frame_t);
+        if (sd->type == ERTB_SENSOR_DISTANTFLUX) {
+            v3 nref;
+            mat_apply_vec(sd->to_world, V(0, 0, 1), &nref);
+            int npix = sd->width * sd->height;
+            weight = vdot(vneg(d), nref) / (INV_TWO_PI * npix);
+        }
+    }
+    double off = sensor_ray_offset(S, sd);
+    ray->d = d;
+    ray->maxt = DBL_MAX;
+    if (sd->target_type == ERTB_TARGET_POINT) {
+        ray->o = vfma(d, -off, V(sd->target[0], sd->target[1], sd->target[2]));
+    } else if (sd->target_type == ERTB_TARGET_RECTANGLE) {
+        /* Shape::sample_position of `rectangle`: uniform on to_world*[-1,1]^2; weight
+         * 1/(pdf*area) = 1 */
+        v3 p;
+        mat_apply_pt(sd->target_to_world, V(2.0 * ax - 1.0, 2.0 * ay - 1.0, 0.0), &p);
+        ray->o = vfma(d, -off, p);
+    } else if (sd->target_type == ERTB_TARGET_DISK) {
+        double x, y;
+        ertbo_square_to_uniform_disk_concentric(ax, ay, &x, &y);
+        v3 p;
+        mat_apply_pt(sd->target_to_world, V(x, y, 0.0), &p);
+        ray->o = vfma(d, -off, p);
+    } else {
+        double x, y;
+        ertbo_square_to_uniform_disk_concentric(ax, ay, &x, &y);
+        double rad = fmax(RAY_EPS, S->desc->bsphere_radius * (1.0 + RAY_EPS));
+        v3 c = V(S->desc->bsphere_center[0], S->desc->bsphere_center[1], S->desc->bsphere_center[2]);
+        v3 perp = vadd(vmul(frame_s, x), vmul(frame_t, y));
+        ray->o = vfma(d, -off, vfma(perp, rad, c));
+    }
+    return weight;
+}
+
+/* ----------------------------------------------------------- integrator */
+typedef struct { uint64_t trips_main, trips_nee, n_scatter, n_surface; } counters_t;
+
+static int target_medium(v3 n, v3 d) { return vdot(d, n) > 0.0 ? 0 : 1; } /* interaction.h:318-332 */
+
+/* volpath.cpp:400-554 sample_emitter: ratio tracking toward the directional emitter.
+ * `ref_n` is the zero vector for medium interactions. */
+static double sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n, int medium,
+                             counters_t *C, v3 *ds_d) {
+    const ertb_scene_desc *D = S->desc;
+    (void) next_1d(rng); (void) next_1d(rng); /* next_2d consumed, volpath.cpp:407 */
+    /* directional.cpp:171-201 */
+    v3 d = S->emitter_d;
+    v3 c = V(D->bsphere_center[0], D->bsphere_center[1], D->bsphere_center[2]);
+    double brad = fmax(RAY_EPS, D->bsphere_radius * (1.0 + RAY_EPS));
+    double radius = fmax(brad, vnorm(vsub(ref_p, c)));
+    double dist = 2.0 * radius;
+    v3 ds_p = vfma(d, -dist, ref_p);
+    *ds_d = vneg(d);
+    double emitter_val = D->irradiance;
+
+    ray_t ray = spawn_ray_to(ref_p, ref_n, ds_p);
+    double max_dist = ray.maxt, total_dist = 0.0, transmittance = 1.0;
+    si_t si; si.t = INFINITY; si.shape = -1;
+    int needs_intersection = 1, active = 1;
+    while (active) {
+        double remaining = max_dist - total_dist;
+        ray.maxt = remaining;
+        if (!(remaining > 0.0)) break;
+        C->trips_nee++;
+        int escaped = 0, active_medium = medium, active_surface = !medium;
+        if (active_medium) {
+            mei_t mei = sample_interaction(S, &ray, next_1d(rng));
+            if (D->homogeneous && mei.t < INFINITY) ray.maxt = fmin(mei.t, remaining);
+            if (needs_intersection) si = scene_intersect(S, &ray);
+            if (si.t < mei.t) mei.t = INFINITY;
+            needs_intersection = 0;
+            { /* is_spectral branch (has_spectral_extinction defaults to true) */
+                double t = fmin(remaining, fmin(mei.t, si.t)) - mei.mint;
+                double tr = exp(-t * mei.combined);
+                double pdf = (si.t < mei.t || mei.t > remaining) ? tr : tr * mei.combined;
+                transmittance *= pdf > 0.0 ? tr / pdf : 0.0;
+            }
+            if (mei.t > remaining && mei.t < INFINITY) total_dist = dist;
+            if (mei.t > remaining) mei.t = INFINITY;
+            escaped = !(mei.t < INFINITY);
+            active_medium = mei.t < INFINITY;
+            if (active_medium) {
+                total_dist += mei.t;
+                ray.o = mei.p;
+                si.t -= mei.t;
+                transmittance *= mei.sigma_n;
+            }
+        }
+        int intersect = active_surface && needs_intersection;
+        if (intersect) { si = scene_intersect(S, &ray); needs_intersection = 0; }
+        active_surface |= escaped;
+        if (active_surface) total_dist += si.t;
+        active_surface = active_surface && (si.t < INFINITY) && !active_medium;
+        if (active_surface) {
+            /* eval_null_transmission: null.cpp -> 1, every other BSDF -> 0 */
+            transmittance *= si.shape == SHAPE_TOA ? 1.0 : 0.0;
+            ray = spawn_ray(si.p, si.n, ray.d);
+            needs_intersection = 1;
+        }
+        ray.maxt = remaining;
+        active = (active_medium || active_surface) && transmittance != 0.0;
+        if (active_surface && si.shape == SHAPE_TOA) medium = target_medium(si.n, ray.d);
+    }
+    return transmittance * emitter_val;
+}
+
+/* volpath.cpp:93-396 (mono, unpolarized).  mis != 0 selects the volpathmis.cpp
+ * Russian-roulette placement (:227-231), the only difference left in mono. */
+static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t *C) {
+    const ertb_scene_desc *D = S->desc;
+    const int mis = D->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
+    const uint64_t max_depth = D->max_depth < 0 ? (uint64_t) 0xffffffffu : (uint64_t) D->max_depth;
+    double throughput = 1.0, result = 0.0, eta = 1.0;
+    int medium = 0; /* sensors sit outside the atmosphere */
+    uint64_t depth = 0;
+    si_t si; si.t = INFINITY; si.shape = -1; si.p = si.n = V(0, 0, 0);
+    int needs_intersection = 1, last_event_was_null = 0;
+
+    for (;;) {
+        /* ---- termination, volpath.cpp:189-202 ---- */
+        if (throughput == 0.0) break;
+        double q = fmin(throughput * eta * eta, 0.95);
+        int perform_rr = depth > (uint64_t) D->rr_depth && !(mis && last_event_was_null);
+        double xi = next_1d(rng);
+        if (perform_rr) {
+            if (!(xi < q)) break;
+            throughput /= q;
+        }
+        last_event_was_null = 0;
+        if (!(depth < max_depth)) break;
+        C->trips_main++;
+
+        int active_medium = medium, active_surface = !medium;
+        int escaped = 0, null_scatter = 0, medium_scatter = 0;
+        mei_t mei; memset(&mei, 0, sizeof mei);
+
+        if (active_medium) { /* :218-259 */
+            mei = sample_interaction(S, &ray, next_1d(rng));
+            if (D->homogeneous && mei.t < INFINITY) ray.maxt = mei.t;
+            if (needs_intersection) si = scene_intersect(S, &ray);
+            needs_intersection = 0;
+            if (si.t < mei.t) mei.t = INFINITY;
+            { /* transmittance_eval_pdf, medium.cpp:87-96 */
+                double t = fmin(mei.t, si.t) - mei.mint;
+                double tr = exp(-t * mei.combined);
+                double pdf = si.t < mei.t ? tr : tr * mei.combined;
+                throughput *= pdf > 0.0 ? tr / pdf : 0.0;
+            }
+            escaped = !(mei.t < INFINITY);
+            active_medium = mei.t < INFINITY;
+            if (active_medium) {
+                double pnull = mei.sigma_n / mei.combined;
+                null_scatter = next_1d(rng) < pnull;
+                medium_scatter = !null_scatter;
+                if (null_scatter) { throughput *= mei.sigma_n / pnull; last_event_was_null = 1; }
+                else depth++;
+            }
+        }
+        if (!(depth < max_depth)) break; /* :262-263: active false -> loop ends */
+
+        if (null_scatter) { ray.o = mei.p; si.t -= mei.t; }
+
+        if (medium_scatter) { /* :270-310 */
+            C->n_scatter++;
+            throughput *= mei.sigma_s / (mei.sigma_t / mei.combined);
+            v3 ds_d;
+            double emitted = sample_emitter(S, rng, mei.p, V(0, 0, 0), medium, C, &ds_d);
+            double pv, ppdf;
+            phase_eval_pdf(S, mei.layer, mei.wi, ds_d, &pv, &ppdf);
+            result += throughput * pv * emitted; /* mis_weight(1, 0) = 1 for a delta emitter */
+            v3 wo; double pw, pp;
+            double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
+            phase_sample(S, mei.layer, mei.wi, s1, u1, u2, &wo, &pw, &pp);
+            if (pp > 0.0) {
+                ray = spawn_ray(mei.p, V(0, 0, 0), wo);
+                needs_intersection = 1;
+                throughput *= pw;
+            }
+        }
+
+        /* ---- surfaces, :312-389 ---- */
+        active_surface |= escaped;
+        if (active_surface && needs_intersection) si = scene_intersect(S, &ray);
+        active_surface = active_surface && si.t < INFINITY;
+        if (active_surface) {
+            frame_t fr = make_frame(si.n);
+            v3 wi = to_local(&fr, vneg(ray.d));
+            v3 wo_world;
+            if (si.shape == SHAPE_TOA) { /* null.cpp:41-87 */
+                (void) next_1d(rng); (void) next_1d(rng); (void) next_1d(rng);
+                wo_world = ray.d;
+            } else {
+                C->n_surface++;
+                if (depth + 1 < max_depth) { /* :349-363 */
+                    v3 ds_d;
+                    double emitted = sample_emitter(S, rng, si.p, si.n, medium, C, &ds_d);
+                    v3 wo = to_local(&fr, ds_d);
+                    result += throughput * bsdf_eval(S, wi, wo) * emitted;
+                }
+                double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
+                v3 wo;
+                throughput *= bsdf_sample(S, wi, s1, u1, u2, &wo);
+                wo_world = to_world(&fr, wo);
+                depth++;
+            }
+            ray = spawn_ray(si.p, si.n, wo_world);
+            needs_intersection = 1;
+            if (si.shape == SHAPE_TOA) medium = target_medium(si.n, ray.d);
+        }
+        if (!(active_surface || active_medium)) break;
+    }
+    return result;
+}
+
+/* ---------------------------------------------------------------- render */
+int ertbo_render(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_t spp,
+                 uint64_t sample_offset, double *sum_wl, double *sum_l, double *sum_l2,
+                 ertb_render_stats *stats, int n_threads) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    if (sensor < 0 || sensor >= desc->n_sensors) { scene_free(&S); return fail("bad sensor index"); }
+    const ertb_sensor_desc *sd = &desc->sensors[sensor];
+    const int W = sd->width, H = sd->height;
+    const int64_t npix = (int64_t) W * H;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#else
+    (void) n_threads;
+#endif
+    /* work items = (pixel, chunk of samples) so a 1-pixel film still uses every core */
+    const uint64_t chunk = 4096;
+    const uint64_t chunks_per_pixel = (spp + chunk - 1) / chunk;
+    const int64_t n_items = npix * (int64_t) chunks_per_pixel;
+    double *a_wl = calloc(npix, sizeof(double)), *a_l = calloc(npix, sizeof(double)),
+           *a_l2 = calloc(npix, sizeof(double));
+    counters_t total = { 0, 0, 0, 0 };
+
+#pragma omp parallel
+    {
+        counters_t C = { 0, 0, 0, 0 };
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t item = 0; item < n_items; ++item) {
+            int64_t pix = item / (int64_t) chunks_per_pixel;
+            uint64_t c0 = (uint64_t) (item % (int64_t) chunks_per_pixel) * chunk;
+            uint64_t c1 = c0 + chunk < spp ? c0 + chunk : spp;
+            int px = (int) (pix % W), py = (int) (pix / W);
+            double s_wl = 0, s_l = 0, s_l2 = 0;
+            for (uint64_t s = c0; s < c1; ++s) {
+                pcg32 rng;
+                uint64_t gid = ((uint64_t) pix << 40) + (sample_offset + s);
+                pcg_seed(&rng, mix64(seed * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL) ^ mix64(gid), gid);
+                /* render_sample, integrator.cpp:449-520 */
+                double fx = (px + next_1d(&rng)) / W, fy = (py + next_1d(&rng)) / H;
+                double ax = next_1d(&rng), ay = next_1d(&rng);
+                ray_t ray;
+                double w = sensor_sample_ray(&S, sd, fx, fy, ax, ay, &ray);
+                double L = volpath_sample(&S, &rng, ray, &C);
+                s_wl += w * L; s_l += L; s_l2 += L * L;
+            }
+#pragma omp critical
+            { a_wl[pix] += s_wl; a_l[pix] += s_l; a_l2[pix] += s_l2; }
+        }
+#pragma omp critical
+        {
+            total.trips_main += C.trips_main; total.trips_nee += C.trips_nee;
+            total.n_scatter += C.n_scatter; total.n_surface += C.n_surface;
+        }
+    }
+    for (int64_t i = 0; i < npix; ++i) {
+        if (sum_wl) sum_wl[i] = a_wl[i];
+        if (sum_l) sum_l[i] = a_l[i];
+        if (sum_l2) sum_l2[i] = a_l2[i];
+    }
+    free(a_wl); free(a_l); free(a_l2);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->n_paths = (uint64_t) npix * spp;
+        stats->trips_main = total.trips_main; stats->trips_nee = total.trips_nee;
+        stats->n_scatter = total.n_scatter; stats->n_surface = total.n_surface;
+    }
+    scene_free(&S);
+    return 0;
+}
+
+/* ------------------------------------------------------------ KAT entries */
+int ertbo_bsdf_eval(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo, double *out) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    for (size_t i = 0; i < n; ++i)
+        out[i] = bsdf_eval(&S, V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
+    scene_free(&S);
+    return 0;
+}
+int ertbo_bsdf_sample(const ertb_scene_desc *desc, size_t n, const double *wi, const double *u,
+                      double *wo, double *weight) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    for (size_t i = 0; i < n; ++i) {
+        v3 o;
+        weight[i] = bsdf_sample(&S, V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), u[3 * i], u[3 * i + 1], u[3 * i + 2], &o);
+        wo[3 * i] = o.x; wo[3 * i + 1] = o.y; wo[3 * i + 2] = o.z;
+    }
+    scene_free(&S);
+    return 0;
+}
+int ertbo_phase_eval(const ertb_scene_desc *desc, int leaf, size_t n, const double *c, double *out) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    if (leaf < 0 || leaf >= desc->n_phase) { scene_free(&S); return fail("bad leaf"); }
+    for (size_t i = 0; i < n; ++i) { double p; leaf_eval_pdf(&S, leaf, c[i], &out[i], &p); }
+    scene_free(&S);
+    return 0;
+}
+int ertbo_phase_sample(const ertb_scene_desc *desc, int leaf, size_t n, const double *u,
+                       double *ct, double *weight, double *pdf) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    if (leaf < 0 || leaf >= desc->n_phase) { scene_free(&S); return fail("bad leaf"); }
+    for (size_t i = 0; i < n; ++i) {
+        v3 wl;
+        leaf_sample(&S, leaf, u[2 * i], u[2 * i + 1], &wl, &weight[i], &pdf[i]);
+        ct[i] = -wl.z; /* local z = wi = -propagation direction */
+    }
+    scene_free(&S);
+    return 0;
+}
+int ertbo_sensor_ray(const ertb_scene_desc *desc, int sensor, size_t n, const double *fs,
+                     const double *as, double *origin, double *dir, double *weight) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    if (sensor < 0 || sensor >= desc->n_sensors) { scene_free(&S); return fail("bad sensor index"); }
+    for (size_t i = 0; i < n; ++i) {
+        ray_t r;
+        weight[i] = sensor_sample_ray(&S, &desc->sensors[sensor], fs[2 * i], fs[2 * i + 1], as[2 * i], as[2 * i + 1], &r);
+        origin[3 * i] = r.o.x; origin[3 * i + 1] = r.o.y; origin[3 * i + 2] = r.o.z;
+        dir[3 * i] = r.d.x; dir[3 * i + 1] = r.d.y; dir[3 * i + 2] = r.d.z;
+    }
+    scene_free(&S);
+    return 0;
+}
+int ertbo_medium_lookup(const ertb_scene_desc *desc, size_t n, const double *p, double *st, double *al) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    for (size_t i = 0; i < n; ++i) {
+        int l = layer_index(&S, V(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
+        st[i] = l >= 0 ? (double) desc->sigma_t_scale * desc->sigma_t[l] : 0.0;
+        al[i] = l >= 0 ? desc->albedo[l] : 0.0;
+    }
+    scene_free(&S);
+    return 0;
+}

@@ -1,0 +1,59 @@
+/*
+ * ertb_oracle.h -- CPU restatement (double precision, plain C) of the reference's
+ * null-collision volumetric path tracer.  TEST INFRASTRUCTURE ONLY: it is the
+ * checker for the CUDA path (tests/, __graft_entry__.smoke(), bench.py's
+ * cpu_baseline / --impl reference legs).  Nothing under eradiate_b200/ may
+ * import, link or call it.
+ *
+ * It consumes the same flat scene descriptor as the CUDA library
+ * (include/eradiate_b200.h) but follows the reference's own formulation:
+ * world-space 3D rays, shape intersections, medium AABB, PCG32 sampler.
+ */
+#ifndef ERTB_ORACLE_H
+#define ERTB_ORACLE_H
+
+#include "../include/eradiate_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *ertbo_last_error(void);
+
+/* MI/src/render/integrator.cpp:398-520 + volpath.cpp:93-572, n_threads OpenMP threads
+ * (0 = all).  Same outputs as ertb_render. */
+int ertbo_render(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_t spp,
+                 uint64_t sample_offset, double *sum_wl, double *sum_l, double *sum_l2,
+                 ertb_render_stats *stats, int n_threads);
+
+/* Point-wise plugin evaluations (double). Same conventions as ertb_kat_*. */
+int ertbo_bsdf_eval(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo,
+                    double *out);
+int ertbo_bsdf_sample(const ertb_scene_desc *desc, size_t n, const double *wi, const double *u,
+                      double *wo, double *weight);
+int ertbo_phase_eval(const ertb_scene_desc *desc, int leaf, size_t n, const double *cos_theta,
+                     double *out);
+int ertbo_phase_sample(const ertb_scene_desc *desc, int leaf, size_t n, const double *u,
+                       double *cos_theta, double *weight, double *pdf);
+int ertbo_sensor_ray(const ertb_scene_desc *desc, int sensor, size_t n, const double *film_sample,
+                     const double *aperture_sample, double *origin, double *dir, double *weight);
+
+/* distr_1d.h restatements exposed for the golden-vector tests. */
+int ertbo_distr_regular(const float *pdf, int n, size_t nq, const double *u, double *x_sampled,
+                        const double *xq, double *pdf_eval, double *integral);
+int ertbo_distr_irregular(const float *nodes, const float *pdf, int n, size_t nq, const double *u,
+                          double *x_sampled, const double *xq, double *pdf_eval, double *integral);
+
+/* Warps (MI/include/mitsuba/core/warp.h) for KATs */
+void ertbo_square_to_uniform_disk_concentric(double u, double v, double *x, double *y);
+void ertbo_square_to_cosine_hemisphere(double u, double v, double *out3);
+void ertbo_square_to_uniform_hemisphere(double u, double v, double *out3);
+
+/* Analytic helpers used by the tests: vertical optical thickness etc. */
+int ertbo_medium_lookup(const ertb_scene_desc *desc, size_t n, const double *p_xyz, double *sigma_t,
+                        double *albedo);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,20 @@
+/* ertb_oracle_ocean.h -- ocean_legacy BSDF restatement (oracle side). See ertb_oracle_ocean.c */
+#ifndef ERTB_ORACLE_OCEAN_H
+#define ERTB_ORACLE_OCEAN_H
+typedef struct ocean_state {
+    int ready;
+    double wavelength, wind_speed, wind_direction, chlorinity, pigmentation;
+    int shadowing;
+    double n_real, n_imag;           /* water index of refraction */
+    double r_omega;                  /* underlight reflectance */
+    double whitecap_coverage, whitecap_reflectance, underlight_attn;
+    double sigma2, sigma_c2, sigma_u2; /* Cox-Munk */
+    double *tr_down, *tr_up;         /* 64-node transmittance tables */
+    int n_tab;
+} ocean_state_t;
+int ocean_init(ocean_state_t *o, const float *params);
+void ocean_free(ocean_state_t *o);
+double ocean_eval(const ocean_state_t *o, double wix, double wiy, double wiz, double wox, double woy, double woz);
+double ocean_sample(const ocean_state_t *o, double wix, double wiy, double wiz, double s1, double u1, double u2, double *wo);
+double ocean_pdf(const ocean_state_t *o, double wix, double wiy, double wiz, double wox, double woy, double woz);
+#endif
