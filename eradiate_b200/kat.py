@@ -1,0 +1,73 @@
+"""
+Point-wise evaluation of the device plugin implementations through the C ABI's
+``ertb_kat_*`` entry points (known-answer tests; one GPU thread per query).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, _lib
+from .kernel._render import _device_scene
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(_abi.c_float_p)
+
+
+def _dp(a):
+    return a.ctypes.data_as(_abi.c_double_p)
+
+
+def bsdf_eval(scene, wi, wo):
+    dev = _device_scene(scene)
+    dev.sync()
+    wi, wo = _f(wi).reshape(-1, 3), _f(wo).reshape(-1, 3)
+    out = np.zeros(wi.shape[0], dtype=np.float32)
+    _lib.check(dev.lib.ertb_kat_bsdf_eval(dev.handle, wi.shape[0], _fp(wi), _fp(wo), _fp(out)))
+    return out
+
+
+def bsdf_sample(scene, wi, u):
+    dev = _device_scene(scene)
+    dev.sync()
+    wi, u = _f(wi).reshape(-1, 3), _f(u).reshape(-1, 2)
+    wo = np.zeros_like(wi)
+    w = np.zeros(wi.shape[0], dtype=np.float32)
+    _lib.check(dev.lib.ertb_kat_bsdf_sample(dev.handle, wi.shape[0], _fp(wi), _fp(u), _fp(wo), _fp(w)))
+    return wo, w
+
+
+def phase_eval(scene, leaf, cos_theta):
+    dev = _device_scene(scene)
+    dev.sync()
+    c = _f(cos_theta).reshape(-1)
+    out = np.zeros_like(c)
+    _lib.check(dev.lib.ertb_kat_phase_eval(dev.handle, leaf, c.size, _fp(c), _fp(out)))
+    return out
+
+
+def phase_sample(scene, leaf, u):
+    dev = _device_scene(scene)
+    dev.sync()
+    u = _f(u).reshape(-1, 2)
+    ct, w, pdf = (np.zeros(u.shape[0], dtype=np.float32) for _ in range(3))
+    _lib.check(dev.lib.ertb_kat_phase_sample(dev.handle, leaf, u.shape[0], _fp(u), _fp(ct), _fp(w), _fp(pdf)))
+    return ct, w, pdf
+
+
+def sensor_ray(scene, sensor, film_sample, aperture_sample):
+    dev = _device_scene(scene)
+    dev.sync()
+    fs, ap = _f(film_sample).reshape(-1, 2), _f(aperture_sample).reshape(-1, 2)
+    n = fs.shape[0]
+    o, d = np.zeros((n, 3)), np.zeros((n, 3))
+    w = np.zeros(n, dtype=np.float32)
+    _lib.check(dev.lib.ertb_kat_sensor_ray(dev.handle, sensor, n, _fp(fs), _fp(ap), _dp(o), _dp(d), _fp(w)))
+    return o, d, w

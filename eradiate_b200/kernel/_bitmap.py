@@ -29,7 +29,10 @@ class Bitmap:
             self._data = data._data.copy()
             self._pixel_format = data._pixel_format
             self._channel_names = list(data._channel_names)
-            self.raw = None if data.raw is None else {k: v.copy() for k, v in data.raw.items()}
+            self.raw = None if data.raw is None else {
+                k: (v.copy() if hasattr(v, "copy") else v) for k, v in data.raw.items()
+            }
+            self.stats = getattr(data, "stats", None)
             return
         a = np.array(data, dtype=np.float32)
         if a.ndim == 2:
@@ -43,6 +46,7 @@ class Bitmap:
         )
         #: float64 per-pixel sums {"sum_wl", "sum_l", "sum_l2", "spp"} (not part of mi.Bitmap)
         self.raw = raw
+        self.stats = None
 
     def pixel_format(self) -> PixelFormat:
         return self._pixel_format

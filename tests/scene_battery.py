@@ -1,0 +1,53 @@
+"""Scene battery shared by the golden-fixture generator and the GPU parity tests."""
+import numpy as np
+
+from eradiate_b200 import scenes
+
+POMMEROL = dict(w=0.526, theta=13.3, b=0.187, c=(1.0 + 0.273) / 2.0, h=0.083, B_0=1.0)
+VZA5 = {"type": "mdistant", "vza": [-70.0, -35.0, 0.0, 35.0, 70.0], "vaa": 0.0}
+
+
+def battery() -> dict:
+    """name -> scene dict.  Small films; every plugin of SURVEY 8a appears at least once."""
+    S = scenes.atmosphere_scene
+    return {
+        # BASELINE configs at reduced size
+        "c1_homogeneous_lambertian_pp": scenes.config_c1(spp=16),
+        "c2_afgl_rpv_spherical": scenes.config_c2(spp=16, n_vza=8),
+        "c3_afgl_aerosol_tab_hdistant": scenes.config_c3(spp=16, res=4),
+        # geometry x medium
+        "afgl_rpv_pp": S(geometry="plane_parallel", sensor=VZA5, sza=50.0, saa=30.0),
+        "homogeneous_spherical_hg": S(geometry="spherical_shell", atmosphere="homogeneous",
+                                      homogeneous_sigma_t=4e-6, homogeneous_albedo=0.9,
+                                      phase={"type": "hg", "g": 0.6}, sensor=VZA5),
+        "thick_isotropic_pp": S(geometry="plane_parallel", atmosphere="homogeneous",
+                                homogeneous_sigma_t=5.0 / scenes.TOA, homogeneous_albedo=0.99,
+                                phase={"type": "isotropic"}, sensor=VZA5,
+                                surface={"type": "diffuse", "reflectance": 0.2}),
+        # BSDFs
+        "rtls_pp": S(geometry="plane_parallel", surface={"type": "rtls"}, sensor=VZA5, n_layers=200),
+        "rtls_rb_spherical": S(surface={"type": "rtls", "f_iso": 0.3, "f_vol": 0.2, "f_geo": 0.05,
+                                        "h": 1.5, "r": 1.2, "b": 0.9}, sensor=VZA5, n_layers=200),
+        "hapke_spherical": S(surface={"type": "hapke", **POMMEROL}, sensor=VZA5, n_layers=200, sza=20.0),
+        "lambertian_spherical_grazing_sun": S(surface={"type": "diffuse", "reflectance": 0.8},
+                                              sensor=VZA5, n_layers=200, sza=85.0, saa=120.0),
+        # phase functions
+        "aerosol_hg_blend_pp": S(geometry="plane_parallel", aerosol=True, aerosol_phase="hg", sensor=VZA5),
+        "aerosol_tab_irregular_spherical": S(aerosol=True, aerosol_phase="tabphase_irregular", sensor=VZA5),
+        "rayleigh_depolarized_pp": S(geometry="plane_parallel", n_layers=100, sensor=VZA5,
+                                     phase={"type": "rayleigh", "depolarization": 0.0279}),
+        # sensors
+        "hdistant_pp": S(geometry="plane_parallel", n_layers=100,
+                         sensor={"type": "hdistant", "film_resolution": (3, 3)}),
+        "distantflux_spherical": S(n_layers=100, sensor={"type": "distantflux", "film_resolution": (3, 2)}),
+        "distantflux_no_target_spherical": S(n_layers=100,
+                                             sensor={"type": "distantflux", "film_resolution": (2, 2),
+                                                     "target": None}),
+        # integrator options
+        "volpathmis_thick": S(geometry="plane_parallel", atmosphere="homogeneous", integrator="volpathmis",
+                              homogeneous_sigma_t=3.0 / scenes.TOA, homogeneous_albedo=0.95, sensor=VZA5,
+                              surface={"type": "diffuse", "reflectance": 0.3}),
+        "max_depth_3_rr_2": S(geometry="plane_parallel", atmosphere="homogeneous", max_depth=3, rr_depth=2,
+                              homogeneous_sigma_t=2.0 / scenes.TOA, sensor=VZA5),
+        "no_atmosphere_rpv_spherical": S(atmosphere=None, sensor=VZA5),
+    }

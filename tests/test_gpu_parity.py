@@ -1,0 +1,338 @@
+"""
+GPU parity tests proper: the CUDA path, called through the C ABI
+(eradiate_b200/csrc/libertb_cuda.so), against the CPU oracle on the same scenes.
+
+* plugin-level KATs: fp32 device functions vs the fp64 oracle, tolerance stated per test;
+* render-level: per-pixel paired z-test + Sidak correction (the reference's own
+  regression statistic, test_tools/regression.py:852-893) against committed oracle
+  fixtures (tests/golden/oracle_renders.json) and against analytic answers;
+* size-independent properties at BASELINE.json's full C2 size: sample-shard additivity,
+  seed determinism, linearity in irradiance, parameter-update equivalence.
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from eradiate_b200 import kat, scenes
+from eradiate_b200.kernel import (
+    KernelContext, mi_load_dict, mi_render, mi_traverse, render, SeedState,
+)
+from tests.scene_battery import POMMEROL, battery
+from tests.util import sidak_ok, stats_from_sums, z_scores
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_renders.json")))
+
+
+def sph_to_dir(theta, phi):
+    theta, phi = np.asarray(theta, float), np.asarray(phi, float)
+    return np.stack([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)], axis=-1)
+
+
+def load(surface=None, phase=None, **kw):
+    kw.setdefault("geometry", "plane_parallel")
+    kw.setdefault("n_layers", 10)
+    return mi_load_dict(scenes.atmosphere_scene(surface=surface, phase=phase, **kw))
+
+
+# ------------------------------------------------------------------------------ KATs
+@pytest.mark.parametrize("bsdf", [
+    {"type": "diffuse", "reflectance": 0.4},
+    {"type": "rpv", "rho_0": 0.027685, "k": 0.95, "g": -0.1},
+    {"type": "rpv", "rho_0": 0.2, "k": 0.6, "g": 0.3, "rho_c": 0.5},
+    {"type": "rtls"},
+    {"type": "rtls", "f_iso": 0.3, "f_vol": 0.2, "f_geo": 0.05, "h": 1.5, "r": 1.2, "b": 0.9},
+    {"type": "hapke", **POMMEROL},
+])
+def test_bsdf_eval_and_sample_match_oracle(oracle, bsdf):
+    sc = load(surface=bsdf)
+    desc = sc.flat.build_desc()
+    rng = np.random.default_rng(0)
+    n = 4096
+    wi = sph_to_dir(rng.uniform(0.0, 1.45, n), rng.uniform(0, 2 * np.pi, n)).astype(np.float32)
+    wo = sph_to_dir(rng.uniform(0.0, 1.45, n), rng.uniform(0, 2 * np.pi, n)).astype(np.float32)
+    got = kat.bsdf_eval(sc, wi, wo)
+    ref = oracle.bsdf_eval(desc, wi, wo)
+    # fp32 with fast intrinsics (__powf, __fdividef) vs fp64: 2e-4 relative
+    assert np.allclose(got, ref, rtol=2e-4, atol=1e-7), np.max(np.abs(got - ref) / np.abs(ref))
+    u = rng.uniform(0, 1, (n, 2)).astype(np.float32)
+    wo_g, w_g = kat.bsdf_sample(sc, wi, u)
+    wo_o, w_o = oracle.bsdf_sample(desc, wi, np.concatenate([np.zeros((n, 1)), u], axis=1))
+    assert np.allclose(wo_g, wo_o, atol=2e-6)
+    ok = wo_o[:, 2] > 0.02  # weights near the horizon amplify the fp32 direction error
+    assert np.allclose(w_g[ok], w_o[ok], rtol=5e-4, atol=1e-7)
+    # below-horizon configurations evaluate to zero (rpv.cpp:174-180)
+    down = sph_to_dir([2.0], [0.3]).astype(np.float32)
+    assert kat.bsdf_eval(sc, down, wo[:1])[0] == 0.0 and kat.bsdf_eval(sc, wi[:1], down)[0] == 0.0
+
+
+def test_hapke_golden_on_device():
+    # ERP/tests/bsdfs/test_hapke.py:82-127 golden values, evaluated by the CUDA implementation
+    sc = load(surface={"type": "hapke", **POMMEROL})
+    for theta_o, golden in ((30.0, 0.24746648), (-89.0, 0.15426355), (80.0, 0.19555340)):
+        ti, to = np.deg2rad(30.0), np.deg2rad(theta_o)
+        val = kat.bsdf_eval(sc, sph_to_dir([ti], [0.0]), sph_to_dir([to], [0.0]))[0] / abs(np.cos(to)) * np.pi
+        assert np.allclose(val, golden, rtol=3e-4), (theta_o, val)
+
+
+@pytest.mark.parametrize("phase", [
+    {"type": "isotropic"},
+    {"type": "rayleigh"},
+    {"type": "rayleigh", "depolarization": 0.0279},
+    {"type": "hg", "g": 0.7},
+    {"type": "hg", "g": -0.3},
+    {"type": "hg", "g": 0.0},
+    {"type": "tabphase", "values": "0.5, 1.0, 1.5"},
+    {"type": "tabphase", "values": ",".join(map(str, scenes.hg_table(0.7, 181)[1]))},
+    {"type": "tabphase_irregular", "values": "0.2, 0.4, 1.0, 4.0, 0.0, 2.0",
+     "nodes": "-1, -0.5, 0.1, 0.6, 0.9, 1"},
+])
+def test_phase_eval_and_sample_match_oracle(oracle, phase):
+    sc = load(atmosphere="afgl", phase=phase)
+    desc = sc.flat.build_desc()
+    c = np.linspace(-1, 1, 2001).astype(np.float32)
+    got, ref = kat.phase_eval(sc, 0, c), oracle.phase_eval(desc, 0, c)
+    assert np.allclose(got, ref, rtol=1e-4, atol=1e-7)
+    rng = np.random.default_rng(1)
+    u = rng.uniform(0, 1, (8192, 2)).astype(np.float32)
+    u[:4, 0] = [0.0, 0.5, 0.25, 0.99999994]
+    ct_g, w_g, p_g = kat.phase_sample(sc, 0, u)
+    ct_o, w_o, p_o = oracle.phase_sample(desc, 0, u)
+    # CDF inversion in fp32: absolute tolerance on the sampled cosine
+    assert np.allclose(ct_g, ct_o, atol=3e-4), np.max(np.abs(ct_g - ct_o))
+    assert np.allclose(w_g, w_o, rtol=1e-4)
+    assert np.allclose(p_g, oracle.phase_eval(desc, 0, -ct_g.astype(np.float64)), rtol=2e-3, atol=1e-6)
+
+
+def test_tabphase_reference_values_on_device():
+    # MI/src/phase/tests/test_tabphase.py:13-93
+    sc = load(atmosphere="afgl", phase={"type": "tabphase", "values": "0.5, 1.0, 1.5"})
+    x = np.linspace(-1, 1, 3)
+    c = np.linspace(-1, 1, 33)
+    ref = 0.5 / np.pi * np.interp(-c, x, [0.5, 1.0, 1.5]) / np.trapezoid([0.5, 1.0, 1.5], x)
+    assert np.allclose(kat.phase_eval(sc, 0, c), ref, rtol=1e-5)
+    sc = load(atmosphere="afgl", phase={"type": "tabphase", "values": "0.0, 0.5, 1.0"})
+    ct, w, pdf = kat.phase_sample(sc, 0, [[0.99999994, 0.0]])
+    assert np.allclose(ct, 1.0, atol=1e-4) and np.allclose(pdf, 0.5 / np.pi, rtol=1e-3)
+
+
+@pytest.mark.parametrize("sensor,geometry", [
+    ({"type": "mdistant", "vza": [-60.0, 0.0, 30.0], "vaa": 40.0}, "plane_parallel"),
+    ({"type": "mdistant", "vza": [-60.0, 0.0, 30.0], "vaa": 40.0, "target": None}, "spherical_shell"),
+    ({"type": "hdistant", "film_resolution": (4, 4)}, "spherical_shell"),
+    ({"type": "distantflux", "film_resolution": (4, 2)}, "plane_parallel"),
+    ({"type": "distantflux", "film_resolution": (4, 2), "target": None}, "spherical_shell"),
+])
+def test_sensor_rays_match_oracle(oracle, sensor, geometry):
+    sc = mi_load_dict(scenes.atmosphere_scene(geometry=geometry, n_layers=10, sensor=dict(sensor)))
+    desc = sc.flat.build_desc()
+    rng = np.random.default_rng(2)
+    fs, ap = rng.uniform(0, 1, (512, 2)).astype(np.float32), rng.uniform(0, 1, (512, 2)).astype(np.float32)
+    o_g, d_g, w_g = kat.sensor_ray(sc, 0, fs, ap)
+    o_o, d_o, w_o = oracle.sensor_ray(desc, 0, fs, ap)
+    assert np.allclose(d_g, d_o, atol=2e-6)
+    assert np.allclose(w_g, w_o, rtol=1e-5)
+    if sensor.get("target", 0) is None and sensor["type"] == "mdistant":
+        # bounding-disk sampling: any orthonormal frame is valid -> compare the radial offsets
+        c = np.array(list(desc.bsphere_center))
+        r_g = np.linalg.norm(np.cross(o_g - c, d_g), axis=1)
+        r_o = np.linalg.norm(np.cross(o_o - c, d_o), axis=1)
+        assert np.allclose(r_g, r_o, rtol=1e-4)
+    else:
+        scale = max(1.0, np.abs(o_o).max())
+        assert np.allclose(o_g, o_o, atol=3e-6 * scale)
+
+
+# --------------------------------------------------------------- render-level parity
+def gpu_render(sc, spp, seed=11, sensor=0):
+    bmp = render(sc, sensor=sensor, seed=seed, spp=spp)
+    raw = bmp.raw
+    mean, var = stats_from_sums(raw["sum_l"].ravel(), raw["sum_l2"].ravel(), spp)
+    return raw["sum_wl"].ravel() / spp, mean, var, bmp.stats
+
+
+@pytest.mark.parametrize("name", list(battery().keys()))
+def test_render_matches_oracle_fixture(name):
+    """Every pixel within the Sidak-corrected z bound of the oracle fixture, and the
+    relative difference of the film mean below 3 combined sigma (north-star criterion)."""
+    gold = GOLDEN["scenes"][name]
+    sc = mi_load_dict(battery()[name])
+    heavy = gold["trips_main_per_path"] + gold["trips_nee_per_path"] > 100
+    spp = 1 << (17 if heavy else 20)
+    wl, mean, var, st = gpu_render(sc, spp)
+    z = z_scores(mean, var, np.array(gold["mean"]), np.array(gold["var_of_mean"]))
+    ok, zc = sidak_ok(z, alpha=0.01)
+    assert ok, f"{name}: |z| max {np.abs(z).max():.2f} > {zc:.2f}\n gpu {mean}\n cpu {gold['mean']}"
+    assert np.all(np.abs(z) <= 4.0)
+    # ray-weighted channel (distantflux weights)
+    zw = (wl.sum() - np.sum(gold["mean_wl"])) / np.sqrt(np.sum(var) + np.sum(gold["var_of_mean"])) \
+        if not np.allclose(wl, mean) else 0.0
+    assert abs(zw) < 5.0 or np.isclose(wl.sum(), np.sum(gold["mean_wl"]), rtol=2e-2)
+    # loop-trip parity: the oracle counts two extra stencil-crossing iterations per
+    # path that enters the atmosphere (volpath.cpp outer iterations); NEE walks with a zero
+    # weight are skipped on the GPU, so its count may only be lower.
+    k_gpu = (st["trips_main"] + st["trips_nee"]) / st["n_paths"]
+    k_cpu = gold["trips_main_per_path"] + gold["trips_nee_per_path"]
+    assert k_gpu <= k_cpu + 0.05
+    assert k_gpu >= 0.55 * k_cpu - 3.0
+    assert np.isclose(st["n_scatter"] / st["n_paths"], gold["scatter_per_path"], rtol=0.05, atol=0.01)
+    assert np.isclose(st["n_surface"] / st["n_paths"], gold["surface_per_path"], rtol=0.05, atol=0.01)
+
+
+@pytest.mark.parametrize("geometry", ["plane_parallel", "spherical_shell"])
+@pytest.mark.parametrize("rho", [0.0, 0.5, 1.0])
+def test_lambertian_brf_no_atmosphere(geometry, rho):
+    # tests/02_system/test_onedim_lambertian_brf.py:112-117 (spp = 1!) and test_basic.py:96-122
+    sza, E0 = 30.0, 1.8
+    sc = mi_load_dict(scenes.atmosphere_scene(
+        geometry=geometry, atmosphere=None, sza=sza, irradiance=E0,
+        surface={"type": "diffuse", "reflectance": rho},
+        sensor={"type": "mdistant", "vza": [-60.0, -20.0, 0.0, 45.0], "vaa": 0.0}))
+    wl, mean, var, _ = gpu_render(sc, 1)
+    brf = np.pi * wl / (E0 * np.cos(np.deg2rad(sza)))
+    assert np.allclose(brf, rho, rtol=1e-3, atol=1e-12)  # tolerance of test_basic.py
+    assert np.allclose(brf, rho, rtol=2e-6, atol=1e-12)  # fp32 arithmetic
+
+
+@pytest.mark.parametrize("geometry", ["plane_parallel", "spherical_shell"])
+def test_beer_lambert_and_single_scattering(geometry):
+    """Analytic answers at high sample counts (tighter than the oracle can afford)."""
+    E0 = 1.8
+    # (1) purely absorbing column above a Lambertian ground, nadir sun and view
+    n = 50
+    sc = mi_load_dict(scenes.atmosphere_scene(geometry=geometry, atmosphere="afgl", n_layers=n, sza=0.0,
+                                              surface={"type": "diffuse", "reflectance": 0.7},
+                                              sensor={"type": "mdistant", "vza": [0.0], "vaa": 0.0}))
+    w = mi_traverse(sc)
+    prof = (np.linspace(2.0, 0.2, n) * 1e-5).astype(np.float32)
+    rel = "volume.data" if geometry == "spherical_shell" else "data"
+    w.parameters.update({
+        f"shape_atmosphere.interior_medium.sigma_t.{rel}": prof,
+        f"shape_atmosphere.interior_medium.albedo.{rel}": np.zeros(n, np.float32),
+    })
+    spp = 1 << 22
+    _, mean, var, _ = gpu_render(sc, spp)
+    tau = float(np.sum(prof.astype(np.float64)) * scenes.TOA / n)
+    expected = 0.7 * np.float32(E0) / np.pi * np.exp(-2.0 * tau)
+    assert abs(mean[0] - expected) < 4.0 * np.sqrt(var[0]) + 2e-6 * expected, (mean, expected)
+    if geometry == "spherical_shell":
+        return
+    # (2) Chandrasekhar single scattering, isotropic homogeneous slab over a black ground
+    tau, w0, sza, vza = 0.8, 0.9, 40.0, 25.0
+    sc = mi_load_dict(scenes.atmosphere_scene(
+        geometry="plane_parallel", atmosphere="homogeneous", homogeneous_sigma_t=tau / scenes.TOA,
+        homogeneous_albedo=w0, phase={"type": "isotropic"}, sza=sza, max_depth=2,
+        surface={"type": "diffuse", "reflectance": 0.0},
+        sensor={"type": "mdistant", "vza": [vza], "vaa": 70.0}))
+    _, mean, var, _ = gpu_render(sc, spp)
+    mu0, muv = np.cos(np.deg2rad(sza)), np.cos(np.deg2rad(vza))
+    expected = w0 * E0 / (4 * np.pi) * mu0 / (mu0 + muv) * (1 - np.exp(-tau * (1 / mu0 + 1 / muv)))
+    assert abs(mean[0] - expected) < 4.0 * np.sqrt(var[0]) + 1e-5 * expected, (mean, expected)
+
+
+def test_rpv_degenerate_equals_lambertian_through_atmosphere():
+    # tests/02_system/test_atmosphere_rpv.py:622-764
+    common = dict(geometry="spherical_shell", atmosphere="afgl", n_layers=120, sza=30.0,
+                  sensor={"type": "mdistant", "vza": np.linspace(-60, 60, 7), "vaa": 0.0})
+    spp = 1 << 20
+    a = mi_load_dict(scenes.atmosphere_scene(surface={"type": "rpv", "rho_0": 0.5, "k": 1.0, "g": 0.0, "rho_c": 1.0}, **common))
+    b = mi_load_dict(scenes.atmosphere_scene(surface={"type": "diffuse", "reflectance": 0.5}, **common))
+    _, m1, v1, _ = gpu_render(a, spp, seed=1)
+    _, m2, v2, _ = gpu_render(b, spp, seed=2)
+    ok, _ = sidak_ok(z_scores(m1, v1, m2, v2))
+    assert ok and np.allclose(m1, m2, rtol=1e-2)
+
+
+# ------------------------------------------ properties at BASELINE.json's full C2 size
+def test_c2_full_size_properties():
+    spp = 1 << 20
+    sc = mi_load_dict(scenes.config_c2(spp=spp))
+    from eradiate_b200.kernel._render import _device_scene
+    dev_render = lambda seed, n, off=0: _device_scene(sc).render(0, seed, n, off)  # noqa: E731
+    full = dev_render(5, spp)
+    assert full[3].n_paths == 32 * spp
+    # (a) sample-shard additivity: paths are keyed by (seed, pixel, sample index), so two
+    #     half-range shards (what two GPUs would render) add up to the full render
+    h1, h2 = dev_render(5, spp // 2, 0), dev_render(5, spp // 2, spp // 2)
+    for k in range(3):
+        assert np.allclose(h1[k] + h2[k], full[k], rtol=1e-9)
+    assert h1[3].trips_main + h2[3].trips_main == full[3].trips_main
+    # (b) determinism: same seed -> same path set (fp64 atomics reorder the sums only)
+    again = dev_render(5, spp)
+    assert again[3].trips_main == full[3].trips_main and again[3].trips_nee == full[3].trips_nee
+    assert np.allclose(again[1], full[1], rtol=1e-10)
+    # (c) a different seed gives a statistically compatible but different film
+    other = dev_render(6, spp)
+    m1, v1 = stats_from_sums(full[1], full[2], spp)
+    m2, v2 = stats_from_sums(other[1], other[2], spp)
+    assert not np.allclose(m1, m2, rtol=1e-9)
+    ok, _ = sidak_ok(z_scores(m1, v1, m2, v2))
+    assert ok
+    # (d) every pixel finite and positive; variance of the mean consistent with 1/spp scaling
+    assert np.all(np.isfinite(m1)) and np.all(m1 > 0)
+    mq, vq = stats_from_sums(h1[1], h1[2], spp // 2)
+    assert np.allclose(vq / v1, 2.0, rtol=0.1)
+
+
+def test_linearity_in_irradiance_and_update_equivalence(oracle):
+    spp = 1 << 16
+    sc = mi_load_dict(scenes.config_c2(spp=spp, n_vza=4))
+    w = mi_traverse(sc, scenes.spectral_update_map(1200, spherical=True))
+    _, m1, _, s1 = gpu_render(sc, spp, seed=3)
+    w.parameters.update({"illumination.irradiance.value": 3.6})
+    _, m2, _, s2 = gpu_render(sc, spp, seed=3)
+    assert np.allclose(2.0 * m1, m2, rtol=1e-5)  # same seed, same paths
+    assert s1["trips_main"] == s2["trips_main"]
+    # spectral update through the update map == a scene freshly built at that wavelength
+    w.parameters.update(w.umap_template.render(KernelContext(w=440.0)))
+    _, m3, v3, _ = gpu_render(sc, spp, seed=3)
+    fresh = mi_load_dict(scenes.atmosphere_scene(
+        geometry="spherical_shell", w_nm=440.0, irradiance=1.8 * 550 / 440,
+        sensor={"type": "mdistant", "vza": np.linspace(-75, 75, 4), "vaa": 0.0}))
+    _, m4, v4, _ = gpu_render(fresh, spp, seed=3)
+    assert np.allclose(m3, m4, rtol=1e-6)
+    wl, l, l2, _ = oracle.render(sc.flat.build_desc(), 0, 99, 1 << 14)
+    mo, vo = stats_from_sums(l, l2, 1 << 14)
+    assert np.all(np.abs(z_scores(m3, v3, mo, vo)) < 4.0)
+
+
+def test_mi_render_boundary_protocol():
+    """mi_load_dict -> mi_traverse -> mi_render exactly as Experiment.init/process drive it
+    (experiments/_core.py:664-744)."""
+    spp = 1 << 14
+    kdict = scenes.config_c2(spp=spp, n_vza=6)
+    kdict["measure_2"] = dict(kdict["measure"], id="measure_2")
+    mi_scene = mi_traverse(mi_load_dict(kdict), scenes.spectral_update_map(1200, spherical=True))
+    mi_scene.drop_parameters()
+    ctxs = [KernelContext(w=w) for w in (440.0, 550.0, 670.0)]
+    results = mi_render(mi_scene, ctxs, spp=0, seed_state=SeedState(0))
+    assert list(results.keys()) == [440.0, 550.0, 670.0]
+    radiance = []
+    for w_, per_sensor in results.items():
+        assert set(per_sensor) == {"measure", "measure_2"}
+        for bmp in per_sensor.values():
+            splits = dict(bmp.split())
+            assert set(splits) == {"<root>", "nested", "m2_nested"}
+            img = np.array(splits["<root>"])
+            assert img.shape == (1, 6, 1) and np.all(img > 0)
+            m2 = np.array(splits["m2_nested"])[:, :, 0]
+            assert np.all(m2 >= img[:, :, 0] ** 2 * 0.999)
+        radiance.append(np.array(dict(per_sensor["measure"].split())["<root>"])[0, :, 0])
+    # Rayleigh optical depth ~ lambda^-4: the blue sky is brighter than the red one
+    assert np.all(radiance[0] / (1.8 * 550 / 440) > radiance[2] / (1.8 * 550 / 670))
+    # the two sensors got different seeds (SeedState.next() per sensor, _render.py:453)
+    a = np.array(results[550.0]["measure"])
+    b = np.array(results[550.0]["measure_2"])
+    assert not np.array_equal(a, b) and np.allclose(a[..., 0], b[..., 0], rtol=0.2)
+
+
+def test_error_paths_through_the_abi():
+    sc = mi_load_dict(scenes.config_c1())
+    with pytest.raises(RuntimeError, match="sensor index"):
+        render(sc, sensor=3, seed=0, spp=4)
+    from eradiate_b200.kernel._render import _device_scene
+    with pytest.raises(RuntimeError, match="spp must be > 0"):
+        _device_scene(sc).render(0, 0, 0)

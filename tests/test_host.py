@@ -1,0 +1,184 @@
+"""
+Host-side logic of the drop-in boundary (CPU only): dict flattening, parameter
+traversal/update protocol, bitmap facade, seeds, error behaviour.  Mirrors the
+reference's tests/01_unit/kernel/test_render.py and test_kernel_dict.py.
+"""
+
+import ctypes as C
+import warnings
+
+import numpy as np
+import pytest
+
+from eradiate_b200 import _abi, scenes
+from eradiate_b200.kernel import (
+    Bitmap, KernelContext, KernelSceneParameterMap, Medium, SceneParameter, SearchSceneParameter,
+    SeedState, develop, mi_load_dict, mi_traverse,
+)
+from eradiate_b200.kernel._scene import unflatten
+
+
+def test_unflatten_dotted_keys():
+    d = {"type": "mdistant", "film.type": "hdrfilm", "film.width": 3, "film.rfilter.type": "box"}
+    assert unflatten(d) == {"type": "mdistant", "film": {"type": "hdrfilm", "width": 3, "rfilter": {"type": "box"}}}
+
+
+def test_flatten_c2_geometry():
+    sc = mi_load_dict(scenes.config_c2(spp=16))
+    f = sc.flat
+    assert f.geometry == _abi.GEOM_SPHERICAL_SHELL
+    assert np.isclose(f.surface_z, scenes.EARTH_RADIUS)
+    assert np.isclose(f.medium_top, scenes.EARTH_RADIUS + scenes.TOA)
+    assert np.isclose(f.medium_bottom, scenes.EARTH_RADIUS, rtol=1e-12)
+    assert f.n_layers() == 1200
+    # scene bbox = cube around the TOA sphere -> bounding sphere radius sqrt(3) * R_toa
+    assert np.isclose(f.bsphere_radius, np.sqrt(3) * (scenes.EARTH_RADIUS + scenes.TOA))
+    d = f.build_desc()
+    assert d.n_phase == 1 and d.phase[0].type == _abi.PHASE_RAYLEIGH
+    assert d.bsdf_type == _abi.BSDF_RPV
+    assert np.allclose(list(d.bsdf_params)[:4], [0.027685, 0.95, -0.1, 0.027685])
+    assert d.sensors[0].n_directions == 32 and d.sensors[0].target_type == _abi.TARGET_POINT
+    sun = -np.array(list(d.emitter_direction))
+    assert np.allclose(sun, scenes.angles_to_direction(30.0, 0.0))
+    assert d.max_depth == -1 and d.rr_depth == 5 and d.integrator == _abi.INTEGRATOR_VOLPATH
+    assert sc.integrator().moment
+
+
+def test_flatten_c1_plane_parallel_homogeneous():
+    sc = mi_load_dict(scenes.config_c1())
+    f = sc.flat
+    d = f.build_desc()
+    assert f.geometry == _abi.GEOM_PLANE_PARALLEL and d.homogeneous == 1 and d.n_layers == 1
+    assert np.isclose(f.surface_z, 0.0) and np.isclose(f.medium_top, scenes.TOA)
+    assert np.isclose(d.sigma_t[0], 1.16e-5) and d.albedo[0] == 1.0
+    assert d.bsdf_type == _abi.BSDF_DIFFUSE and d.bsdf_params[0] == 0.5
+
+
+def test_blendphase_tree_flattening():
+    """Nested blendphase (scenes/phase/_blend.py:188) -> leaf probabilities per layer."""
+    n = 8
+    w_outer = np.linspace(0.0, 1.0, n)
+    w_inner = np.full(n, 0.25)
+    d = scenes.atmosphere_scene(geometry="plane_parallel", atmosphere="afgl", n_layers=n)
+    vol = lambda w: scenes._volume(w, False, scenes.EARTH_RADIUS, scenes.TOA, 1e9)  # noqa: E731
+    d["phase_atmosphere"] = {
+        "type": "blendphase", "id": "phase_atmosphere",
+        "phase_0": {"type": "rayleigh"},
+        "phase_1": {"type": "blendphase", "weight": vol(w_inner),
+                    "phase_0": {"type": "hg", "g": 0.5}, "phase_1": {"type": "isotropic"}},
+        "weight": vol(w_outer),
+    }
+    sc = mi_load_dict(d)
+    desc = sc.flat.build_desc()
+    assert desc.n_phase == 3
+    assert [desc.phase[i].type for i in range(3)] == [_abi.PHASE_RAYLEIGH, _abi.PHASE_HG, _abi.PHASE_ISOTROPIC]
+    pw = np.ctypeslib.as_array(desc.phase_weight, shape=(3, n))
+    assert np.allclose(pw[0], 1 - w_outer, atol=1e-7)
+    assert np.allclose(pw[1], w_outer * 0.75, atol=1e-7)
+    assert np.allclose(pw[2], w_outer * 0.25, atol=1e-7)
+    assert np.allclose(pw.sum(axis=0), 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("mutate,match", [
+    (lambda d: d["integrator"].update({"type": "piecewise_volpath"}) or d.pop("x", None), "piecewise"),
+    (lambda d: d["integrator"].update({"type": "path"}), "unsupported"),
+    (lambda d: d["surface_bsdf"].update({"type": "dielectric"}), "unsupported plugin type 'dielectric'"),
+    (lambda d: d["measure"].update({"type": "perspective"}), "perspective"),
+    (lambda d: d["measure"]["film"].update({"width": 5}), "Film size"),
+    (lambda d: d["measure"]["sampler"].update({"type": "stratified"}), "sampler"),
+    (lambda d: d["illumination"].update({"type": "constant"}), "unsupported"),
+    (lambda d: d["medium_atmosphere"]["sigma_t"]["volume"].update({"filter_type": "trilinear"}), "nearest"),
+])
+def test_unsupported_plugins_raise_runtime_error(mutate, match):
+    # experiments/_core.py:670-671: load errors surface as RuntimeError
+    d = scenes.config_c2(spp=4)
+    if "nested" in d["integrator"] and match in ("piecewise", "unsupported") and "integrator" in str(mutate.__code__.co_consts):
+        d["integrator"] = dict(d["integrator"]["nested"])
+    mutate(d)
+    with pytest.raises(RuntimeError, match=match):
+        mi_load_dict(d)
+
+
+def test_traverse_parameter_keys_and_search():
+    sc = mi_load_dict(scenes.config_c2(spp=4))
+    umap = scenes.spectral_update_map(1200, spherical=True)
+    umap["surface.rho_0"] = SceneParameter(lambda ctx: 0.2, parameter_id="surface_shape.bsdf.rho_0.value")
+    w = mi_traverse(sc, umap)
+    keys = set(w.parameters.keys())
+    # same dotted paths Mitsuba's traversal publishes
+    for k in (
+        "shape_atmosphere.interior_medium.sigma_t.volume.data",
+        "shape_atmosphere.interior_medium.albedo.volume.data",
+        "shape_atmosphere.interior_medium.scale",
+        "illumination.irradiance.value",
+        "surface_shape.bsdf.rho_0.value",
+        "surface_shape.bsdf.k.value",
+        "surface_shape.bsdf.g.value",
+        "surface_shape.bsdf.rho_c.value",
+    ):
+        assert k in keys, k
+    # SearchSceneParameter lookups were resolved (kernel/_render.py:314-321)
+    assert w.umap_template["medium_atmosphere.sigma_t"].parameter_id == \
+        "shape_atmosphere.interior_medium.sigma_t.volume.data"
+    assert w.umap_template["illumination.irradiance.value"].parameter_id == "illumination.irradiance.value"
+    # drop_parameters keeps only what the update map touches (kernel/_render.py:122-140)
+    w.drop_parameters()
+    assert len(w.parameters) == 4
+    # update protocol
+    ctx = KernelContext(w=440.0)
+    w.parameters.update(w.umap_template.render(ctx))
+    flat = sc.flat
+    st = flat._profile(flat.medium.children["sigma_t"], 1200, "sigma_t")
+    assert np.allclose(st, scenes.afgl_like_profile(1200, scenes.TOA, 440.0)[1])
+    assert np.isclose(flat.emitter.children["irradiance"].values["value"], 1.8 * 550 / 440)
+    assert np.isclose(flat.bsdf_params()[0], 0.2)
+    assert flat.medium.children["sigma_t"].children["volume"].dirty
+
+
+def test_traverse_warns_on_unsuccessful_lookup():
+    sc = mi_load_dict(scenes.config_c1())
+    umap = KernelSceneParameterMap({"x": SceneParameter(lambda ctx: 1.0,
+                                    search=SearchSceneParameter(Medium, "does_not_exist", "scale"))})
+    with pytest.warns(UserWarning, match="unsuccessful"):
+        mi_traverse(sc, umap)
+
+
+def test_update_size_mismatch_raises():
+    sc = mi_load_dict(scenes.config_c2(spp=4))
+    w = mi_traverse(sc)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        w.parameters.update({"shape_atmosphere.interior_medium.sigma_t.volume.data": np.zeros(7)})
+    with pytest.raises(KeyError):
+        w.parameters.update({"nope.value": 1.0})
+
+
+def test_bitmap_split_matches_experiment_process_protocol():
+    # experiments/_core.py:714-744
+    sc = mi_load_dict(scenes.config_c2(spp=4, n_vza=5))
+    spp = 10
+    s1 = np.arange(5, dtype=float)
+    bmp = develop(sc, 0, s1 * 2, s1, s1 * s1, spp)
+    splits = dict(bmp.split())
+    assert set(splits) == {"<root>", "nested", "m2_nested"}
+    assert splits["<root>"].pixel_format() == Bitmap.PixelFormat.Y
+    assert splits["m2_nested"].pixel_format() == Bitmap.PixelFormat.XYZ
+    assert np.array(bmp).shape == (1, 5, 7)
+    assert np.allclose(np.array(splits["<root>"])[0, :, 0], s1 * 2 / spp)
+    assert np.allclose(np.array(splits["m2_nested"])[0, :, 0], s1 * s1 / spp)
+    copy = Bitmap(bmp)
+    copy._data[:] = 0
+    assert np.array(bmp).max() > 0  # deep copy (kernel/_render.py:466)
+
+
+def test_seed_state_matches_numpy_seed_sequence():
+    # src/eradiate/rng.py: SeedSequence.spawn(1)[0].generate_state(1)
+    ss = SeedState(0)
+    ref = np.random.SeedSequence(0)
+    for _ in range(3):
+        assert ss.next()[0] == ref.spawn(1)[0].generate_state(1)[0]
+
+
+def test_desc_struct_layout_is_stable():
+    assert C.sizeof(_abi.PhaseDesc) == 40
+    assert C.sizeof(_abi.RenderStats) == 56
+    assert _abi.SceneDesc.sensors.offset + 8 == C.sizeof(_abi.SceneDesc)
