@@ -225,7 +225,7 @@ static int scene_commit(ertb_scene *S) {
 // mdistant.cpp:180-190: ray_offset default
 static double sensor_ray_offset(const ertb_scene *S, const ertb_sensor_desc &sd) {
     if (sd.ray_offset >= 0.0) return sd.ray_offset;
-    const double eps = 1.1920929e-7 * 0.5 * 1500.0; // math::RayEpsilon<float>
+    const double eps = 2.220446049250313e-16 * 0.5 * 1500.0; // math::RayEpsilon<double> (parity target)
     double rad = fmax(eps, S->bs_radius * (1.0 + eps));
     return sd.target_type == ERTB_TARGET_NONE ? rad : 2.0 * rad;
 }
@@ -248,15 +248,26 @@ static int build_sensor(ertb_scene *S, HostSensor &hs) {
             t[6] = 1.f;
             t[2] = 1.f;
             if (sph && sd.target_type == ERTB_TARGET_POINT) {
+                // same case analysis as primary_entry_sph() (origin = target - d * ray_offset)
                 const double *T = sd.target;
-                double b = T[0] * dx + T[1] * dy + T[2] * dz;
-                double c = T[0] * T[0] + T[1] * T[1] + T[2] * T[2] - Rt * Rt;
-                double disc = b * b - c;
-                if (disc < 0.0) { t[6] = 0.f; continue; }
+                const double off = hs.ray_offset, Rg = S->surface_z;
+                double o[3] = { T[0] - dx * off, T[1] - dy * off, T[2] - dz * off };
+                double b = o[0] * dx + o[1] * dy + o[2] * dz;
+                double oo = o[0] * o[0] + o[1] * o[1] + o[2] * o[2];
+                double Rs = oo >= Rt * Rt ? Rt : Rg;
+                double disc = b * b - (oo - Rs * Rs);
+                if (oo < Rg * Rg || disc < 0.0 || b > 0.0) { t[6] = 0.f; continue; }
                 double t0 = -b - sqrt(disc);
-                t[0] = (float) ((T[0] + t0 * dx) / Rt);
-                t[1] = (float) ((T[1] + t0 * dy) / Rt);
-                t[2] = (float) ((T[2] + t0 * dz) / Rt);
+                t[0] = (float) ((o[0] + t0 * dx) / Rs);
+                t[1] = (float) ((o[1] + t0 * dy) / Rs);
+                t[2] = (float) ((o[2] + t0 * dz) / Rs);
+                t[6] = oo >= Rt * Rt ? 1.f : 2.f;
+            } else if (!sph) {
+                double tz = sd.target_type == ERTB_TARGET_POINT ? sd.target[2]
+                          : sd.target_type == ERTB_TARGET_NONE ? S->bs_center[2] : sd.target_to_world[11];
+                double oz = tz - dz * hs.ray_offset - S->surface_z;
+                double Hd = S->has_medium ? S->medium_top - S->surface_z : 0.0;
+                t[6] = (!(dz < 0.0) || oz < 0.0) ? 0.f : (oz >= Hd ? 1.f : 2.f);
             }
         }
         CUDA_TRY(cudaMalloc(&hs.d_table, table.size() * sizeof(float)));
@@ -279,8 +290,9 @@ static void fill_sensor_params(const ertb_scene *S, const HostSensor &hs, ErtbSe
     for (int i = 0; i < 3; ++i) o.target[i] = sd.target[i];
     for (int i = 0; i < 12; ++i) o.target_to_world[i] = sd.target_to_world[i];
     for (int i = 0; i < 3; ++i) o.bs_center[i] = S->bs_center[i];
-    const double eps = 1.1920929e-7 * 0.5 * 1500.0;
+    const double eps = 2.220446049250313e-16 * 0.5 * 1500.0;
     o.bs_radius = fmax(eps, S->bs_radius * (1.0 + eps));
+    o.ray_offset = hs.ray_offset;
     o.flux_norm = (float) (2.0 * M_PI / (double) (sd.width * sd.height));
 }
 

@@ -45,6 +45,7 @@ struct ErtbSensor {
     double target_to_world[12]; // 3x4 row-major
     double bs_center[3];
     double bs_radius;
+    double ray_offset; // origin = target - d * ray_offset (mdistant.cpp:180-190)
     float flux_norm;   // distantflux: 2*pi / n_pixels
 };
 

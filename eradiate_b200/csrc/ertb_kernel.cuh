@@ -123,23 +123,36 @@ __device__ __forceinline__ int layer_of(const ErtbParams &P, float h) {
     return min(max(i, 0), P.n_layers - 1);
 }
 
-// Primary ray through target point T (double, world space) with direction d:
-// entry point on the top-of-atmosphere sphere (spherical) -- mdistant.cpp:192-242,
-// hdistant.cpp:232-275, distantflux.cpp:148-195 place the origin at T - d*ray_offset,
-// outside the scene, so the first hit is the outer stencil.
-__device__ __forceinline__ bool primary_entry_sph(const ErtbParams &P, double tx, double ty, double tz,
-                                                  f3 d, f3 &n0) {
+// Primary ray through target point T (double, world space) with direction d.  The
+// reference places the origin at o = T - d * ray_offset (mdistant.cpp:192-242,
+// hdistant.cpp:232-275, distantflux.cpp:148-195) and the sensor sits in vacuum:
+//   return 1: o is outside the outer stencil and the ray enters it at n0 (h0 = H);
+//   return 2: o lies INSIDE the outer stencil (possible with target-less sensors or a
+//             short ray_offset): the ray travels through vacuum (sensor medium = null)
+//             and hits the ground at n0 without crossing the atmosphere;
+//   return 0: nothing is hit, L = 0.
+__device__ __forceinline__ int primary_entry_sph(const ErtbParams &P, double tx, double ty, double tz,
+                                                 f3 d, double ray_offset, f3 &n0) {
     double dx = d.x, dy = d.y, dz = d.z;
+    double ox = tx - dx * ray_offset, oy = ty - dy * ray_offset, oz = tz - dz * ray_offset;
     double Rt = P.Rd + (double) P.H;
-    double b = tx * dx + ty * dy + tz * dz;
-    double c = tx * tx + ty * ty + tz * tz - Rt * Rt;
-    double disc = b * b - c;
-    if (disc < 0.0) return false;
+    double b = ox * dx + oy * dy + oz * dz;
+    double oo = ox * ox + oy * oy + oz * oz;
+    if (oo >= Rt * Rt) {
+        double disc = b * b - (oo - Rt * Rt);
+        if (disc < 0.0 || b > 0.0) return 0; // missed, or the sphere is behind the origin
+        double t0 = -b - sqrt(disc);
+        double inv = 1.0 / Rt;
+        n0 = mk3((float) ((ox + t0 * dx) * inv), (float) ((oy + t0 * dy) * inv), (float) ((oz + t0 * dz) * inv));
+        return 1;
+    }
+    if (oo < P.Rd * P.Rd) return 0; // origin below the surface: back-facing hit, BSDF = 0
+    double disc = b * b - (oo - P.Rd * P.Rd);
+    if (disc < 0.0 || b > 0.0) return 0; // leaves through the outer stencil
     double t0 = -b - sqrt(disc);
-    double px = tx + t0 * dx, py = ty + t0 * dy, pz = tz + t0 * dz;
-    double inv = 1.0 / Rt;
-    n0 = mk3((float) (px * inv), (float) (py * inv), (float) (pz * inv));
-    return true;
+    double inv = 1.0 / P.Rd;
+    n0 = mk3((float) ((ox + t0 * dx) * inv), (float) ((oy + t0 * dy) * inv), (float) ((oz + t0 * dz) * inv));
+    return 2;
 }
 
 template <bool SPH, bool STATS>
@@ -162,6 +175,7 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
     float thr = 0.f, res = 0.f, wnee = 0.f, wray = 1.f;
     unsigned depth = 0;
     bool last_null = false;
+    bool vacuum = false; // primary ray reached the ground without crossing the medium
     Pcg32 rng;
     rng.state = 0; rng.inc = 1;
 
@@ -226,16 +240,17 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
                 unsigned long long gid = ((unsigned long long) pix << 40) + (P.sample_offset + my_sample);
                 pcg_seed(rng, P.seed, gid);
                 thr = 1.f; res = 0.f; wnee = 0.f; wray = 1.f; depth = 0; last_null = false;
+                vacuum = false;
                 if (STATS) st_paths++;
                 // ---- primary ray (render_sample, integrator.cpp:449-520) ----
                 const ErtbSensor &S = P.sensor;
-                bool valid = true;
+                int valid = 1;
                 if (S.use_table) {
                     const float4 *t4 = reinterpret_cast<const float4 *>(S.table) + 2u * pix;
                     float4 a = __ldg(t4), c4 = __ldg(t4 + 1);
                     n0 = mk3(a.x, a.y, a.z);
                     d = mk3(a.w, c4.x, c4.y);
-                    valid = c4.z != 0.f;
+                    valid = (int) c4.z;
                 } else {
                     unsigned px = pix % (unsigned) S.width, py = pix / (unsigned) S.width;
                     float fx = __fdividef((float) px + pcg_float(rng), (float) S.width);
@@ -280,13 +295,20 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
                             ty = T[4] * lx + T[5] * ly + T[7];
                             tz = T[8] * lx + T[9] * ly + T[11];
                         }
-                        valid = primary_entry_sph(P, tx, ty, tz, d, n0);
+                        valid = primary_entry_sph(P, tx, ty, tz, d, S.ray_offset, n0);
+                    } else {
+                        // plane-parallel: only the origin height matters
+                        double tz = S.target_type == ERTB_TARGET_POINT ? S.target[2]
+                                  : S.target_type == ERTB_TARGET_NONE ? S.bs_center[2] : S.target_to_world[11];
+                        double oz = tz - (double) d.z * S.ray_offset - P.Rd; // height above the ground
+                        valid = !(d.z < 0.f) || oz < 0.0 ? 0 : (oz >= (double) P.H ? 1 : 2);
                     }
                 }
-                if (!SPH) valid = valid && (d.z < 0.f); // upward-looking rays miss the slab top
+                if (!SPH && !(d.z < 0.f)) valid = 0; // upward-looking rays never see the ground
                 h0 = P.H;
                 mode = MODE_SETUP_MAIN;
-                if (!valid) thr = 0.f; // L = 0, still counted as a sample
+                if (valid == 0) thr = 0.f; // L = 0, still counted as a sample
+                if (valid == 2) { vacuum = true; h0 = 0.f; s = 0.f; smax = 0.f; mode = MODE_EV_SURFACE; }
             }
         }
         if (exhausted && __all_sync(0xffffffffu, mode == MODE_IDLE)) break;
@@ -304,10 +326,13 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
                 thr *= tb[P.off_albedo + l];
                 depth++;
                 last_null = false;
-                if (STATS) st_scatter++;
-                if (depth >= P.max_depth || thr == 0.f) {
+                if (depth >= P.max_depth) {
                     mode = MODE_SETUP_MAIN; thr = 0.f;
+                } else if (thr == 0.f) {
+                    if (STATS) st_scatter++;
+                    mode = MODE_SETUP_MAIN;
                 } else {
+                    if (STATS) st_scatter++;
                     // emitter sampling: phase value towards the sun (delta emitter -> MIS weight 1)
                     float ct_sun = dot3(d, sun);
                     float pv = 0.f;
@@ -361,6 +386,9 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
                             float f = bsdf_f(P, ci, co, cos_dphi(ci, co, -dot3(d, sun)));
                             wnee = thr * f * co * P.irradiance;
                         }
+                    }
+                    if (vacuum) { // no medium on either leg: the sample is the direct surface term
+                        res += wnee; wnee = 0.f; thr = 0.f;
                     }
                     float u1 = pcg_float(rng), u2 = pcg_float(rng);
                     f3 wl = cosine_hemisphere(u1, u2);

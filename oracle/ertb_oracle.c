@@ -375,7 +375,17 @@ static si_t scene_intersect(const scene_t *S, const ray_t *ray) {
     else if (tt < INFINITY) { best.t = tt; best.shape = SHAPE_TOA; }
     if (best.t < INFINITY) {
         best.p = ray_at(ray, best.t);
-        best.n = S->spherical ? vnormalize(best.p) : V(0, 0, 1);
+        if (S->spherical) {
+            /* sphere.cpp:684-688: "Re-project onto the sphere to improve accuracy" */
+            best.n = vnormalize(best.p);
+            best.p = vmul(best.n, best.shape == SHAPE_GROUND ? d->surface_z : d->medium_top);
+        } else {
+            /* arectangle.cpp:536-540 / rectangle.cpp: "Re-project onto the rectangle" (the
+             * slab's top face is a planar mesh face, same treatment).  Without it, distant-sensor
+             * rays (t ~ 1e9 m) land ~1e-7 m off the plane, more than the spawn offset. */
+            best.n = V(0, 0, 1);
+            best.p.z = best.shape == SHAPE_GROUND ? d->surface_z : d->medium_top;
+        }
     }
     return best;
 }

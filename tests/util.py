@@ -8,15 +8,16 @@ def stats_from_sums(sum_l, sum_l2, spp):
     return mean, var
 
 
-def z_scores(mean_a, var_a, mean_b, var_b):
-    """Per-pixel paired z statistic (test_tools/regression.py:852-893)."""
-    den = np.sqrt(var_a + var_b)
+def z_scores(mean_a, var_a, mean_b, var_b, rel_floor=0.0):
+    """Per-pixel paired z statistic (test_tools/regression.py:852-893).  `rel_floor` adds an
+    fp32 arithmetic floor (relative) to the denominator for (nearly) deterministic pixels."""
+    den = np.sqrt(var_a + var_b + (rel_floor * np.maximum(np.abs(mean_a), np.abs(mean_b))) ** 2)
     with np.errstate(invalid="ignore", divide="ignore"):
         z = np.where(den > 0, (mean_a - mean_b) / den, np.where(np.isclose(mean_a, mean_b), 0.0, np.inf))
     return z
 
 
-def sidak_ok(z, alpha=0.01):
+def sidak_ok(z, alpha=0.001):
     """Sidak-corrected acceptance of H0 for all pixels (regression.py:871-878)."""
     from scipy import stats
 
