@@ -5,6 +5,7 @@
 //        -Xcompiler -fPIC  (see __graft_entry__.build()).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -496,6 +497,9 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     P.spp = spp;
     P.sample_offset = sample_offset;
     P.n_pixels = (unsigned) (hs.desc.width * hs.desc.height);
+    P.tw = ERTB_TW;
+    if (const char *e = getenv("ERTB_TW")) P.tw = atoi(e); // tuning knob
+
     // persistent grid: as many CTAs as can be resident (queried, not assumed)
     const bool sph = P.spherical;
     int blocks_per_sm = 0;

@@ -86,6 +86,7 @@ struct ErtbParams {
     unsigned long long spp;           // samples per pixel rendered by this launch
     unsigned long long sample_offset; // first sample index (multi-GPU sharding)
     unsigned n_pixels;
+    int tw;                           // scheduler: min. walking lanes for a free-flight trip
     unsigned chunk;                   // samples per work chunk
     unsigned chunks_per_pixel;
     unsigned long long n_chunks;

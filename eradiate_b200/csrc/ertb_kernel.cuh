@@ -34,6 +34,11 @@ enum : int {
     MODE_SETUP_NEE = 6,
 };
 enum : int { KIND_TOA = 0, KIND_GROUND = 1 };
+enum : int { PHASE_STEP = 0, PHASE_SETUP = 1, PHASE_REGEN = 2, PHASE_SURFACE = 3, PHASE_SCATTER = 4 };
+
+#ifndef ERTB_TW
+#define ERTB_TW 12 // minimum number of walking lanes for a free-flight trip (tuned on B200)
+#endif
 
 #define ERTB_BLOCK 256
 
@@ -192,10 +197,35 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
 
     for (;;) {
         // ------------------------------------------------------------------
+        // Warp-level phase scheduler.  Executing every phase every trip leaves ~6 of 32
+        // lanes active per instruction (ncu, profiles/r01): the heavy event code runs for
+        // one or two lanes at a time.  Instead each trip runs ONE phase: the free-flight
+        // step while at least ERTB_TW lanes can walk, otherwise the non-walking phase that
+        // currently holds the most lanes (events are thereby batched across trips).
+        // ------------------------------------------------------------------
+        const unsigned m_walk = __ballot_sync(0xffffffffu, mode == MODE_WALK_MAIN || mode == MODE_WALK_NEE);
+        const unsigned m_setup = __ballot_sync(0xffffffffu, mode == MODE_SETUP_MAIN || mode == MODE_SETUP_NEE);
+        const unsigned m_surf = __ballot_sync(0xffffffffu, mode == MODE_EV_SURFACE);
+        const unsigned m_scat = __ballot_sync(0xffffffffu, mode == MODE_EV_SCATTER);
+        const unsigned m_idle = exhausted ? 0u : __ballot_sync(0xffffffffu, mode == MODE_IDLE);
+        int phase = PHASE_STEP;
+        if (__popc(m_walk) < P.tw) {
+            int best = __popc(m_setup);
+            phase = PHASE_SETUP;
+            if (__popc(m_idle) > best) { best = __popc(m_idle); phase = PHASE_REGEN; }
+            if (__popc(m_surf) > best) { best = __popc(m_surf); phase = PHASE_SURFACE; }
+            if (__popc(m_scat) > best) { best = __popc(m_scat); phase = PHASE_SCATTER; }
+            if (best == 0) {
+                if (m_walk == 0u) break; // nothing left to do for this warp
+                phase = PHASE_STEP;
+            }
+        }
+
+        // ------------------------------------------------------------------
         // A. path regeneration (warp-aggregated pops from the chunk queue)
         // ------------------------------------------------------------------
-        unsigned need = __ballot_sync(0xffffffffu, mode == MODE_IDLE);
-        if (need) {
+        if (phase == PHASE_REGEN) {
+            const unsigned need = m_idle;
             bool got = false;
             unsigned long long my_sample = 0;
             unsigned my_pix = 0;
@@ -311,13 +341,12 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
                 if (valid == 2) { vacuum = true; h0 = 0.f; s = 0.f; smax = 0.f; mode = MODE_EV_SURFACE; }
             }
         }
-        if (exhausted && __all_sync(0xffffffffu, mode == MODE_IDLE)) break;
 
         // ------------------------------------------------------------------
         // B. heavy events: real collision in the medium / surface interaction
         // ------------------------------------------------------------------
-        if (__any_sync(0xffffffffu, mode == MODE_EV_SCATTER || mode == MODE_EV_SURFACE)) {
-            if (mode == MODE_EV_SCATTER) {
+        if (phase == PHASE_SCATTER || phase == PHASE_SURFACE) {
+            if (phase == PHASE_SCATTER && mode == MODE_EV_SCATTER) {
                 // ---- volpath.cpp:261-296 ----
                 float h = altitude_at<SPH>(P, h0, b, s);
                 if (SPH) n0 = normalize3(fma3(d, s, scale3(n0, P.R + h0)));
@@ -369,7 +398,7 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
                     }
                     mode = wnee > 0.f ? MODE_SETUP_NEE : MODE_SETUP_MAIN;
                 }
-            } else if (mode == MODE_EV_SURFACE) {
+            } else if (phase == PHASE_SURFACE && mode == MODE_EV_SURFACE) {
                 // ---- volpath.cpp:344-389 ----
                 if (SPH) n0 = normalize3(fma3(d, smax, scale3(n0, P.R + h0)));
                 h0 = 0.f;
@@ -410,13 +439,13 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
         // ------------------------------------------------------------------
         // C. segment set-up (shared by the main walk and the NEE walk)
         // ------------------------------------------------------------------
-        if (mode == MODE_SETUP_NEE) {
+        if (phase == PHASE_SETUP && mode == MODE_SETUP_NEE) {
             segment_setup<SPH>(P, n0, h0, sun, b, smax, kind);
             s = 0.f;
             if (kind == KIND_GROUND) { wnee = 0.f; mode = MODE_SETUP_MAIN; } // sun below the local horizon
             else mode = MODE_WALK_NEE;
         }
-        if (mode == MODE_SETUP_MAIN) {
+        if (phase == PHASE_SETUP && mode == MODE_SETUP_MAIN) {
             if (thr == 0.f || depth >= P.max_depth) {
                 // ---- path finished: film accumulation (imageblock.cpp:174, moment.cpp:101-104) ----
                 acc_wl += (double) (wray * res);
@@ -439,7 +468,7 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
         // D. one free-flight step: delta tracking (main) / ratio tracking (NEE)
         //    medium.cpp:42-82 with the global majorant of heterogeneous.cpp:163
         // ------------------------------------------------------------------
-        if (mode == MODE_WALK_MAIN || mode == MODE_WALK_NEE) {
+        if (phase == PHASE_STEP && (mode == MODE_WALK_MAIN || mode == MODE_WALK_NEE)) {
             const bool is_main = mode == MODE_WALK_MAIN;
             bool alive = true;
             if (is_main && !P.mis && depth > P.rr_depth) { // volpath.cpp:194-198, every loop trip
