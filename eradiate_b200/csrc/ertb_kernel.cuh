@@ -37,10 +37,13 @@ enum : int { KIND_TOA = 0, KIND_GROUND = 1 };
 enum : int { PHASE_STEP = 0, PHASE_SETUP = 1, PHASE_REGEN = 2, PHASE_SURFACE = 3, PHASE_SCATTER = 4 };
 
 #ifndef ERTB_TW
-#define ERTB_TW 12 // minimum number of walking lanes for a free-flight trip (tuned on B200)
+#define ERTB_TW 4 // minimum number of walking lanes for a free-flight trip (tuned on B200)
 #endif
 
 #define ERTB_BLOCK 256
+#ifndef ERTB_MINB
+#define ERTB_MINB 4
+#endif
 
 __device__ __forceinline__ float fast_sqrt(float x) {
     float r;
@@ -161,7 +164,7 @@ __device__ __forceinline__ int primary_entry_sph(const ErtbParams &P, double tx,
 }
 
 template <bool SPH, bool STATS>
-__global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbParams P) {
+__global__ void __launch_bounds__(ERTB_BLOCK, ERTB_MINB) ertb_render_kernel(const ErtbParams P) {
     extern __shared__ __align__(16) float tb[]; // table blob
     __shared__ __align__(8) unsigned long long mbar;
 
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
 
     unsigned st_main = 0, st_nee = 0, st_scatter = 0, st_surface = 0, st_paths = 0;
 
+    unsigned m_idle = 0u;
     for (;;) {
         // ------------------------------------------------------------------
         // Warp-level phase scheduler.  Executing every phase every trip leaves ~6 of 32
@@ -204,12 +208,12 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
         // currently holds the most lanes (events are thereby batched across trips).
         // ------------------------------------------------------------------
         const unsigned m_walk = __ballot_sync(0xffffffffu, mode == MODE_WALK_MAIN || mode == MODE_WALK_NEE);
-        const unsigned m_setup = __ballot_sync(0xffffffffu, mode == MODE_SETUP_MAIN || mode == MODE_SETUP_NEE);
-        const unsigned m_surf = __ballot_sync(0xffffffffu, mode == MODE_EV_SURFACE);
-        const unsigned m_scat = __ballot_sync(0xffffffffu, mode == MODE_EV_SCATTER);
-        const unsigned m_idle = exhausted ? 0u : __ballot_sync(0xffffffffu, mode == MODE_IDLE);
         int phase = PHASE_STEP;
         if (__popc(m_walk) < P.tw) {
+            const unsigned m_setup = __ballot_sync(0xffffffffu, mode == MODE_SETUP_MAIN || mode == MODE_SETUP_NEE);
+            const unsigned m_surf = __ballot_sync(0xffffffffu, mode == MODE_EV_SURFACE);
+            const unsigned m_scat = __ballot_sync(0xffffffffu, mode == MODE_EV_SCATTER);
+            m_idle = exhausted ? 0u : __ballot_sync(0xffffffffu, mode == MODE_IDLE);
             int best = __popc(m_setup);
             phase = PHASE_SETUP;
             if (__popc(m_idle) > best) { best = __popc(m_idle); phase = PHASE_REGEN; }
@@ -219,6 +223,55 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
                 if (m_walk == 0u) break; // nothing left to do for this warp
                 phase = PHASE_STEP;
             }
+        }
+
+        if (phase == PHASE_STEP) {
+            // ------------------------------------------------------------------
+            // D. one free-flight step: delta tracking (main) / ratio tracking (NEE)
+            //    medium.cpp:42-82 with the global majorant of heterogeneous.cpp:163
+            // ------------------------------------------------------------------
+            if (mode == MODE_WALK_MAIN || mode == MODE_WALK_NEE) {
+                const bool is_main = mode == MODE_WALK_MAIN;
+                bool alive = true;
+                if (is_main && !P.mis && depth > P.rr_depth) { // volpath.cpp:194-198, every loop trip
+                    float q = fminf(thr, 0.95f);
+                    if (pcg_float(rng) >= q) { thr = 0.f; mode = MODE_SETUP_MAIN; alive = false; }
+                    else thr = __fdividef(thr, q);
+                }
+                if (alive) {
+                    if (STATS) { if (is_main) st_main++; else st_nee++; }
+                    float u = pcg_float(rng);
+                    float t = -__logf(1.f - u) * P.inv_majorant; // inv_majorant = +inf without medium
+                    s += t;
+                    if (!(s < smax)) {
+                        // boundary reached
+                        if (is_main) {
+                            if (kind == KIND_GROUND) mode = MODE_EV_SURFACE;
+                            else { // left through the TOA: the path ends, film accumulation
+                                acc_wl += (double) (wray * res);
+                                acc_l += (double) res;
+                                acc_l2 += (double) res * (double) res;
+                                mode = MODE_IDLE;
+                            }
+                        } else {
+                            res += wnee; // shadow ray reached the TOA (ground hits were culled at set-up)
+                            mode = MODE_SETUP_MAIN;
+                        }
+                    } else {
+                        float h = altitude_at<SPH>(P, h0, b, s);
+                        float preal = tb[P.off_preal + layer_of(P, h)];
+                        if (is_main) {
+                            float u2 = pcg_float(rng);
+                            if (u2 >= 1.f - preal) mode = MODE_EV_SCATTER; // real collision
+                            else last_null = true;
+                        } else {
+                            wnee *= 1.f - preal; // ratio tracking: T *= sigma_n / majorant
+                            if (wnee == 0.f) mode = MODE_SETUP_MAIN;
+                        }
+                    }
+                }
+            }
+            continue;
         }
 
         // ------------------------------------------------------------------
@@ -464,46 +517,6 @@ __global__ void __launch_bounds__(ERTB_BLOCK, 2) ertb_render_kernel(const ErtbPa
             }
         }
 
-        // ------------------------------------------------------------------
-        // D. one free-flight step: delta tracking (main) / ratio tracking (NEE)
-        //    medium.cpp:42-82 with the global majorant of heterogeneous.cpp:163
-        // ------------------------------------------------------------------
-        if (phase == PHASE_STEP && (mode == MODE_WALK_MAIN || mode == MODE_WALK_NEE)) {
-            const bool is_main = mode == MODE_WALK_MAIN;
-            bool alive = true;
-            if (is_main && !P.mis && depth > P.rr_depth) { // volpath.cpp:194-198, every loop trip
-                float q = fminf(thr, 0.95f);
-                if (pcg_float(rng) >= q) { thr = 0.f; mode = MODE_SETUP_MAIN; alive = false; }
-                else thr = __fdividef(thr, q);
-            }
-            if (alive) {
-                if (STATS) { if (is_main) st_main++; else st_nee++; }
-                float u = pcg_float(rng);
-                float t = -__logf(1.f - u) * P.inv_majorant; // inv_majorant = +inf without medium
-                s += t;
-                if (!(s < smax)) {
-                    // boundary reached
-                    if (is_main) {
-                        if (kind == KIND_GROUND) mode = MODE_EV_SURFACE;
-                        else { thr = 0.f; mode = MODE_SETUP_MAIN; } // left through the TOA: path ends
-                    } else {
-                        res += wnee; // shadow ray reached the TOA (ground hits were culled at set-up)
-                        mode = MODE_SETUP_MAIN;
-                    }
-                } else {
-                    float h = altitude_at<SPH>(P, h0, b, s);
-                    float preal = tb[P.off_preal + layer_of(P, h)];
-                    if (is_main) {
-                        float u2 = pcg_float(rng);
-                        if (u2 >= 1.f - preal) mode = MODE_EV_SCATTER; // real collision
-                        else last_null = true;
-                    } else {
-                        wnee *= 1.f - preal; // ratio tracking: T *= sigma_n / majorant
-                        if (wnee == 0.f) mode = MODE_SETUP_MAIN;
-                    }
-                }
-            }
-        }
     }
 
     // ---- flush lane accumulators and statistics ----
