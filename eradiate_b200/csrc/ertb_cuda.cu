@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ertb_kernel.cuh"
+#include "ertb_kernel_pool.cuh"
 
 // ----------------------------------------------------------------------------
 // error handling
@@ -502,22 +503,43 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
 
     // persistent grid: as many CTAs as can be resident (queried, not assumed)
     const bool sph = P.spherical;
+    // two execution models of the same estimator: warp-private shared-memory pools (default)
+    // or one register-resident path per lane (ERTB_KERNEL=legacy, kept for A/B measurements)
+    bool use_pool = true;
+    if (const char *e = getenv("ERTB_KERNEL")) use_pool = strcmp(e, "legacy") != 0;
     int blocks_per_sm = 0;
-    const size_t smem = (size_t) S->base.blob_bytes;
-#define ERTB_OCC(SPH, ST)                                                                             \
+    const int block = use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK;
+    size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes) : (size_t) S->base.blob_bytes;
+    if (use_pool && smem > (size_t) S->max_smem_optin) { // huge tables: fall back to the register kernel
+        use_pool = false;
+        smem = (size_t) S->base.blob_bytes;
+    }
+#define ERTB_OCC(KERNEL)                                                                              \
     do {                                                                                              \
-        CUDA_TRY(cudaFuncSetAttribute(ertb_render_kernel<SPH, ST>,                                    \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));      \
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                       \
-            &blocks_per_sm, ertb_render_kernel<SPH, ST>, ERTB_BLOCK, smem));                          \
+        CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, KERNEL, block, smem)); \
     } while (0)
-    if (sph) { if (with_stats) ERTB_OCC(true, true); else ERTB_OCC(true, false); }
-    else     { if (with_stats) ERTB_OCC(false, true); else ERTB_OCC(false, false); }
+#define ERTB_DISPATCH(MACRO)                                                                          \
+    do {                                                                                              \
+        if (use_pool) {                                                                               \
+            if (sph) { if (with_stats) MACRO((ertb_render_pool_kernel<true, true>)); else MACRO((ertb_render_pool_kernel<true, false>)); } \
+            else     { if (with_stats) MACRO((ertb_render_pool_kernel<false, true>)); else MACRO((ertb_render_pool_kernel<false, false>)); } \
+        } else {                                                                                      \
+            if (sph) { if (with_stats) MACRO((ertb_render_kernel<true, true>)); else MACRO((ertb_render_kernel<true, false>)); } \
+            else     { if (with_stats) MACRO((ertb_render_kernel<false, true>)); else MACRO((ertb_render_kernel<false, false>)); } \
+        }                                                                                             \
+    } while (0)
+    ERTB_DISPATCH(ERTB_OCC);
 #undef ERTB_OCC
     if (blocks_per_sm < 1) return set_error("render kernel cannot be resident on this device");
+    if (use_pool) {
+        P.tw = 32; P.twi = 16;
+        if (const char *e = getenv("ERTB_POOL_TW")) P.tw = atoi(e);
+        if (const char *e = getenv("ERTB_POOL_TWI")) P.twi = atoi(e);
+    }
     // chunk: a few thousand paths, so that the queue hands out >> n_warps chunks
     const unsigned long long total = (unsigned long long) P.n_pixels * spp;
-    const unsigned long long n_warps = (unsigned long long) S->sm_count * blocks_per_sm * (ERTB_BLOCK / 32);
+    const unsigned long long n_warps = (unsigned long long) S->sm_count * blocks_per_sm * (block / 32);
     unsigned long long chunk = total / (n_warps * 16ULL);
     if (chunk > 4096) chunk = 4096;
     if (chunk < 32) chunk = 32;
@@ -530,16 +552,13 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     P.stats = stats_dev;
     CUDA_TRY(cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned long long), stream));
 
-    unsigned long long want_blocks = (P.n_chunks * 32ULL + ERTB_BLOCK - 1) / ERTB_BLOCK; // >= 1 lane per path slot
+    unsigned long long want_blocks = (P.n_chunks * 32ULL + block - 1) / block; // >= 1 lane per path slot
     unsigned long long grid = (unsigned long long) S->sm_count * blocks_per_sm;
     if (want_blocks < grid) grid = want_blocks ? want_blocks : 1;
-#define ERTB_LAUNCH(SPH, ST)                                                                          \
-    do {                                                                                              \
-        ertb_render_kernel<SPH, ST><<<(unsigned) grid, ERTB_BLOCK, smem, stream>>>(P);                \
-    } while (0)
-    if (sph) { if (with_stats) ERTB_LAUNCH(true, true); else ERTB_LAUNCH(true, false); }
-    else     { if (with_stats) ERTB_LAUNCH(false, true); else ERTB_LAUNCH(false, false); }
+#define ERTB_LAUNCH(KERNEL) KERNEL<<<(unsigned) grid, block, smem, stream>>>(P)
+    ERTB_DISPATCH(ERTB_LAUNCH);
 #undef ERTB_LAUNCH
+#undef ERTB_DISPATCH
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

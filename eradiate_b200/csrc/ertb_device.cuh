@@ -87,6 +87,7 @@ struct ErtbParams {
     unsigned long long sample_offset; // first sample index (multi-GPU sharding)
     unsigned n_pixels;
     int tw;                           // scheduler: min. walking lanes for a free-flight trip
+    int twi;                          // pool kernel: keep stepping while >= twi loaded records walk
     unsigned chunk;                   // samples per work chunk
     unsigned chunks_per_pixel;
     unsigned long long n_chunks;

@@ -1,0 +1,499 @@
+// ertb_kernel_pool.cuh -- wavefront megakernel with warp-private shared-memory path pools.
+//
+// Same estimator as ertb_kernel.cuh (null-collision volpath, MI/src/integrators/
+// volpath.cpp:93-572); different execution model.  The register-resident kernel keeps
+// one path per lane, so a warp can only batch 32 paths per phase and runs with ~12-19 of
+// 32 lanes active (profiles/r01b).  Here every warp owns a pool of ERTB_POOL_NS path
+// records laid out SoA in shared memory (field-major: conflict-free for consecutive
+// slots).  Each trip the warp
+//   1. reads the mode word of every slot and ballots the per-phase membership masks,
+//   2. picks ONE phase -- the free-flight walk while >= tw records can walk, otherwise
+//      the event phase (surface / scatter / regenerate) holding the most records,
+//   3. compacts up to 32 member slots into a list (ballot + popc ranks) so that lane i
+//      works on the i-th member: lanes stay dense whatever the divergence of path depths,
+//   4. loads only the fields that phase needs, runs it, stores the fields it changed.
+// The walk phase keeps stepping the records it loaded while enough of them are still
+// walking, which amortises the load/store over several free flights.  Path state moves
+// through shared memory only; HBM sees the film atomics and the work-queue counter.
+#pragma once
+
+#include "ertb_kernel.cuh"
+
+#ifndef ERTB_POOL_NS
+#define ERTB_POOL_NS 64 // records per warp (multiple of 32)
+#endif
+#ifndef ERTB_POOL_BLOCK
+#define ERTB_POOL_BLOCK 128
+#endif
+#ifndef ERTB_POOL_MINB
+#define ERTB_POOL_MINB 5
+#endif
+#define ERTB_POOL_K (ERTB_POOL_NS / 32)
+
+enum : int {
+    PF_FLAGS = 0, PF_H0, PF_B, PF_S, PF_SMAX, PF_THR, PF_WNEE, PF_RES, PF_RNG0, PF_RNG1, PF_INC0, PF_INC1,
+    PF_B2, PF_SMAX2, PF_N0X, PF_N0Y, PF_N0Z, PF_DX, PF_DY, PF_DZ, PF_PIX, PF_WRAY, PF_COUNT
+};
+enum : unsigned {
+    PM_DEAD = 0, PM_IDLE = 1, PM_WALK_MAIN = 2, PM_WALK_NEE = 3, PM_SURF = 4, PM_SCAT = 5,
+    PFL_MODE_MASK = 7u, PFL_KIND = 8u, PFL_KIND2 = 16u, PFL_LAST_NULL = 32u, PFL_VACUUM = 64u,
+    PFL_DEPTH_SHIFT = 8
+};
+
+__host__ __device__ inline size_t ertb_pool_smem_bytes(size_t blob_bytes) {
+    size_t blob = (blob_bytes + 15) & ~size_t(15);
+    size_t warps = ERTB_POOL_BLOCK / 32;
+    return blob + warps * (size_t) PF_COUNT * ERTB_POOL_NS * 4 + warps * 32 * 4;
+}
+
+template <bool SPH, bool STATS>
+__global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+    float *tb = smem; // table blob first
+    const unsigned blob_words = ((unsigned) P.blob_bytes + 15u) / 16u * 4u;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float *wp = smem + blob_words + warp * (PF_COUNT * ERTB_POOL_NS);
+    unsigned *wpu = reinterpret_cast<unsigned *>(wp);
+    int *list = reinterpret_cast<int *>(smem + blob_words + (ERTB_POOL_BLOCK / 32) * (PF_COUNT * ERTB_POOL_NS)) + warp * 32;
+
+    if (P.blob_bytes > 0) tma_stage(tb, P.blob, (unsigned) P.blob_bytes, &mbar);
+
+    const f3 sun = mk3(P.sun[0], P.sun[1], P.sun[2]);
+
+    // every record starts "finished with nothing to accumulate"
+#pragma unroll
+    for (int j = 0; j < ERTB_POOL_K; ++j) {
+        wpu[PF_FLAGS * ERTB_POOL_NS + j * 32 + lane] = PM_IDLE;
+        wpu[PF_PIX * ERTB_POOL_NS + j * 32 + lane] = 0xffffffffu;
+        wp[PF_RES * ERTB_POOL_NS + j * 32 + lane] = 0.f;
+        wp[PF_WRAY * ERTB_POOL_NS + j * 32 + lane] = 0.f;
+    }
+    __syncwarp();
+
+    // lane-local film accumulators, tagged with the pixel they belong to
+    double acc_wl = 0.0, acc_l = 0.0, acc_l2 = 0.0;
+    unsigned acc_pix = 0xffffffffu;
+    // warp-uniform work-queue cursor
+    unsigned long long cur_next = 0, cur_end = 0;
+    unsigned cur_pix = 0;
+    bool exhausted = false;
+    unsigned st_main = 0, st_nee = 0, st_scatter = 0, st_surface = 0, st_paths = 0;
+
+#define FLD(f, slot) wp[(f) * ERTB_POOL_NS + (slot)]
+#define FLDU(f, slot) wpu[(f) * ERTB_POOL_NS + (slot)]
+
+    for (;;) {
+        // ---- 1. membership masks -------------------------------------------------
+        unsigned md[ERTB_POOL_K];
+        unsigned sel[ERTB_POOL_K];
+        int n_walk = 0;
+#pragma unroll
+        for (int j = 0; j < ERTB_POOL_K; ++j) {
+            md[j] = FLDU(PF_FLAGS, j * 32 + lane) & PFL_MODE_MASK;
+            sel[j] = __ballot_sync(0xffffffffu, md[j] == PM_WALK_MAIN || md[j] == PM_WALK_NEE);
+            n_walk += __popc(sel[j]);
+        }
+        // ---- 2. phase selection ----------------------------------------------------
+        unsigned phase = PM_WALK_MAIN; // walk
+        int n_sel = n_walk;
+        if (n_walk < P.tw) {
+            unsigned ms[ERTB_POOL_K], mc[ERTB_POOL_K], mi[ERTB_POOL_K];
+            int ns = 0, nc = 0, ni = 0;
+#pragma unroll
+            for (int j = 0; j < ERTB_POOL_K; ++j) {
+                ms[j] = __ballot_sync(0xffffffffu, md[j] == PM_SURF);
+                mc[j] = __ballot_sync(0xffffffffu, md[j] == PM_SCAT);
+                mi[j] = __ballot_sync(0xffffffffu, md[j] == PM_IDLE);
+                ns += __popc(ms[j]); nc += __popc(mc[j]); ni += __popc(mi[j]);
+            }
+            int best = n_walk; // an event phase must hold more records than can walk
+            if (ni > best) { best = ni; phase = PM_IDLE; }
+            if (ns > best) { best = ns; phase = PM_SURF; }
+            if (nc > best) { best = nc; phase = PM_SCAT; }
+            if (best == 0) break; // every record is dead: done
+            if (phase != PM_WALK_MAIN) {
+                n_sel = best;
+#pragma unroll
+                for (int j = 0; j < ERTB_POOL_K; ++j)
+                    sel[j] = phase == PM_IDLE ? mi[j] : (phase == PM_SURF ? ms[j] : mc[j]);
+            }
+        }
+        // ---- 3. compaction: lane i <- i-th member slot -------------------------------
+        {
+            int base = 0;
+#pragma unroll
+            for (int j = 0; j < ERTB_POOL_K; ++j) {
+                int pos = base + __popc(sel[j] & lt_mask);
+                if (((sel[j] >> lane) & 1u) && pos < 32) list[pos] = j * 32 + (int) lane;
+                base += __popc(sel[j]);
+            }
+        }
+        __syncwarp();
+        if (n_sel > 32) n_sel = 32;
+        const bool have = (int) lane < n_sel;
+        const int slot = have ? list[lane] : 0;
+        __syncwarp();
+
+        if (phase == PM_WALK_MAIN) {
+            // =====================================================================
+            // free-flight walk (delta tracking / ratio tracking), medium.cpp:42-82
+            // =====================================================================
+            unsigned flags = 0;
+            float h0 = 0.f, b = 0.f, s = 0.f, smax = 0.f, thr = 0.f, wnee = 0.f, res = 0.f, b2 = 0.f, smax2 = 0.f;
+            Pcg32 rng; rng.state = 0; rng.inc = 1;
+            if (have) {
+                flags = FLDU(PF_FLAGS, slot);
+                h0 = FLD(PF_H0, slot); b = FLD(PF_B, slot); s = FLD(PF_S, slot); smax = FLD(PF_SMAX, slot);
+                thr = FLD(PF_THR, slot); wnee = FLD(PF_WNEE, slot); res = FLD(PF_RES, slot);
+                b2 = FLD(PF_B2, slot); smax2 = FLD(PF_SMAX2, slot);
+                rng.state = (unsigned long long) FLDU(PF_RNG0, slot) | ((unsigned long long) FLDU(PF_RNG1, slot) << 32);
+                rng.inc = (unsigned long long) FLDU(PF_INC0, slot) | ((unsigned long long) FLDU(PF_INC1, slot) << 32);
+            }
+            unsigned mode = have ? (flags & PFL_MODE_MASK) : PM_DEAD;
+            const int keep = max(1, min(P.twi, n_sel));
+            for (;;) {
+                const bool walking = mode == PM_WALK_MAIN || mode == PM_WALK_NEE;
+                if (__popc(__ballot_sync(0xffffffffu, walking)) < keep) break;
+                if (walking) {
+                    const bool is_main = mode == PM_WALK_MAIN;
+                    bool alive = true;
+                    if (is_main && !P.mis && (flags >> PFL_DEPTH_SHIFT) > P.rr_depth) { // volpath.cpp:194-198
+                        float q = fminf(thr, 0.95f);
+                        if (pcg_float(rng) >= q) { thr = 0.f; mode = PM_IDLE; alive = false; }
+                        else thr = __fdividef(thr, q);
+                    }
+                    if (alive) {
+                        if (STATS) { if (is_main) st_main++; else st_nee++; }
+                        float u = pcg_float(rng);
+                        s += -__logf(1.f - u) * P.inv_majorant;
+                        if (!(s < smax)) {
+                            if (is_main) {
+                                mode = (flags & PFL_KIND) ? PM_SURF : PM_IDLE; // ground hit / left through the TOA
+                            } else {
+                                res += wnee; // shadow ray reached the TOA
+                                wnee = 0.f;
+                            }
+                        } else {
+                            float h = altitude_at<SPH>(P, h0, b, s);
+                            float preal = tb[P.off_preal + layer_of(P, h)];
+                            if (is_main) {
+                                if (pcg_float(rng) >= 1.f - preal) mode = PM_SCAT; // real collision
+                                else flags |= PFL_LAST_NULL;
+                            } else {
+                                wnee *= 1.f - preal; // ratio tracking
+                            }
+                        }
+                        if (!is_main && wnee == 0.f) {
+                            // NEE walk over: continue with the main segment prepared by the event
+                            if (thr == 0.f || (flags >> PFL_DEPTH_SHIFT) >= P.max_depth) mode = PM_IDLE;
+                            else {
+                                b = b2; smax = smax2; s = 0.f;
+                                flags = (flags & ~PFL_KIND) | ((flags & PFL_KIND2) ? PFL_KIND : 0u);
+                                mode = PM_WALK_MAIN;
+                            }
+                        }
+                    }
+                }
+            }
+            if (have) {
+                FLDU(PF_FLAGS, slot) = (flags & ~PFL_MODE_MASK) | mode;
+                FLD(PF_B, slot) = b; FLD(PF_S, slot) = s; FLD(PF_SMAX, slot) = smax;
+                FLD(PF_THR, slot) = thr; FLD(PF_WNEE, slot) = wnee; FLD(PF_RES, slot) = res;
+                FLDU(PF_RNG0, slot) = (unsigned) rng.state; FLDU(PF_RNG1, slot) = (unsigned) (rng.state >> 32);
+            }
+            __syncwarp();
+            continue;
+        }
+
+        if (phase == PM_IDLE) {
+            // =====================================================================
+            // finish the previous path of the record + regenerate (integrator.cpp:449-520)
+            // =====================================================================
+            if (have) {
+                unsigned pix_old = FLDU(PF_PIX, slot);
+                if (pix_old != 0xffffffffu) {
+                    if (pix_old != acc_pix) {
+                        if (acc_pix != 0xffffffffu) {
+                            atomicAdd(&P.accum[acc_pix], acc_wl);
+                            atomicAdd(&P.accum[P.n_pixels + acc_pix], acc_l);
+                            atomicAdd(&P.accum[2u * P.n_pixels + acc_pix], acc_l2);
+                        }
+                        acc_wl = acc_l = acc_l2 = 0.0;
+                        acc_pix = pix_old;
+                    }
+                    float r = FLD(PF_RES, slot);
+                    acc_wl += (double) (FLD(PF_WRAY, slot) * r);
+                    acc_l += (double) r;
+                    acc_l2 += (double) r * (double) r;
+                }
+            }
+            // warp-aggregated pops from the chunk queue
+            bool got = false;
+            unsigned long long my_sample = 0;
+            unsigned my_pix = 0;
+            unsigned pending = __ballot_sync(0xffffffffu, have);
+            while (pending && !exhausted) {
+                if (cur_next >= cur_end) {
+                    unsigned long long c = 0;
+                    if (lane == 0) c = atomicAdd(P.work_counter, 1ULL);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (c >= P.n_chunks) { exhausted = true; break; }
+                    cur_pix = (unsigned) (c % P.n_pixels);
+                    unsigned long long k = c / P.n_pixels;
+                    cur_next = k * P.chunk;
+                    cur_end = min(cur_next + (unsigned long long) P.chunk, P.spp);
+                }
+                unsigned long long avail = cur_end - cur_next;
+                unsigned take = (unsigned) min((unsigned long long) __popc(pending), avail);
+                bool mine = (pending >> lane) & 1u;
+                unsigned rank = __popc(pending & lt_mask);
+                if (mine && rank < take) { got = true; my_sample = cur_next + rank; my_pix = cur_pix; }
+                cur_next += take;
+                pending &= ~__ballot_sync(0xffffffffu, mine && rank < take);
+            }
+            if (have && !got) {
+                FLDU(PF_FLAGS, slot) = PM_DEAD;
+                FLDU(PF_PIX, slot) = 0xffffffffu;
+            }
+            if (got) {
+                const unsigned pix = my_pix;
+                Pcg32 rng;
+                unsigned long long gid = ((unsigned long long) pix << 40) + (P.sample_offset + my_sample);
+                pcg_seed(rng, P.seed, gid);
+                if (STATS) st_paths++;
+                float thr = 1.f, wray = 1.f;
+                f3 n0 = mk3(0.f, 0.f, 1.f), d = mk3(0.f, 0.f, -1.f);
+                const ErtbSensor &S = P.sensor;
+                int valid = 1;
+                if (S.use_table) {
+                    const float4 *t4 = reinterpret_cast<const float4 *>(S.table) + 2u * pix;
+                    float4 a = __ldg(t4), c4 = __ldg(t4 + 1);
+                    n0 = mk3(a.x, a.y, a.z);
+                    d = mk3(a.w, c4.x, c4.y);
+                    valid = (int) c4.z;
+                } else {
+                    unsigned px = pix % (unsigned) S.width, py = pix / (unsigned) S.width;
+                    float fx = __fdividef((float) px + pcg_float(rng), (float) S.width);
+                    float fy = __fdividef((float) py + pcg_float(rng), (float) S.height);
+                    float ax = pcg_float(rng), ay = pcg_float(rng);
+                    f3 fs = mk3(1.f, 0.f, 0.f), ft = mk3(0.f, 1.f, 0.f);
+                    if (S.type == ERTB_SENSOR_MDISTANT) {
+                        const float4 *t4 = reinterpret_cast<const float4 *>(S.table) + 2u * pix;
+                        float4 a = __ldg(t4), c4 = __ldg(t4 + 1);
+                        d = mk3(a.w, c4.x, c4.y);
+                        onb(d, fs, ft);
+                    } else {
+                        f3 hv = uniform_hemisphere(fx, fy);
+                        const float *M = S.to_world;
+                        d = mk3(-(M[0] * hv.x + M[1] * hv.y + M[2] * hv.z),
+                                -(M[3] * hv.x + M[4] * hv.y + M[5] * hv.z),
+                                -(M[6] * hv.x + M[7] * hv.y + M[8] * hv.z));
+                        fs = mk3(M[0], M[3], M[6]);
+                        ft = mk3(M[1], M[4], M[7]);
+                        if (S.type == ERTB_SENSOR_DISTANTFLUX) wray = hv.z * S.flux_norm;
+                    }
+                    if (SPH) {
+                        double tx, ty, tz;
+                        if (S.target_type == ERTB_TARGET_POINT) {
+                            tx = S.target[0]; ty = S.target[1]; tz = S.target[2];
+                        } else if (S.target_type == ERTB_TARGET_NONE) {
+                            float ox, oy;
+                            disk_concentric(ax, ay, ox, oy);
+                            tx = S.bs_center[0] + ((double) fs.x * ox + (double) ft.x * oy) * S.bs_radius;
+                            ty = S.bs_center[1] + ((double) fs.y * ox + (double) ft.y * oy) * S.bs_radius;
+                            tz = S.bs_center[2] + ((double) fs.z * ox + (double) ft.z * oy) * S.bs_radius;
+                        } else {
+                            float lx, ly;
+                            if (S.target_type == ERTB_TARGET_RECTANGLE) { lx = fmaf(2.f, ax, -1.f); ly = fmaf(2.f, ay, -1.f); }
+                            else disk_concentric(ax, ay, lx, ly);
+                            const double *T = S.target_to_world;
+                            tx = T[0] * lx + T[1] * ly + T[3];
+                            ty = T[4] * lx + T[5] * ly + T[7];
+                            tz = T[8] * lx + T[9] * ly + T[11];
+                        }
+                        valid = primary_entry_sph(P, tx, ty, tz, d, S.ray_offset, n0);
+                    } else {
+                        double tz = S.target_type == ERTB_TARGET_POINT ? S.target[2]
+                                  : S.target_type == ERTB_TARGET_NONE ? S.bs_center[2] : S.target_to_world[11];
+                        double oz = tz - (double) d.z * S.ray_offset - P.Rd;
+                        valid = !(d.z < 0.f) || oz < 0.0 ? 0 : (oz >= (double) P.H ? 1 : 2);
+                    }
+                }
+                if (!SPH && !(d.z < 0.f)) valid = 0;
+                unsigned flags;
+                float h0 = P.H, b = 0.f, smax = 0.f;
+                if (valid == 1) {
+                    int kind;
+                    segment_setup<SPH>(P, n0, h0, d, b, smax, kind);
+                    flags = PM_WALK_MAIN | (kind == KIND_GROUND ? PFL_KIND : 0u);
+                } else if (valid == 2) {
+                    h0 = 0.f;
+                    flags = PM_SURF | PFL_VACUUM;
+                } else {
+                    thr = 0.f;
+                    flags = PM_IDLE; // L = 0, still counted as a sample
+                }
+                FLDU(PF_FLAGS, slot) = flags;
+                FLD(PF_H0, slot) = h0; FLD(PF_B, slot) = b; FLD(PF_S, slot) = 0.f; FLD(PF_SMAX, slot) = smax;
+                FLD(PF_THR, slot) = thr; FLD(PF_WNEE, slot) = 0.f; FLD(PF_RES, slot) = 0.f;
+                FLDU(PF_RNG0, slot) = (unsigned) rng.state; FLDU(PF_RNG1, slot) = (unsigned) (rng.state >> 32);
+                FLDU(PF_INC0, slot) = (unsigned) rng.inc; FLDU(PF_INC1, slot) = (unsigned) (rng.inc >> 32);
+                FLD(PF_B2, slot) = b; FLD(PF_SMAX2, slot) = smax;
+                FLD(PF_N0X, slot) = n0.x; FLD(PF_N0Y, slot) = n0.y; FLD(PF_N0Z, slot) = n0.z;
+                FLD(PF_DX, slot) = d.x; FLD(PF_DY, slot) = d.y; FLD(PF_DZ, slot) = d.z;
+                FLDU(PF_PIX, slot) = pix; FLD(PF_WRAY, slot) = wray;
+            }
+            __syncwarp();
+            continue;
+        }
+
+        // =========================================================================
+        // heavy events: surface interaction (volpath.cpp:344-389) / real collision (:261-296)
+        // =========================================================================
+        if (have) {
+            unsigned flags = FLDU(PF_FLAGS, slot);
+            f3 n0 = mk3(FLD(PF_N0X, slot), FLD(PF_N0Y, slot), FLD(PF_N0Z, slot));
+            f3 d = mk3(FLD(PF_DX, slot), FLD(PF_DY, slot), FLD(PF_DZ, slot));
+            float h0 = FLD(PF_H0, slot), thr = FLD(PF_THR, slot), res = FLD(PF_RES, slot);
+            Pcg32 rng;
+            rng.state = (unsigned long long) FLDU(PF_RNG0, slot) | ((unsigned long long) FLDU(PF_RNG1, slot) << 32);
+            rng.inc = (unsigned long long) FLDU(PF_INC0, slot) | ((unsigned long long) FLDU(PF_INC1, slot) << 32);
+            unsigned depth = flags >> PFL_DEPTH_SHIFT;
+            float wnee = 0.f;
+            bool dead = false;
+
+            if (phase == PM_SURF) {
+                float sm = (flags & PFL_VACUUM) ? 0.f : FLD(PF_SMAX, slot);
+                if (SPH) n0 = normalize3(fma3(d, sm, scale3(n0, P.R + h0)));
+                h0 = 0.f;
+                if (STATS) st_surface++;
+                float ci = -dot3(n0, d);
+                if (!(ci > 0.f) || P.bsdf_type == ERTB_BSDF_BLACK) {
+                    thr = 0.f; dead = true;
+                } else {
+                    if (depth + 1u < P.max_depth) {
+                        float co = dot3(n0, sun);
+                        if (co > 0.f) {
+                            float f = bsdf_f(P, ci, co, cos_dphi(ci, co, -dot3(d, sun)));
+                            wnee = thr * f * co * P.irradiance;
+                        }
+                    }
+                    if (flags & PFL_VACUUM) { res += wnee; wnee = 0.f; thr = 0.f; dead = true; }
+                    float u1 = pcg_float(rng), u2 = pcg_float(rng);
+                    f3 wl = cosine_hemisphere(u1, u2);
+                    f3 fs, ft;
+                    onb(n0, fs, ft);
+                    f3 nd = fma3(fs, wl.x, fma3(ft, wl.y, scale3(n0, wl.z)));
+                    float weight = 0.f;
+                    if (wl.z > 0.f) weight = bsdf_f(P, ci, wl.z, cos_dphi(ci, wl.z, -dot3(d, nd))) * ERTB_PI;
+                    d = normalize3(nd);
+                    thr *= weight;
+                    depth++;
+                }
+            } else { // PM_SCAT
+                float bb = FLD(PF_B, slot), s = FLD(PF_S, slot);
+                float h = altitude_at<SPH>(P, h0, bb, s);
+                if (SPH) n0 = normalize3(fma3(d, s, scale3(n0, P.R + h0)));
+                h0 = h;
+                int l = layer_of(P, h);
+                thr *= tb[P.off_albedo + l];
+                depth++;
+                if (depth >= P.max_depth) {
+                    thr = 0.f; dead = true;
+                } else {
+                    if (STATS) st_scatter++;
+                    if (thr == 0.f) {
+                        dead = true;
+                    } else {
+                        float ct_sun = dot3(d, sun);
+                        float pv = 0.f;
+                        int leaf = 0;
+                        if (P.n_phase == 1) {
+                            pv = leaf_eval(tb, P.leaf[0], ct_sun);
+                        } else {
+                            float u0 = pcg_float(rng);
+                            float prev = 0.f;
+                            leaf = P.n_phase - 1;
+                            bool picked = false;
+                            for (int i = 0; i < P.n_phase; ++i) {
+                                float cum = (i < P.n_phase - 1) ? tb[P.off_cumw + i * P.n_layers + l] : 1.f;
+                                float w = cum - prev;
+                                prev = cum;
+                                if (w > 0.f) pv = fmaf(w, leaf_eval(tb, P.leaf[i], ct_sun), pv);
+                                if (!picked && u0 < cum) { leaf = i; picked = true; }
+                            }
+                        }
+                        wnee = thr * pv * P.irradiance;
+                        float u1 = pcg_float(rng), u2 = pcg_float(rng);
+                        float pw, ppdf;
+                        float ct = leaf_sample(tb, P.leaf[leaf], u1, pw, ppdf);
+                        if (ppdf > 0.f) {
+                            float st = safe_sqrtf(1.f - ct * ct);
+                            float sp, cp;
+                            __sincosf(2.f * ERTB_PI * u2, &sp, &cp);
+                            f3 fs, ft;
+                            onb(d, fs, ft);
+                            d = normalize3(fma3(fs, st * cp, fma3(ft, st * sp, scale3(d, ct))));
+                            thr *= pw;
+                        }
+                    }
+                }
+            }
+            // volpathmis.cpp:227-231: Russian roulette after a real event only
+            if (!dead && P.mis && depth > P.rr_depth) {
+                float q = fminf(thr, 0.95f);
+                if (pcg_float(rng) >= q) thr = 0.f; else thr = __fdividef(thr, q);
+            }
+            if (thr == 0.f || depth >= P.max_depth) dead = true; // the NEE walk (if any) still runs
+            // ---- segment set-up for the NEE walk and for the main walk that follows it ----
+            float b = 0.f, smax = 0.f, b2 = 0.f, smax2 = 0.f;
+            int kind = KIND_TOA, kind2 = KIND_TOA;
+            if (!dead) segment_setup<SPH>(P, n0, h0, d, b2, smax2, kind2);
+            if (wnee > 0.f) {
+                segment_setup<SPH>(P, n0, h0, sun, b, smax, kind);
+                if (kind == KIND_GROUND) wnee = 0.f; // sun below the local horizon
+            }
+            unsigned mode;
+            if (wnee > 0.f) {
+                mode = PM_WALK_NEE;
+                kind = KIND_TOA;
+            } else if (dead) {
+                mode = PM_IDLE;
+            } else {
+                mode = PM_WALK_MAIN;
+                b = b2; smax = smax2; kind = kind2;
+            }
+            if (dead) thr = 0.f;
+            flags = mode | (kind == KIND_GROUND ? PFL_KIND : 0u) | (kind2 == KIND_GROUND ? PFL_KIND2 : 0u) |
+                    (depth << PFL_DEPTH_SHIFT);
+            FLDU(PF_FLAGS, slot) = flags;
+            FLD(PF_H0, slot) = h0; FLD(PF_B, slot) = b; FLD(PF_S, slot) = 0.f; FLD(PF_SMAX, slot) = smax;
+            FLD(PF_THR, slot) = thr; FLD(PF_WNEE, slot) = wnee; FLD(PF_RES, slot) = res;
+            FLDU(PF_RNG0, slot) = (unsigned) rng.state; FLDU(PF_RNG1, slot) = (unsigned) (rng.state >> 32);
+            FLD(PF_B2, slot) = b2; FLD(PF_SMAX2, slot) = smax2;
+            FLD(PF_N0X, slot) = n0.x; FLD(PF_N0Y, slot) = n0.y; FLD(PF_N0Z, slot) = n0.z;
+            FLD(PF_DX, slot) = d.x; FLD(PF_DY, slot) = d.y; FLD(PF_DZ, slot) = d.z;
+        }
+        __syncwarp();
+    }
+#undef FLD
+#undef FLDU
+
+    if (acc_pix != 0xffffffffu) {
+        atomicAdd(&P.accum[acc_pix], acc_wl);
+        atomicAdd(&P.accum[P.n_pixels + acc_pix], acc_l);
+        atomicAdd(&P.accum[2u * P.n_pixels + acc_pix], acc_l2);
+    }
+    if (STATS && P.stats) {
+        unsigned v[5] = { st_paths, st_main, st_nee, st_scatter, st_surface };
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            unsigned long long x = v[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) atomicAdd(&P.stats[i], x);
+        }
+    }
+}
