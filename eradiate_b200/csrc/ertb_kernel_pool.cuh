@@ -26,7 +26,7 @@
 #define ERTB_POOL_BLOCK 128
 #endif
 #ifndef ERTB_POOL_MINB
-#define ERTB_POOL_MINB 5
+#define ERTB_POOL_MINB 6
 #endif
 #define ERTB_POOL_K (ERTB_POOL_NS / 32)
 
@@ -153,13 +153,16 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
             }
             unsigned mode = have ? (flags & PFL_MODE_MASK) : PM_DEAD;
             const int keep = max(1, min(P.twi, n_sel));
+            // depth is constant during a walk: hoist the Russian-roulette / max-depth predicates
+            const bool rr_on = !P.mis && (flags >> PFL_DEPTH_SHIFT) > P.rr_depth;
+            const bool depth_done = (flags >> PFL_DEPTH_SHIFT) >= P.max_depth;
             for (;;) {
                 const bool walking = mode == PM_WALK_MAIN || mode == PM_WALK_NEE;
                 if (__popc(__ballot_sync(0xffffffffu, walking)) < keep) break;
                 if (walking) {
                     const bool is_main = mode == PM_WALK_MAIN;
                     bool alive = true;
-                    if (is_main && !P.mis && (flags >> PFL_DEPTH_SHIFT) > P.rr_depth) { // volpath.cpp:194-198
+                    if (is_main && rr_on) { // volpath.cpp:194-198: every main loop trip
                         float q = fminf(thr, 0.95f);
                         if (pcg_float(rng) >= q) { thr = 0.f; mode = PM_IDLE; alive = false; }
                         else thr = __fdividef(thr, q);
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                         }
                         if (!is_main && wnee == 0.f) {
                             // NEE walk over: continue with the main segment prepared by the event
-                            if (thr == 0.f || (flags >> PFL_DEPTH_SHIFT) >= P.max_depth) mode = PM_IDLE;
+                            if (thr == 0.f || depth_done) mode = PM_IDLE;
                             else {
                                 b = b2; smax = smax2; s = 0.f;
                                 flags = (flags & ~PFL_KIND) | ((flags & PFL_KIND2) ? PFL_KIND : 0u);
