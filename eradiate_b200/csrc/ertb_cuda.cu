@@ -77,6 +77,10 @@ struct ertb_scene {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
     int max_smem_optin = 0;
+    // ocean_legacy: transmittance tables (device) and the parameters they were built for
+    float *d_ocean = nullptr;
+    double *d_gl = nullptr;
+    double ocean_key[3] = { -1.0, -1.0, -1.0 };
 };
 
 static size_t align4(size_t n) { return (n + 3) & ~size_t(3); }
@@ -153,7 +157,6 @@ static int scene_commit(ertb_scene *S) {
     P.h_off = (float) (S->surface_z - S->medium_bottom);
     P.inv_dz = S->has_medium ? (float) (S->n_layers / (S->medium_top - S->medium_bottom)) : 0.f;
     P.n_phase = S->n_phase;
-    P.off_ocean = -1;
 
     std::vector<float> &blob = S->blob;
     blob.clear();
@@ -213,6 +216,26 @@ static int scene_commit(ertb_scene *S) {
 
     P.bsdf_type = S->bsdf_type;
     memcpy(P.bsdf, S->bsdf_params, sizeof P.bsdf);
+    P.ocean_tables = nullptr;
+    if (S->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+        // OceanBSDF::update() (ocean_legacy.cpp:313-372): scalars on the host, tables on the device
+        double n_real, n_imag;
+        ertb_ocean_host::derive(S->bsdf_params, P.bsdf, n_real, n_imag);
+        const double ws = S->bsdf_params[1];
+        if (!S->d_ocean) {
+            CUDA_TRY(cudaMalloc(&S->d_ocean, 2 * ERTB_OC_RES * ERTB_OC_RES * sizeof(float)));
+            CUDA_TRY(cudaMalloc(&S->d_gl, 2 * ERTB_OC_RES * sizeof(double)));
+            double gl[2 * ERTB_OC_RES];
+            ertb_ocean_host::gauss_legendre(ERTB_OC_RES, gl, gl + ERTB_OC_RES);
+            CUDA_TRY(cudaMemcpy(S->d_gl, gl, sizeof gl, cudaMemcpyHostToDevice));
+        }
+        if (S->ocean_key[0] != n_real || S->ocean_key[1] != n_imag || S->ocean_key[2] != ws) {
+            ertb_ocean_tables_kernel<<<(2 * ERTB_OC_RES * ERTB_OC_RES + 127) / 128, 128>>>(n_real, n_imag, ws, S->d_gl, S->d_ocean);
+            CUDA_TRY(cudaGetLastError());
+            S->ocean_key[0] = n_real; S->ocean_key[1] = n_imag; S->ocean_key[2] = ws;
+        }
+        P.ocean_tables = S->d_ocean;
+    }
     double dn = sqrt(S->emitter_dir[0] * S->emitter_dir[0] + S->emitter_dir[1] * S->emitter_dir[1] +
                      S->emitter_dir[2] * S->emitter_dir[2]);
     for (int i = 0; i < 3; ++i) P.sun[i] = (float) (-S->emitter_dir[i] / dn);
@@ -323,6 +346,8 @@ void ertb_scene_destroy(ertb_scene *S) {
     for (auto &hs : S->sensors)
         if (hs.d_table) cudaFree(hs.d_table);
     if (S->d_blob) cudaFree(S->d_blob);
+    if (S->d_ocean) cudaFree(S->d_ocean);
+    if (S->d_gl) cudaFree(S->d_gl);
     if (S->d_counter) cudaFree(S->d_counter);
     if (S->d_accum) cudaFree(S->d_accum);
     if (S->ev0) cudaEventDestroy(S->ev0);
@@ -340,7 +365,8 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
     if (D->geometry != ERTB_GEOM_PLANE_PARALLEL && D->geometry != ERTB_GEOM_SPHERICAL_SHELL)
         return set_error("unsupported geometry");
     if (D->bsdf_type < 0 || D->bsdf_type > ERTB_BSDF_BLACK) return set_error("unsupported BSDF type");
-    if (D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) return set_error("ocean_legacy BSDF is not implemented on the device yet");
+    if (D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY && D->bsdf_params[6] != 0.f)
+        return set_error("ocean_legacy: only component=0 (full BRDF) is supported");
     if (D->n_sensors < 1 || !D->sensors) return set_error("scene has no sensor");
     if (D->rr_depth <= 0) return set_error("\"rr_depth\" must be set to a value greater than zero!");
     if (D->has_medium) {
@@ -619,16 +645,22 @@ __global__ void kat_bsdf_eval_kernel(ErtbParams P, size_t n, const float *wi, co
     f3 a = mk3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), b = mk3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
     float ci = a.z, co = b.z;
     float v = 0.f;
-    if (ci > 0.f && co > 0.f) v = bsdf_f(P, ci, co, cos_dphi(ci, co, dot3(a, b))) * co;
+    if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) v = oc_eval(P, a, b);
+    else if (ci > 0.f && co > 0.f) v = bsdf_f(P, ci, co, cos_dphi(ci, co, dot3(a, b))) * co;
     out[i] = v;
 }
 __global__ void kat_bsdf_sample_kernel(ErtbParams P, size_t n, const float *wi, const float *u, float *wo, float *w) {
     size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
     if (i >= n) return;
     f3 a = mk3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
-    f3 o = cosine_hemisphere(u[2 * i], u[2 * i + 1]);
+    f3 o;
     float weight = 0.f;
-    if (a.z > 0.f && o.z > 0.f) weight = bsdf_f(P, a.z, o.z, cos_dphi(a.z, o.z, dot3(a, o))) * ERTB_PI;
+    if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+        weight = oc_sample(P, a, u[3 * i], u[3 * i + 1], u[3 * i + 2], o);
+    } else {
+        o = cosine_hemisphere(u[3 * i + 1], u[3 * i + 2]);
+        if (a.z > 0.f && o.z > 0.f) weight = bsdf_f(P, a.z, o.z, cos_dphi(a.z, o.z, dot3(a, o))) * ERTB_PI;
+    }
     wo[3 * i] = o.x; wo[3 * i + 1] = o.y; wo[3 * i + 2] = o.z;
     w[i] = weight;
 }
@@ -675,9 +707,9 @@ int ertb_kat_bsdf_eval(ertb_scene *S, size_t n, const float *wi, const float *wo
 int ertb_kat_bsdf_sample(ertb_scene *S, size_t n, const float *wi, const float *u, float *wo, float *weight) {
     if (kat_prepare(S)) return 1;
     DevBuf<float> a, b, o, w;
-    if (a.alloc(3 * n) || b.alloc(2 * n) || o.alloc(3 * n) || w.alloc(n)) return set_error("cudaMalloc failed");
+    if (a.alloc(3 * n) || b.alloc(3 * n) || o.alloc(3 * n) || w.alloc(n)) return set_error("cudaMalloc failed");
     CUDA_TRY(cudaMemcpy(a.p, wi, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(b.p, u, 2 * n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.p, u, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
     kat_bsdf_sample_kernel<<<KAT_GRID(n)>>>(S->base, n, a.p, b.p, o.p, w.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(wo, o.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));

@@ -72,7 +72,7 @@ struct ErtbParams {
     // surface
     int bsdf_type;
     float bsdf[ERTB_MAX_BSDF_PARAMS];
-    int off_ocean;    // ocean tables in the blob (-1 if unused)
+    const float *ocean_tables; // ocean_legacy: [2][64*64] down/up-welling transmittance (global memory)
     // emitter
     float sun[3];     // unit vector pointing towards the sun (= -emitter direction)
     float irradiance;

@@ -23,6 +23,7 @@
 #pragma once
 
 #include "ertb_device.cuh"
+#include "ertb_ocean.cuh"
 
 enum : int {
     MODE_IDLE = 0,
@@ -161,6 +162,63 @@ __device__ __forceinline__ int primary_entry_sph(const ErtbParams &P, double tx,
     double inv = 1.0 / P.Rd;
     n0 = mk3((float) ((ox + t0 * dx) * inv), (float) ((oy + t0 * dy) * inv), (float) ((oz + t0 * dz) * inv));
     return 2;
+}
+
+// Local shading frame of the ground: ERP/shapes/arectangle.cpp (world x, y) for the slab,
+// MI/src/shapes/sphere.cpp:703-720 + interaction.h:278-288 (s = normalised dp_du = east) for the
+// sphere.  Only the ocean BSDF (wind direction) depends on it.
+template <bool SPH>
+__device__ __forceinline__ void surface_frame(f3 n, f3 &s, f3 &t) {
+    if (SPH) {
+        float rd2 = n.x * n.x + n.y * n.y;
+        if (rd2 > 0.f) {
+            float inv = rsqrtf(rd2);
+            s = mk3(-n.y * inv, n.x * inv, 0.f);
+            t = mk3(n.y * s.z - n.z * s.y, n.z * s.x - n.x * s.z, n.x * s.y - n.y * s.x);
+        } else {
+            onb(n, s, t);
+        }
+    } else {
+        s = mk3(1.f, 0.f, 0.f);
+        t = mk3(0.f, 1.f, 0.f);
+    }
+}
+
+// Surface interaction (volpath.cpp:344-375): BSDF value towards the sun for next-event
+// estimation (`f_sun` = f * cos, 0 when not wanted) and BSDF sampling (new direction `d`,
+// weight = f * cos / pdf).  `ci` = cos of the incident direction with the normal (> 0).
+template <bool SPH>
+__device__ __forceinline__ void surface_interact(const ErtbParams &P, f3 n0, f3 sun, float ci, bool want_nee,
+                                                 Pcg32 &rng, f3 &d, float &f_sun, float &weight) {
+    f_sun = 0.f;
+    weight = 0.f;
+    if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+        f3 fs, ft;
+        surface_frame<SPH>(n0, fs, ft);
+        f3 wi = mk3(-dot3(d, fs), -dot3(d, ft), ci);
+        if (want_nee) {
+            f3 ws = mk3(dot3(sun, fs), dot3(sun, ft), dot3(sun, n0));
+            if (ws.z > 0.f) f_sun = oc_eval(P, wi, ws);
+        }
+        float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
+        f3 wo;
+        weight = oc_sample(P, wi, s1, u1, u2, wo);
+        if (!(wo.z > 0.f)) weight = 0.f;
+        d = normalize3(fma3(fs, wo.x, fma3(ft, wo.y, scale3(n0, wo.z))));
+        return;
+    }
+    if (want_nee) {
+        float co = dot3(n0, sun);
+        if (co > 0.f) f_sun = bsdf_f(P, ci, co, cos_dphi(ci, co, -dot3(d, sun))) * co;
+    }
+    float u1 = pcg_float(rng), u2 = pcg_float(rng);
+    f3 wl = cosine_hemisphere(u1, u2);
+    f3 fs, ft;
+    onb(n0, fs, ft);
+    f3 nd = fma3(fs, wl.x, fma3(ft, wl.y, scale3(n0, wl.z)));
+    if (wl.z > 0.f) // value * cos / pdf = value * pi   (rpv.cpp:119-122)
+        weight = bsdf_f(P, ci, wl.z, cos_dphi(ci, wl.z, -dot3(d, nd))) * ERTB_PI;
+    d = normalize3(nd);
 }
 
 template <bool SPH, bool STATS>
@@ -461,26 +519,12 @@ __global__ void __launch_bounds__(ERTB_BLOCK, ERTB_MINB) ertb_render_kernel(cons
                     thr = 0.f;
                     mode = MODE_SETUP_MAIN;
                 } else {
-                    wnee = 0.f;
-                    if (depth + 1u < P.max_depth) {
-                        float co = dot3(n0, sun);
-                        if (co > 0.f) {
-                            float f = bsdf_f(P, ci, co, cos_dphi(ci, co, -dot3(d, sun)));
-                            wnee = thr * f * co * P.irradiance;
-                        }
-                    }
+                    float f_sun, weight;
+                    surface_interact<SPH>(P, n0, sun, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
+                    wnee = thr * f_sun * P.irradiance;
                     if (vacuum) { // no medium on either leg: the sample is the direct surface term
                         res += wnee; wnee = 0.f; thr = 0.f;
                     }
-                    float u1 = pcg_float(rng), u2 = pcg_float(rng);
-                    f3 wl = cosine_hemisphere(u1, u2);
-                    f3 fs, ft;
-                    onb(n0, fs, ft);
-                    f3 nd = fma3(fs, wl.x, fma3(ft, wl.y, scale3(n0, wl.z)));
-                    float weight = 0.f;
-                    if (wl.z > 0.f) // value * cos / pdf = value * pi   (rpv.cpp:119-122)
-                        weight = bsdf_f(P, ci, wl.z, cos_dphi(ci, wl.z, -dot3(d, nd))) * ERTB_PI;
-                    d = normalize3(nd);
                     thr *= weight;
                     depth++;
                     last_null = false;

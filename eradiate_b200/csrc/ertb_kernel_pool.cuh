@@ -376,22 +376,10 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                 if (!(ci > 0.f) || P.bsdf_type == ERTB_BSDF_BLACK) {
                     thr = 0.f; dead = true;
                 } else {
-                    if (depth + 1u < P.max_depth) {
-                        float co = dot3(n0, sun);
-                        if (co > 0.f) {
-                            float f = bsdf_f(P, ci, co, cos_dphi(ci, co, -dot3(d, sun)));
-                            wnee = thr * f * co * P.irradiance;
-                        }
-                    }
+                    float f_sun, weight;
+                    surface_interact<SPH>(P, n0, sun, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
+                    wnee = thr * f_sun * P.irradiance;
                     if (flags & PFL_VACUUM) { res += wnee; wnee = 0.f; thr = 0.f; dead = true; }
-                    float u1 = pcg_float(rng), u2 = pcg_float(rng);
-                    f3 wl = cosine_hemisphere(u1, u2);
-                    f3 fs, ft;
-                    onb(n0, fs, ft);
-                    f3 nd = fma3(fs, wl.x, fma3(ft, wl.y, scale3(n0, wl.z)));
-                    float weight = 0.f;
-                    if (wl.z > 0.f) weight = bsdf_f(P, ci, wl.z, cos_dphi(ci, wl.z, -dot3(d, nd))) * ERTB_PI;
-                    d = normalize3(nd);
                     thr *= weight;
                     depth++;
                 }

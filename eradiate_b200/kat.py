@@ -37,7 +37,7 @@ def bsdf_eval(scene, wi, wo):
 def bsdf_sample(scene, wi, u):
     dev = _device_scene(scene)
     dev.sync()
-    wi, u = _f(wi).reshape(-1, 3), _f(u).reshape(-1, 2)
+    wi, u = _f(wi).reshape(-1, 3), _f(u).reshape(-1, 3)
     wo = np.zeros_like(wi)
     w = np.zeros(wi.shape[0], dtype=np.float32)
     _lib.check(dev.lib.ertb_kat_bsdf_sample(dev.handle, wi.shape[0], _fp(wi), _fp(u), _fp(wo), _fp(w)))

@@ -403,6 +403,8 @@ class _Loader:
             b.values["pigmentation"] = float(d.get("pigmentation", 0.3))
             b.values["shadowing"] = bool(d.get("shadowing", True))
             b.component = int(d.get("component", 0))
+            if b.component != 0:
+                raise RuntimeError("ocean_legacy: only component=0 (full BRDF) is supported")
         return b
 
     def make_medium(self, d, oid) -> Medium:

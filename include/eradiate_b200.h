@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 3
+#define ERTB_ABI_VERSION 4
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -52,8 +52,8 @@ enum ertb_bsdf_type {
     ERTB_BSDF_RTLS = 2,         /* ERP/bsdfs/rtls.cpp:86-293;  params: f_iso, f_vol, f_geo, h, r, b */
     ERTB_BSDF_HAPKE = 3,        /* ERP/bsdfs/hapke.cpp:93-381; params: w, b, c, theta(deg), B_0, h */
     ERTB_BSDF_OCEAN_LEGACY = 4, /* ERP/bsdfs/ocean_legacy.cpp; params: wavelength(nm), wind_speed,
-                                   wind_direction(deg), chlorinity, pigmentation, shadowing(0/1),
-                                   then 5 host-derived scalars, see _scene.py */
+                                   wind_direction(deg, North-left), chlorinity, pigmentation,
+                                   shadowing(0/1), component (only 0) */
     ERTB_BSDF_BLACK = 5         /* reflectance 0 (no surface contribution) */
 };
 
@@ -223,7 +223,8 @@ int ertb_sensor_pixel_count(const ertb_scene *scene, int sensor);
 /* Known-answer-test entry points: evaluate the device implementations of the
  * plugins point-wise (one thread per query).  Host pointers.
  *   bsdf_eval  : wi, wo local-frame unit vectors (3*n); out = f * cos(theta_o) (n)
- *   bsdf_sample: wi (3*n), u (2*n) -> wo (3*n), weight (n)
+ *   bsdf_sample: wi (3*n), u (3*n: lobe-selection sample1, then sample2.x, sample2.y)
+ *                -> wo (3*n), weight (n)
  *   phase_eval : leaf index, cos between wo and wi ("graphics" convention, n) -> out (n)
  *   phase_sample: leaf index, u (2*n) -> cos_theta of wo w.r.t. propagation dir (n), weight (n), pdf (n)
  *   sensor_ray : film sample (2*n) + aperture sample (2*n) -> origin (3*n) dir (3*n) weight (n) */

@@ -845,6 +845,24 @@ static double sensor_sample_ray(const scene_t *S, const ertb_sensor_desc *sd, do
 /* ----------------------------------------------------------- integrator */
 typedef struct { uint64_t trips_main, trips_nee, n_scatter, n_surface; } counters_t;
 
+/* Shading frame of a surface hit: SurfaceInteraction::initialize_sh_frame
+ * (MI/include/mitsuba/render/interaction.h:278-288) with the sphere's dp_du = (-y, x, 0) 2 pi
+ * (MI/src/shapes/sphere.cpp:703-720) or the rectangle's dp_du = to_world * (2, 0, 0).  Only
+ * the ocean BSDF (absolute wind direction) is sensitive to it. */
+static frame_t surface_frame(const scene_t *S, const si_t *si) {
+    frame_t f;
+    f.n = si->n;
+    if (S->spherical) {
+        v3 dp_du = V(-si->p.y, si->p.x, 0.0);
+        if (dp_du.x == 0.0 && dp_du.y == 0.0) return make_frame(si->n);
+        f.s = vnormalize(vfma(si->n, -vdot(si->n, dp_du), dp_du));
+    } else {
+        f.s = V(1, 0, 0);
+    }
+    f.t = V(f.n.y * f.s.z - f.n.z * f.s.y, f.n.z * f.s.x - f.n.x * f.s.z, f.n.x * f.s.y - f.n.y * f.s.x);
+    return f;
+}
+
 static int target_medium(v3 n, v3 d) { return vdot(d, n) > 0.0 ? 0 : 1; } /* interaction.h:318-332 */
 
 /* volpath.cpp:400-554 sample_emitter: ratio tracking toward the directional emitter.
@@ -993,7 +1011,7 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t
         if (active_surface && needs_intersection) si = scene_intersect(S, &ray);
         active_surface = active_surface && si.t < INFINITY;
         if (active_surface) {
-            frame_t fr = make_frame(si.n);
+            frame_t fr = surface_frame(S, &si);
             v3 wi = to_local(&fr, vneg(ray.d));
             v3 wo_world;
             if (si.shape == SHAPE_TOA) { /* null.cpp:41-87 */

@@ -43,6 +43,17 @@ def battery() -> dict:
         "distantflux_no_target_spherical": S(n_layers=100,
                                              sensor={"type": "distantflux", "film_resolution": (2, 2),
                                                      "target": None}),
+        # ocean_legacy (6SV): glint + whitecaps + underlight, wind direction relative to the frame
+        "ocean_pp": S(geometry="plane_parallel", n_layers=100, sza=35.0, saa=20.0,
+                      surface={"type": "ocean_legacy", "wavelength": 550.0, "wind_speed": 8.0,
+                               "wind_direction": 40.0, "chlorinity": 19.0, "pigmentation": 0.3,
+                               "shadowing": True},
+                      sensor={"type": "mdistant", "vza": [-60.0, -35.0, 0.0, 35.0, 60.0], "vaa": 20.0}),
+        "ocean_spherical_nir": S(n_layers=100, sza=35.0, w_nm=865.0,
+                                 surface={"type": "ocean_legacy", "wavelength": 865.0, "wind_speed": 3.0,
+                                          "wind_direction": 0.0, "shadowing": False},
+                                 sensor={"type": "mdistant", "vza": [-50.0, -35.0, -20.0, 20.0, 50.0],
+                                         "vaa": 0.0, "target": [0.0, 3.0e5, 6.3710484e6]}),
         # integrator options
         "volpathmis_thick": S(geometry="plane_parallel", atmosphere="homogeneous", integrator="volpathmis",
                               homogeneous_sigma_t=3.0 / scenes.TOA, homogeneous_albedo=0.95, sensor=VZA5,

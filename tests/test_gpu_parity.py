@@ -46,6 +46,8 @@ def load(surface=None, phase=None, **kw):
     {"type": "rtls"},
     {"type": "rtls", "f_iso": 0.3, "f_vol": 0.2, "f_geo": 0.05, "h": 1.5, "r": 1.2, "b": 0.9},
     {"type": "hapke", **POMMEROL},
+    {"type": "ocean_legacy", "wavelength": 550.0, "wind_speed": 8.0, "wind_direction": 40.0, "shadowing": True},
+    {"type": "ocean_legacy", "wavelength": 1500.0, "wind_speed": 1.0, "wind_direction": 90.0, "shadowing": False},
 ])
 def test_bsdf_eval_and_sample_match_oracle(oracle, bsdf):
     sc = load(surface=bsdf)
@@ -56,17 +58,44 @@ def test_bsdf_eval_and_sample_match_oracle(oracle, bsdf):
     wo = sph_to_dir(rng.uniform(0.0, 1.45, n), rng.uniform(0, 2 * np.pi, n)).astype(np.float32)
     got = kat.bsdf_eval(sc, wi, wo)
     ref = oracle.bsdf_eval(desc, wi, wo)
-    # fp32 with fast intrinsics (__powf, __fdividef) vs fp64: 2e-4 relative
-    assert np.allclose(got, ref, rtol=2e-4, atol=1e-7), np.max(np.abs(got - ref) / np.abs(ref))
-    u = rng.uniform(0, 1, (n, 2)).astype(np.float32)
+    ocean = bsdf["type"] == "ocean_legacy"
+    # fp32 with fast intrinsics (__powf, __fdividef) vs fp64: 2e-4 relative (ocean: the glint lobe
+    # exp(-tan^2/alpha^2) amplifies fp32 rounding of the half-vector at low wind speed -> 2e-3)
+    assert np.allclose(got, ref, rtol=2e-3 if ocean else 2e-4, atol=1e-6 if ocean else 1e-7), \
+        np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6))
+    u = rng.uniform(0, 1, (n, 3)).astype(np.float32)
     wo_g, w_g = kat.bsdf_sample(sc, wi, u)
-    wo_o, w_o = oracle.bsdf_sample(desc, wi, np.concatenate([np.zeros((n, 1)), u], axis=1))
+    wo_o, w_o = oracle.bsdf_sample(desc, wi, u)
+    if ocean:
+        # visible-normal sampling inverts erf with 3 Newton steps in fp32: compare directions loosely
+        # and the weights only where the sampled lobe agrees
+        same = np.linalg.norm(wo_g - wo_o, axis=1) < 2e-3
+        assert same.mean() > 0.995
+        ok = same & (wo_o[:, 2] > 0.05)
+        assert np.allclose(w_g[ok], w_o[ok], rtol=2e-2, atol=1e-4)
+        return
     assert np.allclose(wo_g, wo_o, atol=1e-5)  # __sincosf / __fdividef in the concentric map
     ok = wo_o[:, 2] > 0.02  # weights near the horizon amplify the fp32 direction error
     assert np.allclose(w_g[ok], w_o[ok], rtol=5e-4, atol=1e-7)
     # below-horizon configurations evaluate to zero (rpv.cpp:174-180)
     down = sph_to_dir([2.0], [0.3]).astype(np.float32)
     assert kat.bsdf_eval(sc, down, wo[:1])[0] == 0.0 and kat.bsdf_eval(sc, wi[:1], down)[0] == 0.0
+
+
+def test_ocean_6sv_golden_on_device():
+    # ERP/tests/bsdfs/test_ocean_legacy.py:52-101 evaluated by the CUDA implementation
+    base = dict(type="ocean_legacy", component=0, wavelength=1500.0, wind_speed=1.0, wind_direction=90.0,
+                chlorinity=19.0, pigmentation=0.3, shadowing=False)
+    vza = np.deg2rad([0.0, 22.475, 44.95, 67.425, 89.9])
+    wi = sph_to_dir(vza, np.zeros(5))
+    wo = sph_to_dir(np.full(5, np.deg2rad(22.475)), np.zeros(5))
+    for override, golden in (
+        ({}, [1.91408132e-03, -5.44804487e-08, -5.45187861e-08, -5.45187861e-08, -5.45187861e-08]),
+        ({"wavelength": 550.0, "wind_speed": 30.0}, [0.11300096, 0.10733355, 0.10722339, 0.1055309, 0.11909937]),
+    ):
+        sc = load(surface={**base, **override})
+        val = kat.bsdf_eval(sc, wi, wo) * np.pi
+        assert np.allclose(val, golden, rtol=1e-3, atol=1e-4), val
 
 
 def test_hapke_golden_on_device():

@@ -416,3 +416,39 @@ def test_grid_nearest_layer_convention_piecewise_golden(oracle):
     for dist, tr in zip(gt_dists, gt_trs):
         got = np.interp(-np.log(tr), tau, H - zs)
         assert np.allclose(got, dist, rtol=2e-5), (got, dist)
+
+
+# ------------------------------------------------------------------------ ocean_legacy
+OCEAN = dict(type="ocean_legacy", component=0, wavelength=1500.0, wind_speed=1.0, wind_direction=90.0,
+             chlorinity=19.0, pigmentation=0.3, shadowing=False)
+
+
+@pytest.mark.parametrize("override,golden", [
+    # ERP/tests/bsdfs/test_ocean_legacy.py:52-101 (6SV reference values, rtol 1e-3, atol 1e-4)
+    ({}, [1.91408132e-03, -5.44804487e-08, -5.45187861e-08, -5.45187861e-08, -5.45187861e-08]),
+    ({"wavelength": 550.0, "wind_speed": 30.0}, [0.11300096, 0.10733355, 0.10722339, 0.1055309, 0.11909937]),
+])
+def test_ocean_legacy_6sv_golden(oracle, override, golden):
+    _, desc = make_desc(surface={**OCEAN, **override})
+    vza = np.deg2rad([0.0, 22.475, 44.95, 67.425, 89.9])
+    wi = sph_to_dir(vza, np.zeros(5))                      # si.wi = view directions
+    wo = sph_to_dir(np.full(5, np.deg2rad(22.475)), np.zeros(5))  # wo = sun direction
+    val = oracle.bsdf_eval(desc, wi, wo) * np.pi
+    assert np.allclose(val, golden, rtol=1e-3, atol=1e-4), val
+
+
+def test_ocean_legacy_sample_pdf_consistency(oracle):
+    """chi^2-style check of ERP/tests/bsdfs/test_ocean_legacy.py:18-33: the sampled directions
+    follow pdf(): E[eval/pdf] over sample() equals the hemispherical integral of eval."""
+    _, desc = make_desc(surface={**OCEAN, "wavelength": 550.0, "wind_speed": 10.0, "shadowing": True})
+    rng = np.random.default_rng(12)
+    wi = sph_to_dir([np.deg2rad(35.0)], [0.4])
+    n = 200000
+    wo, w = oracle.bsdf_sample(desc, np.repeat(wi, n, axis=0), rng.uniform(0, 1, (n, 3)))
+    assert np.all(np.isfinite(w)) and np.all(w >= 0)
+    est = w.mean()
+    # reference integral by uniform-hemisphere quadrature of eval()
+    u = rng.uniform(0, 1, (n, 2))
+    d = oracle.warp("uniform_hemisphere", u[:, 0], u[:, 1])
+    ref = (oracle.bsdf_eval(desc, np.repeat(wi, n, axis=0), d) * 2 * np.pi)
+    assert abs(est - ref.mean()) < 5 * np.sqrt(w.var() / n + ref.var() / n), (est, ref.mean())
