@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -33,6 +33,8 @@ PHASE_RAYLEIGH = 1
 PHASE_HG = 2
 PHASE_TABULATED = 3
 PHASE_TABULATED_IRREGULAR = 4
+PHASE_RAYLEIGH_POLARIZED = 5
+PHASE_TABULATED_POLARIZED = 6
 
 # enum ertb_sensor_type
 SENSOR_MDISTANT = 0
@@ -69,6 +71,7 @@ class PhaseDesc(C.Structure):
         ("params", C.c_float * 4),
         ("values", c_float_p),
         ("nodes", c_float_p),
+        ("mueller", c_float_p * 5),
     ]
 
 
@@ -116,6 +119,8 @@ class SceneDesc(C.Structure):
         ("integrator", C.c_int32),
         ("rr_depth", C.c_int32),
         ("max_depth", C.c_int64),
+        ("polarized", C.c_int32),
+        ("meridian_align", C.c_int32),
         ("n_sensors", C.c_int32),
         ("_pad4", C.c_int32),
         ("sensors", C.POINTER(SensorDesc)),
@@ -159,10 +164,12 @@ EXPORTED_SYMBOLS = (
     "ertb_scene_update",
     "ertb_render",
     "ertb_render_device",
+    "ertb_render_stokes",
     "ertb_sensor_pixel_count",
     "ertb_kat_bsdf_eval",
     "ertb_kat_bsdf_sample",
     "ertb_kat_phase_eval",
     "ertb_kat_phase_sample",
+    "ertb_kat_phase_mueller",
     "ertb_kat_sensor_ray",
 )

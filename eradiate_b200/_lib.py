@@ -43,6 +43,8 @@ def load() -> C.CDLL:
     lib.ertb_scene_update.argtypes = [vp, i32, i32, fp, C.c_size_t]
     lib.ertb_render.argtypes = [vp, i32, u64, u64, u64, dp, dp, dp, C.POINTER(_abi.RenderStats)]
     lib.ertb_render_device.argtypes = [vp, i32, u64, u64, u64, vp, vp, vp]
+    lib.ertb_render_stokes.argtypes = [vp, i32, u64, u64, u64, dp, dp, dp, dp, C.POINTER(_abi.RenderStats)]
+    lib.ertb_kat_phase_mueller.argtypes = [vp, i32, C.c_size_t, fp, fp, fp, fp]
     lib.ertb_sensor_pixel_count.argtypes = [vp, i32]
     lib.ertb_kat_bsdf_eval.argtypes = [vp, C.c_size_t, fp, fp, fp]
     lib.ertb_kat_bsdf_sample.argtypes = [vp, C.c_size_t, fp, fp, fp, fp]

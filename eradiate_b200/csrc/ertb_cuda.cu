@@ -36,6 +36,7 @@ struct HostPhase {
     int type = 0;
     float params[4] = { 0, 0, 0, 0 };
     std::vector<float> values, nodes;
+    std::vector<float> mueller[5]; // tabulated_polarized: m12, m22, m33, m34, m44
 };
 
 struct HostSensor {
@@ -63,6 +64,7 @@ struct ertb_scene {
     float irradiance = 1.f;
     int integrator = 0, rr_depth = 5;
     long long max_depth = -1;
+    int polarized = 0, meridian_align = 0;
     std::vector<HostSensor> sensors;
 
     // derived / device state
@@ -88,7 +90,7 @@ static size_t align4(size_t n) { return (n + 3) & ~size_t(3); }
 // distr_1d.h:548-600 compute_cdf_scalar: trapezoid CDF accumulated in double
 static void build_tab_leaf(const HostPhase &hp, ErtbPhaseLeaf &L, std::vector<float> &blob) {
     const int n = (int) hp.values.size();
-    const bool irregular = hp.type == ERTB_PHASE_TABULATED_IRREGULAR;
+    const bool irregular = hp.type != ERTB_PHASE_TABULATED;
     L.n_nodes = n;
     L.inv_interval = (float) ((n - 1) / 2.0);
     L.off_pdf = (int) blob.size();
@@ -120,6 +122,17 @@ static void build_tab_leaf(const HostPhase &hp, ErtbPhaseLeaf &L, std::vector<fl
         blob.insert(blob.end(), hp.nodes.begin(), hp.nodes.end());
         blob.resize(align4(blob.size()), 0.f);
     }
+    L.off_mueller = -1;
+    L.mueller_stride = 0;
+    if (hp.type == ERTB_PHASE_TABULATED_POLARIZED) {
+        L.off_mueller = (int) blob.size();
+        L.mueller_stride = (int) align4((size_t) n);
+        for (int k = 0; k < 5; ++k) {
+            size_t start = blob.size();
+            if ((int) hp.mueller[k].size() == n) blob.insert(blob.end(), hp.mueller[k].begin(), hp.mueller[k].end());
+            blob.resize(start + L.mueller_stride, 0.f);
+        }
+    }
 }
 
 static int validate_tab(const HostPhase &hp) {
@@ -132,7 +145,7 @@ static int validate_tab(const HostPhase &hp) {
         if (hp.values[i] > 0.f) mass = true;
     }
     if (!mass) return set_error("ContinuousDistribution: no probability mass found!");
-    if (hp.type == ERTB_PHASE_TABULATED_IRREGULAR) {
+    if (hp.type != ERTB_PHASE_TABULATED) {
         if ((int) hp.nodes.size() != n) return set_error("'nodes' and 'values' must have the same length");
         for (int i = 0; i < n - 1; ++i)
             if (!(hp.nodes[i + 1] > hp.nodes[i]))
@@ -193,7 +206,9 @@ static int scene_commit(ertb_scene *S) {
             L.type = hp.type;
             L.p0 = hp.params[0];
             L.off_nodes = -1;
-            if (hp.type == ERTB_PHASE_TABULATED || hp.type == ERTB_PHASE_TABULATED_IRREGULAR) {
+            L.off_mueller = -1;
+            if (hp.type == ERTB_PHASE_TABULATED || hp.type == ERTB_PHASE_TABULATED_IRREGULAR ||
+                hp.type == ERTB_PHASE_TABULATED_POLARIZED) {
                 if (validate_tab(hp)) return 1;
                 build_tab_leaf(hp, L, blob);
             }
@@ -240,6 +255,8 @@ static int scene_commit(ertb_scene *S) {
                      S->emitter_dir[2] * S->emitter_dir[2]);
     for (int i = 0; i < 3; ++i) P.sun[i] = (float) (-S->emitter_dir[i] / dn);
     P.irradiance = S->irradiance;
+    P.polarized = S->polarized;
+    P.meridian_align = S->meridian_align;
     P.mis = S->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
     P.rr_depth = (unsigned) S->rr_depth;
     P.max_depth = S->max_depth < 0 ? 0xffffffffu : (unsigned) S->max_depth;
@@ -400,14 +417,18 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
             HostPhase &hp = S->phase[k];
             hp.type = pd.type;
             memcpy(hp.params, pd.params, sizeof hp.params);
-            if (pd.type == ERTB_PHASE_TABULATED || pd.type == ERTB_PHASE_TABULATED_IRREGULAR) {
+            if (pd.type == ERTB_PHASE_TABULATED || pd.type == ERTB_PHASE_TABULATED_IRREGULAR ||
+                pd.type == ERTB_PHASE_TABULATED_POLARIZED) {
                 if (!pd.values || pd.n_nodes < 2) { delete S; return set_error("tabulated phase: values missing"); }
                 hp.values.assign(pd.values, pd.values + pd.n_nodes);
-                if (pd.type == ERTB_PHASE_TABULATED_IRREGULAR) {
+                if (pd.type != ERTB_PHASE_TABULATED) {
                     if (!pd.nodes) { delete S; return set_error("tabulated phase: nodes missing"); }
                     hp.nodes.assign(pd.nodes, pd.nodes + pd.n_nodes);
                 }
-            } else if (pd.type < 0 || pd.type > ERTB_PHASE_TABULATED_IRREGULAR) {
+                if (pd.type == ERTB_PHASE_TABULATED_POLARIZED)
+                    for (int m = 0; m < 5; ++m)
+                        if (pd.mueller[m]) hp.mueller[m].assign(pd.mueller[m], pd.mueller[m] + pd.n_nodes);
+            } else if (pd.type < 0 || pd.type > ERTB_PHASE_TABULATED_POLARIZED) {
                 delete S;
                 return set_error("unsupported phase function type");
             }
@@ -420,6 +441,16 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
     S->integrator = D->integrator;
     S->rr_depth = D->rr_depth;
     S->max_depth = D->max_depth;
+    S->polarized = D->polarized != 0;
+    S->meridian_align = D->meridian_align != 0;
+    if (S->polarized && D->integrator == ERTB_INTEGRATOR_VOLPATHMIS) {
+        delete S;
+        return set_error("This integrator currently does not support polarized mode!"); // volpathmis.cpp:130-132
+    }
+    if (S->polarized && D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+        delete S;
+        return set_error("ocean_legacy in polarized mode is not implemented yet");
+    }
 
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete S; return set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
@@ -520,6 +551,8 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     ErtbParams P = S->base;
     const HostSensor &hs = S->sensors[sensor];
     fill_sensor_params(S, hs, P.sensor);
+    if (hs.desc.type == ERTB_SENSOR_MDISTANT) { P.sensor_up[0] = 0.f; P.sensor_up[1] = 1.f; P.sensor_up[2] = 0.f; }
+    else { P.sensor_up[0] = (float) hs.desc.to_world[1]; P.sensor_up[1] = (float) hs.desc.to_world[5]; P.sensor_up[2] = (float) hs.desc.to_world[9]; }
     P.seed = seed;
     P.spp = spp;
     P.sample_offset = sample_offset;
@@ -535,8 +568,11 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     if (const char *e = getenv("ERTB_KERNEL")) use_pool = strcmp(e, "legacy") != 0;
     int blocks_per_sm = 0;
     const int block = use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK;
-    size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes) : (size_t) S->base.blob_bytes;
+    const bool pol = S->polarized != 0;
+    if (pol) use_pool = true; // the polarized path exists in the pool kernel only
+    size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol) : (size_t) S->base.blob_bytes;
     if (use_pool && smem > (size_t) S->max_smem_optin) { // huge tables: fall back to the register kernel
+        if (pol) return set_error("scene tables leave no shared memory for the polarized path pools");
         use_pool = false;
         smem = (size_t) S->base.blob_bytes;
     }
@@ -547,9 +583,12 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     } while (0)
 #define ERTB_DISPATCH(MACRO)                                                                          \
     do {                                                                                              \
-        if (use_pool) {                                                                               \
-            if (sph) { if (with_stats) MACRO((ertb_render_pool_kernel<true, true>)); else MACRO((ertb_render_pool_kernel<true, false>)); } \
-            else     { if (with_stats) MACRO((ertb_render_pool_kernel<false, true>)); else MACRO((ertb_render_pool_kernel<false, false>)); } \
+        if (use_pool && pol) {                                                                        \
+            if (sph) { if (with_stats) MACRO((ertb_render_pool_kernel<true, true, true>)); else MACRO((ertb_render_pool_kernel<true, false, true>)); } \
+            else     { if (with_stats) MACRO((ertb_render_pool_kernel<false, true, true>)); else MACRO((ertb_render_pool_kernel<false, false, true>)); } \
+        } else if (use_pool) {                                                                        \
+            if (sph) { if (with_stats) MACRO((ertb_render_pool_kernel<true, true, false>)); else MACRO((ertb_render_pool_kernel<true, false, false>)); } \
+            else     { if (with_stats) MACRO((ertb_render_pool_kernel<false, true, false>)); else MACRO((ertb_render_pool_kernel<false, false, false>)); } \
         } else {                                                                                      \
             if (sph) { if (with_stats) MACRO((ertb_render_kernel<true, true>)); else MACRO((ertb_render_kernel<true, false>)); } \
             else     { if (with_stats) MACRO((ertb_render_kernel<false, true>)); else MACRO((ertb_render_kernel<false, false>)); } \
@@ -591,11 +630,18 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
 
 int ertb_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, uint64_t sample_offset,
                 double *sum_wl, double *sum_l, double *sum_l2, ertb_render_stats *stats) {
+    return ertb_render_stokes(S, sensor, seed, spp, sample_offset, sum_wl, sum_l, sum_l2, nullptr, stats);
+}
+
+int ertb_render_stokes(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, uint64_t sample_offset,
+                       double *sum_wl, double *sum_l, double *sum_l2, double *sum_stokes,
+                       ertb_render_stats *stats) {
     if (!S) return set_error("null scene");
     int npix = ertb_sensor_pixel_count(S, sensor);
     if (npix <= 0) return set_error("invalid sensor index");
     CUDA_TRY(cudaSetDevice(S->device));
-    size_t bytes = (size_t) 3 * npix * sizeof(double);
+    const int rows = S->polarized ? 7 : 3;
+    size_t bytes = (size_t) rows * npix * sizeof(double);
     if (bytes > S->d_accum_capacity) {
         if (S->d_accum) cudaFree(S->d_accum);
         CUDA_TRY(cudaMalloc(&S->d_accum, bytes));
@@ -607,8 +653,12 @@ int ertb_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, uint64_t
     CUDA_TRY(cudaEventRecord(S->ev0, 0));
     if (launch_render(S, sensor, seed, spp, sample_offset, S->d_accum, d_stats, 0, stats != nullptr)) return 1;
     CUDA_TRY(cudaEventRecord(S->ev1, 0));
-    std::vector<double> host((size_t) 3 * npix);
+    std::vector<double> host((size_t) rows * npix);
     CUDA_TRY(cudaMemcpy(host.data(), S->d_accum, bytes, cudaMemcpyDeviceToHost));
+    if (sum_stokes) {
+        if (S->polarized) memcpy(sum_stokes, host.data() + 3 * (size_t) npix, 4 * (size_t) npix * sizeof(double));
+        else memset(sum_stokes, 0, 4 * (size_t) npix * sizeof(double));
+    }
     if (sum_wl) memcpy(sum_wl, host.data(), npix * sizeof(double));
     if (sum_l) memcpy(sum_l, host.data() + npix, npix * sizeof(double));
     if (sum_l2) memcpy(sum_l2, host.data() + 2 * (size_t) npix, npix * sizeof(double));
@@ -678,6 +728,15 @@ __global__ void kat_phase_sample_kernel(ErtbParams P, int leaf, size_t n, const 
     pdf[i] = pp;
 }
 
+__global__ void kat_phase_mueller_kernel(ErtbParams P, int leaf, size_t n, const float *wi, const float *wo, float *M, float *pdf) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m[16], pp;
+    leaf_mueller(P.blob, P.leaf[leaf], mk3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), mk3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), m, pp);
+    for (int k = 0; k < 16; ++k) M[16 * i + k] = m[k];
+    pdf[i] = pp;
+}
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -737,6 +796,20 @@ int ertb_kat_phase_sample(ertb_scene *S, int leaf, size_t n, const float *u, flo
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(ct, c.p, n * sizeof(float), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(weight, w.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(pdf, p.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ertb_kat_phase_mueller(ertb_scene *S, int leaf, size_t n, const float *wi, const float *wo, float *mueller, float *pdf) {
+    if (kat_prepare(S)) return 1;
+    if (leaf < 0 || leaf >= S->n_phase) return set_error("invalid phase leaf index");
+    DevBuf<float> a, b, m, p;
+    if (a.alloc(3 * n) || b.alloc(3 * n) || m.alloc(16 * n) || p.alloc(n)) return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(a.p, wi, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.p, wo, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+    kat_phase_mueller_kernel<<<KAT_GRID(n)>>>(S->base, leaf, n, a.p, b.p, m.p, p.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(mueller, m.p, 16 * n * sizeof(float), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(pdf, p.p, n * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }

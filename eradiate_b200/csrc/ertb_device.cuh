@@ -32,6 +32,8 @@ struct ErtbPhaseLeaf {
     int off_cdf;
     int off_nodes;  // irregular only (else -1)
     int valid0, valid1; // first / last interval with non-zero mass (distr_1d.h:548-600)
+    int off_mueller;    // tabulated_polarized: m12 | m22 | m33 | m34 | m44, `mueller_stride` floats apart
+    int mueller_stride;
 };
 
 struct ErtbSensor {
@@ -77,6 +79,9 @@ struct ErtbParams {
     float sun[3];     // unit vector pointing towards the sun (= -emitter direction)
     float irradiance;
     // integrator
+    int polarized;    // Mueller/Stokes transport (scalar_mono_polarized variant)
+    int meridian_align; // stokes.cpp: output basis in the meridian plane
+    float sensor_up[3]; // else: sensor world_transform * (0, 1, 0)
     int mis;          // volpathmis Russian-roulette placement
     unsigned rr_depth;
     unsigned max_depth; // 0xffffffff = unbounded
@@ -257,6 +262,7 @@ __device__ __forceinline__ float hg_eval(float g, float ct) {
 __device__ __forceinline__ float leaf_eval(const float *tb, const ErtbPhaseLeaf &L, float ct) {
     switch (L.type) {
         case ERTB_PHASE_ISOTROPIC: return ERTB_INV_FOUR_PI;          // isotropic.cpp:52-58
+        case ERTB_PHASE_RAYLEIGH_POLARIZED:
         case ERTB_PHASE_RAYLEIGH: return rayleigh_eval(ct, L.p0);    // rayleigh.cpp:97-107
         case ERTB_PHASE_HG: return hg_eval(L.p0, ct);                // hg.cpp:92-99
         default: return tab_eval(tb, L, ct) * ERTB_INV_TWO_PI;       // tabphase.cpp:107-118
@@ -272,6 +278,7 @@ __device__ __forceinline__ float leaf_sample(const float *tb, const ErtbPhaseLea
             pdf = ERTB_INV_FOUR_PI;
             return fmaf(-2.f, u, 1.f);
         }
+        case ERTB_PHASE_RAYLEIGH_POLARIZED: // rayleigh_polarized.cpp:133-160: same inversion
         case ERTB_PHASE_RAYLEIGH: { // rayleigh.cpp:75-95: Cardano inversion of the CDF
             float z = 2.f * fmaf(2.f, u, -1.f);
             float tmp = sqrtf(fmaf(z, z, 1.f));

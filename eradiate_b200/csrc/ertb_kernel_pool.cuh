@@ -18,6 +18,7 @@
 #pragma once
 
 #include "ertb_kernel.cuh"
+#include "ertb_polar.cuh"
 
 #ifndef ERTB_POOL_NS
 #define ERTB_POOL_NS 64 // records per warp (multiple of 32)
@@ -32,31 +33,37 @@
 
 enum : int {
     PF_FLAGS = 0, PF_H0, PF_B, PF_S, PF_SMAX, PF_THR, PF_WNEE, PF_RES, PF_RNG0, PF_RNG1, PF_INC0, PF_INC1,
-    PF_B2, PF_SMAX2, PF_N0X, PF_N0Y, PF_N0Z, PF_DX, PF_DY, PF_DZ, PF_PIX, PF_WRAY, PF_COUNT
+    PF_B2, PF_SMAX2, PF_N0X, PF_N0Y, PF_N0Z, PF_DX, PF_DY, PF_DZ, PF_PIX, PF_WRAY, PF_COUNT,
+    // polarized records only: throughput Mueller matrix normalised by its (0,0) entry (PF_THR holds
+    // that entry, so the walk phase is identical in both modes), Q/I U/I V/I of the pending NEE
+    // Stokes vector, and the Q, U, V components of the result (PF_RES holds I)
+    PF_T0 = PF_COUNT, PF_QN0 = PF_T0 + 16, PF_RQ = PF_QN0 + 3, PF_COUNT_POL = PF_RQ + 3
 };
 enum : unsigned {
     PM_DEAD = 0, PM_IDLE = 1, PM_WALK_MAIN = 2, PM_WALK_NEE = 3, PM_SURF = 4, PM_SCAT = 5,
     PFL_MODE_MASK = 7u, PFL_KIND = 8u, PFL_KIND2 = 16u, PFL_LAST_NULL = 32u, PFL_VACUUM = 64u,
+    PFL_NEE_QUV = 128u, // polarized: PF_WNEE holds a finished NEE term whose Q, U, V are still to be added
     PFL_DEPTH_SHIFT = 8
 };
 
-__host__ __device__ inline size_t ertb_pool_smem_bytes(size_t blob_bytes) {
+__host__ __device__ inline size_t ertb_pool_smem_bytes(size_t blob_bytes, bool pol = false) {
     size_t blob = (blob_bytes + 15) & ~size_t(15);
     size_t warps = ERTB_POOL_BLOCK / 32;
-    return blob + warps * (size_t) PF_COUNT * ERTB_POOL_NS * 4 + warps * 32 * 4;
+    return blob + warps * (size_t) (pol ? PF_COUNT_POL : PF_COUNT) * ERTB_POOL_NS * 4 + warps * 32 * 4;
 }
 
-template <bool SPH, bool STATS>
-__global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
+template <bool SPH, bool STATS, bool POL>
+__global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
+    constexpr int NF = POL ? PF_COUNT_POL : PF_COUNT;
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) unsigned long long mbar;
     float *tb = smem; // table blob first
     const unsigned blob_words = ((unsigned) P.blob_bytes + 15u) / 16u * 4u;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    float *wp = smem + blob_words + warp * (PF_COUNT * ERTB_POOL_NS);
+    float *wp = smem + blob_words + warp * (NF * ERTB_POOL_NS);
     unsigned *wpu = reinterpret_cast<unsigned *>(wp);
-    int *list = reinterpret_cast<int *>(smem + blob_words + (ERTB_POOL_BLOCK / 32) * (PF_COUNT * ERTB_POOL_NS)) + warp * 32;
+    int *list = reinterpret_cast<int *>(smem + blob_words + (ERTB_POOL_BLOCK / 32) * (NF * ERTB_POOL_NS)) + warp * 32;
 
     if (P.blob_bytes > 0) tma_stage(tb, P.blob, (unsigned) P.blob_bytes, &mbar);
 
@@ -74,6 +81,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
 
     // lane-local film accumulators, tagged with the pixel they belong to
     double acc_wl = 0.0, acc_l = 0.0, acc_l2 = 0.0;
+    double acc_q = 0.0, acc_u = 0.0, acc_v = 0.0; // polarized: sums of w * (S1, S2, S3)
     unsigned acc_pix = 0xffffffffu;
     // warp-uniform work-queue cursor
     unsigned long long cur_next = 0, cur_end = 0;
@@ -171,12 +179,15 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                         if (STATS) { if (is_main) st_main++; else st_nee++; }
                         float u = pcg_float(rng);
                         s += -__logf(1.f - u) * P.inv_majorant;
+                        bool nee_over = false;
                         if (!(s < smax)) {
                             if (is_main) {
                                 mode = (flags & PFL_KIND) ? PM_SURF : PM_IDLE; // ground hit / left through the TOA
                             } else {
-                                res += wnee; // shadow ray reached the TOA
-                                wnee = 0.f;
+                                res += wnee; // shadow ray reached the TOA (I component)
+                                nee_over = true;
+                                if (POL) flags |= PFL_NEE_QUV; // Q, U, V = wnee * (stored ratios), added by the next event
+                                else wnee = 0.f;
                             }
                         } else {
                             float h = altitude_at<SPH>(P, h0, b, s);
@@ -186,9 +197,10 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                                 else flags |= PFL_LAST_NULL;
                             } else {
                                 wnee *= 1.f - preal; // ratio tracking
+                                nee_over = wnee == 0.f;
                             }
                         }
-                        if (!is_main && wnee == 0.f) {
+                        if (nee_over) {
                             // NEE walk over: continue with the main segment prepared by the event
                             if (thr == 0.f || depth_done) mode = PM_IDLE;
                             else {
@@ -222,14 +234,32 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                             atomicAdd(&P.accum[acc_pix], acc_wl);
                             atomicAdd(&P.accum[P.n_pixels + acc_pix], acc_l);
                             atomicAdd(&P.accum[2u * P.n_pixels + acc_pix], acc_l2);
+                            if (POL) {
+                                atomicAdd(&P.accum[3u * P.n_pixels + acc_pix], acc_wl);
+                                atomicAdd(&P.accum[4u * P.n_pixels + acc_pix], acc_q);
+                                atomicAdd(&P.accum[5u * P.n_pixels + acc_pix], acc_u);
+                                atomicAdd(&P.accum[6u * P.n_pixels + acc_pix], acc_v);
+                            }
                         }
                         acc_wl = acc_l = acc_l2 = 0.0;
+                        acc_q = acc_u = acc_v = 0.0;
                         acc_pix = pix_old;
                     }
                     float r = FLD(PF_RES, slot);
-                    acc_wl += (double) (FLD(PF_WRAY, slot) * r);
+                    float wr = FLD(PF_WRAY, slot);
+                    acc_wl += (double) (wr * r);
                     acc_l += (double) r;
                     acc_l2 += (double) r * (double) r;
+                    if (POL) {
+                        float rq = FLD(PF_RQ, slot), ru = FLD(PF_RQ + 1, slot), rv = FLD(PF_RQ + 2, slot);
+                        if (FLDU(PF_FLAGS, slot) & PFL_NEE_QUV) {
+                            float wn = FLD(PF_WNEE, slot);
+                            rq = fmaf(wn, FLD(PF_QN0, slot), rq);
+                            ru = fmaf(wn, FLD(PF_QN0 + 1, slot), ru);
+                            rv = fmaf(wn, FLD(PF_QN0 + 2, slot), rv);
+                        }
+                        acc_q += (double) (wr * rq); acc_u += (double) (wr * ru); acc_v += (double) (wr * rv);
+                    }
                 }
             }
             // warp-aggregated pops from the chunk queue
@@ -347,6 +377,15 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                 FLD(PF_N0X, slot) = n0.x; FLD(PF_N0Y, slot) = n0.y; FLD(PF_N0Z, slot) = n0.z;
                 FLD(PF_DX, slot) = d.x; FLD(PF_DY, slot) = d.y; FLD(PF_DZ, slot) = d.z;
                 FLDU(PF_PIX, slot) = pix; FLD(PF_WRAY, slot) = wray;
+                if (POL) {
+                    // throughput starts as the rotation to the output Stokes basis (stokes.cpp:111-151):
+                    // the accumulated vector is then directly expressed in that basis
+                    float R[16];
+                    stokes_output_rotation(P, d, R);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) FLD(PF_T0 + k, slot) = R[k];
+                    FLD(PF_RQ, slot) = 0.f; FLD(PF_RQ + 1, slot) = 0.f; FLD(PF_RQ + 2, slot) = 0.f;
+                }
             }
             __syncwarp();
             continue;
@@ -366,6 +405,19 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
             unsigned depth = flags >> PFL_DEPTH_SHIFT;
             float wnee = 0.f;
             bool dead = false;
+            // polarized state: T = thr * That (actual Mueller throughput), result (Q, U, V), NEE ratios
+            float T[POL ? 16 : 1], rquv[3] = { 0.f, 0.f, 0.f }, qn[3] = { 0.f, 0.f, 0.f };
+            if (POL) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) T[k] = thr * FLD(PF_T0 + k, slot);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) rquv[k] = FLD(PF_RQ + k, slot);
+                if (flags & PFL_NEE_QUV) { // finish the previous NEE term
+                    float wn = FLD(PF_WNEE, slot);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) rquv[k] = fmaf(wn, FLD(PF_QN0 + k, slot), rquv[k]);
+                }
+            }
 
             if (phase == PM_SURF) {
                 float sm = (flags & PFL_VACUUM) ? 0.f : FLD(PF_SMAX, slot);
@@ -379,7 +431,24 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                     float f_sun, weight;
                     surface_interact<SPH>(P, n0, sun, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
                     wnee = thr * f_sun * P.irradiance;
-                    if (flags & PFL_VACUUM) { res += wnee; wnee = 0.f; thr = 0.f; dead = true; }
+                    if (POL) {
+                        // depolarizer(f): the NEE Stokes vector is T[:,0] * f * E; then T <- T * depolarizer(w)
+                        float inv = thr != 0.f ? __fdividef(1.f, thr) : 0.f;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) qn[k] = T[4 * (k + 1)] * inv;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            T[4 * r] *= weight; T[4 * r + 1] = 0.f; T[4 * r + 2] = 0.f; T[4 * r + 3] = 0.f;
+                        }
+                    }
+                    if (flags & PFL_VACUUM) {
+                        res += wnee;
+                        if (POL) {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) rquv[k] = fmaf(wnee, qn[k], rquv[k]);
+                        }
+                        wnee = 0.f; thr = 0.f; dead = true;
+                    }
                     thr *= weight;
                     depth++;
                 }
@@ -389,7 +458,14 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                 if (SPH) n0 = normalize3(fma3(d, s, scale3(n0, P.R + h0)));
                 h0 = h;
                 int l = layer_of(P, h);
-                thr *= tb[P.off_albedo + l];
+                {
+                    float al = tb[P.off_albedo + l];
+                    thr *= al;
+                    if (POL) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) T[k] *= al;
+                    }
+                }
                 depth++;
                 if (depth >= P.max_depth) {
                     thr = 0.f; dead = true;
@@ -401,8 +477,15 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                         float ct_sun = dot3(d, sun);
                         float pv = 0.f;
                         int leaf = 0;
+                        const f3 wi_w = mk3(-d.x, -d.y, -d.z);
+                        float Pm[POL ? 16 : 1]; // mixture phase matrix towards the sun
+                        if (POL) {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) Pm[k] = 0.f;
+                        }
                         if (P.n_phase == 1) {
-                            pv = leaf_eval(tb, P.leaf[0], ct_sun);
+                            if (POL) { float pp; leaf_mueller(tb, P.leaf[0], wi_w, sun, Pm, pp); }
+                            else pv = leaf_eval(tb, P.leaf[0], ct_sun);
                         } else {
                             float u0 = pcg_float(rng);
                             float prev = 0.f;
@@ -412,11 +495,33 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                                 float cum = (i < P.n_phase - 1) ? tb[P.off_cumw + i * P.n_layers + l] : 1.f;
                                 float w = cum - prev;
                                 prev = cum;
-                                if (w > 0.f) pv = fmaf(w, leaf_eval(tb, P.leaf[i], ct_sun), pv);
+                                if (w > 0.f) {
+                                    if (POL) {
+                                        float Mi[16], pp;
+                                        leaf_mueller(tb, P.leaf[i], wi_w, sun, Mi, pp);
+#pragma unroll
+                                        for (int k = 0; k < 16; ++k) Pm[k] = fmaf(w, Mi[k], Pm[k]);
+                                    } else {
+                                        pv = fmaf(w, leaf_eval(tb, P.leaf[i], ct_sun), pv);
+                                    }
+                                }
                                 if (!picked && u0 < cum) { leaf = i; picked = true; }
                             }
                         }
-                        wnee = thr * pv * P.irradiance;
+                        if (POL) {
+                            // NEE Stokes vector: first column of T * P, times E
+                            float v[4];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r)
+                                v[r] = fmaf(T[4 * r], Pm[0], fmaf(T[4 * r + 1], Pm[4], fmaf(T[4 * r + 2], Pm[8], T[4 * r + 3] * Pm[12])));
+                            wnee = v[0] * P.irradiance;
+                            float inv = v[0] > 0.f ? __fdividef(1.f, v[0]) : 0.f;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) qn[k] = v[k + 1] * inv;
+                            if (!(wnee > 0.f)) wnee = 0.f;
+                        } else {
+                            wnee = thr * pv * P.irradiance;
+                        }
                         float u1 = pcg_float(rng), u2 = pcg_float(rng);
                         float pw, ppdf;
                         float ct = leaf_sample(tb, P.leaf[leaf], u1, pw, ppdf);
@@ -427,7 +532,20 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                             f3 fs, ft;
                             onb(d, fs, ft);
                             d = normalize3(fma3(fs, st * cp, fma3(ft, st * sp, scale3(d, ct))));
-                            thr *= pw;
+                            if (POL) {
+                                // weight = Mueller value / pdf (rayleigh_polarized.cpp:155-157), T <- T * W
+                                float W[16], pp, Tn[16];
+                                leaf_mueller(tb, P.leaf[leaf], wi_w, d, W, pp);
+                                float ip = pp > 0.f ? __fdividef(1.f, pp) : 0.f;
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) W[k] *= ip;
+                                mueller_mul(T, W, Tn);
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) T[k] = Tn[k];
+                                thr = T[0];
+                            } else {
+                                thr *= pw;
+                            }
                         }
                     }
                 }
@@ -437,6 +555,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
                 float q = fminf(thr, 0.95f);
                 if (pcg_float(rng) >= q) thr = 0.f; else thr = __fdividef(thr, q);
             }
+            if (POL && !(thr > 0.f)) thr = 0.f; // unpolarized(throughput) == 0 ends the path (volpath.cpp:191)
             if (thr == 0.f || depth >= P.max_depth) dead = true; // the NEE walk (if any) still runs
             // ---- segment set-up for the NEE walk and for the main walk that follows it ----
             float b = 0.f, smax = 0.f, b2 = 0.f, smax2 = 0.f;
@@ -466,6 +585,13 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
             FLD(PF_B2, slot) = b2; FLD(PF_SMAX2, slot) = smax2;
             FLD(PF_N0X, slot) = n0.x; FLD(PF_N0Y, slot) = n0.y; FLD(PF_N0Z, slot) = n0.z;
             FLD(PF_DX, slot) = d.x; FLD(PF_DY, slot) = d.y; FLD(PF_DZ, slot) = d.z;
+            if (POL) {
+                float inv = thr > 0.f ? __fdividef(1.f, T[0]) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) FLD(PF_T0 + k, slot) = T[k] * inv;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { FLD(PF_QN0 + k, slot) = qn[k]; FLD(PF_RQ + k, slot) = rquv[k]; }
+            }
         }
         __syncwarp();
     }
@@ -476,6 +602,12 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, ERTB_POOL_MINB) ertb_render_p
         atomicAdd(&P.accum[acc_pix], acc_wl);
         atomicAdd(&P.accum[P.n_pixels + acc_pix], acc_l);
         atomicAdd(&P.accum[2u * P.n_pixels + acc_pix], acc_l2);
+        if (POL) {
+            atomicAdd(&P.accum[3u * P.n_pixels + acc_pix], acc_wl);
+            atomicAdd(&P.accum[4u * P.n_pixels + acc_pix], acc_q);
+            atomicAdd(&P.accum[5u * P.n_pixels + acc_pix], acc_u);
+            atomicAdd(&P.accum[6u * P.n_pixels + acc_pix], acc_v);
+        }
     }
     if (STATS && P.stats) {
         unsigned v[5] = { st_paths, st_main, st_nee, st_scatter, st_surface };

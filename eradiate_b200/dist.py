@@ -45,8 +45,9 @@ class ShardedRenderer:
     def accum(self, sensor: int) -> torch.Tensor:
         if sensor not in self._accum:
             npix = self.dev.lib.ertb_sensor_pixel_count(self.dev.handle, sensor)
-            self._accum[sensor] = torch.zeros(3 * npix, dtype=torch.float64, device=f"cuda:{self.device}")
-            self._host[sensor] = torch.zeros(3 * npix, dtype=torch.float64).pin_memory()
+            rows = 7 if self.dev.flat.polarized else 3  # + [S0 | S1 | S2 | S3] for polarized scenes
+            self._accum[sensor] = torch.zeros(rows * npix, dtype=torch.float64, device=f"cuda:{self.device}")
+            self._host[sensor] = torch.zeros(rows * npix, dtype=torch.float64).pin_memory()
         return self._accum[sensor]
 
     def launch(self, sensor: int, seed: int, spp: int, sample_offset: int = 0, stats: torch.Tensor | None = None):
@@ -78,12 +79,13 @@ class ShardedRenderer:
         host = self._host[sensor]
         host.copy_(acc, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        a = host.numpy().reshape(3, -1)
+        a = host.numpy().reshape(7 if self.dev.flat.polarized else 3, -1)
+        self.last_stokes = a[3:7].copy() if self.dev.flat.polarized else None
         return a[0].copy(), a[1].copy(), a[2].copy()
 
     def render_bitmap(self, sensor: int, seed: int, spp_total: int):
         wl, l, l2 = self.render(sensor, seed, spp_total)
-        return develop(self.scene, sensor, wl, l, l2, spp_total)
+        return develop(self.scene, sensor, wl, l, l2, spp_total, stokes=self.last_stokes)
 
 
 def reduce_host_accumulators(arrays, group=None):

@@ -71,3 +71,15 @@ def sensor_ray(scene, sensor, film_sample, aperture_sample):
     w = np.zeros(n, dtype=np.float32)
     _lib.check(dev.lib.ertb_kat_sensor_ray(dev.handle, sensor, n, _fp(fs), _fp(ap), _dp(o), _dp(d), _fp(w)))
     return o, d, w
+
+
+def phase_mueller(scene, leaf, wi, wo):
+    """Mueller matrices (n, 4, 4) and pdf (n) of one phase-function leaf, world-space directions."""
+    dev = _device_scene(scene)
+    dev.sync()
+    wi, wo = _f(wi).reshape(-1, 3), _f(wo).reshape(-1, 3)
+    n = wi.shape[0]
+    M = np.zeros((n, 4, 4), dtype=np.float32)
+    pdf = np.zeros(n, dtype=np.float32)
+    _lib.check(dev.lib.ertb_kat_phase_mueller(dev.handle, leaf, n, _fp(wi), _fp(wo), _fp(M), _fp(pdf)))
+    return M, pdf

@@ -130,6 +130,18 @@ class DeviceScene:
             raise RuntimeError(f"invalid sensor index {sensor}")
         out = [np.zeros(npix, dtype=np.float64) for _ in range(3)]
         stats = _abi.RenderStats()
+        if self.flat.polarized:
+            stokes = np.zeros((4, npix), dtype=np.float64)
+            _lib.check(
+                self.lib.ertb_render_stokes(
+                    self.handle, sensor, seed, spp, sample_offset,
+                    *[o.ctypes.data_as(_abi.c_double_p) for o in out],
+                    stokes.ctypes.data_as(_abi.c_double_p), C.byref(stats),
+                )
+            )
+            self.last_stokes = stokes
+            return out[0], out[1], out[2], stats
+        self.last_stokes = None
         _lib.check(
             self.lib.ertb_render(
                 self.handle, sensor, seed, spp, sample_offset,
@@ -380,13 +392,13 @@ def render(scene, sensor: int = 0, seed: int = 0, spp: int = 0, device: int | No
         spp = s.sampler().sample_count
     dev = _device_scene(scene, device)
     sum_wl, sum_l, sum_l2, stats = dev.render(i_sensor, int(seed) & 0xFFFFFFFFFFFFFFFF, int(spp))
-    bmp = develop(scene, i_sensor, sum_wl, sum_l, sum_l2, spp)
+    bmp = develop(scene, i_sensor, sum_wl, sum_l, sum_l2, spp, stokes=dev.last_stokes)
     bmp.stats = stats.as_dict()
     s.film()._bitmap = bmp
     return bmp
 
 
-def develop(scene, i_sensor: int, sum_wl, sum_l, sum_l2, spp: int) -> Bitmap:
+def develop(scene, i_sensor: int, sum_wl, sum_l, sum_l2, spp: int, stokes=None) -> Bitmap:
     """``HDRFilm::develop`` (``hdrfilm.cpp:304-405``): sums / weight, channel naming."""
     s = scene.sensors()[i_sensor]
     film = s.film()
@@ -394,6 +406,13 @@ def develop(scene, i_sensor: int, sum_wl, sum_l, sum_l2, spp: int) -> Bitmap:
     inv = 1.0 / float(spp)
     chans = [np.asarray(sum_wl).reshape(h, w) * inv]
     names = ["Y"]
+    if getattr(scene.integrator(), "stokes", False):
+        # stokes.cpp:190-196: AOVs S0.R, S0.G, S0.B, S1.R ... come first
+        st = np.zeros((4, h * w)) if stokes is None else np.asarray(stokes)
+        for k in range(4):
+            c = st[k].reshape(h, w) * inv
+            chans += [c, c, c]
+            names += [f"S{k}.R", f"S{k}.G", f"S{k}.B"]
     if scene.integrator().moment:
         m1 = np.asarray(sum_l).reshape(h, w) * inv
         m2 = np.asarray(sum_l2).reshape(h, w) * inv
@@ -406,6 +425,8 @@ def develop(scene, i_sensor: int, sum_wl, sum_l, sum_l2, spp: int) -> Bitmap:
         "sum_l2": np.asarray(sum_l2, dtype=np.float64).reshape(h, w).copy(),
         "spp": int(spp),
     }
+    if stokes is not None:
+        raw["sum_stokes"] = np.asarray(stokes, dtype=np.float64).reshape(4, h, w).copy()
     return Bitmap(data, None, names, raw=raw)
 
 

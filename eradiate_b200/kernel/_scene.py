@@ -224,12 +224,13 @@ class Scene(Object):
 # ------------------------------------------------------------------------------
 
 _SUPPORTED = {
-    "integrator": {"volpath", "volpathmis", "moment"},
+    "integrator": {"volpath", "volpathmis", "moment", "stokes"},
     "emitter": {"directional"},
     "shape": {"sphere", "cube", "rectangle", "arectangle"},
     "medium": {"heterogeneous", "homogeneous"},
     "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "null"},
-    "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase"},
+    "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
+              "rayleigh_polarized", "tabphase_polarized"},
     "sensor": {"mdistant", "hdistant", "distantflux"},
     "volume": {"gridvolume", "sphericalcoordsvolume", "constvolume"},
 }
@@ -239,7 +240,6 @@ _KNOWN_UNSUPPORTED = {
     "piecewise_volpath": "the analytic piecewise integrator is a 'next' row (SURVEY 8f-1); "
     "pass integrator={'type': 'volpath'} and atmosphere.force_majorant=True",
     "piecewise": "the piecewise medium is a 'next' row (SURVEY 8f-1); use force_majorant=True",
-    "stokes": "polarized (Stokes) rendering is not implemented in this kernel yet",
     "path": "surface-only integrators are out of scope",
     "perspective": "perspective sensors (canopy scenes) are a 'next' row (SURVEY 8f-3)",
 }
@@ -342,7 +342,24 @@ class _Loader:
         ph = PhaseFunction(ty, oid)
         if ty == "hg":
             ph.values["g"] = float(d.get("g", 0.8))
-        elif ty == "rayleigh":
+        elif ty == "tabphase_polarized":
+            # ERP/phase/tabphase_polarized.cpp:228-296: m11 on irregular nodes + m12, m22, m33, m34, m44
+            ph.values["nodes"] = _parse_floats(d["nodes"], "nodes").astype(np.float32)
+            ph.values["m11"] = _parse_floats(d["m11"], "m11").astype(np.float32)
+            n = ph.values["nodes"].size
+            if ph.values["m11"].size != n:
+                raise RuntimeError(
+                    "TabulatedPolarizedPhaseFunction: 'cos_theta_str' and 'm11_str' parameters "
+                    "must have the same size!")
+            for name in ("m12", "m22", "m33", "m34", "m44"):
+                raw = d.get(name, "")
+                arr = _parse_floats(raw, name).astype(np.float32) if raw != "" else np.zeros(n, np.float32)
+                if arr.size != n:
+                    raise RuntimeError(
+                        "TabulatedPolarizedPhaseFunction: the provided parameters must have the "
+                        "same size as 'cos_theta_str'!")
+                ph.values[name] = arr
+        elif ty in ("rayleigh", "rayleigh_polarized"):
             dep = d.get("depolarization", 0.0)
             if isinstance(dep, dict):
                 vol = self.make_volume(dep, None)
@@ -528,7 +545,17 @@ class _Loader:
         ty = d["type"]
         it = Integrator(ty, oid)
         it.moment = False
+        it.stokes = False
+        it.meridian_align = False
         inner = d
+        if ty == "stokes":  # MI/src/integrators/stokes.cpp: must be the outermost wrapper
+            it.stokes = True
+            it.meridian_align = bool(d.get("meridian_align", False))
+            nested = [v for v in d.values() if isinstance(v, dict) and "type" in v]
+            if len(nested) != 1:
+                raise RuntimeError("Must specify a sub-integrator!")
+            inner = d = nested[0]
+            ty = inner["type"]
         if ty == "moment":
             it.moment = True
             nested = [v for v in d.values() if isinstance(v, dict) and "type" in v]
@@ -659,6 +686,23 @@ class FlatScene:
         self.sensors = sc.sensors()
         if not self.sensors:
             raise RuntimeError("scene has no sensor")
+        # Polarized transport = the reference's *_polarized variants.  The variant is global state in
+        # Mitsuba; here it is inferred from the scene: a `stokes` integrator or a polarized phase plugin.
+        self.polarized = bool(getattr(self.integrator, "stokes", False))
+        if self.medium is not None:
+            def has_pol(ph):
+                if ph.type == "blendphase":
+                    return has_pol(ph.children["phase_0"]) or has_pol(ph.children["phase_1"])
+                return ph.type.endswith("_polarized")
+            self.polarized = self.polarized or has_pol(self.medium.children["phase_function"])
+        forced = getattr(sc, "_force_polarized", None)
+        if forced is not None:
+            self.polarized = bool(forced)
+        if self.polarized and self.integrator.kernel_type == "volpathmis":
+            # volpathmis.cpp:130-132
+            raise RuntimeError("This integrator currently does not support polarized mode!")
+        if self.polarized and self.bsdf.type == "ocean_legacy":
+            raise RuntimeError("ocean_legacy in polarized mode (polarized Fresnel glint) is not implemented yet")
 
     def _extract_medium(self) -> None:
         m = self.medium
@@ -827,6 +871,12 @@ class FlatScene:
                     nodes = np.ascontiguousarray(nodes, dtype=np.float32)
                     keep.append(nodes)
                     pd.nodes = nodes.ctypes.data_as(_abi.c_float_p)
+                mu = _phase_leaf_mueller(ph)
+                if mu is not None:
+                    for k, arr in enumerate(mu):
+                        arr = np.ascontiguousarray(arr, dtype=np.float32)
+                        keep.append(arr)
+                        pd.mueller[k] = arr.ctypes.data_as(_abi.c_float_p)
 
         d.bsdf_type = self.bsdf_type()
         d.bsdf_params[:] = list(self.bsdf_params())
@@ -838,6 +888,8 @@ class FlatScene:
         )
         d.rr_depth = it.rr_depth
         d.max_depth = it.max_depth
+        d.polarized = int(self.polarized)
+        d.meridian_align = int(getattr(it, "meridian_align", False))
 
         sens = (_abi.SensorDesc * len(self.sensors))()
         for i, s in enumerate(self.sensors):
@@ -865,18 +917,28 @@ class FlatScene:
         return d
 
 
+def _phase_leaf_mueller(ph: PhaseFunction):
+    """m12, m22, m33, m34, m44 arrays of a tabphase_polarized leaf (else None)."""
+    if ph.type != "tabphase_polarized":
+        return None
+    return [ph.values[k] for k in ("m12", "m22", "m33", "m34", "m44")]
+
+
 def _phase_leaf_desc(ph: PhaseFunction):
     params = [0.0, 0.0, 0.0, 0.0]
     if ph.type == "isotropic":
         return _abi.PHASE_ISOTROPIC, params, None, None
-    if ph.type == "rayleigh":
+    if ph.type == "tabphase_polarized":
+        return _abi.PHASE_TABULATED_POLARIZED, params, ph.values["m11"], ph.values["nodes"]
+    if ph.type in ("rayleigh", "rayleigh_polarized"):
         if "depolarization" in ph.children:
             params[0] = float(ph.children["depolarization"].layer_values().flat[0])
         else:
             params[0] = ph.values.get("depolarization", 0.0)
         if params[0] >= 1.0:
             raise RuntimeError("Depolarization factor must be in [0, 1[")
-        return _abi.PHASE_RAYLEIGH, params, None, None
+        ty = _abi.PHASE_RAYLEIGH_POLARIZED if ph.type == "rayleigh_polarized" else _abi.PHASE_RAYLEIGH
+        return ty, params, None, None
     if ph.type == "hg":
         g = ph.values["g"]
         if not (-1.0 < g < 1.0):

@@ -113,6 +113,8 @@ def atmosphere_scene(
     homogeneous_sigma_t: float = 1.16e-5,
     homogeneous_albedo: float = 1.0,
     phase: dict | None = None,
+    stokes: bool = False,
+    meridian_align: bool = True,
 ) -> dict:
     """Build the nested scene dict an ``AtmosphereExperiment`` would emit."""
     if surface is None:
@@ -127,6 +129,9 @@ def atmosphere_scene(
     if rr_depth is not None:
         integ["rr_depth"] = rr_depth
     scene["integrator"] = {"type": "moment", "nested": integ} if moment else integ
+    if stokes:  # integrators/_path_tracers.py:70-78: the stokes wrapper comes last
+        scene["integrator"] = {"type": "stokes", "integrator": scene["integrator"],
+                               "meridian_align": meridian_align}
 
     sun = angles_to_direction(sza, saa)
     scene["illumination"] = {

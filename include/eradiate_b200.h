@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 4
+#define ERTB_ABI_VERSION 5
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -62,7 +62,10 @@ enum ertb_phase_type {
     ERTB_PHASE_RAYLEIGH = 1,   /* MI/src/phase/rayleigh.cpp:61-110; params[0] = depolarization */
     ERTB_PHASE_HG = 2,         /* MI/src/phase/hg.cpp:64-100; params[0] = g */
     ERTB_PHASE_TABULATED = 3,  /* MI/src/phase/tabphase.cpp:77-124 (regular cos-theta grid) */
-    ERTB_PHASE_TABULATED_IRREGULAR = 4 /* ERP/phase/tabphase_irregular.cpp:111-152 */
+    ERTB_PHASE_TABULATED_IRREGULAR = 4, /* ERP/phase/tabphase_irregular.cpp:111-152 */
+    ERTB_PHASE_RAYLEIGH_POLARIZED = 5,  /* ERP/phase/rayleigh_polarized.cpp:55-176; params[0] = depolarization */
+    ERTB_PHASE_TABULATED_POLARIZED = 6  /* ERP/phase/tabphase_polarized.cpp:226-430: `values` = m11 on
+                                           irregular `nodes`, `mueller` = m12, m22, m33, m34, m44 */
 };
 
 enum ertb_sensor_type {
@@ -89,7 +92,8 @@ typedef struct ertb_phase_desc {
     int32_t n_nodes;       /* tabulated: number of entries of `values` (>= 2) */
     float params[4];       /* see enum */
     const float *values;   /* tabulated: pdf samples, physics convention, cos(theta) ascending */
-    const float *nodes;    /* tabulated_irregular: cos(theta) nodes in [-1,1]; NULL otherwise */
+    const float *nodes;    /* tabulated_irregular / _polarized: cos(theta) nodes in [-1,1]; else NULL */
+    const float *mueller[5]; /* tabulated_polarized: m12, m22, m33, m34, m44 (n_nodes each; NULL = 0) */
 } ertb_phase_desc;
 
 typedef struct ertb_sensor_desc {
@@ -153,6 +157,11 @@ typedef struct ertb_scene_desc {
     int32_t integrator;    /* enum ertb_integrator_type */
     int32_t rr_depth;      /* default 5 */
     int64_t max_depth;     /* -1 = unbounded */
+    /* Polarized (Stokes / Mueller) transport: the scalar_mono_polarized variant of the reference.
+     * MI/src/integrators/stokes.cpp:97-168 rotates the Stokes vector to the meridian plane
+     * (`meridian_align`) or to the sensor's x-axis before it is written to S0..S3. */
+    int32_t polarized;
+    int32_t meridian_align;
 
     int32_t n_sensors;
     int32_t _pad4;
@@ -218,6 +227,13 @@ int ertb_render_device(ertb_scene *scene, int sensor, uint64_t seed, uint64_t sp
                        uint64_t sample_offset, void *accum_dev, void *stats_dev,
                        void *stream);
 
+/* Polarized scenes: same as ertb_render plus sum_stokes = [4][n_pixels] sums of
+ * ray_weight * (S0, S1, S2, S3) in the output frame of the stokes integrator (may be NULL).
+ * The device variant expects accum_dev to hold (3 + 4) * n_pixels doubles for polarized scenes. */
+int ertb_render_stokes(ertb_scene *scene, int sensor, uint64_t seed, uint64_t spp,
+                       uint64_t sample_offset, double *sum_wl, double *sum_l, double *sum_l2,
+                       double *sum_stokes, ertb_render_stats *stats);
+
 int ertb_sensor_pixel_count(const ertb_scene *scene, int sensor);
 
 /* Known-answer-test entry points: evaluate the device implementations of the
@@ -227,13 +243,18 @@ int ertb_sensor_pixel_count(const ertb_scene *scene, int sensor);
  *                -> wo (3*n), weight (n)
  *   phase_eval : leaf index, cos between wo and wi ("graphics" convention, n) -> out (n)
  *   phase_sample: leaf index, u (2*n) -> cos_theta of wo w.r.t. propagation dir (n), weight (n), pdf (n)
- *   sensor_ray : film sample (2*n) + aperture sample (2*n) -> origin (3*n) dir (3*n) weight (n) */
+ *   sensor_ray : film sample (2*n) + aperture sample (2*n) -> origin (3*n) dir (3*n) weight (n)
+ */
 int ertb_kat_bsdf_eval(ertb_scene *scene, size_t n, const float *wi, const float *wo, float *out);
 int ertb_kat_bsdf_sample(ertb_scene *scene, size_t n, const float *wi, const float *u,
                          float *wo, float *weight);
 int ertb_kat_phase_eval(ertb_scene *scene, int leaf, size_t n, const float *cos_theta, float *out);
 int ertb_kat_phase_sample(ertb_scene *scene, int leaf, size_t n, const float *u,
                           float *cos_theta, float *weight, float *pdf);
+/* phase_mueller: leaf, wi (3*n, = -propagation direction), wo (3*n) -> 4x4 Mueller matrices in the
+ * implicit Stokes bases of the two directions (16*n, row-major) and pdf (n) */
+int ertb_kat_phase_mueller(ertb_scene *scene, int leaf, size_t n, const float *wi, const float *wo,
+                           float *mueller, float *pdf);
 int ertb_kat_sensor_ray(ertb_scene *scene, int sensor, size_t n, const float *film_sample,
                         const float *aperture_sample, double *origin, double *dir, float *weight);
 

@@ -311,9 +311,10 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
         if (d->n_phase < 1 || d->n_phase > ERTB_MAX_PHASE) return fail("invalid n_phase");
         for (int i = 0; i < d->n_phase; ++i) {
             const ertb_phase_desc *p = &d->phase[i];
-            if (p->type == ERTB_PHASE_TABULATED || p->type == ERTB_PHASE_TABULATED_IRREGULAR) {
-                const float *nodes = p->type == ERTB_PHASE_TABULATED_IRREGULAR ? p->nodes : NULL;
-                if (p->type == ERTB_PHASE_TABULATED_IRREGULAR && !nodes) return fail("nodes missing");
+            if (p->type == ERTB_PHASE_TABULATED || p->type == ERTB_PHASE_TABULATED_IRREGULAR ||
+                p->type == ERTB_PHASE_TABULATED_POLARIZED) {
+                const float *nodes = p->type != ERTB_PHASE_TABULATED ? p->nodes : NULL;
+                if (p->type != ERTB_PHASE_TABULATED && !nodes) return fail("nodes missing");
                 if (distr_init(&S->distr[i], nodes, p->values, p->n_nodes)) return 1;
                 S->has_distr[i] = 1;
             }
@@ -521,6 +522,7 @@ static void leaf_eval_pdf(const scene_t *S, int leaf, double c, double *val, dou
         case ERTB_PHASE_ISOTROPIC: /* isotropic.cpp:39-60 */
             *val = *pdf = INV_FOUR_PI; break;
         case ERTB_PHASE_RAYLEIGH:  /* rayleigh.cpp:97-107 */
+        case ERTB_PHASE_RAYLEIGH_POLARIZED: /* rayleigh_polarized.cpp:122-127 (unpolarized branch) */
             *val = eval_rayleigh(c, p->params[0]); *pdf = eval_rayleigh_pdf(c); break;
         case ERTB_PHASE_HG:        /* hg.cpp:92-99 */
             *val = *pdf = eval_hg(p->params[0], c); break;
@@ -545,6 +547,7 @@ static void leaf_sample(const scene_t *S, int leaf, double u1, double u2, v3 *wo
             *weight = 1.0; *pdf = INV_FOUR_PI;
             break;
         }
+        case ERTB_PHASE_RAYLEIGH_POLARIZED: /* rayleigh_polarized.cpp:133-160: same inversion */
         case ERTB_PHASE_RAYLEIGH: { /* rayleigh.cpp:75-95 */
             double z = 2.0 * (2.0 * u1 - 1.0);
             double tmp = sqrt(z * z + 1.0);
@@ -614,6 +617,144 @@ static void phase_sample(const scene_t *S, int layer, v3 wi, double s1, double u
     leaf_sample(S, leaf, u1, u2, &wl, weight, pdf);
     frame_t f = make_frame(wi); /* medium.cpp:51 sh_frame = Frame3f(wi) */
     *wo = to_world(&f, wl);
+}
+
+
+/* ------------------------------------------------- polarization (Mueller) */
+/* MI/include/mitsuba/render/mueller.h; matrices are row-major double[16]. */
+typedef struct { double m[16]; } mueller_t;
+static mueller_t mu_zero(void) { mueller_t r; memset(&r, 0, sizeof r); return r; }
+static mueller_t mu_identity(double v) { mueller_t r = mu_zero(); r.m[0] = r.m[5] = r.m[10] = r.m[15] = v; return r; }
+static mueller_t mu_mul(const mueller_t *a, const mueller_t *b) {
+    mueller_t r = mu_zero();
+    for (int i = 0; i < 4; ++i) for (int k = 0; k < 4; ++k) { double aik = a->m[4 * i + k];
+        if (aik != 0.0) for (int j = 0; j < 4; ++j) r.m[4 * i + j] += aik * b->m[4 * k + j]; }
+    return r;
+}
+static mueller_t mu_scale(const mueller_t *a, double s) { mueller_t r; for (int i = 0; i < 16; ++i) r.m[i] = a->m[i] * s; return r; }
+static mueller_t mu_transpose(const mueller_t *a) { mueller_t r; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r.m[4 * i + j] = a->m[4 * j + i]; return r; }
+static mueller_t mu_rotator(double theta) { /* mueller.h:164-173 */
+    double s = sin(2.0 * theta), c = cos(2.0 * theta);
+    mueller_t r = mu_zero();
+    r.m[0] = 1; r.m[5] = c; r.m[6] = s; r.m[9] = -s; r.m[10] = c; r.m[15] = 1;
+    return r;
+}
+static v3 vcross(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static v3 stokes_basis(v3 forward) { v3 s, t; coordinate_system(forward, &s, &t); return s; } /* mueller.h:286 */
+/* drjit/sphere.h:53-62 unit_angle */
+static double unit_angle(v3 a, v3 b) {
+    double d = vdot(a, b);
+    v3 diff = d >= 0.0 ? vsub(b, a) : vadd(b, a);
+    double temp = 2.0 * asin(fmin(1.0, 0.5 * vnorm(diff)));
+    return d >= 0.0 ? temp : PI - temp;
+}
+/* mueller.h:316-324 */
+static mueller_t rotate_stokes_basis(v3 forward, v3 basis_current, v3 basis_target) {
+    double theta = unit_angle(vnormalize(basis_current), vnormalize(basis_target));
+    if (vdot(forward, vcross(basis_current, basis_target)) < 0.0) theta = -theta;
+    return mu_rotator(theta);
+}
+/* mueller.h:362-372: R_out * M * R_in^T */
+static mueller_t rotate_mueller_basis(const mueller_t *M, v3 in_fwd, v3 in_cur, v3 in_tgt, v3 out_fwd, v3 out_cur, v3 out_tgt) {
+    mueller_t Rin = rotate_stokes_basis(in_fwd, in_cur, in_tgt), Rout = rotate_stokes_basis(out_fwd, out_cur, out_tgt);
+    mueller_t RinT = mu_transpose(&Rin), t = mu_mul(M, &RinT);
+    return mu_mul(&Rout, &t);
+}
+static int mu_has_nan(const mueller_t *a) { for (int i = 0; i < 16; ++i) if (isnan(a->m[i])) return 1; return 0; }
+
+/* Mueller-valued eval_pdf of one leaf in world space (Radiance mode: light arrives along -wo and
+ * leaves along +wi).  rayleigh_polarized.cpp:55-127, tabphase_polarized.cpp:318-368; the scalar
+ * plugins return Spectrum(value) = value * Identity in a polarized variant. */
+static void leaf_eval_mueller(const scene_t *S, int leaf, v3 wi, v3 wo, mueller_t *M, double *pdf) {
+    const ertb_phase_desc *p = &S->desc->phase[leaf];
+    double ct = -vdot(wo, wi); /* physics convention */
+    int polarized_leaf = 0;
+    if (p->type == ERTB_PHASE_RAYLEIGH_POLARIZED) {
+        double rho = p->params[0];
+        double r1 = (1.0 - rho) / (1.0 + rho / 2.0), r2 = (1.0 + rho) / (1.0 - rho), r3 = (1.0 - 2.0 * rho) / (1.0 - rho);
+        double a = r2 + ct * ct, b = ct * ct + 1.0, c = ct * ct - 1.0, d = 2.0 * ct;
+        double k = (3.0 / 16.0) * INV_PI * r1;
+        *M = mu_zero();
+        M->m[0] = k * a; M->m[1] = k * c; M->m[4] = k * c; M->m[5] = k * b; M->m[10] = k * d; M->m[15] = k * d * r3;
+        *pdf = eval_rayleigh_pdf(ct);
+        polarized_leaf = 1;
+    } else if (p->type == ERTB_PHASE_TABULATED_POLARIZED) {
+        const distr_t *D = &S->distr[leaf];
+        double m11 = distr_eval_pdf(D, ct), norm = D->normalization * INV_TWO_PI;
+        double ms[5] = { 0, 0, 0, 0, 0 };
+        if (ct >= D->x0 && ct <= D->x1) { /* IrregularInterpolant::eval_data (tabphase_polarized.cpp:178-206) */
+            int index = bsearch_pred_nodes(D, ct);
+            if (index > D->n - 1) index = D->n - 1;
+            if (index < 1) index = 1;
+            index -= 1;
+            double t = (ct - D->nodes[index]) / (D->nodes[index + 1] - D->nodes[index]);
+            for (int k = 0; k < 5; ++k)
+                if (p->mueller[k]) ms[k] = (double) p->mueller[k][index] + t * ((double) p->mueller[k][index + 1] - (double) p->mueller[k][index]);
+        }
+        *M = mu_zero();
+        M->m[0] = m11; M->m[1] = ms[0]; M->m[4] = ms[0]; M->m[5] = ms[1];
+        M->m[10] = ms[2]; M->m[11] = ms[3]; M->m[14] = -ms[3]; M->m[15] = ms[4];
+        *M = mu_scale(M, norm);
+        *pdf = m11 * norm;
+        polarized_leaf = 1;
+    } else {
+        double v, pp;
+        leaf_eval_pdf(S, leaf, vdot(wo, wi), &v, &pp);
+        *M = mu_identity(v);
+        *pdf = pp;
+    }
+    if (polarized_leaf) {
+        v3 wo_hat = wo, wi_hat = wi;
+        v3 x_hat = vnormalize(vcross(vneg(wo_hat), wi_hat));
+        v3 p_in = vnormalize(vcross(x_hat, vneg(wo_hat))), p_out = vnormalize(vcross(x_hat, wi_hat));
+        *M = rotate_mueller_basis(M, vneg(wo_hat), p_in, stokes_basis(vneg(wo_hat)), wi_hat, p_out, stokes_basis(wi_hat));
+        if (mu_has_nan(M)) *M = mu_zero();
+    }
+}
+
+/* blendphase.cpp:172-190 with Mueller-valued components */
+static void phase_eval_mueller(const scene_t *S, int layer, v3 wi, v3 wo, mueller_t *M) {
+    *M = mu_zero();
+    for (int i = 0; i < S->desc->n_phase; ++i) {
+        double w = leaf_prob(S, i, layer);
+        if (w == 0.0) continue;
+        mueller_t Mi; double pi_;
+        leaf_eval_mueller(S, i, wi, wo, &Mi, &pi_);
+        for (int k = 0; k < 16; ++k) M->m[k] += w * Mi.m[k];
+    }
+}
+/* sample(): direction from the leaf's scalar sampler, weight = Mueller value / pdf
+ * (rayleigh_polarized.cpp:133-160, tabphase_polarized.cpp:296-316) */
+static void phase_sample_mueller(const scene_t *S, int layer, v3 wi, double s1, double u1, double u2,
+                                 v3 *wo, mueller_t *W, double *pdf) {
+    int n = S->desc->n_phase, leaf = 0;
+    if (n > 1) {
+        double acc = 0.0;
+        leaf = n - 1;
+        for (int i = 0; i < n; ++i) { acc += leaf_prob(S, i, layer); if (s1 < acc) { leaf = i; break; } }
+    }
+    v3 wl; double w_scalar, p_scalar;
+    const ertb_phase_desc *p = &S->desc->phase[leaf];
+    if (p->type == ERTB_PHASE_TABULATED_POLARIZED) { /* m11 drives the sampling (:300-309) */
+        const distr_t *D = &S->distr[leaf];
+        double ctp = distr_sample(D, u1), stp = safe_sqrt(1.0 - ctp * ctp);
+        wl = V(-stp * cos(2.0 * PI * u2), -stp * sin(2.0 * PI * u2), -ctp);
+        w_scalar = 1.0; p_scalar = 0.0;
+    } else {
+        leaf_sample(S, leaf, u1, u2, &wl, &w_scalar, &p_scalar);
+    }
+    frame_t f = make_frame(wi);
+    *wo = to_world(&f, wl);
+    if (p->type == ERTB_PHASE_RAYLEIGH_POLARIZED || p->type == ERTB_PHASE_TABULATED_POLARIZED) {
+        mueller_t M; double pp;
+        leaf_eval_mueller(S, leaf, wi, *wo, &M, &pp);
+        if (p->type == ERTB_PHASE_RAYLEIGH_POLARIZED) pp = p_scalar; /* pdf from the sampled cosine */
+        *pdf = pp;
+        *W = pp > 0.0 ? mu_scale(&M, 1.0 / pp) : mu_zero();
+    } else {
+        *pdf = p_scalar;
+        *W = mu_identity(w_scalar);
+    }
 }
 
 /* ----------------------------------------------------------------- BSDFs */
@@ -1040,10 +1181,146 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t
     return result;
 }
 
+
+/* volpath.cpp:93-396 in a polarized variant: Spectrum = 4x4 Mueller matrix.  `throughput` is
+ * right-multiplied by every weight (throughput *= w), the emitter value is depolarizer(E), so
+ * only the first column of `result` is ever non-zero: it is kept as a Stokes 4-vector.  All the
+ * surface BSDFs of this path return depolarizer(value), which to_world_mueller() leaves unchanged.
+ * stokes.cpp:97-168 then rotates the vector from the implicit basis of -ray.d to the output basis. */
+static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, v3 sensor_up, counters_t *C, double stokes[4]) {
+    const ertb_scene_desc *D = S->desc;
+    const int mis = D->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
+    const uint64_t max_depth = D->max_depth < 0 ? (uint64_t) 0xffffffffu : (uint64_t) D->max_depth;
+    const v3 primary_d = ray.d;
+    mueller_t T = mu_identity(1.0);
+    double result[4] = { 0, 0, 0, 0 }, eta = 1.0;
+    int medium = 0;
+    uint64_t depth = 0;
+    si_t si; si.t = INFINITY; si.shape = -1; si.p = si.n = V(0, 0, 0);
+    int needs_intersection = 1, last_event_was_null = 0;
+
+    for (;;) {
+        int any_nz = 0;
+        for (int i = 0; i < 16; ++i) if (T.m[i] != 0.0) { any_nz = 1; break; }
+        /* active &= any(unpolarized_spectrum(throughput) != 0): the (0,0) entry */
+        if (T.m[0] == 0.0) break;
+        (void) any_nz;
+        double q = fmin(T.m[0] * eta * eta, 0.95);
+        int perform_rr = depth > (uint64_t) D->rr_depth && !(mis && last_event_was_null);
+        double xi = next_1d(rng);
+        if (perform_rr) {
+            if (!(xi < q)) break;
+            T = mu_scale(&T, 1.0 / q);
+        }
+        last_event_was_null = 0;
+        if (!(depth < max_depth)) break;
+        C->trips_main++;
+
+        int active_medium = medium, active_surface = !medium;
+        int escaped = 0, null_scatter = 0, medium_scatter = 0;
+        mei_t mei; memset(&mei, 0, sizeof mei);
+        if (active_medium) {
+            mei = sample_interaction(S, &ray, next_1d(rng));
+            if (D->homogeneous && mei.t < INFINITY) ray.maxt = mei.t;
+            if (needs_intersection) si = scene_intersect(S, &ray);
+            needs_intersection = 0;
+            if (si.t < mei.t) mei.t = INFINITY;
+            {
+                double t = fmin(mei.t, si.t) - mei.mint;
+                double tr = exp(-t * mei.combined);
+                double pdf = si.t < mei.t ? tr : tr * mei.combined;
+                T = mu_scale(&T, pdf > 0.0 ? tr / pdf : 0.0);
+            }
+            escaped = !(mei.t < INFINITY);
+            active_medium = mei.t < INFINITY;
+            if (active_medium) {
+                double pnull = mei.sigma_n / mei.combined;
+                null_scatter = next_1d(rng) < pnull;
+                medium_scatter = !null_scatter;
+                if (null_scatter) { T = mu_scale(&T, mei.sigma_n / pnull); last_event_was_null = 1; }
+                else depth++;
+            }
+        }
+        if (!(depth < max_depth)) break;
+        if (null_scatter) { ray.o = mei.p; si.t -= mei.t; }
+        if (medium_scatter) {
+            C->n_scatter++;
+            T = mu_scale(&T, mei.sigma_s / (mei.sigma_t / mei.combined));
+            v3 ds_d;
+            double emitted = sample_emitter(S, rng, mei.p, V(0, 0, 0), medium, C, &ds_d);
+            mueller_t P;
+            phase_eval_mueller(S, mei.layer, mei.wi, ds_d, &P);
+            mueller_t TP = mu_mul(&T, &P);
+            for (int i = 0; i < 4; ++i) result[i] += TP.m[4 * i] * emitted; /* * depolarizer(E): column 0 */
+            v3 wo; mueller_t W; double pp;
+            double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
+            phase_sample_mueller(S, mei.layer, mei.wi, s1, u1, u2, &wo, &W, &pp);
+            if (pp > 0.0) {
+                ray = spawn_ray(mei.p, V(0, 0, 0), wo);
+                needs_intersection = 1;
+                T = mu_mul(&T, &W);
+            }
+        }
+        active_surface |= escaped;
+        if (active_surface && needs_intersection) si = scene_intersect(S, &ray);
+        active_surface = active_surface && si.t < INFINITY;
+        if (active_surface) {
+            frame_t fr = surface_frame(S, &si);
+            v3 wi = to_local(&fr, vneg(ray.d));
+            v3 wo_world;
+            if (si.shape == SHAPE_TOA) {
+                (void) next_1d(rng); (void) next_1d(rng); (void) next_1d(rng);
+                wo_world = ray.d;
+            } else {
+                C->n_surface++;
+                if (depth + 1 < max_depth) {
+                    v3 ds_d;
+                    double emitted = sample_emitter(S, rng, si.p, si.n, medium, C, &ds_d);
+                    v3 wo = to_local(&fr, ds_d);
+                    double f = bsdf_eval(S, wi, wo); /* depolarizer(f) */
+                    for (int i = 0; i < 4; ++i) result[i] += T.m[4 * i] * f * emitted;
+                }
+                double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
+                v3 wo;
+                double w = bsdf_sample(S, wi, s1, u1, u2, &wo);
+                mueller_t Dw = mu_zero(); Dw.m[0] = w; /* depolarizer(w) */
+                T = mu_mul(&T, &Dw);
+                wo_world = to_world(&fr, wo);
+                depth++;
+            }
+            ray = spawn_ray(si.p, si.n, wo_world);
+            needs_intersection = 1;
+            if (si.shape == SHAPE_TOA) medium = target_medium(si.n, ray.d);
+        }
+        if (!(active_surface || active_medium)) break;
+    }
+    /* stokes.cpp:111-151 */
+    v3 fwd = vneg(primary_d);
+    v3 current = stokes_basis(fwd), target;
+    if (D->meridian_align) {
+        v3 tmp = vcross(V(0, 0, 1), fwd);
+        if (vnorm(tmp) < RAY_EPS) target = V(1, 0, 0);
+        else target = vcross(vnormalize(tmp), fwd);
+    } else {
+        target = vcross(primary_d, sensor_up);
+    }
+    mueller_t R = rotate_stokes_basis(fwd, current, target);
+    for (int i = 0; i < 4; ++i) {
+        stokes[i] = 0.0;
+        for (int j = 0; j < 4; ++j) stokes[i] += R.m[4 * i + j] * result[j];
+    }
+}
+
 /* ---------------------------------------------------------------- render */
 int ertbo_render(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_t spp,
                  uint64_t sample_offset, double *sum_wl, double *sum_l, double *sum_l2,
                  ertb_render_stats *stats, int n_threads) {
+    return ertbo_render_stokes(desc, sensor, seed, spp, sample_offset, sum_wl, sum_l, sum_l2, NULL, stats, n_threads);
+}
+
+int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_t spp,
+                        uint64_t sample_offset, double *sum_wl, double *sum_l, double *sum_l2,
+                        double *sum_stokes, ertb_render_stats *stats, int n_threads) {
     scene_t S;
     if (scene_init(&S, desc)) return 1;
     if (sensor < 0 || sensor >= desc->n_sensors) { scene_free(&S); return fail("bad sensor index"); }
@@ -1060,7 +1337,10 @@ int ertbo_render(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_
     const uint64_t chunks_per_pixel = (spp + chunk - 1) / chunk;
     const int64_t n_items = npix * (int64_t) chunks_per_pixel;
     double *a_wl = calloc(npix, sizeof(double)), *a_l = calloc(npix, sizeof(double)),
-           *a_l2 = calloc(npix, sizeof(double));
+           *a_l2 = calloc(npix, sizeof(double)), *a_st = calloc(4 * npix, sizeof(double));
+    v3 sensor_up;
+    mat_apply_vec(sd->to_world, V(0, 1, 0), &sensor_up);
+    if (sd->type == ERTB_SENSOR_MDISTANT) sensor_up = V(0, 1, 0);
     counters_t total = { 0, 0, 0, 0 };
 
 #pragma omp parallel
@@ -1072,7 +1352,7 @@ int ertbo_render(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_
             uint64_t c0 = (uint64_t) (item % (int64_t) chunks_per_pixel) * chunk;
             uint64_t c1 = c0 + chunk < spp ? c0 + chunk : spp;
             int px = (int) (pix % W), py = (int) (pix / W);
-            double s_wl = 0, s_l = 0, s_l2 = 0;
+            double s_wl = 0, s_l = 0, s_l2 = 0, s_st[4] = { 0, 0, 0, 0 };
             for (uint64_t s = c0; s < c1; ++s) {
                 pcg32 rng;
                 uint64_t gid = ((uint64_t) pix << 40) + (sample_offset + s);
@@ -1082,11 +1362,22 @@ int ertbo_render(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_
                 double ax = next_1d(&rng), ay = next_1d(&rng);
                 ray_t ray;
                 double w = sensor_sample_ray(&S, sd, fx, fy, ax, ay, &ray);
-                double L = volpath_sample(&S, &rng, ray, &C);
+                double L;
+                if (desc->polarized) {
+                    double st[4];
+                    volpath_sample_pol(&S, &rng, ray, sensor_up, &C, st);
+                    L = st[0];
+                    for (int k = 0; k < 4; ++k) s_st[k] += w * st[k];
+                } else {
+                    L = volpath_sample(&S, &rng, ray, &C);
+                }
                 s_wl += w * L; s_l += L; s_l2 += L * L;
             }
 #pragma omp critical
-            { a_wl[pix] += s_wl; a_l[pix] += s_l; a_l2[pix] += s_l2; }
+            {
+                a_wl[pix] += s_wl; a_l[pix] += s_l; a_l2[pix] += s_l2;
+                for (int k = 0; k < 4; ++k) a_st[k * npix + pix] += s_st[k];
+            }
         }
 #pragma omp critical
         {
@@ -1099,7 +1390,8 @@ int ertbo_render(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_
         if (sum_l) sum_l[i] = a_l[i];
         if (sum_l2) sum_l2[i] = a_l2[i];
     }
-    free(a_wl); free(a_l); free(a_l2);
+    if (sum_stokes) memcpy(sum_stokes, a_st, sizeof(double) * 4 * npix);
+    free(a_wl); free(a_l); free(a_l2); free(a_st);
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->n_paths = (uint64_t) npix * spp;
@@ -1173,6 +1465,20 @@ int ertbo_medium_lookup(const ertb_scene_desc *desc, size_t n, const double *p, 
         int l = layer_index(&S, V(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
         st[i] = l >= 0 ? (double) desc->sigma_t_scale * desc->sigma_t[l] : 0.0;
         al[i] = l >= 0 ? desc->albedo[l] : 0.0;
+    }
+    scene_free(&S);
+    return 0;
+}
+
+int ertbo_phase_mueller(const ertb_scene_desc *desc, int leaf, size_t n, const double *wi, const double *wo,
+                        double *mueller, double *pdf) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    if (leaf < 0 || leaf >= desc->n_phase) { scene_free(&S); return fail("bad leaf"); }
+    for (size_t i = 0; i < n; ++i) {
+        mueller_t M;
+        leaf_eval_mueller(&S, leaf, V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), &M, &pdf[i]);
+        memcpy(mueller + 16 * i, M.m, sizeof M.m);
     }
     scene_free(&S);
     return 0;

@@ -26,6 +26,12 @@ int ertbo_render(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_
                  uint64_t sample_offset, double *sum_wl, double *sum_l, double *sum_l2,
                  ertb_render_stats *stats, int n_threads);
 
+int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_t spp,
+                        uint64_t sample_offset, double *sum_wl, double *sum_l, double *sum_l2,
+                        double *sum_stokes, ertb_render_stats *stats, int n_threads);
+int ertbo_phase_mueller(const ertb_scene_desc *desc, int leaf, size_t n, const double *wi, const double *wo,
+                        double *mueller, double *pdf);
+
 /* Point-wise plugin evaluations (double). Same conventions as ertb_kat_*. */
 int ertbo_bsdf_eval(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo,
                     double *out);

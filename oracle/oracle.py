@@ -74,6 +74,34 @@ def render(desc: _abi.SceneDesc, sensor: int = 0, seed: int = 0, spp: int = 1024
     return out[0], out[1], out[2], stats.as_dict()
 
 
+def render_stokes(desc: _abi.SceneDesc, sensor: int = 0, seed: int = 0, spp: int = 1024,
+                  sample_offset: int = 0, n_threads: int = 0):
+    """Returns (sum_wl, sum_l, sum_l2, sum_stokes[4, npix], stats dict)."""
+    lib = load()
+    sd = desc.sensors[sensor]
+    npix = sd.width * sd.height
+    out = [np.zeros(npix, dtype=np.float64) for _ in range(3)]
+    st = np.zeros((4, npix), dtype=np.float64)
+    stats = _abi.RenderStats()
+    _check(
+        lib.ertbo_render_stokes(
+            C.byref(desc), C.c_int(sensor), C.c_uint64(seed), C.c_uint64(spp),
+            C.c_uint64(sample_offset), *[o.ctypes.data_as(dp) for o in out], st.ctypes.data_as(dp),
+            C.byref(stats), C.c_int(n_threads),
+        )
+    )
+    return out[0], out[1], out[2], st, stats.as_dict()
+
+
+def phase_mueller(desc, leaf, wi, wo):
+    wi, wo = _d(wi).reshape(-1, 3), _d(wo).reshape(-1, 3)
+    n = wi.shape[0]
+    M, pdf = np.zeros((n, 4, 4)), np.zeros(n)
+    _check(load().ertbo_phase_mueller(C.byref(desc), C.c_int(leaf), C.c_size_t(n), wi.ctypes.data_as(dp),
+                                      wo.ctypes.data_as(dp), M.ctypes.data_as(dp), pdf.ctypes.data_as(dp)))
+    return M, pdf
+
+
 def bsdf_eval(desc, wi, wo):
     wi, wo = _d(wi).reshape(-1, 3), _d(wo).reshape(-1, 3)
     out = np.zeros(wi.shape[0])

@@ -7,6 +7,25 @@ POMMEROL = dict(w=0.526, theta=13.3, b=0.187, c=(1.0 + 0.273) / 2.0, h=0.083, B_
 VZA5 = {"type": "mdistant", "vza": [-70.0, -35.0, 0.0, 35.0, 70.0], "vaa": 0.0}
 
 
+def polarized_aerosol_scene() -> dict:
+    """Molecular rayleigh_polarized + aerosol tabphase_polarized blend (C5-like, without the ocean)."""
+    d = scenes.atmosphere_scene(geometry="plane_parallel", aerosol=True, aerosol_phase="hg", n_layers=60,
+                                phase={"type": "rayleigh_polarized"}, stokes=True, meridian_align=False,
+                                sza=30.0, saa=0.0, surface={"type": "diffuse", "reflectance": 0.05},
+                                sensor={"type": "mdistant", "vza": [-50.0, -10.0, 40.0], "vaa": 60.0})
+    mu = np.concatenate([np.linspace(-1, 0.6, 33), np.linspace(0.6, 1.0, 41)[1:]])
+    g = 0.65
+    m11 = (1.0 - g * g) / (4.0 * np.pi * (1.0 + g * g - 2.0 * g * mu) ** 1.5)
+    pol = -0.4 * (1 - mu**2) / (1 + mu**2)        # Rayleigh-like linear polarisation, damped
+    fmt = lambda a: ",".join(map(str, a))  # noqa: E731
+    d["phase_atmosphere"]["phase_1"] = {
+        "type": "tabphase_polarized", "nodes": fmt(mu), "m11": fmt(m11), "m12": fmt(pol * m11),
+        "m22": fmt(0.9 * m11), "m33": fmt(0.8 * mu * m11), "m34": fmt(0.1 * (1 - mu**2) * m11),
+        "m44": fmt(0.7 * mu * m11),
+    }
+    return d
+
+
 def battery() -> dict:
     """name -> scene dict.  Small films; every plugin of SURVEY 8a appears at least once."""
     S = scenes.atmosphere_scene
@@ -54,6 +73,17 @@ def battery() -> dict:
                                           "wind_direction": 0.0, "shadowing": False},
                                  sensor={"type": "mdistant", "vza": [-50.0, -35.0, -20.0, 20.0, 50.0],
                                          "vaa": 0.0, "target": [0.0, 3.0e5, 6.3710484e6]}),
+        # polarized (Stokes) transport: rayleigh_polarized / tabphase_polarized + stokes integrator
+        "polarized_rayleigh_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=30.0, stokes=True,
+                                   phase={"type": "rayleigh_polarized", "depolarization": 0.0279},
+                                   surface={"type": "diffuse", "reflectance": 0.1},
+                                   sensor={"type": "mdistant", "vza": [-60.0, -30.0, 0.0, 30.0, 60.0], "vaa": 90.0}),
+        "polarized_rayleigh_spherical_thick": S(geometry="spherical_shell", atmosphere="homogeneous",
+                                                homogeneous_sigma_t=1.0 / scenes.TOA, homogeneous_albedo=0.98,
+                                                phase={"type": "rayleigh_polarized"}, stokes=True, sza=50.0,
+                                                surface={"type": "rpv", "rho_0": 0.1, "k": 0.9, "g": -0.1},
+                                                sensor={"type": "mdistant", "vza": [-70.0, -20.0, 20.0, 70.0], "vaa": 45.0}),
+        "polarized_aerosol_tab_pp": polarized_aerosol_scene(),
         # integrator options
         "volpathmis_thick": S(geometry="plane_parallel", atmosphere="homogeneous", integrator="volpathmis",
                               homogeneous_sigma_t=3.0 / scenes.TOA, homogeneous_albedo=0.95, sensor=VZA5,

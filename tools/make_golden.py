@@ -31,7 +31,11 @@ def main():
         desc = sc.flat.build_desc()
         npix = desc.sensors[0].width * desc.sensors[0].height
         spp = SPP if npix <= 8 else SPP // 2
-        wl, l, l2, st = oracle.render(desc, 0, SEED, spp)
+        stokes = None
+        if desc.polarized:
+            wl, l, l2, stokes, st = oracle.render_stokes(desc, 0, SEED, spp)
+        else:
+            wl, l, l2, st = oracle.render(desc, 0, SEED, spp)
         mean = l / spp
         var = np.maximum(l2 / spp - mean**2, 0) / spp
         out["scenes"][name] = {
@@ -44,6 +48,9 @@ def main():
             "scatter_per_path": st["n_scatter"] / st["n_paths"],
             "surface_per_path": st["n_surface"] / st["n_paths"],
         }
+        if stokes is not None:
+            out["scenes"][name]["stokes"] = (stokes / spp).tolist()
+            out["scenes"][name]["m2"] = (l2 / spp).tolist()
         print(f"{name:40s} mean[0]={mean[0]:.6f} K={(st['trips_main']+st['trips_nee'])/st['n_paths']:.2f}")
     path = os.path.join(ROOT, "tests", "golden", "oracle_renders.json")
     with open(path, "w") as f:
