@@ -179,6 +179,6 @@ def test_seed_state_matches_numpy_seed_sequence():
 
 
 def test_desc_struct_layout_is_stable():
-    assert C.sizeof(_abi.PhaseDesc) == 40
+    assert C.sizeof(_abi.PhaseDesc) == 80
     assert C.sizeof(_abi.RenderStats) == 56
     assert _abi.SceneDesc.sensors.offset + 8 == C.sizeof(_abi.SceneDesc)
