@@ -447,10 +447,6 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
         delete S;
         return set_error("This integrator currently does not support polarized mode!"); // volpathmis.cpp:130-132
     }
-    if (S->polarized && D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
-        delete S;
-        return set_error("ocean_legacy in polarized mode is not implemented yet");
-    }
 
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete S; return set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }

@@ -429,6 +429,46 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                     thr = 0.f; dead = true;
                 } else {
                     float f_sun, weight;
+                    if (POL && P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+                        // Mueller-valued BSDF (polarized Fresnel glint), ocean_legacy.cpp:561-661
+                        f3 fs, ft;
+                        surface_frame<SPH>(n0, fs, ft);
+                        f3 wi = mk3(-dot3(d, fs), -dot3(d, ft), ci);
+                        float Mb[16], v[4] = { 0.f, 0.f, 0.f, 0.f };
+                        if (depth + 1u < P.max_depth) {
+                            f3 ws = mk3(dot3(sun, fs), dot3(sun, ft), dot3(sun, n0));
+                            if (ws.z > 0.f) {
+                                oc_eval_mueller(P, wi, ws, fs, ft, n0, Mb);
+#pragma unroll
+                                for (int r = 0; r < 4; ++r)
+                                    v[r] = fmaf(T[4 * r], Mb[0], fmaf(T[4 * r + 1], Mb[4], fmaf(T[4 * r + 2], Mb[8], T[4 * r + 3] * Mb[12])));
+                            }
+                        }
+                        wnee = v[0] > 0.f ? v[0] * P.irradiance : 0.f;
+                        float inv = v[0] > 0.f ? __fdividef(1.f, v[0]) : 0.f;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) qn[k] = v[k + 1] * inv;
+                        float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
+                        f3 wo;
+                        oc_sample(P, wi, s1, u1, u2, wo);
+                        float pdf = oc_pdf(P, wi, wo);
+                        float Tn[16];
+                        if (pdf > 0.f && wo.z > 0.f) {
+                            oc_eval_mueller(P, wi, wo, fs, ft, n0, Mb);
+                            float ip = __fdividef(1.f, pdf);
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) Mb[k] *= ip;
+                            mueller_mul(T, Mb, Tn);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) Tn[k] = 0.f;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) T[k] = Tn[k];
+                        d = normalize3(fma3(fs, wo.x, fma3(ft, wo.y, scale3(n0, wo.z))));
+                        weight = thr != 0.f ? __fdividef(T[0], thr) : 0.f; // so that thr * weight = T00 below
+                        if (!(weight > 0.f)) weight = 0.f;
+                    } else {
                     surface_interact<SPH>(P, n0, sun, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
                     wnee = thr * f_sun * P.irradiance;
                     if (POL) {
@@ -440,6 +480,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                         for (int r = 0; r < 4; ++r) {
                             T[4 * r] *= weight; T[4 * r + 1] = 0.f; T[4 * r + 2] = 0.f; T[4 * r + 3] = 0.f;
                         }
+                    }
                     }
                     if (flags & PFL_VACUUM) {
                         res += wnee;

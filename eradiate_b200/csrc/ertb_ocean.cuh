@@ -395,3 +395,64 @@ __device__ __forceinline__ float oc_sample(const ErtbParams &P, f3 wi, float s1,
     if (!(pdf > 0.f)) return 0.f;
     return oc_eval(P, wi, wo) / pdf;
 }
+
+// ---------------------------------------------------------------- polarized sun glint
+// fresnel_sunglint_polarized (oceanprops.h:443-545).  `wi` / `wo`: propagation directions of the
+// incident and of the reflected light in the local frame.  Complex arithmetic on float2 (re, im).
+struct cf { float re, im; };
+__device__ __forceinline__ cf cmk(float re, float im) { cf r; r.re = re; r.im = im; return r; }
+__device__ __forceinline__ cf cadd(cf a, cf b) { return cmk(a.re + b.re, a.im + b.im); }
+__device__ __forceinline__ cf csub(cf a, cf b) { return cmk(a.re - b.re, a.im - b.im); }
+__device__ __forceinline__ cf cmul(cf a, cf b) { return cmk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+__device__ __forceinline__ cf cscl(cf a, float s) { return cmk(a.re * s, a.im * s); }
+__device__ __forceinline__ cf cdiv(cf a, cf b) {
+    float d = 1.f / (b.re * b.re + b.im * b.im);
+    return cmk((a.re * b.re + a.im * b.im) * d, (a.im * b.re - a.re * b.im) * d);
+}
+__device__ __forceinline__ cf csqrt_(cf a) {
+    float m = sqrtf(a.re * a.re + a.im * a.im);
+    float re = sqrtf(fmaxf(0.5f * (m + a.re), 0.f)), im = sqrtf(fmaxf(0.5f * (m - a.re), 0.f));
+    return cmk(re, a.im < 0.f ? -im : im);
+}
+__device__ __forceinline__ float cabs2(cf a) { return a.re * a.re + a.im * a.im; }
+__device__ __forceinline__ cf cmulconj(cf a, cf b) { return cmk(a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im); }
+
+__device__ __forceinline__ void oc_fresnel_mueller(float nr, float ni, f3 wi_in, f3 wo_in, float *M) {
+    const cf n1 = cmk(1.f, 0.f), n2 = cmk(nr, ni);
+    float mu_i = fminf(fabsf(wi_in.z), 0.9999999f), mu_o = fminf(fabsf(wo_in.z), 0.9999999f);
+    // phi -> -phi mirrors y: rebuild the unit vectors from (mu, -phi) without trigonometry
+    float si = sqrtf(1.f - mu_i * mu_i), so = sqrtf(1.f - mu_o * mu_o);
+    float ri = rsqrtf(fmaxf(wi_in.x * wi_in.x + wi_in.y * wi_in.y, 1e-30f)), ro = rsqrtf(fmaxf(wo_in.x * wo_in.x + wo_in.y * wo_in.y, 1e-30f));
+    float cpi = (wi_in.x == 0.f && wi_in.y == 0.f) ? 1.f : wi_in.x * ri, spi = (wi_in.x == 0.f && wi_in.y == 0.f) ? 0.f : -wi_in.y * ri;
+    float cpo = (wo_in.x == 0.f && wo_in.y == 0.f) ? 1.f : wo_in.x * ro, spo = (wo_in.x == 0.f && wo_in.y == 0.f) ? 0.f : -wo_in.y * ro;
+    f3 wi = mk3(si * cpi, si * spi, -mu_i), wo = mk3(so * cpo, so * spo, mu_o);
+    f3 kd = mk3(wi.x - wo.x, wi.y - wo.y, wi.z - wo.z);
+    float mu_il = dot3(kd, wi) * rsqrtf(dot3(kd, kd));
+    cf ratio = cdiv(cmul(n1, n1), cmul(n2, n2));
+    cf mu_refr = csqrt_(csub(cmk(1.f, 0.f), cscl(ratio, 1.f - mu_il * mu_il)));
+    cf a = cscl(n1, mu_il), b = cmul(n2, mu_refr), c = cscl(n2, mu_il), d = cmul(n1, mu_refr);
+    cf R_r = cdiv(csub(a, b), cadd(a, b)), R_l = cdiv(csub(c, d), cadd(c, d));
+    // polarisation frames: phi_v = normalize(z x w), theta_v = phi_v x w   (w never vertical: mu <= 0.9999999)
+    f3 pvi = normalize3(mk3(-wi.y, wi.x, 0.f)), pvo = normalize3(mk3(-wo.y, wo.x, 0.f));
+    f3 tvi = mk3(pvi.y * wi.z - pvi.z * wi.y, pvi.z * wi.x - pvi.x * wi.z, pvi.x * wi.y - pvi.y * wi.x);
+    f3 tvo = mk3(pvo.y * wo.z - pvo.z * wo.y, pvo.z * wo.x - pvo.x * wo.z, pvo.x * wo.y - pvo.y * wo.x);
+    float pi_wo = dot3(pvi, wo), po_wi = dot3(pvo, wi), ti_wo = dot3(tvi, wo), to_wi = dot3(tvo, wi);
+    cf f_tt = cadd(cscl(R_r, pi_wo * po_wi), cscl(R_l, ti_wo * to_wi));
+    cf f_tp = cadd(cscl(R_r, -ti_wo * po_wi), cscl(R_l, pi_wo * to_wi));
+    cf f_pt = cadd(cscl(R_r, -pi_wo * to_wi), cscl(R_l, ti_wo * po_wi));
+    cf f_pp = cadd(cscl(R_r, ti_wo * to_wi), cscl(R_l, pi_wo * po_wi));
+    f3 cx = mk3(wi.y * wo.z - wi.z * wo.y, wi.z * wo.x - wi.x * wo.z, wi.x * wo.y - wi.y * wo.x);
+    float c2 = dot3(cx, cx);
+    float coeff = 1.f / fmaxf(c2 * c2, 1e-30f);
+    float tt = cabs2(f_tt), tp = cabs2(f_tp), pt = cabs2(f_pt), pp = cabs2(f_pp);
+    cf ttp = cmulconj(f_tt, f_tp), ptpp = cmulconj(f_pt, f_pp), ttpt = cmulconj(f_tt, f_pt);
+    cf tppp = cmulconj(f_tp, f_pp), ttpp = cmulconj(f_tt, f_pp), tppt = cmulconj(f_tp, f_pt);
+    M[0] = 0.5f * coeff * (tt + tp + pt + pp); M[1] = 0.5f * coeff * (tt - tp + pt - pp);
+    M[2] = -coeff * (ttp.re + ptpp.re); M[3] = -coeff * (ttp.im + ptpp.im);
+    M[4] = 0.5f * coeff * (tt + tp - pt - pp); M[5] = 0.5f * coeff * (tt - tp - pt + pp);
+    M[6] = -coeff * (ttp.re - ptpp.re); M[7] = -coeff * (ttp.im - ptpp.im);
+    M[8] = -coeff * (ttpt.re + tppp.re); M[9] = -coeff * (ttpt.re - tppp.re);
+    M[10] = coeff * (ttpp.re + tppt.re); M[11] = coeff * (ttpp.im - tppt.im);
+    M[12] = coeff * (ttpt.im + tppp.im); M[13] = coeff * (ttpt.im - tppp.im);
+    M[14] = -coeff * (ttpp.im + tppt.im); M[15] = coeff * (ttpp.re - tppt.re);
+}

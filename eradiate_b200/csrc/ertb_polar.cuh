@@ -147,3 +147,49 @@ __device__ __forceinline__ void stokes_output_rotation(const ErtbParams &P, f3 d
     for (int i = 0; i < 16; ++i) R[i] = 0.f;
     R[0] = 1.f; R[5] = c2; R[6] = s2; R[9] = -s2; R[10] = c2; R[15] = 1.f;
 }
+
+#include "ertb_ocean.cuh"
+
+// Polarized ocean BSDF value (times cos) in WORLD implicit Stokes bases (ocean_legacy.cpp:561-661
+// followed by SurfaceInteraction::to_world_mueller).  The reference rotates twice about the same
+// propagation directions (meridian plane -> local implicit basis -> world implicit basis); the two
+// rotations compose, so the meridian-plane axes are carried to world space and rotated once.
+// `wi`, `wo` local (wi = si.wi, wo = towards the light / sampled), (fs, ft, n) = shading frame.
+__device__ __forceinline__ void oc_eval_mueller(const ErtbParams &P, f3 wi, f3 wo, f3 fs, f3 ft, f3 n, float *M) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = 0.f;
+    if (!(wi.z > 0.f && wo.z > 0.f)) return;
+    const float *tdn = P.ocean_tables, *tup = P.ocean_tables + ERTB_OC_RES * ERTB_OC_RES;
+    float wc = P.bsdf[OC_WHITECAP], ul = 0.f;
+    if (P.bsdf[OC_UNDERLIGHT_ON] != 0.f)
+        ul = P.bsdf[OC_UL_NORM] * oc_transmittance(P, tup, wi.z, wo.x, wo.y) * oc_transmittance(P, tdn, wo.z, wo.x, wo.y);
+    const float scale = wo.z * ERTB_INV_PI;
+    // glint geometry factor without Fresnel (eval_glint(wi := wo, wo := si.wi), :405-420)
+    f3 m = normalize3(mk3(wi.x + wo.x, wi.y + wo.y, wi.z + wo.z));
+    float g = oc_beckmann_D(P, m) * oc_gram_charlier(P, m) / (4.f * wi.z * wo.z);
+    if (P.bsdf[OC_SHADOWING] != 0.f) {
+        float G = 1.f / (1.f + oc_lambda(P, wi) + oc_lambda(P, wo));
+        if (dot3(wi, m) * wi.z <= 0.f || dot3(wo, m) * wo.z <= 0.f) G = 0.f;
+        g *= G;
+    }
+    g *= ERTB_PI * (1.f - P.bsdf[OC_COVERAGE]) * scale;
+    f3 in_fwd = neg3(wo), out_fwd = wi; // light arrives along -wo and leaves along si.wi
+    oc_fresnel_mueller(P.bsdf[OC_N_REAL], P.bsdf[OC_N_IMAG], in_fwd, out_fwd, M);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] *= g;
+    // meridian-plane axes (local, normal = z): p = normalize((z x f) x f); fallback (0, 1, 0)
+    f3 z = mk3(0.f, 0.f, 1.f);
+    f3 a_in = cross3(z, in_fwd), a_out = cross3(z, out_fwd);
+    f3 p_in = dot3(a_in, a_in) > 1e-20f ? cross3(a_in, in_fwd) : mk3(0.f, 1.f, 0.f);
+    f3 p_out = dot3(a_out, a_out) > 1e-20f ? cross3(a_out, out_fwd) : mk3(0.f, 1.f, 0.f);
+    // to world
+    f3 in_w = fma3(fs, in_fwd.x, fma3(ft, in_fwd.y, scale3(n, in_fwd.z)));
+    f3 out_w = fma3(fs, out_fwd.x, fma3(ft, out_fwd.y, scale3(n, out_fwd.z)));
+    f3 p_in_w = fma3(fs, p_in.x, fma3(ft, p_in.y, scale3(n, p_in.z)));
+    f3 p_out_w = fma3(fs, p_out.x, fma3(ft, p_out.y, scale3(n, p_out.z)));
+    float ci, si, co, so;
+    basis_rotation(in_w, p_in_w, stokes_basis(in_w), ci, si);
+    basis_rotation(out_w, p_out_w, stokes_basis(out_w), co, so);
+    rotate_mueller(M, ci, si, co, so);
+    M[0] += (wc + (1.f - wc) * ul) * scale; // depolarizer part is rotation invariant
+}

@@ -701,8 +701,7 @@ class FlatScene:
         if self.polarized and self.integrator.kernel_type == "volpathmis":
             # volpathmis.cpp:130-132
             raise RuntimeError("This integrator currently does not support polarized mode!")
-        if self.polarized and self.bsdf.type == "ocean_legacy":
-            raise RuntimeError("ocean_legacy in polarized mode (polarized Fresnel glint) is not implemented yet")
+
 
     def _extract_medium(self) -> None:
         m = self.medium

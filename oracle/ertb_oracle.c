@@ -1182,6 +1182,36 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t
 }
 
 
+
+/* Polarized BSDF value (times cos) in WORLD-space implicit Stokes bases.  Land BSDFs are
+ * depolarizer(value) (rotation invariant).  ocean_legacy.cpp:603-634 builds the glint matrix in
+ * the meridian-plane bases and rotates it to the implicit bases of -wo_hat / wi_hat (local frame);
+ * volpath.cpp:357 / :369 then applies si.to_world_mueller(M, -wo, si.wi) (interaction.h:407-428). */
+static void bsdf_eval_mueller(const scene_t *S, const frame_t *fr, v3 wi, v3 wo, mueller_t *M) {
+    *M = mu_zero();
+    if (S->desc->bsdf_type != ERTB_BSDF_OCEAN_LEGACY) {
+        M->m[0] = bsdf_eval(S, wi, wo);
+        return;
+    }
+    double wil[3] = { wi.x, wi.y, wi.z }, wol[3] = { wo.x, wo.y, wo.z }, dep, gl[16];
+    ocean_eval_polarized(&S->ocean, wil, wol, &dep, gl);
+    mueller_t G; memcpy(G.m, gl, sizeof gl);
+    if (wi.z > 0.0 && wo.z > 0.0) {
+        v3 n = V(0, 0, 1), in_fwd = vneg(wo), out_fwd = wi; /* wo_hat = wo, wi_hat = si.wi */
+        v3 p_in = vnormalize(vcross(vnormalize(vcross(n, in_fwd)), in_fwd));
+        v3 p_out = vnormalize(vcross(vnormalize(vcross(n, out_fwd)), out_fwd));
+        if (isnan(p_in.x) || isnan(p_in.y) || isnan(p_in.z)) p_in = V(0, 1, 0);
+        if (isnan(p_out.x) || isnan(p_out.y) || isnan(p_out.z)) p_out = V(0, 1, 0);
+        G = rotate_mueller_basis(&G, in_fwd, p_in, stokes_basis(in_fwd), out_fwd, p_out, stokes_basis(out_fwd));
+        /* to_world_mueller(M, in_forward_local = -wo, out_forward_local = si.wi) */
+        v3 in_w = to_world(fr, in_fwd), out_w = to_world(fr, out_fwd);
+        G = rotate_mueller_basis(&G, in_w, to_world(fr, stokes_basis(in_fwd)), stokes_basis(in_w),
+                                 out_w, to_world(fr, stokes_basis(out_fwd)), stokes_basis(out_w));
+    }
+    *M = G;
+    M->m[0] += dep;
+}
+
 /* volpath.cpp:93-396 in a polarized variant: Spectrum = 4x4 Mueller matrix.  `throughput` is
  * right-multiplied by every weight (throughput *= w), the emitter value is depolarizer(E), so
  * only the first column of `result` is ever non-zero: it is kept as a Stokes 4-vector.  All the
@@ -1277,13 +1307,21 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, v3 senso
                     v3 ds_d;
                     double emitted = sample_emitter(S, rng, si.p, si.n, medium, C, &ds_d);
                     v3 wo = to_local(&fr, ds_d);
-                    double f = bsdf_eval(S, wi, wo); /* depolarizer(f) */
-                    for (int i = 0; i < 4; ++i) result[i] += T.m[4 * i] * f * emitted;
+                    mueller_t B, TB;
+                    bsdf_eval_mueller(S, &fr, wi, wo, &B);
+                    TB = mu_mul(&T, &B);
+                    for (int i = 0; i < 4; ++i) result[i] += TB.m[4 * i] * emitted;
                 }
                 double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
                 v3 wo;
                 double w = bsdf_sample(S, wi, s1, u1, u2, &wo);
-                mueller_t Dw = mu_zero(); Dw.m[0] = w; /* depolarizer(w) */
+                mueller_t Dw = mu_zero();
+                if (D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) { /* ocean_legacy.cpp:553-558: eval / pdf */
+                    double pdf = ocean_pdf(&S->ocean, wi.x, wi.y, wi.z, wo.x, wo.y, wo.z);
+                    if (pdf > 0.0) { bsdf_eval_mueller(S, &fr, wi, wo, &Dw); Dw = mu_scale(&Dw, 1.0 / pdf); }
+                } else {
+                    Dw.m[0] = w; /* depolarizer(w) */
+                }
                 T = mu_mul(&T, &Dw);
                 wo_world = to_world(&fr, wo);
                 depth++;

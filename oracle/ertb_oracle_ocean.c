@@ -468,3 +468,99 @@ double ocean_sample(const ocean_state_t *o, double wix, double wiy, double wiz, 
     if (!(pdf > 0.0)) return 0.0;
     return ocean_eval(o, wix, wiy, wiz, wo[0], wo[1], wo[2]) / pdf;
 }
+
+/* ------------------------------------------------------------------ polarized glint */
+typedef struct { double re, im; } cplx;
+static cplx c_make(double re, double im) { cplx r = { re, im }; return r; }
+static cplx c_add(cplx a, cplx b) { return c_make(a.re + b.re, a.im + b.im); }
+static cplx c_sub(cplx a, cplx b) { return c_make(a.re - b.re, a.im - b.im); }
+static cplx c_mul(cplx a, cplx b) { return c_make(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+static cplx c_scale(cplx a, double s) { return c_make(a.re * s, a.im * s); }
+static cplx c_div(cplx a, cplx b) { double d = b.re * b.re + b.im * b.im; return c_make((a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d); }
+static cplx c_conj(cplx a) { return c_make(a.re, -a.im); }
+static cplx c_sqrt(cplx a) {
+    double m = sqrt(a.re * a.re + a.im * a.im);
+    double re = sqrt(0.5 * (m + a.re)), im = sqrt(fmax(0.0, 0.5 * (m - a.re)));
+    return c_make(re, a.im < 0.0 ? -im : im);
+}
+static double c_abs2(cplx a) { return a.re * a.re + a.im * a.im; }
+
+/* fresnel_sunglint_polarized (oceanprops.h:443-545): Mueller matrix of the reflection on a facet,
+ * `wi` = propagation direction of the incident light, `wo` = of the reflected light (local frame). */
+static void fresnel_polarized(double nr, double ni, const double wi_in[3], const double wo_in[3], double M[16]) {
+    cplx n1 = c_make(1.0, 0.0), n2 = c_make(nr, ni);
+    double mu_i = fabs(wi_in[2]), mu_o = fabs(wo_in[2]);
+    double phi_i = -atan2(wi_in[1], wi_in[0]), phi_o = -atan2(wo_in[1], wo_in[0]);
+    if (mu_i > 0.9999999) mu_i = 0.9999999;
+    if (mu_o > 0.9999999) mu_o = 0.9999999;
+    double si = sqrt(1.0 - mu_i * mu_i), so = sqrt(1.0 - mu_o * mu_o);
+    double wi[3] = { si * cos(phi_i), si * sin(phi_i), -mu_i }, wo[3] = { so * cos(phi_o), so * sin(phi_o), mu_o };
+    double kd[3] = { wi[0] - wo[0], wi[1] - wo[1], wi[2] - wo[2] };
+    double kd2 = kd[0] * kd[0] + kd[1] * kd[1] + kd[2] * kd[2];
+    double mu_il = (kd[0] * wi[0] + kd[1] * wi[1] + kd[2] * wi[2]) / sqrt(kd2);
+    cplx ratio = c_div(c_mul(n1, n1), c_mul(n2, n2));
+    cplx mu_refr = c_sqrt(c_sub(c_make(1.0, 0.0), c_scale(ratio, 1.0 - mu_il * mu_il)));
+    cplx a = c_scale(n1, mu_il), b = c_mul(n2, mu_refr), c = c_scale(n2, mu_il), d = c_mul(n1, mu_refr);
+    cplx R_r = c_div(c_sub(a, b), c_add(a, b)), R_l = c_div(c_sub(c, d), c_add(c, d));
+    /* polarisation frames */
+    double pvi[3], tvi[3], pvo[3], tvo[3];
+    if (wi[0] == 0.0 && wi[1] == 0.0 && wi[2] == -1.0) { pvi[0] = 0; pvi[1] = 1; pvi[2] = 0; }
+    else { double x = -wi[1], y = wi[0], n = sqrt(x * x + y * y); pvi[0] = x / n; pvi[1] = y / n; pvi[2] = 0; } /* z x wi */
+    tvi[0] = pvi[1] * wi[2] - pvi[2] * wi[1]; tvi[1] = pvi[2] * wi[0] - pvi[0] * wi[2]; tvi[2] = pvi[0] * wi[1] - pvi[1] * wi[0];
+    if (wo[0] == 0.0 && wo[1] == 0.0 && wo[2] == 1.0) { pvo[0] = 0; pvo[1] = 1; pvo[2] = 0; }
+    else { double x = -wo[1], y = wo[0], n = sqrt(x * x + y * y); pvo[0] = x / n; pvo[1] = y / n; pvo[2] = 0; }
+    tvo[0] = pvo[1] * wo[2] - pvo[2] * wo[1]; tvo[1] = pvo[2] * wo[0] - pvo[0] * wo[2]; tvo[2] = pvo[0] * wo[1] - pvo[1] * wo[0];
+    double pi_wo = pvi[0] * wo[0] + pvi[1] * wo[1] + pvi[2] * wo[2], po_wi = pvo[0] * wi[0] + pvo[1] * wi[1] + pvo[2] * wi[2];
+    double ti_wo = tvi[0] * wo[0] + tvi[1] * wo[1] + tvi[2] * wo[2], to_wi = tvo[0] * wi[0] + tvo[1] * wi[1] + tvo[2] * wi[2];
+    cplx f_tt = c_add(c_scale(R_r, pi_wo * po_wi), c_scale(R_l, ti_wo * to_wi));
+    cplx f_tp = c_add(c_scale(R_r, -ti_wo * po_wi), c_scale(R_l, pi_wo * to_wi));
+    cplx f_pt = c_add(c_scale(R_r, -pi_wo * to_wi), c_scale(R_l, ti_wo * po_wi));
+    cplx f_pp = c_add(c_scale(R_r, ti_wo * to_wi), c_scale(R_l, pi_wo * po_wi));
+    double cx[3] = { wi[1] * wo[2] - wi[2] * wo[1], wi[2] * wo[0] - wi[0] * wo[2], wi[0] * wo[1] - wi[1] * wo[0] };
+    double c2 = cx[0] * cx[0] + cx[1] * cx[1] + cx[2] * cx[2];
+    int collinear = wo[0] == -wi[0] && wo[1] == -wi[1] && wo[2] == -wi[2];
+    double coeff = 1.0 / (collinear ? 0.000001 : c2 * c2);
+    double tt = c_abs2(f_tt), tp = c_abs2(f_tp), pt = c_abs2(f_pt), pp = c_abs2(f_pp);
+    cplx ttp = c_mul(f_tt, c_conj(f_tp)), ptpp = c_mul(f_pt, c_conj(f_pp));
+    cplx ttpt = c_mul(f_tt, c_conj(f_pt)), tppp = c_mul(f_tp, c_conj(f_pp));
+    cplx ttpp = c_mul(f_tt, c_conj(f_pp)), tppt = c_mul(f_tp, c_conj(f_pt));
+    M[0] = 0.5 * coeff * (tt + tp + pt + pp); M[1] = 0.5 * coeff * (tt - tp + pt - pp);
+    M[2] = -coeff * (ttp.re + ptpp.re); M[3] = -coeff * (ttp.im + ptpp.im);
+    M[4] = 0.5 * coeff * (tt + tp - pt - pp); M[5] = 0.5 * coeff * (tt - tp - pt + pp);
+    M[6] = -coeff * (ttp.re - ptpp.re); M[7] = -coeff * (ttp.im - ptpp.im);
+    M[8] = -coeff * (ttpt.re + tppp.re); M[9] = -coeff * (ttpt.re - tppp.re);
+    M[10] = coeff * (ttpp.re + tppt.re); M[11] = coeff * (ttpp.im - tppt.im);
+    M[12] = coeff * (ttpt.im + tppp.im); M[13] = coeff * (ttpt.im - tppp.im);
+    M[14] = -coeff * (ttpp.im + tppt.im); M[15] = coeff * (ttpp.re - tppt.re);
+}
+
+/* Scalar factor of the glint lobe without the Fresnel term (eval_glint, :405-420) */
+static double glint_geometry(const ocean_state_t *o, const double wi[3], const double wo[3]) {
+    beckmann_t B = beckmann_make(o);
+    double m[3] = { wi[0] + wo[0], wi[1] + wo[1], wi[2] + wo[2] };
+    double inv = 1.0 / sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+    m[0] *= inv; m[1] *= inv; m[2] *= inv;
+    double gc = gram_charlier(o->wind_direction, o->wind_speed, sqrt(o->sigma_u2), sqrt(o->sigma_c2), m);
+    double result = beckmann_eval(&B, m) * (gc > 0.0 ? gc : 0.0) / (4.0 * wi[2] * wo[2]);
+    if (o->shadowing) result *= beckmann_g_hc(&B, wi, wo, m);
+    return result * PI;
+}
+
+/* Polarized BSDF::eval in Radiance mode (:561-661) BEFORE the basis rotations: returns the
+ * depolarizing part `dep` (whitecaps + underlight, times cos/pi), and the glint Mueller matrix in
+ * the meridian-plane bases (times (1 - coverage) cos/pi). */
+void ocean_eval_polarized(const ocean_state_t *o, const double wi_si[3], const double wo[3], double *dep, double glint[16]) {
+    for (int i = 0; i < 16; ++i) glint[i] = 0.0;
+    *dep = 0.0;
+    if (!(wi_si[2] > 0.0 && wo[2] > 0.0)) return;
+    const double *wo_hat = wo, *wi_hat = wi_si;
+    double wc = o->whitecap_reflectance;
+    double ul = eval_underlight(o, wo_hat, wi_hat);
+    double scale = wo[2] / PI;
+    *dep = (wc + (1.0 - wc) * ul) * scale;
+    double g = glint_geometry(o, wo_hat, wi_hat);
+    double minus_wi[3] = { -wo_hat[0], -wo_hat[1], -wo_hat[2] }; /* eval_glint(wi := wo_hat, wo := wi_hat): F(-wi, wo) */
+    double F[16];
+    fresnel_polarized(o->n_real, o->n_imag, minus_wi, wi_hat, F);
+    for (int i = 0; i < 16; ++i) glint[i] = F[i] * g * (1.0 - o->whitecap_coverage) * scale;
+}

@@ -17,4 +17,5 @@ void ocean_free(ocean_state_t *o);
 double ocean_eval(const ocean_state_t *o, double wix, double wiy, double wiz, double wox, double woy, double woz);
 double ocean_sample(const ocean_state_t *o, double wix, double wiy, double wiz, double s1, double u1, double u2, double *wo);
 double ocean_pdf(const ocean_state_t *o, double wix, double wiy, double wiz, double wox, double woy, double woz);
+void ocean_eval_polarized(const ocean_state_t *o, const double wi_si[3], const double wo[3], double *dep, double glint[16]);
 #endif

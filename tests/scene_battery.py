@@ -84,6 +84,12 @@ def battery() -> dict:
                                                 surface={"type": "rpv", "rho_0": 0.1, "k": 0.9, "g": -0.1},
                                                 sensor={"type": "mdistant", "vza": [-70.0, -20.0, 20.0, 70.0], "vaa": 45.0}),
         "polarized_aerosol_tab_pp": polarized_aerosol_scene(),
+        # C5-like: polarized ocean glint (complex Fresnel Mueller matrix) under a Rayleigh atmosphere
+        "polarized_ocean_pp": S(geometry="plane_parallel", n_layers=60, sza=40.0, saa=0.0, stokes=True,
+                                phase={"type": "rayleigh_polarized"},
+                                surface={"type": "ocean_legacy", "wavelength": 550.0, "wind_speed": 5.0,
+                                         "wind_direction": 30.0, "shadowing": True},
+                                sensor={"type": "mdistant", "vza": [-60.0, -40.0, -20.0, 20.0, 50.0], "vaa": 25.0}),
         # integrator options
         "volpathmis_thick": S(geometry="plane_parallel", atmosphere="homogeneous", integrator="volpathmis",
                               homogeneous_sigma_t=3.0 / scenes.TOA, homogeneous_albedo=0.95, sensor=VZA5,
