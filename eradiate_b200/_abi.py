@@ -59,6 +59,7 @@ PARAM_PHASE_VALUES = 3
 PARAM_BSDF_PARAMS = 4
 PARAM_IRRADIANCE = 5
 PARAM_PHASE_PARAMS = 6
+PARAM_PHASE_MUELLER = 7
 
 c_float_p = C.POINTER(C.c_float)
 c_double_p = C.POINTER(C.c_double)

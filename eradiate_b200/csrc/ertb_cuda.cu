@@ -515,6 +515,14 @@ int ertb_scene_update(ertb_scene *S, int param, int index, const float *data, si
             if (need(4)) return 1;
             memcpy(S->phase[index].params, data, 4 * sizeof(float));
             break;
+        case ERTB_PARAM_PHASE_MUELLER: {
+            int leaf = index / 5, k = index % 5;
+            if (index < 0 || leaf >= S->n_phase || S->phase[leaf].type != ERTB_PHASE_TABULATED_POLARIZED)
+                return set_error("invalid polarized phase leaf index");
+            if (need(S->phase[leaf].values.size())) return 1;
+            S->phase[leaf].mueller[k].assign(data, data + count);
+            break;
+        }
         case ERTB_PARAM_BSDF_PARAMS:
             if (need(ERTB_MAX_BSDF_PARAMS)) return 1;
             memcpy(S->bsdf_params, data, sizeof S->bsdf_params);

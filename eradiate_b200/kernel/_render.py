@@ -118,6 +118,10 @@ class DeviceScene:
                 push(_abi.PARAM_PHASE_PARAMS, i, np.asarray(params))
                 if values is not None:
                     push(_abi.PARAM_PHASE_VALUES, i, values)
+                mu = _scene._phase_leaf_mueller(ph)
+                if mu is not None:
+                    for k, arr in enumerate(mu):
+                        push(_abi.PARAM_PHASE_MUELLER, 5 * i + k, arr)
         push(_abi.PARAM_BSDF_PARAMS, 0, flat.bsdf_params())
         push(_abi.PARAM_IRRADIANCE, 0, [flat.emitter.children["irradiance"].values["value"]])
         self._mark_clean()

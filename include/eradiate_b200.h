@@ -178,7 +178,8 @@ enum ertb_param {
     ERTB_PARAM_PHASE_VALUES = 3, /* index = leaf; float[n_nodes] */
     ERTB_PARAM_BSDF_PARAMS = 4,  /* float[ERTB_MAX_BSDF_PARAMS] */
     ERTB_PARAM_IRRADIANCE = 5,   /* float[1] */
-    ERTB_PARAM_PHASE_PARAMS = 6  /* index = leaf; float[4] */
+    ERTB_PARAM_PHASE_PARAMS = 6, /* index = leaf; float[4] */
+    ERTB_PARAM_PHASE_MUELLER = 7 /* index = leaf * 5 + k (k: m12, m22, m33, m34, m44); float[n_nodes] */
 };
 
 typedef struct ertb_render_stats {
