@@ -144,9 +144,5 @@ def test_polarized_flags_and_errors():
                                 integrator="volpathmis", stokes=True)
     with pytest.raises(RuntimeError, match="does not support polarized mode"):
         mi_load_dict(d)
-    d = scenes.atmosphere_scene(geometry="plane_parallel", n_layers=10, phase={"type": "rayleigh_polarized"},
-                                stokes=True, surface={"type": "ocean_legacy", "wavelength": 550.0})
-    with pytest.raises(RuntimeError, match="ocean_legacy in polarized mode"):
-        mi_load_dict(d)
     sc = mi_load_dict(scenes.atmosphere_scene(geometry="plane_parallel", n_layers=10, stokes=True))
     assert sc.integrator().stokes and sc.integrator().moment and sc.flat.polarized
