@@ -50,6 +50,7 @@ TARGET_DISK = 3
 # enum ertb_integrator_type
 INTEGRATOR_VOLPATH = 0
 INTEGRATOR_VOLPATHMIS = 1
+INTEGRATOR_PIECEWISE_VOLPATH = 2
 
 # enum ertb_param
 PARAM_SIGMA_T = 0

@@ -224,10 +224,10 @@ class Scene(Object):
 # ------------------------------------------------------------------------------
 
 _SUPPORTED = {
-    "integrator": {"volpath", "volpathmis", "moment", "stokes"},
+    "integrator": {"volpath", "volpathmis", "piecewise_volpath", "moment", "stokes"},
     "emitter": {"directional"},
     "shape": {"sphere", "cube", "rectangle", "arectangle"},
-    "medium": {"heterogeneous", "homogeneous"},
+    "medium": {"heterogeneous", "homogeneous", "piecewise"},
     "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "null"},
     "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
               "rayleigh_polarized", "tabphase_polarized"},
@@ -237,9 +237,6 @@ _SUPPORTED = {
 _KIND_OF = {ty: kind for kind, types in _SUPPORTED.items() for ty in types}
 # plugins the reference ships for this slot but that this kernel does not (yet) implement
 _KNOWN_UNSUPPORTED = {
-    "piecewise_volpath": "the analytic piecewise integrator is a 'next' row (SURVEY 8f-1); "
-    "pass integrator={'type': 'volpath'} and atmosphere.force_majorant=True",
-    "piecewise": "the piecewise medium is a 'next' row (SURVEY 8f-1); use force_majorant=True",
     "path": "surface-only integrators are out of scope",
     "perspective": "perspective sensors (canopy scenes) are a 'next' row (SURVEY 8f-3)",
 }
@@ -566,7 +563,7 @@ class _Loader:
                 raise RuntimeError(
                     f"unsupported plugin '{inner['type']}': {_KNOWN_UNSUPPORTED[inner['type']]}"
                 )
-            if inner["type"] not in ("volpath", "volpathmis"):
+            if inner["type"] not in ("volpath", "volpathmis", "piecewise_volpath"):
                 raise RuntimeError(f"unsupported nested integrator '{inner['type']}'")
         it.kernel_type = inner["type"]
         it.max_depth = int(inner.get("max_depth", -1))
@@ -707,6 +704,17 @@ class FlatScene:
         m = self.medium
         st, al = m.children["sigma_t"], m.children["albedo"]
         self.homogeneous = m.type == "homogeneous"
+        if self.integrator.kernel_type == "piecewise_volpath" and m.type != "piecewise":
+            # MI/src/render/medium.cpp:99-118: only ERP/media/piecewise.cpp overrides the *_real interface
+            cls = "HomogeneousMedium" if self.homogeneous else "HeterogeneousMedium"
+            raise RuntimeError(f"{cls}::sample_interaction_real(): not implemented!")
+        if m.type == "piecewise":
+            # piecewise.cpp:445-456: a stack of horizontal layers, grid shape [1, 1, N] along z
+            if self.geometry == _abi.GEOM_SPHERICAL_SHELL:
+                raise RuntimeError("PiecewiseMedium: plane-parallel layer stacks only "
+                                   "(src/eradiate/experiments/_helpers.py:127-165)")
+            if st.type == "gridvolume" and (st.values["data"].shape[1] != 1 or st.values["data"].shape[2] != 1):
+                raise RuntimeError("PiecewiseMedium: x or y resolution bigger than one, assumed shape is [1,1,n]")
         if self.homogeneous:
             if st.type != "constvolume" or al.type != "constvolume":
                 raise RuntimeError("homogeneous medium expects constant sigma_t / albedo")
@@ -883,7 +891,8 @@ class FlatScene:
         d.irradiance = self.emitter.children["irradiance"].values["value"]
         it = self.integrator
         d.integrator = (
-            _abi.INTEGRATOR_VOLPATHMIS if it.kernel_type == "volpathmis" else _abi.INTEGRATOR_VOLPATH
+            {"volpathmis": _abi.INTEGRATOR_VOLPATHMIS,
+             "piecewise_volpath": _abi.INTEGRATOR_PIECEWISE_VOLPATH}.get(it.kernel_type, _abi.INTEGRATOR_VOLPATH)
         )
         d.rr_depth = it.rr_depth
         d.max_depth = it.max_depth

@@ -115,8 +115,16 @@ def atmosphere_scene(
     phase: dict | None = None,
     stokes: bool = False,
     meridian_align: bool = True,
+    force_majorant: bool | None = None,
 ) -> dict:
-    """Build the nested scene dict an ``AtmosphereExperiment`` would emit."""
+    """Build the nested scene dict an ``AtmosphereExperiment`` would emit.
+
+    ``force_majorant`` mirrors ``scenes/atmosphere/_core.py:354,650``: a plane-parallel
+    atmosphere is emitted as a ``piecewise`` medium unless it is set (default: set for every
+    integrator except ``piecewise_volpath``, so that the two media can be compared).
+    """
+    if force_majorant is None:
+        force_majorant = integrator != "piecewise_volpath"
     if surface is None:
         surface = {"type": "rpv", "rho_0": 0.027685, "k": 0.95, "g": -0.1}  # atmospheres.py:100
     surface = _spectrumify(dict(surface))
@@ -222,7 +230,7 @@ def atmosphere_scene(
             }
         else:
             medium = {
-                "type": "heterogeneous",
+                "type": "heterogeneous" if (spherical or force_majorant) else "piecewise",
                 "sigma_t": _volume(sigma_t, spherical, planet_radius, toa, width),
                 "albedo": _volume(albedo, spherical, planet_radius, toa, width),
             }

@@ -83,7 +83,11 @@ enum ertb_target_type {
 
 enum ertb_integrator_type {
     ERTB_INTEGRATOR_VOLPATH = 0,   /* MI/src/integrators/volpath.cpp:93-572 */
-    ERTB_INTEGRATOR_VOLPATHMIS = 1 /* MI/src/integrators/volpathmis.cpp:124-669 (mono: 1x1 weights) */
+    ERTB_INTEGRATOR_VOLPATHMIS = 1, /* MI/src/integrators/volpathmis.cpp:124-669 (mono: 1x1 weights) */
+    /* ERP/integrators/piecewise_volpath.cpp:91-527 over ERP/media/piecewise.cpp:183-429: analytic
+     * free-flight sampling and exact shadow-ray transmittance through the layer stack.  Plane-parallel
+     * heterogeneous media only (src/eradiate/experiments/_helpers.py:127-165). */
+    ERTB_INTEGRATOR_PIECEWISE_VOLPATH = 2
 };
 
 /* One leaf of the (flattened) phase-function tree. */

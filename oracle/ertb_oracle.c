@@ -289,12 +289,17 @@ typedef struct {
     int has_distr[ERTB_MAX_PHASE];
     v3 emitter_d;               /* normalised propagation direction */
     ocean_state_t ocean;        /* ocean_legacy precomputed tables */
+    double *pw_cum, *pw_rcum;   /* piecewise.cpp m_cum_opt_thickness / m_reverse_cum_opt_thickness */
+    double pp_half_width;       /* > 0: finite slab bbox in x, y (known-answer tests only) */
 } scene_t;
+
+static int piecewise_init(scene_t *S);
 
 static void scene_free(scene_t *S) {
     for (int i = 0; i < ERTB_MAX_PHASE; ++i)
         if (S->has_distr[i]) distr_free(&S->distr[i]);
     ocean_free(&S->ocean);
+    free(S->pw_cum); free(S->pw_rcum);
 }
 
 static int scene_init(scene_t *S, const ertb_scene_desc *d) {
@@ -318,6 +323,12 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
                 if (distr_init(&S->distr[i], nodes, p->values, p->n_nodes)) return 1;
                 S->has_distr[i] = 1;
             }
+        }
+        if (d->integrator == ERTB_INTEGRATOR_PIECEWISE_VOLPATH) {
+            /* medium.cpp:99-118: only the piecewise medium implements the *_real interface;
+             * src/eradiate/experiments/_helpers.py:127-165: plane-parallel geometry only */
+            if (d->homogeneous || S->spherical) return fail("sample_interaction_real is not implemented for this medium");
+            if (piecewise_init(S)) return 1;
         }
     }
     S->emitter_d = vnormalize(V(d->emitter_direction[0], d->emitter_direction[1], d->emitter_direction[2]));
@@ -446,6 +457,7 @@ static int medium_aabb(const scene_t *S, const ray_t *ray, double *mint, double 
         for (int i = 0; i < 3; ++i) { lo[i] = -d->medium_top; hi[i] = d->medium_top; }
     } else {
         lo[0] = lo[1] = -INFINITY; hi[0] = hi[1] = INFINITY;
+        if (S->pp_half_width > 0.0) { lo[0] = lo[1] = -S->pp_half_width; hi[0] = hi[1] = S->pp_half_width; }
         lo[2] = d->medium_bottom; hi[2] = d->medium_top;
     }
     double o[3] = { ray->o.x, ray->o.y, ray->o.z }, dd[3] = { ray->d.x, ray->d.y, ray->d.z };
@@ -502,6 +514,151 @@ static mei_t sample_interaction(const scene_t *S, const ray_t *ray, double sampl
         mei.sigma_n = m - st;
     }
     return mei;
+}
+
+/* ------------------------------------------------------ piecewise medium */
+/* ERP/media/piecewise.cpp:445-507 precompute_optical_thickness: running sums of the layer
+ * extinctions (not yet multiplied by the layer thickness), bottom-up and top-down. */
+static int piecewise_init(scene_t *S) {
+    const ertb_scene_desc *d = S->desc;
+    int n = d->n_layers;
+    S->pw_cum = (double *) malloc(sizeof(double) * (size_t) (n > 0 ? n : 1));
+    S->pw_rcum = (double *) malloc(sizeof(double) * (size_t) (n > 0 ? n : 1));
+    if (!S->pw_cum || !S->pw_rcum) return fail("out of memory");
+    double c = 0.0;
+    for (int i = 0; i < n; ++i) { c += (double) d->sigma_t_scale * (double) d->sigma_t[i]; S->pw_cum[i] = c; }
+    c = 0.0;
+    for (int i = n - 1; i >= 0; --i) { c += (double) d->sigma_t_scale * (double) d->sigma_t[i]; S->pw_rcum[n - 1 - i] = c; }
+    return 0;
+}
+
+static double pw_sigma_t(const scene_t *S, int l) {
+    return (double) S->desc->sigma_t_scale * (double) S->desc->sigma_t[l];
+}
+
+static int pw_cell(const scene_t *S, double z) {
+    const ertb_scene_desc *d = S->desc;
+    double voxel = (d->medium_top - d->medium_bottom) / d->n_layers;
+    double f = floor((z - d->medium_bottom) / voxel);
+    if (!(f > 0.0)) return 0; /* also NaN / -inf */
+    return f > (double) (d->n_layers - 1) ? d->n_layers - 1 : (int) f;
+}
+
+/* drjit util.h:135-181 binary_search: first index of [start, end) where pred is false, else end */
+static int pw_bsearch(const double *table, int start, int end, double a, double offset) {
+    int iterations = start < end ? (31 - __builtin_clz((unsigned) (end - start))) + 1 : 0;
+    for (int i = 0; i < iterations; ++i) {
+        int middle = (start + end) >> 1;
+        int cond = a > (table[middle] - offset);
+        if (cond) start = middle + 1 < end ? middle + 1 : end;
+        else end = middle;
+    }
+    return start;
+}
+
+/* piecewise.cpp:183-332 sample_interaction_real: analytic free-flight sampling through the
+ * stack of homogeneous layers.  `aabb` = (active, mint, maxt) of the medium bbox. */
+static mei_t pw_sample_interaction_real(const scene_t *S, const ray_t *ray, double si_t, double sample,
+                                        int aabb_hit, double mint, double maxt, double *tr_out, double *pdf_out) {
+    const ertb_scene_desc *d = S->desc;
+    const int n = d->n_layers;
+    const double voxel = (d->medium_top - d->medium_bottom) / n, inv_voxel = 1.0 / voxel;
+    mei_t mei; memset(&mei, 0, sizeof mei);
+    mei.wi = vneg(ray->d);
+    mei.layer = -1;
+    int active = aabb_hit && (isfinite(mint) || isfinite(maxt));
+    if (!active) { mint = 0.0; maxt = INFINITY; }
+    mint = fmax(0.0, mint);
+    maxt = fmin(si_t, fmin(ray->maxt, maxt));
+    int escaped = !active;
+    mei.mint = mint;
+    mei.t = mint;
+    double cum_opt_thick = 0.0, sampled_t = INFINITY, tr = 0.0, pdf = 0.0;
+    double n_dot_d = fabs(vnormalize(ray->d).z);
+    double delta = n_dot_d == 0.0 ? INFINITY : voxel / n_dot_d;
+    double idelta = 1.0 / delta;
+    int going_up = ray->d.z >= 0.0;
+    int start_idx = pw_cell(S, ray_at(ray, mint).z);
+    int end_idx = pw_cell(S, ray_at(ray, maxt).z);
+    int same_cell = start_idx == end_idx;
+    int opt_start = going_up ? start_idx : n - 1 - start_idx;
+    int opt_end = going_up ? end_idx : n - 1 - end_idx;
+    int index = opt_start;
+    double start_height = (ray_at(ray, mint + RAY_EPS).z - d->medium_bottom) * inv_voxel - (double) start_idx;
+    if (going_up) start_height = 1.0 - start_height;
+    double sigma_t = pw_sigma_t(S, pw_cell(S, ray_at(ray, mint).z));
+    const double *table = going_up ? S->pw_cum : S->pw_rcum;
+    double offset = active ? table[opt_start] : 0.0;
+    offset -= start_height * sigma_t;
+    double log_sample = log(1.0 - sample);
+    int search = active && !same_cell;
+    if (search) index = pw_bsearch(table, opt_start, opt_end, -log_sample * idelta, offset);
+    same_cell |= index == opt_start;
+    search = search && !same_cell;
+    if (search) {
+        mei.t += (start_height + (double) (index - opt_start - 1)) * delta;
+        cum_opt_thick = (table[index - 1] - offset) * delta;
+    }
+    int cell = going_up ? index : n - 1 - index;
+    if (!same_cell) sigma_t = pw_sigma_t(S, cell);
+    escaped |= mei.t > maxt;
+    int sampled = !escaped;
+    if (sampled) sampled_t = -(1.0 / sigma_t) * (log_sample + cum_opt_thick) + mei.t;
+    escaped |= sampled && sampled_t > maxt;
+    sampled |= escaped;
+    if (sampled) {
+        if (escaped) sampled_t = maxt;
+        tr = exp(-(sampled_t - mei.t) * sigma_t - cum_opt_thick);
+        pdf = sampled_t == maxt ? tr : tr * sigma_t;
+    }
+    mei.t = !escaped ? sampled_t : INFINITY;
+    if (!escaped) {
+        mei.p = ray_at(ray, mei.t);
+        mei.layer = cell;
+        mei.sigma_t = sigma_t;
+        mei.sigma_s = sigma_t * (double) d->albedo[cell];
+        mei.sigma_n = 0.0;
+        mei.combined = sigma_t;
+    }
+    *tr_out = tr; *pdf_out = pdf;
+    return mei;
+}
+
+/* piecewise.cpp:335-429 eval_transmittance_pdf_real: exact transmittance of the ray segment
+ * clipped to the medium bbox.  Returns the `escaped` mask. */
+static int pw_eval_transmittance_pdf_real(const scene_t *S, const ray_t *ray, double si_t, int aabb_hit,
+                                          double mint, double maxt, double *tr_out, double *pdf_out) {
+    const ertb_scene_desc *d = S->desc;
+    const int n = d->n_layers;
+    const double voxel = (d->medium_top - d->medium_bottom) / n, inv_voxel = 1.0 / voxel;
+    int active = aabb_hit && (isfinite(mint) || isfinite(maxt));
+    mint = fmax(0.0, mint);
+    int escaped = active && ((maxt >= ray->maxt) || (maxt >= si_t));
+    maxt = active ? fmin(ray->maxt, fmin(maxt, si_t)) : INFINITY;
+    maxt = fmax(0.0, maxt);
+    double n_dot_d = fabs(vnormalize(ray->d).z);
+    double delta = n_dot_d == 0.0 ? INFINITY : voxel / n_dot_d;
+    int going_up = ray->d.z >= 0.0;
+    double zs = ray_at(ray, mint).z, ze = ray_at(ray, maxt).z;
+    int start_idx = pw_cell(S, zs), end_idx = pw_cell(S, ze);
+    int same_cell = start_idx == end_idx;
+    double start_height = (zs - d->medium_bottom) * inv_voxel - (double) start_idx;
+    double end_height = (ze - d->medium_bottom) * inv_voxel - (double) end_idx;
+    if (going_up) start_height = 1.0 - start_height;
+    else end_height = 1.0 - end_height;
+    double s_sigma_t = pw_sigma_t(S, start_idx), e_sigma_t = pw_sigma_t(S, end_idx);
+    int hi = start_idx > end_idx ? start_idx : end_idx, lo = start_idx < end_idx ? start_idx : end_idx;
+    int max_idx = active ? (hi - 1 > 0 ? hi - 1 : 0) : 0;
+    int min_idx = active ? (lo > 0 ? lo : 0) : 0;
+    int use_precomputed = active && max_idx > min_idx;
+    double cum = use_precomputed ? S->pw_cum[max_idx] - S->pw_cum[min_idx] : 0.0;
+    cum += s_sigma_t * start_height + e_sigma_t * end_height;
+    cum *= delta;
+    double opt_thick = active ? (same_cell ? (maxt - mint) * s_sigma_t : cum) : 0.0;
+    double tr = active ? exp(-opt_thick) : 0.0;
+    double pdf = active ? ((si_t < maxt || ray->maxt < maxt) ? tr : tr * e_sigma_t) : 0.0;
+    *tr_out = tr; *pdf_out = pdf;
+    return escaped;
 }
 
 /* ---------------------------------------------------------------- phase */
@@ -1073,11 +1230,69 @@ static double sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n, i
     return transmittance * emitter_val;
 }
 
+/* piecewise_volpath.cpp:404-527 sample_emitter: one exact transmittance evaluation per medium
+ * segment instead of ratio tracking. */
+static double pw_sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n, int medium,
+                                counters_t *C, v3 *ds_d) {
+    const ertb_scene_desc *D = S->desc;
+    (void) next_1d(rng); (void) next_1d(rng); /* next_2d, piecewise_volpath.cpp:413 */
+    v3 d = S->emitter_d; /* directional.cpp:171-201 */
+    v3 c = V(D->bsphere_center[0], D->bsphere_center[1], D->bsphere_center[2]);
+    double brad = fmax(RAY_EPS, D->bsphere_radius * (1.0 + RAY_EPS));
+    double radius = fmax(brad, vnorm(vsub(ref_p, c)));
+    double dist = 2.0 * radius;
+    v3 ds_p = vfma(d, -dist, ref_p);
+    *ds_d = vneg(d);
+    double emitter_val = D->irradiance;
+
+    ray_t ray = spawn_ray_to(ref_p, ref_n, ds_p);
+    double max_dist = ray.maxt, total_dist = 0.0, transmittance = 1.0;
+    int active = 1;
+    while (active) {
+        double remaining = max_dist - total_dist;
+        ray.maxt = remaining;
+        if (!(remaining > 0.0)) break;
+        C->trips_nee++;
+        si_t si = scene_intersect(S, &ray);
+        int escaped = 0, active_medium = medium, active_surface = si.t < INFINITY;
+        if (active_medium) total_dist += fmin(ray.maxt, si.t);
+        if (active_surface && !active_medium) total_dist += si.t;
+        if (active_medium) {
+            double mint, maxt, tr, pdf;
+            int hit = medium_aabb(S, &ray, &mint, &maxt);
+            escaped = pw_eval_transmittance_pdf_real(S, &ray, si.t, hit, mint, maxt, &tr, &pdf);
+            transmittance *= tr; /* "exact estimation" */
+            active_medium = !escaped;
+        }
+        if (active_surface) {
+            transmittance *= si.shape == SHAPE_TOA ? 1.0 : 0.0; /* eval_null_transmission */
+            ray = spawn_ray(si.p, si.n, ray.d);
+        }
+        ray.maxt = remaining;
+        active = (active_medium || active_surface) && transmittance != 0.0;
+        if (active_surface && si.shape == SHAPE_TOA) medium = target_medium(si.n, ray.d);
+    }
+    return transmittance * emitter_val;
+}
+
+/* piecewise_volpath.cpp:215-246: intersect, analytic free flight, tr / pdf weight */
+static double pw_medium_step(const scene_t *S, pcg32 *rng, const ray_t *ray, si_t *si,
+                             int *needs_intersection, mei_t *mei) {
+    if (*needs_intersection) *si = scene_intersect(S, ray);
+    *needs_intersection = 0;
+    double mint, maxt, tr, pdf;
+    int hit = medium_aabb(S, ray, &mint, &maxt);
+    *mei = pw_sample_interaction_real(S, ray, si->t, next_1d(rng), hit, mint, maxt, &tr, &pdf);
+    if (si->t < mei->t) mei->t = INFINITY;
+    return pdf > 0.0 ? tr / pdf : 0.0;
+}
+
 /* volpath.cpp:93-396 (mono, unpolarized).  mis != 0 selects the volpathmis.cpp
  * Russian-roulette placement (:227-231), the only difference left in mono. */
 static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t *C) {
     const ertb_scene_desc *D = S->desc;
     const int mis = D->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
+    const int pw = D->integrator == ERTB_INTEGRATOR_PIECEWISE_VOLPATH;
     const uint64_t max_depth = D->max_depth < 0 ? (uint64_t) 0xffffffffu : (uint64_t) D->max_depth;
     double throughput = 1.0, result = 0.0, eta = 1.0;
     int medium = 0; /* sensors sit outside the atmosphere */
@@ -1103,7 +1318,12 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t
         int escaped = 0, null_scatter = 0, medium_scatter = 0;
         mei_t mei; memset(&mei, 0, sizeof mei);
 
-        if (active_medium) { /* :218-259 */
+        if (active_medium && pw) {
+            throughput *= pw_medium_step(S, rng, &ray, &si, &needs_intersection, &mei);
+            escaped = !(mei.t < INFINITY);
+            active_medium = mei.t < INFINITY;
+            if (active_medium) { medium_scatter = 1; depth++; }
+        } else if (active_medium) { /* :218-259 */
             mei = sample_interaction(S, &ray, next_1d(rng));
             if (D->homogeneous && mei.t < INFINITY) ray.maxt = mei.t;
             if (needs_intersection) si = scene_intersect(S, &ray);
@@ -1133,7 +1353,7 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t
             C->n_scatter++;
             throughput *= mei.sigma_s / (mei.sigma_t / mei.combined);
             v3 ds_d;
-            double emitted = sample_emitter(S, rng, mei.p, V(0, 0, 0), medium, C, &ds_d);
+            double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, mei.p, V(0, 0, 0), medium, C, &ds_d);
             double pv, ppdf;
             phase_eval_pdf(S, mei.layer, mei.wi, ds_d, &pv, &ppdf);
             result += throughput * pv * emitted; /* mis_weight(1, 0) = 1 for a delta emitter */
@@ -1162,7 +1382,7 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t
                 C->n_surface++;
                 if (depth + 1 < max_depth) { /* :349-363 */
                     v3 ds_d;
-                    double emitted = sample_emitter(S, rng, si.p, si.n, medium, C, &ds_d);
+                    double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, si.p, si.n, medium, C, &ds_d);
                     v3 wo = to_local(&fr, ds_d);
                     result += throughput * bsdf_eval(S, wi, wo) * emitted;
                 }
@@ -1220,6 +1440,7 @@ static void bsdf_eval_mueller(const scene_t *S, const frame_t *fr, v3 wi, v3 wo,
 static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, v3 sensor_up, counters_t *C, double stokes[4]) {
     const ertb_scene_desc *D = S->desc;
     const int mis = D->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
+    const int pw = D->integrator == ERTB_INTEGRATOR_PIECEWISE_VOLPATH;
     const uint64_t max_depth = D->max_depth < 0 ? (uint64_t) 0xffffffffu : (uint64_t) D->max_depth;
     const v3 primary_d = ray.d;
     mueller_t T = mu_identity(1.0);
@@ -1249,7 +1470,12 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, v3 senso
         int active_medium = medium, active_surface = !medium;
         int escaped = 0, null_scatter = 0, medium_scatter = 0;
         mei_t mei; memset(&mei, 0, sizeof mei);
-        if (active_medium) {
+        if (active_medium && pw) {
+            T = mu_scale(&T, pw_medium_step(S, rng, &ray, &si, &needs_intersection, &mei));
+            escaped = !(mei.t < INFINITY);
+            active_medium = mei.t < INFINITY;
+            if (active_medium) { medium_scatter = 1; depth++; }
+        } else if (active_medium) {
             mei = sample_interaction(S, &ray, next_1d(rng));
             if (D->homogeneous && mei.t < INFINITY) ray.maxt = mei.t;
             if (needs_intersection) si = scene_intersect(S, &ray);
@@ -1277,7 +1503,7 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, v3 senso
             C->n_scatter++;
             T = mu_scale(&T, mei.sigma_s / (mei.sigma_t / mei.combined));
             v3 ds_d;
-            double emitted = sample_emitter(S, rng, mei.p, V(0, 0, 0), medium, C, &ds_d);
+            double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, mei.p, V(0, 0, 0), medium, C, &ds_d);
             mueller_t P;
             phase_eval_mueller(S, mei.layer, mei.wi, ds_d, &P);
             mueller_t TP = mu_mul(&T, &P);
@@ -1305,7 +1531,7 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, v3 senso
                 C->n_surface++;
                 if (depth + 1 < max_depth) {
                     v3 ds_d;
-                    double emitted = sample_emitter(S, rng, si.p, si.n, medium, C, &ds_d);
+                    double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, si.p, si.n, medium, C, &ds_d);
                     v3 wo = to_local(&fr, ds_d);
                     mueller_t B, TB;
                     bsdf_eval_mueller(S, &fr, wi, wo, &B);
@@ -1503,6 +1729,44 @@ int ertbo_medium_lookup(const ertb_scene_desc *desc, size_t n, const double *p, 
         int l = layer_index(&S, V(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
         st[i] = l >= 0 ? (double) desc->sigma_t_scale * desc->sigma_t[l] : 0.0;
         al[i] = l >= 0 ? desc->albedo[l] : 0.0;
+    }
+    scene_free(&S);
+    return 0;
+}
+
+/* Known-answer entries for ERP/tests/media/test_piecewise.py (sample_interaction_real /
+ * eval_transmittance_pdf_real with ray.maxt = inf). */
+int ertbo_piecewise_sample(const ertb_scene_desc *desc, double half_width, size_t n, const double *o,
+                           const double *d, const double *sample, const double *si_t, double *t,
+                           double *tr, double *pdf) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    if (!S.pw_cum) { scene_free(&S); return fail("not a piecewise scene"); }
+    S.pp_half_width = half_width;
+    for (size_t i = 0; i < n; ++i) {
+        ray_t ray; ray.o = V(o[3 * i], o[3 * i + 1], o[3 * i + 2]); ray.d = V(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        ray.maxt = INFINITY;
+        double mint, maxt;
+        int hit = medium_aabb(&S, &ray, &mint, &maxt);
+        mei_t mei = pw_sample_interaction_real(&S, &ray, si_t[i], sample[i], hit, mint, maxt, &tr[i], &pdf[i]);
+        t[i] = mei.t;
+    }
+    scene_free(&S);
+    return 0;
+}
+
+int ertbo_piecewise_eval(const ertb_scene_desc *desc, double half_width, size_t n, const double *o,
+                         const double *d, const double *si_t, double *tr, double *pdf, int *escaped) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    if (!S.pw_cum) { scene_free(&S); return fail("not a piecewise scene"); }
+    S.pp_half_width = half_width;
+    for (size_t i = 0; i < n; ++i) {
+        ray_t ray; ray.o = V(o[3 * i], o[3 * i + 1], o[3 * i + 2]); ray.d = V(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        ray.maxt = INFINITY;
+        double mint, maxt;
+        int hit = medium_aabb(&S, &ray, &mint, &maxt);
+        escaped[i] = pw_eval_transmittance_pdf_real(&S, &ray, si_t[i], hit, mint, maxt, &tr[i], &pdf[i]);
     }
     scene_free(&S);
     return 0;

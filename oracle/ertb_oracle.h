@@ -29,6 +29,11 @@ int ertbo_render(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_
 int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_t spp,
                         uint64_t sample_offset, double *sum_wl, double *sum_l, double *sum_l2,
                         double *sum_stokes, ertb_render_stats *stats, int n_threads);
+int ertbo_piecewise_sample(const ertb_scene_desc *desc, double half_width, size_t n, const double *o,
+                           const double *d, const double *sample, const double *si_t, double *t,
+                           double *tr, double *pdf);
+int ertbo_piecewise_eval(const ertb_scene_desc *desc, double half_width, size_t n, const double *o,
+                         const double *d, const double *si_t, double *tr, double *pdf, int *escaped);
 int ertbo_phase_mueller(const ertb_scene_desc *desc, int leaf, size_t n, const double *wi, const double *wo,
                         double *mueller, double *pdf);
 

@@ -102,6 +102,34 @@ def phase_mueller(desc, leaf, wi, wo):
     return M, pdf
 
 
+def piecewise_sample(desc, o, d, sample, si_t=None, half_width=0.0):
+    """piecewise.cpp sample_interaction_real -> (t, tr, pdf)."""
+    o, d = _d(o).reshape(-1, 3), _d(d).reshape(-1, 3)
+    n = o.shape[0]
+    u = _d(np.broadcast_to(sample, (n,)))
+    st = _d(np.full(n, np.inf) if si_t is None else np.broadcast_to(si_t, (n,)))
+    t, tr, pdf = np.zeros(n), np.zeros(n), np.zeros(n)
+    _check(load().ertbo_piecewise_sample(C.byref(desc), C.c_double(half_width), C.c_size_t(n),
+                                         o.ctypes.data_as(dp), d.ctypes.data_as(dp), u.ctypes.data_as(dp),
+                                         st.ctypes.data_as(dp), t.ctypes.data_as(dp), tr.ctypes.data_as(dp),
+                                         pdf.ctypes.data_as(dp)))
+    return t, tr, pdf
+
+
+def piecewise_eval(desc, o, d, si_t=None, half_width=0.0):
+    """piecewise.cpp eval_transmittance_pdf_real -> (tr, pdf, escaped)."""
+    o, d = _d(o).reshape(-1, 3), _d(d).reshape(-1, 3)
+    n = o.shape[0]
+    st = _d(np.full(n, np.inf) if si_t is None else np.broadcast_to(si_t, (n,)))
+    tr, pdf = np.zeros(n), np.zeros(n)
+    esc = np.zeros(n, dtype=np.int32)
+    _check(load().ertbo_piecewise_eval(C.byref(desc), C.c_double(half_width), C.c_size_t(n),
+                                       o.ctypes.data_as(dp), d.ctypes.data_as(dp), st.ctypes.data_as(dp),
+                                       tr.ctypes.data_as(dp), pdf.ctypes.data_as(dp),
+                                       esc.ctypes.data_as(C.POINTER(C.c_int))))
+    return tr, pdf, esc.astype(bool)
+
+
 def bsdf_eval(desc, wi, wo):
     wi, wo = _d(wi).reshape(-1, 3), _d(wo).reshape(-1, 3)
     out = np.zeros(wi.shape[0])
