@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -173,5 +173,7 @@ EXPORTED_SYMBOLS = (
     "ertb_kat_phase_eval",
     "ertb_kat_phase_sample",
     "ertb_kat_phase_mueller",
+    "ertb_kat_piecewise_sample",
+    "ertb_kat_piecewise_transmittance",
     "ertb_kat_sensor_ray",
 )

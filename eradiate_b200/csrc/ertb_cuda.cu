@@ -200,6 +200,25 @@ static int scene_commit(ertb_scene *S) {
                 }
             blob.resize(align4(blob.size()), 0.f);
         }
+        P.piecewise = S->integrator == ERTB_INTEGRATOR_PIECEWISE_VOLPATH;
+        if (P.piecewise) {
+            // piecewise.cpp:445-507 precompute_optical_thickness, folded into one table of the vertical
+            // optical depth above each layer boundary (double accumulation, float storage)
+            const double dz = (S->medium_top - S->medium_bottom) / n;
+            P.dz = (float) dz;
+            P.off_sigma = (int) blob.size();
+            for (int i = 0; i < n; ++i) blob.push_back((float) ((double) S->scale * (double) S->sigma_t[i]));
+            blob.resize(align4(blob.size()), 0.f);
+            P.off_tau = (int) blob.size();
+            std::vector<double> tt((size_t) n + 1, 0.0); // from boundary i up to the top
+            for (int i = n - 1; i >= 0; --i) tt[i] = tt[i + 1] + (double) S->scale * (double) S->sigma_t[i] * dz;
+            for (int i = 0; i <= n; ++i) blob.push_back((float) tt[i]);
+            blob.resize(align4(blob.size()), 0.f);
+            // optical depth above the ground level (the grid may start below the surface)
+            double xg = fmin(fmax((S->surface_z - S->medium_bottom) / dz, 0.0), (double) n);
+            int lg = (int) fmin(floor(xg), (double) (n - 1));
+            P.tau_ground = (float) (tt[lg] - (double) S->scale * (double) S->sigma_t[lg] * (xg - lg) * dz);
+        }
         for (int k = 0; k < S->n_phase; ++k) {
             ErtbPhaseLeaf &L = P.leaf[k];
             const HostPhase &hp = S->phase[k];
@@ -448,6 +467,18 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
         return set_error("This integrator currently does not support polarized mode!"); // volpathmis.cpp:130-132
     }
 
+    if (D->integrator < ERTB_INTEGRATOR_VOLPATH || D->integrator > ERTB_INTEGRATOR_PIECEWISE_VOLPATH) {
+        delete S;
+        return set_error("unsupported integrator type");
+    }
+    if (D->integrator == ERTB_INTEGRATOR_PIECEWISE_VOLPATH && S->has_medium &&
+        (S->homogeneous || S->geometry != ERTB_GEOM_PLANE_PARALLEL)) {
+        // medium.cpp:99-118: only the piecewise medium (plane-parallel layer stack) has the *_real interface
+        delete S;
+        return set_error("Medium::sample_interaction_real(): not implemented! (piecewise_volpath needs a "
+                         "plane-parallel piecewise medium)");
+    }
+
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete S; return set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
     cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -573,10 +604,11 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     int blocks_per_sm = 0;
     const int block = use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK;
     const bool pol = S->polarized != 0;
-    if (pol) use_pool = true; // the polarized path exists in the pool kernel only
+    const bool pw = S->base.piecewise != 0;
+    if (pol || pw) use_pool = true; // the polarized and the piecewise paths exist in the pool kernel only
     size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol) : (size_t) S->base.blob_bytes;
     if (use_pool && smem > (size_t) S->max_smem_optin) { // huge tables: fall back to the register kernel
-        if (pol) return set_error("scene tables leave no shared memory for the polarized path pools");
+        if (pol || pw) return set_error("scene tables leave no shared memory for the path pools");
         use_pool = false;
         smem = (size_t) S->base.blob_bytes;
     }
@@ -587,7 +619,11 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     } while (0)
 #define ERTB_DISPATCH(MACRO)                                                                          \
     do {                                                                                              \
-        if (use_pool && pol) {                                                                        \
+        if (pw && pol) {                                                                              \
+            if (with_stats) MACRO((ertb_render_pool_kernel<false, true, true, true>)); else MACRO((ertb_render_pool_kernel<false, false, true, true>)); \
+        } else if (pw) {                                                                              \
+            if (with_stats) MACRO((ertb_render_pool_kernel<false, true, false, true>)); else MACRO((ertb_render_pool_kernel<false, false, false, true>)); \
+        } else if (use_pool && pol) {                                                                 \
             if (sph) { if (with_stats) MACRO((ertb_render_pool_kernel<true, true, true>)); else MACRO((ertb_render_pool_kernel<true, false, true>)); } \
             else     { if (with_stats) MACRO((ertb_render_pool_kernel<false, true, true>)); else MACRO((ertb_render_pool_kernel<false, false, true>)); } \
         } else if (use_pool) {                                                                        \
@@ -815,6 +851,51 @@ int ertb_kat_phase_mueller(ertb_scene *S, int leaf, size_t n, const float *wi, c
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(mueller, m.p, 16 * n * sizeof(float), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(pdf, p.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// piecewise medium: analytic free flight / exact transmittance (ertb_piecewise.cuh)
+__global__ void kat_piecewise_sample_kernel(ErtbParams P, size_t n, const float *z, const float *mu, const float *u,
+                                            float *t, int *kind) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s, h;
+    // (the render kernel draws u on the 2^-24 grid, where 1 - u is exact; arbitrary test inputs are not)
+    kind[i] = pw_flight(P, P.blob, z[i], mu[i], (float) -log1p(-(double) u[i]), s, h);
+    t[i] = s;
+}
+__global__ void kat_piecewise_tr_kernel(ErtbParams P, size_t n, const float *z, const float *mu, float *tr) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tr[i] = mu[i] > 0.f ? pw_transmittance_up(P, P.blob, z[i], mu[i]) : 0.f;
+}
+
+int ertb_kat_piecewise_sample(ertb_scene *S, size_t n, const float *altitude, const float *mu, const float *u,
+                              float *distance, int32_t *kind) {
+    if (kat_prepare(S)) return 1;
+    if (!S->base.piecewise) return set_error("not a piecewise scene");
+    DevBuf<float> a, b, c, t;
+    DevBuf<int> k;
+    if (a.alloc(n) || b.alloc(n) || c.alloc(n) || t.alloc(n) || k.alloc(n)) return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(a.p, altitude, n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.p, mu, n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c.p, u, n * sizeof(float), cudaMemcpyHostToDevice));
+    kat_piecewise_sample_kernel<<<KAT_GRID(n)>>>(S->base, n, a.p, b.p, c.p, t.p, k.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(distance, t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(kind, k.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int ertb_kat_piecewise_transmittance(ertb_scene *S, size_t n, const float *altitude, const float *mu, float *tr) {
+    if (kat_prepare(S)) return 1;
+    if (!S->base.piecewise) return set_error("not a piecewise scene");
+    DevBuf<float> a, b, t;
+    if (a.alloc(n) || b.alloc(n) || t.alloc(n)) return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(a.p, altitude, n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.p, mu, n * sizeof(float), cudaMemcpyHostToDevice));
+    kat_piecewise_tr_kernel<<<KAT_GRID(n)>>>(S->base, n, a.p, b.p, t.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(tr, t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 

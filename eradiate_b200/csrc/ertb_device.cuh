@@ -71,6 +71,11 @@ struct ErtbParams {
     int off_preal;    // sigma_t/majorant per layer
     int off_albedo;
     int off_cumw;     // (n_phase-1) x n_layers cumulative leaf probabilities
+    // piecewise medium (ertb_piecewise.cuh): sigma_t per layer, vertical optical depth above each of
+    // the n_layers + 1 layer boundaries, layer thickness, optical depth above the ground level
+    int piecewise;
+    int off_sigma, off_tau;
+    float dz, tau_ground;
     // surface
     int bsdf_type;
     float bsdf[ERTB_MAX_BSDF_PARAMS];

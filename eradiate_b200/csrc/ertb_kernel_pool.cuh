@@ -15,10 +15,17 @@
 // The walk phase keeps stepping the records it loaded while enough of them are still
 // walking, which amortises the load/store over several free flights.  Path state moves
 // through shared memory only; HBM sees the film atomics and the work-queue counter.
+//
+// PW = true is the piecewise integrator (ERP/integrators/piecewise_volpath.cpp:91-527): there
+// are no null collisions, so the walk phase disappears.  Every event (and the regeneration)
+// ends with the analytic free flight to the NEXT event (ertb_piecewise.cuh), and the shadow ray
+// of an event is one exact transmittance evaluation instead of a ratio-tracking walk; a record
+// is therefore always in one of the three event modes and each trip of a lane is one real event.
 #pragma once
 
 #include "ertb_kernel.cuh"
 #include "ertb_polar.cuh"
+#include "ertb_piecewise.cuh"
 
 #ifndef ERTB_POOL_NS
 #define ERTB_POOL_NS 64 // records per warp (multiple of 32)
@@ -52,8 +59,19 @@ __host__ __device__ inline size_t ertb_pool_smem_bytes(size_t blob_bytes, bool p
     return blob + warps * (size_t) (pol ? PF_COUNT_POL : PF_COUNT) * ERTB_POOL_NS * 4 + warps * 32 * 4;
 }
 
-template <bool SPH, bool STATS, bool POL>
+// free flight that follows a regeneration or an event of the piecewise integrator
+// (piecewise_volpath.cpp:215-246): returns the mode of the next event of the record
+__device__ __forceinline__ unsigned pw_advance(const ErtbParams &P, const float *tb, Pcg32 &rng, float &h0, float mu) {
+    float E = -__logf(1.f - pcg_float(rng));
+    float s, h;
+    int r = pw_flight(P, tb, h0, mu, E, s, h);
+    if (r == PW_COLLISION) { h0 = h; return PM_SCAT; }
+    return r == PW_GROUND ? PM_SURF : PM_IDLE;
+}
+
+template <bool SPH, bool STATS, bool POL, bool PW = false>
 __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
+    static_assert(!(PW && SPH), "the piecewise medium is a plane-parallel layer stack");
     constexpr int NF = POL ? PF_COUNT_POL : PF_COUNT;
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -106,7 +124,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
         // ---- 2. phase selection ----------------------------------------------------
         unsigned phase = PM_WALK_MAIN; // walk
         int n_sel = n_walk;
-        if (n_walk < P.tw) {
+        if (PW || n_walk < P.tw) {
             unsigned ms[ERTB_POOL_K], mc[ERTB_POOL_K], mi[ERTB_POOL_K];
             int ns = 0, nc = 0, ni = 0;
 #pragma unroll
@@ -144,7 +162,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
         const int slot = have ? list[lane] : 0;
         __syncwarp();
 
-        if (phase == PM_WALK_MAIN) {
+        if (!PW && phase == PM_WALK_MAIN) {
             // =====================================================================
             // free-flight walk (delta tracking / ratio tracking), medium.cpp:42-82
             // =====================================================================
@@ -357,7 +375,11 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                 if (!SPH && !(d.z < 0.f)) valid = 0;
                 unsigned flags;
                 float h0 = P.H, b = 0.f, smax = 0.f;
-                if (valid == 1) {
+                if (valid == 1 && PW) {
+                    if (STATS) st_main++;
+                    b = d.z;
+                    flags = pw_advance(P, tb, rng, h0, d.z);
+                } else if (valid == 1) {
                     int kind;
                     segment_setup<SPH>(P, n0, h0, d, b, smax, kind);
                     flags = PM_WALK_MAIN | (kind == KIND_GROUND ? PFL_KIND : 0u);
@@ -592,12 +614,44 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                 }
             }
             // volpathmis.cpp:227-231: Russian roulette after a real event only
-            if (!dead && P.mis && depth > P.rr_depth) {
+            // (piecewise_volpath.cpp:187-193: every loop trip, i.e. once per real event as well)
+            if (!dead && (PW || P.mis) && depth > P.rr_depth) {
                 float q = fminf(thr, 0.95f);
                 if (pcg_float(rng) >= q) thr = 0.f; else thr = __fdividef(thr, q);
             }
             if (POL && !(thr > 0.f)) thr = 0.f; // unpolarized(throughput) == 0 ends the path (volpath.cpp:191)
             if (thr == 0.f || depth >= P.max_depth) dead = true; // the NEE walk (if any) still runs
+            if (PW) {
+                // ---- exact shadow-ray transmittance (piecewise_volpath.cpp:404-527), then the free
+                //      flight to the next event ----
+                if (wnee > 0.f) {
+                    if (STATS) st_nee++;
+                    float c = sun.z > 0.f ? wnee * pw_transmittance_up(P, tb, h0, sun.z) : 0.f;
+                    res += c;
+                    if (POL) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) rquv[k] = fmaf(c, qn[k], rquv[k]);
+                    }
+                }
+                unsigned mode = PM_IDLE;
+                if (dead) thr = 0.f;
+                else {
+                    if (STATS) st_main++;
+                    mode = pw_advance(P, tb, rng, h0, d.z);
+                }
+                FLDU(PF_FLAGS, slot) = mode | (depth << PFL_DEPTH_SHIFT);
+                FLD(PF_H0, slot) = h0; FLD(PF_B, slot) = d.z; FLD(PF_S, slot) = 0.f; FLD(PF_SMAX, slot) = 0.f;
+                FLD(PF_THR, slot) = thr; FLD(PF_WNEE, slot) = 0.f; FLD(PF_RES, slot) = res;
+                FLDU(PF_RNG0, slot) = (unsigned) rng.state; FLDU(PF_RNG1, slot) = (unsigned) (rng.state >> 32);
+                FLD(PF_DX, slot) = d.x; FLD(PF_DY, slot) = d.y; FLD(PF_DZ, slot) = d.z;
+                if (POL) {
+                    float inv = thr > 0.f ? __fdividef(1.f, T[0]) : 0.f;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) FLD(PF_T0 + k, slot) = T[k] * inv;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) FLD(PF_RQ + k, slot) = rquv[k];
+                }
+            } else {
             // ---- segment set-up for the NEE walk and for the main walk that follows it ----
             float b = 0.f, smax = 0.f, b2 = 0.f, smax2 = 0.f;
             int kind = KIND_TOA, kind2 = KIND_TOA;
@@ -633,6 +687,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { FLD(PF_QN0 + k, slot) = qn[k]; FLD(PF_RQ + k, slot) = rquv[k]; }
             }
+            } // !PW
         }
         __syncwarp();
     }

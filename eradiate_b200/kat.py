@@ -83,3 +83,27 @@ def phase_mueller(scene, leaf, wi, wo):
     pdf = np.zeros(n, dtype=np.float32)
     _lib.check(dev.lib.ertb_kat_phase_mueller(dev.handle, leaf, n, _fp(wi), _fp(wo), _fp(M), _fp(pdf)))
     return M, pdf
+
+
+def piecewise_sample(scene, altitude, mu, u):
+    """Analytic free flight of the piecewise medium: (distance, kind) per query; kind 0 = collision,
+    1 = reached the ground, 2 = left through the top of the atmosphere."""
+    dev = _device_scene(scene)
+    dev.sync()
+    z, mu, u = (np.ascontiguousarray(np.broadcast_arrays(_f(altitude), _f(mu), _f(u))[i]) for i in range(3))
+    n = z.size
+    t = np.zeros(n, dtype=np.float32)
+    kind = np.zeros(n, dtype=np.int32)
+    _lib.check(dev.lib.ertb_kat_piecewise_sample(dev.handle, n, _fp(z), _fp(mu), _fp(u), _fp(t),
+                                                 kind.ctypes.data_as(C.POINTER(C.c_int32))))
+    return t, kind
+
+
+def piecewise_transmittance(scene, altitude, mu):
+    """exp(-optical depth) from each altitude to the top of the atmosphere along cosine mu > 0."""
+    dev = _device_scene(scene)
+    dev.sync()
+    z, mu = (np.ascontiguousarray(np.broadcast_arrays(_f(altitude), _f(mu))[i]) for i in range(2))
+    tr = np.zeros(z.size, dtype=np.float32)
+    _lib.check(dev.lib.ertb_kat_piecewise_transmittance(dev.handle, z.size, _fp(z), _fp(mu), _fp(tr)))
+    return tr

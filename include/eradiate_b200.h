@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 5
+#define ERTB_ABI_VERSION 6
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -256,6 +256,16 @@ int ertb_kat_bsdf_sample(ertb_scene *scene, size_t n, const float *wi, const flo
 int ertb_kat_phase_eval(ertb_scene *scene, int leaf, size_t n, const float *cos_theta, float *out);
 int ertb_kat_phase_sample(ertb_scene *scene, int leaf, size_t n, const float *u,
                           float *cos_theta, float *weight, float *pdf);
+/* piecewise medium (ERP/media/piecewise.cpp:183-332 sample_interaction_real, :335-429
+ * eval_transmittance_pdf_real; golden vectors in ERP/tests/media/test_piecewise.py), in the
+ * kernel's reduced coordinates: altitude above the ground (n), vertical direction cosine (n).
+ *   piecewise_sample: + uniform sample (n) -> flight distance (n), kind (n): 0 = collision at
+ *                     that distance, 1 = reached the ground at that distance, 2 = left through the top
+ *   piecewise_transmittance: -> exp(-optical depth) from the altitude to the top along mu > 0 */
+int ertb_kat_piecewise_sample(ertb_scene *scene, size_t n, const float *altitude, const float *mu,
+                              const float *u, float *distance, int32_t *kind);
+int ertb_kat_piecewise_transmittance(ertb_scene *scene, size_t n, const float *altitude, const float *mu,
+                                     float *transmittance);
 /* phase_mueller: leaf, wi (3*n, = -propagation direction), wo (3*n) -> 4x4 Mueller matrices in the
  * implicit Stokes bases of the two directions (16*n, row-major) and pdf (n) */
 int ertb_kat_phase_mueller(ertb_scene *scene, int leaf, size_t n, const float *wi, const float *wo,

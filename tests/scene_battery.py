@@ -97,4 +97,26 @@ def battery() -> dict:
         "max_depth_3_rr_2": S(geometry="plane_parallel", atmosphere="homogeneous", max_depth=3, rr_depth=2,
                               homogeneous_sigma_t=2.0 / scenes.TOA, sensor=VZA5),
         "no_atmosphere_rpv_spherical": S(atmosphere=None, sensor=VZA5),
+        # piecewise medium + piecewise_volpath (the default Eradiate picks for plane-parallel atmospheres,
+        # experiments/_atmosphere.py:165-184): analytic free flights, exact shadow-ray transmittance
+        "piecewise_afgl_rpv_pp": S(geometry="plane_parallel", integrator="piecewise_volpath", sensor=VZA5,
+                                   sza=50.0, saa=30.0),
+        "piecewise_aerosol_blend_rr_pp": S(geometry="plane_parallel", integrator="piecewise_volpath", aerosol=True,
+                                           aerosol_phase="tabphase", n_layers=120, rr_depth=1, sza=65.0, saa=200.0,
+                                           surface={"type": "diffuse", "reflectance": 0.6},
+                                           sensor={"type": "mdistant", "vza": [-80.0, -35.0, 0.0, 35.0, 80.0],
+                                                   "vaa": 45.0}),
+        "piecewise_ocean_hdistant_pp": S(geometry="plane_parallel", integrator="piecewise_volpath", n_layers=50,
+                                         sza=35.0, saa=20.0, max_depth=6,
+                                         surface={"type": "ocean_legacy", "wavelength": 550.0, "wind_speed": 6.0,
+                                                  "wind_direction": 10.0},
+                                         sensor={"type": "hdistant", "film_resolution": (3, 2)}),
+        "piecewise_distantflux_coarse_pp": S(geometry="plane_parallel", integrator="piecewise_volpath", n_layers=3,
+                                             sensor={"type": "distantflux", "film_resolution": (2, 2)}),
+        "polarized_piecewise_rayleigh_pp": S(geometry="plane_parallel", integrator="piecewise_volpath",
+                                             n_layers=100, sza=40.0, saa=30.0, stokes=True,
+                                             phase={"type": "rayleigh_polarized", "depolarization": 0.0279},
+                                             surface={"type": "diffuse", "reflectance": 0.1},
+                                             sensor={"type": "mdistant", "vza": [-60.0, -30.0, 0.0, 30.0, 60.0],
+                                                     "vaa": 90.0}),
     }

@@ -263,6 +263,82 @@ def test_polarized_single_scattering_dolp_on_device():
     assert np.all(Q <= 1e-7) and np.allclose(U / I, 0, atol=2e-3) and np.allclose(V, 0, atol=1e-9)
 
 
+# ------------------------------------------------------------------ piecewise medium
+def _exp_medium_scene():
+    """ERP/tests/media/test_piecewise.py:6-45: 10 exponential layers over 100 km."""
+    H, n, integral, lbd = 100000.0, 10, 3.0, 8300.0
+    ext = (integral / lbd) * np.exp(-np.linspace(0.0, H, n, endpoint=False) / lbd)
+    sc = mi_load_dict(scenes.atmosphere_scene(geometry="plane_parallel", n_layers=n, toa=H,
+                                              integrator="piecewise_volpath"))
+    sc.flat.medium.children["sigma_t"].values["data"][:] = ext.reshape(-1, 1, 1, 1).astype(np.float32)
+    return sc, H
+
+
+def test_piecewise_flight_reference_golden_on_device():
+    """The reference's own golden distances / transmittances (test_piecewise.py:48-152, :185-258)
+    through the device implementation of sample_interaction_real / eval_transmittance_pdf_real."""
+    sc, H = _exp_medium_scene()
+    u = [0.0, 0.25, 0.5, 0.75, 0.99]
+    t, kind = kat.piecewise_sample(sc, H, -1.0, u)  # test01: looking down from the top
+    assert np.allclose(t, [0.0, 74578.93910366, 82117.51365975, 88515.28423884, 98460.51859237], rtol=2e-5)
+    assert np.all(kind == 0)
+    t, kind = kat.piecewise_sample(sc, 0.0, 1.0, u)  # test02: looking up from the ground
+    assert np.allclose(t, [0.0, 7.95920400e02, 1.91770720e03, 3.83541440e03, 1.91443066e04], rtol=2e-5)
+    t, kind = kat.piecewise_sample(sc, 15000.0, 0.0, u)  # test03: horizontal
+    assert np.allclose(t, [0.0, 2655.31469158, 6397.77055374, 12795.54110748, 42505.86749422], rtol=2e-5)
+    heights = [0.0, 9800.0, 10100.0, 27500.0, 40020.0, 75000, 98000.0]  # test05: u = 0.3, looking up
+    t, kind = kat.piecewise_sample(sc, heights, 1.0, 0.3)
+    assert np.allclose(t[:3], [986.80067823, 2824.88988516, 3292.12110592], rtol=2e-5)
+    assert list(kind) == [0, 0, 0, 2, 2, 2, 2]
+    tr = kat.piecewise_transmittance(sc, [0.0, 5000.0, 15000.0, 25000.0, 45000.0, 75000, 100000.0], 1.0)  # test06
+    assert np.allclose(tr, [0.00573247, 0.03493101, 0.36588307, 0.7398143, 0.97331388, 0.99930119, 1.0], rtol=2e-5)
+    # test07 (looking down): transmittance to the ground = P(flight reaches the ground), via the sampler's
+    # escape threshold: the largest u that still collides is 1 - tr
+    gt = np.array([0.03865759, 0.01566748, 0.00663011, 0.00588964, 0.00573872, 0.00573247])
+    hs = np.array([9000.0, 15000.0, 29800.0, 45000.0, 70020, 100000.0])
+    for h, g in zip(hs, gt):
+        _, k = kat.piecewise_sample(sc, h, -1.0, [1.0 - g * 1.001, 1.0 - g * 0.999])
+        assert list(k) == [0, 1], (h, g, k)
+
+
+@pytest.mark.parametrize("which", ["exp10", "afgl120"])
+def test_piecewise_flight_matches_oracle(oracle, which):
+    if which == "exp10":
+        sc, H = _exp_medium_scene()
+    else:
+        H = scenes.TOA
+        sc = mi_load_dict(scenes.atmosphere_scene(geometry="plane_parallel", n_layers=120, aerosol=True,
+                                                  integrator="piecewise_volpath"))
+    desc = sc.flat.build_desc()
+    rng = np.random.default_rng(5)
+    n = 20000
+    z = rng.uniform(0.0, H, n).astype(np.float32)
+    mu = rng.uniform(-1.0, 1.0, n).astype(np.float32)
+    u = rng.uniform(0.0, 1.0, n).astype(np.float32)
+    t, kind = kat.piecewise_sample(sc, z, mu, u)
+    d = np.stack([np.sqrt(1.0 - mu.astype(float) ** 2), np.zeros(n), mu.astype(float)], axis=1)
+    o = np.stack([np.zeros(n), np.zeros(n), z.astype(float)], axis=1)
+    si_t = np.where(mu < 0, z / np.maximum(-mu, 1e-30), np.inf)
+    t_o, tr_o, _ = oracle.piecewise_sample(desc, o, d, u.astype(float), si_t=si_t)
+    kind_o = np.where(np.isfinite(t_o), 0, np.where(mu < 0, 1, 2))
+    # a flight that ends within float32 rounding of a boundary may classify differently
+    same = kind == kind_o
+    assert same.mean() > 0.999, same.mean()
+    c = same & (kind == 0)
+    err = np.abs(t[c] - t_o[c])
+    worst = np.argmax(err / (2e-4 * t_o[c] + 1.0))
+    assert np.allclose(t[c], t_o[c], rtol=2e-4, atol=1.0), (z[c][worst], mu[c][worst], u[c][worst], t[c][worst], t_o[c][worst])
+    assert np.median(np.abs(t[c] / t_o[c] - 1.0)) < 2e-6
+    g = same & (kind == 1)
+    assert np.allclose(t[g], si_t[g], rtol=1e-5)
+    # transmittance to the top along the sun direction (the shadow ray of every event)
+    mus = rng.uniform(0.05, 1.0, n).astype(np.float32)
+    tr = kat.piecewise_transmittance(sc, z, mus)
+    ds = np.stack([np.sqrt(1.0 - mus.astype(float) ** 2), np.zeros(n), mus.astype(float)], axis=1)
+    tr_ref, _, _ = oracle.piecewise_eval(desc, o, ds)
+    assert np.allclose(tr, tr_ref, rtol=2e-4, atol=1e-7)
+
+
 # --------------------------------------------------------------- render-level parity
 def gpu_render(sc, spp, seed=11, sensor=0):
     bmp = render(sc, sensor=sensor, seed=seed, spp=spp)
