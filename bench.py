@@ -143,16 +143,17 @@ def run_reference(args):
     if rank != 0:
         return  # other ranks exit 0 without work
     cores = os.cpu_count() or 1
-    spp = 1 << 14  # bounded sample: 32 x 16384 = 524k paths per step
+    spp = 1 << 18  # bounded sample: 32 x 2^18 = 8.4 M paths per step (~1 s on 16 cores)
     for _ in range(args.warmup):
-        time_cpu_oracle(1 << 10)
+        time_cpu_oracle(1 << 12)
     times = []
     for _ in range(args.steps):
         mp, sec, _ = time_cpu_oracle(spp)
         times.append(sec)
     ms = 1e3 * float(np.mean(times))
     value = N_VZA * spp / (ms * 1e-3) / 1e6
-    sample = f"{args.steps} steps x (32 pixels x spp=2^14 = 524288 paths) of the C2 workload, OpenMP all cores"
+    sample = (f"{args.steps} steps x (32 pixels x spp=2^18 = {N_VZA * spp} paths) of the C2 workload, "
+              f"OpenMP on all {cores} host cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -327,11 +328,11 @@ def run_cuda(args):
         }
         if world == 1:
             cores = os.cpu_count() or 1
-            cpu_spp = 1 << 15  # ~1 M paths: bounded sample of the same workload
+            cpu_spp = 1 << 19  # 16.8 M paths: ~15-30 core-seconds of the same workload
             cpu_val, cpu_s, cpu_k = time_cpu_oracle(cpu_spp, repeats=2)
             line["cpu_baseline"] = {
                 "value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"C2 scene, 32 pixels x spp=2^15 = {N_VZA * cpu_spp} paths, best of 2, "
+                "sample": f"C2 scene, 32 pixels x spp=2^19 = {N_VZA * cpu_spp} paths, best of 2, "
                           f"{cpu_s:.2f} s per call, OpenMP on all {cores} host cores, oracle K={cpu_k:.2f}",
             }
         print(json.dumps(line), flush=True)
@@ -343,7 +344,7 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     args = ap.parse_args()
