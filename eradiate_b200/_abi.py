@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -168,6 +168,9 @@ EXPORTED_SYMBOLS = (
     "ertb_render_device",
     "ertb_render_stokes",
     "ertb_sensor_pixel_count",
+    "ertb_batch_begin",
+    "ertb_batch_push",
+    "ertb_batch_end",
     "ertb_kat_bsdf_eval",
     "ertb_kat_bsdf_sample",
     "ertb_kat_phase_eval",

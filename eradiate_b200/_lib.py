@@ -13,7 +13,8 @@ import os
 
 from . import _abi
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libertb_cuda.so")
+_LIB_PATH = os.environ.get(  # ERTB_LIB: developer knob for A/B runs of two builds of the same ABI
+    "ERTB_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libertb_cuda.so"))
 _lib = None
 
 
@@ -46,6 +47,9 @@ def load() -> C.CDLL:
     lib.ertb_render_stokes.argtypes = [vp, i32, u64, u64, u64, dp, dp, dp, dp, C.POINTER(_abi.RenderStats)]
     lib.ertb_kat_phase_mueller.argtypes = [vp, i32, C.c_size_t, fp, fp, fp, fp]
     lib.ertb_sensor_pixel_count.argtypes = [vp, i32]
+    lib.ertb_batch_begin.argtypes = [vp, i32, C.POINTER(i32), i32]
+    lib.ertb_batch_push.argtypes = [vp, i32, u64, u64, u64]
+    lib.ertb_batch_end.argtypes = [vp, dp, C.c_size_t, C.POINTER(_abi.RenderStats), dp]
     lib.ertb_kat_bsdf_eval.argtypes = [vp, C.c_size_t, fp, fp, fp]
     lib.ertb_kat_bsdf_sample.argtypes = [vp, C.c_size_t, fp, fp, fp, fp]
     lib.ertb_kat_phase_eval.argtypes = [vp, i32, C.c_size_t, fp, fp]

@@ -7,7 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ertb_kernel.cuh"
@@ -47,6 +50,40 @@ struct HostSensor {
     int use_table = 0;
 };
 
+// Where one committed set of device tables lives: the scene's own slot (synchronous uploads on
+// the default stream) or one slot of the batch pipeline (pinned staging buffer, private tables,
+// private stream), so that the tables of context i+1 can be built and uploaded while context i
+// is still rendering.
+struct TableSlot {
+    float *h_pinned = nullptr;
+    size_t h_capacity = 0;
+    float *d_blob = nullptr;
+    size_t d_blob_capacity = 0;
+    float *d_ocean = nullptr; // ocean_legacy transmittance tables and the parameters they were built for
+    double ocean_key[3] = { -1.0, -1.0, -1.0 };
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    bool async = false;
+};
+
+#define ERTB_BATCH_SLOTS 4
+#define ERTB_MIN_WARP_PATHS 32ULL
+
+struct BatchState {
+    bool open = false;
+    bool with_stats = false;
+    int next = 0;
+    std::vector<int> sensors;
+    std::vector<size_t> offsets; // per item, in doubles, into d_accum
+    size_t total = 0;
+    double *d_accum = nullptr;
+    size_t d_accum_capacity = 0;
+    unsigned long long *d_counters = nullptr; // 16 per item: [0] work counter, [8..15] statistics
+    size_t d_counters_capacity = 0;
+    double t_begin = 0.0;
+};
+
 struct ertb_scene {
     int device = 0;
     int geometry = 0;
@@ -71,18 +108,17 @@ struct ertb_scene {
     bool dirty = true;
     ErtbParams base;            // everything but the per-launch fields
     std::vector<float> blob;    // host copy of the table blob
-    float *d_blob = nullptr;
-    size_t d_blob_capacity = 0;
+    TableSlot main;             // tables of the synchronous path
+    TableSlot slots[ERTB_BATCH_SLOTS];
+    BatchState batch;
     unsigned long long *d_counter = nullptr; // work counter + stats (1 + 8)
     double *d_accum = nullptr;
     size_t d_accum_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
+    std::map<std::pair<const void *, size_t>, int> occupancy; // per kernel instantiation and smem size
     int max_smem_optin = 0;
-    // ocean_legacy: transmittance tables (device) and the parameters they were built for
-    float *d_ocean = nullptr;
-    double *d_gl = nullptr;
-    double ocean_key[3] = { -1.0, -1.0, -1.0 };
+    double *d_gl = nullptr;     // Gauss-Legendre nodes/weights of the ocean transmittance quadrature
 };
 
 static size_t align4(size_t n) { return (n + 3) & ~size_t(3); }
@@ -156,7 +192,7 @@ static int validate_tab(const HostPhase &hp) {
 }
 
 // Rebuild derived tables + base kernel parameters and upload them.
-static int scene_commit(ertb_scene *S) {
+static int scene_commit(ertb_scene *S, TableSlot &T) {
     CUDA_TRY(cudaSetDevice(S->device));
     ErtbParams &P = S->base;
     memset(&P, 0, sizeof P);
@@ -239,13 +275,27 @@ static int scene_commit(ertb_scene *S) {
     const size_t blob_bytes = blob.size() * sizeof(float);
     if (blob_bytes > (size_t) S->max_smem_optin - 1024)
         return set_error("scene tables do not fit in one SM's shared memory");
-    if (blob_bytes > S->d_blob_capacity) {
-        if (S->d_blob) cudaFree(S->d_blob);
-        CUDA_TRY(cudaMalloc(&S->d_blob, blob_bytes));
-        S->d_blob_capacity = blob_bytes;
+    if (blob_bytes > T.d_blob_capacity) {
+        if (T.d_blob) cudaFree(T.d_blob);
+        T.d_blob = nullptr;
+        T.d_blob_capacity = 0;
+        CUDA_TRY(cudaMalloc(&T.d_blob, blob_bytes));
+        T.d_blob_capacity = blob_bytes;
     }
-    if (blob_bytes) CUDA_TRY(cudaMemcpy(S->d_blob, blob.data(), blob_bytes, cudaMemcpyHostToDevice));
-    P.blob = S->d_blob;
+    if (blob_bytes && T.async) {
+        if (blob_bytes > T.h_capacity) {
+            if (T.h_pinned) cudaFreeHost(T.h_pinned);
+            T.h_pinned = nullptr;
+            T.h_capacity = 0;
+            CUDA_TRY(cudaMallocHost(&T.h_pinned, blob_bytes));
+            T.h_capacity = blob_bytes;
+        }
+        memcpy(T.h_pinned, blob.data(), blob_bytes);
+        CUDA_TRY(cudaMemcpyAsync(T.d_blob, T.h_pinned, blob_bytes, cudaMemcpyHostToDevice, T.stream));
+    } else if (blob_bytes) {
+        CUDA_TRY(cudaMemcpy(T.d_blob, blob.data(), blob_bytes, cudaMemcpyHostToDevice));
+    }
+    P.blob = T.d_blob;
     P.blob_bytes = (int) blob_bytes;
 
     P.bsdf_type = S->bsdf_type;
@@ -256,19 +306,19 @@ static int scene_commit(ertb_scene *S) {
         double n_real, n_imag;
         ertb_ocean_host::derive(S->bsdf_params, P.bsdf, n_real, n_imag);
         const double ws = S->bsdf_params[1];
-        if (!S->d_ocean) {
-            CUDA_TRY(cudaMalloc(&S->d_ocean, 2 * ERTB_OC_RES * ERTB_OC_RES * sizeof(float)));
+        if (!S->d_gl) {
             CUDA_TRY(cudaMalloc(&S->d_gl, 2 * ERTB_OC_RES * sizeof(double)));
             double gl[2 * ERTB_OC_RES];
             ertb_ocean_host::gauss_legendre(ERTB_OC_RES, gl, gl + ERTB_OC_RES);
             CUDA_TRY(cudaMemcpy(S->d_gl, gl, sizeof gl, cudaMemcpyHostToDevice));
         }
-        if (S->ocean_key[0] != n_real || S->ocean_key[1] != n_imag || S->ocean_key[2] != ws) {
-            ertb_ocean_tables_kernel<<<(2 * ERTB_OC_RES * ERTB_OC_RES + 127) / 128, 128>>>(n_real, n_imag, ws, S->d_gl, S->d_ocean);
+        if (!T.d_ocean) CUDA_TRY(cudaMalloc(&T.d_ocean, 2 * ERTB_OC_RES * ERTB_OC_RES * sizeof(float)));
+        if (T.ocean_key[0] != n_real || T.ocean_key[1] != n_imag || T.ocean_key[2] != ws) {
+            ertb_ocean_tables_kernel<<<(2 * ERTB_OC_RES * ERTB_OC_RES + 127) / 128, 128, 0, T.stream>>>(n_real, n_imag, ws, S->d_gl, T.d_ocean);
             CUDA_TRY(cudaGetLastError());
-            S->ocean_key[0] = n_real; S->ocean_key[1] = n_imag; S->ocean_key[2] = ws;
+            T.ocean_key[0] = n_real; T.ocean_key[1] = n_imag; T.ocean_key[2] = ws;
         }
-        P.ocean_tables = S->d_ocean;
+        P.ocean_tables = T.d_ocean;
     }
     double dn = sqrt(S->emitter_dir[0] * S->emitter_dir[0] + S->emitter_dir[1] * S->emitter_dir[1] +
                      S->emitter_dir[2] * S->emitter_dir[2]);
@@ -279,8 +329,17 @@ static int scene_commit(ertb_scene *S) {
     P.mis = S->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
     P.rr_depth = (unsigned) S->rr_depth;
     P.max_depth = S->max_depth < 0 ? 0xffffffffu : (unsigned) S->max_depth;
-    S->dirty = false;
+    S->dirty = T.async; // a batch slot's tables are private to that batch item
     return 0;
+}
+
+static void slot_release(TableSlot &T) {
+    if (T.h_pinned) cudaFreeHost(T.h_pinned);
+    if (T.d_blob) cudaFree(T.d_blob);
+    if (T.d_ocean) cudaFree(T.d_ocean);
+    if (T.done) cudaEventDestroy(T.done);
+    if (T.stream) cudaStreamDestroy(T.stream);
+    T = TableSlot();
 }
 
 // mdistant.cpp:180-190: ray_offset default
@@ -381,8 +440,10 @@ void ertb_scene_destroy(ertb_scene *S) {
     cudaSetDevice(S->device);
     for (auto &hs : S->sensors)
         if (hs.d_table) cudaFree(hs.d_table);
-    if (S->d_blob) cudaFree(S->d_blob);
-    if (S->d_ocean) cudaFree(S->d_ocean);
+    slot_release(S->main);
+    for (auto &T : S->slots) slot_release(T);
+    if (S->batch.d_accum) cudaFree(S->batch.d_accum);
+    if (S->batch.d_counters) cudaFree(S->batch.d_counters);
     if (S->d_gl) cudaFree(S->d_gl);
     if (S->d_counter) cudaFree(S->d_counter);
     if (S->d_accum) cudaFree(S->d_accum);
@@ -510,7 +571,7 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
         S->sensors.push_back(hs);
         if (build_sensor(S, S->sensors.back())) { ertb_scene_destroy(S); return 1; }
     }
-    if (scene_commit(S)) { ertb_scene_destroy(S); return 1; }
+    if (scene_commit(S, S->main)) { ertb_scene_destroy(S); return 1; }
     *out = S;
     return 0;
 }
@@ -576,14 +637,17 @@ int ertb_sensor_pixel_count(const ertb_scene *S, int sensor) {
 
 static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, uint64_t sample_offset,
                          double *accum_dev, unsigned long long *stats_dev, cudaStream_t stream,
-                         bool with_stats) {
+                         bool with_stats, TableSlot *slot = nullptr, unsigned long long *counter_dev = nullptr) {
     if (!S) return set_error("null scene");
     if (sensor < 0 || sensor >= (int) S->sensors.size()) return set_error("invalid sensor index");
     if (spp == 0) return set_error("spp must be > 0");
     if (sample_offset + spp >= (1ULL << 40)) return set_error("sample index exceeds 2^40");
     CUDA_TRY(cudaSetDevice(S->device));
-    if (S->dirty && scene_commit(S)) return 1;
+    if (slot) {
+        if (scene_commit(S, *slot)) return 1;
+    } else if (S->dirty && scene_commit(S, S->main)) return 1;
     ErtbParams P = S->base;
+    if (!counter_dev) counter_dev = S->d_counter;
     const HostSensor &hs = S->sensors[sensor];
     fill_sensor_params(S, hs, P.sensor);
     if (hs.desc.type == ERTB_SENSOR_MDISTANT) { P.sensor_up[0] = 0.f; P.sensor_up[1] = 1.f; P.sensor_up[2] = 0.f; }
@@ -612,30 +676,40 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
         use_pool = false;
         smem = (size_t) S->base.blob_bytes;
     }
+    // (attribute + occupancy are queried once per kernel instantiation and table size, then cached)
 #define ERTB_OCC(KERNEL)                                                                              \
     do {                                                                                              \
+        auto key = std::make_pair((const void *) KERNEL, smem);                                       \
+        auto it = S->occupancy.find(key);                                                             \
+        if (it != S->occupancy.end()) { blocks_per_sm = it->second; break; }                          \
         CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, KERNEL, block, smem)); \
+        S->occupancy[key] = blocks_per_sm;                                                            \
+    } while (0)
+#define ERTB_POOL_VARIANT(MACRO, SPH_, POL_, PW_)                                                     \
+    do {                                                                                              \
+        if (with_stats) MACRO((ertb_render_pool_kernel<SPH_, true, POL_, PW_, true>));                \
+        else if (coll) MACRO((ertb_render_pool_kernel<SPH_, false, POL_, PW_, true>));                \
+        else MACRO((ertb_render_pool_kernel<SPH_, false, POL_, PW_, false>));                         \
     } while (0)
 #define ERTB_DISPATCH(MACRO)                                                                          \
     do {                                                                                              \
-        if (pw && pol) {                                                                              \
-            if (with_stats) MACRO((ertb_render_pool_kernel<false, true, true, true>)); else MACRO((ertb_render_pool_kernel<false, false, true, true>)); \
-        } else if (pw) {                                                                              \
-            if (with_stats) MACRO((ertb_render_pool_kernel<false, true, false, true>)); else MACRO((ertb_render_pool_kernel<false, false, false, true>)); \
-        } else if (use_pool && pol) {                                                                 \
-            if (sph) { if (with_stats) MACRO((ertb_render_pool_kernel<true, true, true>)); else MACRO((ertb_render_pool_kernel<true, false, true>)); } \
-            else     { if (with_stats) MACRO((ertb_render_pool_kernel<false, true, true>)); else MACRO((ertb_render_pool_kernel<false, false, true>)); } \
+        if (pw && pol) ERTB_POOL_VARIANT(MACRO, false, true, true);                                   \
+        else if (pw) ERTB_POOL_VARIANT(MACRO, false, false, true);                                    \
+        else if (use_pool && pol) {                                                                   \
+            if (sph) ERTB_POOL_VARIANT(MACRO, true, true, false);                                     \
+            else ERTB_POOL_VARIANT(MACRO, false, true, false);                                        \
         } else if (use_pool) {                                                                        \
-            if (sph) { if (with_stats) MACRO((ertb_render_pool_kernel<true, true, false>)); else MACRO((ertb_render_pool_kernel<true, false, false>)); } \
-            else     { if (with_stats) MACRO((ertb_render_pool_kernel<false, true, false>)); else MACRO((ertb_render_pool_kernel<false, false, false>)); } \
+            if (sph) ERTB_POOL_VARIANT(MACRO, true, false, false);                                    \
+            else ERTB_POOL_VARIANT(MACRO, false, false, false);                                       \
         } else {                                                                                      \
             if (sph) { if (with_stats) MACRO((ertb_render_kernel<true, true>)); else MACRO((ertb_render_kernel<true, false>)); } \
             else     { if (with_stats) MACRO((ertb_render_kernel<false, true>)); else MACRO((ertb_render_kernel<false, false>)); } \
         }                                                                                             \
     } while (0)
+    // the occupancy query does not depend on the flush variant; the launch picks it from the chunk size
+    bool coll = false;
     ERTB_DISPATCH(ERTB_OCC);
-#undef ERTB_OCC
     if (blocks_per_sm < 1) return set_error("render kernel cannot be resident on this device");
     if (use_pool) {
         P.tw = 32; P.twi = 16;
@@ -650,20 +724,39 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     if (chunk < 32) chunk = 32;
     if (chunk > spp) chunk = spp;
     P.chunk = (unsigned) chunk;
+    // Lanes switch pixel once or twice per chunk. The per-lane flush atomics of one render (about
+    // n_chunks x 64 lanes x 3) drain at ~0.3 ns each in the L2 atomic unit: hidden behind the walk
+    // for chunks of >= 512 paths (C2: 590), the bottleneck below that -> collective flushes.
+    coll = chunk < 512;
+    if (coll && use_pool && !with_stats) { // same resources, but the attribute is per instantiation
+        int bps = 0;
+        std::swap(bps, blocks_per_sm);
+        ERTB_DISPATCH(ERTB_OCC);
+        if (blocks_per_sm < bps) bps = blocks_per_sm;
+        blocks_per_sm = bps;
+        if (blocks_per_sm < 1) return set_error("render kernel cannot be resident on this device");
+    }
+#undef ERTB_OCC
     P.chunks_per_pixel = (unsigned) ((spp + chunk - 1) / chunk);
     P.n_chunks = (unsigned long long) P.chunks_per_pixel * P.n_pixels;
-    P.work_counter = S->d_counter;
+    P.work_counter = counter_dev;
     P.accum = accum_dev;
     P.stats = stats_dev;
-    CUDA_TRY(cudaMemsetAsync(S->d_counter, 0, sizeof(unsigned long long), stream));
+    CUDA_TRY(cudaMemsetAsync(counter_dev, 0, sizeof(unsigned long long), stream));
 
-    unsigned long long want_blocks = (P.n_chunks * 32ULL + block - 1) / block; // >= 1 lane per path slot
+    // small renders: do not spread the paths over more warps than can keep their pools busy
+    unsigned long long warp_paths = use_pool ? ERTB_MIN_WARP_PATHS : 32ULL;
+    if (const char *e = getenv("ERTB_MIN_WARP_PATHS")) warp_paths = (unsigned long long) atoll(e);
+    if (warp_paths < 32) warp_paths = 32;
+    unsigned long long want_warps = (total + warp_paths - 1) / warp_paths;
+    unsigned long long want_blocks = (want_warps * 32ULL + block - 1) / block;
     unsigned long long grid = (unsigned long long) S->sm_count * blocks_per_sm;
     if (want_blocks < grid) grid = want_blocks ? want_blocks : 1;
 #define ERTB_LAUNCH(KERNEL) KERNEL<<<(unsigned) grid, block, smem, stream>>>(P)
     ERTB_DISPATCH(ERTB_LAUNCH);
 #undef ERTB_LAUNCH
 #undef ERTB_DISPATCH
+#undef ERTB_POOL_VARIANT
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -727,6 +820,124 @@ int ertb_render_device(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, u
 }
 
 // ----------------------------------------------------------------------------
+// Pipelined multi-context rendering (the contexts x sensors loop of _render.py:433-468)
+// ----------------------------------------------------------------------------
+static double wall_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double) ts.tv_sec + 1e-6 * (double) ts.tv_nsec;
+}
+
+static int batch_drain(ertb_scene *S) {
+    for (auto &T : S->slots)
+        if (T.stream) {
+            CUDA_TRY(cudaStreamSynchronize(T.stream));
+            T.busy = false;
+        }
+    return 0;
+}
+
+int ertb_batch_begin(ertb_scene *S, int n_items, const int *sensors, int with_stats) {
+    if (!S || !sensors) return set_error("null argument");
+    if (n_items < 1) return set_error("ertb_batch_begin: empty batch");
+    CUDA_TRY(cudaSetDevice(S->device));
+    BatchState &B = S->batch;
+    if (batch_drain(S)) return 1; // an abandoned batch may still be running
+    B.open = false;
+    const int rows = S->polarized ? 7 : 3;
+    B.sensors.assign(sensors, sensors + n_items);
+    B.offsets.resize(n_items);
+    size_t total = 0;
+    for (int i = 0; i < n_items; ++i) {
+        int npix = ertb_sensor_pixel_count(S, sensors[i]);
+        if (npix <= 0) return set_error("ertb_batch_begin: invalid sensor index");
+        B.offsets[i] = total;
+        total += (size_t) rows * npix;
+    }
+    B.total = total;
+    if (total > B.d_accum_capacity) {
+        if (B.d_accum) cudaFree(B.d_accum);
+        B.d_accum = nullptr;
+        B.d_accum_capacity = 0;
+        CUDA_TRY(cudaMalloc(&B.d_accum, total * sizeof(double)));
+        B.d_accum_capacity = total;
+    }
+    if ((size_t) n_items * 16 > B.d_counters_capacity) {
+        if (B.d_counters) cudaFree(B.d_counters);
+        B.d_counters = nullptr;
+        B.d_counters_capacity = 0;
+        CUDA_TRY(cudaMalloc(&B.d_counters, (size_t) n_items * 16 * sizeof(unsigned long long)));
+        B.d_counters_capacity = (size_t) n_items * 16;
+    }
+    CUDA_TRY(cudaMemset(B.d_accum, 0, total * sizeof(double)));
+    CUDA_TRY(cudaMemset(B.d_counters, 0, (size_t) n_items * 16 * sizeof(unsigned long long)));
+    for (auto &T : S->slots)
+        if (!T.stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&T.stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&T.done, cudaEventDisableTiming));
+            T.async = true;
+        }
+    B.with_stats = with_stats != 0;
+    B.next = 0;
+    B.open = true;
+    B.t_begin = wall_ms();
+    return 0;
+}
+
+int ertb_batch_push(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, uint64_t sample_offset) {
+    if (!S) return set_error("null scene");
+    BatchState &B = S->batch;
+    if (!B.open) return set_error("ertb_batch_push: no open batch");
+    if (B.next >= (int) B.sensors.size()) return set_error("ertb_batch_push: more items than announced");
+    const int i = B.next;
+    if (sensor != B.sensors[i]) return set_error("ertb_batch_push: sensor differs from the announced one");
+    CUDA_TRY(cudaSetDevice(S->device));
+    TableSlot &T = S->slots[i % ERTB_BATCH_SLOTS];
+    if (T.busy) { // the render that last used this slot's tables must have finished
+        CUDA_TRY(cudaEventSynchronize(T.done));
+        T.busy = false;
+    }
+    unsigned long long *ctr = B.d_counters + (size_t) i * 16;
+    if (launch_render(S, sensor, seed, spp, sample_offset, B.d_accum + B.offsets[i],
+                      B.with_stats ? ctr + 8 : nullptr, T.stream, B.with_stats, &T, ctr))
+        return 1;
+    CUDA_TRY(cudaEventRecord(T.done, T.stream));
+    T.busy = true;
+    B.next = i + 1;
+    return 0;
+}
+
+int ertb_batch_end(ertb_scene *S, double *accum_out, size_t count, ertb_render_stats *stats, double *elapsed_ms) {
+    if (!S) return set_error("null scene");
+    BatchState &B = S->batch;
+    if (!B.open) return set_error("ertb_batch_end: no open batch");
+    CUDA_TRY(cudaSetDevice(S->device));
+    B.open = false;
+    if (batch_drain(S)) return 1;
+    if (elapsed_ms) *elapsed_ms = wall_ms() - B.t_begin;
+    if (B.next != (int) B.sensors.size()) return set_error("ertb_batch_end: fewer items pushed than announced");
+    if (accum_out) {
+        if (count != B.total) return set_error("ertb_batch_end: output size mismatch");
+        CUDA_TRY(cudaMemcpy(accum_out, B.d_accum, B.total * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (stats) {
+        std::vector<unsigned long long> h((size_t) B.next * 16);
+        CUDA_TRY(cudaMemcpy(h.data(), B.d_counters, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < B.next; ++i) {
+            const unsigned long long *c = &h[(size_t) i * 16 + 8];
+            memset(&stats[i], 0, sizeof stats[i]);
+            stats[i].n_paths = c[0];
+            stats[i].trips_main = c[1];
+            stats[i].trips_nee = c[2];
+            stats[i].n_scatter = c[3];
+            stats[i].n_surface = c[4];
+            stats[i].n_launches = 1;
+        }
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------
 // KAT kernels: the same device functions the render kernel uses, one thread per query
 // ----------------------------------------------------------------------------
 __global__ void kat_bsdf_eval_kernel(ErtbParams P, size_t n, const float *wi, const float *wo, float *out) {
@@ -787,7 +998,7 @@ struct DevBuf {
 static int kat_prepare(ertb_scene *S) {
     if (!S) return set_error("null scene");
     CUDA_TRY(cudaSetDevice(S->device));
-    if (S->dirty && scene_commit(S)) return 1;
+    if (S->dirty && scene_commit(S, S->main)) return 1;
     return 0;
 }
 #define KAT_GRID(n) (unsigned) (((n) + 127) / 128), 128

@@ -69,7 +69,59 @@ __device__ __forceinline__ unsigned pw_advance(const ErtbParams &P, const float 
     return r == PW_GROUND ? PM_SURF : PM_IDLE;
 }
 
-template <bool SPH, bool STATS, bool POL, bool PW = false>
+#ifndef ERTB_FLUSH_COLLECTIVE_MIN
+#define ERTB_FLUSH_COLLECTIVE_MIN 6
+#endif
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// Film flush. Per-lane atomics made small renders (a few hundred paths per warp) spend most of
+// their time serialised in the L2 atomic unit: every lane of every warp ends up adding to the
+// same few film addresses. When many lanes flush at once (a whole chunk finishing, the end of
+// the kernel) the flush is therefore a warp collective (all 32 lanes call it): the participating
+// lanes' float64 sums are grouped by pixel, reduced with shuffles, and one lane per pixel issues
+// the atomics. A lone straggler switching pixel still flushes on its own -- the collective costs
+// ~100 warp instructions whatever the number of participants.
+template <bool POL>
+__device__ __forceinline__ void film_flush_lane(const ErtbParams &P, unsigned pix, double wl, double l, double l2,
+                                                double q, double u, double v) {
+    atomicAdd(&P.accum[pix], wl);
+    atomicAdd(&P.accum[P.n_pixels + pix], l);
+    atomicAdd(&P.accum[2u * P.n_pixels + pix], l2);
+    if (POL) {
+        atomicAdd(&P.accum[3u * P.n_pixels + pix], wl);
+        atomicAdd(&P.accum[4u * P.n_pixels + pix], q);
+        atomicAdd(&P.accum[5u * P.n_pixels + pix], u);
+        atomicAdd(&P.accum[6u * P.n_pixels + pix], v);
+    }
+}
+
+template <bool POL>
+__device__ __noinline__ void film_flush_warp(const ErtbParams &P, unsigned lane, bool mine, unsigned acc_pix,
+                                             double acc_wl, double acc_l, double acc_l2, double acc_q, double acc_u,
+                                             double acc_v) {
+    if (!mine) acc_pix = 0xffffffffu;
+    unsigned todo = __ballot_sync(0xffffffffu, acc_pix != 0xffffffffu);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const unsigned pix = __shfl_sync(0xffffffffu, acc_pix, leader);
+        const bool in = acc_pix == pix;
+        double wl = warp_sum(in ? acc_wl : 0.0), l = warp_sum(in ? acc_l : 0.0), l2 = warp_sum(in ? acc_l2 : 0.0);
+        double q = 0.0, u = 0.0, v = 0.0;
+        if (POL) { q = warp_sum(in ? acc_q : 0.0); u = warp_sum(in ? acc_u : 0.0); v = warp_sum(in ? acc_v : 0.0); }
+        if ((int) lane == leader) film_flush_lane<POL>(P, pix, wl, l, l2, q, u, v);
+        todo &= ~__ballot_sync(0xffffffffu, in);
+    }
+}
+
+// COLL: collective mid-kernel film flushes, for renders whose chunks are small (many pixel
+// switches per lane). It is a template parameter because any call inside the scheduler loop
+// perturbs the register allocation of the walk phase (-3..7 % on the C2 headline, measured).
+template <bool SPH, bool STATS, bool POL, bool PW = false, bool COLL = false>
 __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
     static_assert(!(PW && SPH), "the piecewise medium is a plane-parallel layer stack");
     constexpr int NF = POL ? PF_COUNT_POL : PF_COUNT;
@@ -244,25 +296,28 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
             // =====================================================================
             // finish the previous path of the record + regenerate (integrator.cpp:449-520)
             // =====================================================================
+            {
+                // lanes about to accumulate a different pixel flush their sums first
+                unsigned pix_chk = have ? FLDU(PF_PIX, slot) : 0xffffffffu;
+                const bool sw = pix_chk != 0xffffffffu && acc_pix != 0xffffffffu && pix_chk != acc_pix;
+                if (COLL) {
+                    if (__popc(__ballot_sync(0xffffffffu, sw)) >= ERTB_FLUSH_COLLECTIVE_MIN)
+                        film_flush_warp<POL>(P, lane, sw, acc_pix, acc_wl, acc_l, acc_l2, acc_q, acc_u, acc_v);
+                    else if (sw)
+                        film_flush_lane<POL>(P, acc_pix, acc_wl, acc_l, acc_l2, acc_q, acc_u, acc_v);
+                } else if (sw) {
+                    film_flush_lane<POL>(P, acc_pix, acc_wl, acc_l, acc_l2, acc_q, acc_u, acc_v);
+                }
+                if (sw) {
+                    acc_wl = acc_l = acc_l2 = 0.0;
+                    acc_q = acc_u = acc_v = 0.0;
+                    acc_pix = 0xffffffffu;
+                }
+            }
             if (have) {
                 unsigned pix_old = FLDU(PF_PIX, slot);
                 if (pix_old != 0xffffffffu) {
-                    if (pix_old != acc_pix) {
-                        if (acc_pix != 0xffffffffu) {
-                            atomicAdd(&P.accum[acc_pix], acc_wl);
-                            atomicAdd(&P.accum[P.n_pixels + acc_pix], acc_l);
-                            atomicAdd(&P.accum[2u * P.n_pixels + acc_pix], acc_l2);
-                            if (POL) {
-                                atomicAdd(&P.accum[3u * P.n_pixels + acc_pix], acc_wl);
-                                atomicAdd(&P.accum[4u * P.n_pixels + acc_pix], acc_q);
-                                atomicAdd(&P.accum[5u * P.n_pixels + acc_pix], acc_u);
-                                atomicAdd(&P.accum[6u * P.n_pixels + acc_pix], acc_v);
-                            }
-                        }
-                        acc_wl = acc_l = acc_l2 = 0.0;
-                        acc_q = acc_u = acc_v = 0.0;
-                        acc_pix = pix_old;
-                    }
+                    acc_pix = pix_old; // (a lane holding another pixel's sums was flushed just above)
                     float r = FLD(PF_RES, slot);
                     float wr = FLD(PF_WRAY, slot);
                     acc_wl += (double) (wr * r);
@@ -694,17 +749,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
 #undef FLD
 #undef FLDU
 
-    if (acc_pix != 0xffffffffu) {
-        atomicAdd(&P.accum[acc_pix], acc_wl);
-        atomicAdd(&P.accum[P.n_pixels + acc_pix], acc_l);
-        atomicAdd(&P.accum[2u * P.n_pixels + acc_pix], acc_l2);
-        if (POL) {
-            atomicAdd(&P.accum[3u * P.n_pixels + acc_pix], acc_wl);
-            atomicAdd(&P.accum[4u * P.n_pixels + acc_pix], acc_q);
-            atomicAdd(&P.accum[5u * P.n_pixels + acc_pix], acc_u);
-            atomicAdd(&P.accum[6u * P.n_pixels + acc_pix], acc_v);
-        }
-    }
+    film_flush_warp<POL>(P, lane, true, acc_pix, acc_wl, acc_l, acc_l2, acc_q, acc_u, acc_v);
     if (STATS && P.stats) {
         unsigned v[5] = { st_paths, st_main, st_nee, st_scatter, st_surface };
 #pragma unroll

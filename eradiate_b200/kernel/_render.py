@@ -164,6 +164,36 @@ class DeviceScene:
             )
         )
 
+    # -- pipelined contexts x sensors loop (ertb_batch_*) -------------------
+    def batch_begin(self, sensors: list[int], with_stats: bool = False) -> None:
+        arr = (C.c_int * len(sensors))(*sensors)
+        _lib.check(self.lib.ertb_batch_begin(self.handle, len(sensors), arr, int(with_stats)))
+        self._batch = (list(sensors), with_stats)
+
+    def batch_push(self, sensor: int, seed: int, spp: int, sample_offset: int = 0) -> None:
+        """Snapshot the current parameters and queue one render; does not wait for it."""
+        self.sync()
+        _lib.check(self.lib.ertb_batch_push(self.handle, sensor, seed, spp, sample_offset))
+
+    def batch_end(self):
+        """Wait for the queued renders. Returns ([accumulators[rows, npix] per item], [stats], ms)."""
+        sensors, with_stats = self._batch
+        rows = 7 if self.flat.polarized else 3
+        npix = [self.lib.ertb_sensor_pixel_count(self.handle, i) for i in sensors]
+        out = np.zeros(rows * sum(npix), dtype=np.float64)
+        stats = (_abi.RenderStats * len(sensors))() if with_stats else None
+        ms = C.c_double(0.0)
+        _lib.check(
+            self.lib.ertb_batch_end(
+                self.handle, out.ctypes.data_as(_abi.c_double_p), out.size, stats, C.byref(ms)
+            )
+        )
+        items, o = [], 0
+        for n in npix:
+            items.append(out[o:o + rows * n].reshape(rows, n))
+            o += rows * n
+        return items, (list(stats) if with_stats else [None] * len(sensors)), ms.value
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.ertb_scene_destroy(self.handle)
@@ -434,19 +464,66 @@ def develop(scene, i_sensor: int, sum_wl, sum_l, sum_l2, spp: int, stokes=None) 
     return Bitmap(data, None, names, raw=raw)
 
 
+def _active_sensors(mi_scene, ctx):
+    sensors = mi_scene.obj.sensors()
+    active_sensors = getattr(ctx, "active_sensors", None)
+    if active_sensors is None:
+        return list(enumerate(sensors))
+    return [(i, sensors[i]) for i in active_sensors]
+
+
+def _mi_render_pipelined(mi_scene, ctxs, spp, seed_state) -> dict:
+    """
+    Same loop, same seeds, same results as the sequential one below, but the renders are
+    queued through ``ertb_batch_*``: the parameter update of context i+1 (host work + table
+    upload) overlaps the render of context i and all films come back with one copy.
+    """
+    scene = mi_scene.obj
+    plan = [(ctx, _active_sensors(mi_scene, ctx)) for ctx in ctxs]
+    dev = _device_scene(scene)
+    dev.batch_begin([i for _, act in plan for i, _ in act])
+    spps = []
+    for ctx, act in plan:
+        mi_scene.parameters.update(mi_scene.umap_template.render(ctx))
+        for i_sensor, mi_sensor in act:
+            seed = int(np.asarray(seed_state.next()).squeeze())
+            n = int(spp) if spp > 0 else mi_sensor.sampler().sample_count
+            dev.batch_push(i_sensor, seed & 0xFFFFFFFFFFFFFFFF, n)
+            spps.append(n)
+    items, _, _ = dev.batch_end()
+    results: dict = {}
+    k = 0
+    for ctx, act in plan:
+        for i_sensor, mi_sensor in act:
+            a = items[k]
+            bmp = develop(scene, i_sensor, a[0], a[1], a[2], spps[k], stokes=a[3:7] if a.shape[0] == 7 else None)
+            mi_sensor.film()._bitmap = bmp
+            results.setdefault(ctx.si.as_hashable, {})[mi_sensor.id()] = bmp
+            k += 1
+    return results
+
+
 def mi_render(
     mi_scene: MitsubaObjectWrapper,
     ctxs: list,
     spp: int = 0,
     seed_state: SeedState | None = None,
+    pipelined: bool = True,
 ) -> dict[t.Any, dict[str, Bitmap]]:
     """
     Render the scene for every context and active sensor (``_render.py:379-470``).
     Returns ``{ctx.si.as_hashable: {sensor_id: Bitmap}}``.
+
+    ``pipelined`` (extension, default on): queue the (context, sensor) renders through the
+    asynchronous batch entry points instead of synchronising after each of them; the seeds
+    drawn and the estimates returned are the same.
     """
     if seed_state is None:
         logger.debug("Using default RNG seed generator")
         seed_state = get_seed_state()
+
+    if pipelined and sum(len(_active_sensors(mi_scene, c)) for c in ctxs) > 1:
+        return _mi_render_pipelined(mi_scene, ctxs, spp, seed_state)
 
     results: dict = {}
     for ctx in ctxs:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 6
+#define ERTB_ABI_VERSION 7
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -240,6 +240,26 @@ int ertb_render_stokes(ertb_scene *scene, int sensor, uint64_t seed, uint64_t sp
                        double *sum_stokes, ertb_render_stats *stats);
 
 int ertb_sensor_pixel_count(const ertb_scene *scene, int sensor);
+
+/* Pipelined version of the contexts x sensors loop of mi_render
+ * (src/eradiate/kernel/_render.py:433-468).  The reference updates the scene
+ * parameters, renders and copies the film back strictly one (context, sensor) at a time.
+ * Here the caller announces the items of the loop, then for each item applies the parameter
+ * updates (ertb_scene_update) and calls ertb_batch_push, which snapshots the current
+ * parameters into private device tables (pinned staging buffer + async copy) and launches
+ * the render on one of ERTB_BATCH_SLOTS streams WITHOUT synchronising: the host prepares
+ * context i+1 while context i renders, and the tail of one render overlaps the head of the
+ * next.  ertb_batch_end waits for everything and returns all accumulators with one copy:
+ * item i occupies rows * n_pixels(sensors[i]) doubles ([sum_wl | sum_l | sum_l2 (| S0..S3)],
+ * rows = 3, or 7 for polarized scenes), items concatenated in push order.  Results are the
+ * same as n_items ertb_render calls with the same arguments.
+ *   stats      : n_items entries or NULL (only filled when with_stats != 0; device_ms is 0)
+ *   elapsed_ms : host wall-clock time from ertb_batch_begin to the end of the last render */
+int ertb_batch_begin(ertb_scene *scene, int n_items, const int *sensors, int with_stats);
+int ertb_batch_push(ertb_scene *scene, int sensor, uint64_t seed, uint64_t spp,
+                    uint64_t sample_offset);
+int ertb_batch_end(ertb_scene *scene, double *accum_out, size_t count,
+                   ertb_render_stats *stats, double *elapsed_ms);
 
 /* Known-answer-test entry points: evaluate the device implementations of the
  * plugins point-wise (one thread per query).  Host pointers.

@@ -523,6 +523,78 @@ def test_mi_render_boundary_protocol():
     assert not np.array_equal(a, b) and np.allclose(a[..., 0], b[..., 0], rtol=0.2)
 
 
+def test_mi_render_pipelined_equals_sequential():
+    """ertb_batch_* (SURVEY 8f-2): queued renders == one synchronous render per (context, sensor),
+    with more contexts than table slots so that slots are recycled while renders are in flight."""
+    spp = 1 << 13
+    kdict = scenes.config_c2(spp=spp, n_vza=5)
+    kdict["measure_2"] = dict(kdict["measure"], id="measure_2")
+    mi_scene = mi_traverse(mi_load_dict(kdict), scenes.spectral_update_map(1200, spherical=True))
+    ctxs = [KernelContext(w=w) for w in np.linspace(400.0, 900.0, 11)]
+    seq = mi_render(mi_scene, ctxs, spp=spp, seed_state=SeedState(5), pipelined=False)
+    pip = mi_render(mi_scene, ctxs, spp=spp, seed_state=SeedState(5), pipelined=True)
+    assert list(seq.keys()) == list(pip.keys())
+    for k in seq:
+        for sid in ("measure", "measure_2"):
+            a, b = seq[k][sid].raw, pip[k][sid].raw
+            for name in ("sum_wl", "sum_l", "sum_l2"):
+                assert np.allclose(a[name], b[name], rtol=1e-10), (k, sid, name)
+            assert np.allclose(np.array(seq[k][sid]), np.array(pip[k][sid]), rtol=1e-6)
+    # a synchronous render after a batch sees the last context's parameters, not a stale slot
+    again = render(mi_scene.obj, sensor=0, seed=123, spp=spp)
+    mi_scene.parameters.update(mi_scene.umap_template.render(ctxs[-1]))
+    ref = render(mi_scene.obj, sensor=0, seed=123, spp=spp)
+    assert np.allclose(again.raw["sum_l"], ref.raw["sum_l"], rtol=1e-10)
+
+
+def test_batch_ocean_tables_are_private_per_item():
+    """Every queued context of an ocean scene carries its own wavelength-dependent transmittance
+    tables (ocean_legacy.cpp:313-372) while earlier contexts are still rendering."""
+    from eradiate_b200.kernel._render import _device_scene
+    spp = 1 << 12
+    kd = scenes.atmosphere_scene(
+        geometry="plane_parallel", atmosphere="afgl",
+        surface={"type": "ocean_legacy", "wavelength": 550.0, "wind_speed": 5.0},
+        sensor={"type": "mdistant", "vza": np.linspace(-60, 60, 4), "vaa": 0.0}, spp=spp)
+    sc = mi_load_dict(kd)
+    w = mi_traverse(sc)
+    key = [k for k in w.parameters.keys() if k.endswith("wavelength")][0]
+    dev = _device_scene(sc)
+    wls = [440.0, 500.0, 550.0, 600.0, 670.0, 865.0]
+    single = []
+    for i, wl in enumerate(wls):
+        w.parameters.update({key: wl})
+        single.append(dev.render(0, 77 + i, spp)[1].copy())
+    dev.batch_begin([0] * len(wls), with_stats=True)
+    for i, wl in enumerate(wls):
+        w.parameters.update({key: wl})
+        dev.batch_push(0, 77 + i, spp)
+    items, stats, ms = dev.batch_end()
+    assert ms > 0.0 and all(st.n_paths == 4 * spp for st in stats)
+    for a, b in zip(single, items):
+        assert np.allclose(a, b[1], rtol=1e-10)
+    assert not np.allclose(items[0][1], items[-1][1], rtol=1e-3)
+
+
+def test_batch_error_paths():
+    from eradiate_b200.kernel._render import _device_scene
+    dev = _device_scene(mi_load_dict(scenes.config_c1()))
+    with pytest.raises(RuntimeError, match="no open batch"):
+        dev.batch_push(0, 1, 16)
+    with pytest.raises(RuntimeError, match="invalid sensor"):
+        dev.batch_begin([0, 4])
+    dev.batch_begin([0, 0])
+    dev.batch_push(0, 1, 16)
+    with pytest.raises(RuntimeError, match="fewer items"):
+        dev.batch_end()
+    dev.batch_begin([0])
+    dev.batch_push(0, 1, 16)
+    with pytest.raises(RuntimeError, match="more items"):
+        dev.batch_push(0, 2, 16)
+    items, _, _ = dev.batch_end()
+    assert items[0].shape == (3, 1) and items[0][1, 0] > 0.0
+
+
 def test_error_paths_through_the_abi():
     sc = mi_load_dict(scenes.config_c1())
     with pytest.raises(RuntimeError, match="sensor index"):
