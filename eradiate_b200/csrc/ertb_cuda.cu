@@ -68,6 +68,7 @@ struct TableSlot {
 };
 
 #define ERTB_BATCH_SLOTS 4
+#define ERTB_BATCH_GRID_DIV 3
 #define ERTB_MIN_WARP_PATHS 32ULL
 
 struct BatchState {
@@ -751,6 +752,13 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     unsigned long long want_warps = (total + warp_paths - 1) / warp_paths;
     unsigned long long want_blocks = (want_warps * 32ULL + block - 1) / block;
     unsigned long long grid = (unsigned long long) S->sm_count * blocks_per_sm;
+    if (slot) {
+        // batch items share the device: with a fraction of the resident CTAs each, consecutive
+        // items run side by side and the drain of one overlaps the bulk of the next
+        int div = ERTB_BATCH_GRID_DIV;
+        if (const char *e = getenv("ERTB_BATCH_GRID_DIV")) div = atoi(e);
+        if (div > 1 && blocks_per_sm / div >= 1) grid = (unsigned long long) S->sm_count * (blocks_per_sm / div);
+    }
     if (want_blocks < grid) grid = want_blocks ? want_blocks : 1;
 #define ERTB_LAUNCH(KERNEL) KERNEL<<<(unsigned) grid, block, smem, stream>>>(P)
     ERTB_DISPATCH(ERTB_LAUNCH);

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .kernel._render import _device_scene, develop
+from .kernel._render import SeedState, _active_sensors, _device_scene, develop, get_seed_state
 
 
 def is_distributed() -> bool:
@@ -97,3 +97,60 @@ def reduce_host_accumulators(arrays, group=None):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         out.append(t.numpy())
     return out
+
+
+# ------------------------------------------------------------------------------
+#      context ("band") sharding of the spectral loop: BASELINE config C5
+# ------------------------------------------------------------------------------
+
+
+def context_shard(n_items: int, rank: int, world: int) -> list[int]:
+    """Items of the contexts x sensors loop dealt round-robin: rank r takes r, r+G, r+2G, ..."""
+    return list(range(int(rank), int(n_items), int(world)))
+
+
+def _render_items_gpu(mi_scene, plan, mine, seeds, spps):
+    """This rank's items through the pipelined batch entry points (one device per rank)."""
+    dev = _device_scene(mi_scene.obj)
+    dev.batch_begin([plan[k][1] for k in mine])
+    last_ctx = None
+    for k in mine:
+        ctx, i_sensor, _ = plan[k]
+        if ctx is not last_ctx:
+            mi_scene.parameters.update(mi_scene.umap_template.render(ctx))
+            last_ctx = ctx
+        dev.batch_push(i_sensor, seeds[k], spps[k])
+    items, _, _ = dev.batch_end()
+    return items
+
+
+def mi_render_sharded(mi_scene, ctxs, spp: int = 0, seed_state: SeedState | None = None,
+                      render_items=_render_items_gpu, group=None) -> dict:
+    """
+    ``mi_render`` with the (context, sensor) items dealt round-robin over the ranks: each rank
+    renders its items at full spp and the films are gathered, so every rank returns the complete
+    ``{ctx.si.as_hashable: {sensor_id: Bitmap}}``. No reduction is involved ("band
+    sharding"). Every rank draws ALL seeds in the global loop order, so item k gets the same seed
+    whatever the world size: the result does not depend on the number of GPUs.
+    """
+    if seed_state is None:
+        seed_state = get_seed_state()
+    rank = dist.get_rank(group) if is_distributed() else 0
+    world = dist.get_world_size(group) if is_distributed() else 1
+    plan = [(ctx, i, s) for ctx in ctxs for i, s in _active_sensors(mi_scene, ctx)]
+    seeds = [int(np.asarray(seed_state.next()).squeeze()) & 0xFFFFFFFFFFFFFFFF for _ in plan]
+    spps = [int(spp) if spp > 0 else s.sampler().sample_count for _, _, s in plan]
+    mine = context_shard(len(plan), rank, world)
+    local = render_items(mi_scene, plan, mine, seeds, spps) if mine else []
+    payload = {k: np.asarray(a) for k, a in zip(mine, local)}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, payload, group=group)
+        payload = {k: a for part in gathered for k, a in part.items()}
+    results: dict = {}
+    for k, (ctx, i_sensor, mi_sensor) in enumerate(plan):
+        a = payload[k]
+        bmp = develop(mi_scene.obj, i_sensor, a[0], a[1], a[2], spps[k],
+                      stokes=a[3:7] if a.shape[0] == 7 else None)
+        results.setdefault(ctx.si.as_hashable, {})[mi_sensor.id()] = bmp
+    return results

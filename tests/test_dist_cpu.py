@@ -69,3 +69,69 @@ def test_two_rank_gloo_sharded_render_equals_single(tmp_path, oracle):
     assert np.allclose(got[0], wl, rtol=1e-12)
     assert np.allclose(got[1], l, rtol=1e-12)
     assert np.allclose(got[2], l2, rtol=1e-12)
+
+
+# --------------------------------------------------------------------------- band sharding
+def _oracle_items(mi_scene, plan, mine, seeds, spps):
+    """Stand-in for the GPU batch (test infrastructure): the CPU oracle renders this rank's items."""
+    from oracle import oracle
+
+    out = []
+    for k in mine:
+        ctx, i_sensor, _ = plan[k]
+        mi_scene.parameters.update(mi_scene.umap_template.render(ctx))
+        wl, l, l2, _ = oracle.render(mi_scene.obj.flat.build_desc(), i_sensor, seeds[k], spps[k], n_threads=2)
+        out.append(np.stack([wl, l, l2]))
+    return out
+
+
+def _band_scene():
+    from eradiate_b200 import scenes
+    from eradiate_b200.kernel import KernelContext, mi_load_dict, mi_traverse
+
+    kdict = scenes.config_c2(spp=64, n_vza=3)
+    kdict["measure_2"] = dict(kdict["measure"], id="measure_2")
+    mi_scene = mi_traverse(mi_load_dict(kdict), scenes.spectral_update_map(1200, spherical=True))
+    ctxs = [KernelContext(w=w) for w in (440.0, 550.0, 670.0, 865.0, 1020.0)]
+    return mi_scene, ctxs
+
+
+def _band_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from eradiate_b200.dist import mi_render_sharded
+    from eradiate_b200.kernel._render import SeedState
+
+    mi_scene, ctxs = _band_scene()
+    res = mi_render_sharded(mi_scene, ctxs, spp=64, seed_state=SeedState(3), render_items=_oracle_items)
+    if rank == 1:  # every rank holds the complete result
+        np.save(out, np.stack([res[c.si.as_hashable][s].raw["sum_l"] for c in ctxs for s in ("measure", "measure_2")]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_context_shard_is_a_partition():
+    from eradiate_b200.dist import context_shard
+
+    for n, world in ((10, 4), (3, 8), (960, 8), (1, 1)):
+        parts = [context_shard(n, r, world) for r in range(world)]
+        assert sorted(k for p in parts for k in p) == list(range(n))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_band_sharded_mi_render_equals_single(tmp_path, oracle):
+    from eradiate_b200.dist import mi_render_sharded
+    from eradiate_b200.kernel._render import SeedState
+
+    out = str(tmp_path / "bands.npy")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_band_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    mi_scene, ctxs = _band_scene()
+    res = mi_render_sharded(mi_scene, ctxs, spp=64, seed_state=SeedState(3), render_items=_oracle_items)
+    assert list(res.keys()) == [c.si.as_hashable for c in ctxs]
+    want = np.stack([res[c.si.as_hashable][s].raw["sum_l"] for c in ctxs for s in ("measure", "measure_2")])
+    assert got.shape == want.shape and np.allclose(got, want, rtol=1e-12)
+    assert not np.allclose(want[0], want[1])  # the two sensors of a context got different seeds

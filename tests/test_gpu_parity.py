@@ -547,6 +547,18 @@ def test_mi_render_pipelined_equals_sequential():
     assert np.allclose(again.raw["sum_l"], ref.raw["sum_l"], rtol=1e-10)
 
 
+def test_band_sharded_mi_render_single_rank_equals_mi_render():
+    from eradiate_b200.dist import mi_render_sharded
+    spp = 1 << 12
+    mi_scene = mi_traverse(mi_load_dict(scenes.config_c2(spp=spp, n_vza=4)),
+                           scenes.spectral_update_map(1200, spherical=True))
+    ctxs = [KernelContext(w=w) for w in (440.0, 550.0, 670.0)]
+    a = mi_render(mi_scene, ctxs, spp=spp, seed_state=SeedState(9))
+    b = mi_render_sharded(mi_scene, ctxs, spp=spp, seed_state=SeedState(9))
+    for k in a:
+        assert np.allclose(a[k]["measure"].raw["sum_l"], b[k]["measure"].raw["sum_l"], rtol=1e-10)
+
+
 def test_batch_ocean_tables_are_private_per_item():
     """Every queued context of an ocean scene carries its own wavelength-dependent transmittance
     tables (ocean_legacy.cpp:313-372) while earlier contexts are still rendering."""
