@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -40,6 +40,7 @@ PHASE_TABULATED_POLARIZED = 6
 SENSOR_MDISTANT = 0
 SENSOR_HDISTANT = 1
 SENSOR_DISTANTFLUX = 2
+SENSOR_PERSPECTIVE = 3
 
 # enum ertb_target_type
 TARGET_NONE = 0
@@ -61,6 +62,7 @@ PARAM_BSDF_PARAMS = 4
 PARAM_IRRADIANCE = 5
 PARAM_PHASE_PARAMS = 6
 PARAM_PHASE_MUELLER = 7
+PARAM_LEAF_BSDF = 8
 
 c_float_p = C.POINTER(C.c_float)
 c_double_p = C.POINTER(C.c_double)
@@ -90,6 +92,21 @@ class SensorDesc(C.Structure):
         ("target", C.c_double * 3),
         ("target_to_world", C.c_double * 16),
         ("ray_offset", C.c_double),
+        ("x_fov_deg", C.c_double),
+        ("near_clip", C.c_double),
+        ("far_clip", C.c_double),
+        ("in_medium", C.c_int32),
+        ("_pad1", C.c_int32),
+    ]
+
+
+class LeafGroupDesc(C.Structure):
+    _fields_ = [
+        ("n_disks", C.c_int32),
+        ("reflectance", C.c_float),
+        ("transmittance", C.c_float),
+        ("_pad", C.c_int32),
+        ("disks", c_float_p),
     ]
 
 
@@ -126,6 +143,11 @@ class SceneDesc(C.Structure):
         ("n_sensors", C.c_int32),
         ("_pad4", C.c_int32),
         ("sensors", C.POINTER(SensorDesc)),
+        ("n_leaf_groups", C.c_int32),
+        ("n_instances", C.c_int32),
+        ("leaf_groups", C.POINTER(LeafGroupDesc)),
+        ("instance_group", C.POINTER(C.c_int32)),
+        ("instance_offset", c_double_p),
     ]
 
 
@@ -179,4 +201,7 @@ EXPORTED_SYMBOLS = (
     "ertb_kat_piecewise_sample",
     "ertb_kat_piecewise_transmittance",
     "ertb_kat_sensor_ray",
+    "ertb_kat_canopy_intersect",
+    "ertb_kat_leaf_bsdf_eval",
+    "ertb_kat_leaf_bsdf_sample",
 )

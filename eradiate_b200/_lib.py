@@ -57,6 +57,9 @@ def load() -> C.CDLL:
     lib.ertb_kat_sensor_ray.argtypes = [vp, i32, C.c_size_t, fp, fp, dp, dp, fp]
     lib.ertb_kat_piecewise_sample.argtypes = [vp, C.c_size_t, fp, fp, fp, fp, C.POINTER(i32)]
     lib.ertb_kat_piecewise_transmittance.argtypes = [vp, C.c_size_t, fp, fp, fp]
+    lib.ertb_kat_canopy_intersect.argtypes = [vp, C.c_size_t, dp, fp, fp, dp, fp, C.POINTER(i32)]
+    lib.ertb_kat_leaf_bsdf_eval.argtypes = [vp, i32, C.c_size_t, fp, fp, fp]
+    lib.ertb_kat_leaf_bsdf_sample.argtypes = [vp, i32, C.c_size_t, fp, fp, fp, fp]
     for name in _abi.EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("ertb_abi_version", "ertb_device_count"):

@@ -1,0 +1,521 @@
+// ertb_canopy.cuh -- plane-parallel scenes with an explicit 3D canopy (BASELINE C4):
+// disk leaves (MI/src/shapes/disk.cpp:388-407) in instanced shape groups
+// (src/eradiate/scenes/biosphere/_core.py:266-296) with the bilambertian leaf BSDF
+// (ERP/bsdfs/bilambertian.cpp:60-215) under a 1D atmosphere, seen by the distant sensors or a
+// perspective camera (MI/src/sensors/perspective.cpp:200-236).
+//
+// Same estimator as the 1D kernels (volpath.cpp:93-572 / piecewise_volpath.cpp:91-527: free
+// flights bounded by the next surface, next-event estimation towards the sun at every real
+// event, Russian roulette), different execution model, because the work is different:
+//   * a path carries a world-space position (float64: kilometres of atmosphere, centimetres of
+//     leaf) and direction; the atmosphere is still only a function of altitude, so the medium
+//     walk is the 1D one (global-majorant delta/ratio tracking, or the analytic piecewise flight);
+//   * every segment that crosses the canopy's bounding box is intersected with a two-level BVH
+//     (instances -> disks) held in global memory (L2 resident: 32 B nodes, 32 B disks), in
+//     float32 coordinates relative to the canopy centre;
+//   * one path per lane, persistent warps, lanes refilled from the chunk queue as soon as their
+//     path ends; each trip of the main loop advances every live lane by one segment.
+#pragma once
+
+#include "ertb_kernel.cuh"
+#include "ertb_kernel_pool.cuh" // film_flush_warp
+#include "ertb_piecewise.cuh"
+
+#define ERTB_CANOPY_BLOCK 128
+#define ERTB_BVH_LEAF 4
+
+// ----------------------------------------------------------------------------
+// BVH traversal
+// ----------------------------------------------------------------------------
+// slab test; returns the entry distance (INFINITY: missed)
+__device__ __forceinline__ float aabb_entry(float4 lo, float4 hi, f3 o, f3 inv, float tmax) {
+    float a = (lo.x - o.x) * inv.x, b = (hi.x - o.x) * inv.x;
+    float t0 = fminf(a, b), t1 = fmaxf(a, b);
+    a = (lo.y - o.y) * inv.y; b = (hi.y - o.y) * inv.y;
+    t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+    a = (lo.z - o.z) * inv.z; b = (hi.z - o.z) * inv.z;
+    t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+    t0 = fmaxf(t0, 0.f); t1 = fminf(t1, tmax);
+    return t0 <= t1 ? t0 : INFINITY;
+}
+
+struct CanopyHit {
+    float t;    // distance along the ray (canopy-local units = metres); INFINITY: none
+    int inst;   // instance (index into C.inst)
+    int disk;   // disk (index into C.disks / 2)
+};
+
+// disk.cpp:388-407: plane hit with 0 <= t <= tmax inside the radius
+__device__ __forceinline__ float disk_hit(float4 c, float4 n, f3 o, f3 d, float tmax) {
+    float dn = d.x * n.x + d.y * n.y + d.z * n.z;
+    float t = __fdividef((c.x - o.x) * n.x + (c.y - o.y) * n.y + (c.z - o.z) * n.z, dn);
+    if (!(t >= 0.f && t <= tmax)) return INFINITY;
+    float px = fmaf(t, d.x, o.x) - c.x, py = fmaf(t, d.y, o.y) - c.y, pz = fmaf(t, d.z, o.z) - c.z;
+    return px * px + py * py + pz * pz <= c.w * c.w ? t : INFINITY;
+}
+
+// Nearest leaf (ANY = false) or any leaf (ANY = true) along o + t d, 0 <= t <= tmax, in canopy-local
+// coordinates. (skip_inst, skip_disk) names the leaf the ray starts on.
+//
+// ONE loop walks both levels: a stack entry is (node, instance), instance < 0 meaning a node of the
+// top-level tree. Lanes of a warp are then always executing the same few instructions (fetch a
+// node, test its two child boxes, push) whichever level and instance each of them is in; with one
+// loop nested in the other, lanes that reach different instances at different times run their
+// bottom-level traversals one after the other (2.3 active lanes per instruction, ncu r01e).
+template <bool ANY>
+__device__ __noinline__ CanopyHit canopy_trace(const ErtbCanopy &C, f3 o, f3 d, float tmax, int skip_inst, int skip_disk) {
+    CanopyHit H;
+    H.t = INFINITY; H.inst = -1; H.disk = -1;
+    const float big = 1e30f;
+    const f3 inv = mk3(fabsf(d.x) > 1e-30f ? 1.f / d.x : copysignf(big, d.x), fabsf(d.y) > 1e-30f ? 1.f / d.y : copysignf(big, d.y),
+                       fabsf(d.z) > 1e-30f ? 1.f / d.z : copysignf(big, d.z));
+    int2 stack[40];
+    int sp = 0;
+    int node = 0, ii = -1;
+    f3 ol = o; // origin in the coordinates of the current level
+    for (;;) {
+        const float4 *q = reinterpret_cast<const float4 *>((ii < 0 ? C.tlas : C.blas) + node);
+        const float4 l0 = __ldg(q), h0 = __ldg(q + 1), l1 = __ldg(q + 2), h1 = __ldg(q + 3);
+        const float lim = fminf(tmax, H.t);
+        float e[2] = { aabb_entry(l0, h0, ol, inv, lim), aabb_entry(l1, h1, ol, inv, lim) };
+        const int c[2] = { __float_as_int(l0.w), __float_as_int(l1.w) }, n[2] = { __float_as_int(h0.w), __float_as_int(h1.w) };
+        int next = -1, next_ii = ii;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (!(e[s] < INFINITY) || n[s] == 0) continue;
+            if (ii < 0) { // instances: their group's root goes on the stack
+                for (int k = c[s]; k < c[s] + n[s]; ++k)
+                    if (sp < 40) stack[sp++] = make_int2(__ldg(C.blas_root + __float_as_int(__ldg(C.inst + k).w)), k);
+            } else { // disks: intersected on the spot
+                for (int k = c[s]; k < c[s] + n[s]; ++k) {
+                    if (k == skip_disk && ii == skip_inst) continue;
+                    float t = disk_hit(__ldg(C.disks + 2 * k), __ldg(C.disks + 2 * k + 1), ol, d, fminf(tmax, H.t));
+                    if (t < H.t) { H.t = t; H.inst = ii; H.disk = k; if (ANY) return H; }
+                }
+            }
+            e[s] = INFINITY;
+        }
+        // inner children: the nearer one next, the other on the stack
+        if (e[0] < INFINITY && e[1] < INFINITY) {
+            const bool first0 = e[0] <= e[1];
+            if (sp < 40) stack[sp++] = make_int2(first0 ? c[1] : c[0], ii);
+            next = first0 ? c[0] : c[1];
+        } else if (e[0] < INFINITY) next = c[0];
+        else if (e[1] < INFINITY) next = c[1];
+        else {
+            if (sp == 0) return H;
+            const int2 top = stack[--sp];
+            next = top.x; next_ii = top.y;
+        }
+        if (next_ii != ii) {
+            ii = next_ii;
+            if (ii < 0) ol = o;
+            else { const float4 in = __ldg(C.inst + ii); ol = mk3(o.x - in.x, o.y - in.y, o.z - in.z); }
+        }
+        node = next;
+    }
+}
+
+// Clip the segment p + t d, 0 <= t <= tmax, to the canopy's bounding box (float64, world space).
+__device__ __forceinline__ bool canopy_clip(const ErtbCanopy &C, const double p[3], f3 d, double tmax, double &t0, double &t1) {
+    t0 = 0.0; t1 = tmax;
+    const float dd[3] = { d.x, d.y, d.z };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (dd[k] != 0.f) {
+            double inv = 1.0 / (double) dd[k];
+            double a = (C.lo[k] - p[k]) * inv, b = (C.hi[k] - p[k]) * inv;
+            t0 = fmax(t0, fmin(a, b)); t1 = fmin(t1, fmax(a, b));
+        } else if (p[k] < C.lo[k] || p[k] > C.hi[k]) return false;
+    }
+    return t0 <= t1;
+}
+
+// nearest leaf along a world-space segment; returns the distance from p (INFINITY: none)
+__device__ __forceinline__ double canopy_nearest(const ErtbCanopy &C, const double p[3], f3 d, double tmax,
+                                                 int skip_inst, int skip_disk, CanopyHit &H) {
+    H.t = INFINITY; H.inst = -1; H.disk = -1;
+    double t0, t1;
+    if (C.n_instances == 0 || !canopy_clip(C, p, d, tmax, t0, t1)) return INFINITY;
+    f3 o = mk3((float) (p[0] + t0 * (double) d.x - C.origin[0]), (float) (p[1] + t0 * (double) d.y - C.origin[1]),
+               (float) (p[2] + t0 * (double) d.z - C.origin[2]));
+    H = canopy_trace<false>(C, o, d, (float) (t1 - t0), skip_inst, skip_disk);
+    return H.inst >= 0 ? t0 + (double) H.t : INFINITY;
+}
+
+__device__ __forceinline__ bool canopy_shadowed(const ErtbCanopy &C, const double p[3], f3 d, int skip_inst, int skip_disk) {
+    double t0, t1;
+    if (C.n_instances == 0 || !canopy_clip(C, p, d, 1e30, t0, t1)) return false;
+    f3 o = mk3((float) (p[0] + t0 * (double) d.x - C.origin[0]), (float) (p[1] + t0 * (double) d.y - C.origin[1]),
+               (float) (p[2] + t0 * (double) d.z - C.origin[2]));
+    return canopy_trace<true>(C, o, d, (float) (t1 - t0), skip_inst, skip_disk).inst >= 0;
+}
+
+// ----------------------------------------------------------------------------
+// bilambertian.cpp (local frame: z = leaf normal; ci / co = cosines of wi / wo with it)
+// ----------------------------------------------------------------------------
+// value * |cos(theta_o)| (:124-159)
+__device__ __forceinline__ float bilambertian_eval(float r, float t, float ci, float co) {
+    return ((ci > 0.f) == (co > 0.f) ? r : t) * ERTB_INV_PI * fabsf(co);
+}
+// (:60-122) returns weight = value / pdf and the sampled local direction
+__device__ __forceinline__ float bilambertian_sample(float r, float t, float ci, float s1, float u1, float u2, f3 &wo) {
+    wo = cosine_hemisphere(u1, u2);
+    float rw = r + t > 0.f ? __fdividef(r, r + t) : 0.f;
+    float tw = r + t > 0.f ? 1.f - rw : 0.f;
+    const bool sel_r = s1 < rw;
+    float value = sel_r ? __fdividef(r, rw) : (tw > 0.f ? __fdividef(t, tw) : 0.f);
+    float pdf = wo.z * ERTB_INV_PI * (sel_r ? rw : tw);
+    if (!(ci > 0.f)) wo.z = -wo.z;
+    if (!sel_r) wo.z = -wo.z;
+    return pdf > 0.f ? value : 0.f;
+}
+
+// ----------------------------------------------------------------------------
+// primary rays: distant sensors aim at a target point T (mdistant.cpp:192-242,
+// hdistant.cpp:232-275, distantflux.cpp:148-195), the camera starts at its pinhole
+// ----------------------------------------------------------------------------
+// returns false when the sample contributes L = 0. Distant sensors: `p` is a point ON the ray (the
+// target), the caller moves it back to where the ray enters the scene.
+__device__ __forceinline__ bool canopy_primary(const ErtbParams &P, unsigned pix, Pcg32 &rng, double p[3], f3 &d,
+                                               float &wray, float &maxt) {
+    const ErtbSensor &S = P.sensor;
+    unsigned px = pix % (unsigned) S.width, py = pix / (unsigned) S.width;
+    float fx = __fdividef((float) px + pcg_float(rng), (float) S.width);
+    float fy = __fdividef((float) py + pcg_float(rng), (float) S.height);
+    float ax = pcg_float(rng), ay = pcg_float(rng);
+    wray = 1.f;
+    maxt = INFINITY;
+    if (S.type == ERTB_SENSOR_PERSPECTIVE) {
+        f3 dc = normalize3(mk3((1.f - 2.f * fx) * S.tan_half_fov, (1.f - 2.f * fy) * S.tan_half_fov / S.aspect, 1.f));
+        const float *M = S.to_world;
+        d = normalize3(mk3(M[0] * dc.x + M[1] * dc.y + M[2] * dc.z, M[3] * dc.x + M[4] * dc.y + M[5] * dc.z,
+                           M[6] * dc.x + M[7] * dc.y + M[8] * dc.z));
+        float inv_z = 1.f / dc.z;
+        float near_t = S.near_clip * inv_z;
+        p[0] = S.cam_origin[0] + (double) (near_t * d.x);
+        p[1] = S.cam_origin[1] + (double) (near_t * d.y);
+        p[2] = S.cam_origin[2] + (double) (near_t * d.z);
+        maxt = (S.far_clip - S.near_clip) * inv_z;
+        return true;
+    }
+    f3 fs = mk3(1.f, 0.f, 0.f), ft = mk3(0.f, 1.f, 0.f);
+    if (S.type == ERTB_SENSOR_MDISTANT) {
+        const float4 *t4 = reinterpret_cast<const float4 *>(S.table) + 2u * pix;
+        float4 a = __ldg(t4), c4 = __ldg(t4 + 1);
+        d = mk3(a.w, c4.x, c4.y);
+        onb(d, fs, ft);
+    } else {
+        f3 hv = uniform_hemisphere(fx, fy);
+        const float *M = S.to_world;
+        d = mk3(-(M[0] * hv.x + M[1] * hv.y + M[2] * hv.z), -(M[3] * hv.x + M[4] * hv.y + M[5] * hv.z),
+                -(M[6] * hv.x + M[7] * hv.y + M[8] * hv.z));
+        fs = mk3(M[0], M[3], M[6]);
+        ft = mk3(M[1], M[4], M[7]);
+        if (S.type == ERTB_SENSOR_DISTANTFLUX) wray = hv.z * S.flux_norm;
+    }
+    if (S.target_type == ERTB_TARGET_POINT) {
+        p[0] = S.target[0]; p[1] = S.target[1]; p[2] = S.target[2];
+    } else if (S.target_type == ERTB_TARGET_NONE) {
+        float ox, oy;
+        disk_concentric(ax, ay, ox, oy);
+        p[0] = S.bs_center[0] + ((double) fs.x * ox + (double) ft.x * oy) * S.bs_radius;
+        p[1] = S.bs_center[1] + ((double) fs.y * ox + (double) ft.y * oy) * S.bs_radius;
+        p[2] = S.bs_center[2] + ((double) fs.z * ox + (double) ft.z * oy) * S.bs_radius;
+    } else {
+        float lx, ly;
+        if (S.target_type == ERTB_TARGET_RECTANGLE) { lx = fmaf(2.f, ax, -1.f); ly = fmaf(2.f, ay, -1.f); }
+        else disk_concentric(ax, ay, lx, ly);
+        const double *T = S.target_to_world;
+        p[0] = T[0] * lx + T[1] * ly + T[3];
+        p[1] = T[4] * lx + T[5] * ly + T[7];
+        p[2] = T[8] * lx + T[9] * ly + T[11];
+    }
+    return d.z < 0.f; // distant sensors look down on a plane-parallel scene
+}
+
+// Sun visibility and atmospheric transmittance from `p` (altitude h above the ground) towards
+// the sun (volpath.cpp:400-554 / piecewise_volpath.cpp:392-527): leaves and the ground are opaque to
+// shadow rays (eval_null_transmission = 0), the medium attenuates by ratio tracking or exactly.
+template <bool PW, bool STATS>
+__device__ __forceinline__ float canopy_sun_transmittance(const ErtbParams &P, const float *tb, const double p[3], float h,
+                                                          bool in_medium, f3 sun, int skip_inst, int skip_disk,
+                                                          Pcg32 &rng, unsigned &st_nee) {
+    if (STATS && !(in_medium && P.has_medium)) st_nee++; // a shadow ray through vacuum is one loop trip
+    if (!(sun.z > 0.f)) return 0.f; // the ground plane is in the way
+    if (canopy_shadowed(P.canopy, p, sun, skip_inst, skip_disk)) return 0.f;
+    if (!in_medium || !P.has_medium) return 1.f;
+    if (PW) {
+        if (STATS) st_nee++;
+        return pw_transmittance_up(P, tb, h, sun.z);
+    }
+    float tr = 1.f, t = 0.f;
+    const float t_top = __fdividef(fmaxf(P.H - h, 0.f), sun.z);
+    for (;;) {
+        if (STATS) st_nee++;
+        t += -__logf(1.f - pcg_float(rng)) * P.inv_majorant;
+        if (!(t < t_top)) break;
+        tr *= 1.f - tb[P.off_preal + layer_of(P, fmaf(t, sun.z, h))];
+        if (tr == 0.f) break;
+    }
+    return tr;
+}
+
+enum : int { CEV_NONE = 0, CEV_COLLISION = 1, CEV_GROUND = 2, CEV_LEAF = 3, CEV_END = 4 };
+
+template <bool STATS, bool PW>
+__global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, 4) ertb_canopy_kernel(const ErtbParams P) {
+    extern __shared__ __align__(16) float tb[]; // table blob
+    __shared__ __align__(8) unsigned long long mbar;
+    if (P.blob_bytes > 0) tma_stage(tb, P.blob, (unsigned) P.blob_bytes, &mbar);
+
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const f3 sun = mk3(P.sun[0], P.sun[1], P.sun[2]);
+    const ErtbCanopy &C = P.canopy;
+    const double z_ground = P.Rd;
+
+    // per-lane path state
+    bool alive = false, in_medium = false, first_segment = false;
+    double p[3] = { 0.0, 0.0, 0.0 };
+    f3 d = mk3(0.f, 0.f, -1.f);
+    float thr = 0.f, res = 0.f, wray = 1.f, maxt = INFINITY;
+    unsigned depth = 0, pix = 0;
+    int on_inst = -1, on_disk = -1; // the leaf the current ray starts on
+    Pcg32 rng;
+    rng.state = 0; rng.inc = 1;
+
+    double acc_wl = 0.0, acc_l = 0.0, acc_l2 = 0.0;
+    unsigned acc_pix = 0xffffffffu;
+    unsigned long long cur_next = 0, cur_end = 0;
+    unsigned cur_pix = 0;
+    bool exhausted = false;
+    unsigned st_main = 0, st_nee = 0, st_scatter = 0, st_surface = 0, st_paths = 0;
+
+    for (;;) {
+        // ---- path regeneration: finished lanes pop the next samples (warp-aggregated) ----
+        {
+            unsigned pending = __ballot_sync(0xffffffffu, !alive);
+            bool got = false;
+            unsigned long long my_sample = 0;
+            unsigned my_pix = 0;
+            while (pending && !exhausted) {
+                if (cur_next >= cur_end) {
+                    unsigned long long c = 0;
+                    if (lane == 0) c = atomicAdd(P.work_counter, 1ULL);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (c >= P.n_chunks) { exhausted = true; break; }
+                    cur_pix = (unsigned) (c % P.n_pixels);
+                    unsigned long long k = c / P.n_pixels;
+                    cur_next = k * P.chunk;
+                    cur_end = min(cur_next + (unsigned long long) P.chunk, P.spp);
+                }
+                unsigned long long avail = cur_end - cur_next;
+                unsigned take = (unsigned) min((unsigned long long) __popc(pending), avail);
+                bool mine = (pending >> lane) & 1u;
+                unsigned rank = __popc(pending & lt_mask);
+                if (mine && rank < take && !got) { got = true; my_sample = cur_next + rank; my_pix = cur_pix; }
+                cur_next += take;
+                pending &= ~__ballot_sync(0xffffffffu, mine && rank < take);
+            }
+            if (got) {
+                pix = my_pix;
+                if (pix != acc_pix) {
+                    if (acc_pix != 0xffffffffu) film_flush_lane<false>(P, acc_pix, acc_wl, acc_l, acc_l2, 0.0, 0.0, 0.0);
+                    acc_wl = acc_l = acc_l2 = 0.0;
+                    acc_pix = pix;
+                }
+                pcg_seed(rng, P.seed, ((unsigned long long) pix << 40) + (P.sample_offset + my_sample));
+                if (STATS) st_paths++;
+                thr = 1.f; res = 0.f; depth = 0; on_inst = on_disk = -1;
+                alive = canopy_primary(P, pix, rng, p, d, wray, maxt);
+                first_segment = true;
+                if (P.sensor.type == ERTB_SENSOR_PERSPECTIVE) {
+                    in_medium = P.sensor.in_medium != 0;
+                } else if (alive) {
+                    // distant sensors sit outside the scene: bring the origin down to where the ray
+                    // enters it (top of the atmosphere, or just above the canopy without one)
+                    in_medium = false;
+                    double z_in = P.has_medium ? z_ground + (double) P.H : fmax(C.n_instances ? C.hi[2] : z_ground, p[2]) + 1.0;
+                    double t_in = (z_in - p[2]) / (double) d.z; // <= 0: move backwards along the ray
+                    p[0] += t_in * (double) d.x; p[1] += t_in * (double) d.y; p[2] = z_in;
+                }
+                // (an invalid primary ray is a sample with L = 0: nothing to accumulate)
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) {
+            if (exhausted) break;
+            continue;
+        }
+
+        if (alive) {
+            // ---- termination (volpath.cpp:189-202) ----
+            bool dead = thr == 0.f || depth >= P.max_depth;
+            if (!dead && depth > P.rr_depth) {
+                float q = fminf(thr, 0.95f);
+                if (pcg_float(rng) >= q) dead = true;
+                else thr = __fdividef(thr, q);
+            }
+            int ev = dead ? CEV_END : CEV_NONE;
+            CanopyHit hit;
+            hit.t = INFINITY; hit.inst = -1; hit.disk = -1;
+            float h = (float) (p[2] - z_ground); // altitude above the ground
+            float nee = 0.f;                      // value of the pending sun sample (before transmittance)
+
+            if (ev == CEV_NONE) {
+                // a ray above the atmosphere travels through vacuum down to its top
+                if (!in_medium && P.has_medium && h >= P.H) {
+                    if (!(d.z < 0.f)) ev = CEV_END; // leaves the scene
+                    else {
+                        double t_in = ((double) P.H - (p[2] - z_ground)) / (double) d.z;
+                        p[0] += t_in * (double) d.x; p[1] += t_in * (double) d.y; p[2] = z_ground + (double) P.H;
+                        h = P.H;
+                        in_medium = true;
+                        if (first_segment) maxt -= (float) t_in;
+                    }
+                }
+            }
+            if (ev == CEV_NONE) {
+                // ---- next surface along the ray: ground plane / top of the slab / nearest leaf ----
+                const bool down = d.z < 0.f;
+                double t_geo = down ? (p[2] - z_ground) / (double) -d.z
+                                    : (in_medium && d.z > 0.f ? fmax((double) P.H - (p[2] - z_ground), 0.0) / (double) d.z : 1e30);
+                int ev_geo = down ? CEV_GROUND : CEV_END; // upward: leaves through the top (or to infinity)
+                if (t_geo > 1e9) { t_geo = 1e9; ev_geo = CEV_END; } // grazing rays: the reference's slab is 1e9 m wide
+                if (first_segment && (double) maxt < t_geo) { t_geo = (double) maxt; ev_geo = CEV_END; } // far clip
+                double t_leaf = canopy_nearest(C, p, d, t_geo, on_inst, on_disk, hit);
+                double t_seg = t_geo;
+                int ev_seg = ev_geo;
+                if (t_leaf < t_geo) { t_seg = t_leaf; ev_seg = CEV_LEAF; }
+
+                // ---- free flight through the medium, bounded by t_seg ----
+                double t_ev = t_seg;
+                ev = ev_seg;
+                if (STATS && !(in_medium && P.has_medium)) st_main++; // a vacuum segment is one loop trip
+                if (in_medium && P.has_medium) {
+                    if (PW) {
+                        if (STATS) st_main++;
+                        float s, hn;
+                        int r = pw_flight(P, tb, h, d.z, -__logf(1.f - pcg_float(rng)), s, hn);
+                        if (r == PW_COLLISION && (double) s < t_seg) { t_ev = (double) s; ev = CEV_COLLISION; }
+                    } else {
+                        float t = 0.f;
+                        const float ts = (float) fmin(t_seg, 1e30);
+                        for (;;) {
+                            if (STATS) st_main++;
+                            t += -__logf(1.f - pcg_float(rng)) * P.inv_majorant;
+                            if (!(t < ts)) break;
+                            float preal = tb[P.off_preal + layer_of(P, fmaf(t, d.z, h))];
+                            if (pcg_float(rng) >= 1.f - preal) { t_ev = (double) t; ev = CEV_COLLISION; break; }
+                        }
+                    }
+                }
+                // ---- move to the event ----
+                if (ev != CEV_END) {
+                    p[0] += t_ev * (double) d.x; p[1] += t_ev * (double) d.y; p[2] += t_ev * (double) d.z;
+                    if (ev == CEV_GROUND) p[2] = z_ground;
+                    h = fmaxf((float) (p[2] - z_ground), 0.f);
+                }
+                first_segment = false;
+            }
+
+            if (ev == CEV_COLLISION) {
+                // ---- real collision (volpath.cpp:261-310) ----
+                int l = layer_of(P, h);
+                thr *= tb[P.off_albedo + l];
+                depth++;
+                on_inst = on_disk = -1;
+                if (STATS) st_scatter++;
+                if (depth >= P.max_depth || thr == 0.f) ev = CEV_END;
+                else {
+                    float ct_sun = dot3(d, sun);
+                    float pv = 0.f;
+                    int leaf = 0;
+                    if (P.n_phase == 1) pv = leaf_eval(tb, P.leaf[0], ct_sun);
+                    else {
+                        float u0 = pcg_float(rng), prev = 0.f;
+                        leaf = P.n_phase - 1;
+                        bool picked = false;
+                        for (int i = 0; i < P.n_phase; ++i) {
+                            float cum = (i < P.n_phase - 1) ? tb[P.off_cumw + i * P.n_layers + l] : 1.f;
+                            float w = cum - prev;
+                            prev = cum;
+                            if (w > 0.f) pv = fmaf(w, leaf_eval(tb, P.leaf[i], ct_sun), pv);
+                            if (!picked && u0 < cum) { leaf = i; picked = true; }
+                        }
+                    }
+                    nee = thr * pv * P.irradiance;
+                    float u1 = pcg_float(rng), u2 = pcg_float(rng);
+                    float pw, ppdf;
+                    float ct = leaf_sample(tb, P.leaf[leaf], u1, pw, ppdf);
+                    if (ppdf > 0.f) {
+                        float st = safe_sqrtf(1.f - ct * ct), sp, cp;
+                        __sincosf(2.f * ERTB_PI * u2, &sp, &cp);
+                        f3 fs, ft;
+                        onb(d, fs, ft);
+                        d = normalize3(fma3(fs, st * cp, fma3(ft, st * sp, scale3(d, ct))));
+                        thr *= pw;
+                    }
+                }
+            } else if (ev == CEV_GROUND) {
+                // ---- ground BSDF (volpath.cpp:344-389), local frame = world axes ----
+                if (STATS) st_surface++;
+                on_inst = on_disk = -1;
+                float ci = -d.z;
+                if (!(ci > 0.f) || P.bsdf_type == ERTB_BSDF_BLACK) ev = CEV_END;
+                else {
+                    float f_sun, weight;
+                    const f3 up = mk3(0.f, 0.f, 1.f);
+                    surface_interact<false>(P, up, sun, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
+                    nee = thr * f_sun * P.irradiance;
+                    thr *= weight;
+                    depth++;
+                }
+            } else if (ev == CEV_LEAF) {
+                // ---- leaf: bilambertian reflection / transmission; the medium does not change ----
+                if (STATS) st_surface++;
+                float4 in = __ldg(C.inst + hit.inst);
+                float4 nn = __ldg(C.disks + 2 * hit.disk + 1);
+                const float *lb = tb + C.off_leaf_bsdf + 2 * __float_as_int(in.w);
+                float2 rt = make_float2(lb[0], lb[1]);
+                f3 n = mk3(nn.x, nn.y, nn.z);
+                float ci = -dot3(n, d);
+                on_inst = hit.inst; on_disk = hit.disk;
+                if (depth + 1u < P.max_depth) {
+                    float co = dot3(n, sun);
+                    nee = thr * bilambertian_eval(rt.x, rt.y, ci, co) * P.irradiance;
+                }
+                float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
+                f3 wl;
+                thr *= bilambertian_sample(rt.x, rt.y, ci, s1, u1, u2, wl);
+                f3 fs, ft;
+                onb(n, fs, ft);
+                d = normalize3(fma3(fs, wl.x, fma3(ft, wl.y, scale3(n, wl.z))));
+                depth++;
+            }
+            // ---- next-event estimation, ONE site for all event kinds: the lanes' shadow rays walk the
+            //      BVH together (volpath.cpp:400-554); the sample is taken at the event position ----
+            if (nee > 0.f)
+                res += nee * canopy_sun_transmittance<PW, STATS>(P, tb, p, h, in_medium && P.has_medium, sun, on_inst, on_disk,
+                                                                   rng, st_nee);
+            if (ev == CEV_END) {
+                acc_wl += (double) (wray * res);
+                acc_l += (double) res;
+                acc_l2 += (double) res * (double) res;
+                alive = false;
+            }
+        }
+    }
+
+    film_flush_warp<false>(P, lane, true, acc_pix, acc_wl, acc_l, acc_l2, 0.0, 0.0, 0.0);
+    if (STATS && P.stats) {
+        unsigned v[5] = { st_paths, st_main, st_nee, st_scatter, st_surface };
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            unsigned long long x = v[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) atomicAdd(&P.stats[i], x);
+        }
+    }
+}

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <utility>
@@ -15,6 +16,7 @@
 
 #include "ertb_kernel.cuh"
 #include "ertb_kernel_pool.cuh"
+#include "ertb_canopy.cuh"
 
 // ----------------------------------------------------------------------------
 // error handling
@@ -85,6 +87,101 @@ struct BatchState {
     double t_begin = 0.0;
 };
 
+// ----------------------------------------------------------------------------
+// canopy: host copy + BVH construction
+// ----------------------------------------------------------------------------
+struct HostLeafGroup {
+    std::vector<float> disks; // n x 7
+    float reflectance = 0.f, transmittance = 0.f;
+};
+
+struct BvhBox {
+    float lo[3], hi[3];
+    void grow(const BvhBox &o) {
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], o.lo[k]); hi[k] = fmaxf(hi[k], o.hi[k]); }
+    }
+    static BvhBox empty() {
+        BvhBox b;
+        for (int k = 0; k < 3; ++k) { b.lo[k] = INFINITY; b.hi[k] = -INFINITY; }
+        return b;
+    }
+};
+
+// Median-split binary BVH over `boxes` (leaves hold <= ERTB_BVH_LEAF primitives), then folded into
+// the device layout where every node carries the boxes of its two children. `order` receives the
+// primitive permutation the leaves index into (offset by `prim_base`); returns the root's index in
+// `out` (several trees share one array).
+struct BinNode { BvhBox box; int first, count, left; };
+
+static int build_bvh(const std::vector<BvhBox> &boxes, std::vector<ErtbBvhNode> &out, std::vector<int> &order, int prim_base) {
+    const int n = (int) boxes.size();
+    order.resize(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::vector<BinNode> nodes;
+    struct Item { int node, first, count; };
+    std::vector<Item> stack;
+    nodes.push_back(BinNode());
+    stack.push_back({ 0, 0, n });
+    while (!stack.empty()) {
+        Item it = stack.back();
+        stack.pop_back();
+        BvhBox bb = BvhBox::empty(), cb = BvhBox::empty();
+        for (int i = it.first; i < it.first + it.count; ++i) {
+            const BvhBox &b = boxes[order[i]];
+            bb.grow(b);
+            BvhBox c;
+            for (int k = 0; k < 3; ++k) c.lo[k] = c.hi[k] = 0.5f * (b.lo[k] + b.hi[k]);
+            cb.grow(c);
+        }
+        for (int k = 0; k < 3; ++k) { // pad by an ulp-scale margin: traversal compares in float
+            float pad = 1e-6f * fmaxf(1.f, fmaxf(fabsf(bb.lo[k]), fabsf(bb.hi[k])));
+            bb.lo[k] -= pad; bb.hi[k] += pad;
+        }
+        BinNode nd;
+        nd.box = bb; nd.first = it.first; nd.count = it.count; nd.left = -1;
+        int axis = 0;
+        float ext = cb.hi[0] - cb.lo[0];
+        for (int k = 1; k < 3; ++k) if (cb.hi[k] - cb.lo[k] > ext) { ext = cb.hi[k] - cb.lo[k]; axis = k; }
+        if (it.count > ERTB_BVH_LEAF && ext > 0.f) {
+            const int mid = it.first + it.count / 2;
+            std::nth_element(order.begin() + it.first, order.begin() + mid, order.begin() + it.first + it.count,
+                             [&](int a, int b) { return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis]; });
+            nd.left = (int) nodes.size();
+            nd.count = 0;
+            nodes.push_back(BinNode());
+            nodes.push_back(BinNode());
+            stack.push_back({ nd.left, it.first, mid - it.first });
+            stack.push_back({ nd.left + 1, mid, it.first + it.count - mid });
+        }
+        nodes[it.node] = nd;
+    }
+    // fold: one wide node per inner binary node (a single-leaf tree gets an inner root with one empty child)
+    std::vector<int> wide_of(nodes.size(), -1);
+    const int root = (int) out.size();
+    auto child = [&](const BinNode &c, float *lo, float *hi, int &ref, int &cnt) {
+        for (int k = 0; k < 3; ++k) { lo[k] = c.box.lo[k]; hi[k] = c.box.hi[k]; }
+        if (c.count > 0) { ref = prim_base + c.first; cnt = c.count; }
+        else { ref = wide_of[&c - nodes.data()]; cnt = 0; }
+    };
+    for (size_t i = 0; i < nodes.size(); ++i)
+        if (nodes[i].left >= 0) { wide_of[i] = (int) out.size(); out.push_back(ErtbBvhNode()); }
+    if (nodes[0].left < 0) {
+        ErtbBvhNode w;
+        child(nodes[0], w.lo0, w.hi0, w.c0, w.n0);
+        for (int k = 0; k < 3; ++k) w.lo1[k] = w.hi1[k] = 3e38f; // a point no segment reaches
+        w.c1 = 0; w.n1 = 0;
+        out.push_back(w);
+        return root;
+    }
+    for (size_t i = 0; i < nodes.size(); ++i)
+        if (nodes[i].left >= 0) {
+            ErtbBvhNode &w = out[wide_of[i]];
+            child(nodes[nodes[i].left], w.lo0, w.hi0, w.c0, w.n0);
+            child(nodes[nodes[i].left + 1], w.lo1, w.hi1, w.c1, w.n1);
+        }
+    return root;
+}
+
 struct ertb_scene {
     int device = 0;
     int geometry = 0;
@@ -120,7 +217,99 @@ struct ertb_scene {
     std::map<std::pair<const void *, size_t>, int> occupancy; // per kernel instantiation and smem size
     int max_smem_optin = 0;
     double *d_gl = nullptr;     // Gauss-Legendre nodes/weights of the ocean transmittance quadrature
+    // canopy (plane-parallel scenes): host description and the device BVH
+    std::vector<HostLeafGroup> leaf_groups;
+    std::vector<int> instance_group;
+    std::vector<double> instance_offset;
+    ErtbCanopy canopy;          // device pointers (zero-initialised: no canopy)
+    void *d_canopy[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    bool needs_3d = false;      // canopy or perspective sensor: rendered by ertb_canopy_kernel
 };
+
+static int build_canopy(ertb_scene *S) {
+    memset(&S->canopy, 0, sizeof S->canopy);
+    const int ninst = (int) S->instance_group.size();
+    if (ninst == 0) return 0;
+    const int ng = (int) S->leaf_groups.size();
+    // world bounding box of every instance
+    std::vector<BvhBox> gbox(ng, BvhBox::empty());
+    std::vector<std::vector<BvhBox>> dboxes(ng);
+    for (int g = 0; g < ng; ++g) {
+        const std::vector<float> &dk = S->leaf_groups[g].disks;
+        const int n = (int) dk.size() / 7;
+        dboxes[g].resize(n);
+        for (int i = 0; i < n; ++i) {
+            BvhBox b;
+            for (int k = 0; k < 3; ++k) {
+                float nk = dk[7 * i + 3 + k];
+                float e = dk[7 * i + 6] * sqrtf(fmaxf(1.f - nk * nk, 0.f));
+                b.lo[k] = dk[7 * i + k] - e; b.hi[k] = dk[7 * i + k] + e;
+            }
+            dboxes[g][i] = b;
+            gbox[g].grow(b);
+        }
+    }
+    double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int i = 0; i < ninst; ++i)
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fmin(lo[k], S->instance_offset[3 * i + k] + (double) gbox[S->instance_group[i]].lo[k]);
+            hi[k] = fmax(hi[k], S->instance_offset[3 * i + k] + (double) gbox[S->instance_group[i]].hi[k]);
+        }
+    ErtbCanopy &C = S->canopy;
+    for (int k = 0; k < 3; ++k) {
+        double pad = 1e-4 * fmax(1.0, hi[k] - lo[k]);
+        C.lo[k] = lo[k] - pad; C.hi[k] = hi[k] + pad;
+        C.origin[k] = 0.5 * (lo[k] + hi[k]);
+    }
+    C.lo[2] = fmax(C.lo[2], S->surface_z); // leaves may dip below the ground plane; rays never do
+    // bottom level: one tree per group, disks reordered into leaf order
+    std::vector<ErtbBvhNode> blas;
+    std::vector<int> blas_root(ng);
+    std::vector<float> disks;
+    for (int g = 0; g < ng; ++g) {
+        std::vector<int> order;
+        blas_root[g] = build_bvh(dboxes[g], blas, order, (int) disks.size() / 8);
+        const std::vector<float> &dk = S->leaf_groups[g].disks;
+        for (int i : order) {
+            const float *q = &dk[7 * (size_t) i];
+            const float row[8] = { q[0], q[1], q[2], q[6], q[3], q[4], q[5], 0.f };
+            disks.insert(disks.end(), row, row + 8);
+        }
+    }
+    // top level over the instances (float coordinates relative to the canopy origin)
+    std::vector<BvhBox> iboxes(ninst);
+    for (int i = 0; i < ninst; ++i)
+        for (int k = 0; k < 3; ++k) {
+            float off = (float) (S->instance_offset[3 * i + k] - C.origin[k]);
+            iboxes[i].lo[k] = off + gbox[S->instance_group[i]].lo[k];
+            iboxes[i].hi[k] = off + gbox[S->instance_group[i]].hi[k];
+        }
+    std::vector<ErtbBvhNode> tlas;
+    std::vector<int> iorder;
+    build_bvh(iboxes, tlas, iorder, 0);
+    std::vector<float> inst(4 * (size_t) ninst);
+    for (int j = 0; j < ninst; ++j) {
+        const int i = iorder[j];
+        for (int k = 0; k < 3; ++k) inst[4 * j + k] = (float) (S->instance_offset[3 * i + k] - C.origin[k]);
+        int g = S->instance_group[i];
+        memcpy(&inst[4 * j + 3], &g, sizeof(float));
+    }
+    const void *src[5] = { tlas.data(), inst.data(), blas.data(), blas_root.data(), disks.data() };
+    const size_t bytes[5] = { tlas.size() * sizeof(ErtbBvhNode), inst.size() * sizeof(float),
+                              blas.size() * sizeof(ErtbBvhNode), blas_root.size() * sizeof(int),
+                              disks.size() * sizeof(float) };
+    for (int k = 0; k < 5; ++k) {
+        CUDA_TRY(cudaMalloc(&S->d_canopy[k], bytes[k]));
+        CUDA_TRY(cudaMemcpy(S->d_canopy[k], src[k], bytes[k], cudaMemcpyHostToDevice));
+    }
+    C.n_instances = ninst;
+    C.tlas = (const ErtbBvhNode *) S->d_canopy[0];
+    C.inst = (const float4 *) S->d_canopy[1];
+    C.blas = (const ErtbBvhNode *) S->d_canopy[2];
+    C.blas_root = (const int *) S->d_canopy[3];
+    C.disks = (const float4 *) S->d_canopy[4];
+    return 0;
+}
 
 static size_t align4(size_t n) { return (n + 3) & ~size_t(3); }
 
@@ -272,6 +461,10 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
     }
     P.majorant = (float) majorant;
     P.inv_majorant = majorant > 0.0 ? (float) (1.0 / majorant) : INFINITY;
+    P.canopy = S->canopy;
+    P.canopy.off_leaf_bsdf = (int) blob.size();
+    for (const HostLeafGroup &g : S->leaf_groups) { blob.push_back(g.reflectance); blob.push_back(g.transmittance); }
+    blob.resize(align4(blob.size()), 0.f);
 
     const size_t blob_bytes = blob.size() * sizeof(float);
     if (blob_bytes > (size_t) S->max_smem_optin - 1024)
@@ -415,6 +608,14 @@ static void fill_sensor_params(const ertb_scene *S, const HostSensor &hs, ErtbSe
     o.bs_radius = fmax(eps, S->bs_radius * (1.0 + eps));
     o.ray_offset = hs.ray_offset;
     o.flux_norm = (float) (2.0 * M_PI / (double) (sd.width * sd.height));
+    if (sd.type == ERTB_SENSOR_PERSPECTIVE) {
+        o.cam_origin[0] = sd.to_world[3]; o.cam_origin[1] = sd.to_world[7]; o.cam_origin[2] = sd.to_world[11];
+        o.tan_half_fov = (float) tan(0.5 * sd.x_fov_deg * M_PI / 180.0);
+        o.aspect = (float) sd.width / (float) sd.height;
+        o.near_clip = (float) sd.near_clip;
+        o.far_clip = (float) sd.far_clip;
+        o.in_medium = sd.in_medium;
+    }
 }
 
 // ----------------------------------------------------------------------------
@@ -446,6 +647,8 @@ void ertb_scene_destroy(ertb_scene *S) {
     if (S->batch.d_accum) cudaFree(S->batch.d_accum);
     if (S->batch.d_counters) cudaFree(S->batch.d_counters);
     if (S->d_gl) cudaFree(S->d_gl);
+    for (void *q : S->d_canopy)
+        if (q) cudaFree(q);
     if (S->d_counter) cudaFree(S->d_counter);
     if (S->d_accum) cudaFree(S->d_accum);
     if (S->ev0) cudaEventDestroy(S->ev0);
@@ -541,6 +744,43 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
                          "plane-parallel piecewise medium)");
     }
 
+    if (D->n_instances > 0) {
+        if (D->geometry != ERTB_GEOM_PLANE_PARALLEL || S->polarized) {
+            delete S;
+            return set_error("explicit canopies are supported in unpolarized plane-parallel scenes only");
+        }
+        if (D->n_leaf_groups < 1 || !D->leaf_groups || !D->instance_group || !D->instance_offset) {
+            delete S;
+            return set_error("canopy arrays missing");
+        }
+        for (int g = 0; g < D->n_leaf_groups; ++g) {
+            const ertb_leaf_group_desc &gd = D->leaf_groups[g];
+            if (gd.n_disks < 1 || !gd.disks) { delete S; return set_error("leaf group without disks"); }
+            HostLeafGroup hg;
+            hg.disks.assign(gd.disks, gd.disks + 7 * (size_t) gd.n_disks);
+            hg.reflectance = gd.reflectance;
+            hg.transmittance = gd.transmittance;
+            S->leaf_groups.push_back(hg);
+        }
+        for (int i = 0; i < D->n_instances; ++i) {
+            if (D->instance_group[i] < 0 || D->instance_group[i] >= D->n_leaf_groups) {
+                delete S;
+                return set_error("instance refers to an unknown leaf group");
+            }
+            S->instance_group.push_back(D->instance_group[i]);
+            for (int k = 0; k < 3; ++k) S->instance_offset.push_back(D->instance_offset[3 * i + k]);
+        }
+        S->needs_3d = true;
+    }
+    for (int i = 0; i < D->n_sensors; ++i)
+        if (D->sensors[i].type == ERTB_SENSOR_PERSPECTIVE) {
+            if (D->geometry != ERTB_GEOM_PLANE_PARALLEL || S->polarized) {
+                delete S;
+                return set_error("perspective sensors are supported in unpolarized plane-parallel scenes only");
+            }
+            S->needs_3d = true;
+        }
+
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete S; return set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
     cudaDeviceGetAttribute(&S->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -564,6 +804,19 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
                 if (!(n > 0.0)) { ertb_scene_destroy(S); return set_error("mdistant: zero-length direction"); }
                 for (int c = 0; c < 3; ++c) hs.directions[3 * k + c] = v[c] / n;
             }
+        } else if (sd.type == ERTB_SENSOR_PERSPECTIVE) {
+            const double z = sd.to_world[11];
+            const bool inside = D->has_medium && z > D->surface_z && z < D->medium_top;
+            if (!(sd.x_fov_deg > 0.0 && sd.x_fov_deg < 180.0) || !(sd.near_clip > 0.0) || !(sd.far_clip > sd.near_clip)) {
+                ertb_scene_destroy(S);
+                return set_error("perspective: invalid field of view or clip planes");
+            }
+            if (z <= D->surface_z) { ertb_scene_destroy(S); return set_error("perspective: the camera is below the surface"); }
+            if (inside != (sd.in_medium != 0)) {
+                ertb_scene_destroy(S);
+                return set_error("perspective: the sensor's medium does not match its position "
+                                 "(experiments/_canopy_atmosphere.py:248-258 sets it for cameras inside the atmosphere)");
+            }
         } else if (sd.type != ERTB_SENSOR_HDISTANT && sd.type != ERTB_SENSOR_DISTANTFLUX) {
             ertb_scene_destroy(S);
             return set_error("unsupported sensor type");
@@ -572,6 +825,7 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
         S->sensors.push_back(hs);
         if (build_sensor(S, S->sensors.back())) { ertb_scene_destroy(S); return 1; }
     }
+    if (build_canopy(S)) { ertb_scene_destroy(S); return 1; }
     if (scene_commit(S, S->main)) { ertb_scene_destroy(S); return 1; }
     *out = S;
     return 0;
@@ -616,6 +870,12 @@ int ertb_scene_update(ertb_scene *S, int param, int index, const float *data, si
             S->phase[leaf].mueller[k].assign(data, data + count);
             break;
         }
+        case ERTB_PARAM_LEAF_BSDF:
+            if (index < 0 || index >= (int) S->leaf_groups.size()) return set_error("invalid leaf group index");
+            if (need(2)) return 1;
+            S->leaf_groups[index].reflectance = data[0];
+            S->leaf_groups[index].transmittance = data[1];
+            break;
         case ERTB_PARAM_BSDF_PARAMS:
             if (need(ERTB_MAX_BSDF_PARAMS)) return 1;
             memcpy(S->bsdf_params, data, sizeof S->bsdf_params);
@@ -667,10 +927,12 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     bool use_pool = true;
     if (const char *e = getenv("ERTB_KERNEL")) use_pool = strcmp(e, "legacy") != 0;
     int blocks_per_sm = 0;
-    const int block = use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK;
     const bool pol = S->polarized != 0;
     const bool pw = S->base.piecewise != 0;
+    const bool c3d = S->needs_3d; // canopy / perspective camera: the 3D kernel (ertb_canopy.cuh)
     if (pol || pw) use_pool = true; // the polarized and the piecewise paths exist in the pool kernel only
+    if (c3d) use_pool = false;
+    const int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK);
     size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol) : (size_t) S->base.blob_bytes;
     if (use_pool && smem > (size_t) S->max_smem_optin) { // huge tables: fall back to the register kernel
         if (pol || pw) return set_error("scene tables leave no shared memory for the path pools");
@@ -695,7 +957,10 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     } while (0)
 #define ERTB_DISPATCH(MACRO)                                                                          \
     do {                                                                                              \
-        if (pw && pol) ERTB_POOL_VARIANT(MACRO, false, true, true);                                   \
+        if (c3d) {                                                                                    \
+            if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true>)); else MACRO((ertb_canopy_kernel<false, true>)); } \
+            else    { if (with_stats) MACRO((ertb_canopy_kernel<true, false>)); else MACRO((ertb_canopy_kernel<false, false>)); } \
+        } else if (pw && pol) ERTB_POOL_VARIANT(MACRO, false, true, true);                            \
         else if (pw) ERTB_POOL_VARIANT(MACRO, false, false, true);                                    \
         else if (use_pool && pol) {                                                                   \
             if (sph) ERTB_POOL_VARIANT(MACRO, true, true, false);                                     \
@@ -1127,6 +1392,19 @@ __global__ void kat_sensor_ray_kernel(ErtbParams P, double ray_offset, size_t n,
     float fx = fs_[2 * i], fy = fs_[2 * i + 1], ax = as_[2 * i], ay = as_[2 * i + 1];
     f3 d, fs = mk3(1.f, 0.f, 0.f), ft = mk3(0.f, 1.f, 0.f);
     float w = 1.f;
+    if (S.type == ERTB_SENSOR_PERSPECTIVE) { // same arithmetic as canopy_primary()
+        f3 dc = normalize3(mk3((1.f - 2.f * fx) * S.tan_half_fov, (1.f - 2.f * fy) * S.tan_half_fov / S.aspect, 1.f));
+        const float *M = S.to_world;
+        d = normalize3(mk3(M[0] * dc.x + M[1] * dc.y + M[2] * dc.z, M[3] * dc.x + M[4] * dc.y + M[5] * dc.z,
+                           M[6] * dc.x + M[7] * dc.y + M[8] * dc.z));
+        float near_t = S.near_clip / dc.z;
+        origin[3 * i] = S.cam_origin[0] + (double) (near_t * d.x);
+        origin[3 * i + 1] = S.cam_origin[1] + (double) (near_t * d.y);
+        origin[3 * i + 2] = S.cam_origin[2] + (double) (near_t * d.z);
+        dir[3 * i] = d.x; dir[3 * i + 1] = d.y; dir[3 * i + 2] = d.z;
+        weight[i] = 1.f;
+        return;
+    }
     if (S.type == ERTB_SENSOR_MDISTANT) {
         int idx = min((int) (fx * (float) S.width), S.width - 1);
         const float *t = S.table + 8 * (size_t) idx;
@@ -1186,3 +1464,82 @@ int ertb_kat_sensor_ray(ertb_scene *S, int sensor, size_t n, const float *film_s
     return 0;
 }
 
+
+// ----------------------------------------------------------------------------
+// canopy KATs: the BVH ray caster and the leaf BSDF of the 3D kernel, point-wise
+// ----------------------------------------------------------------------------
+__global__ void kat_canopy_intersect_kernel(ErtbParams P, size_t n, const double *o, const float *dir, const float *tmax,
+                                            double *t, float *normal, int *group) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[3] = { o[3 * i], o[3 * i + 1], o[3 * i + 2] };
+    f3 d = normalize3(mk3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]));
+    CanopyHit H;
+    double th = canopy_nearest(P.canopy, p, d, (double) tmax[i], -1, -1, H);
+    t[i] = th;
+    group[i] = -1;
+    normal[3 * i] = normal[3 * i + 1] = normal[3 * i + 2] = 0.f;
+    if (H.inst >= 0) {
+        float4 in = __ldg(P.canopy.inst + H.inst), nn = __ldg(P.canopy.disks + 2 * H.disk + 1);
+        group[i] = __float_as_int(in.w);
+        normal[3 * i] = nn.x; normal[3 * i + 1] = nn.y; normal[3 * i + 2] = nn.z;
+    }
+}
+
+int ertb_kat_canopy_intersect(ertb_scene *S, size_t n, const double *origin, const float *dir, const float *tmax,
+                              double *t, float *normal, int *group) {
+    if (kat_prepare(S)) return 1;
+    if (S->canopy.n_instances == 0) return set_error("scene has no canopy");
+    DevBuf<double> o, tt;
+    DevBuf<float> d, tm, nn;
+    DevBuf<int> g;
+    if (o.alloc(3 * n) || tt.alloc(n) || d.alloc(3 * n) || tm.alloc(n) || nn.alloc(3 * n) || g.alloc(n))
+        return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(o.p, origin, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.p, dir, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(tm.p, tmax, n * sizeof(float), cudaMemcpyHostToDevice));
+    kat_canopy_intersect_kernel<<<KAT_GRID(n)>>>(S->base, n, o.p, d.p, tm.p, tt.p, nn.p, g.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(t, tt.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(normal, nn.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(group, g.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+__global__ void kat_leaf_bsdf_kernel(float r, float tr, size_t n, const float *ci, const float *co, const float *u,
+                                     float *out, float *wo) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (co) { out[i] = bilambertian_eval(r, tr, ci[i], co[i]); return; }
+    f3 w;
+    out[i] = bilambertian_sample(r, tr, ci[i], u[3 * i], u[3 * i + 1], u[3 * i + 2], w);
+    wo[3 * i] = w.x; wo[3 * i + 1] = w.y; wo[3 * i + 2] = w.z;
+}
+
+static int kat_leaf_bsdf(ertb_scene *S, int group, size_t n, const float *ci, const float *co, const float *u,
+                         float *out, float *wo) {
+    if (kat_prepare(S)) return 1;
+    if (group < 0 || group >= (int) S->leaf_groups.size()) return set_error("invalid leaf group index");
+    DevBuf<float> a, b, c, o, w;
+    if (a.alloc(n) || b.alloc(n) || c.alloc(3 * n) || o.alloc(n) || w.alloc(3 * n)) return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(a.p, ci, n * sizeof(float), cudaMemcpyHostToDevice));
+    if (co) CUDA_TRY(cudaMemcpy(b.p, co, n * sizeof(float), cudaMemcpyHostToDevice));
+    if (u) CUDA_TRY(cudaMemcpy(c.p, u, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+    const HostLeafGroup &g = S->leaf_groups[group];
+    kat_leaf_bsdf_kernel<<<KAT_GRID(n)>>>(g.reflectance, g.transmittance, n, a.p, co ? b.p : nullptr, c.p, o.p, w.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, o.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (wo) CUDA_TRY(cudaMemcpy(wo, w.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ertb_kat_leaf_bsdf_eval(ertb_scene *S, int group, size_t n, const float *cos_i, const float *cos_o, float *out) {
+    if (!cos_i || !cos_o || !out) return set_error("null argument");
+    return kat_leaf_bsdf(S, group, n, cos_i, cos_o, nullptr, out, nullptr);
+}
+
+int ertb_kat_leaf_bsdf_sample(ertb_scene *S, int group, size_t n, const float *cos_i, const float *u, float *wo,
+                              float *weight) {
+    if (!cos_i || !u || !wo || !weight) return set_error("null argument");
+    return kat_leaf_bsdf(S, group, n, cos_i, nullptr, u, weight, wo);
+}

@@ -49,6 +49,31 @@ struct ErtbSensor {
     double bs_radius;
     double ray_offset; // origin = target - d * ray_offset (mdistant.cpp:180-190)
     float flux_norm;   // distantflux: 2*pi / n_pixels
+    // perspective (perspective.cpp:200-236): pinhole at cam_origin, to_world = camera rotation
+    double cam_origin[3];
+    float tan_half_fov, aspect, near_clip, far_clip;
+    int in_medium;     // the camera sits inside the atmosphere
+};
+
+// Explicit canopy (ertb_canopy.cuh): two-level BVH over translated instances of disk-leaf groups.
+// Coordinates are float32 relative to `origin` (the centre of the canopy's bounding box), so leaf
+// geometry keeps sub-millimetre resolution whatever the extent of the atmosphere around it.
+struct ErtbBvhNode { // 64 B: the boxes of BOTH children, so one fetch decides where to go next
+    float lo0[3]; int c0; // child 0: n0 == 0 -> inner node index c0; n0 > 0 -> leaf of n0 primitives from c0
+    float hi0[3]; int n0;
+    float lo1[3]; int c1; // child 1 (an unreachable point box when the tree is a single leaf)
+    float hi1[3]; int n1;
+};
+struct ErtbCanopy {
+    int n_instances;          // 0: the scene has no canopy
+    const ErtbBvhNode *tlas;  // over the instances (leaf primitives index `inst`)
+    const float4 *inst;       // (offset xyz relative to `origin`, group index as int bits)
+    const ErtbBvhNode *blas;  // all groups' trees, concatenated
+    const int *blas_root;     // per group: root node index in `blas`
+    const float4 *disks;      // 2 per disk, in BVH leaf order: (centre xyz, radius) (normal xyz, -)
+    int off_leaf_bsdf;        // table blob: per group bilambertian (reflectance, transmittance)
+    double origin[3];
+    double lo[3], hi[3];      // world-space bounding box of all instances
 };
 
 struct ErtbParams {
@@ -104,6 +129,7 @@ struct ErtbParams {
     unsigned long long *work_counter; // device, zeroed before launch
     double *accum;                    // [3][n_pixels]: sum w*L | sum L | sum L^2
     unsigned long long *stats;        // [8] or nullptr
+    ErtbCanopy canopy;
 };
 
 // ----------------------------------------------------------------------------

@@ -107,3 +107,35 @@ def piecewise_transmittance(scene, altitude, mu):
     tr = np.zeros(z.size, dtype=np.float32)
     _lib.check(dev.lib.ertb_kat_piecewise_transmittance(dev.handle, z.size, _fp(z), _fp(mu), _fp(tr)))
     return tr
+
+
+def canopy_intersect(scene, origin, direction, tmax=None):
+    """Nearest leaf along world-space rays: (t, normal, group); t = inf for a miss."""
+    dev = _device_scene(scene)
+    o = np.ascontiguousarray(origin, dtype=np.float64).reshape(-1, 3)
+    d = _f(direction).reshape(-1, 3)
+    n = o.shape[0]
+    tm = np.full(n, 1e30, np.float32) if tmax is None else _f(tmax).reshape(-1)
+    t = np.zeros(n, np.float64)
+    nrm = np.zeros((n, 3), np.float32)
+    grp = np.zeros(n, np.int32)
+    _lib.check(dev.lib.ertb_kat_canopy_intersect(dev.handle, n, _dp(o), _fp(d), _fp(tm), _dp(t), _fp(nrm),
+                                                 grp.ctypes.data_as(C.POINTER(C.c_int32))))
+    return t, nrm, grp
+
+
+def leaf_bsdf_eval(scene, group, cos_i, cos_o):
+    dev = _device_scene(scene)
+    ci, co = _f(cos_i).reshape(-1), _f(cos_o).reshape(-1)
+    out = np.zeros(ci.size, np.float32)
+    _lib.check(dev.lib.ertb_kat_leaf_bsdf_eval(dev.handle, group, ci.size, _fp(ci), _fp(co), _fp(out)))
+    return out
+
+
+def leaf_bsdf_sample(scene, group, cos_i, u):
+    dev = _device_scene(scene)
+    ci, u = _f(cos_i).reshape(-1), _f(u).reshape(-1, 3)
+    wo = np.zeros((ci.size, 3), np.float32)
+    w = np.zeros(ci.size, np.float32)
+    _lib.check(dev.lib.ertb_kat_leaf_bsdf_sample(dev.handle, group, ci.size, _fp(ci), _fp(u), _fp(wo), _fp(w)))
+    return wo, w

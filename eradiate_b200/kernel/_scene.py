@@ -224,21 +224,23 @@ class Scene(Object):
 # ------------------------------------------------------------------------------
 
 _SUPPORTED = {
-    "integrator": {"volpath", "volpathmis", "piecewise_volpath", "moment", "stokes"},
+    "integrator": {"volpath", "volpathmis", "piecewise_volpath", "path", "moment", "stokes"},
     "emitter": {"directional"},
-    "shape": {"sphere", "cube", "rectangle", "arectangle"},
+    "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance"},
     "medium": {"heterogeneous", "homogeneous", "piecewise"},
-    "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "null"},
+    "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "null", "bilambertian"},
     "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
               "rayleigh_polarized", "tabphase_polarized"},
-    "sensor": {"mdistant", "hdistant", "distantflux"},
+    "sensor": {"mdistant", "hdistant", "distantflux", "perspective"},
     "volume": {"gridvolume", "sphericalcoordsvolume", "constvolume"},
 }
 _KIND_OF = {ty: kind for kind, types in _SUPPORTED.items() for ty in types}
 # plugins the reference ships for this slot but that this kernel does not (yet) implement
 _KNOWN_UNSUPPORTED = {
-    "path": "surface-only integrators are out of scope",
-    "perspective": "perspective sensors (canopy scenes) are a 'next' row (SURVEY 8f-3)",
+    "cylinder": "canopy elements other than disk leaves (tree trunks) are not implemented",
+    "blendbsdf": "CentralPatchSurface (bitmap-blended ground BSDFs) is not implemented",
+    "ply": "mesh canopy elements are not implemented",
+    "obj": "mesh canopy elements are not implemented",
 }
 
 
@@ -409,6 +411,9 @@ class _Loader:
                 if name not in d:
                     raise RuntimeError(f"hapke: missing required parameter '{name}'")
                 b.children[name] = tex(name, 0.0)
+        elif ty == "bilambertian":  # ERP/bsdfs/bilambertian.cpp:44-49
+            b.children["reflectance"] = tex("reflectance", 0.5)
+            b.children["transmittance"] = tex("transmittance", 0.5)
         elif ty == "ocean_legacy":
             b.values["wavelength"] = float(d.get("wavelength", 550.0))
             b.values["wind_speed"] = float(d.get("wind_speed", 0.1))
@@ -451,10 +456,75 @@ class _Loader:
         e.children["irradiance"] = self.make_texture(d.get("irradiance", 1.0), "irradiance")
         return e
 
+    @staticmethod
+    def _disk_row(m: np.ndarray) -> list[float]:
+        """(centre, unit normal, radius) of a `disk` with to_world `m` (MI/src/shapes/disk.cpp:96-122)."""
+        a = m[:3, :3]
+        du, dv = np.linalg.norm(a[:, 0]), np.linalg.norm(a[:, 1])
+        if abs(du - dv) > 1e-6 * max(du, dv) or abs(a[:, 0] @ a[:, 1]) > 1e-6 * du * dv:
+            raise RuntimeError("disk: only uniformly scaled (circular) disks are supported")
+        n = np.cross(a[:, 0], a[:, 1])
+        n /= np.linalg.norm(n)
+        return [m[0, 3], m[1, 3], m[2, 3], n[0], n[1], n[2], 0.5 * (du + dv)]
+
+    def _child_bsdf(self, d):
+        bsdf = d.get("bsdf")
+        if bsdf is None:
+            cands = [v for v in d.values() if isinstance(v, dict)
+                     and (_KIND_OF.get(v.get("type")) == "bsdf" or
+                          (v.get("type") == "ref" and v.get("id") in self.dict_by_id and
+                           _KIND_OF.get(self.dict_by_id[v["id"]].get("type")) == "bsdf"))]
+            bsdf = cands[0] if cands else {"type": "diffuse"}
+        return self.resolve(bsdf)
+
     def make_shape(self, d, oid) -> Shape:
         ty = d["type"]
         s = Shape(ty, oid)
+        if ty == "shapegroup":
+            # src/eradiate/scenes/biosphere/_core.py:266-275: a group of `disk` leaves. The disks are
+            # kept as one [n, 7] array, not as one node each (a RAMI canopy has > 10^5 of them).
+            rows, bsdf = [], None
+            for key, v in d.items():
+                if not isinstance(v, dict) or "type" not in v:
+                    continue
+                if v["type"] in _KNOWN_UNSUPPORTED:
+                    raise RuntimeError(f"unsupported plugin '{v['type']}': {_KNOWN_UNSUPPORTED[v['type']]}")
+                if v["type"] != "disk":
+                    raise RuntimeError(f"shapegroup: unsupported child shape '{v['type']}' (only 'disk')")
+                b = self._child_bsdf(v)
+                if bsdf is not None and b is not bsdf:
+                    raise RuntimeError("shapegroup: all leaves of a group must share one BSDF")
+                bsdf = b
+                rows.append(self._disk_row(to_matrix(v.get("to_world"))))
+            if not rows:
+                raise RuntimeError("shapegroup: no child shapes")
+            if bsdf.type != "bilambertian":
+                raise RuntimeError(f"canopy leaves must carry a bilambertian BSDF, got '{bsdf.type}'")
+            s.disks = np.asarray(rows, dtype=np.float64)
+            s.children["bsdf"] = bsdf
+            return s
+        if ty == "instance":
+            # _core.py:277-296: `group` reference + translation
+            g = d.get("group") or next((v for v in d.values() if isinstance(v, dict) and v.get("type") in ("ref", "shapegroup")), None)
+            if g is None:
+                raise RuntimeError("instance: missing 'group' reference")
+            grp = self.resolve(g)
+            if grp.type != "shapegroup":
+                raise RuntimeError("instance: 'group' must reference a shapegroup")
+            m = to_matrix(d.get("to_world"))
+            if not np.allclose(m[:3, :3], np.eye(3), atol=1e-12):
+                raise RuntimeError("instance: only translations are supported as to_world")
+            s.group = grp
+            s.offset = m[:3, 3].astype(np.float64).copy()
+            return s
         s.to_world = to_matrix(d.get("to_world"))
+        if ty == "disk":  # a free-standing leaf: a group of one, instanced once at the origin
+            bsdf = self._child_bsdf(d)
+            if bsdf.type != "bilambertian":
+                raise RuntimeError(f"canopy leaves must carry a bilambertian BSDF, got '{bsdf.type}'")
+            s.disks = np.asarray([self._disk_row(s.to_world)], dtype=np.float64)
+            s.children["bsdf"] = bsdf
+            return s
         if ty == "sphere":
             s.center = np.asarray(d.get("center", [0.0, 0.0, 0.0]), dtype=np.float64)
             s.radius = float(d.get("radius", 1.0))
@@ -498,10 +568,39 @@ class _Loader:
         sampler = Sampler("independent")
         sampler.sample_count = int(samp_d.get("sample_count", 4))
         s.children["sampler"] = sampler
+        s.in_medium = False
         if "medium" in d:
-            raise RuntimeError("sensors inside a medium are unsupported")
+            if ty != "perspective":
+                raise RuntimeError("distant sensors inside a medium are unsupported")
+            s.in_medium = True
         s.ray_offset = float(d.get("ray_offset", -1.0))
         s.to_world = to_matrix(d.get("to_world"))
+        if ty == "perspective":
+            # MI/src/sensors/perspective.cpp:130-175 + sensor.cpp parse_fov
+            if "focal_length" in d:
+                raise RuntimeError("perspective: specify 'fov' (focal_length is unsupported)")
+            fov = float(d.get("fov", 0.0))
+            if not (0.0 < fov < 180.0):
+                raise RuntimeError("The horizontal field of view must be in the range [0, 180]!")
+            axis = d.get("fov_axis", "x")
+            aspect = film.width / film.height
+            if axis == "smaller":
+                axis = "y" if aspect > 1 else "x"
+            elif axis == "larger":
+                axis = "x" if aspect > 1 else "y"
+            if axis == "y":
+                fov = np.degrees(2.0 * np.arctan(np.tan(0.5 * np.radians(fov)) * aspect))
+            elif axis == "diagonal":
+                diag = 2.0 * np.tan(0.5 * np.radians(fov))
+                fov = np.degrees(2.0 * np.arctan(0.5 * diag * aspect / np.sqrt(1.0 + aspect * aspect)))
+            elif axis != "x":
+                raise RuntimeError(f"perspective: invalid fov_axis '{axis}'")
+            s.x_fov = float(fov)
+            s.near_clip = float(d.get("near_clip", 1e-2))
+            s.far_clip = float(d.get("far_clip", 1e4))
+            a = s.to_world[:3, :3]
+            if not np.allclose(a.T @ a, np.eye(3), atol=1e-6):
+                raise RuntimeError("Scale factors in the camera-to-world transformation are not allowed!")
         if ty == "mdistant":
             if "to_world" in d:
                 raise RuntimeError(
@@ -563,7 +662,7 @@ class _Loader:
                 raise RuntimeError(
                     f"unsupported plugin '{inner['type']}': {_KNOWN_UNSUPPORTED[inner['type']]}"
                 )
-            if inner["type"] not in ("volpath", "volpathmis", "piecewise_volpath"):
+            if inner["type"] not in ("volpath", "volpathmis", "piecewise_volpath", "path"):
                 raise RuntimeError(f"unsupported nested integrator '{inner['type']}'")
         it.kernel_type = inner["type"]
         it.max_depth = int(inner.get("max_depth", -1))
@@ -630,6 +729,8 @@ class FlatScene:
         self.emitter = emitters[0]
         self.integrator = sc.integrator()
 
+        canopy = [s for s in shapes if s.type in ("shapegroup", "instance", "disk")]
+        shapes = [s for s in shapes if s.type not in ("shapegroup", "instance", "disk")]
         atm = [s for s in shapes if "interior_medium" in s.children]
         srf = [s for s in shapes if "interior_medium" not in s.children]
         if len(atm) > 1:
@@ -678,11 +779,39 @@ class FlatScene:
                     raise RuntimeError("plane-parallel atmosphere must use a cube stencil")
                 self.medium_top = float(hi[2])
             self._extract_medium()
+        # canopy: leaf groups + translated instances -----------------------------
+        self.leaf_groups: list[Shape] = []
+        self.instances: list[tuple[int, np.ndarray]] = []
+        for c in canopy:
+            grp = c.group if c.type == "instance" else c
+            if grp not in self.leaf_groups:
+                self.leaf_groups.append(grp)
+            if c.type != "shapegroup":  # a shapegroup alone is not rendered (MI/src/shapes/shapegroup.cpp)
+                off = c.offset if c.type == "instance" else np.zeros(3)
+                self.instances.append((self.leaf_groups.index(grp), off))
+        if self.instances:
+            if self.geometry != _abi.GEOM_PLANE_PARALLEL:
+                raise RuntimeError("explicit canopies are supported in plane-parallel scenes only "
+                                   "(src/eradiate/experiments/_canopy_atmosphere.py:74)")
+            for gi, off in self.instances:
+                dk = self.leaf_groups[gi].disks
+                ext = dk[:, 6:7] * np.sqrt(np.maximum(1.0 - dk[:, 3:6] ** 2, 0.0))
+                lo, hi = (dk[:, :3] - ext).min(axis=0) + off, (dk[:, :3] + ext).max(axis=0) + off
+                bbox_lo, bbox_hi = np.minimum(bbox_lo, lo), np.maximum(bbox_hi, hi)
+                if (dk[:, 2] + off[2]).min() < self.surface_z:
+                    raise RuntimeError("canopy leaf centres must lie above the ground surface")
+                if self.atm_shape is not None and hi[2] > self.medium_top:
+                    raise RuntimeError("canopy leaves must lie below the top of the atmosphere")
         self.bsphere_center = 0.5 * (bbox_lo + bbox_hi)
         self.bsphere_radius = float(0.5 * np.linalg.norm(bbox_hi - bbox_lo))
         self.sensors = sc.sensors()
         if not self.sensors:
             raise RuntimeError("scene has no sensor")
+        if self.integrator.kernel_type == "path" and self.medium is not None:
+            raise RuntimeError("the 'path' integrator ignores participating media; use volpath")
+        for sn in self.sensors:
+            if sn.type == "perspective" and self.geometry != _abi.GEOM_PLANE_PARALLEL:
+                raise RuntimeError("perspective sensors are supported in plane-parallel scenes only")
         # Polarized transport = the reference's *_polarized variants.  The variant is global state in
         # Mitsuba; here it is inferred from the scene: a `stokes` integrator or a polarized phase plugin.
         self.polarized = bool(getattr(self.integrator, "stokes", False))
@@ -820,6 +949,11 @@ class FlatScene:
             p[6] = float(b.component)
         return p
 
+    def leaf_bsdf_params(self, group: int) -> tuple[float, float]:
+        b = self.leaf_groups[group].children["bsdf"]
+        return (float(b.children["reflectance"].values["value"]),
+                float(b.children["transmittance"].values["value"]))
+
     def bsdf_type(self) -> int:
         return {
             "diffuse": _abi.BSDF_DIFFUSE,
@@ -831,7 +965,8 @@ class FlatScene:
 
     # -- ctypes descriptor -----------------------------------------------------------------
     def build_desc(self) -> _abi.SceneDesc:
-        """Build the POD descriptor.  Buffers stay alive as long as ``self``."""
+        """Build the POD descriptor. The numpy buffers it points to are owned by the returned object
+        (an earlier descriptor stays valid when ``build_desc`` is called again)."""
         keep: list = []
         d = _abi.SceneDesc()
         d.abi_version = _abi.ABI_VERSION
@@ -906,7 +1041,11 @@ class FlatScene:
                 "mdistant": _abi.SENSOR_MDISTANT,
                 "hdistant": _abi.SENSOR_HDISTANT,
                 "distantflux": _abi.SENSOR_DISTANTFLUX,
+                "perspective": _abi.SENSOR_PERSPECTIVE,
             }[s.type]
+            if s.type == "perspective":
+                sd.x_fov_deg, sd.near_clip, sd.far_clip = s.x_fov, s.near_clip, s.far_clip
+                sd.in_medium = int(s.in_medium)
             sd.width, sd.height = s.film().width, s.film().height
             if s.type == "mdistant":
                 dirs = np.ascontiguousarray(s.directions, dtype=np.float64)
@@ -921,6 +1060,22 @@ class FlatScene:
         keep.append(sens)
         d.n_sensors = len(self.sensors)
         d.sensors = C.cast(sens, C.POINTER(_abi.SensorDesc))
+        if self.instances:
+            groups = (_abi.LeafGroupDesc * len(self.leaf_groups))()
+            for i, g in enumerate(self.leaf_groups):
+                disks = np.ascontiguousarray(g.disks, dtype=np.float32)
+                keep.append(disks)
+                groups[i].n_disks = disks.shape[0]
+                groups[i].disks = disks.ctypes.data_as(_abi.c_float_p)
+                groups[i].reflectance, groups[i].transmittance = self.leaf_bsdf_params(i)
+            inst_g = np.ascontiguousarray([gi for gi, _ in self.instances], dtype=np.int32)
+            inst_o = np.ascontiguousarray([off for _, off in self.instances], dtype=np.float64)
+            keep += [groups, inst_g, inst_o]
+            d.n_leaf_groups, d.n_instances = len(self.leaf_groups), len(self.instances)
+            d.leaf_groups = C.cast(groups, C.POINTER(_abi.LeafGroupDesc))
+            d.instance_group = inst_g.ctypes.data_as(C.POINTER(C.c_int32))
+            d.instance_offset = inst_o.ctypes.data_as(_abi.c_double_p)
+        d._keepalive = keep  # the buffers live as long as the descriptor that points to them
         self._keepalive = keep
         return d
 

@@ -116,8 +116,11 @@ def atmosphere_scene(
     stokes: bool = False,
     meridian_align: bool = True,
     force_majorant: bool | None = None,
+    canopy: dict | None = None,
+    extra_sensors: list | None = None,
 ) -> dict:
-    """Build the nested scene dict an ``AtmosphereExperiment`` would emit.
+    """Build the nested scene dict an ``AtmosphereExperiment`` would emit (with ``canopy``: a
+    ``CanopyAtmosphereExperiment``, see :func:`disc_canopy`).
 
     ``force_majorant`` mirrors ``scenes/atmosphere/_core.py:354,650``: a plane-parallel
     atmosphere is emitted as a ``piecewise`` medium unless it is set (default: set for every
@@ -255,10 +258,95 @@ def atmosphere_scene(
                 "interior": {"type": "ref", "id": "medium_atmosphere"},
             }
 
+    if canopy is not None:
+        if spherical:
+            raise ValueError("canopies need the plane-parallel geometry")
+        scene.update(disc_canopy(**canopy))
+        # experiments/_canopy_atmosphere.py:200-210: distant measures target the top of the unit cell
+        lx, ly, lz = canopy.get("size", (10.0, 10.0, 2.0))
+        target = {
+            "type": "rectangle",
+            "to_world": ScalarTransform4f().translate([0.0, 0.0, lz]).scale([0.5 * lx, 0.5 * ly, 1.0]),
+        }
     if sensor is None:
         sensor = {"type": "mdistant", "vza": np.linspace(-75.0, 75.0, 32), "vaa": 0.0}
     scene["measure"] = _sensor_dict(dict(sensor), target, spp)
+    for k, extra in enumerate(extra_sensors or []):
+        extra = dict(extra)
+        extra.setdefault("id", f"measure_{k + 2}")
+        if extra.get("type") == "perspective" and extra.pop("inside_atmosphere", False) and atmosphere is not None:
+            extra["medium"] = {"type": "ref", "id": "medium_atmosphere"}
+        sid = extra["id"]
+        scene[sid] = _sensor_dict(extra, target, spp)
     return scene
+
+
+def leaf_normals(n: int, orientation, rng) -> np.ndarray:
+    """Leaf normals: 'uniform' (spherical leaf angle distribution), 'planophile' (all +z) or a vector."""
+    if isinstance(orientation, str) and orientation == "uniform":
+        mu = rng.uniform(-1.0, 1.0, n)
+        phi = rng.uniform(0.0, 2.0 * np.pi, n)
+        st = np.sqrt(1.0 - mu * mu)
+        return np.stack([st * np.cos(phi), st * np.sin(phi), mu], axis=1)
+    if isinstance(orientation, str) and orientation == "planophile":
+        return np.tile([0.0, 0.0, 1.0], (n, 1))
+    v = np.asarray(orientation, dtype=np.float64)
+    return np.tile(v / np.linalg.norm(v), (n, 1))
+
+
+def disc_canopy(
+    lai: float = 3.0,
+    radius: float = 0.1,
+    size=(10.0, 10.0, 2.0),
+    padding: int = 0,
+    orientation="uniform",
+    reflectance: float = 0.5,
+    transmittance: float = 0.4,
+    seed: int = 1,
+    n_leaves: int | None = None,
+    z_bottom: float = 0.0,
+) -> dict:
+    """
+    Homogeneous disc canopy (RAMI "HOM" scenes) exactly as ``DiscreteCanopy.homogeneous`` +
+    ``InstancedCanopyElement`` emit it (``scenes/biosphere/_leaf_cloud.py:1150-1175``,
+    ``_core.py:266-296``, ``_discrete.py:139-200``): one ``bilambertian`` BSDF, a ``shapegroup`` of
+    ``disk`` leaves (to_world = look_at x scale), and (2*padding+1)^2 translated ``instance``s.
+    The leaf count follows the leaf area index: n = LAI * lx * ly / (pi r^2).
+    """
+    lx, ly, lz = (float(v) for v in size)
+    if n_leaves is None:
+        n_leaves = max(1, int(round(lai * lx * ly / (np.pi * radius * radius))))
+    rng = np.random.default_rng(seed)
+    pos = np.stack([rng.uniform(-0.5 * lx, 0.5 * lx, n_leaves), rng.uniform(-0.5 * ly, 0.5 * ly, n_leaves),
+                    z_bottom + rng.uniform(0.0, lz, n_leaves)], axis=1)
+    nrm = leaf_normals(n_leaves, orientation, rng)
+    out: dict = {
+        "bsdf_leaf_cloud": {
+            "type": "bilambertian",
+            "reflectance": {"type": "uniform", "value": float(reflectance)},
+            "transmittance": {"type": "uniform", "value": float(transmittance)},
+        }
+    }
+    group: dict = {"type": "shapegroup"}
+    for i in range(n_leaves):
+        n = nrm[i]
+        up = np.array([1.0, 0.0, 0.0]) if abs(n[2]) > 0.9 else np.array([0.0, 0.0, 1.0])
+        group[f"leaf_cloud_leaf_{i}"] = {
+            "type": "disk",
+            "bsdf": {"type": "ref", "id": "bsdf_leaf_cloud"},
+            "to_world": ScalarTransform4f().look_at(origin=pos[i], target=pos[i] + n, up=up).scale(radius),
+        }
+    out["leaf_cloud"] = group
+    k = 0
+    for ix in range(-padding, padding + 1):
+        for iy in range(-padding, padding + 1):
+            out[f"leaf_cloud_instance_{k}"] = {
+                "type": "instance",
+                "group": {"type": "ref", "id": "leaf_cloud"},
+                "to_world": ScalarTransform4f().translate([ix * lx, iy * ly, 0.0]),
+            }
+            k += 1
+    return out
 
 
 def _spectrumify(bsdf: dict) -> dict:
@@ -308,13 +396,24 @@ def _sensor_dict(sensor: dict, target, spp: int) -> dict:
         view = angles_to_direction(np.abs(vza), az)
         out["directions"] = ",".join(map(str, (-view).ravel(order="C")))
         width, height = vza.size, 1
+    elif ty == "perspective":  # scenes/measure/_perspective.py:150-165
+        res = sensor.pop("film_resolution", (32, 32))
+        width, height = int(res[0]), int(res[1])
+        out["fov"] = float(sensor.pop("fov", 50.0))
+        out["far_clip"] = float(sensor.pop("far_clip", 1e4))
+        out["to_world"] = ScalarTransform4f().look_at(
+            origin=sensor.pop("origin"), target=sensor.pop("look_at", [0.0, 0.0, 0.0]),
+            up=sensor.pop("up", [0.0, 0.0, 1.0]))
+        if "medium" in sensor:
+            out["medium"] = sensor.pop("medium")
+        target = None
     else:
         res = sensor.pop("film_resolution", (32, 32))
         width, height = int(res[0]), int(res[1])
         if "to_world" in sensor:
             out["to_world"] = sensor.pop("to_world")
     tgt = sensor.pop("target", target)
-    if tgt is not None:
+    if tgt is not None and ty != "perspective":
         out["target"] = tgt
     if "ray_offset" in sensor:
         out["ray_offset"] = sensor.pop("ray_offset")
@@ -364,6 +463,22 @@ def config_c3(spp: int = 1 << 22, res: int = 32, w_nm: float = 865.0) -> dict:
         aerosol=True,
         w_nm=w_nm,
         sensor={"type": "hdistant", "film_resolution": (res, res)},
+        spp=spp,
+    )
+
+
+def config_c4(spp: int = 1 << 22, lai: float = 3.0, radius: float = 0.1, size=(25.0, 25.0, 2.0),
+              padding: int = 2, n_vza: int = 32, film=(64, 64), n_layers: int = 1200) -> dict:
+    """C4: RAMI-style homogeneous disc canopy under the AFGL1986-shaped atmosphere, RPV floor,
+    mono 670 nm, plane-parallel; mdistant (principal plane) + a perspective camera above the canopy."""
+    return atmosphere_scene(
+        geometry="plane_parallel", atmosphere="afgl", n_layers=n_layers, w_nm=670.0,
+        canopy={"lai": lai, "radius": radius, "size": size, "padding": padding,
+                "reflectance": 0.0546, "transmittance": 0.0149},  # RAMI HOM red-band leaf optics
+        sensor={"type": "mdistant", "vza": np.linspace(-75.0, 75.0, n_vza), "vaa": 0.0},
+        extra_sensors=[{"type": "perspective", "origin": [0.0, -1.5 * size[1], 0.75 * size[1]],
+                        "look_at": [0.0, 0.0, 0.5 * size[2]], "fov": 40.0, "film_resolution": film,
+                        "inside_atmosphere": True}],
         spp=spp,
     )
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 7
+#define ERTB_ABI_VERSION 8
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -71,7 +71,8 @@ enum ertb_phase_type {
 enum ertb_sensor_type {
     ERTB_SENSOR_MDISTANT = 0,   /* ERP/sensors/mdistant.cpp:192-242 */
     ERTB_SENSOR_HDISTANT = 1,   /* ERP/sensors/hdistant.cpp:232-275 */
-    ERTB_SENSOR_DISTANTFLUX = 2 /* ERP/sensors/distantflux.cpp:148-195 */
+    ERTB_SENSOR_DISTANTFLUX = 2, /* ERP/sensors/distantflux.cpp:148-195 */
+    ERTB_SENSOR_PERSPECTIVE = 3  /* MI/src/sensors/perspective.cpp:200-236 (pinhole; canopy scenes) */
 };
 
 enum ertb_target_type {
@@ -112,7 +113,30 @@ typedef struct ertb_sensor_desc {
     double target[3];      /* point target */
     double target_to_world[16]; /* rectangle/disk target: maps [-1,1]^2 x {0} (unit disk) to world */
     double ray_offset;     /* < 0: derive from the scene bounding sphere (mdistant.cpp:180-190) */
+    /* perspective (to_world = camera-to-world; film width x height): horizontal/vertical field of
+     * view resolved to the X axis by the host (perspective.cpp parse_fov), clip planes
+     * (near_clip 1e-2, far_clip 1e4 by default), and whether the camera sits inside the
+     * atmosphere (the `medium` reference Eradiate adds, experiments/_canopy_atmosphere.py:248-258) */
+    double x_fov_deg;
+    double near_clip, far_clip;
+    int32_t in_medium;
+    int32_t _pad1;
 } ertb_sensor_desc;
+
+/* Explicit 3D canopies (src/eradiate/scenes/biosphere/_leaf_cloud.py:1150-1175,
+ * _core.py:266-296): `shapegroup`s of `disk` leaves sharing one `bilambertian` BSDF
+ * (ERP/bsdfs/bilambertian.cpp:60-215), placed in the scene by `instance`s whose to_world is a
+ * pure translation.  Plane-parallel scenes only; the leaves sit inside the atmosphere and do
+ * not change the medium of a path (no medium interface).
+ * disks: n_disks x 7 floats = centre xyz, unit normal xyz, radius (MI/src/shapes/disk.cpp:
+ * to_world = look_at x uniform scale). */
+typedef struct ertb_leaf_group_desc {
+    int32_t n_disks;
+    float reflectance;     /* bilambertian `reflectance` (uniform) */
+    float transmittance;   /* bilambertian `transmittance` (uniform) */
+    int32_t _pad;
+    const float *disks;
+} ertb_leaf_group_desc;
 
 typedef struct ertb_scene_desc {
     int32_t abi_version;   /* must be ERTB_ABI_VERSION */
@@ -170,6 +194,13 @@ typedef struct ertb_scene_desc {
     int32_t n_sensors;
     int32_t _pad4;
     const ertb_sensor_desc *sensors;
+
+    /* Canopy (all zero / NULL for 1D scenes) */
+    int32_t n_leaf_groups;
+    int32_t n_instances;
+    const ertb_leaf_group_desc *leaf_groups;
+    const int32_t *instance_group;  /* n_instances: index into leaf_groups */
+    const double *instance_offset;  /* n_instances x 3: translation of the instance */
 } ertb_scene_desc;
 
 /* Named updatable parameters (KernelSceneParameterMap keys resolve to these;
@@ -183,7 +214,8 @@ enum ertb_param {
     ERTB_PARAM_BSDF_PARAMS = 4,  /* float[ERTB_MAX_BSDF_PARAMS] */
     ERTB_PARAM_IRRADIANCE = 5,   /* float[1] */
     ERTB_PARAM_PHASE_PARAMS = 6, /* index = leaf; float[4] */
-    ERTB_PARAM_PHASE_MUELLER = 7 /* index = leaf * 5 + k (k: m12, m22, m33, m34, m44); float[n_nodes] */
+    ERTB_PARAM_PHASE_MUELLER = 7, /* index = leaf * 5 + k (k: m12, m22, m33, m34, m44); float[n_nodes] */
+    ERTB_PARAM_LEAF_BSDF = 8     /* index = leaf group; float[2]: reflectance, transmittance */
 };
 
 typedef struct ertb_render_stats {
@@ -292,6 +324,18 @@ int ertb_kat_phase_mueller(ertb_scene *scene, int leaf, size_t n, const float *w
                            float *mueller, float *pdf);
 int ertb_kat_sensor_ray(ertb_scene *scene, int sensor, size_t n, const float *film_sample,
                         const float *aperture_sample, double *origin, double *dir, float *weight);
+
+/* Canopy KATs (3D kernel): the BVH ray caster and the leaf BSDF, point-wise. Host pointers.
+ *   canopy_intersect: world-space origins (3*n doubles), directions (3*n floats, normalised on the
+ *                     device), tmax (n) -> distance t (inf = miss), leaf normal (3*n), leaf group (n; -1)
+ *   leaf_bsdf_eval  : bilambertian of `group`: cos of wi / wo with the leaf normal -> f * |cos_o|
+ *   leaf_bsdf_sample: cos_i (n), u (3*n: lobe selection, then the 2D sample) -> local wo (3*n), weight */
+int ertb_kat_canopy_intersect(ertb_scene *scene, size_t n, const double *origin, const float *dir,
+                              const float *tmax, double *t, float *normal, int *group);
+int ertb_kat_leaf_bsdf_eval(ertb_scene *scene, int group, size_t n, const float *cos_i,
+                            const float *cos_o, float *out);
+int ertb_kat_leaf_bsdf_sample(ertb_scene *scene, int group, size_t n, const float *cos_i,
+                              const float *u, float *wo, float *weight);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,7 @@
 #endif
 
 #include "ertb_oracle_ocean.h"
+#include "ertb_oracle_canopy.h"
 
 #define PI 3.14159265358979323846
 #define INV_PI (1.0 / PI)
@@ -291,6 +292,7 @@ typedef struct {
     ocean_state_t ocean;        /* ocean_legacy precomputed tables */
     double *pw_cum, *pw_rcum;   /* piecewise.cpp m_cum_opt_thickness / m_reverse_cum_opt_thickness */
     double pp_half_width;       /* > 0: finite slab bbox in x, y (known-answer tests only) */
+    canopy_t canopy;            /* explicit disk-leaf canopy (plane-parallel scenes) */
 } scene_t;
 
 static int piecewise_init(scene_t *S);
@@ -300,6 +302,7 @@ static void scene_free(scene_t *S) {
         if (S->has_distr[i]) distr_free(&S->distr[i]);
     ocean_free(&S->ocean);
     free(S->pw_cum); free(S->pw_rcum);
+    canopy_free(&S->canopy);
 }
 
 static int scene_init(scene_t *S, const ertb_scene_desc *d) {
@@ -334,13 +337,17 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
     S->emitter_d = vnormalize(V(d->emitter_direction[0], d->emitter_direction[1], d->emitter_direction[2]));
     if (d->bsdf_type == ERTB_BSDF_OCEAN_LEGACY)
         if (ocean_init(&S->ocean, d->bsdf_params)) return fail("ocean_legacy init failed");
+    if (d->n_instances > 0) {
+        if (S->spherical || d->polarized) return fail("canopies: plane-parallel, unpolarized scenes only");
+        if (canopy_init(&S->canopy, d)) return fail("canopy init failed");
+    }
     return 0;
 }
 
 /* ------------------------------------------------------------- geometry */
 typedef struct { v3 o, d; double maxt; } ray_t;
-enum { SHAPE_GROUND = 0, SHAPE_TOA = 1 };
-typedef struct { double t; v3 p, n; int shape; } si_t; /* t = INFINITY when invalid */
+enum { SHAPE_GROUND = 0, SHAPE_TOA = 1, SHAPE_LEAF = 2 };
+typedef struct { double t; v3 p, n; int shape; int group; } si_t; /* t = INFINITY when invalid */
 
 static inline v3 ray_at(const ray_t *r, double t) { return vfma(r->d, t, r->o); }
 
@@ -368,7 +375,7 @@ static double sphere_intersect(const ray_t *ray, double radius) {
  * `cube` top face; horizontal extent treated as unbounded: default width 1e6 km) */
 static si_t scene_intersect(const scene_t *S, const ray_t *ray) {
     const ertb_scene_desc *d = S->desc;
-    si_t best; best.t = INFINITY; best.shape = -1; best.p = best.n = V(0, 0, 0);
+    si_t best; best.t = INFINITY; best.shape = -1; best.group = -1; best.p = best.n = V(0, 0, 0);
     double tg = INFINITY, tt = INFINITY;
     if (S->spherical) {
         tg = sphere_intersect(ray, d->surface_z);
@@ -397,6 +404,15 @@ static si_t scene_intersect(const scene_t *S, const ray_t *ray) {
              * rays (t ~ 1e9 m) land ~1e-7 m off the plane, more than the spawn offset. */
             best.n = V(0, 0, 1);
             best.p.z = best.shape == SHAPE_GROUND ? d->surface_z : d->medium_top;
+        }
+    }
+    if (S->canopy.n_instances > 0) { /* leaves: disks in instanced shape groups */
+        double o[3] = { ray->o.x, ray->o.y, ray->o.z }, dd[3] = { ray->d.x, ray->d.y, ray->d.z };
+        canopy_hit_t h = canopy_intersect(&S->canopy, o, dd, fmin(ray->maxt, best.t));
+        if (h.t < best.t) {
+            best.t = h.t; best.shape = SHAPE_LEAF; best.group = h.group;
+            best.p = V(h.p[0], h.p[1], h.p[2]);
+            best.n = V(h.n[0], h.n[1], h.n[2]);
         }
     }
     return best;
@@ -1067,6 +1083,26 @@ static double bsdf_sample(const scene_t *S, v3 wi, double s1, double u1, double 
     }
 }
 
+/* BSDF of the shape that was hit: the ground model or a leaf group's bilambertian */
+static double surf_eval(const scene_t *S, const si_t *si, v3 wi, v3 wo) {
+    if (si->shape == SHAPE_LEAF) {
+        const canopy_group_t *G = &S->canopy.groups[si->group];
+        double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
+        return bilambertian_eval(G->reflectance, G->transmittance, a, b);
+    }
+    return bsdf_eval(S, wi, wo);
+}
+static double surf_sample(const scene_t *S, const si_t *si, v3 wi, double s1, double u1, double u2, v3 *wo) {
+    if (si->shape == SHAPE_LEAF) {
+        const canopy_group_t *G = &S->canopy.groups[si->group];
+        double a[3] = { wi.x, wi.y, wi.z }, o[3];
+        double w = bilambertian_sample(G->reflectance, G->transmittance, a, s1, u1, u2, o);
+        *wo = V(o[0], o[1], o[2]);
+        return w;
+    }
+    return bsdf_sample(S, wi, s1, u1, u2, wo);
+}
+
 /* -------------------------------------------------------------- sensors */
 static void mat_apply_vec(const double *m, v3 v, v3 *o) { /* row-major 4x4, direction */
     *o = V(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z,
@@ -1089,6 +1125,17 @@ static double sensor_sample_ray(const scene_t *S, const ertb_sensor_desc *sd, do
                                 double ax, double ay, ray_t *ray) {
     v3 d, frame_s = V(1, 0, 0), frame_t = V(0, 1, 0);
     double weight = 1.0;
+    if (sd->type == ERTB_SENSOR_PERSPECTIVE) {
+        /* perspective.cpp:200-236 with sample_to_camera = inverse of sensor.h:234-269 */
+        double tn = tan(0.5 * sd->x_fov_deg * PI / 180.0), aspect = (double) sd->width / (double) sd->height;
+        v3 dc = vnormalize(V((1.0 - 2.0 * fx) * tn, (1.0 - 2.0 * fy) * tn / aspect, 1.0));
+        mat_apply_vec(sd->to_world, dc, &d);
+        double inv_z = 1.0 / dc.z, near_t = sd->near_clip * inv_z, far_t = sd->far_clip * inv_z;
+        ray->o = vfma(d, near_t, V(sd->to_world[3], sd->to_world[7], sd->to_world[11]));
+        ray->d = d;
+        ray->maxt = far_t - near_t;
+        return 1.0;
+    }
     if (sd->type == ERTB_SENSOR_MDISTANT) { /* mdistant.cpp:192-242 */
         int idx = (int) (fx * sd->n_directions);
         if (idx > sd->n_directions - 1) idx = sd->n_directions - 1;
@@ -1289,15 +1336,15 @@ static double pw_medium_step(const scene_t *S, pcg32 *rng, const ray_t *ray, si_
 
 /* volpath.cpp:93-396 (mono, unpolarized).  mis != 0 selects the volpathmis.cpp
  * Russian-roulette placement (:227-231), the only difference left in mono. */
-static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t *C) {
+static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium0, counters_t *C) {
     const ertb_scene_desc *D = S->desc;
     const int mis = D->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
     const int pw = D->integrator == ERTB_INTEGRATOR_PIECEWISE_VOLPATH;
     const uint64_t max_depth = D->max_depth < 0 ? (uint64_t) 0xffffffffu : (uint64_t) D->max_depth;
     double throughput = 1.0, result = 0.0, eta = 1.0;
-    int medium = 0; /* sensors sit outside the atmosphere */
+    int medium = medium0; /* distant sensors sit outside the atmosphere; a camera may be inside */
     uint64_t depth = 0;
-    si_t si; si.t = INFINITY; si.shape = -1; si.p = si.n = V(0, 0, 0);
+    si_t si; si.t = INFINITY; si.shape = -1; si.group = -1; si.p = si.n = V(0, 0, 0);
     int needs_intersection = 1, last_event_was_null = 0;
 
     for (;;) {
@@ -1372,7 +1419,7 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t
         if (active_surface && needs_intersection) si = scene_intersect(S, &ray);
         active_surface = active_surface && si.t < INFINITY;
         if (active_surface) {
-            frame_t fr = surface_frame(S, &si);
+            frame_t fr = si.shape == SHAPE_LEAF ? make_frame(si.n) : surface_frame(S, &si);
             v3 wi = to_local(&fr, vneg(ray.d));
             v3 wo_world;
             if (si.shape == SHAPE_TOA) { /* null.cpp:41-87 */
@@ -1384,11 +1431,11 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, counters_t
                     v3 ds_d;
                     double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, si.p, si.n, medium, C, &ds_d);
                     v3 wo = to_local(&fr, ds_d);
-                    result += throughput * bsdf_eval(S, wi, wo) * emitted;
+                    result += throughput * surf_eval(S, &si, wi, wo) * emitted;
                 }
                 double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
                 v3 wo;
-                throughput *= bsdf_sample(S, wi, s1, u1, u2, &wo);
+                throughput *= surf_sample(S, &si, wi, s1, u1, u2, &wo);
                 wo_world = to_world(&fr, wo);
                 depth++;
             }
@@ -1633,7 +1680,7 @@ int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, 
                     L = st[0];
                     for (int k = 0; k < 4; ++k) s_st[k] += w * st[k];
                 } else {
-                    L = volpath_sample(&S, &rng, ray, &C);
+                    L = volpath_sample(&S, &rng, ray, sd->type == ERTB_SENSOR_PERSPECTIVE && sd->in_medium, &C);
                 }
                 s_wl += w * L; s_l += L; s_l2 += L * L;
             }
@@ -1783,5 +1830,36 @@ int ertbo_phase_mueller(const ertb_scene_desc *desc, int leaf, size_t n, const d
         memcpy(mueller + 16 * i, M.m, sizeof M.m);
     }
     scene_free(&S);
+    return 0;
+}
+
+/* ------------------------------------------------------------ canopy KATs */
+int ertbo_canopy_intersect(const ertb_scene_desc *desc, size_t n, const double *o, const double *d,
+                           const double *tmax, double *t, double *normal, int *group) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    if (S.canopy.n_instances == 0) { scene_free(&S); return fail("scene has no canopy"); }
+    for (size_t i = 0; i < n; ++i) {
+        v3 dd = vnormalize(V(d[3 * i], d[3 * i + 1], d[3 * i + 2]));
+        double dv[3] = { dd.x, dd.y, dd.z };
+        canopy_hit_t h = canopy_intersect(&S.canopy, o + 3 * i, dv, tmax ? tmax[i] : INFINITY);
+        t[i] = h.t;
+        group[i] = h.group;
+        for (int k = 0; k < 3; ++k) normal[3 * i + k] = h.t < INFINITY ? h.n[k] : 0.0;
+    }
+    scene_free(&S);
+    return 0;
+}
+
+/* mode 0: eval (wo given), 1: pdf, 2: sample (u = sample1, sample2) -> wo, out = weight */
+int ertbo_leaf_bsdf(const ertb_scene_desc *desc, int grp, int mode, size_t n, const double *wi, double *wo,
+                    const double *u, double *out) {
+    if (grp < 0 || grp >= desc->n_leaf_groups) return fail("invalid leaf group");
+    double r = desc->leaf_groups[grp].reflectance, t = desc->leaf_groups[grp].transmittance;
+    for (size_t i = 0; i < n; ++i) {
+        if (mode == 0) out[i] = bilambertian_eval(r, t, wi + 3 * i, wo + 3 * i);
+        else if (mode == 1) out[i] = bilambertian_pdf(r, t, wi + 3 * i, wo + 3 * i);
+        else out[i] = bilambertian_sample(r, t, wi + 3 * i, u[3 * i], u[3 * i + 1], u[3 * i + 2], wo + 3 * i);
+    }
     return 0;
 }

@@ -67,4 +67,11 @@ int ertbo_medium_lookup(const ertb_scene_desc *desc, size_t n, const double *p_x
 #ifdef __cplusplus
 }
 #endif
+/* canopy KATs (ertb_oracle_canopy.c): nearest leaf along world-space rays; bilambertian
+ * eval (mode 0) / pdf (1) / sample (2) of leaf group `group` in the leaf's local frame */
+int ertbo_canopy_intersect(const ertb_scene_desc *desc, size_t n, const double *o, const double *d,
+                           const double *tmax, double *t, double *normal, int *group);
+int ertbo_leaf_bsdf(const ertb_scene_desc *desc, int group, int mode, size_t n, const double *wi, double *wo,
+                    const double *u, double *out);
+
 #endif

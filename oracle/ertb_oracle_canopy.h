@@ -1,0 +1,52 @@
+/*
+ * ertb_oracle_canopy.h -- explicit 3D canopies for the CPU oracle (TEST INFRASTRUCTURE ONLY).
+ *
+ * Disk leaves in instanced shape groups (src/eradiate/scenes/biosphere/_leaf_cloud.py:1150-1175,
+ * _core.py:266-296), intersected as MI/src/shapes/disk.cpp:388-407 does, with the bilambertian
+ * leaf BSDF of ERP/bsdfs/bilambertian.cpp:60-215.  The acceleration structure is a uniform 3D
+ * grid walked with a DDA -- deliberately NOT the BVH of the CUDA library, so that the GPU/oracle
+ * parity tests cross-check two independent ray casters.
+ */
+#ifndef ERTB_ORACLE_CANOPY_H
+#define ERTB_ORACLE_CANOPY_H
+
+#include "../include/eradiate_b200.h"
+
+typedef struct {
+    int n_disks;
+    const float *disks;  /* n x 7 (borrowed from the descriptor) */
+    double lo[3], hi[3]; /* bounding box of the group (local coordinates) */
+    int res[3];
+    double cell[3];
+    int *cell_start;     /* res[0]*res[1]*res[2] + 1 */
+    int *cell_items;
+    double reflectance, transmittance;
+} canopy_group_t;
+
+typedef struct {
+    int n_groups, n_instances;
+    canopy_group_t *groups;
+    const int *instance_group;
+    const double *instance_offset;
+} canopy_t;
+
+typedef struct {
+    double t;        /* INFINITY: no hit */
+    double p[3];     /* hit point re-projected onto the disk (disk.cpp:482-485) */
+    double n[3];     /* disk normal (m_frame.n) */
+    int group;
+} canopy_hit_t;
+
+int canopy_init(canopy_t *C, const ertb_scene_desc *d);
+void canopy_free(canopy_t *C);
+/* nearest leaf along o + t d, 0 <= t <= maxt */
+canopy_hit_t canopy_intersect(const canopy_t *C, const double o[3], const double d[3], double maxt);
+
+/* bilambertian.cpp: local frame, z = leaf normal.  eval returns f * |cos(theta_o)|. */
+double bilambertian_eval(double r, double t, const double wi[3], const double wo[3]);
+double bilambertian_pdf(double r, double t, const double wi[3], const double wo[3]);
+/* returns the weight (value / pdf) and the sampled direction */
+double bilambertian_sample(double r, double t, const double wi[3], double sample1, double u1, double u2,
+                           double wo[3]);
+
+#endif

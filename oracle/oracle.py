@@ -226,3 +226,29 @@ def medium_lookup(desc, points):
     _check(load().ertbo_medium_lookup(C.byref(desc), C.c_size_t(p.shape[0]), p.ctypes.data_as(dp),
                                       st.ctypes.data_as(dp), al.ctypes.data_as(dp)))
     return st, al
+
+
+def canopy_intersect(desc, origin, direction, tmax=None):
+    """Nearest leaf along world-space rays (uniform-grid DDA): (t, normal, group)."""
+    o, d = _d(origin).reshape(-1, 3), _d(direction).reshape(-1, 3)
+    n = o.shape[0]
+    tm = _d(np.full(n, np.inf) if tmax is None else np.broadcast_to(tmax, (n,)))
+    t, nrm = np.zeros(n), np.zeros((n, 3))
+    grp = np.zeros(n, dtype=np.int32)
+    _check(load().ertbo_canopy_intersect(C.byref(desc), C.c_size_t(n), o.ctypes.data_as(dp), d.ctypes.data_as(dp),
+                                         tm.ctypes.data_as(dp), t.ctypes.data_as(dp), nrm.ctypes.data_as(dp),
+                                         grp.ctypes.data_as(C.POINTER(C.c_int))))
+    return t, nrm, grp
+
+
+def leaf_bsdf(desc, group, mode, wi, wo=None, u=None):
+    """bilambertian eval ('eval'), pdf ('pdf') or sample ('sample' -> (wo, weight)) in the leaf frame."""
+    wi = _d(wi).reshape(-1, 3)
+    n = wi.shape[0]
+    out = np.zeros(n)
+    m = {"eval": 0, "pdf": 1, "sample": 2}[mode]
+    wo = np.zeros((n, 3)) if wo is None else _d(wo).reshape(-1, 3).copy()
+    uu = np.zeros((n, 3)) if u is None else _d(u).reshape(-1, 3)
+    _check(load().ertbo_leaf_bsdf(C.byref(desc), C.c_int(group), C.c_int(m), C.c_size_t(n), wi.ctypes.data_as(dp),
+                                  wo.ctypes.data_as(dp), uu.ctypes.data_as(dp), out.ctypes.data_as(dp)))
+    return (wo, out) if mode == "sample" else out

@@ -26,6 +26,21 @@ def polarized_aerosol_scene() -> dict:
     return d
 
 
+CANOPY = {"lai": 2.5, "radius": 0.1, "size": (4.0, 4.0, 1.0), "padding": 1, "seed": 6}
+
+
+def _first_sensor(d: dict) -> dict:
+    """Fixtures hold sensor 0 only: drop the others."""
+    keep, seen = {}, False
+    for k, v in d.items():
+        is_sensor = isinstance(v, dict) and v.get("type") in ("mdistant", "hdistant", "distantflux", "perspective")
+        if is_sensor and seen:
+            continue
+        seen = seen or is_sensor
+        keep[k] = v
+    return keep
+
+
 def battery() -> dict:
     """name -> scene dict.  Small films; every plugin of SURVEY 8a appears at least once."""
     S = scenes.atmosphere_scene
@@ -113,6 +128,34 @@ def battery() -> dict:
                                          sensor={"type": "hdistant", "film_resolution": (3, 2)}),
         "piecewise_distantflux_coarse_pp": S(geometry="plane_parallel", integrator="piecewise_volpath", n_layers=3,
                                              sensor={"type": "distantflux", "film_resolution": (2, 2)}),
+        # explicit 3D canopies (SURVEY 8f-3 / BASELINE C4): disk leaves in instanced shape groups, bilambertian
+        # leaf BSDF, plane-parallel atmosphere around them; rendered by the 3D kernel (ertb_canopy.cuh)
+        "canopy_path_no_atmosphere": S(geometry="plane_parallel", atmosphere=None, integrator="path", sza=35.0, saa=40.0,
+                                       canopy=dict(CANOPY, reflectance=0.5, transmittance=0.4),
+                                       surface={"type": "diffuse", "reflectance": 0.3},
+                                       sensor={"type": "mdistant", "vza": [-60.0, -20.0, 0.0, 35.0, 70.0], "vaa": 40.0}),
+        "canopy_volpath_afgl_rpv_pp": S(geometry="plane_parallel", n_layers=100, w_nm=670.0, sza=30.0, canopy=CANOPY,
+                                        sensor=VZA5),
+        "canopy_piecewise_aerosol_pp": S(geometry="plane_parallel", n_layers=120, integrator="piecewise_volpath",
+                                         aerosol=True, aerosol_phase="hg", sza=50.0, saa=120.0,
+                                         canopy=dict(CANOPY, orientation="planophile", seed=9), sensor=VZA5),
+        "canopy_perspective_inside_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=200.0,
+                                          canopy=dict(CANOPY, reflectance=0.45, transmittance=0.45),
+                                          surface={"type": "diffuse", "reflectance": 0.15},
+                                          sensor={"type": "perspective", "origin": [1.0, -9.0, 6.0], "look_at": [0.0, 0.0, 0.5],
+                                                  "fov": 45.0, "film_resolution": (3, 2),
+                                                  "medium": {"type": "ref", "id": "medium_atmosphere"}}),
+        "canopy_perspective_above_toa_homogeneous": S(geometry="plane_parallel", atmosphere="homogeneous", toa=2000.0,
+                                                      homogeneous_sigma_t=2e-4, homogeneous_albedo=0.95, sza=20.0,
+                                                      canopy=CANOPY, surface={"type": "rtls"},
+                                                      sensor={"type": "perspective", "origin": [0.0, -300.0, 2500.0],
+                                                              "look_at": [0.0, 0.0, 0.0], "fov": 0.25, "far_clip": 1e5,
+                                                              "film_resolution": (2, 2)}),
+        "canopy_hdistant_maxdepth_pp": S(geometry="plane_parallel", n_layers=50, max_depth=4, rr_depth=2, sza=25.0,
+                                         canopy=dict(CANOPY, reflectance=0.6, transmittance=0.3),
+                                         sensor={"type": "hdistant", "film_resolution": (2, 2)}),
+        "c4_canopy_afgl_rpv_reduced": _first_sensor(scenes.config_c4(spp=16, lai=2.0, radius=0.1, size=(4.0, 4.0, 1.5),
+                                                                     padding=1, n_vza=6, film=(2, 2), n_layers=200)),
         "polarized_piecewise_rayleigh_pp": S(geometry="plane_parallel", integrator="piecewise_volpath",
                                              n_layers=100, sza=40.0, saa=30.0, stokes=True,
                                              phase={"type": "rayleigh_polarized", "depolarization": 0.0279},

@@ -164,6 +164,8 @@ def test_tabphase_reference_values_on_device():
     ({"type": "hdistant", "film_resolution": (4, 4)}, "spherical_shell"),
     ({"type": "distantflux", "film_resolution": (4, 2)}, "plane_parallel"),
     ({"type": "distantflux", "film_resolution": (4, 2), "target": None}, "spherical_shell"),
+    ({"type": "perspective", "origin": [3.0, -40.0, 25.0], "look_at": [0.0, 1.0, 0.5], "fov": 35.0,
+      "film_resolution": (8, 4), "medium": {"type": "ref", "id": "medium_atmosphere"}}, "plane_parallel"),
 ])
 def test_sensor_rays_match_oracle(oracle, sensor, geometry):
     sc = mi_load_dict(scenes.atmosphere_scene(geometry=geometry, n_layers=10, sensor=dict(sensor)))
@@ -183,6 +185,103 @@ def test_sensor_rays_match_oracle(oracle, sensor, geometry):
     else:
         scale = max(1.0, np.abs(o_o).max())
         assert np.allclose(o_g, o_o, atol=3e-6 * scale)
+
+
+# ------------------------------------------------------------------ canopy KATs (3D kernel)
+def test_canopy_ray_caster_matches_oracle(oracle):
+    """Two independent ray casters (device: two-level BVH in float32 around the canopy centre; oracle:
+    uniform-grid DDA in float64) must agree on the nearest leaf of every ray, also for origins
+    kilometres away from the canopy (primary rays entering from the top of the atmosphere)."""
+    sc = mi_load_dict(scenes.atmosphere_scene(
+        geometry="plane_parallel", atmosphere=None, integrator="path",
+        canopy={"lai": 2.5, "radius": 0.08, "size": (5.0, 5.0, 1.5), "padding": 2, "seed": 12},
+        sensor={"type": "mdistant", "vza": [0.0], "vaa": 0.0}))
+    desc = sc.flat.build_desc()
+    rng = np.random.default_rng(21)
+    n = 40000
+    o = np.stack([rng.uniform(-13, 13, n), rng.uniform(-13, 13, n), rng.uniform(0.0, 2.5, n)], axis=1)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    far = slice(0, 4000)  # start 50-120 km up the ray, aimed at the canopy
+    d[far, 2] = -np.abs(d[far, 2]) - 0.2
+    d[far] /= np.linalg.norm(d[far], axis=1, keepdims=True)
+    o[far] = o[far] - d[far] * rng.uniform(5e4, 1.2e5, (4000, 1))
+    tmax = np.where(rng.random(n) < 0.25, rng.uniform(0.05, 4.0, n), 1e30).astype(np.float32)
+    tmax[far] = 1e30
+    t_g, n_g, g_g = kat.canopy_intersect(sc, o, d, tmax)
+    t_o, n_o, g_o = oracle.canopy_intersect(desc, o, d.astype(np.float32).astype(np.float64), tmax.astype(np.float64))
+    z_hit = o[:, 2] + np.where(np.isfinite(t_o), t_o, 0.0) * d[:, 2]
+    ok = ~(np.isfinite(t_o) & (z_hit < 1e-3))  # the device clips the canopy at the ground plane: rays stop there
+    # grazing hits on a disk's rim can fall on either side in float32: allow a handful
+    differ = np.isfinite(t_g[ok]) != np.isfinite(t_o[ok])
+    assert differ.sum() <= 3, differ.sum()
+    both = ok & np.isfinite(t_g) & np.isfinite(t_o)
+    assert both.sum() > 15000 and (~np.isfinite(t_o)).sum() > 3000
+    near = both.copy()
+    near[far] = False
+    bad = np.abs(t_g[near] - t_o[near]) > 2e-5 + 2e-5 * t_o[near]
+    assert bad.sum() <= 3  # (a rim hit may also swap the nearest of two overlapping leaves)
+    # far origins: the float32 direction (normalised in float32 on the device, in float64 by the oracle)
+    # moves the aim point by ~1e-7 x 100 km; the entry point itself is computed in float64
+    # (a few rays then graze a different leaf first)
+    assert np.mean(np.abs(t_g[both & ~near] - t_o[both & ~near]) > 2e-2) < 0.01
+    same = both & (np.abs(t_g - t_o) < 1e-3)
+    assert np.allclose(n_g[same], n_o[same], atol=1e-6) and np.all(g_g[same] == g_o[same])
+
+
+@pytest.mark.parametrize("r, t", [(0.5, 0.4), (0.0546, 0.0149), (1.0, 0.0), (0.0, 0.7), (0.0, 0.0)])
+def test_leaf_bsdf_matches_oracle(oracle, r, t):
+    """bilambertian on the device vs the oracle (which is pinned on the reference's own test values)."""
+    sc = mi_load_dict(scenes.atmosphere_scene(geometry="plane_parallel", atmosphere=None, integrator="path",
+                                              canopy={"n_leaves": 3, "reflectance": r, "transmittance": t}))
+    desc = sc.flat.build_desc()
+    rng = np.random.default_rng(3)
+    n = 4096
+    wi = sph_to_dir(np.arccos(rng.uniform(-1, 1, n)), rng.uniform(0, 2 * np.pi, n))
+    wo = sph_to_dir(np.arccos(rng.uniform(-1, 1, n)), rng.uniform(0, 2 * np.pi, n))
+    ev_g = kat.leaf_bsdf_eval(sc, 0, wi[:, 2], wo[:, 2])
+    assert np.allclose(ev_g, oracle.leaf_bsdf(desc, 0, "eval", wi, wo), rtol=2e-6, atol=1e-9)
+    u = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    wo_g, w_g = kat.leaf_bsdf_sample(sc, 0, wi[:, 2], u)
+    wo_o, w_o = oracle.leaf_bsdf(desc, 0, "sample", wi, u=u.astype(np.float64))
+    # lobe selection compares sample1 with r / (r + t): skip samples within float32 rounding of it
+    clear = np.abs(u[:, 0] - (r / (r + t) if r + t > 0 else 0.0)) > 1e-6
+    assert np.allclose(w_g[clear], w_o[clear], rtol=2e-6, atol=1e-9)
+    assert np.allclose(wo_g[clear], wo_o[clear], atol=5e-5)  # fast-math sincos in the concentric warp
+
+
+def test_canopy_leaf_optics_update_equals_fresh_scene():
+    """leaf reflectance / transmittance are scene parameters (leaf_cloud.py:1177-1200): updating them
+    through the parameter table == loading a scene built with those values; the BVH is untouched."""
+    can = {"lai": 2.0, "radius": 0.1, "size": (3.0, 3.0, 1.0), "padding": 1, "seed": 8}
+    mk = lambda r, t: mi_load_dict(scenes.atmosphere_scene(  # noqa: E731
+        geometry="plane_parallel", n_layers=40, canopy=dict(can, reflectance=r, transmittance=t),
+        sensor={"type": "mdistant", "vza": [-40.0, 10.0], "vaa": 0.0}))
+    sc = mk(0.5, 0.4)
+    w = mi_traverse(sc)
+    spp = 1 << 14
+    a = render(sc, seed=4, spp=spp).raw["sum_l"].copy()
+    w.parameters.update({"leaf_cloud.bsdf.reflectance.value": 0.1, "leaf_cloud.bsdf.transmittance.value": 0.05})
+    b = render(sc, seed=4, spp=spp).raw["sum_l"].copy()
+    c = render(mk(0.1, 0.05), seed=4, spp=spp).raw["sum_l"]
+    assert np.allclose(b, c, rtol=1e-9) and np.all(b < 0.8 * a)
+
+
+def test_canopy_gap_fraction_on_device():
+    """Same analytic answer the oracle is pinned on (tests/test_canopy_oracle.py): planophile black leaves
+    over a white ground, hot spot exp(-LAI) vs decorrelated exp(-2 LAI) (up to the leaf-size correlation)."""
+    lai, sza = 1.0, 30.0
+    sc = mi_load_dict(scenes.atmosphere_scene(
+        geometry="plane_parallel", atmosphere=None, integrator="path", max_depth=2, sza=sza, saa=0.0,
+        surface={"type": "diffuse", "reflectance": 1.0},
+        canopy={"lai": lai, "radius": 0.03, "size": (4.0, 4.0, 1.0), "padding": 3, "orientation": "planophile",
+                "reflectance": 0.0, "transmittance": 0.0, "seed": 2},
+        sensor={"type": "mdistant", "vza": [30.0, -55.0], "vaa": 0.0}))
+    spp = 1 << 20
+    mean = render(sc, seed=1, spp=spp).raw["sum_l"].ravel() / spp
+    e = 1.8 * np.cos(np.radians(sza)) / np.pi
+    assert abs(mean[0] / (e * np.exp(-lai)) - 1.0) < 0.03
+    assert abs(mean[1] / (e * np.exp(-2.0 * lai)) - 1.0) < 0.03
 
 
 # ------------------------------------------------------------------ polarized KATs

@@ -86,9 +86,10 @@ def _set_integrator(ty):
 
 
 @pytest.mark.parametrize("mutate,match", [
-    (_set_integrator("path"), "unsupported"),
+    (_set_integrator("path"), "ignores participating media"),
     (lambda d: d["surface_bsdf"].update({"type": "dielectric"}), "unsupported plugin type 'dielectric'"),
-    (lambda d: d["measure"].update({"type": "perspective"}), "perspective"),
+    (lambda d: d["measure"].update({"type": "perspective"}), "field of view"),
+    (lambda d: d.update({"trunk": {"type": "cylinder"}}), "tree trunks"),
     (lambda d: d["measure"]["film"].update({"width": 5}), "Film size"),
     (lambda d: d["measure"]["sampler"].update({"type": "stratified"}), "sampler"),
     (lambda d: d["illumination"].update({"type": "constant"}), "unsupported"),
@@ -193,4 +194,7 @@ def test_seed_state_matches_numpy_seed_sequence():
 def test_desc_struct_layout_is_stable():
     assert C.sizeof(_abi.PhaseDesc) == 80
     assert C.sizeof(_abi.RenderStats) == 56
-    assert _abi.SceneDesc.sensors.offset + 8 == C.sizeof(_abi.SceneDesc)
+    assert C.sizeof(_abi.SensorDesc) == 352
+    assert C.sizeof(_abi.LeafGroupDesc) == 24
+    assert C.sizeof(_abi.SceneDesc) == 608
+    assert _abi.SceneDesc.instance_offset.offset + 8 == C.sizeof(_abi.SceneDesc)

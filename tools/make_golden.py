@@ -5,7 +5,7 @@ loop-trip counters of the CPU oracle for the scene battery at a fixed seed.
 The reference itself cannot be imported or built in this environment,
 so these fixtures are outputs of the oracle restatement -- pinned separately against the
 reference's golden vectors by tests/test_oracle_golden.py and test_oracle_system.py.
-Run:  python tools/make_golden.py
+Run:  python tools/make_golden.py [--only-missing]
 """
 import json
 import os
@@ -25,8 +25,13 @@ SEED = 20261017
 
 
 def main():
+    path = os.path.join(ROOT, "tests", "golden", "oracle_renders.json")
     out = {"spp": SPP, "seed": SEED, "scenes": {}}
+    if "--only-missing" in sys.argv and os.path.exists(path):  # keep the fixtures already committed
+        out = json.load(open(path))
     for name, d in battery().items():
+        if name in out["scenes"]:
+            continue
         sc = mi_load_dict(d)
         desc = sc.flat.build_desc()
         npix = desc.sensors[0].width * desc.sensors[0].height
@@ -52,7 +57,6 @@ def main():
             out["scenes"][name]["stokes"] = (stokes / spp).tolist()
             out["scenes"][name]["m2"] = (l2 / spp).tolist()
         print(f"{name:40s} mean[0]={mean[0]:.6f} K={(st['trips_main']+st['trips_nee'])/st['n_paths']:.2f}")
-    path = os.path.join(ROOT, "tests", "golden", "oracle_renders.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", path)
