@@ -14,7 +14,11 @@
 //     (instances -> disks) held in global memory (L2 resident: 32 B nodes, 32 B disks), in
 //     float32 coordinates relative to the canopy centre;
 //   * one path per lane, persistent warps, lanes refilled from the chunk queue as soon as their
-//     path ends; each trip of the main loop advances every live lane by one segment.
+//     path ends. A lane is a small state machine (segment set-up -> BVH walk -> free flight and
+//     event -> shadow-ray BVH walk -> shading) and the BVH walk is RESUMABLE: every trip of the
+//     main loop advances all walking lanes by at most ERTB_TRACE_STEPS nodes, then runs the other
+//     stages for the lanes that are ready. Rays that need 10 node visits therefore do not wait
+//     for the one that needs 300 (lock-step walks ran with 4 of 32 lanes active, ncu r01e).
 #pragma once
 
 #include "ertb_kernel.cuh"
@@ -22,7 +26,12 @@
 #include "ertb_piecewise.cuh"
 
 #define ERTB_CANOPY_BLOCK 128
-#define ERTB_BVH_LEAF 4
+#ifndef ERTB_CANOPY_MINB
+#define ERTB_CANOPY_MINB 5 // 96 registers: 20 warps / SM hide the dependent node fetches (B200: +14 % over 4)
+#endif
+#ifndef ERTB_BVH_LEAF
+#define ERTB_BVH_LEAF 1 // primitives per BVH leaf: disk tests run with ~1.5 active lanes, box tests with many
+#endif
 
 // ----------------------------------------------------------------------------
 // BVH traversal
@@ -54,29 +63,42 @@ __device__ __forceinline__ float disk_hit(float4 c, float4 n, f3 o, f3 d, float 
     return px * px + py * py + pz * pz <= c.w * c.w ? t : INFINITY;
 }
 
-// Nearest leaf (ANY = false) or any leaf (ANY = true) along o + t d, 0 <= t <= tmax, in canopy-local
-// coordinates. (skip_inst, skip_disk) names the leaf the ray starts on.
-//
-// ONE loop walks both levels: a stack entry is (node, instance), instance < 0 meaning a node of the
-// top-level tree. Lanes of a warp are then always executing the same few instructions (fetch a
-// node, test its two child boxes, push) whichever level and instance each of them is in; with one
-// loop nested in the other, lanes that reach different instances at different times run their
-// bottom-level traversals one after the other (2.3 active lanes per instruction, ncu r01e).
-template <bool ANY>
-__device__ __noinline__ CanopyHit canopy_trace(const ErtbCanopy &C, f3 o, f3 d, float tmax, int skip_inst, int skip_disk) {
+#ifndef ERTB_TRACE_STEPS
+#define ERTB_TRACE_STEPS 32
+#endif
+#define ERTB_TRACE_STACK 40
+
+// A BVH walk that can be suspended: everything but the stack (a per-lane local array).
+struct TraceState {
+    f3 o;        // ray origin, canopy-local
+    float tmax;
+    int node, ii, sp; // current node, its instance (< 0: top level), stack height
+    int skip_inst, skip_disk; // the leaf the ray starts on
     CanopyHit H;
-    H.t = INFINITY; H.inst = -1; H.disk = -1;
+};
+
+__device__ __forceinline__ void trace_begin(TraceState &T, f3 o, float tmax, int skip_inst, int skip_disk) {
+    T.o = o; T.tmax = tmax; T.node = 0; T.ii = -1; T.sp = 0;
+    T.skip_inst = skip_inst; T.skip_disk = skip_disk;
+    T.H.t = INFINITY; T.H.inst = -1; T.H.disk = -1;
+}
+
+// Advance the walk by at most `steps` nodes; returns true when it is over (T.H holds the nearest leaf,
+// or, with `any`, the first leaf found). ONE loop walks both levels: a stack entry is (node, instance),
+// instance < 0 meaning a node of the top-level tree, so the lanes of a warp always execute the same
+// few instructions (fetch a node, test its two child boxes, push) whichever level each of them is in.
+__device__ __forceinline__ bool trace_run(const ErtbCanopy &C, TraceState &T, int2 *stack, f3 d, bool any, int steps) {
     const float big = 1e30f;
     const f3 inv = mk3(fabsf(d.x) > 1e-30f ? 1.f / d.x : copysignf(big, d.x), fabsf(d.y) > 1e-30f ? 1.f / d.y : copysignf(big, d.y),
                        fabsf(d.z) > 1e-30f ? 1.f / d.z : copysignf(big, d.z));
-    int2 stack[40];
-    int sp = 0;
-    int node = 0, ii = -1;
-    f3 ol = o; // origin in the coordinates of the current level
-    for (;;) {
+    int node = T.node, ii = T.ii, sp = T.sp;
+    f3 ol = T.o;
+    if (ii >= 0) { const float4 in = __ldg(C.inst + ii); ol = mk3(T.o.x - in.x, T.o.y - in.y, T.o.z - in.z); }
+    bool done = false;
+    for (int step = 0; step < steps; ++step) {
         const float4 *q = reinterpret_cast<const float4 *>((ii < 0 ? C.tlas : C.blas) + node);
         const float4 l0 = __ldg(q), h0 = __ldg(q + 1), l1 = __ldg(q + 2), h1 = __ldg(q + 3);
-        const float lim = fminf(tmax, H.t);
+        const float lim = fminf(T.tmax, T.H.t);
         float e[2] = { aabb_entry(l0, h0, ol, inv, lim), aabb_entry(l1, h1, ol, inv, lim) };
         const int c[2] = { __float_as_int(l0.w), __float_as_int(l1.w) }, n[2] = { __float_as_int(h0.w), __float_as_int(h1.w) };
         int next = -1, next_ii = ii;
@@ -85,35 +107,47 @@ __device__ __noinline__ CanopyHit canopy_trace(const ErtbCanopy &C, f3 o, f3 d, 
             if (!(e[s] < INFINITY) || n[s] == 0) continue;
             if (ii < 0) { // instances: their group's root goes on the stack
                 for (int k = c[s]; k < c[s] + n[s]; ++k)
-                    if (sp < 40) stack[sp++] = make_int2(__ldg(C.blas_root + __float_as_int(__ldg(C.inst + k).w)), k);
+                    if (sp < ERTB_TRACE_STACK) stack[sp++] = make_int2(__ldg(C.blas_root + __float_as_int(__ldg(C.inst + k).w)), k);
             } else { // disks: intersected on the spot
                 for (int k = c[s]; k < c[s] + n[s]; ++k) {
-                    if (k == skip_disk && ii == skip_inst) continue;
-                    float t = disk_hit(__ldg(C.disks + 2 * k), __ldg(C.disks + 2 * k + 1), ol, d, fminf(tmax, H.t));
-                    if (t < H.t) { H.t = t; H.inst = ii; H.disk = k; if (ANY) return H; }
+                    if (k == T.skip_disk && ii == T.skip_inst) continue;
+                    float t = disk_hit(__ldg(C.disks + 2 * k), __ldg(C.disks + 2 * k + 1), ol, d, fminf(T.tmax, T.H.t));
+                    if (t < T.H.t) { T.H.t = t; T.H.inst = ii; T.H.disk = k; }
                 }
             }
             e[s] = INFINITY;
         }
+        if (any && T.H.inst >= 0) { done = true; break; }
         // inner children: the nearer one next, the other on the stack
         if (e[0] < INFINITY && e[1] < INFINITY) {
             const bool first0 = e[0] <= e[1];
-            if (sp < 40) stack[sp++] = make_int2(first0 ? c[1] : c[0], ii);
+            if (sp < ERTB_TRACE_STACK) stack[sp++] = make_int2(first0 ? c[1] : c[0], ii);
             next = first0 ? c[0] : c[1];
         } else if (e[0] < INFINITY) next = c[0];
         else if (e[1] < INFINITY) next = c[1];
         else {
-            if (sp == 0) return H;
+            if (sp == 0) { done = true; break; }
             const int2 top = stack[--sp];
             next = top.x; next_ii = top.y;
         }
         if (next_ii != ii) {
             ii = next_ii;
-            if (ii < 0) ol = o;
-            else { const float4 in = __ldg(C.inst + ii); ol = mk3(o.x - in.x, o.y - in.y, o.z - in.z); }
+            if (ii < 0) ol = T.o;
+            else { const float4 in = __ldg(C.inst + ii); ol = mk3(T.o.x - in.x, T.o.y - in.y, T.o.z - in.z); }
         }
         node = next;
     }
+    T.node = node; T.ii = ii; T.sp = sp;
+    return done;
+}
+
+// whole walk in one call (KAT entry point)
+__device__ __noinline__ CanopyHit canopy_trace(const ErtbCanopy &C, f3 o, f3 d, float tmax, bool any, int skip_inst, int skip_disk) {
+    TraceState T;
+    int2 stack[ERTB_TRACE_STACK];
+    trace_begin(T, o, tmax, skip_inst, skip_disk);
+    while (!trace_run(C, T, stack, d, any, ERTB_TRACE_STEPS)) { }
+    return T.H;
 }
 
 // Clip the segment p + t d, 0 <= t <= tmax, to the canopy's bounding box (float64, world space).
@@ -131,24 +165,20 @@ __device__ __forceinline__ bool canopy_clip(const ErtbCanopy &C, const double p[
     return t0 <= t1;
 }
 
+// canopy-local float origin of the point p + t0 d
+__device__ __forceinline__ f3 canopy_local(const ErtbCanopy &C, const double p[3], f3 d, double t0) {
+    return mk3((float) (p[0] + t0 * (double) d.x - C.origin[0]), (float) (p[1] + t0 * (double) d.y - C.origin[1]),
+               (float) (p[2] + t0 * (double) d.z - C.origin[2]));
+}
+
 // nearest leaf along a world-space segment; returns the distance from p (INFINITY: none)
 __device__ __forceinline__ double canopy_nearest(const ErtbCanopy &C, const double p[3], f3 d, double tmax,
                                                  int skip_inst, int skip_disk, CanopyHit &H) {
     H.t = INFINITY; H.inst = -1; H.disk = -1;
     double t0, t1;
     if (C.n_instances == 0 || !canopy_clip(C, p, d, tmax, t0, t1)) return INFINITY;
-    f3 o = mk3((float) (p[0] + t0 * (double) d.x - C.origin[0]), (float) (p[1] + t0 * (double) d.y - C.origin[1]),
-               (float) (p[2] + t0 * (double) d.z - C.origin[2]));
-    H = canopy_trace<false>(C, o, d, (float) (t1 - t0), skip_inst, skip_disk);
+    H = canopy_trace(C, canopy_local(C, p, d, t0), d, (float) (t1 - t0), false, skip_inst, skip_disk);
     return H.inst >= 0 ? t0 + (double) H.t : INFINITY;
-}
-
-__device__ __forceinline__ bool canopy_shadowed(const ErtbCanopy &C, const double p[3], f3 d, int skip_inst, int skip_disk) {
-    double t0, t1;
-    if (C.n_instances == 0 || !canopy_clip(C, p, d, 1e30, t0, t1)) return false;
-    f3 o = mk3((float) (p[0] + t0 * (double) d.x - C.origin[0]), (float) (p[1] + t0 * (double) d.y - C.origin[1]),
-               (float) (p[2] + t0 * (double) d.z - C.origin[2]));
-    return canopy_trace<true>(C, o, d, (float) (t1 - t0), skip_inst, skip_disk).inst >= 0;
 }
 
 // ----------------------------------------------------------------------------
@@ -234,17 +264,11 @@ __device__ __forceinline__ bool canopy_primary(const ErtbParams &P, unsigned pix
     return d.z < 0.f; // distant sensors look down on a plane-parallel scene
 }
 
-// Sun visibility and atmospheric transmittance from `p` (altitude h above the ground) towards
-// the sun (volpath.cpp:400-554 / piecewise_volpath.cpp:392-527): leaves and the ground are opaque to
-// shadow rays (eval_null_transmission = 0), the medium attenuates by ratio tracking or exactly.
+// Atmospheric transmittance from altitude h towards the sun, sun.z > 0 (volpath.cpp:400-554 ratio
+// tracking / piecewise_volpath.cpp:392-527 exact); occlusion by leaves is the shadow-ray BVH walk.
 template <bool PW, bool STATS>
-__device__ __forceinline__ float canopy_sun_transmittance(const ErtbParams &P, const float *tb, const double p[3], float h,
-                                                          bool in_medium, f3 sun, int skip_inst, int skip_disk,
+__device__ __forceinline__ float sun_medium_transmittance(const ErtbParams &P, const float *tb, float h, f3 sun,
                                                           Pcg32 &rng, unsigned &st_nee) {
-    if (STATS && !(in_medium && P.has_medium)) st_nee++; // a shadow ray through vacuum is one loop trip
-    if (!(sun.z > 0.f)) return 0.f; // the ground plane is in the way
-    if (canopy_shadowed(P.canopy, p, sun, skip_inst, skip_disk)) return 0.f;
-    if (!in_medium || !P.has_medium) return 1.f;
     if (PW) {
         if (STATS) st_nee++;
         return pw_transmittance_up(P, tb, h, sun.z);
@@ -262,9 +286,11 @@ __device__ __forceinline__ float canopy_sun_transmittance(const ErtbParams &P, c
 }
 
 enum : int { CEV_NONE = 0, CEV_COLLISION = 1, CEV_GROUND = 2, CEV_LEAF = 3, CEV_END = 4 };
+// lane state machine
+enum : int { LP_NEW = 0, LP_SEGMENT = 1, LP_TRACE = 2, LP_FLIGHT = 3, LP_SHADE = 4 };
 
 template <bool STATS, bool PW>
-__global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, 4) ertb_canopy_kernel(const ErtbParams P) {
+__global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_canopy_kernel(const ErtbParams P) {
     extern __shared__ __align__(16) float tb[]; // table blob
     __shared__ __align__(8) unsigned long long mbar;
     if (P.blob_bytes > 0) tma_stage(tb, P.blob, (unsigned) P.blob_bytes, &mbar);
@@ -274,14 +300,22 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, 4) ertb_canopy_kernel(const
     const f3 sun = mk3(P.sun[0], P.sun[1], P.sun[2]);
     const ErtbCanopy &C = P.canopy;
     const double z_ground = P.Rd;
+    const bool medium = P.has_medium != 0;
 
     // per-lane path state
-    bool alive = false, in_medium = false, first_segment = false;
+    int phase = LP_NEW;
+    bool in_medium = false, first_segment = false, shadow = false;
     double p[3] = { 0.0, 0.0, 0.0 };
     f3 d = mk3(0.f, 0.f, -1.f);
-    float thr = 0.f, res = 0.f, wray = 1.f, maxt = INFINITY;
+    float thr = 0.f, res = 0.f, wray = 1.f, maxt = INFINITY, nee = 0.f;
     unsigned depth = 0, pix = 0;
     int on_inst = -1, on_disk = -1; // the leaf the current ray starts on
+    // the segment being resolved: distance / kind of the next analytic surface, start of the BVH walk
+    double t_geo = 0.0, t_clip0 = 0.0;
+    int ev_geo = CEV_END;
+    TraceState T;
+    int2 stack[ERTB_TRACE_STACK];
+    trace_begin(T, mk3(0.f, 0.f, 0.f), 0.f, -1, -1);
     Pcg32 rng;
     rng.state = 0; rng.inc = 1;
 
@@ -292,10 +326,18 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, 4) ertb_canopy_kernel(const
     bool exhausted = false;
     unsigned st_main = 0, st_nee = 0, st_scatter = 0, st_surface = 0, st_paths = 0;
 
+#define CANOPY_FINISH()                                 \
+    do {                                                \
+        acc_wl += (double) (wray * res);                \
+        acc_l += (double) res;                          \
+        acc_l2 += (double) res * (double) res;          \
+        phase = LP_NEW;                                 \
+    } while (0)
+
     for (;;) {
-        // ---- path regeneration: finished lanes pop the next samples (warp-aggregated) ----
+        // ================= regeneration: finished lanes pop the next samples (warp-aggregated) =================
         {
-            unsigned pending = __ballot_sync(0xffffffffu, !alive);
+            unsigned pending = exhausted ? 0u : __ballot_sync(0xffffffffu, phase == LP_NEW);
             bool got = false;
             unsigned long long my_sample = 0;
             unsigned my_pix = 0;
@@ -328,27 +370,26 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, 4) ertb_canopy_kernel(const
                 pcg_seed(rng, P.seed, ((unsigned long long) pix << 40) + (P.sample_offset + my_sample));
                 if (STATS) st_paths++;
                 thr = 1.f; res = 0.f; depth = 0; on_inst = on_disk = -1;
-                alive = canopy_primary(P, pix, rng, p, d, wray, maxt);
+                const bool valid = canopy_primary(P, pix, rng, p, d, wray, maxt);
                 first_segment = true;
                 if (P.sensor.type == ERTB_SENSOR_PERSPECTIVE) {
                     in_medium = P.sensor.in_medium != 0;
-                } else if (alive) {
+                } else if (valid) {
                     // distant sensors sit outside the scene: bring the origin down to where the ray
                     // enters it (top of the atmosphere, or just above the canopy without one)
                     in_medium = false;
-                    double z_in = P.has_medium ? z_ground + (double) P.H : fmax(C.n_instances ? C.hi[2] : z_ground, p[2]) + 1.0;
+                    double z_in = medium ? z_ground + (double) P.H : fmax(C.n_instances ? C.hi[2] : z_ground, p[2]) + 1.0;
                     double t_in = (z_in - p[2]) / (double) d.z; // <= 0: move backwards along the ray
                     p[0] += t_in * (double) d.x; p[1] += t_in * (double) d.y; p[2] = z_in;
                 }
                 // (an invalid primary ray is a sample with L = 0: nothing to accumulate)
+                if (valid) phase = LP_SEGMENT;
             }
         }
-        if (!__any_sync(0xffffffffu, alive)) {
-            if (exhausted) break;
-            continue;
-        }
+        if (exhausted && !__any_sync(0xffffffffu, phase != LP_NEW)) break;
 
-        if (alive) {
+        // ================= segment set-up: termination, analytic surfaces, start of the BVH walk =================
+        if (phase == LP_SEGMENT) {
             // ---- termination (volpath.cpp:189-202) ----
             bool dead = thr == 0.f || depth >= P.max_depth;
             if (!dead && depth > P.rr_depth) {
@@ -356,69 +397,77 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, 4) ertb_canopy_kernel(const
                 if (pcg_float(rng) >= q) dead = true;
                 else thr = __fdividef(thr, q);
             }
-            int ev = dead ? CEV_END : CEV_NONE;
-            CanopyHit hit;
-            hit.t = INFINITY; hit.inst = -1; hit.disk = -1;
-            float h = (float) (p[2] - z_ground); // altitude above the ground
-            float nee = 0.f;                      // value of the pending sun sample (before transmittance)
-
-            if (ev == CEV_NONE) {
-                // a ray above the atmosphere travels through vacuum down to its top
-                if (!in_medium && P.has_medium && h >= P.H) {
-                    if (!(d.z < 0.f)) ev = CEV_END; // leaves the scene
-                    else {
-                        double t_in = ((double) P.H - (p[2] - z_ground)) / (double) d.z;
-                        p[0] += t_in * (double) d.x; p[1] += t_in * (double) d.y; p[2] = z_ground + (double) P.H;
-                        h = P.H;
-                        in_medium = true;
-                        if (first_segment) maxt -= (float) t_in;
-                    }
+            // a ray above the atmosphere travels through vacuum down to its top
+            if (!dead && !in_medium && medium && (float) (p[2] - z_ground) >= P.H) {
+                if (!(d.z < 0.f)) dead = true; // leaves the scene
+                else {
+                    double t_in = ((double) P.H - (p[2] - z_ground)) / (double) d.z;
+                    p[0] += t_in * (double) d.x; p[1] += t_in * (double) d.y; p[2] = z_ground + (double) P.H;
+                    in_medium = true;
+                    if (first_segment) maxt -= (float) t_in;
                 }
             }
-            if (ev == CEV_NONE) {
-                // ---- next surface along the ray: ground plane / top of the slab / nearest leaf ----
+            if (dead) CANOPY_FINISH();
+            else {
+                // ---- next analytic surface: ground plane / top of the slab ----
                 const bool down = d.z < 0.f;
-                double t_geo = down ? (p[2] - z_ground) / (double) -d.z
-                                    : (in_medium && d.z > 0.f ? fmax((double) P.H - (p[2] - z_ground), 0.0) / (double) d.z : 1e30);
-                int ev_geo = down ? CEV_GROUND : CEV_END; // upward: leaves through the top (or to infinity)
+                t_geo = down ? (p[2] - z_ground) / (double) -d.z
+                             : (in_medium && d.z > 0.f ? fmax((double) P.H - (p[2] - z_ground), 0.0) / (double) d.z : 1e30);
+                ev_geo = down ? CEV_GROUND : CEV_END; // upward: leaves through the top (or to infinity)
                 if (t_geo > 1e9) { t_geo = 1e9; ev_geo = CEV_END; } // grazing rays: the reference's slab is 1e9 m wide
                 if (first_segment && (double) maxt < t_geo) { t_geo = (double) maxt; ev_geo = CEV_END; } // far clip
-                double t_leaf = canopy_nearest(C, p, d, t_geo, on_inst, on_disk, hit);
-                double t_seg = t_geo;
-                int ev_seg = ev_geo;
-                if (t_leaf < t_geo) { t_seg = t_leaf; ev_seg = CEV_LEAF; }
+                // ---- nearest leaf: walk the BVH over the part of the segment inside the canopy's box ----
+                double t1;
+                shadow = false;
+                T.H.t = INFINITY; T.H.inst = -1; T.H.disk = -1;
+                phase = LP_FLIGHT;
+                if (C.n_instances && canopy_clip(C, p, d, t_geo, t_clip0, t1)) {
+                    trace_begin(T, canopy_local(C, p, d, t_clip0), (float) (t1 - t_clip0), on_inst, on_disk);
+                    phase = LP_TRACE;
+                }
+            }
+        }
 
-                // ---- free flight through the medium, bounded by t_seg ----
-                double t_ev = t_seg;
-                ev = ev_seg;
-                if (STATS && !(in_medium && P.has_medium)) st_main++; // a vacuum segment is one loop trip
-                if (in_medium && P.has_medium) {
-                    if (PW) {
+        // ================= BVH walk, one slice (nearest leaf of a path segment, or any leaf on a shadow ray) =================
+        if (__any_sync(0xffffffffu, phase == LP_TRACE)) {
+            if (phase == LP_TRACE && trace_run(C, T, stack, shadow ? sun : d, shadow, ERTB_TRACE_STEPS))
+                phase = shadow ? LP_SHADE : LP_FLIGHT;
+        }
+
+        // ================= free flight to the next event, the event, the sun sample it generates =================
+        if (phase == LP_FLIGHT) {
+            float h = (float) (p[2] - z_ground); // altitude above the ground
+            double t_seg = t_geo;
+            int ev = ev_geo;
+            if (T.H.inst >= 0) { t_seg = t_clip0 + (double) T.H.t; ev = CEV_LEAF; }
+            double t_ev = t_seg;
+            nee = 0.f;
+            // ---- free flight through the medium, bounded by t_seg (medium.cpp:42-82 / piecewise.cpp:183-332) ----
+            if (STATS && !(in_medium && medium)) st_main++; // a vacuum segment is one loop trip
+            if (in_medium && medium) {
+                if (PW) {
+                    if (STATS) st_main++;
+                    float s, hn;
+                    int r = pw_flight(P, tb, h, d.z, -__logf(1.f - pcg_float(rng)), s, hn);
+                    if (r == PW_COLLISION && (double) s < t_seg) { t_ev = (double) s; ev = CEV_COLLISION; }
+                } else {
+                    float t = 0.f;
+                    const float ts = (float) t_seg;
+                    for (;;) {
                         if (STATS) st_main++;
-                        float s, hn;
-                        int r = pw_flight(P, tb, h, d.z, -__logf(1.f - pcg_float(rng)), s, hn);
-                        if (r == PW_COLLISION && (double) s < t_seg) { t_ev = (double) s; ev = CEV_COLLISION; }
-                    } else {
-                        float t = 0.f;
-                        const float ts = (float) fmin(t_seg, 1e30);
-                        for (;;) {
-                            if (STATS) st_main++;
-                            t += -__logf(1.f - pcg_float(rng)) * P.inv_majorant;
-                            if (!(t < ts)) break;
-                            float preal = tb[P.off_preal + layer_of(P, fmaf(t, d.z, h))];
-                            if (pcg_float(rng) >= 1.f - preal) { t_ev = (double) t; ev = CEV_COLLISION; break; }
-                        }
+                        t += -__logf(1.f - pcg_float(rng)) * P.inv_majorant;
+                        if (!(t < ts)) break;
+                        float preal = tb[P.off_preal + layer_of(P, fmaf(t, d.z, h))];
+                        if (pcg_float(rng) >= 1.f - preal) { t_ev = (double) t; ev = CEV_COLLISION; break; }
                     }
                 }
-                // ---- move to the event ----
-                if (ev != CEV_END) {
-                    p[0] += t_ev * (double) d.x; p[1] += t_ev * (double) d.y; p[2] += t_ev * (double) d.z;
-                    if (ev == CEV_GROUND) p[2] = z_ground;
-                    h = fmaxf((float) (p[2] - z_ground), 0.f);
-                }
-                first_segment = false;
             }
-
+            first_segment = false;
+            if (ev != CEV_END) {
+                p[0] += t_ev * (double) d.x; p[1] += t_ev * (double) d.y; p[2] += t_ev * (double) d.z;
+                if (ev == CEV_GROUND) p[2] = z_ground;
+                h = fmaxf((float) (p[2] - z_ground), 0.f);
+            }
             if (ev == CEV_COLLISION) {
                 // ---- real collision (volpath.cpp:261-310) ----
                 int l = layer_of(P, h);
@@ -474,38 +523,53 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, 4) ertb_canopy_kernel(const
             } else if (ev == CEV_LEAF) {
                 // ---- leaf: bilambertian reflection / transmission; the medium does not change ----
                 if (STATS) st_surface++;
-                float4 in = __ldg(C.inst + hit.inst);
-                float4 nn = __ldg(C.disks + 2 * hit.disk + 1);
+                float4 in = __ldg(C.inst + T.H.inst);
+                float4 nn = __ldg(C.disks + 2 * T.H.disk + 1);
                 const float *lb = tb + C.off_leaf_bsdf + 2 * __float_as_int(in.w);
-                float2 rt = make_float2(lb[0], lb[1]);
                 f3 n = mk3(nn.x, nn.y, nn.z);
                 float ci = -dot3(n, d);
-                on_inst = hit.inst; on_disk = hit.disk;
-                if (depth + 1u < P.max_depth) {
-                    float co = dot3(n, sun);
-                    nee = thr * bilambertian_eval(rt.x, rt.y, ci, co) * P.irradiance;
-                }
+                on_inst = T.H.inst; on_disk = T.H.disk;
+                if (depth + 1u < P.max_depth) nee = thr * bilambertian_eval(lb[0], lb[1], ci, dot3(n, sun)) * P.irradiance;
                 float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
                 f3 wl;
-                thr *= bilambertian_sample(rt.x, rt.y, ci, s1, u1, u2, wl);
+                thr *= bilambertian_sample(lb[0], lb[1], ci, s1, u1, u2, wl);
                 f3 fs, ft;
                 onb(n, fs, ft);
                 d = normalize3(fma3(fs, wl.x, fma3(ft, wl.y, scale3(n, wl.z))));
                 depth++;
             }
-            // ---- next-event estimation, ONE site for all event kinds: the lanes' shadow rays walk the
-            //      BVH together (volpath.cpp:400-554); the sample is taken at the event position ----
-            if (nee > 0.f)
-                res += nee * canopy_sun_transmittance<PW, STATS>(P, tb, p, h, in_medium && P.has_medium, sun, on_inst, on_disk,
-                                                                   rng, st_nee);
-            if (ev == CEV_END) {
-                acc_wl += (double) (wray * res);
-                acc_l += (double) res;
-                acc_l2 += (double) res * (double) res;
-                alive = false;
+            if (ev == CEV_END) CANOPY_FINISH();
+            else {
+                // ---- next-event estimation (volpath.cpp:400-554): leaves and the ground are opaque to the
+                //      shadow ray, the medium attenuates it. The occlusion test is the second BVH walk. ----
+                phase = LP_SEGMENT;
+                if (STATS && nee > 0.f && !(in_medium && medium)) st_nee++; // a vacuum shadow ray is one loop trip
+                if (!(sun.z > 0.f)) nee = 0.f; // the ground plane is in the way
+                if (nee > 0.f) {
+                    double t1;
+                    shadow = true;
+                    T.H.inst = -1;
+                    phase = LP_SHADE;
+                    if (C.n_instances && canopy_clip(C, p, sun, 1e30, t_clip0, t1)) {
+                        trace_begin(T, canopy_local(C, p, sun, t_clip0), (float) (t1 - t_clip0), on_inst, on_disk);
+                        phase = LP_TRACE;
+                    }
+                }
             }
         }
+
+        // ================= shading: the sun sample of the last event, if nothing was in the way =================
+        if (phase == LP_SHADE) {
+            if (T.H.inst < 0) {
+                float tr = 1.f;
+                if (in_medium && medium)
+                    tr = sun_medium_transmittance<PW, STATS>(P, tb, fmaxf((float) (p[2] - z_ground), 0.f), sun, rng, st_nee);
+                res = fmaf(nee, tr, res);
+            }
+            phase = LP_SEGMENT;
+        }
     }
+#undef CANOPY_FINISH
 
     film_flush_warp<false>(P, lane, true, acc_pix, acc_wl, acc_l, acc_l2, 0.0, 0.0, 0.0);
     if (STATS && P.stats) {
