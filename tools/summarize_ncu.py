@@ -62,7 +62,7 @@ top = sorted(d.items(), key=lambda kv: -kv[1][1])[:25]
 
 with open(out + ".md", "w") as f:
     f.write(f"# ncu summary: `{rep.split('/')[-1]}`\n\n{note}\n\n")
-    f.write("Captured with `ncu --set full --clock-control none --import-source on -k regex:ertb_render_kernel` "
+    f.write("Captured with `ncu --set full --clock-control none --import-source on -k regex:<kernel>` "
             "under gpurun (1x B200); numbers under the profiler are cold-cache/serialised -- use shares, not absolutes.\n\n")
     for n, k in enumerate(kernels):
         f.write(f"## launch {n}\n\n| metric | value | unit |\n|---|---|---|\n")
