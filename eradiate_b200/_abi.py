@@ -160,7 +160,7 @@ class RenderStats(C.Structure):
         ("n_surface", C.c_uint64),
         ("device_ms", C.c_double),
         ("n_launches", C.c_int32),
-        ("_pad", C.c_int32),
+        ("n_bands", C.c_int32),
     ]
 
     def as_dict(self) -> dict:
@@ -174,6 +174,7 @@ class RenderStats(C.Structure):
                 "n_surface",
                 "device_ms",
                 "n_launches",
+                "n_bands",
             )
         }
 

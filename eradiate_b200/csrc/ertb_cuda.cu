@@ -313,6 +313,61 @@ static int build_canopy(ertb_scene *S) {
 
 static size_t align4(size_t n) { return (n + 3) & ~size_t(3); }
 
+// Banded majorant (ertb_kernel_pool.cuh): cut the layer stack into <= ERTB_MAX_BANDS contiguous bands
+// minimising the expected number of loop trips of a vertical traverse,
+//     sum over bands (band majorant x band thickness)  +  ERTB_BAND_PENALTY x (number of bands),
+// i.e. tentative collisions plus one boundary stop per band. O(n^2 x bands) dynamic programme.
+#define ERTB_MAX_BANDS 8
+#define ERTB_BAND_PENALTY 1.0
+#define ERTB_BAND_MIN_GAIN 0.5
+static std::vector<int> choose_bands(const std::vector<double> &sigma, double dz) {
+    const int n = (int) sigma.size();
+    // candidate cut points: the layer edges with the largest jumps of log(sigma_t) plus a uniform
+    // comb, <= 96 in all, so that the programme costs microseconds (it runs at every parameter update)
+    std::vector<int> cand;
+    if (n <= 96) {
+        for (int i = 0; i <= n; ++i) cand.push_back(i);
+    } else {
+        std::vector<std::pair<double, int>> jump;
+        for (int i = 1; i < n; ++i) {
+            double a = fmax(sigma[i - 1], 1e-300), b = fmax(sigma[i], 1e-300);
+            jump.push_back({ -fabs(log(a / b)), i });
+        }
+        std::partial_sort(jump.begin(), jump.begin() + 48, jump.end());
+        std::vector<char> mark(n + 1, 0);
+        mark[0] = mark[n] = 1;
+        for (int k = 0; k < 48; ++k) mark[jump[k].second] = 1;
+        for (int k = 1; k < 48; ++k) mark[(int) ((long long) k * n / 48)] = 1;
+        for (int i = 0; i <= n; ++i) if (mark[i]) cand.push_back(i);
+    }
+    const int m = (int) cand.size(); // cand[0] = 0, cand[m - 1] = n
+    std::vector<double> segmax(m - 1, 0.0);
+    for (int c = 0; c + 1 < m; ++c)
+        for (int i = cand[c]; i < cand[c + 1]; ++i) segmax[c] = fmax(segmax[c], sigma[i]);
+    const double INF = 1e300;
+    std::vector<std::vector<double>> cost(ERTB_MAX_BANDS + 1, std::vector<double>(m, INF));
+    std::vector<std::vector<int>> from(ERTB_MAX_BANDS + 1, std::vector<int>(m, -1));
+    cost[0][0] = 0.0;
+    for (int k = 1; k <= ERTB_MAX_BANDS; ++k)
+        for (int j = 1; j < m; ++j) {
+            double mx = 0.0;
+            for (int i = j - 1; i >= 0; --i) { // band = layers [cand[i], cand[j])
+                mx = fmax(mx, segmax[i]);
+                if (cost[k - 1][i] >= INF) continue;
+                double c = cost[k - 1][i] + mx * dz * (cand[j] - cand[i]) + ERTB_BAND_PENALTY;
+                if (c < cost[k][j]) { cost[k][j] = c; from[k][j] = i; }
+            }
+        }
+    int best = 1;
+    for (int k = 2; k <= ERTB_MAX_BANDS; ++k) if (cost[k][m - 1] < cost[best][m - 1] - 1e-12) best = k;
+    // a trip of the banded walk costs ~1.6x a trip of the plain one (measured on C2, where the programme
+    // finds 8.5 trips per path against 10.2 and the kernel is 30 % slower): bands must halve the trips
+    if (cost[best][m - 1] > ERTB_BAND_MIN_GAIN * cost[1][m - 1]) best = 1;
+    std::vector<int> starts(best);
+    for (int k = best, j = m - 1; k >= 1; --k) { j = from[k][j]; starts[k - 1] = cand[j]; }
+    return starts; // first layer of every band (starts[0] = 0)
+}
+
 // distr_1d.h:548-600 compute_cdf_scalar: trapezoid CDF accumulated in double
 static void build_tab_leaf(const HostPhase &hp, ErtbPhaseLeaf &L, std::vector<float> &blob) {
     const int n = (int) hp.values.size();
@@ -425,6 +480,42 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
                     blob.push_back((float) cum[i]);
                 }
             blob.resize(align4(blob.size()), 0.f);
+        }
+        // banded majorant (pool kernel only; ERTB_MAJORANT=global keeps the reference's single majorant)
+        P.n_bands = 1;
+        {
+            const char *e = getenv("ERTB_MAJORANT");
+            const bool want = !(e && strcmp(e, "global") == 0) && !S->homogeneous && !S->needs_3d && n > 1 &&
+                              S->integrator != ERTB_INTEGRATOR_PIECEWISE_VOLPATH && majorant > 0.0;
+            if (want) {
+                std::vector<double> sg(n);
+                for (int i = 0; i < n; ++i) sg[i] = (double) S->scale * (double) S->sigma_t[i];
+                const double dz = (S->medium_top - S->medium_bottom) / n;
+                std::vector<int> starts = choose_bands(sg, dz);
+                const int nb = (int) starts.size();
+                if (nb > 1) {
+                    P.n_bands = nb;
+                    P.off_band_lo = (int) blob.size();
+                    for (int k = 0; k < nb; ++k) // altitude above the ground of the band's lower boundary
+                        blob.push_back((float) (S->medium_bottom + starts[k] * dz - S->surface_z));
+                    blob.push_back((float) (S->medium_top - S->surface_z));
+                    blob.resize(align4(blob.size()), 0.f);
+                    P.off_band_ratio = (int) blob.size();
+                    for (int k = 0; k < nb; ++k) {
+                        double mx = 0.0;
+                        for (int i = starts[k]; i < (k + 1 < nb ? starts[k + 1] : n); ++i) mx = fmax(mx, sg[i]);
+                        // (a band of vacuum gets a token majorant: its flights overshoot the band at once)
+                        blob.push_back((float) (majorant / fmax(mx, 1e-6 * majorant)));
+                    }
+                    blob.resize(align4(blob.size()), 0.f);
+                    P.off_band_of = (int) blob.size();
+                    for (int i = 0, k = 0; i < n; ++i) {
+                        while (k + 1 < nb && i >= starts[k + 1]) ++k;
+                        blob.push_back((float) k);
+                    }
+                    blob.resize(align4(blob.size()), 0.f);
+                }
+            }
         }
         P.piecewise = S->integrator == ERTB_INTEGRATOR_PIECEWISE_VOLPATH;
         if (P.piecewise) {
@@ -933,7 +1024,8 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     if (pol || pw) use_pool = true; // the polarized and the piecewise paths exist in the pool kernel only
     if (c3d) use_pool = false;
     const int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK);
-    size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol) : (size_t) S->base.blob_bytes;
+    const bool bands = S->base.n_bands > 1;
+    size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol, bands && !pw) : (size_t) S->base.blob_bytes;
     if (use_pool && smem > (size_t) S->max_smem_optin) { // huge tables: fall back to the register kernel
         if (pol || pw) return set_error("scene tables leave no shared memory for the path pools");
         use_pool = false;
@@ -949,11 +1041,16 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, KERNEL, block, smem)); \
         S->occupancy[key] = blocks_per_sm;                                                            \
     } while (0)
+#define ERTB_POOL_VARIANT_B(MACRO, SPH_, POL_, PW_, B_)                                               \
+    do {                                                                                              \
+        if (with_stats) MACRO((ertb_render_pool_kernel<SPH_, true, POL_, PW_, true, B_>));            \
+        else if (coll) MACRO((ertb_render_pool_kernel<SPH_, false, POL_, PW_, true, B_>));            \
+        else MACRO((ertb_render_pool_kernel<SPH_, false, POL_, PW_, false, B_>));                     \
+    } while (0)
 #define ERTB_POOL_VARIANT(MACRO, SPH_, POL_, PW_)                                                     \
     do {                                                                                              \
-        if (with_stats) MACRO((ertb_render_pool_kernel<SPH_, true, POL_, PW_, true>));                \
-        else if (coll) MACRO((ertb_render_pool_kernel<SPH_, false, POL_, PW_, true>));                \
-        else MACRO((ertb_render_pool_kernel<SPH_, false, POL_, PW_, false>));                         \
+        if (!PW_ && bands) ERTB_POOL_VARIANT_B(MACRO, SPH_, POL_, false, true);                       \
+        else ERTB_POOL_VARIANT_B(MACRO, SPH_, POL_, PW_, false);                                      \
     } while (0)
 #define ERTB_DISPATCH(MACRO)                                                                          \
     do {                                                                                              \
@@ -1030,6 +1127,7 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
 #undef ERTB_LAUNCH
 #undef ERTB_DISPATCH
 #undef ERTB_POOL_VARIANT
+#undef ERTB_POOL_VARIANT_B
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1081,6 +1179,7 @@ int ertb_render_stokes(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, u
         stats->n_surface = h[4];
         stats->device_ms = ms;
         stats->n_launches = 1;
+        stats->n_bands = S->base.n_bands;
     }
     return 0;
 }
@@ -1205,6 +1304,7 @@ int ertb_batch_end(ertb_scene *S, double *accum_out, size_t count, ertb_render_s
             stats[i].n_scatter = c[3];
             stats[i].n_surface = c[4];
             stats[i].n_launches = 1;
+            stats[i].n_bands = S->base.n_bands;
         }
     }
     return 0;

@@ -96,6 +96,11 @@ struct ErtbParams {
     int off_preal;    // sigma_t/majorant per layer
     int off_albedo;
     int off_cumw;     // (n_phase-1) x n_layers cumulative leaf probabilities
+    // banded majorant (pool kernel, BANDS instances): the layer stack is cut into n_bands altitude bands,
+    // each with its own majorant. Blob: band_lo[n_bands + 1] (altitudes above the ground of the band
+    // boundaries), band_ratio[n_bands] (global majorant / band majorant), band_of_layer[n_layers]
+    int n_bands;
+    int off_band_lo, off_band_ratio, off_band_of;
     // piecewise medium (ertb_piecewise.cuh): sigma_t per layer, vertical optical depth above each of
     // the n_layers + 1 layer boundaries, layer thickness, optical depth above the ground level
     int piecewise;

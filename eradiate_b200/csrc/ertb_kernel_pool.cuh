@@ -53,10 +53,12 @@ enum : unsigned {
     PFL_DEPTH_SHIFT = 8
 };
 
-__host__ __device__ inline size_t ertb_pool_smem_bytes(size_t blob_bytes, bool pol = false) {
+// BANDS instances append two fields to the record: the distance of the next band boundary along the
+// segment, and (band index | descending << 8)
+__host__ __device__ inline size_t ertb_pool_smem_bytes(size_t blob_bytes, bool pol = false, bool bands = false) {
     size_t blob = (blob_bytes + 15) & ~size_t(15);
     size_t warps = ERTB_POOL_BLOCK / 32;
-    return blob + warps * (size_t) (pol ? PF_COUNT_POL : PF_COUNT) * ERTB_POOL_NS * 4 + warps * 32 * 4;
+    return blob + warps * (size_t) ((pol ? PF_COUNT_POL : PF_COUNT) + (bands ? 2 : 0)) * ERTB_POOL_NS * 4 + warps * 32 * 4;
 }
 
 // free flight that follows a regeneration or an event of the piecewise integrator
@@ -67,6 +69,47 @@ __device__ __forceinline__ unsigned pw_advance(const ErtbParams &P, const float 
     int r = pw_flight(P, tb, h0, mu, E, s, h);
     if (r == PW_COLLISION) { h0 = h; return PM_SCAT; }
     return r == PW_GROUND ? PM_SURF : PM_IDLE;
+}
+
+// ----------------------------------------------------------------------------
+// Banded majorant (BANDS instances). The reference samples free flights against ONE majorant,
+// scale * max(sigma_t) over the whole grid (heterogeneous.cpp:163): an aerosol layer of optical
+// depth 0.5 between 1 and 2 km makes every kilometre of the 120 km column as expensive as a
+// kilometre of aerosol -- 476 loop trips per path on BASELINE C3, > 95 % of them null collisions.
+// Delta and ratio tracking stay unbiased with ANY majorant that bounds sigma_t locally, and free
+// flights are memoryless, so the host cuts the layer stack into a few altitude bands (dynamic
+// programme over the profile, ertb_cuda.cu) and the walk samples against the majorant of the band
+// it is in; a flight that would leave the band stops at the boundary and continues from there
+// with the next band's majorant. Same estimator in expectation (lower variance for the ratio
+// tracker), an order of magnitude fewer trips when the profile has a thin dense layer; with one
+// band (clear-sky profiles such as C2) this is the reference's walk, trip for trip, and the
+// BANDS = false instances are used.
+// ----------------------------------------------------------------------------
+// distance, along the segment (h0, b), at which a record in band `bi` reaches the band's boundary
+// (`down`: it is descending; cleared when a spherical ray passes its perigee inside the band)
+template <bool SPH>
+__device__ __forceinline__ float band_exit(const ErtbParams &P, const float *tb, float h0, float b, int bi, bool &down,
+                                           float smax) {
+    const float *lo = tb + P.off_band_lo;
+    if (down) {
+        const float hk = bi > 0 ? lo[bi] : 0.f; // band 0 ends at the ground
+        if (SPH) {
+            float c = (h0 - hk) * (2.f * P.R + h0 + hk);
+            float disc = fmaf(b, b, -c);
+            if (disc >= 0.f) return bi > 0 ? fminf(fmaxf(__fdividef(c, fast_sqrt(disc) - b), 0.f), smax) : smax;
+            down = false; // perigee inside this band: it is left through its top
+        } else {
+            return bi > 0 ? fminf(fmaxf(__fdividef(h0 - hk, -b), 0.f), smax) : smax;
+        }
+    }
+    if (bi >= P.n_bands - 1) return smax;
+    const float hk = lo[bi + 1];
+    if (SPH) {
+        float c = fmaxf((hk - h0) * (2.f * P.R + hk + h0), 0.f);
+        float sq = fast_sqrt(fmaf(b, b, c));
+        return fminf(b > 0.f ? __fdividef(c, b + sq) : sq - b, smax);
+    }
+    return fminf(fmaxf(__fdividef(hk - h0, b), 0.f), smax);
 }
 
 #ifndef ERTB_FLUSH_COLLECTIVE_MIN
@@ -121,10 +164,12 @@ __device__ __noinline__ void film_flush_warp(const ErtbParams &P, unsigned lane,
 // COLL: collective mid-kernel film flushes, for renders whose chunks are small (many pixel
 // switches per lane). It is a template parameter because any call inside the scheduler loop
 // perturbs the register allocation of the walk phase (-3..7 % on the C2 headline, measured).
-template <bool SPH, bool STATS, bool POL, bool PW = false, bool COLL = false>
+template <bool SPH, bool STATS, bool POL, bool PW = false, bool COLL = false, bool BANDS = false>
 __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
+    static_assert(!(PW && BANDS), "the piecewise integrator has no null collisions");
     static_assert(!(PW && SPH), "the piecewise medium is a plane-parallel layer stack");
-    constexpr int NF = POL ? PF_COUNT_POL : PF_COUNT;
+    constexpr int NF = (POL ? PF_COUNT_POL : PF_COUNT) + (BANDS ? 2 : 0);
+    constexpr int PF_SB = NF - 2, PF_BAND = NF - 1; // (BANDS only)
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) unsigned long long mbar;
     float *tb = smem; // table blob first
@@ -229,6 +274,9 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                 rng.state = (unsigned long long) FLDU(PF_RNG0, slot) | ((unsigned long long) FLDU(PF_RNG1, slot) << 32);
                 rng.inc = (unsigned long long) FLDU(PF_INC0, slot) | ((unsigned long long) FLDU(PF_INC1, slot) << 32);
             }
+            float sb = 0.f;     // BANDS: where the current band ends along the segment
+            unsigned band = 0u; //        band index | descending << 8
+            if (BANDS && have) { sb = FLD(PF_SB, slot); band = FLDU(PF_BAND, slot); }
             unsigned mode = have ? (flags & PFL_MODE_MASK) : PM_DEAD;
             const int keep = max(1, min(P.twi, n_sel));
             // depth is constant during a walk: hoist the Russian-roulette / max-depth predicates
@@ -247,10 +295,29 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                     }
                     if (alive) {
                         if (STATS) { if (is_main) st_main++; else st_nee++; }
+                        float inv_maj = P.inv_majorant, bratio = 1.f;
+                        if (BANDS) {
+                            if (s == 0.f) { // a new segment (every event starts one with s = 0): band of its origin
+                                int bi = (int) tb[P.off_band_of + layer_of(P, h0)];
+                                bool down = b < 0.f;
+                                sb = band_exit<SPH>(P, tb, h0, b, bi, down, smax);
+                                band = (unsigned) bi | (down ? 256u : 0u);
+                            }
+                            bratio = tb[P.off_band_ratio + (band & 255u)];
+                            inv_maj *= bratio;
+                        }
                         float u = pcg_float(rng);
-                        s += -__logf(1.f - u) * P.inv_majorant;
+                        s += -__logf(1.f - u) * inv_maj;
                         bool nee_over = false;
-                        if (!(s < smax)) {
+                        if (BANDS && !(s < sb) && sb < smax) {
+                            // the flight leaves the band: stop at the boundary, carry on with the next band's
+                            // majorant (no event; free flights are memoryless)
+                            bool down = (band & 256u) != 0u;
+                            int bi = (int) (band & 255u) + (down ? -1 : 1);
+                            s = sb > 0.f ? sb : 1e-30f; // (s = 0 marks a new segment)
+                            sb = band_exit<SPH>(P, tb, h0, b, bi, down, smax);
+                            band = (unsigned) bi | (down ? 256u : 0u);
+                        } else if (!(s < smax)) {
                             if (is_main) {
                                 mode = (flags & PFL_KIND) ? PM_SURF : PM_IDLE; // ground hit / left through the TOA
                             } else {
@@ -262,6 +329,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                         } else {
                             float h = altitude_at<SPH>(P, h0, b, s);
                             float preal = tb[P.off_preal + layer_of(P, h)];
+                            if (BANDS) preal = fminf(preal * bratio, 1.f); // relative to the band's majorant
                             if (is_main) {
                                 if (pcg_float(rng) >= 1.f - preal) mode = PM_SCAT; // real collision
                                 else flags |= PFL_LAST_NULL;
@@ -287,6 +355,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                 FLD(PF_B, slot) = b; FLD(PF_S, slot) = s; FLD(PF_SMAX, slot) = smax;
                 FLD(PF_THR, slot) = thr; FLD(PF_WNEE, slot) = wnee; FLD(PF_RES, slot) = res;
                 FLDU(PF_RNG0, slot) = (unsigned) rng.state; FLDU(PF_RNG1, slot) = (unsigned) (rng.state >> 32);
+                if (BANDS) { FLD(PF_SB, slot) = sb; FLDU(PF_BAND, slot) = band; }
             }
             __syncwarp();
             continue;

@@ -483,6 +483,75 @@ def config_c4(spp: int = 1 << 22, lai: float = 3.0, radius: float = 0.1, size=(2
     )
 
 
+def polarized_aerosol_table(g: float = 0.65, n_back: int = 33, n_fwd: int = 41) -> dict:
+    """Synthetic `tabphase_polarized` aerosol (HG-shaped m11 on irregular nodes, Rayleigh-like
+    linear polarisation, damped; ERP/phase/tabphase_polarized.cpp:228-296) as comma-joined strings."""
+    mu = np.concatenate([np.linspace(-1, 0.6, n_back), np.linspace(0.6, 1.0, n_fwd)[1:]])
+    m11 = (1.0 - g * g) / (4.0 * np.pi * (1.0 + g * g - 2.0 * g * mu) ** 1.5)
+    pol = -0.4 * (1 - mu**2) / (1 + mu**2)
+    fmt = lambda a: ",".join(map(str, a))  # noqa: E731
+    return {
+        "type": "tabphase_polarized", "nodes": fmt(mu), "m11": fmt(m11), "m12": fmt(pol * m11),
+        "m22": fmt(0.9 * m11), "m33": fmt(0.8 * mu * m11), "m34": fmt(0.1 * (1 - mu**2) * m11),
+        "m44": fmt(0.7 * mu * m11),
+    }
+
+
+def config_c5(spp: int = 1 << 20, n_vza: int = 1, w_nm: float = 550.0, n_layers: int = 1200,
+              geometry: str = "spherical_shell") -> dict:
+    """C5: polarized (Stokes) transport, `ocean_legacy` surface under the AFGL1986-shaped molecular
+    atmosphere (`rayleigh_polarized`) + aerosol layer (`tabphase_polarized`); one context of the
+    400-1000 nm sweep (see :func:`spectral_update_map_c5`)."""
+    vza = np.linspace(-60.0, 60.0, n_vza) if n_vza > 1 else np.array([30.0])
+    sensor = {"type": "mdistant", "vza": vza, "vaa": 40.0}
+    if geometry == "spherical_shell":
+        # Keep the target away from (0, 0, R): that is the pole of the sphere's (u, v) parametrisation,
+        # where dp_du = (-y, x, 0) vanishes (MI/src/shapes/sphere.cpp:703-720) and the shading frame an
+        # anisotropic BSDF (the ocean's wind direction) refers to is decided by rounding noise.
+        y = 3.0e5
+        sensor["target"] = [0.0, y, float(np.sqrt(EARTH_RADIUS**2 - y * y))]
+    d = atmosphere_scene(
+        geometry=geometry, atmosphere="afgl", n_layers=n_layers, aerosol=True, aerosol_phase="hg", w_nm=w_nm,
+        phase={"type": "rayleigh_polarized", "depolarization": 0.0279}, stokes=True, sza=35.0, saa=0.0,
+        surface={"type": "ocean_legacy", "wavelength": w_nm, "wind_speed": 5.0, "wind_direction": 30.0,
+                 "chlorinity": 19.0, "pigmentation": 0.3, "shadowing": True},
+        sensor=sensor, spp=spp)
+    d["phase_atmosphere"]["phase_1"] = polarized_aerosol_table()
+    return d
+
+
+def spectral_update_map_c5(n_layers: int = 1200, spherical: bool = True) -> KernelSceneParameterMap:
+    """C5 sweep: per-context sigma_t / albedo / blend weight / irradiance and the ocean BSDF wavelength
+    (`scenes/bsdfs/_ocean_legacy.py`: `wavelength` is a spectral scene parameter)."""
+    from .kernel._scene import BSDF, PhaseFunction
+
+    rel = "volume.data" if spherical else "data"
+
+    def mix(ctx):
+        z, st_m, al_m = afgl_like_profile(n_layers, TOA, ctx.si.w)
+        st_a, al_a = aerosol_layer(z)
+        ss_m, ss_a = st_m.astype(np.float64) * al_m, st_a * al_a
+        tot = st_m + st_a
+        with np.errstate(invalid="ignore", divide="ignore"):
+            w = np.where(ss_m + ss_a > 0, ss_a / (ss_m + ss_a), 0.0)
+        return tot.astype(np.float32), ((ss_m + ss_a) / tot).astype(np.float32), w.astype(np.float32)
+
+    umap = spectral_update_map(n_layers, spherical)
+    umap.data["medium_atmosphere.sigma_t"] = SceneParameter(
+        lambda ctx: mix(ctx)[0], KernelSceneParameterFlags.SPECTRAL,
+        search=SearchSceneParameter(Medium, "medium_atmosphere", f"sigma_t.{rel}"))
+    umap.data["medium_atmosphere.albedo"] = SceneParameter(
+        lambda ctx: mix(ctx)[1], KernelSceneParameterFlags.SPECTRAL,
+        search=SearchSceneParameter(Medium, "medium_atmosphere", f"albedo.{rel}"))
+    umap.data["phase_atmosphere.weight"] = SceneParameter(
+        lambda ctx: mix(ctx)[2], KernelSceneParameterFlags.SPECTRAL,
+        search=SearchSceneParameter(PhaseFunction, "phase_atmosphere", f"weight.{rel}"))
+    umap.data["surface_bsdf.wavelength"] = SceneParameter(
+        lambda ctx: float(ctx.si.w), KernelSceneParameterFlags.SPECTRAL,
+        search=SearchSceneParameter(BSDF, "surface_bsdf", "wavelength"))
+    return umap
+
+
 def spectral_update_map(n_layers: int = 1200, spherical: bool = True) -> KernelSceneParameterMap:
     """
     Update map equivalent to ``atmosphere/_core.py:777-805`` +

@@ -226,7 +226,7 @@ typedef struct ertb_render_stats {
     uint64_t n_surface;      /* surface (non-null) interactions */
     double device_ms;        /* kernel time measured with CUDA events on the launch stream */
     int32_t n_launches;      /* kernels launched by this call */
-    int32_t _pad;
+    int32_t n_bands;         /* altitude bands of the majorant (1 = the reference's global majorant) */
 } ertb_render_stats;
 
 typedef struct ertb_scene ertb_scene; /* opaque */

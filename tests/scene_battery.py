@@ -13,16 +13,7 @@ def polarized_aerosol_scene() -> dict:
                                 phase={"type": "rayleigh_polarized"}, stokes=True, meridian_align=False,
                                 sza=30.0, saa=0.0, surface={"type": "diffuse", "reflectance": 0.05},
                                 sensor={"type": "mdistant", "vza": [-50.0, -10.0, 40.0], "vaa": 60.0})
-    mu = np.concatenate([np.linspace(-1, 0.6, 33), np.linspace(0.6, 1.0, 41)[1:]])
-    g = 0.65
-    m11 = (1.0 - g * g) / (4.0 * np.pi * (1.0 + g * g - 2.0 * g * mu) ** 1.5)
-    pol = -0.4 * (1 - mu**2) / (1 + mu**2)        # Rayleigh-like linear polarisation, damped
-    fmt = lambda a: ",".join(map(str, a))  # noqa: E731
-    d["phase_atmosphere"]["phase_1"] = {
-        "type": "tabphase_polarized", "nodes": fmt(mu), "m11": fmt(m11), "m12": fmt(pol * m11),
-        "m22": fmt(0.9 * m11), "m33": fmt(0.8 * mu * m11), "m34": fmt(0.1 * (1 - mu**2) * m11),
-        "m44": fmt(0.7 * mu * m11),
-    }
+    d["phase_atmosphere"]["phase_1"] = scenes.polarized_aerosol_table()
     return d
 
 
@@ -105,6 +96,8 @@ def battery() -> dict:
                                 surface={"type": "ocean_legacy", "wavelength": 550.0, "wind_speed": 5.0,
                                          "wind_direction": 30.0, "shadowing": True},
                                 sensor={"type": "mdistant", "vza": [-60.0, -40.0, -20.0, 20.0, 50.0], "vaa": 25.0}),
+        # BASELINE C5 at reduced size: polarized ocean + molecular + polarized aerosol, one band of the sweep
+        "c5_polarized_ocean_aerosol_reduced": scenes.config_c5(spp=16, n_vza=4, w_nm=865.0, n_layers=120),
         # integrator options
         "volpathmis_thick": S(geometry="plane_parallel", atmosphere="homogeneous", integrator="volpathmis",
                               homogeneous_sigma_t=3.0 / scenes.TOA, homogeneous_albedo=0.95, sensor=VZA5,
