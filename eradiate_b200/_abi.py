@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -41,6 +41,8 @@ SENSOR_MDISTANT = 0
 SENSOR_HDISTANT = 1
 SENSOR_DISTANTFLUX = 2
 SENSOR_PERSPECTIVE = 3
+SENSOR_MPDISTANT = 4
+SENSOR_MRADIANCEMETER = 5
 
 # enum ertb_target_type
 TARGET_NONE = 0
@@ -97,6 +99,7 @@ class SensorDesc(C.Structure):
         ("far_clip", C.c_double),
         ("in_medium", C.c_int32),
         ("_pad1", C.c_int32),
+        ("origins", c_double_p),
     ]
 
 

@@ -229,8 +229,21 @@ __device__ __forceinline__ bool canopy_primary(const ErtbParams &P, unsigned pix
         maxt = (S.far_clip - S.near_clip) * inv_z;
         return true;
     }
+    if (S.type == ERTB_SENSOR_MRADIANCEMETER) { // mradiancemeter.cpp:147-172: explicit rays
+        const float4 *t4 = reinterpret_cast<const float4 *>(S.table) + 2u * pix;
+        float4 a = __ldg(t4), c4 = __ldg(t4 + 1);
+        d = mk3(a.w, c4.x, c4.y);
+        p[0] = S.origins[3u * pix]; p[1] = S.origins[3u * pix + 1]; p[2] = S.origins[3u * pix + 2];
+        return c4.z != 0.f;
+    }
     f3 fs = mk3(1.f, 0.f, 0.f), ft = mk3(0.f, 1.f, 0.f);
-    if (S.type == ERTB_SENSOR_MDISTANT) {
+    if (S.type == ERTB_SENSOR_MPDISTANT) { // mpdistant.cpp:214-262: the film sample picks the target point
+        const float *M = S.to_world;
+        d = normalize3(mk3(M[2], M[5], M[8]));
+        fs = mk3(M[0], M[3], M[6]);
+        ft = mk3(M[1], M[4], M[7]);
+        ax = fx; ay = fy;
+    } else if (S.type == ERTB_SENSOR_MDISTANT) {
         const float4 *t4 = reinterpret_cast<const float4 *>(S.table) + 2u * pix;
         float4 a = __ldg(t4), c4 = __ldg(t4 + 1);
         d = mk3(a.w, c4.x, c4.y);
@@ -372,7 +385,7 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 thr = 1.f; res = 0.f; depth = 0; on_inst = on_disk = -1;
                 const bool valid = canopy_primary(P, pix, rng, p, d, wray, maxt);
                 first_segment = true;
-                if (P.sensor.type == ERTB_SENSOR_PERSPECTIVE) {
+                if (P.sensor.type == ERTB_SENSOR_PERSPECTIVE || P.sensor.type == ERTB_SENSOR_MRADIANCEMETER) {
                     in_medium = P.sensor.in_medium != 0;
                 } else if (valid) {
                     // distant sensors sit outside the scene: bring the origin down to where the ray

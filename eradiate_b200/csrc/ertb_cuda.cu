@@ -47,6 +47,8 @@ struct HostPhase {
 struct HostSensor {
     ertb_sensor_desc desc;
     std::vector<double> directions; // normalised
+    std::vector<double> origins;    // mradiancemeter
+    double *d_origins = nullptr;    // device copy (3D kernel)
     float *d_table = nullptr;       // device primary-ray table
     double ray_offset = 0.0;
     int use_table = 0;
@@ -223,7 +225,9 @@ struct ertb_scene {
     std::vector<double> instance_offset;
     ErtbCanopy canopy;          // device pointers (zero-initialised: no canopy)
     void *d_canopy[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
-    bool needs_3d = false;      // canopy or perspective sensor: rendered by ertb_canopy_kernel
+    bool needs_3d = false;      // canopy / perspective / mpdistant / mradiancemeter in a plane-parallel scene:
+                                // rendered by ertb_canopy_kernel
+    bool needs_legacy = false;  // mpdistant / mradiancemeter in a spherical shell: the register-resident kernel
 };
 
 static int build_canopy(ertb_scene *S) {
@@ -640,6 +644,54 @@ static int build_sensor(ertb_scene *S, HostSensor &hs) {
     hs.ray_offset = sensor_ray_offset(S, sd);
     const int npix = sd.width * sd.height;
     const bool sph = S->geometry == ERTB_GEOM_SPHERICAL_SHELL;
+    if (sd.type == ERTB_SENSOR_MRADIANCEMETER) {
+        // mradiancemeter.cpp:147-172: explicit rays. Per pixel [n0 | d | class | h0]: class 1 = enters the
+        // atmosphere at n0 (h0 = H), 2 = reaches the ground through vacuum at n0, 3 = starts INSIDE the
+        // atmosphere at altitude h0 above n0's foot point, 0 = sees nothing
+        if (sd.n_directions != sd.width || sd.height != 1) return set_error("Film size must be [n_radiancemeters, 1]");
+        hs.use_table = 1;
+        std::vector<float> table((size_t) npix * 8, 0.f);
+        const double Rg = S->surface_z, Rt = S->has_medium ? S->medium_top : S->surface_z;
+        for (int i = 0; i < npix; ++i) {
+            const double *o = &hs.origins[3 * (size_t) i];
+            const double dx = hs.directions[3 * i], dy = hs.directions[3 * i + 1], dz = hs.directions[3 * i + 2];
+            float *t = &table[(size_t) i * 8];
+            t[3] = (float) dx; t[4] = (float) dy; t[5] = (float) dz;
+            t[2] = 1.f;
+            if (sph) {
+                const double oo = o[0] * o[0] + o[1] * o[1] + o[2] * o[2], r = sqrt(oo), b = o[0] * dx + o[1] * dy + o[2] * dz;
+                if (r < Rg) continue;
+                if (S->has_medium && r < Rt) {
+                    if (!sd.in_medium) return set_error("mradiancemeter: an origin lies inside the atmosphere but the sensor has no medium");
+                    t[0] = (float) (o[0] / r); t[1] = (float) (o[1] / r); t[2] = (float) (o[2] / r);
+                    t[6] = 3.f; t[7] = (float) (r - Rg);
+                    continue;
+                }
+                if (sd.in_medium) return set_error("mradiancemeter: the sensor has a medium but an origin lies outside the atmosphere");
+                const double Rs = S->has_medium ? Rt : Rg;
+                const double disc = b * b - (oo - Rs * Rs);
+                if (disc < 0.0 || b > 0.0) continue;
+                const double t0 = -b - sqrt(disc);
+                t[0] = (float) ((o[0] + t0 * dx) / Rs); t[1] = (float) ((o[1] + t0 * dy) / Rs); t[2] = (float) ((o[2] + t0 * dz) / Rs);
+                t[6] = S->has_medium ? 1.f : 2.f; t[7] = S->has_medium ? (float) (Rt - Rg) : 0.f;
+            } else {
+                const double h = o[2] - Rg, H = Rt - Rg;
+                if (h < 0.0) continue;
+                if (S->has_medium && h < H) {
+                    if (!sd.in_medium) return set_error("mradiancemeter: an origin lies inside the atmosphere but the sensor has no medium");
+                    t[6] = 3.f; t[7] = (float) h;
+                } else {
+                    if (sd.in_medium) return set_error("mradiancemeter: the sensor has a medium but an origin lies outside the atmosphere");
+                    if (dz < 0.0) { t[6] = S->has_medium ? 1.f : 2.f; t[7] = (float) H; }
+                }
+            }
+        }
+        CUDA_TRY(cudaMalloc(&hs.d_table, table.size() * sizeof(float)));
+        CUDA_TRY(cudaMemcpy(hs.d_table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&hs.d_origins, hs.origins.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(hs.d_origins, hs.origins.data(), hs.origins.size() * sizeof(double), cudaMemcpyHostToDevice));
+        return 0;
+    }
     if (sd.type == ERTB_SENSOR_MDISTANT) {
         if (sd.n_directions != sd.width || sd.height != 1)
             return set_error("Film size must be [sensor_count, 1]");
@@ -699,6 +751,8 @@ static void fill_sensor_params(const ertb_scene *S, const HostSensor &hs, ErtbSe
     o.bs_radius = fmax(eps, S->bs_radius * (1.0 + eps));
     o.ray_offset = hs.ray_offset;
     o.flux_norm = (float) (2.0 * M_PI / (double) (sd.width * sd.height));
+    o.origins = hs.d_origins;
+    if (sd.type == ERTB_SENSOR_MRADIANCEMETER) o.in_medium = sd.in_medium;
     if (sd.type == ERTB_SENSOR_PERSPECTIVE) {
         o.cam_origin[0] = sd.to_world[3]; o.cam_origin[1] = sd.to_world[7]; o.cam_origin[2] = sd.to_world[11];
         o.tan_half_fov = (float) tan(0.5 * sd.x_fov_deg * M_PI / 180.0);
@@ -731,8 +785,10 @@ int ertb_device_count(void) {
 void ertb_scene_destroy(ertb_scene *S) {
     if (!S) return;
     cudaSetDevice(S->device);
-    for (auto &hs : S->sensors)
+    for (auto &hs : S->sensors) {
         if (hs.d_table) cudaFree(hs.d_table);
+        if (hs.d_origins) cudaFree(hs.d_origins);
+    }
     slot_release(S->main);
     for (auto &T : S->slots) slot_release(T);
     if (S->batch.d_accum) cudaFree(S->batch.d_accum);
@@ -864,6 +920,16 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
         S->needs_3d = true;
     }
     for (int i = 0; i < D->n_sensors; ++i)
+        if (D->sensors[i].type == ERTB_SENSOR_MPDISTANT || D->sensors[i].type == ERTB_SENSOR_MRADIANCEMETER) {
+            if (D->geometry == ERTB_GEOM_PLANE_PARALLEL) {
+                if (S->polarized) { delete S; return set_error("mpdistant / mradiancemeter: polarized scenes are not supported"); }
+                S->needs_3d = true;
+            } else {
+                if (S->polarized) { delete S; return set_error("mpdistant / mradiancemeter: polarized scenes are not supported"); }
+                S->needs_legacy = true;
+            }
+        }
+    for (int i = 0; i < D->n_sensors; ++i)
         if (D->sensors[i].type == ERTB_SENSOR_PERSPECTIVE) {
             if (D->geometry != ERTB_GEOM_PLANE_PARALLEL || S->polarized) {
                 delete S;
@@ -886,7 +952,12 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
         hs.desc = D->sensors[i];
         const ertb_sensor_desc &sd = hs.desc;
         if (sd.width < 1 || sd.height < 1) { ertb_scene_destroy(S); return set_error("invalid film size"); }
-        if (sd.type == ERTB_SENSOR_MDISTANT) {
+        if (sd.type == ERTB_SENSOR_MRADIANCEMETER && (!sd.origins || !sd.directions || sd.n_directions < 1)) {
+            ertb_scene_destroy(S);
+            return set_error("mradiancemeter: origins / directions missing");
+        }
+        if (sd.type == ERTB_SENSOR_MRADIANCEMETER) hs.origins.assign(sd.origins, sd.origins + 3 * (size_t) sd.n_directions);
+        if (sd.type == ERTB_SENSOR_MDISTANT || sd.type == ERTB_SENSOR_MRADIANCEMETER) {
             if (!sd.directions || sd.n_directions < 1) { ertb_scene_destroy(S); return set_error("mdistant: directions missing"); }
             hs.directions.resize(3 * (size_t) sd.n_directions);
             for (int k = 0; k < sd.n_directions; ++k) {
@@ -908,11 +979,12 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
                 return set_error("perspective: the sensor's medium does not match its position "
                                  "(experiments/_canopy_atmosphere.py:248-258 sets it for cameras inside the atmosphere)");
             }
-        } else if (sd.type != ERTB_SENSOR_HDISTANT && sd.type != ERTB_SENSOR_DISTANTFLUX) {
+        } else if (sd.type != ERTB_SENSOR_HDISTANT && sd.type != ERTB_SENSOR_DISTANTFLUX && sd.type != ERTB_SENSOR_MPDISTANT) {
             ertb_scene_destroy(S);
             return set_error("unsupported sensor type");
         }
         hs.desc.directions = nullptr;
+        hs.desc.origins = nullptr;
         S->sensors.push_back(hs);
         if (build_sensor(S, S->sensors.back())) { ertb_scene_destroy(S); return 1; }
     }
@@ -1023,6 +1095,10 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     const bool c3d = S->needs_3d; // canopy / perspective camera: the 3D kernel (ertb_canopy.cuh)
     if (pol || pw) use_pool = true; // the polarized and the piecewise paths exist in the pool kernel only
     if (c3d) use_pool = false;
+    if (S->needs_legacy) {
+        if (pol || pw) return set_error("mpdistant / mradiancemeter: unsupported with this integrator in a spherical shell");
+        use_pool = false;
+    }
     const int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK);
     const bool bands = S->base.n_bands > 1;
     size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol, bands && !pw) : (size_t) S->base.blob_bytes;
@@ -1505,7 +1581,20 @@ __global__ void kat_sensor_ray_kernel(ErtbParams P, double ray_offset, size_t n,
         weight[i] = 1.f;
         return;
     }
-    if (S.type == ERTB_SENSOR_MDISTANT) {
+    if (S.type == ERTB_SENSOR_MRADIANCEMETER) {
+        int idx = min((int) (fx * (float) S.width), S.width - 1);
+        const float *t = S.table + 8 * (size_t) idx;
+        for (int k = 0; k < 3; ++k) { origin[3 * i + k] = S.origins[3 * idx + k]; dir[3 * i + k] = t[3 + k]; }
+        weight[i] = 1.f;
+        return;
+    }
+    if (S.type == ERTB_SENSOR_MPDISTANT) {
+        const float *M = S.to_world;
+        d = normalize3(mk3(M[2], M[5], M[8]));
+        fs = mk3(M[0], M[3], M[6]);
+        ft = mk3(M[1], M[4], M[7]);
+        ax = fx; ay = fy;
+    } else if (S.type == ERTB_SENSOR_MDISTANT) {
         int idx = min((int) (fx * (float) S.width), S.width - 1);
         const float *t = S.table + 8 * (size_t) idx;
         d = mk3(t[3], t[4], t[5]);

@@ -52,7 +52,8 @@ struct ErtbSensor {
     // perspective (perspective.cpp:200-236): pinhole at cam_origin, to_world = camera rotation
     double cam_origin[3];
     float tan_half_fov, aspect, near_clip, far_clip;
-    int in_medium;     // the camera sits inside the atmosphere
+    int in_medium;     // the camera / the radiancemeters sit inside the atmosphere
+    const double *origins; // mradiancemeter: [n][3] ray origins (3D kernel; the 1D kernels use `table`)
 };
 
 // Explicit canopy (ertb_canopy.cuh): two-level BVH over translated instances of disk-leaf groups.

@@ -386,19 +386,27 @@ __global__ void __launch_bounds__(ERTB_BLOCK, ERTB_MINB) ertb_render_kernel(cons
                 // ---- primary ray (render_sample, integrator.cpp:449-520) ----
                 const ErtbSensor &S = P.sensor;
                 int valid = 1;
+                float h_start = P.H;
                 if (S.use_table) {
                     const float4 *t4 = reinterpret_cast<const float4 *>(S.table) + 2u * pix;
                     float4 a = __ldg(t4), c4 = __ldg(t4 + 1);
                     n0 = mk3(a.x, a.y, a.z);
                     d = mk3(a.w, c4.x, c4.y);
                     valid = (int) c4.z;
+                    h_start = c4.w; // mradiancemeter: altitude of an origin inside the atmosphere (class 3)
                 } else {
                     unsigned px = pix % (unsigned) S.width, py = pix / (unsigned) S.width;
                     float fx = __fdividef((float) px + pcg_float(rng), (float) S.width);
                     float fy = __fdividef((float) py + pcg_float(rng), (float) S.height);
                     float ax = pcg_float(rng), ay = pcg_float(rng);
                     f3 fs = mk3(1.f, 0.f, 0.f), ft = mk3(0.f, 1.f, 0.f);
-                    if (S.type == ERTB_SENSOR_MDISTANT) {
+                    if (S.type == ERTB_SENSOR_MPDISTANT) { // mpdistant.cpp:214-262
+                        const float *M = S.to_world;
+                        d = normalize3(mk3(M[2], M[5], M[8]));
+                        fs = mk3(M[0], M[3], M[6]);
+                        ft = mk3(M[1], M[4], M[7]);
+                        ax = fx; ay = fy;
+                    } else if (S.type == ERTB_SENSOR_MDISTANT) {
                         const float4 *t4 = reinterpret_cast<const float4 *>(S.table) + 2u * pix;
                         float4 a = __ldg(t4), c4 = __ldg(t4 + 1);
                         d = mk3(a.w, c4.x, c4.y);
@@ -445,8 +453,12 @@ __global__ void __launch_bounds__(ERTB_BLOCK, ERTB_MINB) ertb_render_kernel(cons
                         valid = !(d.z < 0.f) || oz < 0.0 ? 0 : (oz >= (double) P.H ? 1 : 2);
                     }
                 }
-                if (!SPH && !(d.z < 0.f)) valid = 0; // upward-looking rays never see the ground
-                h0 = P.H;
+                if (valid == 3) valid = 1; // starts inside the atmosphere at h_start, looking anywhere
+                else {
+                    if (!SPH && !(d.z < 0.f)) valid = 0; // upward-looking rays never see the ground
+                    h_start = P.H;
+                }
+                h0 = h_start;
                 mode = MODE_SETUP_MAIN;
                 if (valid == 0) thr = 0.f; // L = 0, still counted as a sample
                 if (valid == 2) { vacuum = true; h0 = 0.f; s = 0.f; smax = 0.f; mode = MODE_EV_SURFACE; }

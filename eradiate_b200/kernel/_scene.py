@@ -23,7 +23,7 @@ import typing as t
 import numpy as np
 
 from .. import _abi
-from ._types import to_grid, to_matrix
+from ._types import ScalarTransform4f, to_grid, to_matrix
 
 # ------------------------------------------------------------------------------
 #                               dict utilities
@@ -231,7 +231,7 @@ _SUPPORTED = {
     "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "null", "bilambertian"},
     "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
               "rayleigh_polarized", "tabphase_polarized"},
-    "sensor": {"mdistant", "hdistant", "distantflux", "perspective"},
+    "sensor": {"mdistant", "hdistant", "distantflux", "perspective", "mpdistant", "mradiancemeter"},
     "volume": {"gridvolume", "sphericalcoordsvolume", "constvolume"},
 }
 _KIND_OF = {ty: kind for kind, types in _SUPPORTED.items() for ty in types}
@@ -570,7 +570,7 @@ class _Loader:
         s.children["sampler"] = sampler
         s.in_medium = False
         if "medium" in d:
-            if ty != "perspective":
+            if ty not in ("perspective", "mradiancemeter"):
                 raise RuntimeError("distant sensors inside a medium are unsupported")
             s.in_medium = True
         s.ray_offset = float(d.get("ray_offset", -1.0))
@@ -601,6 +601,37 @@ class _Loader:
             a = s.to_world[:3, :3]
             if not np.allclose(a.T @ a, np.eye(3), atol=1e-6):
                 raise RuntimeError("Scale factors in the camera-to-world transformation are not allowed!")
+        if ty == "mradiancemeter":  # ERP/sensors/mradiancemeter.cpp:72-133
+            if "to_world" in d:
+                raise RuntimeError(
+                    "This sensor is specified through a set of origin and direction values and cannot "
+                    "use the to_world transform."
+                )
+            org = _parse_floats(d["origins"], "origins")
+            dirs = _parse_floats(d["directions"], "directions")
+            if org.size % 3 != 0:
+                raise RuntimeError(f"Invalid specification! Number of parameters {org.size}, is not a multiple of three.")
+            if org.size != dirs.size:
+                raise RuntimeError(
+                    f"Invalid specification! Number of parameters for origins and directions ({org.size}, "
+                    f"{dirs.size}) are not equal.")
+            s.origins, s.directions = org.reshape(-1, 3), dirs.reshape(-1, 3)
+            if (film.width, film.height) != (s.origins.shape[0], 1):
+                raise RuntimeError(
+                    f"Film size must be [n_radiancemeters, 1]. Expected [{s.origins.shape[0]}, 1], "
+                    f"found: [{film.width}, {film.height}]")
+        if ty == "mpdistant":  # ERP/sensors/mpdistant.cpp:171-205
+            if "direction" in d:
+                if "to_world" in d:
+                    raise RuntimeError("Only one of the parameters 'direction' and 'to_world' can be specified at the same time!")
+                v = np.asarray(d["direction"], dtype=np.float64)
+                v = v / np.linalg.norm(v)
+                sign = np.copysign(1.0, v[2])  # coordinate_system(direction) -> (s, t): up = t
+                a, b = -1.0 / (sign + v[2]), v[0] * v[1] * (-1.0 / (sign + v[2]))
+                up = np.array([b, sign + v[1] * v[1] * a, -v[1]])
+                s.to_world = ScalarTransform4f().look_at([0.0, 0.0, 0.0], v, up).matrix
+            if float(d.get("target_radius", -1.0)) >= 0.0:
+                raise RuntimeError("mpdistant: 'target_radius' is unsupported")
         if ty == "mdistant":
             if "to_world" in d:
                 raise RuntimeError(
@@ -824,6 +855,9 @@ class FlatScene:
         forced = getattr(sc, "_force_polarized", None)
         if forced is not None:
             self.polarized = bool(forced)
+        for sn in self.sensors:
+            if sn.type in ("mpdistant", "mradiancemeter") and self.polarized:
+                raise RuntimeError(f"{sn.type}: polarized scenes are not supported with this sensor")
         if self.polarized and self.integrator.kernel_type == "volpathmis":
             # volpathmis.cpp:130-132
             raise RuntimeError("This integrator currently does not support polarized mode!")
@@ -1042,12 +1076,19 @@ class FlatScene:
                 "hdistant": _abi.SENSOR_HDISTANT,
                 "distantflux": _abi.SENSOR_DISTANTFLUX,
                 "perspective": _abi.SENSOR_PERSPECTIVE,
+                "mpdistant": _abi.SENSOR_MPDISTANT,
+                "mradiancemeter": _abi.SENSOR_MRADIANCEMETER,
             }[s.type]
+            if s.type == "mradiancemeter":
+                org = np.ascontiguousarray(s.origins, dtype=np.float64)
+                keep.append(org)
+                sd.origins = org.ctypes.data_as(_abi.c_double_p)
+                sd.in_medium = int(s.in_medium)
             if s.type == "perspective":
                 sd.x_fov_deg, sd.near_clip, sd.far_clip = s.x_fov, s.near_clip, s.far_clip
                 sd.in_medium = int(s.in_medium)
             sd.width, sd.height = s.film().width, s.film().height
-            if s.type == "mdistant":
+            if s.type in ("mdistant", "mradiancemeter"):
                 dirs = np.ascontiguousarray(s.directions, dtype=np.float64)
                 keep.append(dirs)
                 sd.n_directions = dirs.shape[0]

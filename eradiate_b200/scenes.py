@@ -396,6 +396,20 @@ def _sensor_dict(sensor: dict, target, spp: int) -> dict:
         view = angles_to_direction(np.abs(vza), az)
         out["directions"] = ",".join(map(str, (-view).ravel(order="C")))
         width, height = vza.size, 1
+    elif ty == "mradiancemeter":  # scenes/measure/_multi_radiancemeter.py:87-96
+        org = np.asarray(sensor.pop("origins"), dtype=np.float64).reshape(-1, 3)
+        dirs = np.asarray(sensor.pop("directions"), dtype=np.float64).reshape(-1, 3)
+        out["origins"] = ",".join(map(str, org.ravel(order="C")))
+        out["directions"] = ",".join(map(str, dirs.ravel(order="C")))
+        if "medium" in sensor:
+            out["medium"] = sensor.pop("medium")
+        width, height = org.shape[0], 1
+        target = None
+    elif ty == "mpdistant":  # scenes/measure/_distant.py (MultiPixelDistantMeasure): one direction, an image
+        res = sensor.pop("film_resolution", (8, 8))
+        width, height = int(res[0]), int(res[1])
+        view = angles_to_direction(float(sensor.pop("vza", 0.0)), float(sensor.pop("vaa", 0.0)))
+        out["direction"] = [float(v) for v in -np.asarray(view).ravel()]
     elif ty == "perspective":  # scenes/measure/_perspective.py:150-165
         res = sensor.pop("film_resolution", (32, 32))
         width, height = int(res[0]), int(res[1])
@@ -413,10 +427,12 @@ def _sensor_dict(sensor: dict, target, spp: int) -> dict:
         if "to_world" in sensor:
             out["to_world"] = sensor.pop("to_world")
     tgt = sensor.pop("target", target)
-    if tgt is not None and ty != "perspective":
+    if tgt is not None and ty not in ("perspective", "mradiancemeter"):
         out["target"] = tgt
     if "ray_offset" in sensor:
         out["ray_offset"] = sensor.pop("ray_offset")
+    if "medium" in sensor:
+        out["medium"] = sensor.pop("medium")
     out["film"] = {
         "type": "hdrfilm",
         "width": width,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 8
+#define ERTB_ABI_VERSION 9
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -72,7 +72,13 @@ enum ertb_sensor_type {
     ERTB_SENSOR_MDISTANT = 0,   /* ERP/sensors/mdistant.cpp:192-242 */
     ERTB_SENSOR_HDISTANT = 1,   /* ERP/sensors/hdistant.cpp:232-275 */
     ERTB_SENSOR_DISTANTFLUX = 2, /* ERP/sensors/distantflux.cpp:148-195 */
-    ERTB_SENSOR_PERSPECTIVE = 3  /* MI/src/sensors/perspective.cpp:200-236 (pinhole; canopy scenes) */
+    ERTB_SENSOR_PERSPECTIVE = 3, /* MI/src/sensors/perspective.cpp:200-236 (pinhole; canopy scenes) */
+    /* ERP/sensors/mpdistant.cpp:214-262: ONE direction (to_world * z), the film sample picks the point of the
+     * target the ray goes through (an image of the target region seen from infinity) */
+    ERTB_SENSOR_MPDISTANT = 4,
+    /* ERP/sensors/mradiancemeter.cpp:147-172: one (origin, direction) per film column; origins may lie inside
+     * the atmosphere (`in_medium`), e.g. ground-based sky radiance */
+    ERTB_SENSOR_MRADIANCEMETER = 5
 };
 
 enum ertb_target_type {
@@ -119,8 +125,9 @@ typedef struct ertb_sensor_desc {
      * atmosphere (the `medium` reference Eradiate adds, experiments/_canopy_atmosphere.py:248-258) */
     double x_fov_deg;
     double near_clip, far_clip;
-    int32_t in_medium;
+    int32_t in_medium;     /* perspective / mradiancemeter: the sensor sits inside the atmosphere */
     int32_t _pad1;
+    const double *origins; /* mradiancemeter: 3*n ray origins (directions: `directions`, n = width) */
 } ertb_sensor_desc;
 
 /* Explicit 3D canopies (src/eradiate/scenes/biosphere/_leaf_cloud.py:1150-1175,

@@ -1136,7 +1136,21 @@ static double sensor_sample_ray(const scene_t *S, const ertb_sensor_desc *sd, do
         ray->maxt = far_t - near_t;
         return 1.0;
     }
-    if (sd->type == ERTB_SENSOR_MDISTANT) { /* mdistant.cpp:192-242 */
+    if (sd->type == ERTB_SENSOR_MRADIANCEMETER) { /* mradiancemeter.cpp:147-172 */
+        int idx = (int) (fx * sd->n_directions);
+        if (idx > sd->n_directions - 1) idx = sd->n_directions - 1;
+        ray->o = V(sd->origins[3 * idx], sd->origins[3 * idx + 1], sd->origins[3 * idx + 2]);
+        ray->d = vnormalize(V(sd->directions[3 * idx], sd->directions[3 * idx + 1], sd->directions[3 * idx + 2]));
+        ray->maxt = DBL_MAX;
+        return 1.0;
+    }
+    if (sd->type == ERTB_SENSOR_MPDISTANT) { /* mpdistant.cpp:214-262: the film sample picks the target point */
+        mat_apply_vec(sd->to_world, V(0, 0, 1), &d);
+        d = vnormalize(d);
+        mat_apply_vec(sd->to_world, V(1, 0, 0), &frame_s);
+        mat_apply_vec(sd->to_world, V(0, 1, 0), &frame_t);
+        ax = fx; ay = fy;
+    } else if (sd->type == ERTB_SENSOR_MDISTANT) { /* mdistant.cpp:192-242 */
         int idx = (int) (fx * sd->n_directions);
         if (idx > sd->n_directions - 1) idx = sd->n_directions - 1;
         d = vnormalize(V(sd->directions[3 * idx], sd->directions[3 * idx + 1], sd->directions[3 * idx + 2]));
@@ -1680,7 +1694,8 @@ int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, 
                     L = st[0];
                     for (int k = 0; k < 4; ++k) s_st[k] += w * st[k];
                 } else {
-                    L = volpath_sample(&S, &rng, ray, sd->type == ERTB_SENSOR_PERSPECTIVE && sd->in_medium, &C);
+                    int in_medium = (sd->type == ERTB_SENSOR_PERSPECTIVE || sd->type == ERTB_SENSOR_MRADIANCEMETER) && sd->in_medium;
+                    L = volpath_sample(&S, &rng, ray, in_medium, &C);
                 }
                 s_wl += w * L; s_l += L; s_l2 += L * L;
             }

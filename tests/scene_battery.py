@@ -149,6 +149,26 @@ def battery() -> dict:
                                          sensor={"type": "hdistant", "film_resolution": (2, 2)}),
         "c4_canopy_afgl_rpv_reduced": _first_sensor(scenes.config_c4(spp=16, lai=2.0, radius=0.1, size=(4.0, 4.0, 1.5),
                                                                      padding=1, n_vza=6, film=(2, 2), n_layers=200)),
+        # explicit rays (mradiancemeter) and images from infinity (mpdistant)
+        "mradiancemeter_sky_and_nadir_spherical": S(
+            n_layers=100, sza=50.0, saa=30.0, surface={"type": "diffuse", "reflectance": 0.3},
+            sensor={"type": "mradiancemeter", "medium": {"type": "ref", "id": "medium_atmosphere"},
+                    # ground-based sky radiance (looking up, off the sun) and an airborne nadir view at 10 km
+                    "origins": [[0.0, 0.0, scenes.EARTH_RADIUS + 1.0]] * 3 + [[0.0, 2.0e4, scenes.EARTH_RADIUS + 1.0e4]],
+                    "directions": [[0.0, 0.0, 1.0], [0.5, 0.0, 0.8660254], [-0.6, 0.3, 0.7416198], [0.0, 0.1, -0.9949874]]}),
+        "mradiancemeter_piecewise_aerosol_pp": S(
+            geometry="plane_parallel", n_layers=120, integrator="piecewise_volpath", aerosol=True, aerosol_phase="hg",
+            sza=40.0, sensor={"type": "mradiancemeter", "medium": {"type": "ref", "id": "medium_atmosphere"},
+                              "origins": [[0.0, 0.0, 2.0], [10.0, 0.0, 3000.0], [0.0, 5.0, 1.5e4]],
+                              "directions": [[0.3, 0.2, 0.9327379], [0.0, 0.6, -0.8], [0.0, 0.0, -1.0]]}),
+        "mradiancemeter_from_space_no_medium_flag_pp": S(
+            geometry="plane_parallel", n_layers=60,
+            sensor={"type": "mradiancemeter", "origins": [[0.0, 0.0, 2.0e5], [1.0e4, 0.0, 1.5e5]],
+                    "directions": [[0.0, 0.0, -1.0], [0.5, 0.0, -0.8660254]]}),
+        "mpdistant_canopy_image_pp": S(geometry="plane_parallel", n_layers=60, sza=30.0, canopy=CANOPY,
+                                       sensor={"type": "mpdistant", "vza": 25.0, "vaa": 60.0, "film_resolution": (3, 2)}),
+        "mpdistant_spherical": S(n_layers=100, sza=60.0, sensor={"type": "mpdistant", "vza": 40.0, "vaa": 0.0,
+                                                                "film_resolution": (2, 2)}),
         "polarized_piecewise_rayleigh_pp": S(geometry="plane_parallel", integrator="piecewise_volpath",
                                              n_layers=100, sza=40.0, saa=30.0, stokes=True,
                                              phase={"type": "rayleigh_polarized", "depolarization": 0.0279},

@@ -166,6 +166,11 @@ def test_tabphase_reference_values_on_device():
     ({"type": "distantflux", "film_resolution": (4, 2), "target": None}, "spherical_shell"),
     ({"type": "perspective", "origin": [3.0, -40.0, 25.0], "look_at": [0.0, 1.0, 0.5], "fov": 35.0,
       "film_resolution": (8, 4), "medium": {"type": "ref", "id": "medium_atmosphere"}}, "plane_parallel"),
+    ({"type": "mpdistant", "vza": 35.0, "vaa": 110.0, "film_resolution": (8, 4)}, "plane_parallel"),
+    ({"type": "mpdistant", "vza": 35.0, "vaa": 110.0, "film_resolution": (8, 4), "target": None}, "spherical_shell"),
+    ({"type": "mradiancemeter", "medium": {"type": "ref", "id": "medium_atmosphere"},
+      "origins": [[0.0, 0.0, 2.0], [10.0, 0.0, 3000.0], [0.0, 5.0, 1.5e4]],
+      "directions": [[0.3, 0.2, 0.9327379], [0.0, 0.6, -0.8], [0.0, 0.0, -1.0]]}, "plane_parallel"),
 ])
 def test_sensor_rays_match_oracle(oracle, sensor, geometry):
     sc = mi_load_dict(scenes.atmosphere_scene(geometry=geometry, n_layers=10, sensor=dict(sensor)))
@@ -557,6 +562,29 @@ def test_beer_lambert_and_single_scattering(geometry):
     mu0, muv = np.cos(np.deg2rad(sza)), np.cos(np.deg2rad(vza))
     expected = w0 * E0 / (4 * np.pi) * mu0 / (mu0 + muv) * (1 - np.exp(-tau * (1 / mu0 + 1 / muv)))
     assert abs(mean[0] - expected) < 4.0 * np.sqrt(var[0]) + 1e-5 * expected, (mean, expected)
+
+
+@pytest.mark.parametrize("geometry", ["plane_parallel", "spherical_shell"])
+def test_single_scattered_sky_radiance_from_the_ground_on_device(geometry):
+    """mradiancemeter inside the atmosphere (3D kernel in the slab, register kernel in the shell): the closed
+    form the oracle is pinned on (tests/test_sensors_oracle.py). In the shell the slab formula holds for a thin
+    atmosphere seen near the zenith (curvature enters at order H / R)."""
+    tau, w0, sza, E0 = 0.6, 0.9, 50.0, 1.8
+    mu_s = np.cos(np.radians(sza))
+    sph = geometry == "spherical_shell"
+    mus = np.array([1.0, 0.8]) if sph else np.array([1.0, 0.7, 0.35])
+    dirs = np.stack([-np.sqrt(1 - mus**2), np.zeros_like(mus), mus], axis=1)
+    z0 = scenes.EARTH_RADIUS if sph else 0.0
+    toa = 3000.0 if sph else scenes.TOA
+    sc = mi_load_dict(scenes.atmosphere_scene(
+        geometry=geometry, atmosphere="homogeneous", homogeneous_sigma_t=tau / toa, homogeneous_albedo=w0, toa=toa,
+        phase={"type": "isotropic"}, sza=sza, max_depth=2, surface={"type": "diffuse", "reflectance": 0.0},
+        sensor={"type": "mradiancemeter", "medium": {"type": "ref", "id": "medium_atmosphere"},
+                "origins": np.tile([0.0, 0.0, z0 + 0.5], (mus.size, 1)), "directions": dirs}))
+    spp = 1 << 22
+    _, mean, var, _ = gpu_render(sc, spp)
+    want = w0 * E0 / (4 * np.pi * mus) * (np.exp(-tau / mus) - np.exp(-tau / mu_s)) / (1 / mu_s - 1 / mus)
+    assert np.all(np.abs(mean - want) < 4.0 * np.sqrt(var) + (3e-3 if sph else 1e-4) * want), (mean, want)
 
 
 def test_rpv_degenerate_equals_lambertian_through_atmosphere():

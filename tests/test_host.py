@@ -194,7 +194,7 @@ def test_seed_state_matches_numpy_seed_sequence():
 def test_desc_struct_layout_is_stable():
     assert C.sizeof(_abi.PhaseDesc) == 80
     assert C.sizeof(_abi.RenderStats) == 56
-    assert C.sizeof(_abi.SensorDesc) == 352
+    assert C.sizeof(_abi.SensorDesc) == 360
     assert C.sizeof(_abi.LeafGroupDesc) == 24
     assert C.sizeof(_abi.SceneDesc) == 608
     assert _abi.SceneDesc.instance_offset.offset + 8 == C.sizeof(_abi.SceneDesc)
