@@ -109,7 +109,8 @@ struct BvhBox {
     }
 };
 
-// Median-split binary BVH over `boxes` (leaves hold <= ERTB_BVH_LEAF primitives), then folded into
+// Binary BVH over `boxes` (binned SAH splits, median split for small nodes; leaves hold <= ERTB_BVH_LEAF
+// primitives), then folded into
 // the device layout where every node carries the boxes of its two children. `order` receives the
 // primitive permutation the leaves index into (offset by `prim_base`); returns the root's index in
 // `out` (several trees share one array).
@@ -145,7 +146,58 @@ static int build_bvh(const std::vector<BvhBox> &boxes, std::vector<ErtbBvhNode> 
         float ext = cb.hi[0] - cb.lo[0];
         for (int k = 1; k < 3; ++k) if (cb.hi[k] - cb.lo[k] > ext) { ext = cb.hi[k] - cb.lo[k]; axis = k; }
         if (it.count > ERTB_BVH_LEAF && ext > 0.f) {
-            const int mid = it.first + it.count / 2;
+            int mid = it.first + it.count / 2;
+            bool split_done = false;
+            if (it.count > 8) {
+                // binned surface-area heuristic: 16 bins per axis over the centroid bounds; the split that
+                // minimises area(left) * n_left + area(right) * n_right wins (fewer boxes pierced per ray)
+                const int NBIN = 16;
+                auto area = [](const BvhBox &b) {
+                    float dx = fmaxf(b.hi[0] - b.lo[0], 0.f), dy = fmaxf(b.hi[1] - b.lo[1], 0.f), dz = fmaxf(b.hi[2] - b.lo[2], 0.f);
+                    return dx * dy + dy * dz + dz * dx;
+                };
+                double best_cost = 1e300;
+                int best_axis = -1, best_bin = -1;
+                for (int ax = 0; ax < 3; ++ax) {
+                    const float lo = cb.lo[ax], w = cb.hi[ax] - cb.lo[ax];
+                    if (!(w > 0.f)) continue;
+                    BvhBox bb_bin[NBIN];
+                    int cnt[NBIN];
+                    for (int k = 0; k < NBIN; ++k) { bb_bin[k] = BvhBox::empty(); cnt[k] = 0; }
+                    for (int i = it.first; i < it.first + it.count; ++i) {
+                        const BvhBox &b = boxes[order[i]];
+                        int k = (int) (NBIN * (0.5f * (b.lo[ax] + b.hi[ax]) - lo) / w);
+                        k = k < 0 ? 0 : (k >= NBIN ? NBIN - 1 : k);
+                        bb_bin[k].grow(b);
+                        cnt[k]++;
+                    }
+                    float right_area[NBIN];
+                    int right_cnt[NBIN];
+                    BvhBox acc = BvhBox::empty();
+                    int c = 0;
+                    for (int k = NBIN - 1; k > 0; --k) { acc.grow(bb_bin[k]); c += cnt[k]; right_area[k] = c ? area(acc) : 0.f; right_cnt[k] = c; }
+                    acc = BvhBox::empty();
+                    c = 0;
+                    for (int k = 0; k < NBIN - 1; ++k) { // split between bin k and k + 1
+                        acc.grow(bb_bin[k]); c += cnt[k];
+                        if (c == 0 || right_cnt[k + 1] == 0) continue;
+                        double cost = (double) area(acc) * c + (double) right_area[k + 1] * right_cnt[k + 1];
+                        if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = k; }
+                    }
+                }
+                if (best_axis >= 0) {
+                    const float lo = cb.lo[best_axis], w = cb.hi[best_axis] - cb.lo[best_axis];
+                    auto it_mid = std::partition(order.begin() + it.first, order.begin() + it.first + it.count, [&](int a) {
+                        int k = (int) (16 * (0.5f * (boxes[a].lo[best_axis] + boxes[a].hi[best_axis]) - lo) / w);
+                        k = k < 0 ? 0 : (k >= 16 ? 15 : k);
+                        return k <= best_bin;
+                    });
+                    mid = (int) (it_mid - order.begin());
+                    split_done = mid > it.first && mid < it.first + it.count;
+                    if (!split_done) mid = it.first + it.count / 2;
+                }
+            }
+            if (!split_done)
             std::nth_element(order.begin() + it.first, order.begin() + mid, order.begin() + it.first + it.count,
                              [&](int a, int b) { return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis]; });
             nd.left = (int) nodes.size();
