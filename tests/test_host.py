@@ -16,6 +16,7 @@ from eradiate_b200.kernel import (
     SeedState, develop, mi_load_dict, mi_traverse,
 )
 from eradiate_b200.kernel._scene import unflatten
+from eradiate_b200.kernel._types import ScalarTransform4f
 
 
 def test_unflatten_dotted_keys():
@@ -198,3 +199,98 @@ def test_desc_struct_layout_is_stable():
     assert C.sizeof(_abi.LeafGroupDesc) == 24
     assert C.sizeof(_abi.SceneDesc) == 608
     assert _abi.SceneDesc.instance_offset.offset + 8 == C.sizeof(_abi.SceneDesc)
+
+
+# ------------------------------------------------------------------ canopy / 3D scenes (host side)
+def _canopy_scene(**kw):
+    kw.setdefault("canopy", {"lai": 1.0, "radius": 0.2, "size": (2.0, 2.0, 1.0), "padding": 1, "seed": 3})
+    kw.setdefault("geometry", "plane_parallel")
+    kw.setdefault("n_layers", 10)
+    return scenes.atmosphere_scene(**kw)
+
+
+def test_flatten_canopy_groups_instances_and_leaf_optics():
+    """shapegroup + instances exactly as _core.py:266-296 / _leaf_cloud.py:1150-1175 emit them."""
+    kd = _canopy_scene(canopy={"lai": 1.0, "radius": 0.2, "size": (2.0, 2.0, 1.0), "padding": 1, "seed": 3,
+                               "reflectance": 0.3, "transmittance": 0.2})
+    sc = mi_load_dict(kd)
+    f = sc.flat
+    n = int(round(1.0 * 4.0 / (np.pi * 0.04)))
+    assert len(f.leaf_groups) == 1 and f.leaf_groups[0].disks.shape == (n, 7) and len(f.instances) == 9
+    dk = f.leaf_groups[0].disks
+    assert np.allclose(np.linalg.norm(dk[:, 3:6], axis=1), 1.0) and np.allclose(dk[:, 6], 0.2)
+    offs = sorted(tuple(o) for _, o in f.instances)
+    assert offs[0] == (-2.0, -2.0, 0.0) and offs[-1] == (2.0, 2.0, 0.0)
+    d = f.build_desc()
+    assert d.n_leaf_groups == 1 and d.n_instances == 9 and d.leaf_groups[0].n_disks == n
+    assert np.isclose(d.leaf_groups[0].reflectance, 0.3) and np.isclose(d.leaf_groups[0].transmittance, 0.2)
+    # the distant sensor targets the top of the unit cell (experiments/_canopy_atmosphere.py:200-210)
+    assert d.sensors[0].target_type == _abi.TARGET_RECTANGLE
+    # leaf optics are scene parameters; the leaves themselves are not exposed one by one
+    keys = list(mi_traverse(sc).parameters.keys())
+    assert "leaf_cloud.bsdf.reflectance.value" in keys and "leaf_cloud.bsdf.transmittance.value" in keys
+    assert not any("leaf_cloud_leaf_" in k for k in keys)
+
+
+def test_perspective_sensor_fov_axis_and_medium():
+    cam = {"type": "perspective", "origin": [0.0, -10.0, 5.0], "look_at": [0.0, 0.0, 0.0], "fov": 40.0,
+           "film_resolution": (8, 4)}
+    kd = _canopy_scene(sensor=dict(cam, medium={"type": "ref", "id": "medium_atmosphere"}))
+    d = mi_load_dict(kd).flat.build_desc()
+    s = d.sensors[0]
+    assert s.type == _abi.SENSOR_PERSPECTIVE and s.in_medium == 1 and np.isclose(s.x_fov_deg, 40.0)
+    assert np.isclose(s.near_clip, 1e-2) and np.isclose(s.far_clip, 1e4)
+    kd["measure"]["fov_axis"] = "y"  # sensor.cpp parse_fov: vertical fov -> horizontal through the aspect ratio
+    s = mi_load_dict(kd).flat.build_desc().sensors[0]
+    assert np.isclose(s.x_fov_deg, np.degrees(2 * np.arctan(np.tan(np.radians(20.0)) * 2.0)))
+
+
+@pytest.mark.parametrize("mutate,match", [
+    (lambda d: d["leaf_cloud_instance_0"].update(
+        {"to_world": ScalarTransform4f().rotate([0, 0, 1], 30.0)}), "only translations"),
+    (lambda d: d["leaf_cloud"].update({"trunk": {"type": "cylinder"}}), "tree trunks"),
+    (lambda d: d["leaf_cloud"].update({"cube": {"type": "cube"}}), "unsupported child shape"),
+    (lambda d: d["bsdf_leaf_cloud"].update({"type": "diffuse"}), "bilambertian"),
+    (lambda d: d["leaf_cloud_instance_0"].update(
+        {"to_world": ScalarTransform4f().translate([0.0, 0.0, 2.0e5])}), "below the top of the atmosphere"),
+    (lambda d: d["leaf_cloud_instance_0"].update(
+        {"to_world": ScalarTransform4f().translate([0.0, 0.0, -5.0])}), "above the ground"),
+    (lambda d: d["leaf_cloud"].update(
+        {"leaf_cloud_leaf_0": dict(d["leaf_cloud"]["leaf_cloud_leaf_0"],
+                                   to_world=ScalarTransform4f().scale([1.0, 2.0, 1.0]))}), "circular"),
+    (lambda d: d["surface_bsdf"].update({"type": "blendbsdf"}), "CentralPatchSurface"),
+])
+def test_canopy_restrictions_raise_at_load(mutate, match):
+    kd = _canopy_scene()
+    mutate(kd)
+    with pytest.raises(RuntimeError, match=match):
+        mi_load_dict(kd)
+
+
+def test_canopy_and_camera_need_the_plane_parallel_geometry():
+    kd = scenes.atmosphere_scene(geometry="spherical_shell", n_layers=10)
+    kd.update(scenes.disc_canopy(n_leaves=3))
+    with pytest.raises(RuntimeError, match="plane-parallel scenes only"):
+        mi_load_dict(kd)
+    kd = scenes.atmosphere_scene(geometry="spherical_shell", n_layers=10, sensor={
+        "type": "perspective", "origin": [0.0, 50.0, scenes.EARTH_RADIUS + 10.0], "look_at": [0.0, 0.0, 0.0]})
+    with pytest.raises(RuntimeError, match="plane-parallel scenes only"):
+        mi_load_dict(kd)
+
+
+def test_path_integrator_is_accepted_without_a_medium_only():
+    sc = mi_load_dict(_canopy_scene(atmosphere=None, integrator="path"))
+    assert sc.flat.build_desc().has_medium == 0
+    with pytest.raises(RuntimeError, match="ignores participating media"):
+        mi_load_dict(_canopy_scene(integrator="path"))
+
+
+def test_descriptor_owns_its_buffers():
+    """A descriptor stays valid when build_desc() is called again (the device scene builds its own)."""
+    sc = mi_load_dict(_canopy_scene())
+    d1 = sc.flat.build_desc()
+    first = np.ctypeslib.as_array(d1.leaf_groups[0].disks, (d1.leaf_groups[0].n_disks, 7)).copy()
+    for _ in range(3):
+        sc.flat.build_desc()
+    again = np.ctypeslib.as_array(d1.leaf_groups[0].disks, (d1.leaf_groups[0].n_disks, 7))
+    assert np.array_equal(first, again)
