@@ -564,12 +564,6 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
                         blob.push_back((float) (majorant / fmax(mx, 1e-6 * majorant)));
                     }
                     blob.resize(align4(blob.size()), 0.f);
-                    P.off_band_of = (int) blob.size();
-                    for (int i = 0, k = 0; i < n; ++i) {
-                        while (k + 1 < nb && i >= starts[k + 1]) ++k;
-                        blob.push_back((float) k);
-                    }
-                    blob.resize(align4(blob.size()), 0.f);
                 }
             }
         }

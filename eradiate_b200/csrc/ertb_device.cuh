@@ -99,9 +99,9 @@ struct ErtbParams {
     int off_cumw;     // (n_phase-1) x n_layers cumulative leaf probabilities
     // banded majorant (pool kernel, BANDS instances): the layer stack is cut into n_bands altitude bands,
     // each with its own majorant. Blob: band_lo[n_bands + 1] (altitudes above the ground of the band
-    // boundaries), band_ratio[n_bands] (global majorant / band majorant), band_of_layer[n_layers]
+    // boundaries), band_ratio[n_bands] (global majorant / band majorant)
     int n_bands;
-    int off_band_lo, off_band_ratio, off_band_of;
+    int off_band_lo, off_band_ratio;
     // piecewise medium (ertb_piecewise.cuh): sigma_t per layer, vertical optical depth above each of
     // the n_layers + 1 layer boundaries, layer thickness, optical depth above the ground level
     int piecewise;

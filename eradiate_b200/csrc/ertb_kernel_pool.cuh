@@ -87,6 +87,14 @@ __device__ __forceinline__ unsigned pw_advance(const ErtbParams &P, const float 
 // ----------------------------------------------------------------------------
 // distance, along the segment (h0, b), at which a record in band `bi` reaches the band's boundary
 // (`down`: it is descending; cleared when a spherical ray passes its perigee inside the band)
+// band holding altitude h (<= 8 bands: a handful of compares, cheaper than a per-layer table in shared memory)
+__device__ __forceinline__ int band_of(const ErtbParams &P, const float *tb, float h) {
+    const float *lo = tb + P.off_band_lo;
+    int bi = 0;
+    for (int k = 1; k < P.n_bands; ++k) bi += h >= lo[k] ? 1 : 0;
+    return bi;
+}
+
 template <bool SPH>
 __device__ __forceinline__ float band_exit(const ErtbParams &P, const float *tb, float h0, float b, int bi, bool &down,
                                            float smax) {
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                         float inv_maj = P.inv_majorant, bratio = 1.f;
                         if (BANDS) {
                             if (s == 0.f) { // a new segment (every event starts one with s = 0): band of its origin
-                                int bi = (int) tb[P.off_band_of + layer_of(P, h0)];
+                                int bi = band_of(P, tb, h0);
                                 bool down = b < 0.f;
                                 sb = band_exit<SPH>(P, tb, h0, b, bi, down, smax);
                                 band = (unsigned) bi | (down ? 256u : 0u);
