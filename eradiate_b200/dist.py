@@ -109,7 +109,7 @@ def context_shard(n_items: int, rank: int, world: int) -> list[int]:
     return list(range(int(rank), int(n_items), int(world)))
 
 
-def _render_items_gpu(mi_scene, plan, mine, seeds, spps):
+def _render_items_gpu(mi_scene, plan, mine, seeds, spps, offsets=None):
     """This rank's items through the pipelined batch entry points (one device per rank)."""
     dev = _device_scene(mi_scene.obj)
     dev.batch_begin([plan[k][1] for k in mine])
@@ -119,20 +119,27 @@ def _render_items_gpu(mi_scene, plan, mine, seeds, spps):
         if ctx is not last_ctx:
             mi_scene.parameters.update(mi_scene.umap_template.render(ctx))
             last_ctx = ctx
-        dev.batch_push(i_sensor, seeds[k], spps[k])
+        dev.batch_push(i_sensor, seeds[k], spps[k], 0 if offsets is None else offsets[k])
     items, _, _ = dev.batch_end()
     return items
 
 
 def mi_render_sharded(mi_scene, ctxs, spp: int = 0, seed_state: SeedState | None = None,
-                      render_items=_render_items_gpu, group=None) -> dict:
+                      render_items=_render_items_gpu, group=None, shard: str = "contexts") -> dict:
     """
-    ``mi_render`` with the (context, sensor) items dealt round-robin over the ranks: each rank
-    renders its items at full spp and the films are gathered, so every rank returns the complete
-    ``{ctx.si.as_hashable: {sensor_id: Bitmap}}``. No reduction is involved ("band
-    sharding"). Every rank draws ALL seeds in the global loop order, so item k gets the same seed
-    whatever the world size: the result does not depend on the number of GPUs.
+    ``mi_render`` over all ranks; every rank returns the complete
+    ``{ctx.si.as_hashable: {sensor_id: Bitmap}}``. Every rank draws ALL seeds in the global loop
+    order, so item k gets the same seed whatever the world size.
+
+    ``shard="contexts"`` (BASELINE C5, SURVEY 8e "band sharding"): the (context, sensor) items are
+    dealt round-robin to the ranks, each rendered at full spp by one rank; the films are gathered,
+    no reduction is involved, and the result does not depend on the number of GPUs at all.
+
+    ``shard="samples"`` (BASELINE C3): every rank renders a disjoint range of the samples of EVERY
+    item (same seed, sample offsets) and ONE all-reduce sums the accumulators of all items.
     """
+    if shard not in ("contexts", "samples"):
+        raise ValueError("shard must be 'contexts' or 'samples'")
     if seed_state is None:
         seed_state = get_seed_state()
     rank = dist.get_rank(group) if is_distributed() else 0
@@ -140,13 +147,31 @@ def mi_render_sharded(mi_scene, ctxs, spp: int = 0, seed_state: SeedState | None
     plan = [(ctx, i, s) for ctx in ctxs for i, s in _active_sensors(mi_scene, ctx)]
     seeds = [int(np.asarray(seed_state.next()).squeeze()) & 0xFFFFFFFFFFFFFFFF for _ in plan]
     spps = [int(spp) if spp > 0 else s.sampler().sample_count for _, _, s in plan]
-    mine = context_shard(len(plan), rank, world)
-    local = render_items(mi_scene, plan, mine, seeds, spps) if mine else []
-    payload = {k: np.asarray(a) for k, a in zip(mine, local)}
-    if world > 1:
-        gathered = [None] * world
-        dist.all_gather_object(gathered, payload, group=group)
-        payload = {k: a for part in gathered for k, a in part.items()}
+    if shard == "samples":
+        ranges = [shard_range(n, rank, world) for n in spps]
+        mine = [k for k in range(len(plan)) if ranges[k][1] > 0]
+        local = render_items(mi_scene, plan, mine, seeds, {k: ranges[k][1] for k in mine},
+                             {k: ranges[k][0] for k in mine}) if mine else []
+        shapes = [(7 if mi_scene.obj.flat.polarized else 3, s.film().width * s.film().height) for _, _, s in plan]
+        flat = np.zeros(sum(r * n for r, n in shapes), dtype=np.float64)
+        pos = np.cumsum([0] + [r * n for r, n in shapes])
+        for k, a in zip(mine, local):
+            flat[pos[k]:pos[k + 1]] = np.asarray(a, dtype=np.float64).ravel()
+        if world > 1:
+            t = torch.from_numpy(flat)
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            flat = t.cpu().numpy()
+        payload = {k: flat[pos[k]:pos[k + 1]].reshape(shapes[k]) for k in range(len(plan))}
+    else:
+        mine = context_shard(len(plan), rank, world)
+        local = render_items(mi_scene, plan, mine, seeds, spps) if mine else []
+        payload = {k: np.asarray(a) for k, a in zip(mine, local)}
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, payload, group=group)
+            payload = {k: a for part in gathered for k, a in part.items()}
     results: dict = {}
     for k, (ctx, i_sensor, mi_sensor) in enumerate(plan):
         a = payload[k]

@@ -72,7 +72,7 @@ def test_two_rank_gloo_sharded_render_equals_single(tmp_path, oracle):
 
 
 # --------------------------------------------------------------------------- band sharding
-def _oracle_items(mi_scene, plan, mine, seeds, spps):
+def _oracle_items(mi_scene, plan, mine, seeds, spps, offsets=None):
     """Stand-in for the GPU batch (test infrastructure): the CPU oracle renders this rank's items."""
     from oracle import oracle
 
@@ -80,7 +80,8 @@ def _oracle_items(mi_scene, plan, mine, seeds, spps):
     for k in mine:
         ctx, i_sensor, _ = plan[k]
         mi_scene.parameters.update(mi_scene.umap_template.render(ctx))
-        wl, l, l2, _ = oracle.render(mi_scene.obj.flat.build_desc(), i_sensor, seeds[k], spps[k], n_threads=2)
+        wl, l, l2, _ = oracle.render(mi_scene.obj.flat.build_desc(), i_sensor, seeds[k], spps[k],
+                                     sample_offset=0 if offsets is None else offsets[k], n_threads=2)
         out.append(np.stack([wl, l, l2]))
     return out
 
@@ -96,7 +97,10 @@ def _band_scene():
     return mi_scene, ctxs
 
 
-def _band_worker(rank, world, port, out):
+SPP_BAND = 65  # odd on purpose: ragged sample shards
+
+
+def _band_worker(rank, world, port, out, shard):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -104,7 +108,7 @@ def _band_worker(rank, world, port, out):
     from eradiate_b200.kernel._render import SeedState
 
     mi_scene, ctxs = _band_scene()
-    res = mi_render_sharded(mi_scene, ctxs, spp=64, seed_state=SeedState(3), render_items=_oracle_items)
+    res = mi_render_sharded(mi_scene, ctxs, spp=SPP_BAND, seed_state=SeedState(3), render_items=_oracle_items, shard=shard)
     if rank == 1:  # every rank holds the complete result
         np.save(out, np.stack([res[c.si.as_hashable][s].raw["sum_l"] for c in ctxs for s in ("measure", "measure_2")]))
     dist.barrier()
@@ -121,16 +125,17 @@ def test_context_shard_is_a_partition():
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_gloo_band_sharded_mi_render_equals_single(tmp_path, oracle):
+@pytest.mark.parametrize("shard", ["contexts", "samples"])
+def test_two_rank_gloo_sharded_mi_render_equals_single(tmp_path, oracle, shard):
     from eradiate_b200.dist import mi_render_sharded
     from eradiate_b200.kernel._render import SeedState
 
     out = str(tmp_path / "bands.npy")
-    port = 31500 + (os.getpid() % 2000)
-    mp.spawn(_band_worker, args=(2, port, out), nprocs=2, join=True)
+    port = 31500 + (os.getpid() % 2000) + (7 if shard == "samples" else 0)
+    mp.spawn(_band_worker, args=(2, port, out, shard), nprocs=2, join=True)
     got = np.load(out)
     mi_scene, ctxs = _band_scene()
-    res = mi_render_sharded(mi_scene, ctxs, spp=64, seed_state=SeedState(3), render_items=_oracle_items)
+    res = mi_render_sharded(mi_scene, ctxs, spp=SPP_BAND, seed_state=SeedState(3), render_items=_oracle_items)
     assert list(res.keys()) == [c.si.as_hashable for c in ctxs]
     want = np.stack([res[c.si.as_hashable][s].raw["sum_l"] for c in ctxs for s in ("measure", "measure_2")])
     assert got.shape == want.shape and np.allclose(got, want, rtol=1e-12)

@@ -715,8 +715,10 @@ def test_band_sharded_mi_render_single_rank_equals_mi_render():
     ctxs = [KernelContext(w=w) for w in (440.0, 550.0, 670.0)]
     a = mi_render(mi_scene, ctxs, spp=spp, seed_state=SeedState(9))
     b = mi_render_sharded(mi_scene, ctxs, spp=spp, seed_state=SeedState(9))
+    c = mi_render_sharded(mi_scene, ctxs, spp=spp, seed_state=SeedState(9), shard="samples")
     for k in a:
         assert np.allclose(a[k]["measure"].raw["sum_l"], b[k]["measure"].raw["sum_l"], rtol=1e-10)
+        assert np.allclose(a[k]["measure"].raw["sum_l"], c[k]["measure"].raw["sum_l"], rtol=1e-10)
 
 
 def test_batch_ocean_tables_are_private_per_item():
