@@ -277,9 +277,7 @@ struct ertb_scene {
     std::vector<double> instance_offset;
     ErtbCanopy canopy;          // device pointers (zero-initialised: no canopy)
     void *d_canopy[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
-    bool needs_3d = false;      // canopy / perspective / mpdistant / mradiancemeter in a plane-parallel scene:
-                                // rendered by ertb_canopy_kernel
-    bool needs_legacy = false;  // mpdistant / mradiancemeter in a spherical shell: the register-resident kernel
+    bool needs_3d = false;      // canopy or perspective sensor: rendered by ertb_canopy_kernel
 };
 
 static int build_canopy(ertb_scene *S) {
@@ -966,16 +964,6 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
         S->needs_3d = true;
     }
     for (int i = 0; i < D->n_sensors; ++i)
-        if (D->sensors[i].type == ERTB_SENSOR_MPDISTANT || D->sensors[i].type == ERTB_SENSOR_MRADIANCEMETER) {
-            if (D->geometry == ERTB_GEOM_PLANE_PARALLEL) {
-                if (S->polarized) { delete S; return set_error("mpdistant / mradiancemeter: polarized scenes are not supported"); }
-                S->needs_3d = true;
-            } else {
-                if (S->polarized) { delete S; return set_error("mpdistant / mradiancemeter: polarized scenes are not supported"); }
-                S->needs_legacy = true;
-            }
-        }
-    for (int i = 0; i < D->n_sensors; ++i)
         if (D->sensors[i].type == ERTB_SENSOR_PERSPECTIVE) {
             if (D->geometry != ERTB_GEOM_PLANE_PARALLEL || S->polarized) {
                 delete S;
@@ -1120,7 +1108,7 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     if (!counter_dev) counter_dev = S->d_counter;
     const HostSensor &hs = S->sensors[sensor];
     fill_sensor_params(S, hs, P.sensor);
-    if (hs.desc.type == ERTB_SENSOR_MDISTANT) { P.sensor_up[0] = 0.f; P.sensor_up[1] = 1.f; P.sensor_up[2] = 0.f; }
+    if (hs.desc.type == ERTB_SENSOR_MDISTANT || hs.desc.type == ERTB_SENSOR_MRADIANCEMETER) { P.sensor_up[0] = 0.f; P.sensor_up[1] = 1.f; P.sensor_up[2] = 0.f; }
     else { P.sensor_up[0] = (float) hs.desc.to_world[1]; P.sensor_up[1] = (float) hs.desc.to_world[5]; P.sensor_up[2] = (float) hs.desc.to_world[9]; }
     P.seed = seed;
     P.spp = spp;
@@ -1141,10 +1129,9 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     const bool c3d = S->needs_3d; // canopy / perspective camera: the 3D kernel (ertb_canopy.cuh)
     if (pol || pw) use_pool = true; // the polarized and the piecewise paths exist in the pool kernel only
     if (c3d) use_pool = false;
-    if (S->needs_legacy) {
-        if (pol || pw) return set_error("mpdistant / mradiancemeter: unsupported with this integrator in a spherical shell");
-        use_pool = false;
-    }
+    // general primary rays: the GEN instances of the pool kernel (compiled with statistics on)
+    const bool gen = !c3d && (hs.desc.type == ERTB_SENSOR_MPDISTANT || hs.desc.type == ERTB_SENSOR_MRADIANCEMETER);
+    if (gen) use_pool = true;
     const int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK);
     const bool bands = S->base.n_bands > 1;
     size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol, bands && !pw) : (size_t) S->base.blob_bytes;
@@ -1165,7 +1152,8 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     } while (0)
 #define ERTB_POOL_VARIANT_B(MACRO, SPH_, POL_, PW_, B_)                                               \
     do {                                                                                              \
-        if (with_stats) MACRO((ertb_render_pool_kernel<SPH_, true, POL_, PW_, true, B_>));            \
+        if (gen) MACRO((ertb_render_pool_kernel<SPH_, true, POL_, PW_, true, B_, true>));             \
+        else if (with_stats) MACRO((ertb_render_pool_kernel<SPH_, true, POL_, PW_, true, B_>));       \
         else if (coll) MACRO((ertb_render_pool_kernel<SPH_, false, POL_, PW_, true, B_>));            \
         else MACRO((ertb_render_pool_kernel<SPH_, false, POL_, PW_, false, B_>));                     \
     } while (0)

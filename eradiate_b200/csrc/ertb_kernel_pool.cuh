@@ -172,7 +172,10 @@ __device__ __noinline__ void film_flush_warp(const ErtbParams &P, unsigned lane,
 // COLL: collective mid-kernel film flushes, for renders whose chunks are small (many pixel
 // switches per lane). It is a template parameter because any call inside the scheduler loop
 // perturbs the register allocation of the walk phase (-3..7 % on the C2 headline, measured).
-template <bool SPH, bool STATS, bool POL, bool PW = false, bool COLL = false, bool BANDS = false>
+// GEN: general primary rays -- `mradiancemeter` (explicit rays whose origin may lie inside the atmosphere:
+// class 3 of the per-pixel table carries the start altitude) and `mpdistant` (the film sample picks the
+// target point). A template parameter for the same reason as COLL: the C2 instance must not change.
+template <bool SPH, bool STATS, bool POL, bool PW = false, bool COLL = false, bool BANDS = false, bool GEN = false>
 __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
     static_assert(!(PW && BANDS), "the piecewise integrator has no null collisions");
     static_assert(!(PW && SPH), "the piecewise medium is a plane-parallel layer stack");
@@ -450,19 +453,27 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                 f3 n0 = mk3(0.f, 0.f, 1.f), d = mk3(0.f, 0.f, -1.f);
                 const ErtbSensor &S = P.sensor;
                 int valid = 1;
+                float h_start = P.H;
                 if (S.use_table) {
                     const float4 *t4 = reinterpret_cast<const float4 *>(S.table) + 2u * pix;
                     float4 a = __ldg(t4), c4 = __ldg(t4 + 1);
                     n0 = mk3(a.x, a.y, a.z);
                     d = mk3(a.w, c4.x, c4.y);
                     valid = (int) c4.z;
+                    if (GEN) h_start = c4.w;
                 } else {
                     unsigned px = pix % (unsigned) S.width, py = pix / (unsigned) S.width;
                     float fx = __fdividef((float) px + pcg_float(rng), (float) S.width);
                     float fy = __fdividef((float) py + pcg_float(rng), (float) S.height);
                     float ax = pcg_float(rng), ay = pcg_float(rng);
                     f3 fs = mk3(1.f, 0.f, 0.f), ft = mk3(0.f, 1.f, 0.f);
-                    if (S.type == ERTB_SENSOR_MDISTANT) {
+                    if (GEN && S.type == ERTB_SENSOR_MPDISTANT) { // mpdistant.cpp:214-262
+                        const float *M = S.to_world;
+                        d = normalize3(mk3(M[2], M[5], M[8]));
+                        fs = mk3(M[0], M[3], M[6]);
+                        ft = mk3(M[1], M[4], M[7]);
+                        ax = fx; ay = fy;
+                    } else if (S.type == ERTB_SENSOR_MDISTANT) {
                         const float4 *t4 = reinterpret_cast<const float4 *>(S.table) + 2u * pix;
                         float4 a = __ldg(t4), c4 = __ldg(t4 + 1);
                         d = mk3(a.w, c4.x, c4.y);
@@ -504,9 +515,13 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ert
                         valid = !(d.z < 0.f) || oz < 0.0 ? 0 : (oz >= (double) P.H ? 1 : 2);
                     }
                 }
-                if (!SPH && !(d.z < 0.f)) valid = 0;
+                if (GEN && valid == 3) valid = 1; // starts inside the atmosphere at h_start, looking anywhere
+                else {
+                    if (!SPH && !(d.z < 0.f)) valid = 0;
+                    h_start = P.H;
+                }
                 unsigned flags;
-                float h0 = P.H, b = 0.f, smax = 0.f;
+                float h0 = GEN ? h_start : P.H, b = 0.f, smax = 0.f;
                 if (valid == 1 && PW) {
                     if (STATS) st_main++;
                     b = d.z;

@@ -855,9 +855,6 @@ class FlatScene:
         forced = getattr(sc, "_force_polarized", None)
         if forced is not None:
             self.polarized = bool(forced)
-        for sn in self.sensors:
-            if sn.type in ("mpdistant", "mradiancemeter") and self.polarized:
-                raise RuntimeError(f"{sn.type}: polarized scenes are not supported with this sensor")
         if self.polarized and self.integrator.kernel_type == "volpathmis":
             # volpathmis.cpp:130-132
             raise RuntimeError("This integrator currently does not support polarized mode!")

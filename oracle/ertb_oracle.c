@@ -1498,7 +1498,7 @@ static void bsdf_eval_mueller(const scene_t *S, const frame_t *fr, v3 wi, v3 wo,
  * only the first column of `result` is ever non-zero: it is kept as a Stokes 4-vector.  All the
  * surface BSDFs of this path return depolarizer(value), which to_world_mueller() leaves unchanged.
  * stokes.cpp:97-168 then rotates the vector from the implicit basis of -ray.d to the output basis. */
-static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, v3 sensor_up, counters_t *C, double stokes[4]) {
+static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, int medium0, v3 sensor_up, counters_t *C, double stokes[4]) {
     const ertb_scene_desc *D = S->desc;
     const int mis = D->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
     const int pw = D->integrator == ERTB_INTEGRATOR_PIECEWISE_VOLPATH;
@@ -1506,9 +1506,9 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, v3 senso
     const v3 primary_d = ray.d;
     mueller_t T = mu_identity(1.0);
     double result[4] = { 0, 0, 0, 0 }, eta = 1.0;
-    int medium = 0;
+    int medium = medium0;
     uint64_t depth = 0;
-    si_t si; si.t = INFINITY; si.shape = -1; si.p = si.n = V(0, 0, 0);
+    si_t si; si.t = INFINITY; si.shape = -1; si.group = -1; si.p = si.n = V(0, 0, 0);
     int needs_intersection = 1, last_event_was_null = 0;
 
     for (;;) {
@@ -1665,7 +1665,7 @@ int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, 
            *a_l2 = calloc(npix, sizeof(double)), *a_st = calloc(4 * npix, sizeof(double));
     v3 sensor_up;
     mat_apply_vec(sd->to_world, V(0, 1, 0), &sensor_up);
-    if (sd->type == ERTB_SENSOR_MDISTANT) sensor_up = V(0, 1, 0);
+    if (sd->type == ERTB_SENSOR_MDISTANT || sd->type == ERTB_SENSOR_MRADIANCEMETER) sensor_up = V(0, 1, 0);
     counters_t total = { 0, 0, 0, 0 };
 
 #pragma omp parallel
@@ -1688,13 +1688,13 @@ int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, 
                 ray_t ray;
                 double w = sensor_sample_ray(&S, sd, fx, fy, ax, ay, &ray);
                 double L;
+                const int in_medium = (sd->type == ERTB_SENSOR_PERSPECTIVE || sd->type == ERTB_SENSOR_MRADIANCEMETER) && sd->in_medium;
                 if (desc->polarized) {
                     double st[4];
-                    volpath_sample_pol(&S, &rng, ray, sensor_up, &C, st);
+                    volpath_sample_pol(&S, &rng, ray, in_medium, sensor_up, &C, st);
                     L = st[0];
                     for (int k = 0; k < 4; ++k) s_st[k] += w * st[k];
                 } else {
-                    int in_medium = (sd->type == ERTB_SENSOR_PERSPECTIVE || sd->type == ERTB_SENSOR_MRADIANCEMETER) && sd->in_medium;
                     L = volpath_sample(&S, &rng, ray, in_medium, &C);
                 }
                 s_wl += w * L; s_l += L; s_l2 += L * L;

@@ -20,6 +20,11 @@ def polarized_aerosol_scene() -> dict:
 CANOPY = {"lai": 2.5, "radius": 0.1, "size": (4.0, 4.0, 1.0), "padding": 1, "seed": 6}
 
 
+def _with_polarized_aerosol(d: dict) -> dict:
+    d["phase_atmosphere"]["phase_1"] = scenes.polarized_aerosol_table()
+    return d
+
+
 def _first_sensor(d: dict) -> dict:
     """Fixtures hold sensor 0 only: drop the others."""
     keep, seen = {}, False
@@ -165,6 +170,15 @@ def battery() -> dict:
             geometry="plane_parallel", n_layers=60,
             sensor={"type": "mradiancemeter", "origins": [[0.0, 0.0, 2.0e5], [1.0e4, 0.0, 1.5e5]],
                     "directions": [[0.0, 0.0, -1.0], [0.5, 0.0, -0.8660254]]}),
+        # polarized sky radiance seen from the ground (AERONET-like almucantar points): rayleigh_polarized +
+        # polarized aerosol blend in a spherical shell -> GEN + POL + BANDS instance of the pool kernel
+        "polarized_sky_from_ground_aerosol_spherical": _with_polarized_aerosol(S(
+            n_layers=120, sza=55.0, saa=0.0, aerosol=True, aerosol_phase="hg", stokes=True,
+            phase={"type": "rayleigh_polarized", "depolarization": 0.0279},
+            surface={"type": "diffuse", "reflectance": 0.1},
+            sensor={"type": "mradiancemeter", "medium": {"type": "ref", "id": "medium_atmosphere"},
+                    "origins": [[0.0, 0.0, scenes.EARTH_RADIUS + 2.0]] * 3,
+                    "directions": [[0.0, 0.0, 1.0], [-0.5735764, 0.0, 0.8191520], [0.4096, 0.7094, 0.5735764]]})),
         "mpdistant_canopy_image_pp": S(geometry="plane_parallel", n_layers=60, sza=30.0, canopy=CANOPY,
                                        sensor={"type": "mpdistant", "vza": 25.0, "vaa": 60.0, "film_resolution": (3, 2)}),
         "mpdistant_spherical": S(n_layers=100, sza=60.0, sensor={"type": "mpdistant", "vza": 40.0, "vaa": 0.0,
