@@ -1185,7 +1185,7 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     ERTB_DISPATCH(ERTB_OCC);
     if (blocks_per_sm < 1) return set_error("render kernel cannot be resident on this device");
     if (use_pool) {
-        P.tw = 32; P.twi = 16;
+        P.tw = 32; P.twi = bands ? 8 : 16; // (banded walks lose lanes at band boundaries: keep stepping longer; C3 +4 %)
         if (const char *e = getenv("ERTB_POOL_TW")) P.tw = atoi(e);
         if (const char *e = getenv("ERTB_POOL_TWI")) P.twi = atoi(e);
     }
