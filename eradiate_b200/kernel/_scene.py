@@ -241,6 +241,15 @@ _KNOWN_UNSUPPORTED = {
     "blendbsdf": "CentralPatchSurface (bitmap-blended ground BSDFs) is not implemented",
     "ply": "mesh canopy elements are not implemented",
     "obj": "mesh canopy elements are not implemented",
+    # the reference's remaining plugins for this slot
+    "astroobject": "finite-size solar discs need emitter-hit MIS, which the kernels do not carry (use 'directional')",
+    "ocean_grasp": "only the 'ocean_legacy' (6SV) ocean model is implemented",
+    "ocean_mishchenko": "only the 'ocean_legacy' (6SV) ocean model is implemented",
+    "maignan": "this BSDF is not implemented",
+    "mqdiffuse": "tabulated measured BSDFs are not implemented",
+    "measured_mono": "tabulated measured BSDFs are not implemented",
+    "selectbsdf": "this BSDF adapter is not implemented",
+    "multiphase": "use nested 'blendphase' nodes (flattened to <= 4 leaves)",
 }
 
 
