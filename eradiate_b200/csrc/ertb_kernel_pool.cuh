@@ -36,6 +36,9 @@
 #ifndef ERTB_POOL_MINB
 #define ERTB_POOL_MINB 6
 #endif
+#ifndef ERTB_POOL_MINB_POL
+#define ERTB_POOL_MINB_POL 3 // polarized instances: Mueller-matrix events need > 128 registers
+#endif
 #define ERTB_POOL_K (ERTB_POOL_NS / 32)
 
 enum : int {
@@ -176,7 +179,7 @@ __device__ __noinline__ void film_flush_warp(const ErtbParams &P, unsigned lane,
 // class 3 of the per-pixel table carries the start altitude) and `mpdistant` (the film sample picks the
 // target point). A template parameter for the same reason as COLL: the C2 instance must not change.
 template <bool SPH, bool STATS, bool POL, bool PW = false, bool COLL = false, bool BANDS = false, bool GEN = false>
-__global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? 3 : ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
+__global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
     static_assert(!(PW && BANDS), "the piecewise integrator has no null collisions");
     static_assert(!(PW && SPH), "the piecewise medium is a plane-parallel layer stack");
     constexpr int NF = (POL ? PF_COUNT_POL : PF_COUNT) + (BANDS ? 2 : 0);
