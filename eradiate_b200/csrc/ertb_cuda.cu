@@ -245,6 +245,7 @@ struct ertb_scene {
     int has_medium = 0, n_layers = 0, homogeneous = 0;
     float scale = 1.f;
     std::vector<float> sigma_t, albedo, phase_weight;
+    std::vector<int> band_starts; // banded majorant: first layer of every band chosen at the last commit
     int n_phase = 0;
     HostPhase phase[ERTB_MAX_PHASE];
     int bsdf_type = 0;
@@ -545,7 +546,28 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
                 std::vector<double> sg(n);
                 for (int i = 0; i < n; ++i) sg[i] = (double) S->scale * (double) S->sigma_t[i];
                 const double dz = (S->medium_top - S->medium_bottom) / n;
-                std::vector<int> starts = choose_bands(sg, dz);
+                // The programme costs ~0.1 ms: spectral loops commit once per context, so (1) skip it when even
+                // the ideal partition (every layer its own band, two boundary stops) cannot halve the trips,
+                // (2) keep the previous cut while it still does (its majorants are re-derived below anyway).
+                double tau = 0.0, mxg = 0.0;
+                for (int i = 0; i < n; ++i) { tau += sg[i] * dz; mxg = fmax(mxg, sg[i]); }
+                const double cost_global = mxg * dz * n + ERTB_BAND_PENALTY;
+                std::vector<int> starts(1, 0);
+                if (tau + 2.0 * ERTB_BAND_PENALTY < ERTB_BAND_MIN_GAIN * cost_global) {
+                    bool reuse = false;
+                    if (S->band_starts.size() > 1 && S->band_starts.back() < n) {
+                        double c = 0.0;
+                        for (size_t k = 0; k < S->band_starts.size(); ++k) {
+                            const int a = S->band_starts[k], b = k + 1 < S->band_starts.size() ? S->band_starts[k + 1] : n;
+                            double mx = 0.0;
+                            for (int i = a; i < b; ++i) mx = fmax(mx, sg[i]);
+                            c += mx * dz * (b - a) + ERTB_BAND_PENALTY;
+                        }
+                        reuse = c < ERTB_BAND_MIN_GAIN * cost_global;
+                    }
+                    starts = reuse ? S->band_starts : choose_bands(sg, dz);
+                }
+                S->band_starts = starts;
                 const int nb = (int) starts.size();
                 if (nb > 1) {
                     P.n_bands = nb;
