@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -65,6 +65,7 @@ PARAM_IRRADIANCE = 5
 PARAM_PHASE_PARAMS = 6
 PARAM_PHASE_MUELLER = 7
 PARAM_LEAF_BSDF = 8
+PARAM_PATCH_BSDF_PARAMS = 9
 
 c_float_p = C.POINTER(C.c_float)
 c_double_p = C.POINTER(C.c_double)
@@ -151,6 +152,10 @@ class SceneDesc(C.Structure):
         ("leaf_groups", C.POINTER(LeafGroupDesc)),
         ("instance_group", C.POINTER(C.c_int32)),
         ("instance_offset", c_double_p),
+        ("has_patch", C.c_int32),
+        ("patch_bsdf_type", C.c_int32),
+        ("patch_bsdf_params", C.c_float * MAX_BSDF_PARAMS),
+        ("patch_rect", C.c_double * 4),
     ]
 
 

@@ -201,6 +201,18 @@ __device__ __forceinline__ float bilambertian_sample(float r, float t, float ci,
     return pdf > 0.f ? value : 0.f;
 }
 
+// land BSDF value (without the cosine) for an explicit (type, parameter array): the patch of a
+// CentralPatchSurface; same device functions as bsdf_f()
+__device__ __forceinline__ float land_bsdf(int type, const float *prm, float ci, float co, float cdphi) {
+    switch (type) {
+        case ERTB_BSDF_DIFFUSE: return prm[0] * ERTB_INV_PI;
+        case ERTB_BSDF_RPV: return rpv_eval(prm, ci, co, cdphi);
+        case ERTB_BSDF_RTLS: return rtls_eval(prm, ci, co, cdphi);
+        case ERTB_BSDF_HAPKE: return hapke_eval(prm, ci, co, cdphi);
+        default: return 0.f;
+    }
+}
+
 // ----------------------------------------------------------------------------
 // primary rays: distant sensors aim at a target point T (mdistant.cpp:192-242,
 // hdistant.cpp:232-275, distantflux.cpp:148-195), the camera starts at its pinhole
@@ -525,7 +537,21 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 on_inst = on_disk = -1;
                 float ci = -d.z;
                 if (!(ci > 0.f) || P.bsdf_type == ERTB_BSDF_BLACK) ev = CEV_END;
-                else {
+                else if (C.patch_type >= 0 && fabs(p[0] - C.patch_rect[0]) <= C.patch_rect[2] &&
+                         fabs(p[1] - C.patch_rect[1]) <= C.patch_rect[3]) {
+                    // CentralPatchSurface (blendbsdf.cpp:108-165 with a 0/1 mask): the patch's own land BSDF
+                    const float *pp = tb + C.off_patch_bsdf;
+                    if (depth + 1u < P.max_depth && sun.z > 0.f)
+                        nee = thr * land_bsdf(C.patch_type, pp, ci, sun.z, cos_dphi(ci, sun.z, -dot3(d, sun))) * sun.z * P.irradiance;
+                    float u1 = pcg_float(rng), u2 = pcg_float(rng);
+                    f3 wl = cosine_hemisphere(u1, u2);
+                    float weight = 0.f;
+                    if (wl.z > 0.f) // value * cos / pdf = value * pi (rpv.cpp:119-122)
+                        weight = land_bsdf(C.patch_type, pp, ci, wl.z, cos_dphi(ci, wl.z, -dot3(d, wl))) * ERTB_PI;
+                    d = normalize3(wl); // local frame of the ground = world axes
+                    thr *= weight;
+                    depth++;
+                } else {
                     float f_sun, weight;
                     const f3 up = mk3(0.f, 0.f, 1.f);
                     surface_interact<false>(P, up, sun, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);

@@ -250,6 +250,9 @@ struct ertb_scene {
     HostPhase phase[ERTB_MAX_PHASE];
     int bsdf_type = 0;
     float bsdf_params[ERTB_MAX_BSDF_PARAMS];
+    int has_patch = 0, patch_bsdf_type = 0; // CentralPatchSurface: second ground BSDF inside a rectangle
+    float patch_bsdf_params[ERTB_MAX_BSDF_PARAMS];
+    double patch_rect[4] = { 0, 0, 0, 0 };
     double emitter_dir[3];
     float irradiance = 1.f;
     int integrator = 0, rr_depth = 5;
@@ -626,6 +629,14 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
     P.canopy.off_leaf_bsdf = (int) blob.size();
     for (const HostLeafGroup &g : S->leaf_groups) { blob.push_back(g.reflectance); blob.push_back(g.transmittance); }
     blob.resize(align4(blob.size()), 0.f);
+    P.canopy.patch_type = -1;
+    if (S->has_patch) { // the patch BSDF travels with the tables (spectral updates, batch slots)
+        P.canopy.patch_type = S->patch_bsdf_type;
+        P.canopy.off_patch_bsdf = (int) blob.size();
+        blob.insert(blob.end(), S->patch_bsdf_params, S->patch_bsdf_params + ERTB_MAX_BSDF_PARAMS);
+        blob.resize(align4(blob.size()), 0.f);
+        for (int k = 0; k < 4; ++k) P.canopy.patch_rect[k] = S->patch_rect[k];
+    }
 
     const size_t blob_bytes = blob.size() * sizeof(float);
     if (blob_bytes > (size_t) S->max_smem_optin - 1024)
@@ -933,6 +944,23 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
     }
     S->bsdf_type = D->bsdf_type;
     memcpy(S->bsdf_params, D->bsdf_params, sizeof S->bsdf_params);
+    memset(S->patch_bsdf_params, 0, sizeof S->patch_bsdf_params);
+    if (D->has_patch) {
+        if (D->geometry != ERTB_GEOM_PLANE_PARALLEL || D->polarized) {
+            delete S;
+            return set_error("CentralPatchSurface is supported in unpolarized plane-parallel scenes only");
+        }
+        if (D->patch_bsdf_type < ERTB_BSDF_DIFFUSE || D->patch_bsdf_type > ERTB_BSDF_HAPKE ||
+            D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+            delete S;
+            return set_error("CentralPatchSurface: only the diffuse / rpv / rtls / hapke BSDFs can be blended");
+        }
+        S->has_patch = 1;
+        S->patch_bsdf_type = D->patch_bsdf_type;
+        memcpy(S->patch_bsdf_params, D->patch_bsdf_params, sizeof S->patch_bsdf_params);
+        memcpy(S->patch_rect, D->patch_rect, sizeof S->patch_rect);
+        S->needs_3d = true;
+    }
     memcpy(S->emitter_dir, D->emitter_direction, sizeof S->emitter_dir);
     S->irradiance = D->irradiance;
     S->integrator = D->integrator;
@@ -1094,6 +1122,11 @@ int ertb_scene_update(ertb_scene *S, int param, int index, const float *data, si
             if (need(2)) return 1;
             S->leaf_groups[index].reflectance = data[0];
             S->leaf_groups[index].transmittance = data[1];
+            break;
+        case ERTB_PARAM_PATCH_BSDF_PARAMS:
+            if (!S->has_patch) return set_error("scene has no central patch");
+            if (need(ERTB_MAX_BSDF_PARAMS)) return 1;
+            memcpy(S->patch_bsdf_params, data, sizeof S->patch_bsdf_params);
             break;
         case ERTB_PARAM_BSDF_PARAMS:
             if (need(ERTB_MAX_BSDF_PARAMS)) return 1;

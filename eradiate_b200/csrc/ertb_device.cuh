@@ -75,6 +75,10 @@ struct ErtbCanopy {
     int off_leaf_bsdf;        // table blob: per group bilambertian (reflectance, transmittance)
     double origin[3];
     double lo[3], hi[3];      // world-space bounding box of all instances
+    // CentralPatchSurface: a second ground BSDF (type, 16 params in the table blob) inside a rectangle
+    int patch_type;           // < 0: none
+    int off_patch_bsdf;
+    double patch_rect[4];     // cx, cy, hx, hy
 };
 
 struct ErtbParams {

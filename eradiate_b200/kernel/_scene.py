@@ -228,7 +228,7 @@ _SUPPORTED = {
     "emitter": {"directional"},
     "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance"},
     "medium": {"heterogeneous", "homogeneous", "piecewise"},
-    "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "null", "bilambertian"},
+    "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "null", "bilambertian", "blendbsdf"},
     "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
               "rayleigh_polarized", "tabphase_polarized"},
     "sensor": {"mdistant", "hdistant", "distantflux", "perspective", "mpdistant", "mradiancemeter"},
@@ -238,7 +238,6 @@ _KIND_OF = {ty: kind for kind, types in _SUPPORTED.items() for ty in types}
 # plugins the reference ships for this slot but that this kernel does not (yet) implement
 _KNOWN_UNSUPPORTED = {
     "cylinder": "canopy elements other than disk leaves (tree trunks) are not implemented",
-    "blendbsdf": "CentralPatchSurface (bitmap-blended ground BSDFs) is not implemented",
     "ply": "mesh canopy elements are not implemented",
     "obj": "mesh canopy elements are not implemented",
     # the reference's remaining plugins for this slot
@@ -420,6 +419,28 @@ class _Loader:
                 if name not in d:
                     raise RuntimeError(f"hapke: missing required parameter '{name}'")
                 b.children[name] = tex(name, 0.0)
+        elif ty == "blendbsdf":
+            # MI/src/bsdfs/blendbsdf.cpp as emitted by CentralPatchSurface (scenes/surface/_central_patch.py:
+            # 185-215): weight = the 3x3 central-patch mask (nearest filter, clamped), so the blend is a switch:
+            # bsdf_1 on the patch, bsdf_0 around it. Any other weight texture is rejected.
+            wt = d.get("weight")
+            ok = (isinstance(wt, dict) and wt.get("type") == "bitmap"
+                  and str(wt.get("filename", "")).endswith("central_patch_surface_mask.bmp")
+                  and wt.get("filter_type", "bilinear") == "nearest" and wt.get("wrap_mode", "repeat") == "clamp")
+            if not ok:
+                raise RuntimeError("blendbsdf: only the CentralPatchSurface form is supported (weight = the "
+                                   "'central_patch_surface_mask.bmp' bitmap, nearest filter, clamped)")
+            m = to_matrix(wt.get("to_uv"))
+            if not (m[0, 0] > 0 and m[1, 1] > 0 and abs(m[0, 1]) < 1e-12 and abs(m[1, 0]) < 1e-12):
+                raise RuntimeError("blendbsdf: unsupported 'to_uv' transform of the patch mask")
+            b.uv_scale = (float(m[0, 0]), float(m[1, 1]))
+            for key in ("bsdf_0", "bsdf_1"):
+                if key not in d:
+                    raise RuntimeError("BlendBSDF: Two child BSDFs must be specified!")
+                child = self.resolve(d[key])
+                if child.type not in ("diffuse", "rpv", "rtls", "hapke"):
+                    raise RuntimeError(f"blendbsdf: nested BSDF '{child.type}' is not supported")
+                b.children[key] = child
         elif ty == "bilambertian":  # ERP/bsdfs/bilambertian.cpp:44-49
             b.children["reflectance"] = tex("reflectance", 0.5)
             b.children["transmittance"] = tex("transmittance", 0.5)
@@ -780,6 +801,11 @@ class FlatScene:
         self.surface_shape = srf[0]
         self.atm_shape = atm[0] if atm else None
         self.bsdf: BSDF = self.surface_shape.children["bsdf"]
+        self.patch_bsdf: BSDF | None = None
+        if self.bsdf.type == "blendbsdf":  # CentralPatchSurface: background + patch
+            self.patch_blend = self.bsdf
+            self.patch_bsdf = self.bsdf.children["bsdf_1"]
+            self.bsdf = self.bsdf.children["bsdf_0"]
         if self.bsdf.type == "null":
             raise RuntimeError("the surface shape must not carry a null BSDF")
         if self.atm_shape is not None and self.atm_shape.children["bsdf"].type != "null":
@@ -787,6 +813,8 @@ class FlatScene:
 
         # geometry ------------------------------------------------------------------
         s = self.surface_shape
+        if s.type == "sphere" and self.patch_bsdf is not None:
+            raise RuntimeError("CentralPatchSurface is supported in plane-parallel scenes only")
         if s.type == "sphere":
             self.geometry = _abi.GEOM_SPHERICAL_SHELL
             if not np.allclose(s.center, 0.0, atol=1e-6 * s.radius):
@@ -798,6 +826,14 @@ class FlatScene:
             if not np.allclose(n / np.linalg.norm(n), [0, 0, 1], atol=1e-9):
                 raise RuntimeError("the ground rectangle must be horizontal (normal +Z)")
             self.surface_z = float(s.to_world[2, 3])
+            if self.patch_bsdf is not None:
+                # uv = (local + 1) / 2 over the rectangle; the mask's central third, shrunk by the to_uv scale
+                a = s.to_world[:3, :3]
+                if abs(a[0, 1]) > 1e-9 * abs(a[0, 0]) or abs(a[1, 0]) > 1e-9 * abs(a[1, 1]):
+                    raise RuntimeError("CentralPatchSurface: the ground rectangle must be axis-aligned")
+                sx, sy = self.patch_blend.uv_scale
+                self.patch_rect = (float(s.to_world[0, 3]), float(s.to_world[1, 3]),
+                                   abs(float(a[0, 0])) / (3.0 * sx), abs(float(a[1, 1])) / (3.0 * sy))
         else:
             raise RuntimeError(f"unsupported surface shape '{s.type}'")
 
@@ -967,8 +1003,8 @@ class FlatScene:
             )
         return leaves
 
-    def bsdf_params(self) -> np.ndarray:
-        b = self.bsdf
+    def bsdf_params(self, b: BSDF | None = None) -> np.ndarray:
+        b = self.bsdf if b is None else b
         p = np.zeros(_abi.MAX_BSDF_PARAMS, dtype=np.float32)
         tv = lambda name: b.children[name].values["value"]  # noqa: E731
         if b.type == "diffuse":
@@ -994,14 +1030,14 @@ class FlatScene:
         return (float(b.children["reflectance"].values["value"]),
                 float(b.children["transmittance"].values["value"]))
 
-    def bsdf_type(self) -> int:
+    def bsdf_type(self, b: BSDF | None = None) -> int:
         return {
             "diffuse": _abi.BSDF_DIFFUSE,
             "rpv": _abi.BSDF_RPV,
             "rtls": _abi.BSDF_RTLS,
             "hapke": _abi.BSDF_HAPKE,
             "ocean_legacy": _abi.BSDF_OCEAN_LEGACY,
-        }[self.bsdf.type]
+        }[(self.bsdf if b is None else b).type]
 
     # -- ctypes descriptor -----------------------------------------------------------------
     def build_desc(self) -> _abi.SceneDesc:
@@ -1107,6 +1143,11 @@ class FlatScene:
         keep.append(sens)
         d.n_sensors = len(self.sensors)
         d.sensors = C.cast(sens, C.POINTER(_abi.SensorDesc))
+        if self.patch_bsdf is not None:
+            d.has_patch = 1
+            d.patch_bsdf_type = self.bsdf_type(self.patch_bsdf)
+            d.patch_bsdf_params[:] = list(self.bsdf_params(self.patch_bsdf))
+            d.patch_rect[:] = list(self.patch_rect)
         if self.instances:
             groups = (_abi.LeafGroupDesc * len(self.leaf_groups))()
             for i, g in enumerate(self.leaf_groups):

@@ -118,6 +118,7 @@ def atmosphere_scene(
     force_majorant: bool | None = None,
     canopy: dict | None = None,
     extra_sensors: list | None = None,
+    central_patch: dict | None = None,
 ) -> dict:
     """Build the nested scene dict an ``AtmosphereExperiment`` would emit (with ``canopy``: a
     ``CanopyAtmosphereExperiment``, see :func:`disc_canopy`).
@@ -172,6 +173,26 @@ def atmosphere_scene(
             "bsdf": {"type": "ref", "id": "surface_bsdf"},
         }
         target = [0.0, 0.0, 0.0]
+
+    if central_patch is not None:
+        # CentralPatchSurface (scenes/surface/_central_patch.py:185-215): `surface` is the background, the
+        # patch BSDF covers `edges` around the origin; blendbsdf weighted by the 3x3 central-patch mask
+        if spherical:
+            raise ValueError("the central patch needs the plane-parallel geometry")
+        ex, ey = central_patch["edges"]
+        sx, sy = width / (3.0 * ex), width / (3.0 * ey)
+        background = dict(surface)
+        background.pop("id", None)
+        scene["surface_bsdf"] = {
+            "type": "blendbsdf", "id": "surface_bsdf",
+            "bsdf_0": background,
+            "bsdf_1": _spectrumify(dict(central_patch["bsdf"])),
+            "weight": {
+                "type": "bitmap", "filename": "texture/central_patch_surface_mask.bmp", "filter_type": "nearest",
+                "to_uv": ScalarTransform4f().scale([sx, sy, 1.0]).translate([-0.5 + 0.5 / sx, -0.5 + 0.5 / sy, 0.0]),
+                "wrap_mode": "clamp",
+            },
+        }
 
     if atmosphere is not None:
         if atmosphere == "afgl":

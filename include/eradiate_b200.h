@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 9
+#define ERTB_ABI_VERSION 10
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -208,6 +208,15 @@ typedef struct ertb_scene_desc {
     const ertb_leaf_group_desc *leaf_groups;
     const int32_t *instance_group;  /* n_instances: index into leaf_groups */
     const double *instance_offset;  /* n_instances x 3: translation of the instance */
+
+    /* CentralPatchSurface (src/eradiate/scenes/surface/_central_patch.py:185-215): a `blendbsdf` whose
+     * weight is the 3x3 central-patch mask, i.e. `patch_bsdf` inside the axis-aligned rectangle
+     * [cx - hx, cx + hx] x [cy - hy, cy + hy] of the ground plane and the scene BSDF (bsdf_type /
+     * bsdf_params = `bsdf_0`, the background) outside. Plane-parallel scenes; land BSDFs only. */
+    int32_t has_patch;
+    int32_t patch_bsdf_type;        /* enum ertb_bsdf_type; not the ocean */
+    float patch_bsdf_params[ERTB_MAX_BSDF_PARAMS];
+    double patch_rect[4];           /* cx, cy, hx, hy (metres) */
 } ertb_scene_desc;
 
 /* Named updatable parameters (KernelSceneParameterMap keys resolve to these;
@@ -222,7 +231,8 @@ enum ertb_param {
     ERTB_PARAM_IRRADIANCE = 5,   /* float[1] */
     ERTB_PARAM_PHASE_PARAMS = 6, /* index = leaf; float[4] */
     ERTB_PARAM_PHASE_MUELLER = 7, /* index = leaf * 5 + k (k: m12, m22, m33, m34, m44); float[n_nodes] */
-    ERTB_PARAM_LEAF_BSDF = 8     /* index = leaf group; float[2]: reflectance, transmittance */
+    ERTB_PARAM_LEAF_BSDF = 8,    /* index = leaf group; float[2]: reflectance, transmittance */
+    ERTB_PARAM_PATCH_BSDF_PARAMS = 9 /* float[ERTB_MAX_BSDF_PARAMS]: the central patch's BSDF */
 };
 
 typedef struct ertb_render_stats {

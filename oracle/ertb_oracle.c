@@ -1044,12 +1044,10 @@ static double eval_hapke(const float *P, v3 wi, v3 wo) {
 }
 
 /* BSDF::eval (value * cos_theta_o), local frame */
-static double bsdf_eval(const scene_t *S, v3 wi, v3 wo) {
-    const ertb_scene_desc *d = S->desc;
+static double bsdf_eval_tp(const scene_t *S, int type, const float *P, v3 wi, v3 wo) {
     double cti = wi.z, cto = wo.z;
     if (!(cti > 0.0 && cto > 0.0)) return 0.0;
-    const float *P = d->bsdf_params;
-    switch (d->bsdf_type) {
+    switch (type) {
         case ERTB_BSDF_DIFFUSE: return (double) P[0] * INV_PI * cto;  /* diffuse.cpp:127-143 */
         case ERTB_BSDF_RPV: return eval_rpv(P, wi, wo) * fabs(cto);   /* rpv.cpp:169-181 */
         case ERTB_BSDF_RTLS: return eval_rtls(P, wi, wo) * fabs(cto); /* rtls.cpp:245-257 */
@@ -1058,12 +1056,14 @@ static double bsdf_eval(const scene_t *S, v3 wi, v3 wo) {
         default: return 0.0;
     }
 }
+static double bsdf_eval(const scene_t *S, v3 wi, v3 wo) {
+    return bsdf_eval_tp(S, S->desc->bsdf_type, S->desc->bsdf_params, wi, wo);
+}
 /* BSDF::sample -> wo (local), weight = eval / pdf */
-static double bsdf_sample(const scene_t *S, v3 wi, double s1, double u1, double u2, v3 *wo) {
-    const ertb_scene_desc *d = S->desc;
+static double bsdf_sample_tp(const scene_t *S, int type, const float *P, v3 wi, double s1, double u1, double u2, v3 *wo) {
     *wo = V(0, 0, 1);
     if (!(wi.z > 0.0)) return 0.0;
-    if (d->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+    if (type == ERTB_BSDF_OCEAN_LEGACY) {
         double o[3], w = ocean_sample(&S->ocean, wi.x, wi.y, wi.z, s1, u1, u2, o);
         *wo = V(o[0], o[1], o[2]);
         return w;
@@ -1073,14 +1073,21 @@ static double bsdf_sample(const scene_t *S, v3 wi, double s1, double u1, double 
     *wo = V(o[0], o[1], o[2]);
     double pdf = INV_PI * o[2];
     if (!(pdf > 0.0)) return 0.0;
-    const float *P = d->bsdf_params;
-    switch (d->bsdf_type) {
+    switch (type) {
         case ERTB_BSDF_DIFFUSE: return (double) P[0];               /* diffuse.cpp:121-123 */
         case ERTB_BSDF_RPV: return eval_rpv(P, wi, *wo) * o[2] / pdf; /* rpv.cpp:119-122 */
         case ERTB_BSDF_RTLS: return eval_rtls(P, wi, *wo) * o[2] / pdf;
         case ERTB_BSDF_HAPKE: return eval_hapke(P, wi, *wo) * o[2] / pdf;
         default: return 0.0;
     }
+}
+static double bsdf_sample(const scene_t *S, v3 wi, double s1, double u1, double u2, v3 *wo) {
+    return bsdf_sample_tp(S, S->desc->bsdf_type, S->desc->bsdf_params, wi, s1, u1, u2, wo);
+}
+/* CentralPatchSurface: blendbsdf.cpp:108-165 with the 0/1 central-patch mask as weight = bsdf_1 on the patch */
+static int on_patch(const scene_t *S, v3 p) {
+    const ertb_scene_desc *d = S->desc;
+    return d->has_patch && fabs(p.x - d->patch_rect[0]) <= d->patch_rect[2] && fabs(p.y - d->patch_rect[1]) <= d->patch_rect[3];
 }
 
 /* BSDF of the shape that was hit: the ground model or a leaf group's bilambertian */
@@ -1090,6 +1097,7 @@ static double surf_eval(const scene_t *S, const si_t *si, v3 wi, v3 wo) {
         double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
         return bilambertian_eval(G->reflectance, G->transmittance, a, b);
     }
+    if (on_patch(S, si->p)) return bsdf_eval_tp(S, S->desc->patch_bsdf_type, S->desc->patch_bsdf_params, wi, wo);
     return bsdf_eval(S, wi, wo);
 }
 static double surf_sample(const scene_t *S, const si_t *si, v3 wi, double s1, double u1, double u2, v3 *wo) {
@@ -1100,6 +1108,8 @@ static double surf_sample(const scene_t *S, const si_t *si, v3 wi, double s1, do
         *wo = V(o[0], o[1], o[2]);
         return w;
     }
+    if (on_patch(S, si->p))
+        return bsdf_sample_tp(S, S->desc->patch_bsdf_type, S->desc->patch_bsdf_params, wi, s1, u1, u2, wo);
     return bsdf_sample(S, wi, s1, u1, u2, wo);
 }
 

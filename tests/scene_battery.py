@@ -179,6 +179,13 @@ def battery() -> dict:
             sensor={"type": "mradiancemeter", "medium": {"type": "ref", "id": "medium_atmosphere"},
                     "origins": [[0.0, 0.0, scenes.EARTH_RADIUS + 2.0]] * 3,
                     "directions": [[0.0, 0.0, 1.0], [-0.5735764, 0.0, 0.8191520], [0.4096, 0.7094, 0.5735764]]})),
+        # CentralPatchSurface: RPV patch under the canopy cell, Lambertian background around it
+        "central_patch_canopy_mpdistant_pp": S(
+            geometry="plane_parallel", n_layers=60, sza=35.0, saa=10.0, canopy=dict(CANOPY, lai=1.0, padding=0),
+            surface={"type": "diffuse", "reflectance": 0.05},
+            central_patch={"edges": (4.0, 4.0), "bsdf": {"type": "rpv", "rho_0": 0.25, "k": 0.8, "g": -0.1}},
+            sensor={"type": "mpdistant", "vza": 20.0, "vaa": 45.0, "film_resolution": (3, 3),
+                    "target": {"type": "rectangle", "to_world": scenes.ScalarTransform4f().scale([4.0, 4.0, 1.0])}}),
         "mpdistant_canopy_image_pp": S(geometry="plane_parallel", n_layers=60, sza=30.0, canopy=CANOPY,
                                        sensor={"type": "mpdistant", "vza": 25.0, "vaa": 60.0, "film_resolution": (3, 2)}),
         "mpdistant_spherical": S(n_layers=100, sza=60.0, sensor={"type": "mpdistant", "vza": 40.0, "vaa": 0.0,

@@ -207,3 +207,25 @@ def test_perspective_sensor_ray_convention(oracle):
     left /= np.linalg.norm(left)
     assert dirs[1] @ left > 0 > dirs[2] @ left
     assert dirs[3][2] > dirs[4][2]  # film y = 0 is the top row
+
+
+def test_central_patch_surface_switches_bsdf_on_the_patch(oracle):
+    """CentralPatchSurface = blendbsdf with the 0/1 central-patch mask (blendbsdf.cpp:108-165): seen from
+    infinity without an atmosphere, pixels on the patch show rho_1 E cos / pi, pixels around it rho_0 E cos / pi."""
+    sza, rho0, rho1 = 40.0, 0.1, 0.6
+    sc = mi_load_dict(scenes.atmosphere_scene(
+        geometry="plane_parallel", atmosphere=None, integrator="path", sza=sza,
+        surface={"type": "diffuse", "reflectance": rho0},
+        central_patch={"edges": (4.0, 2.0), "bsdf": {"type": "diffuse", "reflectance": rho1}},
+        sensor={"type": "mpdistant", "vza": 30.0, "vaa": 70.0, "film_resolution": (4, 4),
+                # an 8 m x 8 m image around the origin: 2 m pixels; the patch covers |x| <= 2, |y| <= 1
+                "target": {"type": "rectangle", "to_world": scenes.ScalarTransform4f().scale([4.0, 4.0, 1.0])}}))
+    d = sc.flat.build_desc()
+    assert d.has_patch == 1 and np.allclose(list(d.patch_rect), [0.0, 0.0, 2.0, 1.0])
+    mean, err, _, _ = _render(oracle, d, 20000)
+    img, err = mean.reshape(4, 4), err.reshape(4, 4)  # [row = y, column = x], pixels span [-4,-2], [-2,0], [0,2], [2,4]
+    e = E0 * np.cos(np.radians(sza)) / np.pi
+    assert np.allclose(img[[0, 3], :], rho0 * e, rtol=1e-6)      # |y| > 2: background
+    assert np.allclose(img[:, [0, 3]], rho0 * e, rtol=1e-6)      # |x| > 2: background
+    # the four central pixels: |x| <= 2 is on the patch, |y| <= 1 is half of each pixel's height
+    assert np.all(np.abs(img[1:3, 1:3] - 0.5 * (rho0 + rho1) * e) < 5.0 * err[1:3, 1:3] + 1e-9)

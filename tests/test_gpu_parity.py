@@ -273,6 +273,30 @@ def test_canopy_leaf_optics_update_equals_fresh_scene():
     assert np.allclose(b, c, rtol=1e-9) and np.all(b < 0.8 * a)
 
 
+def test_central_patch_surface_on_device():
+    """CentralPatchSurface in the 3D kernel: same closed form the oracle is pinned on, and the patch BSDF is an
+    updatable scene parameter (`<shape>.bsdf.bsdf_1.*`, _central_patch.py:228-243)."""
+    sza, rho0, rho1 = 40.0, 0.1, 0.6
+    sc = mi_load_dict(scenes.atmosphere_scene(
+        geometry="plane_parallel", atmosphere=None, integrator="path", sza=sza,
+        surface={"type": "diffuse", "reflectance": rho0},
+        central_patch={"edges": (4.0, 4.0), "bsdf": {"type": "diffuse", "reflectance": rho1}},
+        sensor={"type": "mpdistant", "vza": 30.0, "vaa": 70.0, "film_resolution": (4, 4),
+                "target": {"type": "rectangle", "to_world": scenes.ScalarTransform4f().scale([4.0, 4.0, 1.0])}}))
+    e = np.float32(1.8) * np.cos(np.radians(sza)) / np.pi
+    spp = 1 << 12
+    img = (render(sc, seed=2, spp=spp).raw["sum_l"] / spp).reshape(4, 4)
+    want = np.full((4, 4), rho0 * e)
+    want[1:3, 1:3] = rho1 * e  # the patch covers |x|, |y| <= 2 = the four central 2 m pixels
+    assert np.allclose(img, want, rtol=2e-6)
+    w = mi_traverse(sc)
+    w.parameters.update({"surface_shape.bsdf.bsdf_1.reflectance.value": 0.9, "surface_shape.bsdf.bsdf_0.reflectance.value": 0.2})
+    img = (render(sc, seed=2, spp=spp).raw["sum_l"] / spp).reshape(4, 4)
+    want = np.full((4, 4), 0.2 * e)
+    want[1:3, 1:3] = 0.9 * e
+    assert np.allclose(img, want, rtol=2e-6)
+
+
 def test_canopy_gap_fraction_on_device():
     """Same analytic answer the oracle is pinned on (tests/test_canopy_oracle.py): planophile black leaves
     over a white ground, hot spot exp(-LAI) vs decorrelated exp(-2 LAI) (up to the leaf-size correlation)."""

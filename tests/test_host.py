@@ -197,8 +197,8 @@ def test_desc_struct_layout_is_stable():
     assert C.sizeof(_abi.RenderStats) == 56
     assert C.sizeof(_abi.SensorDesc) == 360
     assert C.sizeof(_abi.LeafGroupDesc) == 24
-    assert C.sizeof(_abi.SceneDesc) == 608
-    assert _abi.SceneDesc.instance_offset.offset + 8 == C.sizeof(_abi.SceneDesc)
+    assert C.sizeof(_abi.SceneDesc) == 712
+    assert _abi.SceneDesc.patch_rect.offset + 32 == C.sizeof(_abi.SceneDesc)
 
 
 # ------------------------------------------------------------------ canopy / 3D scenes (host side)
