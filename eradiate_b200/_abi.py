@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -66,6 +66,7 @@ PARAM_PHASE_PARAMS = 6
 PARAM_PHASE_MUELLER = 7
 PARAM_LEAF_BSDF = 8
 PARAM_PATCH_BSDF_PARAMS = 9
+PARAM_TRUNK_BSDF = 10
 
 c_float_p = C.POINTER(C.c_float)
 c_double_p = C.POINTER(C.c_double)
@@ -111,6 +112,12 @@ class LeafGroupDesc(C.Structure):
         ("transmittance", C.c_float),
         ("_pad", C.c_int32),
         ("disks", c_float_p),
+        ("n_cylinders", C.c_int32),
+        ("n_trunk_disks", C.c_int32),
+        ("cylinders", c_float_p),
+        ("trunk_disks", c_float_p),
+        ("trunk_reflectance", C.c_float),
+        ("_pad2", C.c_int32),
     ]
 
 

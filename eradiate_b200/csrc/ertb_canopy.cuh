@@ -69,6 +69,31 @@ __device__ __forceinline__ float disk_hit(float4 c, float4 n, f3 o, f3 d, float 
 #define ERTB_TRACE_STACK 40
 
 // A BVH walk that can be suspended: everything but the stack (a per-lane local array).
+// cylinder.cpp:560-615: open tube of radius c.w around the segment (c.xyz, c.xyz + ax.xyz); quadratic in the
+// plane orthogonal to the axis, near root first, the far one if the near one is cut off by the ends
+__device__ __forceinline__ float cylinder_hit(float4 c, float4 ax, f3 o, f3 d, float tmax) {
+    const float L2 = ax.x * ax.x + ax.y * ax.y + ax.z * ax.z, iL = rsqrtf(L2), L = L2 * iL;
+    const f3 u = mk3(ax.x * iL, ax.y * iL, ax.z * iL), w = mk3(o.x - c.x, o.y - c.y, o.z - c.z);
+    const float du = dot3(d, u), wu = dot3(w, u);
+    const f3 dp = fma3(u, -du, d), wp = fma3(u, -wu, w);
+    const float A = dot3(dp, dp), B = 2.f * dot3(dp, wp), Cc = dot3(wp, wp) - c.w * c.w;
+    const float disc = B * B - 4.f * A * Cc;
+    if (!(A > 0.f) || disc < 0.f) return INFINITY;
+    const float temp = -0.5f * (B + copysignf(sqrtf(disc), B));
+    float x0 = temp / A, x1 = Cc / temp;
+    if (temp == 0.f) x0 = x1 = 0.f;
+    const float tn = fminf(x0, x1), tf = fmaxf(x0, x1);
+    if (!(tn <= tmax && tf >= 0.f) || (tn < 0.f && tf > tmax)) return INFINITY;
+    const float zn = fmaf(du, tn, wu), zf = fmaf(du, tf, wu);
+    if (zn >= 0.f && zn <= L && tn >= 0.f) return tn;
+    if (zf >= 0.f && zf <= L && tf <= tmax) return tf;
+    return INFINITY;
+}
+
+__device__ __forceinline__ float prim_hit(float4 a, float4 b, f3 o, f3 d, float tmax) {
+    return __float_as_int(b.w) == 2 ? cylinder_hit(a, b, o, d, tmax) : disk_hit(a, b, o, d, tmax);
+}
+
 struct TraceState {
     f3 o;        // ray origin, canopy-local
     float tmax;
@@ -111,7 +136,7 @@ __device__ __forceinline__ bool trace_run(const ErtbCanopy &C, TraceState &T, in
             } else { // disks: intersected on the spot
                 for (int k = c[s]; k < c[s] + n[s]; ++k) {
                     if (k == T.skip_disk && ii == T.skip_inst) continue;
-                    float t = disk_hit(__ldg(C.disks + 2 * k), __ldg(C.disks + 2 * k + 1), ol, d, fminf(T.tmax, T.H.t));
+                    float t = prim_hit(__ldg(C.disks + 2 * k), __ldg(C.disks + 2 * k + 1), ol, d, fminf(T.tmax, T.H.t));
                     if (t < T.H.t) { T.H.t = t; T.H.inst = ii; T.H.disk = k; }
                 }
             }
@@ -169,6 +194,19 @@ __device__ __forceinline__ bool canopy_clip(const ErtbCanopy &C, const double p[
 __device__ __forceinline__ f3 canopy_local(const ErtbCanopy &C, const double p[3], f3 d, double t0) {
     return mk3((float) (p[0] + t0 * (double) d.x - C.origin[0]), (float) (p[1] + t0 * (double) d.y - C.origin[1]),
                (float) (p[2] + t0 * (double) d.z - C.origin[2]));
+}
+
+// surface normal and kind (0 leaf, 1 trunk cap, 2 trunk tube) of the primitive hit at world point q
+__device__ __forceinline__ f3 canopy_normal(const ErtbCanopy &C, const double q[3], const CanopyHit &H, int &kind) {
+    const float4 a = __ldg(C.disks + 2 * H.disk), b = __ldg(C.disks + 2 * H.disk + 1);
+    kind = __float_as_int(b.w);
+    if (kind != 2) return mk3(b.x, b.y, b.z);
+    const float4 in = __ldg(C.inst + H.inst);
+    const f3 w = mk3((float) (q[0] - C.origin[0]) - in.x - a.x, (float) (q[1] - C.origin[1]) - in.y - a.y,
+                     (float) (q[2] - C.origin[2]) - in.z - a.z);
+    const float iL = rsqrtf(b.x * b.x + b.y * b.y + b.z * b.z);
+    const f3 u = mk3(b.x * iL, b.y * iL, b.z * iL);
+    return normalize3(fma3(u, -dot3(w, u), w)); // radial, pointing outwards
 }
 
 // nearest leaf along a world-space segment; returns the distance from p (INFINITY: none)
@@ -563,15 +601,18 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 // ---- leaf: bilambertian reflection / transmission; the medium does not change ----
                 if (STATS) st_surface++;
                 float4 in = __ldg(C.inst + T.H.inst);
-                float4 nn = __ldg(C.disks + 2 * T.H.disk + 1);
-                const float *lb = tb + C.off_leaf_bsdf + 2 * __float_as_int(in.w);
-                f3 n = mk3(nn.x, nn.y, nn.z);
+                const float *lb = tb + C.off_leaf_bsdf + 4 * __float_as_int(in.w);
+                int kind;
+                f3 n = canopy_normal(C, p, T.H, kind);
                 float ci = -dot3(n, d);
                 on_inst = T.H.inst; on_disk = T.H.disk;
-                if (depth + 1u < P.max_depth) nee = thr * bilambertian_eval(lb[0], lb[1], ci, dot3(n, sun)) * P.irradiance;
+                // leaves: bilambertian (r, t); trunk parts: one-sided Lambertian = (rho, 0) seen from the front only
+                float r_ = lb[0], t_ = lb[1];
+                if (kind != 0) { r_ = ci > 0.f ? lb[2] : 0.f; t_ = 0.f; }
+                if (depth + 1u < P.max_depth) nee = thr * bilambertian_eval(r_, t_, ci, dot3(n, sun)) * P.irradiance;
                 float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
                 f3 wl;
-                thr *= bilambertian_sample(lb[0], lb[1], ci, s1, u1, u2, wl);
+                thr *= bilambertian_sample(r_, t_, ci, s1, u1, u2, wl);
                 f3 fs, ft;
                 onb(n, fs, ft);
                 d = normalize3(fma3(fs, wl.x, fma3(ft, wl.y, scale3(n, wl.z))));

@@ -93,8 +93,10 @@ struct BatchState {
 // canopy: host copy + BVH construction
 // ----------------------------------------------------------------------------
 struct HostLeafGroup {
-    std::vector<float> disks; // n x 7
-    float reflectance = 0.f, transmittance = 0.f;
+    std::vector<float> disks;       // n x 7 leaves
+    std::vector<float> trunk_disks; // trunk caps (diffuse)
+    std::vector<float> cylinders;   // n x 7: p0, p1, radius (diffuse)
+    float reflectance = 0.f, transmittance = 0.f, trunk_reflectance = 0.f;
 };
 
 struct BvhBox {
@@ -292,19 +294,42 @@ static int build_canopy(ertb_scene *S) {
     // world bounding box of every instance
     std::vector<BvhBox> gbox(ng, BvhBox::empty());
     std::vector<std::vector<BvhBox>> dboxes(ng);
+    // primitives of a group, in this order: leaf disks (kind 0), trunk cap disks (kind 1), cylinders (kind 2)
+    std::vector<std::vector<float>> prims(ng); // 8 floats each: device record, kind in the last slot
     for (int g = 0; g < ng; ++g) {
-        const std::vector<float> &dk = S->leaf_groups[g].disks;
-        const int n = (int) dk.size() / 7;
-        dboxes[g].resize(n);
-        for (int i = 0; i < n; ++i) {
+        const HostLeafGroup &hg = S->leaf_groups[g];
+        for (int pass = 0; pass < 2; ++pass) {
+            const std::vector<float> &dk = pass == 0 ? hg.disks : hg.trunk_disks;
+            for (size_t i = 0; i < dk.size() / 7; ++i) {
+                const float *q = &dk[7 * i];
+                BvhBox b;
+                for (int k = 0; k < 3; ++k) {
+                    float e = q[6] * sqrtf(fmaxf(1.f - q[3 + k] * q[3 + k], 0.f));
+                    b.lo[k] = q[k] - e; b.hi[k] = q[k] + e;
+                }
+                dboxes[g].push_back(b);
+                gbox[g].grow(b);
+                int kind = pass;
+                float row[8] = { q[0], q[1], q[2], q[6], q[3], q[4], q[5], 0.f };
+                memcpy(&row[7], &kind, sizeof(float));
+                prims[g].insert(prims[g].end(), row, row + 8);
+            }
+        }
+        for (size_t i = 0; i < hg.cylinders.size() / 7; ++i) {
+            const float *q = &hg.cylinders[7 * i];
+            const float ax[3] = { q[3] - q[0], q[4] - q[1], q[5] - q[2] };
+            const float L = sqrtf(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
             BvhBox b;
             for (int k = 0; k < 3; ++k) {
-                float nk = dk[7 * i + 3 + k];
-                float e = dk[7 * i + 6] * sqrtf(fmaxf(1.f - nk * nk, 0.f));
-                b.lo[k] = dk[7 * i + k] - e; b.hi[k] = dk[7 * i + k] + e;
+                float u = ax[k] / L, e = q[6] * sqrtf(fmaxf(1.f - u * u, 0.f));
+                b.lo[k] = fminf(q[k], q[3 + k]) - e; b.hi[k] = fmaxf(q[k], q[3 + k]) + e;
             }
-            dboxes[g][i] = b;
+            dboxes[g].push_back(b);
             gbox[g].grow(b);
+            int kind = 2;
+            float row[8] = { q[0], q[1], q[2], q[6], ax[0], ax[1], ax[2], 0.f }; // p0, radius | axis vector p1 - p0
+            memcpy(&row[7], &kind, sizeof(float));
+            prims[g].insert(prims[g].end(), row, row + 8);
         }
     }
     double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
@@ -327,12 +352,7 @@ static int build_canopy(ertb_scene *S) {
     for (int g = 0; g < ng; ++g) {
         std::vector<int> order;
         blas_root[g] = build_bvh(dboxes[g], blas, order, (int) disks.size() / 8);
-        const std::vector<float> &dk = S->leaf_groups[g].disks;
-        for (int i : order) {
-            const float *q = &dk[7 * (size_t) i];
-            const float row[8] = { q[0], q[1], q[2], q[6], q[3], q[4], q[5], 0.f };
-            disks.insert(disks.end(), row, row + 8);
-        }
+        for (int i : order) disks.insert(disks.end(), &prims[g][8 * (size_t) i], &prims[g][8 * (size_t) i] + 8);
     }
     // top level over the instances (float coordinates relative to the canopy origin)
     std::vector<BvhBox> iboxes(ninst);
@@ -627,7 +647,9 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
     P.inv_majorant = majorant > 0.0 ? (float) (1.0 / majorant) : INFINITY;
     P.canopy = S->canopy;
     P.canopy.off_leaf_bsdf = (int) blob.size();
-    for (const HostLeafGroup &g : S->leaf_groups) { blob.push_back(g.reflectance); blob.push_back(g.transmittance); }
+    for (const HostLeafGroup &g : S->leaf_groups) { // 4 floats per group: leaf r, leaf t, trunk rho, -
+        blob.push_back(g.reflectance); blob.push_back(g.transmittance); blob.push_back(g.trunk_reflectance); blob.push_back(0.f);
+    }
     blob.resize(align4(blob.size()), 0.f);
     P.canopy.patch_type = -1;
     if (S->has_patch) { // the patch BSDF travels with the tables (spectral updates, batch slots)
@@ -1001,6 +1023,11 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
             hg.disks.assign(gd.disks, gd.disks + 7 * (size_t) gd.n_disks);
             hg.reflectance = gd.reflectance;
             hg.transmittance = gd.transmittance;
+            if ((gd.n_trunk_disks > 0 && !gd.trunk_disks) || (gd.n_cylinders > 0 && !gd.cylinders) ||
+                gd.n_trunk_disks < 0 || gd.n_cylinders < 0) { delete S; return set_error("trunk arrays missing"); }
+            if (gd.n_trunk_disks) hg.trunk_disks.assign(gd.trunk_disks, gd.trunk_disks + 7 * (size_t) gd.n_trunk_disks);
+            if (gd.n_cylinders) hg.cylinders.assign(gd.cylinders, gd.cylinders + 7 * (size_t) gd.n_cylinders);
+            hg.trunk_reflectance = gd.trunk_reflectance;
             S->leaf_groups.push_back(hg);
         }
         for (int i = 0; i < D->n_instances; ++i) {
@@ -1122,6 +1149,11 @@ int ertb_scene_update(ertb_scene *S, int param, int index, const float *data, si
             if (need(2)) return 1;
             S->leaf_groups[index].reflectance = data[0];
             S->leaf_groups[index].transmittance = data[1];
+            break;
+        case ERTB_PARAM_TRUNK_BSDF:
+            if (index < 0 || index >= (int) S->leaf_groups.size()) return set_error("invalid leaf group index");
+            if (need(1)) return 1;
+            S->leaf_groups[index].trunk_reflectance = data[0];
             break;
         case ERTB_PARAM_PATCH_BSDF_PARAMS:
             if (!S->has_patch) return set_error("scene has no central patch");
@@ -1758,9 +1790,12 @@ __global__ void kat_canopy_intersect_kernel(ErtbParams P, size_t n, const double
     group[i] = -1;
     normal[3 * i] = normal[3 * i + 1] = normal[3 * i + 2] = 0.f;
     if (H.inst >= 0) {
-        float4 in = __ldg(P.canopy.inst + H.inst), nn = __ldg(P.canopy.disks + 2 * H.disk + 1);
+        float4 in = __ldg(P.canopy.inst + H.inst);
         group[i] = __float_as_int(in.w);
-        normal[3 * i] = nn.x; normal[3 * i + 1] = nn.y; normal[3 * i + 2] = nn.z;
+        double q[3] = { p[0] + th * (double) d.x, p[1] + th * (double) d.y, p[2] + th * (double) d.z };
+        int kind;
+        f3 n = canopy_normal(P.canopy, q, H, kind);
+        normal[3 * i] = n.x; normal[3 * i + 1] = n.y; normal[3 * i + 2] = n.z;
     }
 }
 

@@ -71,8 +71,9 @@ struct ErtbCanopy {
     const float4 *inst;       // (offset xyz relative to `origin`, group index as int bits)
     const ErtbBvhNode *blas;  // all groups' trees, concatenated
     const int *blas_root;     // per group: root node index in `blas`
-    const float4 *disks;      // 2 per disk, in BVH leaf order: (centre xyz, radius) (normal xyz, -)
-    int off_leaf_bsdf;        // table blob: per group bilambertian (reflectance, transmittance)
+    const float4 *disks;      // 2 per primitive, in BVH leaf order: disk (centre, radius) (normal, kind 0 leaf / 1 trunk
+                              // cap); cylinder (p0, radius) (axis vector p1 - p0, kind 2)
+    int off_leaf_bsdf;        // table blob: per group (leaf reflectance, leaf transmittance, trunk reflectance, -)
     double origin[3];
     double lo[3], hi[3];      // world-space bounding box of all instances
     // CentralPatchSurface: a second ground BSDF (type, 16 params in the table blob) inside a rectangle

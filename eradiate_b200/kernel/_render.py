@@ -124,6 +124,8 @@ class DeviceScene:
                         push(_abi.PARAM_PHASE_MUELLER, 5 * i + k, arr)
         for i in range(len(flat.leaf_groups) if flat.instances else 0):
             push(_abi.PARAM_LEAF_BSDF, i, flat.leaf_bsdf_params(i))
+            if "trunk_bsdf" in flat.leaf_groups[i].children:
+                push(_abi.PARAM_TRUNK_BSDF, i, [flat.trunk_reflectance(i)])
         if flat.patch_bsdf is not None:
             push(_abi.PARAM_PATCH_BSDF_PARAMS, 0, flat.bsdf_params(flat.patch_bsdf))
         push(_abi.PARAM_BSDF_PARAMS, 0, flat.bsdf_params())

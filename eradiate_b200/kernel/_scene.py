@@ -226,7 +226,7 @@ class Scene(Object):
 _SUPPORTED = {
     "integrator": {"volpath", "volpathmis", "piecewise_volpath", "path", "moment", "stokes"},
     "emitter": {"directional"},
-    "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance"},
+    "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance", "cylinder"},
     "medium": {"heterogeneous", "homogeneous", "piecewise"},
     "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "null", "bilambertian", "blendbsdf"},
     "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
@@ -237,7 +237,6 @@ _SUPPORTED = {
 _KIND_OF = {ty: kind for kind, types in _SUPPORTED.items() for ty in types}
 # plugins the reference ships for this slot but that this kernel does not (yet) implement
 _KNOWN_UNSUPPORTED = {
-    "cylinder": "canopy elements other than disk leaves (tree trunks) are not implemented",
     "ply": "mesh canopy elements are not implemented",
     "obj": "mesh canopy elements are not implemented",
     # the reference's remaining plugins for this slot
@@ -513,25 +512,45 @@ class _Loader:
         if ty == "shapegroup":
             # src/eradiate/scenes/biosphere/_core.py:266-275: a group of `disk` leaves. The disks are
             # kept as one [n, 7] array, not as one node each (a RAMI canopy has > 10^5 of them).
-            rows, bsdf = [], None
+            rows, trunk_rows, cyl_rows, bsdf, trunk_bsdf = [], [], [], None, None
             for key, v in d.items():
                 if not isinstance(v, dict) or "type" not in v:
                     continue
                 if v["type"] in _KNOWN_UNSUPPORTED:
                     raise RuntimeError(f"unsupported plugin '{v['type']}': {_KNOWN_UNSUPPORTED[v['type']]}")
-                if v["type"] != "disk":
-                    raise RuntimeError(f"shapegroup: unsupported child shape '{v['type']}' (only 'disk')")
+                if v["type"] not in ("disk", "cylinder"):
+                    raise RuntimeError(f"shapegroup: unsupported child shape '{v['type']}' (only 'disk' and 'cylinder')")
                 b = self._child_bsdf(v)
-                if bsdf is not None and b is not bsdf:
-                    raise RuntimeError("shapegroup: all leaves of a group must share one BSDF")
-                bsdf = b
-                rows.append(self._disk_row(to_matrix(v.get("to_world"))))
+                if b.type == "bilambertian" and v["type"] == "disk":  # a leaf
+                    if bsdf is not None and b is not bsdf:
+                        raise RuntimeError("shapegroup: all leaves of a group must share one BSDF")
+                    bsdf = b
+                    rows.append(self._disk_row(to_matrix(v.get("to_world"))))
+                elif b.type == "diffuse":  # trunk parts (_tree.py:150-180): a cylinder and its cap
+                    if trunk_bsdf is not None and b is not trunk_bsdf:
+                        raise RuntimeError("shapegroup: all trunk parts of a group must share one BSDF")
+                    trunk_bsdf = b
+                    if v["type"] == "disk":
+                        trunk_rows.append(self._disk_row(to_matrix(v.get("to_world"))))
+                    else:  # MI/src/shapes/cylinder.cpp:110-135: p0, p1, radius
+                        if "to_world" in v and not np.allclose(to_matrix(v["to_world"]), np.eye(4)):
+                            raise RuntimeError("cylinder: specify p0 / p1 / radius (to_world is unsupported)")
+                        p0 = np.asarray(v.get("p0", [0.0, 0.0, 0.0]), dtype=np.float64)
+                        p1 = np.asarray(v.get("p1", [0.0, 0.0, 1.0]), dtype=np.float64)
+                        if not np.linalg.norm(p1 - p0) > 0:
+                            raise RuntimeError("cylinder: p0 and p1 must differ")
+                        cyl_rows.append([*p0, *p1, float(v.get("radius", 1.0))])
+                else:
+                    raise RuntimeError(f"canopy leaves must carry a bilambertian BSDF and trunks a diffuse one, "
+                                       f"got '{b.type}' on a {v['type']}")
             if not rows:
-                raise RuntimeError("shapegroup: no child shapes")
-            if bsdf.type != "bilambertian":
-                raise RuntimeError(f"canopy leaves must carry a bilambertian BSDF, got '{bsdf.type}'")
+                raise RuntimeError("shapegroup: no leaf (bilambertian disk) among the child shapes")
             s.disks = np.asarray(rows, dtype=np.float64)
+            s.trunk_disks = np.asarray(trunk_rows, dtype=np.float64).reshape(-1, 7)
+            s.cylinders = np.asarray(cyl_rows, dtype=np.float64).reshape(-1, 7)
             s.children["bsdf"] = bsdf
+            if trunk_bsdf is not None:
+                s.children["trunk_bsdf"] = trunk_bsdf
             return s
         if ty == "instance":
             # _core.py:277-296: `group` reference + translation
@@ -553,6 +572,8 @@ class _Loader:
             if bsdf.type != "bilambertian":
                 raise RuntimeError(f"canopy leaves must carry a bilambertian BSDF, got '{bsdf.type}'")
             s.disks = np.asarray([self._disk_row(s.to_world)], dtype=np.float64)
+            s.trunk_disks = np.zeros((0, 7))
+            s.cylinders = np.zeros((0, 7))
             s.children["bsdf"] = bsdf
             return s
         if ty == "sphere":
@@ -870,9 +891,14 @@ class FlatScene:
                 raise RuntimeError("explicit canopies are supported in plane-parallel scenes only "
                                    "(src/eradiate/experiments/_canopy_atmosphere.py:74)")
             for gi, off in self.instances:
-                dk = self.leaf_groups[gi].disks
+                g = self.leaf_groups[gi]
+                dk = np.vstack([g.disks, g.trunk_disks])
                 ext = dk[:, 6:7] * np.sqrt(np.maximum(1.0 - dk[:, 3:6] ** 2, 0.0))
                 lo, hi = (dk[:, :3] - ext).min(axis=0) + off, (dk[:, :3] + ext).max(axis=0) + off
+                for c in g.cylinders:
+                    lo = np.minimum(lo, np.minimum(c[:3], c[3:6]) - c[6] + off)
+                    hi = np.maximum(hi, np.maximum(c[:3], c[3:6]) + c[6] + off)
+                dk = g.disks
                 bbox_lo, bbox_hi = np.minimum(bbox_lo, lo), np.maximum(bbox_hi, hi)
                 if (dk[:, 2] + off[2]).min() < self.surface_z:
                     raise RuntimeError("canopy leaf centres must lie above the ground surface")
@@ -1025,6 +1051,10 @@ class FlatScene:
             p[6] = float(b.component)
         return p
 
+    def trunk_reflectance(self, group: int) -> float:
+        b = self.leaf_groups[group].children.get("trunk_bsdf")
+        return 0.0 if b is None else float(b.children["reflectance"].values["value"])
+
     def leaf_bsdf_params(self, group: int) -> tuple[float, float]:
         b = self.leaf_groups[group].children["bsdf"]
         return (float(b.children["reflectance"].values["value"]),
@@ -1156,6 +1186,15 @@ class FlatScene:
                 groups[i].n_disks = disks.shape[0]
                 groups[i].disks = disks.ctypes.data_as(_abi.c_float_p)
                 groups[i].reflectance, groups[i].transmittance = self.leaf_bsdf_params(i)
+                cyl = np.ascontiguousarray(g.cylinders, dtype=np.float32)
+                tdk = np.ascontiguousarray(g.trunk_disks, dtype=np.float32)
+                keep += [cyl, tdk]
+                groups[i].n_cylinders, groups[i].n_trunk_disks = cyl.shape[0], tdk.shape[0]
+                if cyl.shape[0]:
+                    groups[i].cylinders = cyl.ctypes.data_as(_abi.c_float_p)
+                if tdk.shape[0]:
+                    groups[i].trunk_disks = tdk.ctypes.data_as(_abi.c_float_p)
+                groups[i].trunk_reflectance = self.trunk_reflectance(i)
             inst_g = np.ascontiguousarray([gi for gi, _ in self.instances], dtype=np.int32)
             inst_o = np.ascontiguousarray([off for _, off in self.instances], dtype=np.float64)
             keep += [groups, inst_g, inst_o]

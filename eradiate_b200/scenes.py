@@ -282,7 +282,10 @@ def atmosphere_scene(
     if canopy is not None:
         if spherical:
             raise ValueError("canopies need the plane-parallel geometry")
-        scene.update(disc_canopy(**canopy))
+        if "trees" in canopy:  # {"trees": {...abstract_tree_canopy arguments...}, "size": (lx, ly, lz)}
+            scene.update(abstract_tree_canopy(**canopy["trees"]))
+        else:
+            scene.update(disc_canopy(**canopy))
         # experiments/_canopy_atmosphere.py:200-210: distant measures target the top of the unit cell
         lx, ly, lz = canopy.get("size", (10.0, 10.0, 2.0))
         target = {
@@ -502,6 +505,52 @@ def config_c3(spp: int = 1 << 22, res: int = 32, w_nm: float = 865.0) -> dict:
         sensor={"type": "hdistant", "film_resolution": (res, res)},
         spp=spp,
     )
+
+
+def abstract_tree_canopy(
+    positions=((0.0, 0.0), (3.0, 1.0), (-2.0, 2.5)),
+    trunk_height: float = 2.0,
+    trunk_radius: float = 0.1,
+    crown_radius: float = 1.0,
+    n_leaves: int = 300,
+    leaf_radius: float = 0.06,
+    reflectance: float = 0.45,
+    transmittance: float = 0.45,
+    trunk_reflectance: float = 0.3,
+    seed: int = 5,
+) -> dict:
+    """
+    Instanced `AbstractTree`s (``scenes/biosphere/_tree.py:150-180``): a shape group made of a spherical leaf
+    cloud (`disk` leaves, `bilambertian`), a trunk `cylinder` from z = -0.1 to the crown base and its cap `disk`
+    (one `diffuse` BSDF), placed by translated `instance`s (``_core.py:266-296``).
+    """
+    rng = np.random.default_rng(seed)
+    v = rng.normal(size=(n_leaves, 3))
+    v *= (crown_radius * rng.uniform(0.0, 1.0, (n_leaves, 1)) ** (1.0 / 3.0)) / np.linalg.norm(v, axis=1, keepdims=True)
+    pos = v + np.array([0.0, 0.0, trunk_height + crown_radius])
+    nrm = leaf_normals(n_leaves, "uniform", rng)
+    out: dict = {
+        "bsdf_leaf_cloud": {"type": "bilambertian", "reflectance": {"type": "uniform", "value": float(reflectance)},
+                            "transmittance": {"type": "uniform", "value": float(transmittance)}},
+        "bsdf_tree": {"type": "diffuse", "reflectance": {"type": "uniform", "value": float(trunk_reflectance)}},
+    }
+    group: dict = {"type": "shapegroup"}
+    for i in range(n_leaves):
+        n = nrm[i]
+        up = np.array([1.0, 0.0, 0.0]) if abs(n[2]) > 0.9 else np.array([0.0, 0.0, 1.0])
+        group[f"leaf_cloud_leaf_{i}"] = {
+            "type": "disk", "bsdf": {"type": "ref", "id": "bsdf_leaf_cloud"},
+            "to_world": ScalarTransform4f().look_at(origin=pos[i], target=pos[i] + n, up=up).scale(leaf_radius),
+        }
+    group["trunk_cyl_tree"] = {"type": "cylinder", "bsdf": {"type": "ref", "id": "bsdf_tree"}, "radius": trunk_radius,
+                               "p0": [0.0, 0.0, -0.1], "p1": [0.0, 0.0, trunk_height]}
+    group["trunk_cap_tree"] = {"type": "disk", "bsdf": {"type": "ref", "id": "bsdf_tree"},
+                               "to_world": ScalarTransform4f().scale(trunk_radius).translate([0.0, 0.0, trunk_height / trunk_radius])}
+    out["tree"] = group
+    for k, (x, y) in enumerate(positions):
+        out[f"tree_instance_{k}"] = {"type": "instance", "group": {"type": "ref", "id": "tree"},
+                                     "to_world": ScalarTransform4f().translate([float(x), float(y), 0.0])}
+    return out
 
 
 def config_c4(spp: int = 1 << 22, lai: float = 3.0, radius: float = 0.1, size=(25.0, 25.0, 2.0),

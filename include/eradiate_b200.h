@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 10
+#define ERTB_ABI_VERSION 11
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -132,8 +132,8 @@ typedef struct ertb_sensor_desc {
 
 /* Explicit 3D canopies (src/eradiate/scenes/biosphere/_leaf_cloud.py:1150-1175,
  * _core.py:266-296): `shapegroup`s of `disk` leaves sharing one `bilambertian` BSDF
- * (ERP/bsdfs/bilambertian.cpp:60-215), placed in the scene by `instance`s whose to_world is a
- * pure translation.  Plane-parallel scenes only; the leaves sit inside the atmosphere and do
+ * (ERP/bsdfs/bilambertian.cpp:60-215), optionally with a trunk, placed in the scene by `instance`s
+ * whose to_world is a pure translation.  Plane-parallel scenes only; the leaves sit inside the atmosphere and do
  * not change the medium of a path (no medium interface).
  * disks: n_disks x 7 floats = centre xyz, unit normal xyz, radius (MI/src/shapes/disk.cpp:
  * to_world = look_at x uniform scale). */
@@ -143,6 +143,15 @@ typedef struct ertb_leaf_group_desc {
     float transmittance;   /* bilambertian `transmittance` (uniform) */
     int32_t _pad;
     const float *disks;
+    /* AbstractTree (src/eradiate/scenes/biosphere/_tree.py:150-180): the group may also hold a trunk, i.e.
+     * `cylinder`s (MI/src/shapes/cylinder.cpp:560-615, open tubes) and cap `disk`s sharing ONE one-sided
+     * `diffuse` BSDF (MI/src/bsdfs/diffuse.cpp:100-178). */
+    int32_t n_cylinders;
+    int32_t n_trunk_disks;
+    const float *cylinders;     /* n_cylinders x 7: p0 xyz, p1 xyz, radius */
+    const float *trunk_disks;   /* n_trunk_disks x 7, same layout as `disks` */
+    float trunk_reflectance;
+    int32_t _pad2;
 } ertb_leaf_group_desc;
 
 typedef struct ertb_scene_desc {
@@ -232,7 +241,8 @@ enum ertb_param {
     ERTB_PARAM_PHASE_PARAMS = 6, /* index = leaf; float[4] */
     ERTB_PARAM_PHASE_MUELLER = 7, /* index = leaf * 5 + k (k: m12, m22, m33, m34, m44); float[n_nodes] */
     ERTB_PARAM_LEAF_BSDF = 8,    /* index = leaf group; float[2]: reflectance, transmittance */
-    ERTB_PARAM_PATCH_BSDF_PARAMS = 9 /* float[ERTB_MAX_BSDF_PARAMS]: the central patch's BSDF */
+    ERTB_PARAM_PATCH_BSDF_PARAMS = 9, /* float[ERTB_MAX_BSDF_PARAMS]: the central patch's BSDF */
+    ERTB_PARAM_TRUNK_BSDF = 10        /* index = leaf group; float[1]: trunk reflectance */
 };
 
 typedef struct ertb_render_stats {

@@ -347,7 +347,7 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
 /* ------------------------------------------------------------- geometry */
 typedef struct { v3 o, d; double maxt; } ray_t;
 enum { SHAPE_GROUND = 0, SHAPE_TOA = 1, SHAPE_LEAF = 2 };
-typedef struct { double t; v3 p, n; int shape; int group; } si_t; /* t = INFINITY when invalid */
+typedef struct { double t; v3 p, n; int shape; int group; int trunk; } si_t; /* t = INFINITY when invalid */
 
 static inline v3 ray_at(const ray_t *r, double t) { return vfma(r->d, t, r->o); }
 
@@ -375,7 +375,7 @@ static double sphere_intersect(const ray_t *ray, double radius) {
  * `cube` top face; horizontal extent treated as unbounded: default width 1e6 km) */
 static si_t scene_intersect(const scene_t *S, const ray_t *ray) {
     const ertb_scene_desc *d = S->desc;
-    si_t best; best.t = INFINITY; best.shape = -1; best.group = -1; best.p = best.n = V(0, 0, 0);
+    si_t best; best.t = INFINITY; best.shape = -1; best.group = -1; best.trunk = 0; best.p = best.n = V(0, 0, 0);
     double tg = INFINITY, tt = INFINITY;
     if (S->spherical) {
         tg = sphere_intersect(ray, d->surface_z);
@@ -410,7 +410,7 @@ static si_t scene_intersect(const scene_t *S, const ray_t *ray) {
         double o[3] = { ray->o.x, ray->o.y, ray->o.z }, dd[3] = { ray->d.x, ray->d.y, ray->d.z };
         canopy_hit_t h = canopy_intersect(&S->canopy, o, dd, fmin(ray->maxt, best.t));
         if (h.t < best.t) {
-            best.t = h.t; best.shape = SHAPE_LEAF; best.group = h.group;
+            best.t = h.t; best.shape = SHAPE_LEAF; best.group = h.group; best.trunk = h.kind == CANOPY_TRUNK;
             best.p = V(h.p[0], h.p[1], h.p[2]);
             best.n = V(h.n[0], h.n[1], h.n[2]);
         }
@@ -1095,12 +1095,20 @@ static double surf_eval(const scene_t *S, const si_t *si, v3 wi, v3 wo) {
     if (si->shape == SHAPE_LEAF) {
         const canopy_group_t *G = &S->canopy.groups[si->group];
         double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
+        if (si->trunk) /* diffuse.cpp:127-143: one-sided Lambertian */
+            return wi.z > 0.0 && wo.z > 0.0 ? G->trunk_reflectance * INV_PI * wo.z : 0.0;
         return bilambertian_eval(G->reflectance, G->transmittance, a, b);
     }
     if (on_patch(S, si->p)) return bsdf_eval_tp(S, S->desc->patch_bsdf_type, S->desc->patch_bsdf_params, wi, wo);
     return bsdf_eval(S, wi, wo);
 }
 static double surf_sample(const scene_t *S, const si_t *si, v3 wi, double s1, double u1, double u2, v3 *wo) {
+    if (si->shape == SHAPE_LEAF && si->trunk) { /* diffuse.cpp:100-125 */
+        double o[3];
+        ertbo_square_to_cosine_hemisphere(u1, u2, o);
+        *wo = V(o[0], o[1], o[2]);
+        return wi.z > 0.0 && o[2] > 0.0 ? S->canopy.groups[si->group].trunk_reflectance : 0.0;
+    }
     if (si->shape == SHAPE_LEAF) {
         const canopy_group_t *G = &S->canopy.groups[si->group];
         double a[3] = { wi.x, wi.y, wi.z }, o[3];

@@ -19,19 +19,45 @@ static void disk_bounds(const float *dk, double lo[3], double hi[3]) {
     }
 }
 
+static void cyl_bounds(const float *c, double lo[3], double hi[3]) {
+    double ax[3] = { c[3] - c[0], c[4] - c[1], c[5] - c[2] };
+    double L = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    for (int k = 0; k < 3; ++k) {
+        double u = ax[k] / L, e = (double) c[6] * sqrt(fmax(1.0 - u * u, 0.0));
+        lo[k] = fmin(c[k], c[3 + k]) - e;
+        hi[k] = fmax(c[k], c[3 + k]) + e;
+    }
+}
+
+/* bounds of primitive i of a group: disks [0, n_disks), then cylinders */
+static void prim_bounds(const canopy_group_t *G, int i, double lo[3], double hi[3]) {
+    if (i < G->n_disks) disk_bounds(G->disks + 7 * i, lo, hi);
+    else cyl_bounds(G->cylinders + 7 * (i - G->n_disks), lo, hi);
+}
+
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 static int group_init(canopy_group_t *G, const ertb_leaf_group_desc *gd) {
     memset(G, 0, sizeof *G);
-    G->n_disks = gd->n_disks;
-    G->disks = gd->disks;
+    if (gd->n_disks < 1 || !gd->disks) return 1;
+    if ((gd->n_trunk_disks > 0 && !gd->trunk_disks) || (gd->n_cylinders > 0 && !gd->cylinders)) return 1;
+    G->n_leaf_disks = gd->n_disks;
+    G->n_disks = gd->n_disks + gd->n_trunk_disks;
+    G->n_cylinders = gd->n_cylinders;
+    G->disks = malloc(sizeof(float) * 7 * (size_t) G->n_disks);
+    if (!G->disks) return 1;
+    memcpy(G->disks, gd->disks, sizeof(float) * 7 * (size_t) gd->n_disks);
+    if (gd->n_trunk_disks)
+        memcpy(G->disks + 7 * (size_t) gd->n_disks, gd->trunk_disks, sizeof(float) * 7 * (size_t) gd->n_trunk_disks);
+    G->cylinders = gd->cylinders;
     G->reflectance = gd->reflectance;
     G->transmittance = gd->transmittance;
-    if (gd->n_disks < 1 || !gd->disks) return 1;
+    G->trunk_reflectance = gd->trunk_reflectance;
+    const int n_prims = G->n_disks + G->n_cylinders;
     for (int k = 0; k < 3; ++k) { G->lo[k] = INFINITY; G->hi[k] = -INFINITY; }
-    for (int i = 0; i < gd->n_disks; ++i) {
+    for (int i = 0; i < n_prims; ++i) {
         double lo[3], hi[3];
-        disk_bounds(gd->disks + 7 * i, lo, hi);
+        prim_bounds(G, i, lo, hi);
         for (int k = 0; k < 3; ++k) { G->lo[k] = fmin(G->lo[k], lo[k]); G->hi[k] = fmax(G->hi[k], hi[k]); }
     }
     for (int k = 0; k < 3; ++k) { /* pad: flat groups, hits exactly on the faces */
@@ -40,7 +66,7 @@ static int group_init(canopy_group_t *G, const ertb_leaf_group_desc *gd) {
     }
     /* ~2 disks per cell */
     double vol = (G->hi[0] - G->lo[0]) * (G->hi[1] - G->lo[1]) * (G->hi[2] - G->lo[2]);
-    double s = cbrt(vol / fmax(1.0, gd->n_disks / 2.0));
+    double s = cbrt(vol / fmax(1.0, n_prims / 2.0));
     for (int k = 0; k < 3; ++k) {
         G->res[k] = clampi((int) ceil((G->hi[k] - G->lo[k]) / s), 1, 256);
         G->cell[k] = (G->hi[k] - G->lo[k]) / G->res[k];
@@ -49,9 +75,9 @@ static int group_init(canopy_group_t *G, const ertb_leaf_group_desc *gd) {
     G->cell_start = calloc(ncell + 1, sizeof(int));
     if (!G->cell_start) return 1;
     for (int pass = 0; pass < 2; ++pass) {
-        for (int i = 0; i < gd->n_disks; ++i) {
+        for (int i = 0; i < n_prims; ++i) {
             double lo[3], hi[3];
-            disk_bounds(gd->disks + 7 * i, lo, hi);
+            prim_bounds(G, i, lo, hi);
             int a[3], b[3];
             for (int k = 0; k < 3; ++k) {
                 a[k] = clampi((int) floor((lo[k] - G->lo[k]) / G->cell[k]), 0, G->res[k] - 1);
@@ -95,7 +121,7 @@ int canopy_init(canopy_t *C, const ertb_scene_desc *d) {
 }
 
 void canopy_free(canopy_t *C) {
-    for (int g = 0; g < C->n_groups; ++g) { free(C->groups[g].cell_start); free(C->groups[g].cell_items); }
+    for (int g = 0; g < C->n_groups; ++g) { free(C->groups[g].cell_start); free(C->groups[g].cell_items); free(C->groups[g].disks); }
     free(C->groups);
     memset(C, 0, sizeof *C);
 }
@@ -111,7 +137,40 @@ static double disk_hit(const float *dk, const double o[3], const double d[3], do
     return px * px + py * py + pz * pz <= r2 ? t : INFINITY;
 }
 
-/* nearest disk of one group (ray in the group's local coordinates); returns the disk index */
+/* MI/src/shapes/cylinder.cpp:560-615: open tube of radius r around the segment p0 p1. Quadratic in the
+ * plane orthogonal to the axis (math::solve_quadratic), near root first, far root if the near one is cut
+ * off by the ends; no hit when the segment [0, maxt] lies entirely inside or entirely outside. */
+static double cyl_hit(const float *c, const double o[3], const double d[3], double maxt) {
+    double ax[3] = { c[3] - c[0], c[4] - c[1], c[5] - c[2] };
+    double L = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    double u[3] = { ax[0] / L, ax[1] / L, ax[2] / L };
+    double w[3] = { o[0] - c[0], o[1] - c[1], o[2] - c[2] };
+    double du = d[0] * u[0] + d[1] * u[1] + d[2] * u[2], wu = w[0] * u[0] + w[1] * u[1] + w[2] * u[2];
+    double dp[3] = { d[0] - du * u[0], d[1] - du * u[1], d[2] - du * u[2] };
+    double wp[3] = { w[0] - wu * u[0], w[1] - wu * u[1], w[2] - wu * u[2] };
+    double A = dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2];
+    double B = 2.0 * (dp[0] * wp[0] + dp[1] * wp[1] + dp[2] * wp[2]);
+    double Cc = wp[0] * wp[0] + wp[1] * wp[1] + wp[2] * wp[2] - (double) c[6] * c[6];
+    if (A == 0.0) return INFINITY;
+    double disc = B * B - 4.0 * A * Cc;
+    if (disc < 0.0) return INFINITY;
+    double temp = -0.5 * (B + copysign(sqrt(disc), B));
+    double x0 = temp / A, x1 = Cc / temp;
+    if (temp == 0.0) x0 = x1 = 0.0;
+    double near_t = fmin(x0, x1), far_t = fmax(x0, x1);
+    if (!(near_t <= maxt && far_t >= 0.0)) return INFINITY;
+    if (near_t < 0.0 && far_t > maxt) return INFINITY;
+    double zn = wu + du * near_t, zf = wu + du * far_t;
+    if (zn >= 0.0 && zn <= L && near_t >= 0.0) return near_t;
+    if (zf >= 0.0 && zf <= L && far_t <= maxt) return far_t;
+    return INFINITY;
+}
+
+static double prim_hit(const canopy_group_t *G, int i, const double o[3], const double d[3], double maxt) {
+    return i < G->n_disks ? disk_hit(G->disks + 7 * i, o, d, maxt) : cyl_hit(G->cylinders + 7 * (i - G->n_disks), o, d, maxt);
+}
+
+/* nearest primitive of one group (ray in the group's local coordinates); returns the primitive index */
 static int group_intersect(const canopy_group_t *G, const double o[3], const double d[3], double maxt, double *t_out) {
     double t0 = 0.0, t1 = maxt;
     for (int k = 0; k < 3; ++k) {
@@ -142,7 +201,7 @@ static int group_intersect(const canopy_group_t *G, const double o[3], const dou
         double t_exit = fmin(tnext[0], fmin(tnext[1], tnext[2]));
         for (int j = G->cell_start[ci]; j < G->cell_start[ci + 1]; ++j) {
             int i = G->cell_items[j];
-            double t = disk_hit(G->disks + 7 * i, o, d, maxt);
+            double t = prim_hit(G, i, o, d, maxt);
             if (t < best_t) { best_t = t; best = i; }
         }
         if (best_t <= t_exit || t_exit > t1) break; /* a hit inside the cells visited so far is final */
@@ -166,12 +225,25 @@ canopy_hit_t canopy_intersect(const canopy_t *C, const double o[3], const double
         double t;
         int k = group_intersect(G, ol, d, fmin(maxt, H.t), &t);
         if (k >= 0 && t < H.t) {
-            const float *dk = G->disks + 7 * k;
             H.t = t; H.group = C->instance_group[i];
+            H.kind = k < G->n_leaf_disks ? CANOPY_LEAF : CANOPY_TRUNK;
             double p[3] = { o[0] + t * d[0], o[1] + t * d[1], o[2] + t * d[2] };
-            double c[3] = { dk[0] + off[0], dk[1] + off[1], dk[2] + off[2] };
-            double dist = (c[0] - p[0]) * dk[3] + (c[1] - p[1]) * dk[4] + (c[2] - p[2]) * dk[5];
-            for (int a = 0; a < 3; ++a) { H.n[a] = dk[3 + a]; H.p[a] = p[a] + dist * dk[3 + a]; }
+            if (k < G->n_disks) {
+                const float *dk = G->disks + 7 * k;
+                double c[3] = { dk[0] + off[0], dk[1] + off[1], dk[2] + off[2] };
+                double dist = (c[0] - p[0]) * dk[3] + (c[1] - p[1]) * dk[4] + (c[2] - p[2]) * dk[5];
+                for (int a = 0; a < 3; ++a) { H.n[a] = dk[3 + a]; H.p[a] = p[a] + dist * dk[3 + a]; }
+            } else { /* cylinder.cpp:660-700: radial normal, hit point pulled back onto the tube */
+                const float *c = G->cylinders + 7 * (k - G->n_disks);
+                double ax[3] = { c[3] - c[0], c[4] - c[1], c[5] - c[2] };
+                double L = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+                double w[3] = { p[0] - c[0] - off[0], p[1] - c[1] - off[1], p[2] - c[2] - off[2] };
+                double wu = (w[0] * ax[0] + w[1] * ax[1] + w[2] * ax[2]) / L;
+                double r[3], rn = 0.0;
+                for (int a = 0; a < 3; ++a) { r[a] = w[a] - wu * ax[a] / L; rn += r[a] * r[a]; }
+                rn = sqrt(rn);
+                for (int a = 0; a < 3; ++a) { H.n[a] = r[a] / rn; H.p[a] = p[a] + ((double) c[6] - rn) * H.n[a]; }
+            }
         }
     }
     return H;

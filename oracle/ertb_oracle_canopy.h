@@ -12,9 +12,16 @@
 
 #include "../include/eradiate_b200.h"
 
+/* primitive kinds of a group: leaf disks first, then the trunk's cap disks, then its cylinders */
+enum { CANOPY_LEAF = 0, CANOPY_TRUNK = 1 };
+
 typedef struct {
-    int n_disks;
-    const float *disks;  /* n x 7 (borrowed from the descriptor) */
+    int n_disks;         /* leaves + trunk disks */
+    int n_leaf_disks;
+    int n_cylinders;
+    float *disks;        /* n_disks x 7 (owned copy: leaves, then trunk disks) */
+    const float *cylinders; /* n_cylinders x 7: p0, p1, radius (borrowed) */
+    double trunk_reflectance;
     double lo[3], hi[3]; /* bounding box of the group (local coordinates) */
     int res[3];
     double cell[3];
@@ -33,8 +40,9 @@ typedef struct {
 typedef struct {
     double t;        /* INFINITY: no hit */
     double p[3];     /* hit point re-projected onto the disk (disk.cpp:482-485) */
-    double n[3];     /* disk normal (m_frame.n) */
+    double n[3];     /* disk normal (m_frame.n) / outward normal of the cylinder */
     int group;
+    int kind;        /* CANOPY_LEAF (bilambertian) or CANOPY_TRUNK (one-sided diffuse) */
 } canopy_hit_t;
 
 int canopy_init(canopy_t *C, const ertb_scene_desc *d);

@@ -186,6 +186,11 @@ def battery() -> dict:
             central_patch={"edges": (4.0, 4.0), "bsdf": {"type": "rpv", "rho_0": 0.25, "k": 0.8, "g": -0.1}},
             sensor={"type": "mpdistant", "vza": 20.0, "vaa": 45.0, "film_resolution": (3, 3),
                     "target": {"type": "rectangle", "to_world": scenes.ScalarTransform4f().scale([4.0, 4.0, 1.0])}}),
+        # AbstractTree instances: spherical leaf clouds on cylinder trunks with a diffuse bark
+        "canopy_abstract_trees_pp": S(geometry="plane_parallel", n_layers=60, sza=40.0, saa=30.0,
+                                      canopy={"trees": {}, "size": (8.0, 8.0, 4.1)},
+                                      surface={"type": "diffuse", "reflectance": 0.2},
+                                      sensor={"type": "mdistant", "vza": [-55.0, -20.0, 0.0, 30.0, 65.0], "vaa": 30.0}),
         "mpdistant_canopy_image_pp": S(geometry="plane_parallel", n_layers=60, sza=30.0, canopy=CANOPY,
                                        sensor={"type": "mpdistant", "vza": 25.0, "vaa": 60.0, "film_resolution": (3, 2)}),
         "mpdistant_spherical": S(n_layers=100, sza=60.0, sensor={"type": "mpdistant", "vza": 40.0, "vaa": 0.0,

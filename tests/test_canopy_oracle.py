@@ -229,3 +229,82 @@ def test_central_patch_surface_switches_bsdf_on_the_patch(oracle):
     assert np.allclose(img[:, [0, 3]], rho0 * e, rtol=1e-6)      # |x| > 2: background
     # the four central pixels: |x| <= 2 is on the patch, |y| <= 1 is half of each pixel's height
     assert np.all(np.abs(img[1:3, 1:3] - 0.5 * (rho0 + rho1) * e) < 5.0 * err[1:3, 1:3] + 1e-9)
+
+
+# ------------------------------------------------------------------ tree trunks (cylinder + cap, diffuse)
+def _tree_scene(sensor, **kw):
+    trees = dict(positions=((0.0, 0.0),), n_leaves=1, crown_radius=0.01, trunk_height=2.0, trunk_radius=0.25,
+                 trunk_reflectance=0.4, reflectance=0.0, transmittance=0.0)
+    trees.update(kw)
+    return mi_load_dict(scenes.atmosphere_scene(
+        geometry="plane_parallel", atmosphere=None, integrator="path", sza=50.0, saa=0.0, max_depth=2,
+        surface={"type": "diffuse", "reflectance": 0.0}, canopy={"trees": trees, "size": (2.0, 2.0, 2.1)}, sensor=sensor))
+
+
+def _brute_force_cylinder(c, o, d, tmax):
+    """MI/src/shapes/cylinder.cpp:560-615 in numpy (open tube, near root first, far root otherwise)."""
+    ax = c[3:6] - c[:3]
+    L = np.linalg.norm(ax)
+    u = ax / L
+    w = o - c[:3]
+    du, wu = d @ u, w @ u
+    dp, wp = d - du[:, None] * u, w - wu[:, None] * u
+    A, B, C_ = (dp * dp).sum(1), 2 * (dp * wp).sum(1), (wp * wp).sum(1) - c[6] ** 2
+    disc = B * B - 4 * A * C_
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sq = np.sqrt(np.maximum(disc, 0))
+        t0, t1 = (-B - sq) / (2 * A), (-B + sq) / (2 * A)
+    tn, tf = np.minimum(t0, t1), np.maximum(t0, t1)
+    zn, zf = wu + du * tn, wu + du * tf
+    ok = (disc >= 0) & (tn <= tmax) & (tf >= 0) & ~((tn < 0) & (tf > tmax))
+    near = ok & (zn >= 0) & (zn <= L) & (tn >= 0)
+    far = ok & ~near & (zf >= 0) & (zf <= L) & (tf <= tmax)
+    return np.where(near, tn, np.where(far, tf, np.inf))
+
+
+def test_cylinder_ray_caster_equals_brute_force(oracle):
+    sc = _tree_scene({"type": "mdistant", "vza": [0.0], "vaa": 0.0}, positions=((0.0, 0.0), (1.5, -0.5)))
+    d = sc.flat.build_desc()
+    g = sc.flat.leaf_groups[0]
+    rng = np.random.default_rng(4)
+    n = 4000
+    o = np.stack([rng.uniform(-2, 3, n), rng.uniform(-2, 2, n), rng.uniform(-0.05, 3.0, n)], axis=1)
+    dirs = rng.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    inside = rng.random(n) < 0.15  # some origins inside the tube: only the far wall can be hit
+    o[inside] = np.stack([rng.uniform(-0.15, 0.15, inside.sum()), rng.uniform(-0.15, 0.15, inside.sum()),
+                          rng.uniform(0.1, 1.9, inside.sum())], axis=1)
+    tmax = np.where(rng.random(n) < 0.3, rng.uniform(0.05, 2.0, n), np.inf)
+    t, nrm, grp = oracle.canopy_intersect(d, o, dirs, tmax)
+    want = np.full(n, np.inf)
+    for _, off in sc.flat.instances:
+        cyl = g.cylinders[0].astype(np.float32).astype(np.float64).copy()
+        cyl[:3] += off
+        cyl[3:6] += off
+        want = np.minimum(want, _brute_force_cylinder(cyl, o, dirs, tmax))
+        want = np.minimum(want, _brute_force(np.vstack([g.disks, g.trunk_disks]).astype(np.float32).astype(np.float64),
+                                             [off], o, dirs, tmax))
+    assert np.array_equal(np.isfinite(t), np.isfinite(want))
+    hit = np.isfinite(t)
+    assert hit.sum() > 300 and (hit & inside).sum() > 50
+    assert np.allclose(t[hit], want[hit], rtol=1e-9, atol=1e-9)
+
+
+def test_trunk_is_a_one_sided_lambertian_tube(oracle):
+    """Rays aimed at known points of a lone trunk (black ground, no atmosphere, direct light only):
+    L = rho E max(n . s, 0) / pi with n the outward normal of the tube, or +z on its cap."""
+    sza, rho, r = 50.0, 0.4, 0.25
+    s_dir = np.array([np.sin(np.radians(sza)), 0.0, np.cos(np.radians(sza))])  # towards the sun (saa = 0 -> +x)
+    phis = np.radians([0.0, 60.0, 120.0, 200.0])
+    pts = np.stack([r * np.cos(phis), r * np.sin(phis), [0.5, 1.0, 1.5, 0.7]], axis=1)
+    nrm = np.stack([np.cos(phis), np.sin(phis), np.zeros(4)], axis=1)
+    org = pts + 3.0 * nrm + np.array([0.0, 0.0, 0.4])        # look at the wall from outside, slightly from above
+    pts = np.vstack([pts, [[0.05, -0.1, 2.0]]])             # and at the cap from straight above
+    nrm = np.vstack([nrm, [[0.0, 0.0, 1.0]]])
+    org = np.vstack([org, [[0.05, -0.1, 6.0]]])
+    dirs = pts - org
+    sc = _tree_scene({"type": "mradiancemeter", "origins": org, "directions": dirs}, trunk_reflectance=rho, trunk_radius=r)
+    mean, err, st, _ = _render(oracle, sc.flat.build_desc(), 64)
+    want = rho * E0 * np.maximum(nrm @ s_dir, 0.0) / np.pi
+    assert np.allclose(mean, want, rtol=1e-6, atol=1e-12), (mean, want)
+    assert want[2] == 0.0 and want[3] == 0.0 and want[0] > 0 and want[4] > 0

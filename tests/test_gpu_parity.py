@@ -235,6 +235,49 @@ def test_canopy_ray_caster_matches_oracle(oracle):
     assert np.allclose(n_g[same], n_o[same], atol=1e-6) and np.all(g_g[same] == g_o[same])
 
 
+def test_tree_trunk_ray_caster_and_radiance(oracle):
+    """AbstractTree trunks (cylinder + cap disk, one-sided diffuse): the BVH ray caster against the oracle's
+    grid, including origins inside the tube, and the closed-form radiance of the lit wall and cap."""
+    from tests.test_canopy_oracle import _tree_scene
+    sc = _tree_scene({"type": "mdistant", "vza": [0.0], "vaa": 0.0}, positions=((0.0, 0.0), (1.5, -0.5)))
+    desc = sc.flat.build_desc()
+    rng = np.random.default_rng(4)
+    n = 20000
+    o = np.stack([rng.uniform(-2, 3, n), rng.uniform(-2, 2, n), rng.uniform(0.01, 3.0, n)], axis=1)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    inside = rng.random(n) < 0.15
+    o[inside] = np.stack([rng.uniform(-0.15, 0.15, inside.sum()), rng.uniform(-0.15, 0.15, inside.sum()),
+                          rng.uniform(0.1, 1.9, inside.sum())], axis=1)
+    t_g, n_g, _ = kat.canopy_intersect(sc, o, d)
+    t_o, n_o, _ = oracle.canopy_intersect(desc, o, d.astype(np.float32).astype(np.float64))
+    z_hit = o[:, 2] + np.where(np.isfinite(t_o), t_o, 0.0) * d[:, 2]
+    ok = ~(np.isfinite(t_o) & (z_hit < 1e-3))  # the device clips the canopy at the ground plane
+    assert (np.isfinite(t_g[ok]) != np.isfinite(t_o[ok])).sum() <= 3
+    both = ok & np.isfinite(t_g) & np.isfinite(t_o)
+    assert both.sum() > 1500 and (both & inside).sum() > 300
+    assert np.sum(np.abs(t_g[both] - t_o[both]) > 2e-5 + 2e-5 * t_o[both]) <= 3
+    with np.errstate(invalid="ignore"):
+        same = both & (np.abs(t_g - t_o) < 1e-4)
+    assert np.allclose(n_g[same], n_o[same], atol=2e-4)  # radial normals: float32 hit point / 0.25 m radius
+    # closed form: L = rho E max(n . s, 0) / pi on the wall and on the cap
+    sza, rho, r = 50.0, 0.4, 0.25
+    s_dir = np.array([np.sin(np.radians(sza)), 0.0, np.cos(np.radians(sza))])
+    phis = np.radians([0.0, 60.0, 120.0, 200.0])
+    pts = np.stack([r * np.cos(phis), r * np.sin(phis), [0.5, 1.0, 1.5, 0.7]], axis=1)
+    nrm = np.stack([np.cos(phis), np.sin(phis), np.zeros(4)], axis=1)
+    org = np.vstack([pts + 3.0 * nrm + np.array([0.0, 0.0, 0.4]), [[0.05, -0.1, 6.0]]])
+    pts, nrm = np.vstack([pts, [[0.05, -0.1, 2.0]]]), np.vstack([nrm, [[0.0, 0.0, 1.0]]])
+    sc = _tree_scene({"type": "mradiancemeter", "origins": org, "directions": pts - org}, trunk_reflectance=rho, trunk_radius=r)
+    mean = render(sc, seed=1, spp=256).raw["sum_l"].ravel() / 256
+    want = rho * 1.8 * np.maximum(nrm @ s_dir, 0.0) / np.pi
+    assert np.allclose(mean, want, rtol=2e-4, atol=1e-7), (mean, want)
+    # the bark is a scene parameter (`<group>.trunk_bsdf.reflectance.value`)
+    mi_traverse(sc).parameters.update({"tree.trunk_bsdf.reflectance.value": 0.8})
+    mean2 = render(sc, seed=1, spp=256).raw["sum_l"].ravel() / 256
+    assert np.allclose(mean2, 2.0 * mean, rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("r, t", [(0.5, 0.4), (0.0546, 0.0149), (1.0, 0.0), (0.0, 0.7), (0.0, 0.0)])
 def test_leaf_bsdf_matches_oracle(oracle, r, t):
     """bilambertian on the device vs the oracle (which is pinned on the reference's own test values)."""

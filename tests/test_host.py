@@ -90,7 +90,7 @@ def _set_integrator(ty):
     (_set_integrator("path"), "ignores participating media"),
     (lambda d: d["surface_bsdf"].update({"type": "dielectric"}), "unsupported plugin type 'dielectric'"),
     (lambda d: d["measure"].update({"type": "perspective"}), "field of view"),
-    (lambda d: d.update({"trunk": {"type": "cylinder"}}), "tree trunks"),
+    (lambda d: d.update({"mesh": {"type": "ply"}}), "mesh canopy elements"),
     (lambda d: d["measure"]["film"].update({"width": 5}), "Film size"),
     (lambda d: d["measure"]["sampler"].update({"type": "stratified"}), "sampler"),
     (lambda d: d["illumination"].update({"type": "constant"}), "unsupported"),
@@ -196,7 +196,7 @@ def test_desc_struct_layout_is_stable():
     assert C.sizeof(_abi.PhaseDesc) == 80
     assert C.sizeof(_abi.RenderStats) == 56
     assert C.sizeof(_abi.SensorDesc) == 360
-    assert C.sizeof(_abi.LeafGroupDesc) == 24
+    assert C.sizeof(_abi.LeafGroupDesc) == 56
     assert C.sizeof(_abi.SceneDesc) == 712
     assert _abi.SceneDesc.patch_rect.offset + 32 == C.sizeof(_abi.SceneDesc)
 
@@ -248,7 +248,7 @@ def test_perspective_sensor_fov_axis_and_medium():
 @pytest.mark.parametrize("mutate,match", [
     (lambda d: d["leaf_cloud_instance_0"].update(
         {"to_world": ScalarTransform4f().rotate([0, 0, 1], 30.0)}), "only translations"),
-    (lambda d: d["leaf_cloud"].update({"trunk": {"type": "cylinder"}}), "tree trunks"),
+    (lambda d: d["leaf_cloud"].update({"trunk": {"type": "cylinder", "bsdf": {"type": "rpv"}}}), "trunks a diffuse one"),
     (lambda d: d["leaf_cloud"].update({"cube": {"type": "cube"}}), "unsupported child shape"),
     (lambda d: d["bsdf_leaf_cloud"].update({"type": "diffuse"}), "bilambertian"),
     (lambda d: d["leaf_cloud_instance_0"].update(
