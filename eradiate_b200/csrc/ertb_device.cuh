@@ -166,9 +166,14 @@ __device__ __forceinline__ void onb(f3 n, f3 &s, f3 &t) {
 }
 
 // ----------------------------------------------------------------------------
-// RNG: PCG32 (MI/ext/drjit/include/drjit/random.h:108-195), one stream per path
-// keyed by (seed, pixel, sample index) so results do not depend on how paths are
-// scheduled over lanes, CTAs or GPUs.
+// RNG: one stream per path keyed by (seed, pixel, sample index), so results do not depend on how
+// paths are scheduled over lanes, CTAs or GPUs. The reference's sampler is PCG32
+// (MI/ext/drjit/include/drjit/random.h:108-195, kept under -DERTB_RNG_PCG32 and used by the oracle);
+// its 64-bit multiply-add costs ~13 % of the C2 step in 32-bit integer instructions
+// (profiles/r01d_pool_regions.md). The default generator is xoroshiro64** (Blackman & Vigna 2018): same
+// 64 bits of state (the `inc` word is unused), 32-bit operations only, +3.7 % on C2. Estimates are
+// statistically equivalent, not bit-identical, to any other generator's -- as between two seeds of the
+// reference (SURVEY 8b "Seeds").
 // ----------------------------------------------------------------------------
 struct Pcg32 {
     unsigned long long state, inc;
@@ -181,16 +186,31 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
     return z ^ (z >> 31);
 }
 __device__ __forceinline__ unsigned pcg_next(Pcg32 &r) {
+#ifndef ERTB_RNG_PCG32
+    // xoroshiro64** (Blackman & Vigna 2018) on the two halves of `state`: 32-bit operations only
+    unsigned s0 = (unsigned) r.state, s1 = (unsigned) (r.state >> 32);
+    const unsigned x = s0 * 0x9E3779BBu;
+    const unsigned result = __funnelshift_l(x, x, 5) * 5u;
+    s1 ^= s0;
+    s0 = __funnelshift_l(s0, s0, 26) ^ s1 ^ (s1 << 9);
+    s1 = __funnelshift_l(s1, s1, 13);
+    r.state = (unsigned long long) s0 | ((unsigned long long) s1 << 32);
+    return result;
+#else
     unsigned long long old = r.state;
     r.state = old * ERTB_PCG_MULT + r.inc;
     unsigned xs = (unsigned) (((old >> 18u) ^ old) >> 27u);
     unsigned rot = (unsigned) (old >> 59u);
     return __funnelshift_r(xs, xs, rot);
+#endif
 }
 __device__ __forceinline__ void pcg_seed(Pcg32 &r, unsigned long long seed, unsigned long long gid) {
     // distinct hashing constants from the oracle's: the two realisations are independent
     r.inc = (gid << 1u) | 1u;
     r.state = mix64(seed + 0xD1B54A32D192ED03ULL * (gid + 1ULL));
+#ifndef ERTB_RNG_PCG32
+    if (r.state == 0ULL) r.state = 0x9E3779B97F4A7C15ULL;
+#endif
     pcg_next(r);
 }
 // uniform in [0, 1): 24 random bits (MI/src/samplers/independent.cpp:77-86, float variant)
