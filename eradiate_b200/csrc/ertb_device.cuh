@@ -214,7 +214,13 @@ __device__ __forceinline__ void pcg_seed(Pcg32 &r, unsigned long long seed, unsi
     pcg_next(r);
 }
 // uniform in [0, 1): 24 random bits (MI/src/samplers/independent.cpp:77-86, float variant)
+#ifdef ERTB_FLOAT_I2F
+// (the reference's conversion: 24 bits through an int -> float conversion and a multiply)
 __device__ __forceinline__ float pcg_float(Pcg32 &r) { return (float) (pcg_next(r) >> 8) * 5.9604644775390625e-8f; }
+#else
+// 23 random mantissa bits under the exponent of 1.0, minus 1: no conversion instruction (quarter-rate pipe); C2 +1.2 %
+__device__ __forceinline__ float pcg_float(Pcg32 &r) { return __uint_as_float(0x3f800000u | (pcg_next(r) >> 9)) - 1.f; }
+#endif
 
 // ----------------------------------------------------------------------------
 // warps (MI/include/mitsuba/core/warp.h)

@@ -42,7 +42,10 @@
 #define ERTB_POOL_K (ERTB_POOL_NS / 32)
 
 enum : int {
-    PF_FLAGS = 0, PF_H0, PF_B, PF_S, PF_SMAX, PF_THR, PF_WNEE, PF_RES, PF_RNG0, PF_RNG1, PF_INC0, PF_INC1,
+    PF_FLAGS = 0, PF_H0, PF_B, PF_S, PF_SMAX, PF_THR, PF_WNEE, PF_RES, PF_RNG0, PF_RNG1,
+#ifdef ERTB_RNG_PCG32
+    PF_INC0, PF_INC1, // (PCG32 carries a per-stream increment; xoroshiro64** has 64 bits of state in all)
+#endif
     PF_B2, PF_SMAX2, PF_N0X, PF_N0Y, PF_N0Z, PF_DX, PF_DY, PF_DZ, PF_PIX, PF_WRAY, PF_COUNT,
     // polarized records only: throughput Mueller matrix normalised by its (0,0) entry (PF_THR holds
     // that entry, so the walk phase is identical in both modes), Q/I U/I V/I of the pending NEE
@@ -286,7 +289,9 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                 thr = FLD(PF_THR, slot); wnee = FLD(PF_WNEE, slot); res = FLD(PF_RES, slot);
                 b2 = FLD(PF_B2, slot); smax2 = FLD(PF_SMAX2, slot);
                 rng.state = (unsigned long long) FLDU(PF_RNG0, slot) | ((unsigned long long) FLDU(PF_RNG1, slot) << 32);
+#ifdef ERTB_RNG_PCG32
                 rng.inc = (unsigned long long) FLDU(PF_INC0, slot) | ((unsigned long long) FLDU(PF_INC1, slot) << 32);
+#endif
             }
             float sb = 0.f;     // BANDS: where the current band ends along the segment
             unsigned band = 0u; //        band index | descending << 8
@@ -544,7 +549,9 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                 FLD(PF_H0, slot) = h0; FLD(PF_B, slot) = b; FLD(PF_S, slot) = 0.f; FLD(PF_SMAX, slot) = smax;
                 FLD(PF_THR, slot) = thr; FLD(PF_WNEE, slot) = 0.f; FLD(PF_RES, slot) = 0.f;
                 FLDU(PF_RNG0, slot) = (unsigned) rng.state; FLDU(PF_RNG1, slot) = (unsigned) (rng.state >> 32);
+#ifdef ERTB_RNG_PCG32
                 FLDU(PF_INC0, slot) = (unsigned) rng.inc; FLDU(PF_INC1, slot) = (unsigned) (rng.inc >> 32);
+#endif
                 FLD(PF_B2, slot) = b; FLD(PF_SMAX2, slot) = smax;
                 FLD(PF_N0X, slot) = n0.x; FLD(PF_N0Y, slot) = n0.y; FLD(PF_N0Z, slot) = n0.z;
                 FLD(PF_DX, slot) = d.x; FLD(PF_DY, slot) = d.y; FLD(PF_DZ, slot) = d.z;
@@ -573,7 +580,11 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
             float h0 = FLD(PF_H0, slot), thr = FLD(PF_THR, slot), res = FLD(PF_RES, slot);
             Pcg32 rng;
             rng.state = (unsigned long long) FLDU(PF_RNG0, slot) | ((unsigned long long) FLDU(PF_RNG1, slot) << 32);
+#ifdef ERTB_RNG_PCG32
             rng.inc = (unsigned long long) FLDU(PF_INC0, slot) | ((unsigned long long) FLDU(PF_INC1, slot) << 32);
+#else
+            rng.inc = 1ULL;
+#endif
             unsigned depth = flags >> PFL_DEPTH_SHIFT;
             float wnee = 0.f;
             bool dead = false;
