@@ -11,7 +11,8 @@ from eradiate_b200.kernel import mi_load_dict, render
 from oracle import oracle
 from tests.scene_battery import battery
 
-NAMES = ["canopy_volpath_afgl_rpv_pp", "canopy_piecewise_aerosol_pp", "canopy_perspective_inside_pp",
+NAMES = ["c2_afgl_rpv_spherical", "afgl_rpv_pp", "thick_isotropic_pp", "ocean_pp", "polarized_rayleigh_pp", "piecewise_afgl_rpv_pp",
+         "canopy_abstract_trees_pp", "canopy_volpath_afgl_rpv_pp", "canopy_piecewise_aerosol_pp", "canopy_perspective_inside_pp",
          "canopy_path_no_atmosphere", "c4_canopy_afgl_rpv_reduced", "central_patch_canopy_mpdistant_pp",
          "mradiancemeter_sky_and_nadir_spherical", "mradiancemeter_piecewise_aerosol_pp", "mpdistant_spherical",
          "c3_afgl_aerosol_tab_hdistant", "aerosol_tab_irregular_spherical"]
@@ -23,7 +24,8 @@ for name in NAMES:
     heavy = name.startswith(("c3_", "aerosol"))
     ospp = 1 << ((17 if heavy else 20) + int(os.environ.get("DEEP", "0")))
     t0 = time.perf_counter()
-    wl, l, l2, st = oracle.render(d, 0, 77, ospp)
+    wl, l, l2, st = (oracle.render(d, 0, 77, ospp) if not d.polarized else
+                     (lambda r: (r[0], r[1], r[2], r[4]))(oracle.render_stokes(d, 0, 77, ospp)))
     om = l / ospp
     ov = np.maximum(l2 / ospp - om * om, 0) / ospp
     t1 = time.perf_counter()
