@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -26,6 +26,9 @@ BSDF_RTLS = 2
 BSDF_HAPKE = 3
 BSDF_OCEAN_LEGACY = 4
 BSDF_BLACK = 5
+BSDF_OCEAN_MISHCHENKO = 6
+BSDF_OCEAN_GRASP = 7
+BSDF_MAIGNAN = 8
 
 # enum ertb_phase_type
 PHASE_ISOTROPIC = 0
@@ -214,6 +217,7 @@ EXPORTED_SYMBOLS = (
     "ertb_kat_phase_eval",
     "ertb_kat_phase_sample",
     "ertb_kat_phase_mueller",
+    "ertb_kat_bsdf_mueller",
     "ertb_kat_piecewise_sample",
     "ertb_kat_piecewise_transmittance",
     "ertb_kat_sensor_ray",

@@ -46,6 +46,7 @@ def load() -> C.CDLL:
     lib.ertb_render_device.argtypes = [vp, i32, u64, u64, u64, vp, vp, vp]
     lib.ertb_render_stokes.argtypes = [vp, i32, u64, u64, u64, dp, dp, dp, dp, C.POINTER(_abi.RenderStats)]
     lib.ertb_kat_phase_mueller.argtypes = [vp, i32, C.c_size_t, fp, fp, fp, fp]
+    lib.ertb_kat_bsdf_mueller.argtypes = [vp, C.c_size_t, fp, fp, fp]
     lib.ertb_sensor_pixel_count.argtypes = [vp, i32]
     lib.ertb_batch_begin.argtypes = [vp, i32, C.POINTER(i32), i32]
     lib.ertb_batch_push.argtypes = [vp, i32, u64, u64, u64]

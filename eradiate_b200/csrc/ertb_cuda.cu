@@ -707,6 +707,8 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
             T.ocean_key[0] = n_real; T.ocean_key[1] = n_imag; T.ocean_key[2] = ws;
         }
         P.ocean_tables = T.d_ocean;
+    } else if (S->bsdf_type >= ERTB_BSDF_OCEAN_MISHCHENKO) {
+        ertb_ocean_host::derive_glint(S->bsdf_type, S->bsdf_params, P.bsdf);
     }
     double dn = sqrt(S->emitter_dir[0] * S->emitter_dir[0] + S->emitter_dir[1] * S->emitter_dir[1] +
                      S->emitter_dir[2] * S->emitter_dir[2]);
@@ -911,7 +913,9 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
     if (device < 0 || device >= ndev) return set_error("invalid CUDA device index");
     if (D->geometry != ERTB_GEOM_PLANE_PARALLEL && D->geometry != ERTB_GEOM_SPHERICAL_SHELL)
         return set_error("unsupported geometry");
-    if (D->bsdf_type < 0 || D->bsdf_type > ERTB_BSDF_BLACK) return set_error("unsupported BSDF type");
+    if (D->bsdf_type < 0 || D->bsdf_type > ERTB_BSDF_MAIGNAN) return set_error("unsupported BSDF type");
+    if (D->bsdf_type == ERTB_BSDF_OCEAN_GRASP && D->bsdf_params[6] != 0.f)
+        return set_error("ocean_grasp: only component=0 (full BRDF) is supported");
     if (D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY && D->bsdf_params[6] != 0.f)
         return set_error("ocean_legacy: only component=0 (full BRDF) is supported");
     if (D->n_sensors < 1 || !D->sensors) return set_error("scene has no sensor");
@@ -973,7 +977,7 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
             return set_error("CentralPatchSurface is supported in unpolarized plane-parallel scenes only");
         }
         if (D->patch_bsdf_type < ERTB_BSDF_DIFFUSE || D->patch_bsdf_type > ERTB_BSDF_HAPKE ||
-            D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+            D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY || D->bsdf_type >= ERTB_BSDF_OCEAN_MISHCHENKO) {
             delete S;
             return set_error("CentralPatchSurface: only the diffuse / rpv / rtls / hapke BSDFs can be blended");
         }
@@ -1516,7 +1520,7 @@ __global__ void kat_bsdf_eval_kernel(ErtbParams P, size_t n, const float *wi, co
     f3 a = mk3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), b = mk3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
     float ci = a.z, co = b.z;
     float v = 0.f;
-    if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) v = oc_eval(P, a, b);
+    if (bsdf_is_local(P.bsdf_type)) v = lf_eval(P, a, b);
     else if (ci > 0.f && co > 0.f) v = bsdf_f(P, ci, co, cos_dphi(ci, co, dot3(a, b))) * co;
     out[i] = v;
 }
@@ -1526,8 +1530,8 @@ __global__ void kat_bsdf_sample_kernel(ErtbParams P, size_t n, const float *wi, 
     f3 a = mk3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
     f3 o;
     float weight = 0.f;
-    if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
-        weight = oc_sample(P, a, u[3 * i], u[3 * i + 1], u[3 * i + 2], o);
+    if (bsdf_is_local(P.bsdf_type)) {
+        weight = lf_sample(P, a, u[3 * i], u[3 * i + 1], u[3 * i + 2], o);
     } else {
         o = cosine_hemisphere(u[3 * i + 1], u[3 * i + 2]);
         if (a.z > 0.f && o.z > 0.f) weight = bsdf_f(P, a.z, o.z, cos_dphi(a.z, o.z, dot3(a, o))) * ERTB_PI;
@@ -1556,6 +1560,21 @@ __global__ void kat_phase_mueller_kernel(ErtbParams P, int leaf, size_t n, const
     leaf_mueller(P.blob, P.leaf[leaf], mk3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), mk3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), m, pp);
     for (int k = 0; k < 16; ++k) M[16 * i + k] = m[k];
     pdf[i] = pp;
+}
+
+__global__ void kat_bsdf_mueller_kernel(ErtbParams P, size_t n, const float *wi, const float *wo, float *M) {
+    size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 a = mk3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), b = mk3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+    float m[16];
+    // shading frame = the axes: the world implicit bases are then the local ones BSDF::eval refers to
+    if (bsdf_is_local(P.bsdf_type)) {
+        lf_eval_mueller(P, false, a, b, mk3(1.f, 0.f, 0.f), mk3(0.f, 1.f, 0.f), mk3(0.f, 0.f, 1.f), m);
+    } else {
+        for (int k = 0; k < 16; ++k) m[k] = 0.f;
+        if (a.z > 0.f && b.z > 0.f) m[0] = bsdf_f(P, a.z, b.z, cos_dphi(a.z, b.z, dot3(a, b))) * b.z;
+    }
+    for (int k = 0; k < 16; ++k) M[16 * i + k] = m[k];
 }
 
 template <typename T>
@@ -1594,6 +1613,17 @@ int ertb_kat_bsdf_sample(ertb_scene *S, size_t n, const float *wi, const float *
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(wo, o.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(weight, w.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int ertb_kat_bsdf_mueller(ertb_scene *S, size_t n, const float *wi, const float *wo, float *mueller) {
+    if (kat_prepare(S)) return 1;
+    DevBuf<float> a, b, m;
+    if (a.alloc(3 * n) || b.alloc(3 * n) || m.alloc(16 * n)) return set_error("cudaMalloc failed");
+    CUDA_TRY(cudaMemcpy(a.p, wi, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(b.p, wo, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+    kat_bsdf_mueller_kernel<<<KAT_GRID(n)>>>(S->base, n, a.p, b.p, m.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(mueller, m.p, 16 * n * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
 int ertb_kat_phase_eval(ertb_scene *S, int leaf, size_t n, const float *c, float *out) {

@@ -192,17 +192,17 @@ __device__ __forceinline__ void surface_interact(const ErtbParams &P, f3 n0, f3 
                                                  Pcg32 &rng, f3 &d, float &f_sun, float &weight) {
     f_sun = 0.f;
     weight = 0.f;
-    if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+    if (bsdf_is_local(P.bsdf_type)) { // 6SV ocean, ocean_mishchenko, ocean_grasp, maignan
         f3 fs, ft;
         surface_frame<SPH>(n0, fs, ft);
         f3 wi = mk3(-dot3(d, fs), -dot3(d, ft), ci);
         if (want_nee) {
             f3 ws = mk3(dot3(sun, fs), dot3(sun, ft), dot3(sun, n0));
-            if (ws.z > 0.f) f_sun = oc_eval(P, wi, ws);
+            if (ws.z > 0.f) f_sun = lf_eval(P, wi, ws);
         }
         float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
         f3 wo;
-        weight = oc_sample(P, wi, s1, u1, u2, wo);
+        weight = lf_sample(P, wi, s1, u1, u2, wo);
         if (!(wo.z > 0.f)) weight = 0.f;
         d = normalize3(fma3(fs, wo.x, fma3(ft, wo.y, scale3(n0, wo.z))));
         return;

@@ -612,8 +612,9 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                     thr = 0.f; dead = true;
                 } else {
                     float f_sun, weight;
-                    if (POL && P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
-                        // Mueller-valued BSDF (polarized Fresnel glint), ocean_legacy.cpp:561-661
+                    if (POL && bsdf_is_local(P.bsdf_type)) {
+                        // Mueller-valued BSDF (polarized Fresnel matrix): ocean_legacy.cpp:561-661,
+                        // ocean_mishchenko.cpp:228-296, ocean_grasp.cpp:354-455, maignan.cpp:105-166
                         f3 fs, ft;
                         surface_frame<SPH>(n0, fs, ft);
                         f3 wi = mk3(-dot3(d, fs), -dot3(d, ft), ci);
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                         if (depth + 1u < P.max_depth) {
                             f3 ws = mk3(dot3(sun, fs), dot3(sun, ft), dot3(sun, n0));
                             if (ws.z > 0.f) {
-                                oc_eval_mueller(P, wi, ws, fs, ft, n0, Mb);
+                                lf_eval_mueller(P, false, wi, ws, fs, ft, n0, Mb);
 #pragma unroll
                                 for (int r = 0; r < 4; ++r)
                                     v[r] = fmaf(T[4 * r], Mb[0], fmaf(T[4 * r + 1], Mb[4], fmaf(T[4 * r + 2], Mb[8], T[4 * r + 3] * Mb[12])));
@@ -633,14 +634,11 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                         for (int k = 0; k < 3; ++k) qn[k] = v[k + 1] * inv;
                         float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
                         f3 wo;
-                        oc_sample(P, wi, s1, u1, u2, wo);
-                        float pdf = oc_pdf(P, wi, wo);
+                        if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) oc_sample(P, wi, s1, u1, u2, wo);
+                        else wo = gl_sample_dir(P, wi, s1, u1, u2);
                         float Tn[16];
-                        if (pdf > 0.f && wo.z > 0.f) {
-                            oc_eval_mueller(P, wi, wo, fs, ft, n0, Mb);
-                            float ip = __fdividef(1.f, pdf);
-#pragma unroll
-                            for (int k = 0; k < 16; ++k) Mb[k] *= ip;
+                        if (wo.z > 0.f) { // the weight BSDF::sample returns, as a matrix
+                            lf_eval_mueller(P, true, wi, wo, fs, ft, n0, Mb);
                             mueller_mul(T, Mb, Tn);
                         } else {
 #pragma unroll

@@ -161,6 +161,33 @@ inline void gauss_legendre(int n, double *x, double *w) {
         w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
     }
 }
+// ocean_mishchenko / ocean_grasp / maignan: raw plugin parameters -> the slots the device code reads
+// (ocean_mishchenko.cpp:136-142, ocean_grasp.cpp:155-188, oceanprops.h:330-363, :582-584)
+inline void derive_glint(int type, const float *raw, float *out) {
+    for (int i = 0; i < ERTB_MAX_BSDF_PARAMS; ++i) out[i] = 0.f;
+    double ws = 0.0, eta, k, ext;
+    if (type == ERTB_BSDF_OCEAN_MISHCHENKO) { ws = raw[0]; eta = raw[1]; k = raw[2]; ext = raw[3]; }
+    else if (type == ERTB_BSDF_OCEAN_GRASP) { ws = raw[1]; eta = raw[2]; k = raw[3]; ext = raw[4]; }
+    else { eta = raw[2]; k = raw[3]; ext = raw[4]; }
+    out[OC_N_REAL] = (float) (eta / ext);
+    out[OC_N_IMAG] = (float) (k / ext);
+    if (type == ERTB_BSDF_MAIGNAN) {
+        out[15] = (float) ((double) raw[0] * exp(-(double) raw[1])); // MG_CEXP
+        return;
+    }
+    const double sigma = sqrt(0.5 * (0.00512 * ws + 0.003)), alpha = fmax(sqrt(2.0) * sigma, 1e-4);
+    out[OC_SIGMA_U] = out[OC_SIGMA_C] = (float) sigma;
+    out[OC_ALPHA_UP] = out[OC_ALPHA_VP] = (float) alpha;
+    out[OC_SHADOWING] = 1.f;
+    out[OC_WIND_SPEED] = (float) ws;
+    if (type == ERTB_BSDF_OCEAN_GRASP) {
+        const double cov = fmin(1.0, fmax(0.0, 2.95e-06 * pow(ws, 3.52))), um = (double) raw[0] * 0.001;
+        const double eff = um >= 0.6 ? 0.22 * exp(-1.75 * pow(um - 0.6, 0.99)) : 0.22;
+        out[OC_COVERAGE] = (float) cov;
+        out[OC_WHITECAP] = (float) (cov * eff);
+        out[OC_R_OMEGA] = raw[5]; // water body reflectance
+    }
+}
 } // namespace ertb_ocean_host
 
 // ----------------------------------------------------------------- transmittance tables
@@ -455,4 +482,121 @@ __device__ __forceinline__ void oc_fresnel_mueller(float nr, float ni, f3 wi_in,
     M[10] = coeff * (ttpp.re + tppt.re); M[11] = coeff * (ttpp.im - tppt.im);
     M[12] = coeff * (ttpt.im + tppp.im); M[13] = coeff * (ttpt.im - tppp.im);
     M[14] = -coeff * (ttpp.im + tppt.im); M[15] = coeff * (ttpp.re - tppt.re);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Isotropic-Beckmann glint family: ocean_mishchenko, ocean_grasp, maignan.
+//   ERP/bsdfs/ocean_mishchenko.cpp:136-142 update(), :144-226 sample, :228-296 eval, :298-325 pdf
+//   ERP/bsdfs/ocean_grasp.cpp:202-238 eval_glint, :246-255 lambda, :267-352 sample, :354-455 eval, :457-512 pdf
+//   ERP/bsdfs/maignan.cpp:105-166 eval_maignan, :168-194 sample, :196-211 eval, :213-224 pdf
+// The host (scene_commit) derives the OC_* slots the Beckmann helpers above read (sigma_u = sigma_c =
+// sqrt(mss / 2), wind direction 0, no correlation), so D, G1, the height-correlated G and the
+// visible-normal sampling are the very same device functions the 6SV ocean uses.  Slots reused:
+// OC_N_REAL / OC_N_IMAG = lower index relative to the (real) exterior index, OC_COVERAGE, OC_WHITECAP
+// (Monahan / Frouin, ocean_grasp), OC_R_OMEGA = water body reflectance, MG_CEXP = C exp(-ndvi).
+// ------------------------------------------------------------------------------------------------
+#define MG_CEXP 15 /* first slot the 6SV ocean leaves free */
+
+__device__ __forceinline__ bool bsdf_is_glint_family(int t) { return t >= ERTB_BSDF_OCEAN_MISHCHENKO; }
+__device__ __forceinline__ bool bsdf_is_local(int t) { return t == ERTB_BSDF_OCEAN_LEGACY || t >= ERTB_BSDF_OCEAN_MISHCHENKO; }
+
+__device__ __forceinline__ float gl_grasp_lambda(float vz, float sigma) { // ocean_grasp.cpp:246-255
+    float st = sigma * safe_sqrtf(1.f - vz * vz) / vz;
+    return 0.5f * (0.7978845608f * st * __expf(-1.f / (2.f * st * st)) - erfcf(0.70710678f / st));
+}
+__device__ __forceinline__ float gl_fresnel00(const ErtbParams &P, f3 wi, f3 wo) {
+    float M[16];
+    oc_fresnel_mueller(P.bsdf[OC_N_REAL], P.bsdf[OC_N_IMAG], mk3(-wo.x, -wo.y, -wo.z), wi, M);
+    return M[0];
+}
+// scalar factor in front of the Fresnel matrix in BSDF::eval (with the cosine where the plugin has one)
+__device__ __forceinline__ float gl_geometry(const ErtbParams &P, f3 wi, f3 wo) {
+    if (P.bsdf_type == ERTB_BSDF_MAIGNAN) { // maignan.cpp:116-136; cos(Theta) = wi . wo
+        float cT = clampf(dot3(wi, wo), -1.f, 1.f);
+        float tan_a = sqrtf((1.f - cT) / (1.f + cT));
+        return P.bsdf[MG_CEXP] * __expf(-tan_a) / (4.f * (wi.z + wo.z));
+    }
+    f3 m = normalize3(mk3(wi.x + wo.x, wi.y + wo.y, wi.z + wo.z));
+    float D = oc_beckmann_D(P, m);
+    const bool facing = dot3(wi, m) * wi.z > 0.f && dot3(wo, m) * wo.z > 0.f;
+    if (P.bsdf_type == ERTB_BSDF_OCEAN_MISHCHENKO) { // :249-254
+        float G = facing ? 1.f / (1.f + oc_lambda(P, wi) + oc_lambda(P, wo)) : 0.f;
+        return D * G / (4.f * wi.z);
+    }
+    const float sigma = P.bsdf[OC_SIGMA_U];
+    float G = facing ? 1.f / (1.f + gl_grasp_lambda(wo.z, sigma) + gl_grasp_lambda(wi.z, sigma)) : 0.f;
+    return (1.f - P.bsdf[OC_COVERAGE]) * D * G / (4.f * wi.z); // pi D G / (4 ci co) * co / pi
+}
+__device__ __forceinline__ float gl_dep(const ErtbParams &P, f3 wo) { // ocean_grasp.cpp:395-404, :436
+    if (P.bsdf_type != ERTB_BSDF_OCEAN_GRASP) return 0.f;
+    return (P.bsdf[OC_WHITECAP] + (1.f - P.bsdf[OC_COVERAGE]) * P.bsdf[OC_R_OMEGA]) * wo.z * ERTB_INV_PI;
+}
+__device__ __forceinline__ float gl_eval(const ErtbParams &P, f3 wi, f3 wo) {
+    if (!(wi.z > 0.f && wo.z > 0.f)) return 0.f;
+    return gl_dep(P, wo) + gl_geometry(P, wi, wo) * gl_fresnel00(P, wi, wo);
+}
+__device__ __forceinline__ float gl_pdf(const ErtbParams &P, f3 wi, f3 wo) {
+    if (!(wi.z > 0.f && wo.z > 0.f)) return 0.f;
+    if (P.bsdf_type == ERTB_BSDF_MAIGNAN) return wo.z * ERTB_INV_PI;
+    f3 m = normalize3(mk3(wi.x + wo.x, wi.y + wo.y, wi.z + wo.z));
+    float spec = oc_beckmann_D(P, m) * oc_g1(P, wi, m) / (4.f * wi.z);
+    if (P.bsdf_type == ERTB_BSDF_OCEAN_MISHCHENKO) return (dot3(wi, m) > 0.f && dot3(wo, m) > 0.f) ? spec : 0.f;
+    const float cov = P.bsdf[OC_COVERAGE], p_spec = 1.f / (P.bsdf[OC_R_OMEGA] + 1.f), pc = wo.z * ERTB_INV_PI;
+    return cov * pc + (1.f - cov) * ((1.f - p_spec) * pc + p_spec * spec);
+}
+// visible-normal sample of the isotropic distribution + mirror reflection
+__device__ __forceinline__ f3 gl_reflect_sample(const ErtbParams &P, f3 wi, float u1, float u2, f3 &m) {
+    const float a = fmaxf(1.41421356f * P.bsdf[OC_SIGMA_U], 1e-4f);
+    f3 p = normalize3(mk3(a * wi.x, a * wi.y, wi.z));
+    float st2 = 1.f - p.z * p.z, sphi = 0.f, cphi = 1.f;
+    if (st2 > 0.f) { float is = rsqrtf(st2); sphi = p.y * is; cphi = p.x * is; }
+    float sx, sy;
+    oc_sample_visible_11(p.z, u1, u2, sx, sy);
+    m = normalize3(mk3(-(cphi * sx - sphi * sy) * a, -(sphi * sx + cphi * sy) * a, 1.f));
+    float dp = dot3(wi, m);
+    return mk3(2.f * dp * m.x - wi.x, 2.f * dp * m.y - wi.y, 2.f * dp * m.z - wi.z);
+}
+// BSDF::sample: direction only
+__device__ __forceinline__ f3 gl_sample_dir(const ErtbParams &P, f3 wi, float s1, float u1, float u2) {
+    f3 m;
+    if (P.bsdf_type == ERTB_BSDF_MAIGNAN) return cosine_hemisphere(u1, u2);
+    if (P.bsdf_type == ERTB_BSDF_OCEAN_MISHCHENKO) return gl_reflect_sample(P, wi, u1, u2, m);
+    const float cov = P.bsdf[OC_COVERAGE], p_diff = 1.f - 1.f / (P.bsdf[OC_R_OMEGA] + 1.f); // :285-318
+    if (s1 < cov || (s1 - cov) / (1.f - cov) < p_diff) return cosine_hemisphere(u1, u2);
+    return gl_reflect_sample(P, wi, u1, u2, m);
+}
+// scalar factor of the weight BSDF::sample returns for `wo`, in front of the Fresnel matrix, and the
+// factor `dscale` applying to the depolarizing part
+__device__ __forceinline__ float gl_weight_geometry(const ErtbParams &P, f3 wi, f3 wo, float &dscale) {
+    dscale = 0.f;
+    if (!(wi.z > 0.f && wo.z > 0.f)) return 0.f;
+    if (P.bsdf_type == ERTB_BSDF_MAIGNAN) return gl_geometry(P, wi, wo); // C F, not divided by the pdf (:189-193)
+    if (P.bsdf_type == ERTB_BSDF_OCEAN_MISHCHENKO) { // F G / G1 (:170-181)
+        f3 m = normalize3(mk3(wi.x + wo.x, wi.y + wo.y, wi.z + wo.z));
+        float g1 = oc_g1(P, wi, m);
+        if (!(oc_beckmann_D(P, m) * g1 * fabsf(dot3(wi, m)) != 0.f)) return 0.f;
+        float G = (dot3(wo, m) * wo.z > 0.f) ? 1.f / (1.f + oc_lambda(P, wi) + oc_lambda(P, wo)) : 0.f;
+        return G / g1;
+    }
+    float pdf = gl_pdf(P, wi, wo);
+    dscale = pdf > 0.f ? 1.f / pdf : 0.f;
+    return gl_geometry(P, wi, wo) * dscale;
+}
+// BSDF::sample (scalar): returns the weight
+__device__ __forceinline__ float gl_sample(const ErtbParams &P, f3 wi, float s1, float u1, float u2, f3 &wo) {
+    wo = mk3(0.f, 0.f, 1.f);
+    if (!(wi.z > 0.f)) return 0.f;
+    wo = gl_sample_dir(P, wi, s1, u1, u2);
+    float dscale;
+    float g = gl_weight_geometry(P, wi, wo, dscale);
+    if (!(wo.z > 0.f)) return 0.f;
+    return gl_dep(P, wo) * dscale + g * gl_fresnel00(P, wi, wo);
+}
+
+// dispatch over the local-frame BSDFs (6SV ocean + glint family)
+__device__ __forceinline__ float lf_eval(const ErtbParams &P, f3 wi, f3 wo) {
+    return P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY ? oc_eval(P, wi, wo) : gl_eval(P, wi, wo);
+}
+__device__ __forceinline__ float lf_sample(const ErtbParams &P, f3 wi, float s1, float u1, float u2, f3 &wo) {
+    return P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY ? oc_sample(P, wi, s1, u1, u2, wo) : gl_sample(P, wi, s1, u1, u2, wo);
 }

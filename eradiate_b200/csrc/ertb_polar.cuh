@@ -150,29 +150,44 @@ __device__ __forceinline__ void stokes_output_rotation(const ErtbParams &P, f3 d
 
 #include "ertb_ocean.cuh"
 
-// Polarized ocean BSDF value (times cos) in WORLD implicit Stokes bases (ocean_legacy.cpp:561-661
-// followed by SurfaceInteraction::to_world_mueller).  The reference rotates twice about the same
-// propagation directions (meridian plane -> local implicit basis -> world implicit basis); the two
-// rotations compose, so the meridian-plane axes are carried to world space and rotated once.
+// Polarized value of a local-frame BSDF (6SV ocean, ocean_mishchenko, ocean_grasp, maignan) in WORLD implicit
+// Stokes bases: BSDF::eval (ocean_legacy.cpp:561-661, ocean_mishchenko.cpp:228-296, ocean_grasp.cpp:354-455,
+// maignan.cpp:105-166) followed by SurfaceInteraction::to_world_mueller.  The reference rotates twice about the
+// same propagation directions (meridian plane -> local implicit basis -> world implicit basis); the two rotations
+// compose, so the meridian-plane axes are carried to world space and rotated once.
+// `weight`: return the weight BSDF::sample gives for the sampled `wo` instead (eval / pdf for the two-lobe
+// oceans, F G / G1 for ocean_mishchenko, C F for maignan).
 // `wi`, `wo` local (wi = si.wi, wo = towards the light / sampled), (fs, ft, n) = shading frame.
-__device__ __forceinline__ void oc_eval_mueller(const ErtbParams &P, f3 wi, f3 wo, f3 fs, f3 ft, f3 n, float *M) {
+__device__ __forceinline__ void lf_eval_mueller(const ErtbParams &P, bool weight, f3 wi, f3 wo, f3 fs, f3 ft, f3 n, float *M) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) M[i] = 0.f;
     if (!(wi.z > 0.f && wo.z > 0.f)) return;
-    const float *tdn = P.ocean_tables, *tup = P.ocean_tables + ERTB_OC_RES * ERTB_OC_RES;
-    float wc = P.bsdf[OC_WHITECAP], ul = 0.f;
-    if (P.bsdf[OC_UNDERLIGHT_ON] != 0.f)
-        ul = P.bsdf[OC_UL_NORM] * oc_transmittance(P, tup, wi.z, wo.x, wo.y) * oc_transmittance(P, tdn, wo.z, wo.x, wo.y);
-    const float scale = wo.z * ERTB_INV_PI;
-    // glint geometry factor without Fresnel (eval_glint(wi := wo, wo := si.wi), :405-420)
-    f3 m = normalize3(mk3(wi.x + wo.x, wi.y + wo.y, wi.z + wo.z));
-    float g = oc_beckmann_D(P, m) * oc_gram_charlier(P, m) / (4.f * wi.z * wo.z);
-    if (P.bsdf[OC_SHADOWING] != 0.f) {
-        float G = 1.f / (1.f + oc_lambda(P, wi) + oc_lambda(P, wo));
-        if (dot3(wi, m) * wi.z <= 0.f || dot3(wo, m) * wo.z <= 0.f) G = 0.f;
-        g *= G;
+    float g, dep;
+    if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+        const float *tdn = P.ocean_tables, *tup = P.ocean_tables + ERTB_OC_RES * ERTB_OC_RES;
+        float wc = P.bsdf[OC_WHITECAP], ul = 0.f;
+        if (P.bsdf[OC_UNDERLIGHT_ON] != 0.f)
+            ul = P.bsdf[OC_UL_NORM] * oc_transmittance(P, tup, wi.z, wo.x, wo.y) * oc_transmittance(P, tdn, wo.z, wo.x, wo.y);
+        float scale = wo.z * ERTB_INV_PI;
+        if (weight) { // ocean_legacy.cpp:553-558
+            float pdf = oc_pdf(P, wi, wo);
+            scale = pdf > 0.f ? __fdividef(scale, pdf) : 0.f;
+        }
+        // glint geometry factor without Fresnel (eval_glint(wi := wo, wo := si.wi), :405-420)
+        f3 m = normalize3(mk3(wi.x + wo.x, wi.y + wo.y, wi.z + wo.z));
+        g = oc_beckmann_D(P, m) * oc_gram_charlier(P, m) / (4.f * wi.z * wo.z);
+        if (P.bsdf[OC_SHADOWING] != 0.f) {
+            float G = 1.f / (1.f + oc_lambda(P, wi) + oc_lambda(P, wo));
+            if (dot3(wi, m) * wi.z <= 0.f || dot3(wo, m) * wo.z <= 0.f) G = 0.f;
+            g *= G;
+        }
+        g *= ERTB_PI * (1.f - P.bsdf[OC_COVERAGE]) * scale;
+        dep = (wc + (1.f - wc) * ul) * scale;
+    } else {
+        float dscale = 1.f;
+        g = weight ? gl_weight_geometry(P, wi, wo, dscale) : gl_geometry(P, wi, wo);
+        dep = gl_dep(P, wo) * dscale;
     }
-    g *= ERTB_PI * (1.f - P.bsdf[OC_COVERAGE]) * scale;
     f3 in_fwd = neg3(wo), out_fwd = wi; // light arrives along -wo and leaves along si.wi
     oc_fresnel_mueller(P.bsdf[OC_N_REAL], P.bsdf[OC_N_IMAG], in_fwd, out_fwd, M);
 #pragma unroll
@@ -191,5 +206,5 @@ __device__ __forceinline__ void oc_eval_mueller(const ErtbParams &P, f3 wi, f3 w
     basis_rotation(in_w, p_in_w, stokes_basis(in_w), ci, si);
     basis_rotation(out_w, p_out_w, stokes_basis(out_w), co, so);
     rotate_mueller(M, ci, si, co, so);
-    M[0] += (wc + (1.f - wc) * ul) * scale; // depolarizer part is rotation invariant
+    M[0] += dep; // depolarizer part is rotation invariant
 }

@@ -34,6 +34,16 @@ def bsdf_eval(scene, wi, wo):
     return out
 
 
+def bsdf_mueller(scene, wi, wo):
+    """BSDF::eval of a polarized scene as 4x4 Mueller matrices (local frame, implicit Stokes bases)."""
+    dev = _device_scene(scene)
+    dev.sync()
+    wi, wo = _f(wi).reshape(-1, 3), _f(wo).reshape(-1, 3)
+    M = np.zeros((wi.shape[0], 4, 4), dtype=np.float32)
+    _lib.check(dev.lib.ertb_kat_bsdf_mueller(dev.handle, wi.shape[0], _fp(wi), _fp(wo), _fp(M)))
+    return M
+
+
 def bsdf_sample(scene, wi, u):
     dev = _device_scene(scene)
     dev.sync()

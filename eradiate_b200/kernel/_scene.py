@@ -228,7 +228,8 @@ _SUPPORTED = {
     "emitter": {"directional"},
     "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance", "cylinder"},
     "medium": {"heterogeneous", "homogeneous", "piecewise"},
-    "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "null", "bilambertian", "blendbsdf"},
+    "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "ocean_mishchenko", "ocean_grasp", "maignan",
+             "null", "bilambertian", "blendbsdf"},
     "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
               "rayleigh_polarized", "tabphase_polarized"},
     "sensor": {"mdistant", "hdistant", "distantflux", "perspective", "mpdistant", "mradiancemeter"},
@@ -241,9 +242,6 @@ _KNOWN_UNSUPPORTED = {
     "obj": "mesh canopy elements are not implemented",
     # the reference's remaining plugins for this slot
     "astroobject": "finite-size solar discs need emitter-hit MIS, which the kernels do not carry (use 'directional')",
-    "ocean_grasp": "only the 'ocean_legacy' (6SV) ocean model is implemented",
-    "ocean_mishchenko": "only the 'ocean_legacy' (6SV) ocean model is implemented",
-    "maignan": "this BSDF is not implemented",
     "mqdiffuse": "tabulated measured BSDFs are not implemented",
     "measured_mono": "tabulated measured BSDFs are not implemented",
     "selectbsdf": "this BSDF adapter is not implemented",
@@ -453,6 +451,29 @@ class _Loader:
             b.component = int(d.get("component", 0))
             if b.component != 0:
                 raise RuntimeError("ocean_legacy: only component=0 (full BRDF) is supported")
+        elif ty == "ocean_mishchenko":  # ocean_mishchenko.cpp:95-113 (`shadowing` is read and never used)
+            b.values["wind_speed"] = float(d.get("wind_speed", 0.1))
+            b.children["eta"] = tex("eta", 1.33)
+            b.children["k"] = tex("k", 0.0)
+            b.children["ext_ior"] = tex("ext_ior", 1.000277)
+        elif ty == "ocean_grasp":  # ocean_grasp.cpp:120-146
+            if "wavelength" not in d:
+                raise RuntimeError("ocean_grasp: missing required parameter 'wavelength'")
+            b.values["wavelength"] = float(d["wavelength"])
+            b.children["wind_speed"] = tex("wind_speed", 0.1)
+            b.children["eta"] = tex("eta", 1.33)
+            b.children["k"] = tex("k", 0.0)
+            b.children["ext_ior"] = tex("ext_ior", 1.000277)
+            b.children["water_body_reflectance"] = tex("water_body_reflectance", 0.0)
+            b.component = int(d.get("component", 0))
+            if b.component != 0:
+                raise RuntimeError("ocean_grasp: only component=0 (full BRDF) is supported")
+        elif ty == "maignan":  # maignan.cpp:92-101 (constructor defaults, not the documented ones)
+            b.children["C"] = tex("C", 0.1)
+            b.children["ndvi"] = tex("ndvi", 0.0)
+            b.children["refr_re"] = tex("refr_re", 1.5)
+            b.children["refr_im"] = tex("refr_im", 0.0)
+            b.children["ext_ior"] = tex("ext_ior", 1.000277)
         return b
 
     def make_medium(self, d, oid) -> Medium:
@@ -1049,6 +1070,16 @@ class FlatScene:
             p[0], p[1], p[2] = v["wavelength"], v["wind_speed"], v["wind_direction"]
             p[3], p[4], p[5] = v["chlorinity"], v["pigmentation"], float(v["shadowing"])
             p[6] = float(b.component)
+        elif b.type == "ocean_mishchenko":
+            p[0] = b.values["wind_speed"]
+            p[1], p[2], p[3] = tv("eta"), tv("k"), tv("ext_ior")
+        elif b.type == "ocean_grasp":
+            p[0], p[1] = b.values["wavelength"], tv("wind_speed")
+            p[2], p[3], p[4], p[5] = tv("eta"), tv("k"), tv("ext_ior"), tv("water_body_reflectance")
+            p[6] = float(b.component)
+        elif b.type == "maignan":
+            for i, name in enumerate(("C", "ndvi", "refr_re", "refr_im", "ext_ior")):
+                p[i] = tv(name)
         return p
 
     def trunk_reflectance(self, group: int) -> float:
@@ -1067,6 +1098,9 @@ class FlatScene:
             "rtls": _abi.BSDF_RTLS,
             "hapke": _abi.BSDF_HAPKE,
             "ocean_legacy": _abi.BSDF_OCEAN_LEGACY,
+            "ocean_mishchenko": _abi.BSDF_OCEAN_MISHCHENKO,
+            "ocean_grasp": _abi.BSDF_OCEAN_GRASP,
+            "maignan": _abi.BSDF_MAIGNAN,
         }[(self.bsdf if b is None else b).type]
 
     # -- ctypes descriptor -----------------------------------------------------------------

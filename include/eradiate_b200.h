@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 11
+#define ERTB_ABI_VERSION 12
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -54,7 +54,18 @@ enum ertb_bsdf_type {
     ERTB_BSDF_OCEAN_LEGACY = 4, /* ERP/bsdfs/ocean_legacy.cpp; params: wavelength(nm), wind_speed,
                                    wind_direction(deg, North-left), chlorinity, pigmentation,
                                    shadowing(0/1), component (only 0) */
-    ERTB_BSDF_BLACK = 5         /* reflectance 0 (no surface contribution) */
+    ERTB_BSDF_BLACK = 5,        /* reflectance 0 (no surface contribution) */
+    /* ERP/bsdfs/ocean_mishchenko.cpp:86-346 (sun glint only: isotropic Beckmann facets of the Cox-Munk
+     * mean square slope, height-correlated Smith G, Mishchenko-Travis Fresnel matrix);
+     * params: wind_speed, eta, k, ext_ior */
+    ERTB_BSDF_OCEAN_MISHCHENKO = 6,
+    /* ERP/bsdfs/ocean_grasp.cpp:107-539 (Frouin whitecaps + Lambertian water body + glint);
+     * params: wavelength(nm), wind_speed, eta, k, ext_ior, water_body_reflectance, component (only 0) */
+    ERTB_BSDF_OCEAN_GRASP = 7,
+    /* ERP/bsdfs/maignan.cpp:83-254 (Maignan et al. 2009 polarized land reflectance; eval() carries no
+     * cosine and sample() returns C*F without dividing by the pdf -- reproduced as is);
+     * params: C, ndvi, refr_re, refr_im, ext_ior */
+    ERTB_BSDF_MAIGNAN = 8
 };
 
 enum ertb_phase_type {
@@ -349,6 +360,10 @@ int ertb_kat_piecewise_transmittance(ertb_scene *scene, size_t n, const float *a
  * implicit Stokes bases of the two directions (16*n, row-major) and pdf (n) */
 int ertb_kat_phase_mueller(ertb_scene *scene, int leaf, size_t n, const float *wi, const float *wo,
                            float *mueller, float *pdf);
+/* bsdf_mueller (polarized scenes): wi = si.wi, wo (3*n, local frame, z = normal) -> BSDF::eval as a 4x4
+ * Mueller matrix in the implicit Stokes bases of -wo and wi (16*n, row-major), i.e. what the reference's
+ * plugin tests read (ERP/tests/bsdfs/test_ocean_mishchenko.py:44-109, test_maignan.py:28-88) */
+int ertb_kat_bsdf_mueller(ertb_scene *scene, size_t n, const float *wi, const float *wo, float *mueller);
 int ertb_kat_sensor_ray(ertb_scene *scene, int sensor, size_t n, const float *film_sample,
                         const float *aperture_sample, double *origin, double *dir, float *weight);
 

@@ -290,12 +290,16 @@ typedef struct {
     int has_distr[ERTB_MAX_PHASE];
     v3 emitter_d;               /* normalised propagation direction */
     ocean_state_t ocean;        /* ocean_legacy precomputed tables */
+    glint_state_t glint;        /* ocean_mishchenko / ocean_grasp / maignan */
     double *pw_cum, *pw_rcum;   /* piecewise.cpp m_cum_opt_thickness / m_reverse_cum_opt_thickness */
     double pp_half_width;       /* > 0: finite slab bbox in x, y (known-answer tests only) */
     canopy_t canopy;            /* explicit disk-leaf canopy (plane-parallel scenes) */
 } scene_t;
 
 static int piecewise_init(scene_t *S);
+static int is_glint_family(int type) {
+    return type == ERTB_BSDF_OCEAN_MISHCHENKO || type == ERTB_BSDF_OCEAN_GRASP || type == ERTB_BSDF_MAIGNAN;
+}
 
 static void scene_free(scene_t *S) {
     for (int i = 0; i < ERTB_MAX_PHASE; ++i)
@@ -337,6 +341,11 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
     S->emitter_d = vnormalize(V(d->emitter_direction[0], d->emitter_direction[1], d->emitter_direction[2]));
     if (d->bsdf_type == ERTB_BSDF_OCEAN_LEGACY)
         if (ocean_init(&S->ocean, d->bsdf_params)) return fail("ocean_legacy init failed");
+    if (is_glint_family(d->bsdf_type)) {
+        if (d->bsdf_type == ERTB_BSDF_OCEAN_GRASP && d->bsdf_params[6] != 0.f)
+            return fail("ocean_grasp: only component=0 (full BRDF) is supported");
+        glint_init(&S->glint, d->bsdf_type, d->bsdf_params);
+    }
     if (d->n_instances > 0) {
         if (S->spherical || d->polarized) return fail("canopies: plane-parallel, unpolarized scenes only");
         if (canopy_init(&S->canopy, d)) return fail("canopy init failed");
@@ -1053,6 +1062,10 @@ static double bsdf_eval_tp(const scene_t *S, int type, const float *P, v3 wi, v3
         case ERTB_BSDF_RTLS: return eval_rtls(P, wi, wo) * fabs(cto); /* rtls.cpp:245-257 */
         case ERTB_BSDF_HAPKE: return eval_hapke(P, wi, wo) * fabs(cto);
         case ERTB_BSDF_OCEAN_LEGACY: return ocean_eval(&S->ocean, wi.x, wi.y, wi.z, wo.x, wo.y, wo.z);
+        case ERTB_BSDF_OCEAN_MISHCHENKO: case ERTB_BSDF_OCEAN_GRASP: case ERTB_BSDF_MAIGNAN: {
+            double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
+            return glint_eval(&S->glint, a, b);
+        }
         default: return 0.0;
     }
 }
@@ -1065,6 +1078,11 @@ static double bsdf_sample_tp(const scene_t *S, int type, const float *P, v3 wi, 
     if (!(wi.z > 0.0)) return 0.0;
     if (type == ERTB_BSDF_OCEAN_LEGACY) {
         double o[3], w = ocean_sample(&S->ocean, wi.x, wi.y, wi.z, s1, u1, u2, o);
+        *wo = V(o[0], o[1], o[2]);
+        return w;
+    }
+    if (is_glint_family(type)) {
+        double a[3] = { wi.x, wi.y, wi.z }, o[3], w = glint_sample(&S->glint, a, s1, u1, u2, o);
         *wo = V(o[0], o[1], o[2]);
         return w;
     }
@@ -1486,14 +1504,29 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
  * depolarizer(value) (rotation invariant).  ocean_legacy.cpp:603-634 builds the glint matrix in
  * the meridian-plane bases and rotates it to the implicit bases of -wo_hat / wi_hat (local frame);
  * volpath.cpp:357 / :369 then applies si.to_world_mueller(M, -wo, si.wi) (interaction.h:407-428). */
-static void bsdf_eval_mueller(const scene_t *S, const frame_t *fr, v3 wi, v3 wo, mueller_t *M) {
+/* `weight` = 0: BSDF::eval; 1: the weight BSDF::sample returns for the sampled direction `wo` (eval / pdf for
+ * the two-lobe ocean models, F G / G1 for ocean_mishchenko.cpp:180-181, C F for maignan.cpp:189-193).
+ * `fr` = NULL: stop after the plugin's own rotation (local implicit bases: what BSDF::eval returns). */
+static void bsdf_mueller(const scene_t *S, const frame_t *fr, int weight, v3 wi, v3 wo, mueller_t *M) {
     *M = mu_zero();
-    if (S->desc->bsdf_type != ERTB_BSDF_OCEAN_LEGACY) {
+    const int type = S->desc->bsdf_type;
+    if (type != ERTB_BSDF_OCEAN_LEGACY && !is_glint_family(type)) {
         M->m[0] = bsdf_eval(S, wi, wo);
+        if (weight) M->m[0] = wo.z > 0.0 ? M->m[0] / (INV_PI * wo.z) : 0.0;
         return;
     }
     double wil[3] = { wi.x, wi.y, wi.z }, wol[3] = { wo.x, wo.y, wo.z }, dep, gl[16];
-    ocean_eval_polarized(&S->ocean, wil, wol, &dep, gl);
+    if (type == ERTB_BSDF_OCEAN_LEGACY) {
+        ocean_eval_polarized(&S->ocean, wil, wol, &dep, gl);
+        if (weight) { /* ocean_legacy.cpp:553-558: eval / pdf */
+            double pdf = ocean_pdf(&S->ocean, wi.x, wi.y, wi.z, wo.x, wo.y, wo.z);
+            double ip = pdf > 0.0 ? 1.0 / pdf : 0.0;
+            dep *= ip;
+            for (int i = 0; i < 16; ++i) gl[i] *= ip;
+        }
+    } else {
+        glint_polarized(&S->glint, weight, wil, wol, &dep, gl);
+    }
     mueller_t G; memcpy(G.m, gl, sizeof gl);
     if (wi.z > 0.0 && wo.z > 0.0) {
         v3 n = V(0, 0, 1), in_fwd = vneg(wo), out_fwd = wi; /* wo_hat = wo, wi_hat = si.wi */
@@ -1502,13 +1535,18 @@ static void bsdf_eval_mueller(const scene_t *S, const frame_t *fr, v3 wi, v3 wo,
         if (isnan(p_in.x) || isnan(p_in.y) || isnan(p_in.z)) p_in = V(0, 1, 0);
         if (isnan(p_out.x) || isnan(p_out.y) || isnan(p_out.z)) p_out = V(0, 1, 0);
         G = rotate_mueller_basis(&G, in_fwd, p_in, stokes_basis(in_fwd), out_fwd, p_out, stokes_basis(out_fwd));
-        /* to_world_mueller(M, in_forward_local = -wo, out_forward_local = si.wi) */
-        v3 in_w = to_world(fr, in_fwd), out_w = to_world(fr, out_fwd);
-        G = rotate_mueller_basis(&G, in_w, to_world(fr, stokes_basis(in_fwd)), stokes_basis(in_w),
-                                 out_w, to_world(fr, stokes_basis(out_fwd)), stokes_basis(out_w));
+        if (fr) {
+            /* to_world_mueller(M, in_forward_local = -wo, out_forward_local = si.wi) */
+            v3 in_w = to_world(fr, in_fwd), out_w = to_world(fr, out_fwd);
+            G = rotate_mueller_basis(&G, in_w, to_world(fr, stokes_basis(in_fwd)), stokes_basis(in_w),
+                                     out_w, to_world(fr, stokes_basis(out_fwd)), stokes_basis(out_w));
+        }
     }
     *M = G;
     M->m[0] += dep;
+}
+static void bsdf_eval_mueller(const scene_t *S, const frame_t *fr, v3 wi, v3 wo, mueller_t *M) {
+    bsdf_mueller(S, fr, 0, wi, wo, M);
 }
 
 /* volpath.cpp:93-396 in a polarized variant: Spectrum = 4x4 Mueller matrix.  `throughput` is
@@ -1621,9 +1659,9 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, int medi
                 v3 wo;
                 double w = bsdf_sample(S, wi, s1, u1, u2, &wo);
                 mueller_t Dw = mu_zero();
-                if (D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY) { /* ocean_legacy.cpp:553-558: eval / pdf */
-                    double pdf = ocean_pdf(&S->ocean, wi.x, wi.y, wi.z, wo.x, wo.y, wo.z);
-                    if (pdf > 0.0) { bsdf_eval_mueller(S, &fr, wi, wo, &Dw); Dw = mu_scale(&Dw, 1.0 / pdf); }
+                if (D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY || is_glint_family(D->bsdf_type)) {
+                    (void) w;
+                    bsdf_mueller(S, &fr, 1, wi, wo, &Dw);
                 } else {
                     Dw.m[0] = w; /* depolarizer(w) */
                 }
@@ -1752,6 +1790,17 @@ int ertbo_bsdf_eval(const ertb_scene_desc *desc, size_t n, const double *wi, con
     if (scene_init(&S, desc)) return 1;
     for (size_t i = 0; i < n; ++i)
         out[i] = bsdf_eval(&S, V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
+    scene_free(&S);
+    return 0;
+}
+int ertbo_bsdf_mueller(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo, double *mueller) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    for (size_t i = 0; i < n; ++i) {
+        mueller_t M;
+        bsdf_mueller(&S, NULL, 0, V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), &M);
+        memcpy(mueller + 16 * i, M.m, sizeof M.m);
+    }
     scene_free(&S);
     return 0;
 }

@@ -37,6 +37,10 @@ int ertbo_piecewise_eval(const ertb_scene_desc *desc, double half_width, size_t 
 int ertbo_phase_mueller(const ertb_scene_desc *desc, int leaf, size_t n, const double *wi, const double *wo,
                         double *mueller, double *pdf);
 
+/* BSDF::eval of a polarized variant: 4x4 Mueller matrices (16*n, row-major) in the implicit Stokes bases
+ * of -wo and wi, local frame (z = normal). */
+int ertbo_bsdf_mueller(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo, double *mueller);
+
 /* Point-wise plugin evaluations (double). Same conventions as ertb_kat_*. */
 int ertbo_bsdf_eval(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo,
                     double *out);

@@ -14,6 +14,7 @@
  * Morel 1988) as tabulated by 6SV and by oceanprops.h:32-160.
  */
 #include "ertb_oracle_ocean.h"
+#include "../include/eradiate_b200.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -563,4 +564,182 @@ void ocean_eval_polarized(const ocean_state_t *o, const double wi_si[3], const d
     double F[16];
     fresnel_polarized(o->n_real, o->n_imag, minus_wi, wi_hat, F);
     for (int i = 0; i < 16; ++i) glint[i] = F[i] * g * (1.0 - o->whitecap_coverage) * scale;
+}
+
+/* ====================================================================================================
+ * Isotropic-Beckmann glint family (TEST INFRASTRUCTURE, as above).  Restates
+ *   ERP/bsdfs/ocean_mishchenko.cpp:136-142 update(), :144-226 sample, :228-296 eval, :298-325 pdf
+ *   ERP/bsdfs/ocean_grasp.cpp:155-165 parameters_changed, :172-174 eval_sigma, :186-188 whitecaps,
+ *       :202-238 eval_glint, :246-255 lambda, :267-352 sample, :354-455 eval, :457-512 pdf
+ *   ERP/bsdfs/maignan.cpp:105-166 eval_maignan, :168-194 sample, :196-211 eval, :213-224 pdf
+ *   oceanprops.h:330-336 whitecap_coverage_monahan, :350-363 whitecap_reflectance_frouin,
+ *       :443-545 fresnel_sunglint_polarized, :582-584 cox_munk_msslope_squared
+ * The exterior index is real, so only n_lower / n_ext enters the Fresnel coefficients.
+ * ==================================================================================================== */
+void glint_init(glint_state_t *g, int type, const float *p) {
+    memset(g, 0, sizeof *g);
+    g->type = type;
+    if (type == ERTB_BSDF_OCEAN_MISHCHENKO) { /* params: wind_speed, eta, k, ext_ior */
+        g->sigma = sqrt(0.5 * (0.00512 * (double) p[0] + 0.003));
+        g->nr = (double) p[1] / (double) p[3]; g->ni = (double) p[2] / (double) p[3];
+    } else if (type == ERTB_BSDF_OCEAN_GRASP) { /* params: wavelength, wind_speed, eta, k, ext_ior, wbr */
+        double wl = p[0], ws = p[1];
+        g->sigma = sqrt(0.5 * (0.00512 * ws + 0.003));
+        g->nr = (double) p[2] / (double) p[4]; g->ni = (double) p[3] / (double) p[4];
+        g->coverage = fmax(0.0, fmin(1.0, 2.95e-06 * pow(ws, 3.52)));
+        double um = wl * 0.001;
+        double eff = um >= 0.6 ? 0.22 * exp(-1.75 * pow(um - 0.6, 0.99)) : 0.22;
+        g->whitecap = g->coverage * eff;
+        g->wbr = p[5];
+    } else { /* maignan: C, ndvi, refr_re, refr_im, ext_ior */
+        g->cexp = (double) p[0] * exp(-(double) p[1]);
+        g->nr = (double) p[2] / (double) p[4]; g->ni = (double) p[3] / (double) p[4];
+    }
+}
+static beckmann_t glint_beckmann(const glint_state_t *g) {
+    beckmann_t B;
+    B.au = B.av = fmax(sqrt(2.0) * g->sigma, 1e-4); /* MicrofacetDistribution(Beckmann, alpha, sample_visible) */
+    B.angle = 0.0;
+    B.aup = B.avp = B.au;
+    B.corr = 0.0;
+    return B;
+}
+static void half_vector(const double a[3], const double b[3], double m[3]) {
+    m[0] = a[0] + b[0]; m[1] = a[1] + b[1]; m[2] = a[2] + b[2];
+    double inv = 1.0 / sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+    m[0] *= inv; m[1] *= inv; m[2] *= inv;
+}
+static double dot3d(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+/* ocean_grasp.cpp:246-255 */
+static double grasp_lambda(const double v[3], double sigma) {
+    double st = sigma * sqrt(1.0 - v[2] * v[2]) / v[2];
+    return 0.5 * (sqrt(2.0 / PI) * st * exp(-1.0 / (2.0 * st * st)) - (1.0 - erf(1.0 / (sqrt(2.0) * st))));
+}
+/* scalar geometry factor in front of the Fresnel matrix in BSDF::eval (cosine included where the plugin has it) */
+static double glint_geometry_iso(const glint_state_t *g, const double wi[3], const double wo[3]) {
+    beckmann_t B = glint_beckmann(g);
+    double m[3];
+    half_vector(wi, wo, m);
+    double D = beckmann_eval(&B, m);
+    if (g->type == ERTB_BSDF_OCEAN_MISHCHENKO) { /* :249-254 */
+        if (D == 0.0) return 0.0;
+        return D * beckmann_g_hc(&B, wi, wo, m) / (4.0 * wi[2]);
+    }
+    /* ocean_grasp eval_glint(wi := wo_hat = wo, wo := wi_hat = si.wi) :202-238, then (1 - coverage) cos / pi */
+    double G = 1.0 / (1.0 + grasp_lambda(wo, g->sigma) + grasp_lambda(wi, g->sigma));
+    if (dot3d(wo, m) * wo[2] <= 0.0) G = 0.0;
+    if (dot3d(wi, m) * wi[2] <= 0.0) G = 0.0;
+    double value = PI * D * G / (4.0 * wo[2] * wi[2]);
+    return (1.0 - g->coverage) * value * wo[2] / PI;
+}
+static double maignan_c(const glint_state_t *g, const double wi[3], const double wo[3]) { /* :116-136 */
+    double ci = wi[2], co = wo[2];
+    double si = sqrt(fmax(0.0, 1.0 - ci * ci)), so = sqrt(fmax(0.0, 1.0 - co * co));
+    double spi = 0, cpi = 1, spo = 0, cpo = 1; /* Frame3f::sincos_phi: (0, 1) along the normal */
+    double ni2 = wi[0] * wi[0] + wi[1] * wi[1], no2 = wo[0] * wo[0] + wo[1] * wo[1];
+    if (ni2 > 0.0) { double inv = 1.0 / sqrt(ni2); spi = wi[1] * inv; cpi = wi[0] * inv; }
+    if (no2 > 0.0) { double inv = 1.0 / sqrt(no2); spo = wo[1] * inv; cpo = wo[0] * inv; }
+    double cdphi = cpi * cpo + spi * spo;
+    double cT = ci * co + si * so * cdphi;
+    double tan_a = sqrt((1.0 - cT) / (1.0 + cT));
+    return g->cexp * exp(-tan_a) / (4.0 * (ci + co));
+}
+static double glint_dep(const glint_state_t *g, const double wo[3]) {
+    if (g->type != ERTB_BSDF_OCEAN_GRASP) return 0.0;
+    return (g->whitecap + (1.0 - g->coverage) * g->wbr) * wo[2] / PI; /* :395-404, :436 */
+}
+
+double glint_eval(const glint_state_t *g, const double wi[3], const double wo[3]) {
+    if (!(wi[2] > 0.0 && wo[2] > 0.0)) return 0.0;
+    double in_fwd[3] = { -wo[0], -wo[1], -wo[2] }, F[16];
+    fresnel_polarized(g->nr, g->ni, in_fwd, wi, F); /* F(-wo_hat, wi_hat), wo_hat = wo, wi_hat = si.wi */
+    if (g->type == ERTB_BSDF_MAIGNAN) return maignan_c(g, wi, wo) * F[0];
+    return glint_dep(g, wo) + glint_geometry_iso(g, wi, wo) * F[0];
+}
+double glint_pdf(const glint_state_t *g, const double wi[3], const double wo[3]) {
+    if (!(wi[2] > 0.0 && wo[2] > 0.0)) return 0.0;
+    if (g->type == ERTB_BSDF_MAIGNAN) return wo[2] / PI;
+    beckmann_t B = glint_beckmann(g);
+    double m[3];
+    half_vector(wi, wo, m);
+    double spec = beckmann_eval(&B, m) * beckmann_g1(&B, wi, m) / (4.0 * wi[2]);
+    if (g->type == ERTB_BSDF_OCEAN_MISHCHENKO)
+        return (dot3d(wi, m) > 0.0 && dot3d(wo, m) > 0.0) ? spec : 0.0;
+    double p_spec = 1.0 / (g->wbr + 1.0), p_diff = 1.0 - p_spec, pc = wo[2] / PI;
+    return g->coverage * pc + (1.0 - g->coverage) * (p_diff * pc + p_spec * spec);
+}
+static void cosine_hemisphere_d(double u1, double u2, double wo[3]) { /* warp.h:412-433 */
+    double x = 2.0 * u1 - 1.0, y = 2.0 * u2 - 1.0, r, phi;
+    if (x == 0.0 && y == 0.0) { r = 0.0; phi = 0.0; }
+    else if (fabs(x) < fabs(y)) { r = y; phi = 0.5 * PI - 0.25 * PI * x / y; }
+    else { r = x; phi = 0.25 * PI * y / x; }
+    wo[0] = r * cos(phi); wo[1] = r * sin(phi);
+    wo[2] = sqrt(fmax(0.0, 1.0 - wo[0] * wo[0] - wo[1] * wo[1]));
+}
+/* validity of a Mishchenko sample (:170-178): distr.sample's pdf != 0 and the reflected direction is up */
+static int mishchenko_valid(const beckmann_t *B, const double wi[3], const double wo[3], const double m[3]) {
+    double pdf_m = beckmann_eval(B, m) * beckmann_g1(B, wi, m) * fabs(dot3d(wi, m)) / wi[2];
+    return pdf_m != 0.0 && wo[2] > 0.0;
+}
+double glint_sample(const glint_state_t *g, const double wi[3], double s1, double u1, double u2, double wo[3]) {
+    wo[0] = wo[1] = 0.0; wo[2] = 1.0;
+    if (!(wi[2] > 0.0)) return 0.0;
+    beckmann_t B = glint_beckmann(g);
+    if (g->type == ERTB_BSDF_MAIGNAN) { /* :183-193: C * F, NOT divided by the pdf */
+        cosine_hemisphere_d(u1, u2, wo);
+        if (!(wo[2] / PI > 0.0)) return 0.0;
+        double in_fwd[3] = { -wo[0], -wo[1], -wo[2] }, F[16];
+        fresnel_polarized(g->nr, g->ni, in_fwd, wi, F);
+        return maignan_c(g, wi, wo) * F[0];
+    }
+    if (g->type == ERTB_BSDF_OCEAN_MISHCHENKO) {
+        double m[3];
+        beckmann_sample(&B, wi, u1, u2, m);
+        double dp = dot3d(wi, m);
+        wo[0] = 2.0 * dp * m[0] - wi[0]; wo[1] = 2.0 * dp * m[1] - wi[1]; wo[2] = 2.0 * dp * m[2] - wi[2];
+        if (!mishchenko_valid(&B, wi, wo, m)) return 0.0;
+        double in_fwd[3] = { -wo[0], -wo[1], -wo[2] }, F[16];
+        fresnel_polarized(g->nr, g->ni, in_fwd, wi, F);
+        return F[0] * beckmann_g_hc(&B, wi, wo, m) / beckmann_g1(&B, wi, m);
+    }
+    /* ocean_grasp :285-351 */
+    double p_spec = 1.0 / (g->wbr + 1.0), p_diff = 1.0 - p_spec;
+    int foam = s1 < g->coverage;
+    double s1p = (s1 - g->coverage) / (1.0 - g->coverage);
+    if (foam || s1p < p_diff) {
+        cosine_hemisphere_d(u1, u2, wo);
+    } else {
+        double m[3];
+        beckmann_sample(&B, wi, u1, u2, m);
+        double dp = dot3d(wi, m);
+        wo[0] = 2.0 * dp * m[0] - wi[0]; wo[1] = 2.0 * dp * m[1] - wi[1]; wo[2] = 2.0 * dp * m[2] - wi[2];
+    }
+    double pdf = glint_pdf(g, wi, wo);
+    if (!(pdf > 0.0)) return 0.0;
+    return glint_eval(g, wi, wo) / pdf;
+}
+void glint_polarized(const glint_state_t *g, int weight, const double wi[3], const double wo[3], double *dep, double M[16]) {
+    for (int i = 0; i < 16; ++i) M[i] = 0.0;
+    *dep = 0.0;
+    if (!(wi[2] > 0.0 && wo[2] > 0.0)) return;
+    double in_fwd[3] = { -wo[0], -wo[1], -wo[2] }, F[16], scale, dscale = 1.0;
+    fresnel_polarized(g->nr, g->ni, in_fwd, wi, F);
+    if (g->type == ERTB_BSDF_MAIGNAN) {
+        scale = maignan_c(g, wi, wo); /* eval and sample weight coincide (maignan.cpp:189-193, :207-210) */
+    } else if (g->type == ERTB_BSDF_OCEAN_MISHCHENKO && weight) {
+        beckmann_t B = glint_beckmann(g);
+        double m[3];
+        half_vector(wi, wo, m);
+        if (!mishchenko_valid(&B, wi, wo, m)) return;
+        scale = beckmann_g_hc(&B, wi, wo, m) / beckmann_g1(&B, wi, m);
+    } else {
+        scale = glint_geometry_iso(g, wi, wo);
+        *dep = glint_dep(g, wo);
+        if (weight) { /* ocean_grasp: eval / pdf */
+            double pdf = glint_pdf(g, wi, wo);
+            dscale = pdf > 0.0 ? 1.0 / pdf : 0.0;
+        }
+    }
+    *dep *= dscale;
+    for (int i = 0; i < 16; ++i) M[i] = F[i] * scale * dscale;
 }

@@ -130,6 +130,14 @@ def piecewise_eval(desc, o, d, si_t=None, half_width=0.0):
     return tr, pdf, esc.astype(bool)
 
 
+def bsdf_mueller(desc, wi, wo):
+    wi, wo = _d(wi).reshape(-1, 3), _d(wo).reshape(-1, 3)
+    M = np.zeros((wi.shape[0], 4, 4))
+    _check(load().ertbo_bsdf_mueller(C.byref(desc), C.c_size_t(wi.shape[0]), wi.ctypes.data_as(dp),
+                                     wo.ctypes.data_as(dp), M.ctypes.data_as(dp)))
+    return M
+
+
 def bsdf_eval(desc, wi, wo):
     wi, wo = _d(wi).reshape(-1, 3), _d(wo).reshape(-1, 3)
     out = np.zeros(wi.shape[0])

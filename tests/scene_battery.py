@@ -84,6 +84,18 @@ def battery() -> dict:
                                           "wind_direction": 0.0, "shadowing": False},
                                  sensor={"type": "mdistant", "vza": [-50.0, -35.0, -20.0, 20.0, 50.0],
                                          "vaa": 0.0, "target": [0.0, 3.0e5, 6.3710484e6]}),
+        # SURVEY 8f-4 glint family: ocean_mishchenko (glint only), ocean_grasp (whitecaps + water body + glint),
+        # maignan (polarized land reflectance; eval without cosine, sample weight C F)
+        "ocean_mishchenko_pp": S(geometry="plane_parallel", n_layers=100, sza=35.0, saa=20.0,
+                                 surface={"type": "ocean_mishchenko", "wind_speed": 5.0, "eta": 1.34, "k": 0.0},
+                                 sensor={"type": "mdistant", "vza": [-60.0, -35.0, -25.0, 0.0, 35.0], "vaa": 20.0}),
+        "ocean_grasp_spherical": S(n_layers=100, sza=30.0,
+                                   surface={"type": "ocean_grasp", "wavelength": 550.0, "wind_speed": 12.0,
+                                            "eta": 1.336, "k": 0.0, "water_body_reflectance": 0.02},
+                                   sensor={"type": "mdistant", "vza": [-50.0, -30.0, -15.0, 20.0, 50.0], "vaa": 0.0}),
+        "maignan_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=10.0,
+                        surface={"type": "maignan", "C": 5.0, "ndvi": 0.4, "refr_re": 1.5, "refr_im": 0.0},
+                        sensor={"type": "mdistant", "vza": [-60.0, -40.0, 0.0, 30.0, 60.0], "vaa": 10.0}),
         # polarized (Stokes) transport: rayleigh_polarized / tabphase_polarized + stokes integrator
         "polarized_rayleigh_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=30.0, stokes=True,
                                    phase={"type": "rayleigh_polarized", "depolarization": 0.0279},
@@ -101,6 +113,19 @@ def battery() -> dict:
                                 surface={"type": "ocean_legacy", "wavelength": 550.0, "wind_speed": 5.0,
                                          "wind_direction": 30.0, "shadowing": True},
                                 sensor={"type": "mdistant", "vza": [-60.0, -40.0, -20.0, 20.0, 50.0], "vaa": 25.0}),
+        "polarized_mishchenko_pp": S(geometry="plane_parallel", n_layers=60, sza=40.0, saa=0.0, stokes=True,
+                                     phase={"type": "rayleigh_polarized"},
+                                     surface={"type": "ocean_mishchenko", "wind_speed": 4.0, "eta": 1.33, "k": 0.0,
+                                              "ext_ior": 1.0},
+                                     sensor={"type": "mdistant", "vza": [-60.0, -40.0, -20.0, 20.0, 50.0], "vaa": 25.0}),
+        "polarized_grasp_spherical": S(n_layers=60, sza=35.0, stokes=True, phase={"type": "rayleigh_polarized"},
+                                       surface={"type": "ocean_grasp", "wavelength": 670.0, "wind_speed": 10.0,
+                                                "eta": 1.331, "k": 0.0, "water_body_reflectance": 0.01},
+                                       sensor={"type": "mdistant", "vza": [-55.0, -35.0, -10.0, 30.0, 60.0], "vaa": 15.0}),
+        "polarized_maignan_pp": S(geometry="plane_parallel", n_layers=60, sza=45.0, saa=0.0, stokes=True,
+                                  phase={"type": "rayleigh_polarized", "depolarization": 0.0279},
+                                  surface={"type": "maignan", "C": 6.66, "ndvi": 0.3, "refr_re": 1.5, "refr_im": 0.0},
+                                  sensor={"type": "mdistant", "vza": [-65.0, -45.0, -20.0, 25.0, 55.0], "vaa": 30.0}),
         # BASELINE C5 at reduced size: polarized ocean + molecular + polarized aerosol, one band of the sweep
         "c5_polarized_ocean_aerosol_reduced": scenes.config_c5(spp=16, n_vza=4, w_nm=865.0, n_layers=120),
         # integrator options

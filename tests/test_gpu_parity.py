@@ -48,6 +48,9 @@ def load(surface=None, phase=None, **kw):
     {"type": "hapke", **POMMEROL},
     {"type": "ocean_legacy", "wavelength": 550.0, "wind_speed": 8.0, "wind_direction": 40.0, "shadowing": True},
     {"type": "ocean_legacy", "wavelength": 1500.0, "wind_speed": 1.0, "wind_direction": 90.0, "shadowing": False},
+    {"type": "ocean_mishchenko", "wind_speed": 6.0, "eta": 1.34, "k": 0.0},
+    {"type": "ocean_grasp", "wavelength": 865.0, "wind_speed": 12.0, "eta": 1.33, "water_body_reflectance": 0.03},
+    {"type": "maignan", "C": 5.0, "ndvi": 0.4, "refr_re": 1.5, "refr_im": 0.0},
 ])
 def test_bsdf_eval_and_sample_match_oracle(oracle, bsdf):
     sc = load(surface=bsdf)
@@ -58,7 +61,17 @@ def test_bsdf_eval_and_sample_match_oracle(oracle, bsdf):
     wo = sph_to_dir(rng.uniform(0.0, 1.45, n), rng.uniform(0, 2 * np.pi, n)).astype(np.float32)
     got = kat.bsdf_eval(sc, wi, wo)
     ref = oracle.bsdf_eval(desc, wi, wo)
-    ocean = bsdf["type"] == "ocean_legacy"
+    ocean = bsdf["type"] in ("ocean_legacy", "ocean_mishchenko", "ocean_grasp")
+    if bsdf["type"] == "maignan":
+        # maignan.cpp:168-224: cosine-hemisphere directions; the weight is eval() at the sampled direction
+        assert np.allclose(got, ref, rtol=5e-4, atol=1e-7), np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6))
+        u = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+        wo_g, w_g = kat.bsdf_sample(sc, wi, u)
+        wo_o, w_o = oracle.bsdf_sample(desc, wi, u)
+        assert np.allclose(wo_g[:, :2], wo_o[:, :2], atol=1e-5) and np.allclose(wo_g[:, 2], wo_o[:, 2], atol=5e-4)
+        ok = wo_o[:, 2] > 0.02
+        assert np.allclose(w_g[ok], w_o[ok], rtol=2e-3, atol=1e-7)
+        return
     # fp32 with fast intrinsics (__powf, __fdividef) vs fp64: 2e-4 relative (ocean: the glint lobe
     # exp(-tan^2/alpha^2) amplifies fp32 rounding of the half-vector at low wind speed -> 2e-3)
     assert np.allclose(got, ref, rtol=2e-3 if ocean else 2e-4, atol=1e-6 if ocean else 1e-7), \
@@ -97,6 +110,55 @@ def test_ocean_6sv_golden_on_device():
         sc = load(surface={**base, **override})
         val = kat.bsdf_eval(sc, wi, wo) * np.pi
         assert np.allclose(val, golden, rtol=1e-3, atol=1e-4), val
+
+
+def test_mishchenko_and_maignan_golden_mueller_on_device(oracle):
+    """ERP/tests/bsdfs/test_ocean_mishchenko.py:44-109 and test_maignan.py:28-88 evaluated by the CUDA
+    implementation (polarized BSDF::eval in the local implicit Stokes bases), plus agreement with the
+    oracle's two-rotation formulation over random geometries for the three glint-family plugins."""
+    def dirs(theta, phi):
+        return sph_to_dir([np.deg2rad(theta)], [np.deg2rad(phi)])
+
+    mish = dict(type="ocean_mishchenko", wind_speed=2.0, eta=1.33, k=0.0, ext_ior=1.0)
+    sc = load(surface=mish, stokes=True)
+    M = kat.bsdf_mueller(sc, dirs(15.0, 0.0), dirs(15.0, 180.0))[0]
+    gold = np.diag([0.125155, 0.125155, -0.124450, -0.124450])
+    gold[0, 1] = gold[1, 0] = -0.0132689
+    assert np.allclose(M, gold, rtol=1e-3, atol=1e-4), M
+    sc = load(surface={**mish, "wind_speed": 10.0, "eta": 1.39}, stokes=True)
+    M = kat.bsdf_mueller(sc, dirs(60.0, 0.0), dirs(40.0, 180.0))[0]
+    gold = np.diag([0.733924e-01, 0.733924e-01, -0.172412e-01, -0.172412e-01])
+    gold[0, 1] = gold[1, 0] = -0.713385e-01
+    assert np.allclose(M, gold, rtol=1e-3, atol=1e-4), M
+    sc = load(surface=dict(type="maignan", C=4.98, ndvi=0.8, refr_re=1.5, refr_im=0.0, ext_ior=1.0), stokes=True)
+    M = kat.bsdf_mueller(sc, dirs(40.0, 0.0), dirs(40.0, 5.0))[0]
+    gold = [[1.42013086e-02, 1.48094732e-05, -1.60061711e-06, 0.0], [1.48624285e-05, 1.41894910e-02, -5.79237472e-04, 0.0],
+            [9.95336109e-07, -5.79236308e-04, -1.41894845e-02, 0.0], [0.0, 0.0, 0.0, -1.42013021e-02]]
+    assert np.allclose(M, gold, rtol=1e-3, atol=1e-6), M
+    rng = np.random.default_rng(4)
+    n = 2048
+    wi = sph_to_dir(rng.uniform(0.05, 1.3, n), rng.uniform(0, 2 * np.pi, n)).astype(np.float32)
+    for surface in (
+        {**mish, "wind_speed": 8.0},
+        dict(type="ocean_grasp", wavelength=670.0, wind_speed=10.0, eta=1.331, water_body_reflectance=0.02),
+        dict(type="maignan", C=6.66, ndvi=0.3),
+    ):
+        sc = load(surface=surface, stokes=True)
+        desc = sc.flat.build_desc()
+        if surface["type"] == "maignan":
+            wo = sph_to_dir(rng.uniform(0.05, 1.3, n), rng.uniform(0, 2 * np.pi, n)).astype(np.float32)
+        else:  # stay inside the glint lobe, where the matrix is not negligible
+            mirror = wi * np.array([-1.0, -1.0, 1.0], dtype=np.float32)
+            wo = mirror + rng.normal(0, 0.08, (n, 3)).astype(np.float32)
+            wo /= np.linalg.norm(wo, axis=1, keepdims=True)
+            wo = wo.astype(np.float32)
+        got = kat.bsdf_mueller(sc, wi, wo)
+        ref = oracle.bsdf_mueller(desc, wi, wo)
+        scale = np.abs(ref[:, 0, 0])[:, None, None]
+        ok = (wo[:, 2] > 0.05) & (ref[:, 0, 0] > 1e-4 * ref[:, 0, 0].max())
+        assert ok.sum() > n // 4
+        err = np.abs(got - ref)[ok] / scale[ok]
+        assert err.max() < 5e-3, (surface["type"], err.max())
 
 
 def test_hapke_golden_on_device():

@@ -104,6 +104,32 @@ def test_unsupported_plugins_raise_runtime_error(mutate, match):
         mi_load_dict(d)
 
 
+def test_glint_family_bsdfs_load_with_reference_defaults_and_keys():
+    """ocean_mishchenko.cpp:95-123, ocean_grasp.cpp:120-153, maignan.cpp:92-111: constructor defaults, the
+    parameters traverse() publishes (scalars by name, textures as `<name>.value`), and what they flatten to."""
+    def bsdf_of(surface):
+        d = scenes.atmosphere_scene(surface=surface, geometry="plane_parallel", n_layers=4)
+        sc = mi_load_dict(d)
+        keys = {k.split(".bsdf.")[-1] for k in mi_traverse(sc).parameters.keys() if ".bsdf." in k}
+        desc = sc.flat.build_desc()
+        return desc.bsdf_type, np.array(desc.bsdf_params[:8]), keys
+
+    ty, p, keys = bsdf_of({"type": "ocean_mishchenko"})
+    assert ty == _abi.BSDF_OCEAN_MISHCHENKO and np.allclose(p[:4], [0.1, 1.33, 0.0, 1.000277])
+    assert keys == {"wind_speed", "eta.value", "k.value", "ext_ior.value"}
+    ty, p, keys = bsdf_of({"type": "ocean_grasp", "wavelength": 865.0})
+    assert ty == _abi.BSDF_OCEAN_GRASP and np.allclose(p[:7], [865.0, 0.1, 1.33, 0.0, 1.000277, 0.0, 0.0])
+    assert keys == {"wavelength", "wind_speed.value", "eta.value", "k.value", "ext_ior.value",
+                    "water_body_reflectance.value"}
+    ty, p, keys = bsdf_of({"type": "maignan"})
+    assert ty == _abi.BSDF_MAIGNAN and np.allclose(p[:5], [0.1, 0.0, 1.5, 0.0, 1.000277])
+    assert keys == {"C.value", "ndvi.value", "refr_re.value", "refr_im.value", "ext_ior.value"}
+    with pytest.raises(RuntimeError, match="wavelength"):
+        bsdf_of({"type": "ocean_grasp"})
+    with pytest.raises(RuntimeError, match="component"):
+        bsdf_of({"type": "ocean_grasp", "wavelength": 550.0, "component": 2})
+
+
 def test_piecewise_volpath_needs_a_piecewise_medium():
     # only ERP/media/piecewise.cpp overrides the *_real interface (medium.cpp:99-118); the scene is
     # flattened at load time here, so the reference's render-time error surfaces from mi_load_dict

@@ -452,3 +452,179 @@ def test_ocean_legacy_sample_pdf_consistency(oracle):
     d = oracle.warp("uniform_hemisphere", u[:, 0], u[:, 1])
     ref = (oracle.bsdf_eval(desc, np.repeat(wi, n, axis=0), d) * 2 * np.pi)
     assert abs(est - ref.mean()) < 5 * np.sqrt(w.var() / n + ref.var() / n), (est, ref.mean())
+
+
+# --------------------------------------------------------- ocean_mishchenko / ocean_grasp / maignan
+MISHCHENKO = dict(type="ocean_mishchenko", wind_speed=2.0, eta=1.33, k=0.0, ext_ior=1.0)
+MAIGNAN = dict(type="maignan", C=5.0, ndvi=0.8, refr_re=1.5, refr_im=0.0, ext_ior=1.0)
+
+
+def _deg_dir(theta, phi):
+    return sph_to_dir([np.deg2rad(theta)], [np.deg2rad(phi)])
+
+
+@pytest.mark.parametrize("override,vza,sza,saa,golden,rtol,atol", [
+    # ERP/tests/bsdfs/test_ocean_mishchenko.py:44-109: Mishchenko's reference code, 550 nm / 2 m/s ...
+    ({}, 15.0, 15.0, 180.0,
+     [[0.125155, -0.0132689, 0.0, 0.0], [-0.0132689, 0.125155, 0.0, 0.0],
+      [0.0, 0.0, -0.124450, 0.0], [0.0, 0.0, 0.0, -0.124450]], 1e-4, 1e-5),
+    # ... and 900 nm / 10 m/s / eta 1.39 after a parameter update
+    ({"wind_speed": 10.0, "eta": 1.39}, 60.0, 40.0, 180.0,
+     [[0.733924e-01, -0.713385e-01, 0.0, 0.0], [-0.713385e-01, 0.733924e-01, 0.0, 0.0],
+      [0.0, 0.0, -0.172412e-01, 0.0], [0.0, 0.0, 0.0, -0.172412e-01]], 1e-3, 1e-4),
+])
+def test_ocean_mishchenko_golden_mueller(oracle, override, vza, sza, saa, golden, rtol, atol):
+    _, desc = make_desc(surface={**MISHCHENKO, **override}, stokes=True)
+    M = oracle.bsdf_mueller(desc, _deg_dir(vza, 0.0), _deg_dir(sza, saa))[0]
+    assert np.allclose(M, golden, rtol=rtol, atol=atol), M
+    # unpolarized variants return the (0, 0) entry (ocean_mishchenko.cpp:289-293)
+    _, d0 = make_desc(surface={**MISHCHENKO, **override})
+    assert np.isclose(oracle.bsdf_eval(d0, _deg_dir(vza, 0.0), _deg_dir(sza, saa))[0], M[0, 0], rtol=1e-12)
+
+
+def test_ocean_mishchenko_update_equals_fresh_scene(oracle):
+    # test_ocean_mishchenko.py:91-96: params["wind_speed"], params["eta.value"] then update()
+    from eradiate_b200.kernel import mi_traverse
+    sc, _ = make_desc(surface=MISHCHENKO, stokes=True)
+    w = mi_traverse(sc)
+    keys = {k.split("bsdf.")[-1]: k for k in w.parameters.keys() if ".bsdf." in k}
+    assert set(keys) == {"wind_speed", "eta.value", "k.value", "ext_ior.value"}  # ocean_mishchenko.cpp:118-123
+    w.parameters.update({keys["wind_speed"]: 10.0, keys["eta.value"]: 1.39})
+    M = oracle.bsdf_mueller(sc.flat.build_desc(), _deg_dir(60.0, 0.0), _deg_dir(40.0, 180.0))[0]
+    _, fresh = make_desc(surface={**MISHCHENKO, "wind_speed": 10.0, "eta": 1.39}, stokes=True)
+    assert np.array_equal(M, oracle.bsdf_mueller(fresh, _deg_dir(60.0, 0.0), _deg_dir(40.0, 180.0))[0])
+
+
+def _fresnel_unpolarized(n, cos_i):
+    sin_t2 = (1.0 - cos_i**2) / n**2
+    cos_t = np.sqrt(1.0 - sin_t2)
+    rs = (cos_i - n * cos_t) / (cos_i + n * cos_t)
+    rp = (n * cos_i - cos_t) / (n * cos_i + cos_t)
+    return 0.5 * (rs**2 + rp**2)
+
+
+def test_ocean_mishchenko_m00_vs_microfacet_model(oracle):
+    """(0, 0) entry = D G F / (4 cos_i) written from the published formulas: Beckmann facets with
+    alpha^2 = Cox-Munk mean square slope 0.003 + 0.00512 U, Walter et al. 2007 rational Smith Lambda,
+    unpolarized Fresnel reflectance at the facet."""
+    ws, eta = 7.0, 1.34
+    _, desc = make_desc(surface={**MISHCHENKO, "wind_speed": ws, "eta": eta})
+    rng = np.random.default_rng(5)
+    n = 2000
+    wi = sph_to_dir(rng.uniform(0.05, 1.2, n), rng.uniform(0, 2 * np.pi, n))
+    wo = sph_to_dir(rng.uniform(0.05, 1.2, n), rng.uniform(0, 2 * np.pi, n))
+    alpha = np.sqrt(0.003 + 0.00512 * ws)
+    m = wi + wo
+    m /= np.linalg.norm(m, axis=1, keepdims=True)
+    ct = m[:, 2]
+    D = np.exp(-(1.0 - ct**2) / ct**2 / alpha**2) / (np.pi * alpha**2 * ct**4)
+
+    def lam(v):
+        a = 1.0 / (alpha * np.sqrt(1.0 - v[:, 2] ** 2) / v[:, 2])
+        return np.where(a >= 1.6, 0.0, (1.0 - 1.259 * a + 0.396 * a * a) / (3.535 * a + 2.181 * a * a))
+
+    G = 1.0 / (1.0 + lam(wi) + lam(wo))
+    F = _fresnel_unpolarized(eta, np.sum(wi * m, axis=1))
+    ref = D * G * F / (4.0 * wi[:, 2])
+    got = oracle.bsdf_eval(desc, wi, wo)
+    ok = D * ct > 1e-20
+    assert np.allclose(got[ok], ref[ok], rtol=1e-6, atol=1e-12), np.max(np.abs(got[ok] / ref[ok] - 1))
+
+
+@pytest.mark.parametrize("surface", [
+    {**MISHCHENKO, "wind_speed": 6.0},
+    {"type": "ocean_grasp", "wavelength": 550.0, "wind_speed": 12.0, "eta": 1.336, "water_body_reflectance": 0.05},
+])
+def test_glint_sample_pdf_consistency(oracle, surface):
+    """chi^2-style check (test_ocean_mishchenko.py:15-31, test_ocean_grasp.py:15-31): E[weight] over
+    sample() equals the hemispherical integral of eval()."""
+    _, desc = make_desc(surface=surface)
+    rng = np.random.default_rng(21)
+    wi = sph_to_dir([np.deg2rad(40.0)], [0.7])
+    n = 200000
+    wo, w = oracle.bsdf_sample(desc, np.repeat(wi, n, axis=0), rng.uniform(0, 1, (n, 3)))
+    assert np.all(np.isfinite(w)) and np.all(w >= 0)
+    # the glint lobe is narrow: integrate eval() by importance sampling a cone around the mirror direction
+    mirror = np.array([-wi[0, 0], -wi[0, 1], wi[0, 2]])
+    cos_max = np.cos(np.deg2rad(60.0))
+    u = rng.uniform(0, 1, (n, 2))
+    ct = 1.0 - u[:, 0] * (1.0 - cos_max)
+    st, ph = np.sqrt(1.0 - ct**2), 2 * np.pi * u[:, 1]
+    a = np.cross(mirror, [0.0, 0.0, 1.0]); a /= np.linalg.norm(a)
+    b = np.cross(mirror, a)
+    d = ct[:, None] * mirror + st[:, None] * (np.cos(ph)[:, None] * a + np.sin(ph)[:, None] * b)
+    cone = oracle.bsdf_eval(desc, np.repeat(wi, n, axis=0), d) * 2 * np.pi * (1.0 - cos_max)
+    # outside the cone only the diffuse part of ocean_grasp remains
+    d2 = oracle.warp("uniform_hemisphere", u[:, 0], u[:, 1])
+    out = np.where(d2 @ mirror < cos_max, oracle.bsdf_eval(desc, np.repeat(wi, n, axis=0), d2) * 2 * np.pi, 0.0)
+    ref, var = cone.mean() + out.mean(), cone.var() / n + out.var() / n
+    assert abs(w.mean() - ref) < 5 * np.sqrt(w.var() / n + var), (w.mean(), ref)
+
+
+def test_ocean_grasp_components(oracle):
+    """ocean_grasp.cpp:354-455 term by term: Frouin whitecaps x Monahan coverage (oceanprops.h:330-363) and
+    the Lambertian water body outside the glint; the glint is Mishchenko's with the exact Smith Lambda
+    (erf form, :246-255) instead of the rational fit: same value within the fit's accuracy."""
+    wl, ws, wbr = 865.0, 15.0, 0.03
+    g = {"type": "ocean_grasp", "wavelength": wl, "wind_speed": ws, "eta": 1.33, "k": 0.0, "ext_ior": 1.0,
+         "water_body_reflectance": wbr}
+    _, desc = make_desc(surface=g)
+    cov = 2.95e-6 * ws**3.52
+    wc = cov * 0.22 * np.exp(-1.75 * (wl * 1e-3 - 0.6) ** 0.99)
+    # far from the specular direction (backscattering side) only the diffuse terms remain
+    wi, wo = _deg_dir(50.0, 0.0), _deg_dir(50.0, 10.0)
+    val = oracle.bsdf_eval(desc, wi, wo)[0]
+    assert np.isclose(val, (wc + (1.0 - cov) * wbr) * wo[0, 2] / np.pi, rtol=1e-9)
+    # in the glint: subtract the diffuse part, compare with ocean_mishchenko
+    _, dm = make_desc(surface={**MISHCHENKO, "wind_speed": ws})
+    rng = np.random.default_rng(3)
+    n = 500
+    wi = sph_to_dir(rng.uniform(0.1, 1.0, n), np.zeros(n))
+    wo = sph_to_dir(np.arccos(wi[:, 2]) + rng.normal(0, 0.08, n), np.full(n, np.pi) + rng.normal(0, 0.08, n))
+    glint = oracle.bsdf_eval(desc, wi, wo) - (wc + (1.0 - cov) * wbr) * wo[:, 2] / np.pi
+    ref = (1.0 - cov) * oracle.bsdf_eval(dm, wi, wo)
+    ok = ref > 1e-3
+    assert ok.sum() > 300 and np.allclose(glint[ok], ref[ok], rtol=2e-2)
+
+
+@pytest.mark.parametrize("override,wi_deg,wo_deg,golden", [
+    # ERP/tests/bsdfs/test_maignan.py:28-58 (evergreen needleleaf, 550 nm) and :60-88 (savanna, 900 nm);
+    # the reference values are float32 outputs: compared to 2e-7 absolute
+    ({"C": 4.98, "ndvi": 0.8}, (40.0, 0.0), (40.0, 5.0),
+     [[1.42013086e-02, 1.48094732e-05, -1.60061711e-06, 0.0],
+      [1.48624285e-05, 1.41894910e-02, -5.79237472e-04, 0.0],
+      [9.95336109e-07, -5.79236308e-04, -1.41894845e-02, 0.0],
+      [0.0, 0.0, 0.0, -1.42013021e-02]]),
+    ({"C": 6.66, "ndvi": 0.3}, (0.0, 0.0), (40.0, 170.0),
+     [[1.9543538e-02, -3.1128337e-03, -1.1320484e-03, 0.0],
+      [3.1127632e-03, -1.9510504e-02, -8.9618654e-05, 0.0],
+      [-1.1322410e-03, 9.2017806e-05, 1.9293837e-02, 0.0],
+      [0.0, 0.0, 0.0, -1.9260805e-02]]),
+])
+def test_maignan_golden_mueller(oracle, override, wi_deg, wo_deg, golden):
+    _, desc = make_desc(surface={**MAIGNAN, **override}, stokes=True)
+    M = oracle.bsdf_mueller(desc, _deg_dir(*wi_deg), _deg_dir(*wo_deg))[0]
+    # (wi along the normal runs into the clamp mu <= 0.9999999 of oceanprops.h:476-477, which rounds differently in float32)
+    assert np.allclose(M, golden, rtol=2e-5, atol=6e-7), M
+
+
+def test_maignan_sample_conventions(oracle):
+    """maignan.cpp:168-224 as written: cosine-hemisphere sampling, pdf = cos / pi, eval() without the
+    foreshortening factor, and a sample weight equal to eval() at the sampled direction (not eval / pdf)."""
+    _, desc = make_desc(surface={**MAIGNAN, "ext_ior": 1.000277})
+    rng = np.random.default_rng(8)
+    n = 1000
+    wi = sph_to_dir(rng.uniform(0.0, 1.4, n), rng.uniform(0, 2 * np.pi, n))
+    u = rng.uniform(0, 1, (n, 3))
+    wo, w = oracle.bsdf_sample(desc, wi, u)
+    c = oracle.warp("cosine_hemisphere", u[:, 1], u[:, 2])
+    assert np.allclose(wo, c, atol=1e-14)
+    assert np.allclose(w, oracle.bsdf_eval(desc, wi, wo), rtol=1e-12)
+    # Eq. 21 of Maignan et al. 2009 at one geometry, from the formula
+    ti, to, dphi = np.deg2rad(30.0), np.deg2rad(50.0), np.deg2rad(140.0)
+    cT = np.cos(ti) * np.cos(to) + np.sin(ti) * np.sin(to) * np.cos(dphi)
+    tan_a = np.tan(0.5 * np.arccos(cT))  # alpha = half the angle between the two directions
+    F = _fresnel_unpolarized(1.5 / 1.000277, np.cos(0.5 * np.arccos(cT)))
+    ref = 5.0 * np.exp(-tan_a) * np.exp(-0.8) * F / (4.0 * (np.cos(ti) + np.cos(to)))
+    got = oracle.bsdf_eval(desc, sph_to_dir([ti], [0.3]), sph_to_dir([to], [0.3 + dphi]))[0]
+    assert np.isclose(got, ref, rtol=1e-6), (got, ref)
