@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -29,6 +29,7 @@ BSDF_BLACK = 5
 BSDF_OCEAN_MISHCHENKO = 6
 BSDF_OCEAN_GRASP = 7
 BSDF_MAIGNAN = 8
+BSDF_MQDIFFUSE = 9
 
 # enum ertb_phase_type
 PHASE_ISOTROPIC = 0
@@ -166,6 +167,9 @@ class SceneDesc(C.Structure):
         ("patch_bsdf_type", C.c_int32),
         ("patch_bsdf_params", C.c_float * MAX_BSDF_PARAMS),
         ("patch_rect", C.c_double * 4),
+        ("bsdf_table", c_float_p),
+        ("bsdf_table_res", C.c_int32 * 3),
+        ("_pad5", C.c_int32),
     ]
 
 

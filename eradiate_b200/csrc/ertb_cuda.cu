@@ -277,6 +277,8 @@ struct ertb_scene {
     std::map<std::pair<const void *, size_t>, int> occupancy; // per kernel instantiation and smem size
     int max_smem_optin = 0;
     double *d_gl = nullptr;     // Gauss-Legendre nodes/weights of the ocean transmittance quadrature
+    float *d_bsdf_table = nullptr; // mqdiffuse: the measured table, [z][y][x] (static)
+    int bsdf_table_res[3] = { 0, 0, 0 };
     // canopy (plane-parallel scenes): host description and the device BVH
     std::vector<HostLeafGroup> leaf_groups;
     std::vector<int> instance_group;
@@ -707,6 +709,9 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
             T.ocean_key[0] = n_real; T.ocean_key[1] = n_imag; T.ocean_key[2] = ws;
         }
         P.ocean_tables = T.d_ocean;
+    } else if (S->bsdf_type == ERTB_BSDF_MQDIFFUSE) {
+        for (int i = 0; i < 3; ++i) P.bsdf[i] = (float) S->bsdf_table_res[i];
+        P.ocean_tables = S->d_bsdf_table;
     } else if (S->bsdf_type >= ERTB_BSDF_OCEAN_MISHCHENKO) {
         ertb_ocean_host::derive_glint(S->bsdf_type, S->bsdf_params, P.bsdf);
     }
@@ -895,6 +900,7 @@ void ertb_scene_destroy(ertb_scene *S) {
     if (S->batch.d_accum) cudaFree(S->batch.d_accum);
     if (S->batch.d_counters) cudaFree(S->batch.d_counters);
     if (S->d_gl) cudaFree(S->d_gl);
+    if (S->d_bsdf_table) cudaFree(S->d_bsdf_table);
     for (void *q : S->d_canopy)
         if (q) cudaFree(q);
     if (S->d_counter) cudaFree(S->d_counter);
@@ -913,7 +919,12 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
     if (device < 0 || device >= ndev) return set_error("invalid CUDA device index");
     if (D->geometry != ERTB_GEOM_PLANE_PARALLEL && D->geometry != ERTB_GEOM_SPHERICAL_SHELL)
         return set_error("unsupported geometry");
-    if (D->bsdf_type < 0 || D->bsdf_type > ERTB_BSDF_MAIGNAN) return set_error("unsupported BSDF type");
+    if (D->bsdf_type < 0 || D->bsdf_type > ERTB_BSDF_MQDIFFUSE) return set_error("unsupported BSDF type");
+    if (D->bsdf_type == ERTB_BSDF_MQDIFFUSE) {
+        if (!D->bsdf_table) return set_error("mqdiffuse: missing table");
+        for (int i = 0; i < 3; ++i)
+            if (D->bsdf_table_res[i] < 1 || D->bsdf_table_res[i] > 4096) return set_error("mqdiffuse: invalid table resolution");
+    }
     if (D->bsdf_type == ERTB_BSDF_OCEAN_GRASP && D->bsdf_params[6] != 0.f)
         return set_error("ocean_grasp: only component=0 (full BRDF) is supported");
     if (D->bsdf_type == ERTB_BSDF_OCEAN_LEGACY && D->bsdf_params[6] != 0.f)
@@ -1061,6 +1072,15 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
         cudaEventCreate(&S->ev0) != cudaSuccess || cudaEventCreate(&S->ev1) != cudaSuccess) {
         ertb_scene_destroy(S);
         return set_error("device allocation failed");
+    }
+    if (D->bsdf_type == ERTB_BSDF_MQDIFFUSE) { // the measured table lives in global memory (L2-resident)
+        size_t n = 1;
+        for (int i = 0; i < 3; ++i) { S->bsdf_table_res[i] = D->bsdf_table_res[i]; n *= (size_t) D->bsdf_table_res[i]; }
+        if (cudaMalloc(&S->d_bsdf_table, n * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(S->d_bsdf_table, D->bsdf_table, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            ertb_scene_destroy(S);
+            return set_error("mqdiffuse: table upload failed");
+        }
     }
     for (int i = 0; i < D->n_sensors; ++i) {
         HostSensor hs;
@@ -1568,11 +1588,12 @@ __global__ void kat_bsdf_mueller_kernel(ErtbParams P, size_t n, const float *wi,
     f3 a = mk3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), b = mk3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
     float m[16];
     // shading frame = the axes: the world implicit bases are then the local ones BSDF::eval refers to
-    if (bsdf_is_local(P.bsdf_type)) {
+    if (bsdf_is_mueller(P.bsdf_type)) {
         lf_eval_mueller(P, false, a, b, mk3(1.f, 0.f, 0.f), mk3(0.f, 1.f, 0.f), mk3(0.f, 0.f, 1.f), m);
     } else {
         for (int k = 0; k < 16; ++k) m[k] = 0.f;
-        if (a.z > 0.f && b.z > 0.f) m[0] = bsdf_f(P, a.z, b.z, cos_dphi(a.z, b.z, dot3(a, b))) * b.z;
+        if (bsdf_is_local(P.bsdf_type)) m[0] = lf_eval(P, a, b);
+        else if (a.z > 0.f && b.z > 0.f) m[0] = bsdf_f(P, a.z, b.z, cos_dphi(a.z, b.z, dot3(a, b))) * b.z;
     }
     for (int k = 0; k < 16; ++k) M[16 * i + k] = m[k];
 }

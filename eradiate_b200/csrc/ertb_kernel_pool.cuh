@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                     thr = 0.f; dead = true;
                 } else {
                     float f_sun, weight;
-                    if (POL && bsdf_is_local(P.bsdf_type)) {
+                    if (POL && bsdf_is_mueller(P.bsdf_type)) {
                         // Mueller-valued BSDF (polarized Fresnel matrix): ocean_legacy.cpp:561-661,
                         // ocean_mishchenko.cpp:228-296, ocean_grasp.cpp:354-455, maignan.cpp:105-166
                         f3 fs, ft;

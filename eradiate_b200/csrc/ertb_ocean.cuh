@@ -497,7 +497,11 @@ __device__ __forceinline__ void oc_fresnel_mueller(float nr, float ni, f3 wi_in,
 // ------------------------------------------------------------------------------------------------
 #define MG_CEXP 15 /* first slot the 6SV ocean leaves free */
 
-__device__ __forceinline__ bool bsdf_is_glint_family(int t) { return t >= ERTB_BSDF_OCEAN_MISHCHENKO; }
+// BSDFs whose value is a Mueller matrix in polarized scenes (Fresnel reflection on facets)
+__device__ __forceinline__ bool bsdf_is_mueller(int t) {
+    return t == ERTB_BSDF_OCEAN_LEGACY || (t >= ERTB_BSDF_OCEAN_MISHCHENKO && t <= ERTB_BSDF_MAIGNAN);
+}
+// BSDFs evaluated on local-frame vectors (everything that is not a function of (cos_i, cos_o, cos dphi) only)
 __device__ __forceinline__ bool bsdf_is_local(int t) { return t == ERTB_BSDF_OCEAN_LEGACY || t >= ERTB_BSDF_OCEAN_MISHCHENKO; }
 
 __device__ __forceinline__ float gl_grasp_lambda(float vz, float sigma) { // ocean_grasp.cpp:246-255
@@ -593,10 +597,57 @@ __device__ __forceinline__ float gl_sample(const ErtbParams &P, f3 wi, float s1,
     return gl_dep(P, wo) * dscale + g * gl_fresnel00(P, wi, wo);
 }
 
-// dispatch over the local-frame BSDFs (6SV ocean + glint family)
+// ------------------------------------------------------------------------------------------------
+// mqdiffuse (ERP/bsdfs/mqdiffuse.cpp:94-176): trilinear lookup of the measured table at
+// (cos_theta_o, phi_d / 2 pi, cos_theta_i), remapped so that the first / last texel sit on 0 / 1
+// (:96-100), clamp wrap mode (drjit/texture.h linear filter: both neighbours clamped to the grid).
+// P.bsdf[0..2] = resolution (x, y, z), P.ocean_tables = data[z][y][x].
+// eval() wraps a negative azimuth difference by 2 pi (:153); sample() does not (:125-131), so a sampled
+// direction with atan2(wo) < atan2(wi) reads the phi_d = 0 plane through the clamp -- kept as is.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mq_tex(const ErtbParams &P, float cos_o, float phi_d, float cos_i) {
+    const int rx = (int) P.bsdf[0], ry = (int) P.bsdf[1], rz = (int) P.bsdf[2];
+    float px = cos_o * (float) (rx - 1), py = phi_d * (0.5f * ERTB_INV_PI) * (float) (ry - 1), pz = cos_i * (float) (rz - 1);
+    float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    float wx = px - fx, wy = py - fy, wz = pz - fz;
+    int x0 = min(max((int) fx, 0), rx - 1), x1 = min(max((int) fx + 1, 0), rx - 1);
+    int y0 = min(max((int) fy, 0), ry - 1), y1 = min(max((int) fy + 1, 0), ry - 1);
+    int z0 = min(max((int) fz, 0), rz - 1), z1 = min(max((int) fz + 1, 0), rz - 1);
+    const float *d = P.ocean_tables;
+#define MQ_AT(z, y, x) __ldg(d + ((size_t) (z) * ry + (y)) * rx + (x))
+    float c00 = fmaf(wx, MQ_AT(z0, y0, x1) - MQ_AT(z0, y0, x0), MQ_AT(z0, y0, x0));
+    float c01 = fmaf(wx, MQ_AT(z0, y1, x1) - MQ_AT(z0, y1, x0), MQ_AT(z0, y1, x0));
+    float c10 = fmaf(wx, MQ_AT(z1, y0, x1) - MQ_AT(z1, y0, x0), MQ_AT(z1, y0, x0));
+    float c11 = fmaf(wx, MQ_AT(z1, y1, x1) - MQ_AT(z1, y1, x0), MQ_AT(z1, y1, x0));
+#undef MQ_AT
+    float c0 = fmaf(wy, c01 - c00, c00), c1 = fmaf(wy, c11 - c10, c10);
+    return fmaf(wz, c1 - c0, c0);
+}
+__device__ __forceinline__ float mq_phi_d(f3 wi, f3 wo) { // fmod(atan2(wo) - atan2(wi), 2 pi): sign of the dividend
+    return fmodf(atan2f(wo.y, wo.x) - atan2f(wi.y, wi.x), 2.f * ERTB_PI);
+}
+__device__ __forceinline__ float mq_eval(const ErtbParams &P, f3 wi, f3 wo) {
+    if (!(wi.z > 0.f && wo.z > 0.f)) return 0.f;
+    float phi_d = mq_phi_d(wi, wo);
+    if (phi_d < 0.f) phi_d += 2.f * ERTB_PI;
+    return mq_tex(P, wo.z, phi_d, wi.z) * wo.z;
+}
+__device__ __forceinline__ float mq_sample(const ErtbParams &P, f3 wi, float u1, float u2, f3 &wo) {
+    wo = mk3(0.f, 0.f, 1.f);
+    if (!(wi.z > 0.f)) return 0.f;
+    wo = cosine_hemisphere(u1, u2);
+    if (!(wo.z > 0.f)) return 0.f;
+    return mq_tex(P, wo.z, mq_phi_d(wi, wo), wi.z) * ERTB_PI; // value * cos / pdf
+}
+
+// dispatch over the local-frame BSDFs (6SV ocean, glint family, mqdiffuse)
 __device__ __forceinline__ float lf_eval(const ErtbParams &P, f3 wi, f3 wo) {
-    return P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY ? oc_eval(P, wi, wo) : gl_eval(P, wi, wo);
+    if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) return oc_eval(P, wi, wo);
+    if (P.bsdf_type == ERTB_BSDF_MQDIFFUSE) return mq_eval(P, wi, wo);
+    return gl_eval(P, wi, wo);
 }
 __device__ __forceinline__ float lf_sample(const ErtbParams &P, f3 wi, float s1, float u1, float u2, f3 &wo) {
-    return P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY ? oc_sample(P, wi, s1, u1, u2, wo) : gl_sample(P, wi, s1, u1, u2, wo);
+    if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) return oc_sample(P, wi, s1, u1, u2, wo);
+    if (P.bsdf_type == ERTB_BSDF_MQDIFFUSE) return mq_sample(P, wi, u1, u2, wo);
+    return gl_sample(P, wi, s1, u1, u2, wo);
 }

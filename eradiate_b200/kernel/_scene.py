@@ -229,7 +229,7 @@ _SUPPORTED = {
     "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance", "cylinder"},
     "medium": {"heterogeneous", "homogeneous", "piecewise"},
     "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "ocean_mishchenko", "ocean_grasp", "maignan",
-             "null", "bilambertian", "blendbsdf"},
+             "mqdiffuse", "null", "bilambertian", "blendbsdf"},
     "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
               "rayleigh_polarized", "tabphase_polarized"},
     "sensor": {"mdistant", "hdistant", "distantflux", "perspective", "mpdistant", "mradiancemeter"},
@@ -242,8 +242,7 @@ _KNOWN_UNSUPPORTED = {
     "obj": "mesh canopy elements are not implemented",
     # the reference's remaining plugins for this slot
     "astroobject": "finite-size solar discs need emitter-hit MIS, which the kernels do not carry (use 'directional')",
-    "mqdiffuse": "tabulated measured BSDFs are not implemented",
-    "measured_mono": "tabulated measured BSDFs are not implemented",
+    "measured_mono": "only the quasi-diffuse measured BSDF ('mqdiffuse') is implemented",
     "selectbsdf": "this BSDF adapter is not implemented",
     "multiphase": "use nested 'blendphase' nodes (flattened to <= 4 leaves)",
 }
@@ -468,6 +467,15 @@ class _Loader:
             b.component = int(d.get("component", 0))
             if b.component != 0:
                 raise RuntimeError("ocean_grasp: only component=0 (full BRDF) is supported")
+        elif ty == "mqdiffuse":  # mqdiffuse.cpp:60-92
+            if "grid" in d and "filename" in d:
+                raise RuntimeError('Cannot specify both "grid" and "filename".')
+            if "grid" not in d:
+                raise RuntimeError("mqdiffuse: needs a 'grid' (file loading is not supported)")
+            data = to_grid(d["grid"])
+            if data.shape[-1] != 1:
+                raise RuntimeError("mqdiffuse: only 1-channel grids are supported")
+            b.table = np.ascontiguousarray(data[..., 0], dtype=np.float32)  # [z, y, x] = [cos_theta_i, phi_d, cos_theta_o]
         elif ty == "maignan":  # maignan.cpp:92-101 (constructor defaults, not the documented ones)
             b.children["C"] = tex("C", 0.1)
             b.children["ndvi"] = tex("ndvi", 0.0)
@@ -1101,6 +1109,7 @@ class FlatScene:
             "ocean_mishchenko": _abi.BSDF_OCEAN_MISHCHENKO,
             "ocean_grasp": _abi.BSDF_OCEAN_GRASP,
             "maignan": _abi.BSDF_MAIGNAN,
+            "mqdiffuse": _abi.BSDF_MQDIFFUSE,
         }[(self.bsdf if b is None else b).type]
 
     # -- ctypes descriptor -----------------------------------------------------------------
@@ -1162,6 +1171,11 @@ class FlatScene:
 
         d.bsdf_type = self.bsdf_type()
         d.bsdf_params[:] = list(self.bsdf_params())
+        if self.bsdf.type == "mqdiffuse":
+            tab = self.bsdf.table
+            keep.append(tab)
+            d.bsdf_table = tab.ctypes.data_as(_abi.c_float_p)
+            d.bsdf_table_res[:] = [tab.shape[2], tab.shape[1], tab.shape[0]]
         d.emitter_direction[:] = list(self.emitter.direction)
         d.irradiance = self.emitter.children["irradiance"].values["value"]
         it = self.integrator

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 12
+#define ERTB_ABI_VERSION 13
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -65,7 +65,11 @@ enum ertb_bsdf_type {
     /* ERP/bsdfs/maignan.cpp:83-254 (Maignan et al. 2009 polarized land reflectance; eval() carries no
      * cosine and sample() returns C*F without dividing by the pdf -- reproduced as is);
      * params: C, ndvi, refr_re, refr_im, ext_ior */
-    ERTB_BSDF_MAIGNAN = 8
+    ERTB_BSDF_MAIGNAN = 8,
+    /* ERP/bsdfs/mqdiffuse.cpp:56-210 (measured quasi-diffuse: trilinear, clamped lookup of a
+     * (cos_theta_o, phi_d, cos_theta_i) table, cosine-hemisphere sampling); no params, table in
+     * `bsdf_table` / `bsdf_table_res` */
+    ERTB_BSDF_MQDIFFUSE = 9
 };
 
 enum ertb_phase_type {
@@ -237,6 +241,11 @@ typedef struct ertb_scene_desc {
     int32_t patch_bsdf_type;        /* enum ertb_bsdf_type; not the ocean */
     float patch_bsdf_params[ERTB_MAX_BSDF_PARAMS];
     double patch_rect[4];           /* cx, cy, hx, hy (metres) */
+    /* mqdiffuse: the plugin's VolumeGrid, data[z][y][x] with x = cos_theta_o, y = phi_d / 2 pi, z = cos_theta_i
+     * (mqdiffuse.cpp:80-86); copied at scene creation, not updatable (the plugin exposes no parameter) */
+    const float *bsdf_table;
+    int32_t bsdf_table_res[3];      /* x, y, z */
+    int32_t _pad5;
 } ertb_scene_desc;
 
 /* Named updatable parameters (KernelSceneParameterMap keys resolve to these;

@@ -341,6 +341,9 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
     S->emitter_d = vnormalize(V(d->emitter_direction[0], d->emitter_direction[1], d->emitter_direction[2]));
     if (d->bsdf_type == ERTB_BSDF_OCEAN_LEGACY)
         if (ocean_init(&S->ocean, d->bsdf_params)) return fail("ocean_legacy init failed");
+    if (d->bsdf_type == ERTB_BSDF_MQDIFFUSE &&
+        (!d->bsdf_table || d->bsdf_table_res[0] < 1 || d->bsdf_table_res[1] < 1 || d->bsdf_table_res[2] < 1))
+        return fail("mqdiffuse: missing table");
     if (is_glint_family(d->bsdf_type)) {
         if (d->bsdf_type == ERTB_BSDF_OCEAN_GRASP && d->bsdf_params[6] != 0.f)
             return fail("ocean_grasp: only component=0 (full BRDF) is supported");
@@ -1052,6 +1055,32 @@ static double eval_hapke(const float *P, v3 wi, v3 wo) {
     return w * 0.25 * INV_PI * mu_ratio * (Pf * (1.0 + B) + M) * Sf;
 }
 
+/* mqdiffuse.cpp:94-107 eval_texture: p = (cos_theta_o, phi_d / 2 pi, cos_theta_i) remapped by (1 - 1/res) + 0.5/res,
+ * then the Dr.Jit linear filter with clamp wrap mode (drjit/texture.h: pos = p * res - 0.5, both neighbours of
+ * every axis clamped to [0, res - 1]).  data[z][y][x]. */
+static double mq_texture(const ertb_scene_desc *d, double cos_o, double phi_d, double cos_i) {
+    const int res[3] = { d->bsdf_table_res[0], d->bsdf_table_res[1], d->bsdf_table_res[2] };
+    double p[3] = { cos_o, phi_d / (2.0 * PI), cos_i }, w[3];
+    int i0[3], i1[3];
+    for (int a = 0; a < 3; ++a) {
+        double ps = 1.0 / res[a];
+        double q = p[a] * (1.0 - ps) + 0.5 * ps;
+        double pos = q * res[a] - 0.5, fl = floor(pos);
+        w[a] = pos - fl;
+        int i = (int) fl;
+        i0[a] = i < 0 ? 0 : (i > res[a] - 1 ? res[a] - 1 : i);
+        i1[a] = i + 1 < 0 ? 0 : (i + 1 > res[a] - 1 ? res[a] - 1 : i + 1);
+    }
+#define MQ_AT(z, y, x) ((double) d->bsdf_table[((size_t) (z) * res[1] + (y)) * res[0] + (x)])
+    double c00 = MQ_AT(i0[2], i0[1], i0[0]) * (1 - w[0]) + MQ_AT(i0[2], i0[1], i1[0]) * w[0];
+    double c01 = MQ_AT(i0[2], i1[1], i0[0]) * (1 - w[0]) + MQ_AT(i0[2], i1[1], i1[0]) * w[0];
+    double c10 = MQ_AT(i1[2], i0[1], i0[0]) * (1 - w[0]) + MQ_AT(i1[2], i0[1], i1[0]) * w[0];
+    double c11 = MQ_AT(i1[2], i1[1], i0[0]) * (1 - w[0]) + MQ_AT(i1[2], i1[1], i1[0]) * w[0];
+#undef MQ_AT
+    double c0 = c00 * (1 - w[1]) + c01 * w[1], c1 = c10 * (1 - w[1]) + c11 * w[1];
+    return c0 * (1 - w[2]) + c1 * w[2];
+}
+
 /* BSDF::eval (value * cos_theta_o), local frame */
 static double bsdf_eval_tp(const scene_t *S, int type, const float *P, v3 wi, v3 wo) {
     double cti = wi.z, cto = wo.z;
@@ -1065,6 +1094,11 @@ static double bsdf_eval_tp(const scene_t *S, int type, const float *P, v3 wi, v3
         case ERTB_BSDF_OCEAN_MISHCHENKO: case ERTB_BSDF_OCEAN_GRASP: case ERTB_BSDF_MAIGNAN: {
             double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
             return glint_eval(&S->glint, a, b);
+        }
+        case ERTB_BSDF_MQDIFFUSE: { /* mqdiffuse.cpp:139-161 */
+            double phi_d = fmod(atan2(wo.y, wo.x) - atan2(wi.y, wi.x), 2.0 * PI);
+            if (phi_d < 0.0) phi_d += 2.0 * PI;
+            return mq_texture(S->desc, cto, phi_d, cti) * cto;
         }
         default: return 0.0;
     }
@@ -1096,6 +1130,10 @@ static double bsdf_sample_tp(const scene_t *S, int type, const float *P, v3 wi, 
         case ERTB_BSDF_RPV: return eval_rpv(P, wi, *wo) * o[2] / pdf; /* rpv.cpp:119-122 */
         case ERTB_BSDF_RTLS: return eval_rtls(P, wi, *wo) * o[2] / pdf;
         case ERTB_BSDF_HAPKE: return eval_hapke(P, wi, *wo) * o[2] / pdf;
+        case ERTB_BSDF_MQDIFFUSE: { /* mqdiffuse.cpp:109-137: a negative difference is NOT wrapped here */
+            double phi_d = fmod(atan2(o[1], o[0]) - atan2(wi.y, wi.x), 2.0 * PI);
+            return mq_texture(S->desc, o[2], phi_d, wi.z) * o[2] / pdf;
+        }
         default: return 0.0;
     }
 }

@@ -37,6 +37,17 @@ def _first_sensor(d: dict) -> dict:
     return keep
 
 
+def mq_table(nx=16, ny=25, nz=12):
+    """A quasi-diffuse measured BRDF table [cos_theta_i][phi_d][cos_theta_o] for `mqdiffuse`, deliberately not
+    symmetric in phi_d -> 2 pi - phi_d (so that the sign of the azimuth difference matters) and with distinct
+    first / last phi_d planes (so that the un-wrapped azimuth of mqdiffuse.cpp:125-131 shows)."""
+    from eradiate_b200.kernel import VolumeGrid
+
+    co, ph, ci = np.meshgrid(np.linspace(0, 1, nx), np.linspace(0, 2 * np.pi, ny), np.linspace(0, 1, nz), indexing="ij")
+    v = 0.25 / np.pi * (1.0 + 0.3 * np.cos(ph) + 0.15 * np.sin(ph) + 0.1 * ph / (2 * np.pi)) * (0.7 + 0.5 * co * ci)
+    return VolumeGrid(np.ascontiguousarray(v.transpose(2, 1, 0)).astype(np.float32))
+
+
 def battery() -> dict:
     """name -> scene dict.  Small films; every plugin of SURVEY 8a appears at least once."""
     S = scenes.atmosphere_scene
@@ -96,6 +107,15 @@ def battery() -> dict:
         "maignan_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=10.0,
                         surface={"type": "maignan", "C": 5.0, "ndvi": 0.4, "refr_re": 1.5, "refr_im": 0.0},
                         sensor={"type": "mdistant", "vza": [-60.0, -40.0, 0.0, 30.0, 60.0], "vaa": 10.0}),
+        "mqdiffuse_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=25.0,
+                          surface={"type": "mqdiffuse", "grid": mq_table()},
+                          sensor={"type": "mdistant", "vza": [-60.0, -30.0, 0.0, 30.0, 60.0], "vaa": 70.0}),
+        "mqdiffuse_spherical_thick": S(geometry="spherical_shell", atmosphere="homogeneous",
+                                       homogeneous_sigma_t=1.0 / scenes.TOA, homogeneous_albedo=0.95,
+                                       phase={"type": "hg", "g": 0.5}, sza=30.0, saa=200.0,
+                                       surface={"type": "mqdiffuse", "grid": mq_table(9, 13, 7)},
+                                       sensor={"type": "mdistant", "vza": [-50.0, -20.0, 20.0, 50.0], "vaa": 140.0,
+                                               "target": [2.0e5, 3.0e5, 6.3679007e6]}),
         # polarized (Stokes) transport: rayleigh_polarized / tabphase_polarized + stokes integrator
         "polarized_rayleigh_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=30.0, stokes=True,
                                    phase={"type": "rayleigh_polarized", "depolarization": 0.0279},
@@ -126,6 +146,10 @@ def battery() -> dict:
                                   phase={"type": "rayleigh_polarized", "depolarization": 0.0279},
                                   surface={"type": "maignan", "C": 6.66, "ndvi": 0.3, "refr_re": 1.5, "refr_im": 0.0},
                                   sensor={"type": "mdistant", "vza": [-65.0, -45.0, -20.0, 25.0, 55.0], "vaa": 30.0}),
+        "polarized_mqdiffuse_pp": S(geometry="plane_parallel", n_layers=60, sza=50.0, saa=10.0, stokes=True,
+                                    phase={"type": "rayleigh_polarized"},
+                                    surface={"type": "mqdiffuse", "grid": mq_table()},
+                                    sensor={"type": "mdistant", "vza": [-55.0, -25.0, 15.0, 45.0], "vaa": 100.0}),
         # BASELINE C5 at reduced size: polarized ocean + molecular + polarized aerosol, one band of the sweep
         "c5_polarized_ocean_aerosol_reduced": scenes.config_c5(spp=16, n_vza=4, w_nm=865.0, n_layers=120),
         # integrator options

@@ -51,8 +51,12 @@ def load(surface=None, phase=None, **kw):
     {"type": "ocean_mishchenko", "wind_speed": 6.0, "eta": 1.34, "k": 0.0},
     {"type": "ocean_grasp", "wavelength": 865.0, "wind_speed": 12.0, "eta": 1.33, "water_body_reflectance": 0.03},
     {"type": "maignan", "C": 5.0, "ndvi": 0.4, "refr_re": 1.5, "refr_im": 0.0},
+    {"type": "mqdiffuse"},
 ])
 def test_bsdf_eval_and_sample_match_oracle(oracle, bsdf):
+    if bsdf["type"] == "mqdiffuse":
+        from tests.scene_battery import mq_table
+        bsdf = {**bsdf, "grid": mq_table()}
     sc = load(surface=bsdf)
     desc = sc.flat.build_desc()
     rng = np.random.default_rng(0)
@@ -62,14 +66,17 @@ def test_bsdf_eval_and_sample_match_oracle(oracle, bsdf):
     got = kat.bsdf_eval(sc, wi, wo)
     ref = oracle.bsdf_eval(desc, wi, wo)
     ocean = bsdf["type"] in ("ocean_legacy", "ocean_mishchenko", "ocean_grasp")
-    if bsdf["type"] == "maignan":
-        # maignan.cpp:168-224: cosine-hemisphere directions; the weight is eval() at the sampled direction
+    if bsdf["type"] in ("maignan", "mqdiffuse"):
+        # maignan.cpp:168-224 / mqdiffuse.cpp:109-137: cosine-hemisphere directions; the weight is eval() at the sampled direction
         assert np.allclose(got, ref, rtol=5e-4, atol=1e-7), np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6))
         u = rng.uniform(0, 1, (n, 3)).astype(np.float32)
         wo_g, w_g = kat.bsdf_sample(sc, wi, u)
         wo_o, w_o = oracle.bsdf_sample(desc, wi, u)
         assert np.allclose(wo_g[:, :2], wo_o[:, :2], atol=1e-5) and np.allclose(wo_g[:, 2], wo_o[:, 2], atol=5e-4)
         ok = wo_o[:, 2] > 0.02
+        if bsdf["type"] == "mqdiffuse":  # the un-wrapped azimuth difference switches planes at 0: skip the fp32 ties
+            dphi = np.arctan2(wo_o[:, 1], wo_o[:, 0]) - np.arctan2(wi[:, 1].astype(np.float64), wi[:, 0])
+            ok &= np.abs(dphi) > 1e-3
         assert np.allclose(w_g[ok], w_o[ok], rtol=2e-3, atol=1e-7)
         return
     # fp32 with fast intrinsics (__powf, __fdividef) vs fp64: 2e-4 relative (ocean: the glint lobe
@@ -159,6 +166,21 @@ def test_mishchenko_and_maignan_golden_mueller_on_device(oracle):
         assert ok.sum() > n // 4
         err = np.abs(got - ref)[ok] / scale[ok]
         assert err.max() < 5e-3, (surface["type"], err.max())
+
+
+def test_mqdiffuse_golden_on_device():
+    # ERP/tests/bsdfs/test_mqdiffuse.py:66-125 evaluated by the CUDA implementation
+    from eradiate_b200.kernel import VolumeGrid
+    data = np.array([[np.linspace(0, 1, 5), -np.linspace(0, 1, 5), np.linspace(0, 1, 5)],
+                     [np.linspace(1, 2, 5), -np.linspace(1, 2, 5), np.linspace(1, 2, 5)]])
+    sc = load(surface={"type": "mqdiffuse", "grid": VolumeGrid(data)})
+    for theta_o, phi_o, theta_i, expected in (
+        (np.pi / 3, 0.0, 0.0, 1.5), (np.pi * 0.4195693767448338, 0.0, 0.0, 1.25), (np.pi / 3, np.pi, 0.0, -1.5),
+        (np.pi / 3, 0.5 * np.pi, 0.0, 0.0), (np.pi / 3, 1.5 * np.pi, 0.0, 0.0), (np.pi / 3, 0.0, np.pi / 2, 0.5),
+        (np.pi / 3, np.pi, np.pi / 2, -0.5), (np.pi / 2, np.pi, 0.0, -1.0),
+    ):
+        val = kat.bsdf_eval(sc, sph_to_dir([theta_i], [0.0]), sph_to_dir([theta_o], [phi_o]))[0]
+        assert np.isclose(val, expected * np.cos(theta_o), atol=2e-6), (theta_o, phi_o, theta_i, val)
 
 
 def test_hapke_golden_on_device():

@@ -628,3 +628,62 @@ def test_maignan_sample_conventions(oracle):
     ref = 5.0 * np.exp(-tan_a) * np.exp(-0.8) * F / (4.0 * (np.cos(ti) + np.cos(to)))
     got = oracle.bsdf_eval(desc, sph_to_dir([ti], [0.3]), sph_to_dir([to], [0.3 + dphi]))[0]
     assert np.isclose(got, ref, rtol=1e-6), (got, ref)
+
+
+# ---------------------------------------------------------------------------------------- mqdiffuse
+MQ_SAMPLE_DATA = np.array([  # ERP/tests/bsdfs/test_mqdiffuse.py:66-89: [cos_theta_i][phi_d][cos_theta_o]
+    [np.linspace(0, 1, 5), -np.linspace(0, 1, 5), np.linspace(0, 1, 5)],
+    [np.linspace(1, 2, 5), -np.linspace(1, 2, 5), np.linspace(1, 2, 5)],
+])
+
+
+def _mq_desc(data=MQ_SAMPLE_DATA):
+    from eradiate_b200.kernel import VolumeGrid
+    return make_desc(surface={"type": "mqdiffuse", "grid": VolumeGrid(data)})
+
+
+@pytest.mark.parametrize("theta_o,phi_o,theta_i,phi_i,expected", [
+    # ERP/tests/bsdfs/test_mqdiffuse.py:97-114 (hand-picked entries of the table above)
+    [np.pi / 3, 0.0, 0.0, 0.0, 1.5],
+    [np.pi * 0.4195693767448338, 0.0, 0.0, 0.0, 1.25],
+    [np.pi / 3, np.pi, 0.0, 0.0, -1.5],
+    [np.pi / 3, 0.5 * np.pi, 0.0, 0.0, 0.0],
+    [np.pi / 3, 1.5 * np.pi, 0.0, 0.0, 0.0],
+    [np.pi / 2, 0.0, np.pi / 2, 0.0, 0.0],
+    [np.pi / 3, 0.0, np.pi / 2, 0.0, 0.5],
+    [np.pi / 3, np.pi, np.pi / 2, 0.0, -0.5],
+    [np.pi / 2, np.pi, np.pi / 2, 0.0, 0.0],
+    [np.pi / 2, np.pi, 0.0, 0.0, -1.0],
+])
+def test_mqdiffuse_golden_eval(oracle, theta_o, phi_o, theta_i, phi_i, expected):
+    _, desc = _mq_desc()
+    val = oracle.bsdf_eval(desc, sph_to_dir([theta_i], [phi_i]), sph_to_dir([theta_o], [phi_o]))[0]
+    assert np.isclose(val, expected * np.cos(theta_o), atol=1e-6)  # test_mqdiffuse.py:115-125
+
+
+def test_mqdiffuse_vs_scipy_interpolation_and_sampling(oracle):
+    """eval() against an independent trilinear interpolation (scipy) of a random table on the grid the plugin
+    defines (nodes at linspace(0, 1) / linspace(0, 2 pi), mqdiffuse.cpp:94-107); sample(): cosine-hemisphere
+    directions, weight = value * pi, where a negative azimuth difference is not wrapped (:125-131) and hence
+    reads the phi_d = 0 plane."""
+    from scipy.interpolate import RegularGridInterpolator
+
+    rng = np.random.default_rng(17)
+    nz, ny, nx = 6, 9, 7
+    data = rng.uniform(0.05, 0.3, (nz, ny, nx))
+    _, desc = _mq_desc(data)
+    interp = RegularGridInterpolator((np.linspace(0, 1, nz), np.linspace(0, 2 * np.pi, ny), np.linspace(0, 1, nx)),
+                                     data.astype(np.float32).astype(np.float64))
+    n = 4000
+    wi = sph_to_dir(rng.uniform(0.0, 1.5, n), rng.uniform(-np.pi, np.pi, n))
+    wo = sph_to_dir(rng.uniform(0.0, 1.5, n), rng.uniform(-np.pi, np.pi, n))
+    phi_d = np.mod(np.arctan2(wo[:, 1], wo[:, 0]) - np.arctan2(wi[:, 1], wi[:, 0]), 2 * np.pi)
+    ref = interp(np.stack([wi[:, 2], phi_d, wo[:, 2]], axis=-1)) * wo[:, 2]
+    assert np.allclose(oracle.bsdf_eval(desc, wi, wo), ref, rtol=1e-9, atol=1e-12)
+    u = rng.uniform(0, 1, (n, 3))
+    wo_s, w = oracle.bsdf_sample(desc, wi, u)
+    assert np.allclose(wo_s, oracle.warp("cosine_hemisphere", u[:, 1], u[:, 2]), atol=1e-14)
+    diff = np.arctan2(wo_s[:, 1], wo_s[:, 0]) - np.arctan2(wi[:, 1], wi[:, 0])
+    phi_s = np.where(diff < 0, 0.0, np.fmod(diff, 2 * np.pi))
+    ref_w = interp(np.stack([wi[:, 2], phi_s, wo_s[:, 2]], axis=-1)) * np.pi
+    assert (diff < 0).mean() > 0.3 and np.allclose(w, ref_w, rtol=1e-9)
