@@ -231,7 +231,7 @@ _SUPPORTED = {
     "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "ocean_mishchenko", "ocean_grasp", "maignan",
              "mqdiffuse", "null", "bilambertian", "blendbsdf"},
     "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
-              "rayleigh_polarized", "tabphase_polarized"},
+              "rayleigh_polarized", "tabphase_polarized", "multiphase"},
     "sensor": {"mdistant", "hdistant", "distantflux", "perspective", "mpdistant", "mradiancemeter"},
     "volume": {"gridvolume", "sphericalcoordsvolume", "constvolume"},
 }
@@ -244,8 +244,15 @@ _KNOWN_UNSUPPORTED = {
     "astroobject": "finite-size solar discs need emitter-hit MIS, which the kernels do not carry (use 'directional')",
     "measured_mono": "only the quasi-diffuse measured BSDF ('mqdiffuse') is implemented",
     "selectbsdf": "this BSDF adapter is not implemented",
-    "multiphase": "use nested 'blendphase' nodes (flattened to <= 4 leaves)",
 }
+
+
+def _phase_leaf_nodes(ph):
+    """Leaves below a blendphase / multiphase node."""
+    kids = [c for name, c in ph.children.items() if name.startswith("phase")]
+    if ph.type not in ("blendphase", "multiphase"):
+        return [ph]
+    return [leaf for c in kids for leaf in _phase_leaf_nodes(c)]
 
 
 class _Loader:
@@ -391,6 +398,19 @@ class _Loader:
             ph.children["weight"] = self.make_volume(d.get("weight", 0.5), None)
             ph.children["phase_0"] = self.resolve(nested[0])
             ph.children["phase_1"] = self.resolve(nested[1])
+        elif ty == "multiphase":
+            # ERP/phase/multiphase.cpp:75-112: nested phase functions in order of appearance, `weight<i>` volumes
+            # (normalised internally), optional mixture MIS of the sampling weight (default on)
+            ph.use_mis = bool(d.get("use_mis", True))
+            nested = [v for k, v in d.items() if isinstance(v, dict) and not k.startswith("weight")
+                      and (_KIND_OF.get(v.get("type")) == "phase" or v.get("type") == "ref")]
+            if len(nested) < 2:
+                raise RuntimeError("MultiPhase: At least 2 child phase functions must be specified!")
+            for i, child in enumerate(nested):
+                if f"weight{i}" not in d:
+                    raise RuntimeError(f"multiphase: missing required parameter 'weight{i}'")
+                ph.children[f"phase{i}"] = self.resolve(child)
+                ph.children[f"weight{i}"] = self.make_volume(d[f"weight{i}"], None)
         return ph
 
     def make_bsdf(self, d, oid) -> BSDF:
@@ -1048,6 +1068,29 @@ class FlatScene:
                 w = np.clip(self._profile(ph.children["weight"], n, "blendphase.weight"), 0.0, 1.0)
                 walk(ph.children["phase_0"], prob * (1.0 - w))
                 walk(ph.children["phase_1"], prob * w)
+            elif ph.type == "multiphase":
+                # multiphase.cpp:123-207: component i is drawn with probability w_i / sum(w) and, without MIS,
+                # returns its own weight -- the flattened blend.  With MIS the weight becomes
+                # sum_j w_j value_j / sum_j w_j pdf_j at the sampled direction, which is the component's own
+                # weight (1) whenever every component's value equals its pdf; the kernels do not carry the general
+                # form (Mueller-valued or depolarized-Rayleigh components).
+                k = sum(1 for name in ph.children if name.startswith("phase"))
+                ws = [np.asarray(self._profile(ph.children[f"weight{i}"], n, f"multiphase.weight{i}"), np.float64)
+                      for i in range(k)]
+                total = np.sum(ws, axis=0)
+                if np.any(total <= 0.0):
+                    raise RuntimeError("multiphase: the weights must have a positive sum in every layer")
+                if getattr(ph, "use_mis", True):
+                    for leaf in _phase_leaf_nodes(ph):
+                        dep = leaf.values.get("depolarization", 0.0) if "depolarization" not in leaf.children \
+                            else float(leaf.children["depolarization"].layer_values().flat[0])
+                        if leaf.type in ("rayleigh_polarized", "tabphase_polarized") or \
+                                (leaf.type == "rayleigh" and dep != 0.0):
+                            raise RuntimeError(
+                                "multiphase: use_mis=True is only supported for components whose value equals their "
+                                f"pdf (got '{leaf.type}'); pass use_mis=False")
+                for i in range(k):
+                    walk(ph.children[f"phase{i}"], prob * (ws[i] / total))
             else:
                 leaves.append((ph, prob.astype(np.float32)))
 

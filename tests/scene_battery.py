@@ -37,6 +37,29 @@ def _first_sensor(d: dict) -> dict:
     return keep
 
 
+def multiphase_scene(nested_blend: bool = False) -> dict:
+    """Three phase functions mixed by per-layer `multiphase` weights (not normalised: multiphase.cpp:131-138 does
+    it) over the AFGL-shaped profile; `nested_blend`: the equivalent tree of two `blendphase` nodes."""
+    n = 80
+    zn = (np.arange(n) + 0.5) / n
+    w = [np.full(n, 1.0), 3.0 * np.exp(-6.0 * zn), 0.5 * zn]
+    vol = lambda v: scenes._volume(v, False, scenes.EARTH_RADIUS, scenes.TOA, 1.0e9)  # noqa: E731
+    leaves = [{"type": "rayleigh"}, {"type": "hg", "g": 0.7}, {"type": "isotropic"}]
+    if nested_blend:  # blendphase.cpp:100-141: weight = probability of phase_1
+        phase = {"type": "blendphase", "phase_0": leaves[0],
+                 "phase_1": {"type": "blendphase", "phase_0": leaves[1], "phase_1": leaves[2],
+                             "weight": vol(w[2] / (w[1] + w[2]))},
+                 "weight": vol((w[1] + w[2]) / (w[0] + w[1] + w[2]))}
+    else:
+        phase = {"type": "multiphase", "use_mis": True}
+        for i in range(3):
+            phase[f"phase{i}"] = leaves[i]
+            phase[f"weight{i}"] = vol(w[i])
+    return scenes.atmosphere_scene(geometry="plane_parallel", n_layers=n, phase=phase, sza=50.0, saa=0.0,
+                                   surface={"type": "diffuse", "reflectance": 0.15},
+                                   sensor={"type": "mdistant", "vza": [-65.0, -30.0, 0.0, 30.0, 65.0], "vaa": 0.0})
+
+
 def mq_table(nx=16, ny=25, nz=12):
     """A quasi-diffuse measured BRDF table [cos_theta_i][phi_d][cos_theta_o] for `mqdiffuse`, deliberately not
     symmetric in phi_d -> 2 pi - phi_d (so that the sign of the azimuth difference matters) and with distinct
@@ -107,6 +130,7 @@ def battery() -> dict:
         "maignan_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=10.0,
                         surface={"type": "maignan", "C": 5.0, "ndvi": 0.4, "refr_re": 1.5, "refr_im": 0.0},
                         sensor={"type": "mdistant", "vza": [-60.0, -40.0, 0.0, 30.0, 60.0], "vaa": 10.0}),
+        "multiphase_three_components_pp": multiphase_scene(),
         "mqdiffuse_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=25.0,
                           surface={"type": "mqdiffuse", "grid": mq_table()},
                           sensor={"type": "mdistant", "vza": [-60.0, -30.0, 0.0, 30.0, 60.0], "vaa": 70.0}),

@@ -130,6 +130,43 @@ def test_glint_family_bsdfs_load_with_reference_defaults_and_keys():
         bsdf_of({"type": "ocean_grasp", "wavelength": 550.0, "component": 2})
 
 
+def test_multiphase_flattens_like_the_equivalent_blend_tree():
+    """ERP/phase/multiphase.cpp:123-207: component i is drawn with probability w_i / sum(w) and evaluated as the
+    normalised mixture, i.e. the leaves of the equivalent nested `blendphase` tree; weights need not sum to 1."""
+    from tests.scene_battery import multiphase_scene
+
+    a = mi_load_dict(multiphase_scene()).flat.build_desc()
+    b = mi_load_dict(multiphase_scene(nested_blend=True)).flat.build_desc()
+    assert a.n_phase == b.n_phase == 3
+    assert [a.phase[i].type for i in range(3)] == [_abi.PHASE_RAYLEIGH, _abi.PHASE_HG, _abi.PHASE_ISOTROPIC]
+    wa = np.ctypeslib.as_array(a.phase_weight, shape=(3, a.n_layers))
+    wb = np.ctypeslib.as_array(b.phase_weight, shape=(3, b.n_layers))
+    assert np.allclose(wa, wb, atol=2e-7) and np.allclose(wa.sum(axis=0), 1.0, atol=1e-6)
+    # traverse() publishes phase<i> / weight<i> (multiphase.cpp:114-119)
+    keys = {k.split("phase_function.")[-1] for k in mi_traverse(mi_load_dict(multiphase_scene())).parameters.keys()
+            if "phase_function." in k}
+    assert {"weight0.data", "weight1.data", "weight2.data", "phase1.g"} <= keys, keys
+
+
+@pytest.mark.parametrize("phase,match", [
+    ({"type": "multiphase", "phase0": {"type": "isotropic"}, "weight0": 1.0}, "At least 2 child phase functions"),
+    ({"type": "multiphase", "phase0": {"type": "isotropic"}, "weight0": 1.0, "phase1": {"type": "hg"}}, "weight1"),
+    ({"type": "multiphase", "phase0": {"type": "isotropic"}, "weight0": 1.0,
+      "phase1": {"type": "rayleigh", "depolarization": 0.03}, "weight1": 1.0}, "use_mis=False"),
+])
+def test_multiphase_load_errors(phase, match):
+    with pytest.raises(RuntimeError, match=match):
+        mi_load_dict(scenes.atmosphere_scene(phase=phase, geometry="plane_parallel", n_layers=4)).flat.build_desc()
+
+
+def test_multiphase_without_mis_accepts_any_component():
+    phase = {"type": "multiphase", "use_mis": False, "phase0": {"type": "hg", "g": 0.3}, "weight0": 0.2,
+             "phase1": {"type": "rayleigh", "depolarization": 0.03}, "weight1": 0.6}
+    d = mi_load_dict(scenes.atmosphere_scene(phase=phase, geometry="plane_parallel", n_layers=4)).flat.build_desc()
+    w = np.ctypeslib.as_array(d.phase_weight, shape=(2, 4))
+    assert np.allclose(w[0], 0.25) and np.allclose(w[1], 0.75)
+
+
 def test_piecewise_volpath_needs_a_piecewise_medium():
     # only ERP/media/piecewise.cpp overrides the *_real interface (medium.cpp:99-118); the scene is
     # flattened at load time here, so the reference's render-time error surfaces from mi_load_dict

@@ -687,3 +687,19 @@ def test_mqdiffuse_vs_scipy_interpolation_and_sampling(oracle):
     phi_s = np.where(diff < 0, 0.0, np.fmod(diff, 2 * np.pi))
     ref_w = interp(np.stack([wi[:, 2], phi_s, wo_s[:, 2]], axis=-1)) * np.pi
     assert (diff < 0).mean() > 0.3 and np.allclose(w, ref_w, rtol=1e-9)
+
+
+# --------------------------------------------------------------------------------------- multiphase
+@pytest.mark.parametrize("weight,g", [(0.2, 0.2), (0.8, 0.2)])
+def test_multiphase_mixture_eval(oracle, weight, g):
+    # ERP/tests/phase/test_multiphase.py:38-68 (eval of the blend at wi = wo = +z) and :71-110 (the pdf of each
+    # component as sample() returns it without MIS)
+    phase = {"type": "multiphase", "use_mis": False, "phase0": {"type": "isotropic"}, "weight0": weight,
+             "phase1": {"type": "hg", "g": g}, "weight1": 1 - weight}
+    _, desc = make_desc(phase=phase)
+    w = np.ctypeslib.as_array(desc.phase_weight, shape=(2, desc.n_layers))[:, 0]
+    vals = [oracle.phase_eval(desc, leaf, [1.0])[0] for leaf in range(2)]
+    inv_four_pi = 1.0 / (4.0 * np.pi)
+    assert np.isclose(vals[0], inv_four_pi) and np.isclose(vals[1], inv_four_pi * (1 - g) / (1 + g) ** 2)
+    expected = weight * inv_four_pi + (1 - weight) * inv_four_pi * (1.0 - g) / (1.0 + g) ** 2
+    assert np.isclose(w[0] * vals[0] + w[1] * vals[1], expected, rtol=1e-6)
