@@ -16,6 +16,12 @@ NAMES = ["c2_afgl_rpv_spherical", "afgl_rpv_pp", "thick_isotropic_pp", "ocean_pp
          "canopy_path_no_atmosphere", "c4_canopy_afgl_rpv_reduced", "central_patch_canopy_mpdistant_pp",
          "mradiancemeter_sky_and_nadir_spherical", "mradiancemeter_piecewise_aerosol_pp", "mpdistant_spherical",
          "c3_afgl_aerosol_tab_hdistant", "aerosol_tab_irregular_spherical"]
+# SURVEY 8f-4 plugins added last (glint family, mqdiffuse, multiphase); DEEP_NAMES=new selects only these
+NEW = ["ocean_mishchenko_pp", "ocean_grasp_spherical", "maignan_pp", "polarized_mishchenko_pp", "polarized_grasp_spherical",
+       "polarized_maignan_pp", "mqdiffuse_pp", "mqdiffuse_spherical_thick", "polarized_mqdiffuse_pp",
+       "multiphase_three_components_pp"]
+sel = os.environ.get("DEEP_NAMES", "")
+NAMES = NEW if sel == "new" else (sel.split(",") if sel else NAMES + NEW)
 bad = 0
 B = battery()
 for name in NAMES:
@@ -24,8 +30,11 @@ for name in NAMES:
     heavy = name.startswith(("c3_", "aerosol"))
     ospp = 1 << ((17 if heavy else 20) + int(os.environ.get("DEEP", "0")))
     t0 = time.perf_counter()
-    wl, l, l2, st = (oracle.render(d, 0, 77, ospp) if not d.polarized else
-                     (lambda r: (r[0], r[1], r[2], r[4]))(oracle.render_stokes(d, 0, 77, ospp)))
+    ostokes = None
+    if d.polarized:
+        wl, l, l2, ostokes, st = oracle.render_stokes(d, 0, 77, ospp)
+    else:
+        wl, l, l2, st = oracle.render(d, 0, 77, ospp)
     om = l / ospp
     ov = np.maximum(l2 / ospp - om * om, 0) / ospp
     t1 = time.perf_counter()
@@ -35,6 +44,12 @@ for name in NAMES:
     gv = np.maximum(bmp.raw["sum_l2"].ravel() / gspp - gm * gm, 0) / gspp
     z = (gm - om) / np.sqrt(gv + ov + 1e-300)
     rel = np.max(np.abs(gm - om) / np.maximum(om, 1e-12))
+    if ostokes is not None:  # Q, U, V: per-sample |Q| <= I, so the second moment of I bounds their variance
+        gs = np.asarray(bmp.raw["sum_stokes"]).reshape(4, -1) / gspp
+        os_ = np.asarray(ostokes).reshape(4, -1) / ospp
+        bound = np.sqrt(bmp.raw["sum_l2"].ravel() / gspp / gspp + l2 / ospp / ospp)
+        zq = np.abs(gs[1:] - os_[1:]) / bound
+        z = np.concatenate([z, zq.ravel()])
     flag = "" if np.all(np.abs(z) <= 4.0) else "   <-- CHECK"
     bad += flag != ""
     print(f"{name:44s} |z|max {np.abs(z).max():4.2f}  max rel diff {rel:.2e}  rel sigma(cpu) {np.max(np.sqrt(ov) / np.maximum(om, 1e-12)):.1e}"
