@@ -70,6 +70,22 @@ def ncu_traffic_bytes():
         return None
 
 
+def ncu_issue(kernel_ms, sm_mhz, n_sm):
+    """Instruction-issue view of the same kernel (the bound DESIGN.md names): warp instructions per launch from
+    the committed ncu capture / the kernel time measured live, against n_sm x 4 schedulers x 1 inst/clk."""
+    path = os.path.join(ROOT, "profiles", "render_kernel_traffic.json")
+    try:
+        d = json.load(open(path))
+        inst, lanes = float(d["warp_inst_per_launch"]), float(d["thread_inst_per_warp_inst"])
+        achieved = inst / (kernel_ms * 1e-3) / 1e9
+        peak = n_sm * 4 * float(sm_mhz) * 1e6 / 1e9
+        return {"achieved": achieved, "peak": peak, "unit": "G warp-inst/s", "frac": achieved / peak,
+                "active_lanes_per_inst": lanes,
+                "note": "instruction count of one C2 launch from profiles/r01k (ncu), time measured live"}
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -342,6 +358,9 @@ def run_cuda(args):
                         "the instruction-issue rate (see DESIGN.md, profiles/)",
             },
         }
+        if args.config == "c2" and clocks and clocks.get("sm_mhz"):
+            line["roofline"]["issue"] = ncu_issue(kern_ms, clocks["sm_mhz"],
+                                                  torch.cuda.get_device_properties(0).multi_processor_count)
         if world == 1 and args.config == "c2":
             cores = os.cpu_count() or 1
             cpu_spp = 1 << 19  # 16.8 M paths: ~15-30 core-seconds of the same workload

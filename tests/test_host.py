@@ -260,8 +260,9 @@ def test_desc_struct_layout_is_stable():
     assert C.sizeof(_abi.RenderStats) == 56
     assert C.sizeof(_abi.SensorDesc) == 360
     assert C.sizeof(_abi.LeafGroupDesc) == 56
-    assert C.sizeof(_abi.SceneDesc) == 712
-    assert _abi.SceneDesc.patch_rect.offset + 32 == C.sizeof(_abi.SceneDesc)
+    assert C.sizeof(_abi.SceneDesc) == 736
+    assert _abi.SceneDesc.patch_rect.offset + 32 == _abi.SceneDesc.bsdf_table.offset == 712
+    assert _abi.SceneDesc.bsdf_table_res.offset == 720
 
 
 # ------------------------------------------------------------------ canopy / 3D scenes (host side)
