@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -170,6 +170,7 @@ class SceneDesc(C.Structure):
         ("bsdf_table", c_float_p),
         ("bsdf_table_res", C.c_int32 * 3),
         ("_pad5", C.c_int32),
+        ("emitter_angular_diameter", C.c_double),
     ]
 
 

@@ -277,6 +277,7 @@ struct ertb_scene {
     std::map<std::pair<const void *, size_t>, int> occupancy; // per kernel instantiation and smem size
     int max_smem_optin = 0;
     double *d_gl = nullptr;     // Gauss-Legendre nodes/weights of the ocean transmittance quadrature
+    double astro_diameter = 0.0;   // astroobject: angular diameter in degrees (0 = directional emitter)
     float *d_bsdf_table = nullptr; // mqdiffuse: the measured table, [z][y][x] (static)
     int bsdf_table_res[3] = { 0, 0, 0 };
     // canopy (plane-parallel scenes): host description and the device BVH
@@ -719,6 +720,14 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
                      S->emitter_dir[2] * S->emitter_dir[2]);
     for (int i = 0; i < 3; ++i) P.sun[i] = (float) (-S->emitter_dir[i] / dn);
     P.irradiance = S->irradiance;
+    P.astro_omc = P.astro_sin2 = P.astro_radiance = 0.f;
+    if (S->astro_diameter > 0.0) { // astroobject.cpp:75-80
+        const double a = 0.5 * S->astro_diameter * M_PI / 180.0;
+        const double omc = 2.0 * sin(0.5 * a) * sin(0.5 * a); // 1 - cos a without cancellation
+        P.astro_omc = (float) omc;
+        P.astro_sin2 = (float) (sin(a) * sin(a));
+        P.astro_radiance = (float) ((double) S->irradiance / (2.0 * M_PI * omc));
+    }
     P.polarized = S->polarized;
     P.meridian_align = S->meridian_align;
     P.mis = S->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
@@ -981,6 +990,17 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
     }
     S->bsdf_type = D->bsdf_type;
     memcpy(S->bsdf_params, D->bsdf_params, sizeof S->bsdf_params);
+    if (D->emitter_angular_diameter != 0.0) {
+        if (!(D->emitter_angular_diameter > 0.0 && D->emitter_angular_diameter < 180.0)) {
+            delete S;
+            return set_error("Invalid angular diameter specified! (must be in ]0, 180[)");
+        }
+        if (D->n_instances > 0 || D->has_patch || D->integrator == ERTB_INTEGRATOR_VOLPATHMIS) {
+            delete S;
+            return set_error("astroobject: 1D scenes with the volpath / piecewise_volpath integrators only");
+        }
+        S->astro_diameter = D->emitter_angular_diameter;
+    }
     memset(S->patch_bsdf_params, 0, sizeof S->patch_bsdf_params);
     if (D->has_patch) {
         if (D->geometry != ERTB_GEOM_PLANE_PARALLEL || D->polarized) {
@@ -1240,6 +1260,10 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     const bool c3d = S->needs_3d; // canopy / perspective camera: the 3D kernel (ertb_canopy.cuh)
     if (pol || pw) use_pool = true; // the polarized and the piecewise paths exist in the pool kernel only
     if (c3d) use_pool = false;
+    if (S->astro_diameter > 0.0) { // the finite solar disc exists in the pool kernel only
+        if (c3d) return set_error("astroobject: not supported with a perspective camera or a canopy");
+        use_pool = true;
+    }
     // general primary rays: the GEN instances of the pool kernel (compiled with statistics on)
     const bool gen = !c3d && (hs.desc.type == ERTB_SENSOR_MPDISTANT || hs.desc.type == ERTB_SENSOR_MRADIANCEMETER);
     if (gen) use_pool = true;
@@ -1247,7 +1271,7 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     const bool bands = S->base.n_bands > 1;
     size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol, bands && !pw) : (size_t) S->base.blob_bytes;
     if (use_pool && smem > (size_t) S->max_smem_optin) { // huge tables: fall back to the register kernel
-        if (pol || pw) return set_error("scene tables leave no shared memory for the path pools");
+        if (pol || pw || S->astro_diameter > 0.0) return set_error("scene tables leave no shared memory for the path pools");
         use_pool = false;
         smem = (size_t) S->base.blob_bytes;
     }

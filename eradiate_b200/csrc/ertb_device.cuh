@@ -119,6 +119,9 @@ struct ErtbParams {
     // emitter
     float sun[3];     // unit vector pointing towards the sun (= -emitter direction)
     float irradiance;
+    // astroobject (astroobject.cpp:54-242): a uniform disc of angular radius a around `sun`; 0 = directional.
+    // 1 - cos a and sin^2 a are derived in double on the host (cos a = 1 - 1.1e-5 for the Sun)
+    float astro_omc, astro_sin2, astro_radiance; // 1 - cos a, sin^2 a, irradiance / solid angle
     // integrator
     int polarized;    // Mueller/Stokes transport (scalar_mono_polarized variant)
     int meridian_align; // stokes.cpp: output basis in the meridian plane

@@ -408,6 +408,13 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                     acc_pix = pix_old; // (a lane holding another pixel's sums was flushed just above)
                     float r = FLD(PF_RES, slot);
                     float wr = FLD(PF_WRAY, slot);
+                    if (P.astro_radiance > 0.f && (FLDU(PF_FLAGS, slot) >> PFL_DEPTH_SHIFT) == 0u) {
+                        // astroobject: a primary ray that left the scene without any event looks at the sky and
+                        // sees the disc if it points into it (volpath.cpp:328-346, count_direct; throughput 1)
+                        f3 dd = mk3(FLD(PF_DX, slot), FLD(PF_DY, slot), FLD(PF_DZ, slot));
+                        f3 cx = cross3(dd, sun);
+                        if (dot3(dd, sun) > 0.f && dot3(cx, cx) < P.astro_sin2) r += P.astro_radiance;
+                    }
                     acc_wl += (double) (wr * r);
                     acc_l += (double) r;
                     acc_l2 += (double) r * (double) r;
@@ -588,6 +595,21 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
             unsigned depth = flags >> PFL_DEPTH_SHIFT;
             float wnee = 0.f;
             bool dead = false;
+            // Next-event direction: the sun, or a point of the solar disc (astroobject.cpp:141-175: uniform in
+            // the cone, weight E).  The disc is sampled by next-event estimation ONLY: no MIS weight here and no
+            // emitter hit for scattered rays -- the same expectation as the reference's MIS pair (volpath.cpp:
+            // 286-290, :336-343), whose second technique carries (pdf_scatter x solid angle)^2 of the weight.
+            f3 sun_e = sun;
+            if (P.astro_omc > 0.f) {
+                float ox, oy;
+                disk_concentric(pcg_float(rng), pcg_float(rng), ox, oy);
+                float pn = fmaf(ox, ox, oy * oy);
+                float t = P.astro_omc * pn;           // 1 - cos(theta) of the sample
+                float sc = sqrtf(P.astro_omc * (2.f - t)); // sin(theta) / sqrt(pn)
+                f3 fs, ft;
+                onb(sun, fs, ft);
+                sun_e = normalize3(fma3(fs, ox * sc, fma3(ft, oy * sc, scale3(sun, 1.f - t))));
+            }
             // polarized state: T = thr * That (actual Mueller throughput), result (Q, U, V), NEE ratios
             float T[POL ? 16 : 1], rquv[3] = { 0.f, 0.f, 0.f }, qn[3] = { 0.f, 0.f, 0.f };
             if (POL) {
@@ -610,6 +632,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                 float ci = -dot3(n0, d);
                 if (!(ci > 0.f) || P.bsdf_type == ERTB_BSDF_BLACK) {
                     thr = 0.f; dead = true;
+                    depth++; // absorbed by the ground: not an escape (the astroobject direct view tests depth == 0)
                 } else {
                     float f_sun, weight;
                     if (POL && bsdf_is_mueller(P.bsdf_type)) {
@@ -620,7 +643,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                         f3 wi = mk3(-dot3(d, fs), -dot3(d, ft), ci);
                         float Mb[16], v[4] = { 0.f, 0.f, 0.f, 0.f };
                         if (depth + 1u < P.max_depth) {
-                            f3 ws = mk3(dot3(sun, fs), dot3(sun, ft), dot3(sun, n0));
+                            f3 ws = mk3(dot3(sun_e, fs), dot3(sun_e, ft), dot3(sun_e, n0));
                             if (ws.z > 0.f) {
                                 lf_eval_mueller(P, false, wi, ws, fs, ft, n0, Mb);
 #pragma unroll
@@ -650,7 +673,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                         weight = thr != 0.f ? __fdividef(T[0], thr) : 0.f; // so that thr * weight = T00 below
                         if (!(weight > 0.f)) weight = 0.f;
                     } else {
-                    surface_interact<SPH>(P, n0, sun, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
+                    surface_interact<SPH>(P, n0, sun_e, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
                     wnee = thr * f_sun * P.irradiance;
                     if (POL) {
                         // depolarizer(f): the NEE Stokes vector is T[:,0] * f * E; then T <- T * depolarizer(w)
@@ -696,7 +719,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                     if (thr == 0.f) {
                         dead = true;
                     } else {
-                        float ct_sun = dot3(d, sun);
+                        float ct_sun = dot3(d, sun_e);
                         float pv = 0.f;
                         int leaf = 0;
                         const f3 wi_w = mk3(-d.x, -d.y, -d.z);
@@ -706,7 +729,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                             for (int k = 0; k < 16; ++k) Pm[k] = 0.f;
                         }
                         if (P.n_phase == 1) {
-                            if (POL) { float pp; leaf_mueller(tb, P.leaf[0], wi_w, sun, Pm, pp); }
+                            if (POL) { float pp; leaf_mueller(tb, P.leaf[0], wi_w, sun_e, Pm, pp); }
                             else pv = leaf_eval(tb, P.leaf[0], ct_sun);
                         } else {
                             float u0 = pcg_float(rng);
@@ -720,7 +743,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                                 if (w > 0.f) {
                                     if (POL) {
                                         float Mi[16], pp;
-                                        leaf_mueller(tb, P.leaf[i], wi_w, sun, Mi, pp);
+                                        leaf_mueller(tb, P.leaf[i], wi_w, sun_e, Mi, pp);
 #pragma unroll
                                         for (int k = 0; k < 16; ++k) Pm[k] = fmaf(w, Mi[k], Pm[k]);
                                     } else {
@@ -785,7 +808,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                 //      flight to the next event ----
                 if (wnee > 0.f) {
                     if (STATS) st_nee++;
-                    float c = sun.z > 0.f ? wnee * pw_transmittance_up(P, tb, h0, sun.z) : 0.f;
+                    float c = sun_e.z > 0.f ? wnee * pw_transmittance_up(P, tb, h0, sun_e.z) : 0.f;
                     res += c;
                     if (POL) {
 #pragma unroll
@@ -816,7 +839,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
             int kind = KIND_TOA, kind2 = KIND_TOA;
             if (!dead) segment_setup<SPH>(P, n0, h0, d, b2, smax2, kind2);
             if (wnee > 0.f) {
-                segment_setup<SPH>(P, n0, h0, sun, b, smax, kind);
+                segment_setup<SPH>(P, n0, h0, sun_e, b, smax, kind);
                 if (kind == KIND_GROUND) wnee = 0.f; // sun below the local horizon
             }
             unsigned mode;

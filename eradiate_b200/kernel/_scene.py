@@ -225,7 +225,7 @@ class Scene(Object):
 
 _SUPPORTED = {
     "integrator": {"volpath", "volpathmis", "piecewise_volpath", "path", "moment", "stokes"},
-    "emitter": {"directional"},
+    "emitter": {"directional", "astroobject"},
     "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance", "cylinder"},
     "medium": {"heterogeneous", "homogeneous", "piecewise"},
     "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "ocean_mishchenko", "ocean_grasp", "maignan",
@@ -241,7 +241,6 @@ _KNOWN_UNSUPPORTED = {
     "ply": "mesh canopy elements are not implemented",
     "obj": "mesh canopy elements are not implemented",
     # the reference's remaining plugins for this slot
-    "astroobject": "finite-size solar discs need emitter-hit MIS, which the kernels do not carry (use 'directional')",
     "measured_mono": "only the quasi-diffuse measured BSDF ('mqdiffuse') is implemented",
     "selectbsdf": "this BSDF adapter is not implemented",
 }
@@ -527,10 +526,21 @@ class _Loader:
     def make_emitter(self, d, oid) -> Emitter:
         e = Emitter(d["type"], oid)
         if "direction" in d:
+            if "to_world" in d:
+                raise RuntimeError("Only one of the parameters 'direction' and 'to_world' can be specified at the "
+                                   "same time!'")
             direction = np.asarray(d["direction"], dtype=np.float64)
         else:
             direction = to_matrix(d.get("to_world"))[:3, :3] @ np.array([0.0, 0.0, 1.0])
         e.direction = direction / np.linalg.norm(direction)
+        e.angular_diameter = 0.0
+        if d["type"] == "astroobject":
+            # astroobject.cpp:62-88: `direction` / to_world * z points TOWARDS the object (the opposite of
+            # `directional`, whose direction is the one light travels); default diameter = the Sun's
+            e.direction = -e.direction
+            e.angular_diameter = float(d.get("angular_diameter", 0.5358))
+            if not (0.0 < e.angular_diameter < 180.0):
+                raise RuntimeError("Invalid angular diameter specified! (must be in ]0, 180[°)")
         e.children["irradiance"] = self.make_texture(d.get("irradiance", 1.0), "irradiance")
         return e
 
@@ -1221,6 +1231,7 @@ class FlatScene:
             d.bsdf_table_res[:] = [tab.shape[2], tab.shape[1], tab.shape[0]]
         d.emitter_direction[:] = list(self.emitter.direction)
         d.irradiance = self.emitter.children["irradiance"].values["value"]
+        d.emitter_angular_diameter = getattr(self.emitter, "angular_diameter", 0.0)
         it = self.integrator
         d.integrator = (
             {"volpathmis": _abi.INTEGRATOR_VOLPATHMIS,

@@ -119,6 +119,7 @@ def atmosphere_scene(
     canopy: dict | None = None,
     extra_sensors: list | None = None,
     central_patch: dict | None = None,
+    angular_diameter: float | None = None,
 ) -> dict:
     """Build the nested scene dict an ``AtmosphereExperiment`` would emit (with ``canopy``: a
     ``CanopyAtmosphereExperiment``, see :func:`disc_canopy`).
@@ -151,6 +152,14 @@ def atmosphere_scene(
         "to_world": _look_at_direction(-sun),
         "irradiance": {"type": "uniform", "value": irradiance},
     }
+    if angular_diameter is not None:
+        # illumination/_astro_object.py:57-77: same look_at, but towards the object (direction with flip=False)
+        scene["illumination"] = {
+            "type": "astroobject",
+            "to_world": _look_at_direction(sun),
+            "angular_diameter": angular_diameter,
+            "irradiance": {"type": "uniform", "value": irradiance},
+        }
 
     spherical = geometry == "spherical_shell"
     if not spherical and geometry != "plane_parallel":

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 13
+#define ERTB_ABI_VERSION 14
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -246,6 +246,10 @@ typedef struct ertb_scene_desc {
     const float *bsdf_table;
     int32_t bsdf_table_res[3];      /* x, y, z */
     int32_t _pad5;
+    /* ERP/emitters/astroobject.cpp:54-242: the light source is a uniform disc of this angular diameter (degrees,
+     * in ]0, 180[) centred on -emitter_direction, radiating `irradiance` / solid angle; 0 = the delta
+     * `directional` emitter.  1D scenes, volpath / piecewise_volpath. */
+    double emitter_angular_diameter;
 } ertb_scene_desc;
 
 /* Named updatable parameters (KernelSceneParameterMap keys resolve to these;

@@ -291,6 +291,8 @@ typedef struct {
     v3 emitter_d;               /* normalised propagation direction */
     ocean_state_t ocean;        /* ocean_legacy precomputed tables */
     glint_state_t glint;        /* ocean_mishchenko / ocean_grasp / maignan */
+    int astro;                  /* astroobject.cpp: finite disc instead of the delta directional emitter */
+    double astro_cos, astro_omega; /* cos(angular radius), solid angle 2 pi (1 - cos) */
     double *pw_cum, *pw_rcum;   /* piecewise.cpp m_cum_opt_thickness / m_reverse_cum_opt_thickness */
     double pp_half_width;       /* > 0: finite slab bbox in x, y (known-answer tests only) */
     canopy_t canopy;            /* explicit disk-leaf canopy (plane-parallel scenes) */
@@ -341,6 +343,14 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
     S->emitter_d = vnormalize(V(d->emitter_direction[0], d->emitter_direction[1], d->emitter_direction[2]));
     if (d->bsdf_type == ERTB_BSDF_OCEAN_LEGACY)
         if (ocean_init(&S->ocean, d->bsdf_params)) return fail("ocean_legacy init failed");
+    S->astro = d->emitter_angular_diameter > 0.0;
+    if (S->astro) { /* astroobject.cpp:75-80 */
+        if (!(d->emitter_angular_diameter < 180.0)) return fail("Invalid angular diameter specified! (must be in ]0, 180[)");
+        if (d->n_instances > 0 || d->has_patch || d->integrator == ERTB_INTEGRATOR_VOLPATHMIS)
+            return fail("astroobject: 1D scenes with the volpath / piecewise_volpath integrators only");
+        S->astro_cos = cos(0.5 * d->emitter_angular_diameter * PI / 180.0);
+        S->astro_omega = 2.0 * PI * (1.0 - S->astro_cos);
+    }
     if (d->bsdf_type == ERTB_BSDF_MQDIFFUSE &&
         (!d->bsdf_table || d->bsdf_table_res[0] < 1 || d->bsdf_table_res[1] < 1 || d->bsdf_table_res[2] < 1))
         return fail("mqdiffuse: missing table");
@@ -898,7 +908,8 @@ static void leaf_eval_mueller(const scene_t *S, int leaf, v3 wi, v3 wo, mueller_
 }
 
 /* blendphase.cpp:172-190 with Mueller-valued components */
-static void phase_eval_mueller(const scene_t *S, int layer, v3 wi, v3 wo, mueller_t *M) {
+static void phase_eval_mueller_pdf(const scene_t *S, int layer, v3 wi, v3 wo, mueller_t *M, double *pdf) {
+    *pdf = 0.0;
     *M = mu_zero();
     for (int i = 0; i < S->desc->n_phase; ++i) {
         double w = leaf_prob(S, i, layer);
@@ -906,6 +917,7 @@ static void phase_eval_mueller(const scene_t *S, int layer, v3 wi, v3 wo, muelle
         mueller_t Mi; double pi_;
         leaf_eval_mueller(S, i, wi, wo, &Mi, &pi_);
         for (int k = 0; k < 16; ++k) M->m[k] += w * Mi.m[k];
+        *pdf += w * pi_;
     }
 }
 /* sample(): direction from the leaf's scalar sampler, weight = Mueller value / pdf
@@ -1298,14 +1310,41 @@ static frame_t surface_frame(const scene_t *S, const si_t *si) {
 
 static int target_medium(v3 n, v3 d) { return vdot(d, n) > 0.0 ? 0 : 1; } /* interaction.h:318-332 */
 
+/* volpath.cpp:567-572 */
+static double mis_weight(double pdf_a, double pdf_b) {
+    pdf_a *= pdf_a; pdf_b *= pdf_b;
+    double w = pdf_a / (pdf_a + pdf_b);
+    return w == w ? w : 0.0; /* detach(select(isfinite(w), w, 0)) */
+}
+/* Direction towards the emitter, its density and the emitter value / density: directional.cpp:171-201
+ * (delta: *pdf = 0 flags it) or astroobject.cpp:141-175 (warp::square_to_uniform_cone about the axis,
+ * warp.h:474-497; pdf = 1 / omega, weight = E / omega / pdf = E). */
+static v3 emitter_direction_sample(const scene_t *S, double u1, double u2, double *pdf) {
+    v3 axis = vneg(S->emitter_d);
+    *pdf = 0.0;
+    if (!S->astro) return axis;
+    double x, y;
+    ertbo_square_to_uniform_disk_concentric(u1, u2, &x, &y);
+    double pn = x * x + y * y, omc = 1.0 - S->astro_cos;
+    double z = S->astro_cos + omc * (1.0 - pn);
+    double f = pn > 0.0 ? safe_sqrt((1.0 - z * z) / pn) : 0.0;
+    frame_t fr = make_frame(axis);
+    *pdf = 1.0 / S->astro_omega;
+    return vnormalize(to_world(&fr, V(x * f, y * f, z)));
+}
+/* astroobject.cpp:111-124 eval for a ray leaving the scene along `d`; :206-215 pdf_direction */
+static double astro_eval(const scene_t *S, v3 d) {
+    return S->astro && vdot(d, vneg(S->emitter_d)) > S->astro_cos ? S->desc->irradiance / S->astro_omega : 0.0;
+}
+
 /* volpath.cpp:400-554 sample_emitter: ratio tracking toward the directional emitter.
  * `ref_n` is the zero vector for medium interactions. */
 static double sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n, int medium,
-                             counters_t *C, v3 *ds_d) {
+                             counters_t *C, v3 *ds_d, double *ds_pdf) {
     const ertb_scene_desc *D = S->desc;
-    (void) next_1d(rng); (void) next_1d(rng); /* next_2d consumed, volpath.cpp:407 */
-    /* directional.cpp:171-201 */
-    v3 d = S->emitter_d;
+    double e1 = next_1d(rng), e2 = next_1d(rng); /* next_2d, volpath.cpp:407 */
+    /* directional.cpp:171-201 / astroobject.cpp:141-175 */
+    v3 d = vneg(emitter_direction_sample(S, e1, e2, ds_pdf));
     v3 c = V(D->bsphere_center[0], D->bsphere_center[1], D->bsphere_center[2]);
     double brad = fmax(RAY_EPS, D->bsphere_radius * (1.0 + RAY_EPS));
     double radius = fmax(brad, vnorm(vsub(ref_p, c)));
@@ -1368,10 +1407,10 @@ static double sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n, i
 /* piecewise_volpath.cpp:404-527 sample_emitter: one exact transmittance evaluation per medium
  * segment instead of ratio tracking. */
 static double pw_sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n, int medium,
-                                counters_t *C, v3 *ds_d) {
+                                counters_t *C, v3 *ds_d, double *ds_pdf) {
     const ertb_scene_desc *D = S->desc;
-    (void) next_1d(rng); (void) next_1d(rng); /* next_2d, piecewise_volpath.cpp:413 */
-    v3 d = S->emitter_d; /* directional.cpp:171-201 */
+    double e1 = next_1d(rng), e2 = next_1d(rng); /* next_2d, piecewise_volpath.cpp:413 */
+    v3 d = vneg(emitter_direction_sample(S, e1, e2, ds_pdf)); /* directional.cpp:171-201 / astroobject.cpp:141-175 */
     v3 c = V(D->bsphere_center[0], D->bsphere_center[1], D->bsphere_center[2]);
     double brad = fmax(RAY_EPS, D->bsphere_radius * (1.0 + RAY_EPS));
     double radius = fmax(brad, vnorm(vsub(ref_p, c)));
@@ -1424,6 +1463,25 @@ static double pw_medium_step(const scene_t *S, pcg32 *rng, const ray_t *ray, si_
 
 /* volpath.cpp:93-396 (mono, unpolarized).  mis != 0 selects the volpathmis.cpp
  * Russian-roulette placement (:227-231), the only difference left in mono. */
+/* BSDF::pdf of the ground (only needed for MIS against a non-delta emitter: astroobject scenes, no canopy) */
+static double surf_pdf(const scene_t *S, v3 wi, v3 wo) {
+    if (!(wi.z > 0.0 && wo.z > 0.0)) return 0.0;
+    const int type = S->desc->bsdf_type;
+    if (type == ERTB_BSDF_OCEAN_LEGACY) return ocean_pdf(&S->ocean, wi.x, wi.y, wi.z, wo.x, wo.y, wo.z);
+    if (type == ERTB_BSDF_OCEAN_MISHCHENKO || type == ERTB_BSDF_OCEAN_GRASP) {
+        double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
+        return glint_pdf(&S->glint, a, b);
+    }
+    return INV_PI * wo.z; /* warp::square_to_cosine_hemisphere_pdf */
+}
+/* volpath.cpp:328-346: a ray that leaves the scene looks at the environment emitter (astroobject).  Direct for
+ * camera rays and specular chains, MIS-weighted against the emitter sampling of the last event otherwise. */
+static double astro_hit(const scene_t *S, v3 d, uint64_t depth, int specular_chain, double last_pdf) {
+    double em = astro_eval(S, d);
+    if (em == 0.0) return 0.0;
+    return (depth == 0 || specular_chain) ? em : em * mis_weight(last_pdf, 1.0 / S->astro_omega);
+}
+
 static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium0, counters_t *C) {
     const ertb_scene_desc *D = S->desc;
     const int mis = D->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
@@ -1434,6 +1492,8 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
     uint64_t depth = 0;
     si_t si; si.t = INFINITY; si.shape = -1; si.group = -1; si.p = si.n = V(0, 0, 0);
     int needs_intersection = 1, last_event_was_null = 0;
+    int specular_chain = 1;  /* volpath.cpp:113 (hide_emitters = false) */
+    double last_pdf = 0.0;   /* last_scatter_direction_pdf */
 
     for (;;) {
         /* ---- termination, volpath.cpp:189-202 ---- */
@@ -1488,16 +1548,20 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
             C->n_scatter++;
             throughput *= mei.sigma_s / (mei.sigma_t / mei.combined);
             v3 ds_d;
-            double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, mei.p, V(0, 0, 0), medium, C, &ds_d);
+            double ds_pdf;
+            double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, mei.p, V(0, 0, 0), medium, C, &ds_d, &ds_pdf);
             double pv, ppdf;
             phase_eval_pdf(S, mei.layer, mei.wi, ds_d, &pv, &ppdf);
-            result += throughput * pv * emitted; /* mis_weight(1, 0) = 1 for a delta emitter */
+            /* mis_weight(ds.pdf, select(ds.delta, 0, phase_pdf)): 1 for a delta emitter */
+            result += throughput * pv * emitted * (ds_pdf > 0.0 ? mis_weight(ds_pdf, ppdf) : 1.0);
+            specular_chain = 0; /* :276-277 */
             v3 wo; double pw, pp;
             double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
             phase_sample(S, mei.layer, mei.wi, s1, u1, u2, &wo, &pw, &pp);
             if (pp > 0.0) {
                 ray = spawn_ray(mei.p, V(0, 0, 0), wo);
                 needs_intersection = 1;
+                last_pdf = pp;
                 throughput *= pw;
             }
         }
@@ -1505,6 +1569,8 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
         /* ---- surfaces, :312-389 ---- */
         active_surface |= escaped;
         if (active_surface && needs_intersection) si = scene_intersect(S, &ray);
+        if (S->astro && active_surface && !(si.t < INFINITY))
+            result += throughput * astro_hit(S, ray.d, depth, specular_chain, last_pdf);
         active_surface = active_surface && si.t < INFINITY;
         if (active_surface) {
             frame_t fr = si.shape == SHAPE_LEAF ? make_frame(si.n) : surface_frame(S, &si);
@@ -1517,13 +1583,17 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
                 C->n_surface++;
                 if (depth + 1 < max_depth) { /* :349-363 */
                     v3 ds_d;
-                    double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, si.p, si.n, medium, C, &ds_d);
+                    double ds_pdf;
+                    double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, si.p, si.n, medium, C, &ds_d, &ds_pdf);
                     v3 wo = to_local(&fr, ds_d);
-                    result += throughput * surf_eval(S, &si, wi, wo) * emitted;
+                    result += throughput * surf_eval(S, &si, wi, wo) * emitted *
+                              (ds_pdf > 0.0 ? mis_weight(ds_pdf, surf_pdf(S, wi, wo)) : 1.0);
                 }
                 double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
                 v3 wo;
                 throughput *= surf_sample(S, &si, wi, s1, u1, u2, &wo);
+                if (S->astro) last_pdf = surf_pdf(S, wi, wo); /* bs.pdf, :383 */
+                specular_chain = 0; /* every ground BSDF here is smooth, :387 */
                 wo_world = to_world(&fr, wo);
                 depth++;
             }
@@ -1604,6 +1674,8 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, int medi
     uint64_t depth = 0;
     si_t si; si.t = INFINITY; si.shape = -1; si.group = -1; si.p = si.n = V(0, 0, 0);
     int needs_intersection = 1, last_event_was_null = 0;
+    int specular_chain = 1;
+    double last_pdf = 0.0;
 
     for (;;) {
         int any_nz = 0;
@@ -1658,22 +1730,31 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, int medi
             C->n_scatter++;
             T = mu_scale(&T, mei.sigma_s / (mei.sigma_t / mei.combined));
             v3 ds_d;
-            double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, mei.p, V(0, 0, 0), medium, C, &ds_d);
+            double ds_pdf;
+            double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, mei.p, V(0, 0, 0), medium, C, &ds_d, &ds_pdf);
             mueller_t P;
-            phase_eval_mueller(S, mei.layer, mei.wi, ds_d, &P);
+            double ppdf;
+            phase_eval_mueller_pdf(S, mei.layer, mei.wi, ds_d, &P, &ppdf);
             mueller_t TP = mu_mul(&T, &P);
-            for (int i = 0; i < 4; ++i) result[i] += TP.m[4 * i] * emitted; /* * depolarizer(E): column 0 */
+            const double wm = ds_pdf > 0.0 ? mis_weight(ds_pdf, ppdf) : 1.0;
+            for (int i = 0; i < 4; ++i) result[i] += TP.m[4 * i] * emitted * wm; /* * depolarizer(E): column 0 */
+            specular_chain = 0;
             v3 wo; mueller_t W; double pp;
             double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
             phase_sample_mueller(S, mei.layer, mei.wi, s1, u1, u2, &wo, &W, &pp);
             if (pp > 0.0) {
                 ray = spawn_ray(mei.p, V(0, 0, 0), wo);
                 needs_intersection = 1;
+                last_pdf = pp;
                 T = mu_mul(&T, &W);
             }
         }
         active_surface |= escaped;
         if (active_surface && needs_intersection) si = scene_intersect(S, &ray);
+        if (S->astro && active_surface && !(si.t < INFINITY)) { /* depolarizer(E / omega): column 0 of T */
+            const double em = astro_hit(S, ray.d, depth, specular_chain, last_pdf);
+            for (int i = 0; i < 4; ++i) result[i] += T.m[4 * i] * em;
+        }
         active_surface = active_surface && si.t < INFINITY;
         if (active_surface) {
             frame_t fr = surface_frame(S, &si);
@@ -1686,12 +1767,14 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, int medi
                 C->n_surface++;
                 if (depth + 1 < max_depth) {
                     v3 ds_d;
-                    double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, si.p, si.n, medium, C, &ds_d);
+                    double ds_pdf;
+                    double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, si.p, si.n, medium, C, &ds_d, &ds_pdf);
                     v3 wo = to_local(&fr, ds_d);
                     mueller_t B, TB;
                     bsdf_eval_mueller(S, &fr, wi, wo, &B);
                     TB = mu_mul(&T, &B);
-                    for (int i = 0; i < 4; ++i) result[i] += TB.m[4 * i] * emitted;
+                    const double wm = ds_pdf > 0.0 ? mis_weight(ds_pdf, surf_pdf(S, wi, wo)) : 1.0;
+                    for (int i = 0; i < 4; ++i) result[i] += TB.m[4 * i] * emitted * wm;
                 }
                 double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
                 v3 wo;
@@ -1704,6 +1787,8 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, int medi
                     Dw.m[0] = w; /* depolarizer(w) */
                 }
                 T = mu_mul(&T, &Dw);
+                if (S->astro) last_pdf = surf_pdf(S, wi, wo);
+                specular_chain = 0;
                 wo_world = to_world(&fr, wo);
                 depth++;
             }

@@ -140,6 +140,26 @@ def battery() -> dict:
                                        surface={"type": "mqdiffuse", "grid": mq_table(9, 13, 7)},
                                        sensor={"type": "mdistant", "vza": [-50.0, -20.0, 20.0, 50.0], "vaa": 140.0,
                                                "target": [2.0e5, 3.0e5, 6.3679007e6]}),
+        # astroobject: a solar disc instead of the delta directional emitter (next-event directions in a cone, the
+        # disc seen directly by unscattered primary rays)
+        "astro_wide_disc_afgl_rpv_pp": S(geometry="plane_parallel", n_layers=100, sza=50.0, saa=30.0,
+                                         angular_diameter=12.0, sensor=VZA5),
+        "astro_sun_aerosol_tab_spherical": S(n_layers=120, sza=35.0, aerosol=True, aerosol_phase="tabphase",
+                                             angular_diameter=0.5358,
+                                             sensor={"type": "mdistant", "vza": [-60.0, -20.0, 20.0, 60.0], "vaa": 0.0}),
+        "astro_piecewise_ocean_grasp_pp": S(geometry="plane_parallel", n_layers=80, integrator="piecewise_volpath",
+                                            sza=30.0, angular_diameter=6.0,
+                                            surface={"type": "ocean_grasp", "wavelength": 550.0, "wind_speed": 3.0,
+                                                     "water_body_reflectance": 0.01},
+                                            sensor={"type": "mdistant", "vza": [-45.0, -30.0, -15.0, 30.0], "vaa": 0.0}),
+        "astro_direct_beam_from_ground_spherical": S(
+            n_layers=100, sza=40.0, saa=0.0, angular_diameter=0.5358, surface={"type": "diffuse", "reflectance": 0.2},
+            sensor={"type": "mradiancemeter", "medium": {"type": "ref", "id": "medium_atmosphere"},
+                    # a sun photometer at the ground: disc centre, inside near the limb, the aureole just outside,
+                    # and the zenith sky
+                    "origins": [[0.0, 0.0, scenes.EARTH_RADIUS + 1.0]] * 4,
+                    "directions": [list(scenes.angles_to_direction(40.0, 0.0)), list(scenes.angles_to_direction(40.2, 0.0)),
+                                   list(scenes.angles_to_direction(40.4, 0.0)), [0.0, 0.0, 1.0]]}),
         # polarized (Stokes) transport: rayleigh_polarized / tabphase_polarized + stokes integrator
         "polarized_rayleigh_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=30.0, stokes=True,
                                    phase={"type": "rayleigh_polarized", "depolarization": 0.0279},
@@ -174,6 +194,10 @@ def battery() -> dict:
                                     phase={"type": "rayleigh_polarized"},
                                     surface={"type": "mqdiffuse", "grid": mq_table()},
                                     sensor={"type": "mdistant", "vza": [-55.0, -25.0, 15.0, 45.0], "vaa": 100.0}),
+        "polarized_astro_mishchenko_pp": S(geometry="plane_parallel", n_layers=60, sza=40.0, saa=0.0, stokes=True,
+                                           phase={"type": "rayleigh_polarized"}, angular_diameter=3.0,
+                                           surface={"type": "ocean_mishchenko", "wind_speed": 2.0, "eta": 1.33},
+                                           sensor={"type": "mdistant", "vza": [-50.0, -40.0, -30.0, 20.0], "vaa": 0.0}),
         # BASELINE C5 at reduced size: polarized ocean + molecular + polarized aerosol, one band of the sweep
         "c5_polarized_ocean_aerosol_reduced": scenes.config_c5(spp=16, n_vza=4, w_nm=865.0, n_layers=120),
         # integrator options

@@ -167,6 +167,28 @@ def test_multiphase_without_mis_accepts_any_component():
     assert np.allclose(w[0], 0.25) and np.allclose(w[1], 0.75)
 
 
+def test_astroobject_emitter_conventions():
+    """ERP/emitters/astroobject.cpp:54-108: `direction` / to_world * z points TOWARDS the object (the opposite of
+    `directional`), default diameter 0.5358 deg, diameter validated in ]0, 180[."""
+    sun = scenes.angles_to_direction(30.0, 40.0)
+    a = mi_load_dict(scenes.atmosphere_scene(sza=30.0, saa=40.0, angular_diameter=1.5, n_layers=4)).flat.build_desc()
+    b = mi_load_dict(scenes.atmosphere_scene(sza=30.0, saa=40.0, n_layers=4)).flat.build_desc()
+    assert np.allclose(list(a.emitter_direction), -sun, atol=1e-12)  # the direction light travels, as `directional`
+    assert np.allclose(list(a.emitter_direction), list(b.emitter_direction), atol=1e-12)
+    assert a.emitter_angular_diameter == 1.5 and b.emitter_angular_diameter == 0.0
+    d = scenes.atmosphere_scene(n_layers=4, angular_diameter=1.0)
+    d["illumination"] = {"type": "astroobject", "direction": list(sun)}
+    c = mi_load_dict(d).flat.build_desc()
+    assert np.allclose(list(c.emitter_direction), -sun, atol=1e-12) and c.emitter_angular_diameter == 0.5358
+    for bad in (0.0, 180.0):
+        d["illumination"]["angular_diameter"] = bad
+        with pytest.raises(RuntimeError, match="Invalid angular diameter"):
+            mi_load_dict(d)
+    d["illumination"] = {"type": "astroobject", "direction": list(sun), "to_world": np.eye(4)}
+    with pytest.raises(RuntimeError, match="Only one of the parameters"):
+        mi_load_dict(d)
+
+
 def test_piecewise_volpath_needs_a_piecewise_medium():
     # only ERP/media/piecewise.cpp overrides the *_real interface (medium.cpp:99-118); the scene is
     # flattened at load time here, so the reference's render-time error surfaces from mi_load_dict
@@ -260,7 +282,7 @@ def test_desc_struct_layout_is_stable():
     assert C.sizeof(_abi.RenderStats) == 56
     assert C.sizeof(_abi.SensorDesc) == 360
     assert C.sizeof(_abi.LeafGroupDesc) == 56
-    assert C.sizeof(_abi.SceneDesc) == 736
+    assert C.sizeof(_abi.SceneDesc) == 744
     assert _abi.SceneDesc.patch_rect.offset + 32 == _abi.SceneDesc.bsdf_table.offset == 712
     assert _abi.SceneDesc.bsdf_table_res.offset == 720
 

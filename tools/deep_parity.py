@@ -19,7 +19,8 @@ NAMES = ["c2_afgl_rpv_spherical", "afgl_rpv_pp", "thick_isotropic_pp", "ocean_pp
 # SURVEY 8f-4 plugins added last (glint family, mqdiffuse, multiphase); DEEP_NAMES=new selects only these
 NEW = ["ocean_mishchenko_pp", "ocean_grasp_spherical", "maignan_pp", "polarized_mishchenko_pp", "polarized_grasp_spherical",
        "polarized_maignan_pp", "mqdiffuse_pp", "mqdiffuse_spherical_thick", "polarized_mqdiffuse_pp",
-       "multiphase_three_components_pp"]
+       "multiphase_three_components_pp", "astro_wide_disc_afgl_rpv_pp", "astro_sun_aerosol_tab_spherical",
+       "astro_piecewise_ocean_grasp_pp", "astro_direct_beam_from_ground_spherical", "polarized_astro_mishchenko_pp"]
 sel = os.environ.get("DEEP_NAMES", "")
 NAMES = NEW if sel == "new" else (sel.split(",") if sel else NAMES + NEW)
 bad = 0
@@ -27,7 +28,7 @@ B = battery()
 for name in NAMES:
     sc = mi_load_dict(B[name])
     d = sc.flat.build_desc()
-    heavy = name.startswith(("c3_", "aerosol"))
+    heavy = name.startswith(("c3_", "aerosol", "astro_sun_aerosol"))
     ospp = 1 << ((17 if heavy else 20) + int(os.environ.get("DEEP", "0")))
     t0 = time.perf_counter()
     ostokes = None
