@@ -210,6 +210,9 @@ def run_cuda(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, in front of the one JSON line of the contract
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     if rank == 0:
         g.build_cuda()

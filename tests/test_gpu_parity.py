@@ -634,6 +634,41 @@ def test_render_matches_oracle_fixture(name):
         assert np.isclose(st["n_surface"] / st["n_paths"], gold["surface_per_path"], rtol=0.05, atol=0.01)
 
 
+@pytest.mark.parametrize("name", [
+    "c2_afgl_rpv_spherical", "afgl_rpv_pp", "thick_isotropic_pp", "rtls_rb_spherical", "ocean_pp", "ocean_mishchenko_pp",
+    "ocean_grasp_spherical", "maignan_pp", "mqdiffuse_spherical_thick", "multiphase_three_components_pp",
+    "c3_afgl_aerosol_tab_hdistant", "volpathmis_thick",
+])
+def test_register_kernel_matches_oracle_fixture(name, monkeypatch):
+    """The register-resident kernel (csrc/ertb_kernel.cuh: one path per lane; the fallback when a scene's tables
+    leave no shared memory for the pools, selectable with ERTB_KERNEL=legacy) against the same fixtures."""
+    monkeypatch.setenv("ERTB_KERNEL", "legacy")
+    gold = GOLDEN["scenes"][name]
+    sc = mi_load_dict(battery()[name])
+    heavy = gold["trips_main_per_path"] + gold["trips_nee_per_path"] > 100
+    spp = 1 << (16 if heavy else 19)
+    wl, mean, var, st = gpu_render(sc, spp, seed=31)
+    z = z_scores(mean, var, np.array(gold["mean"]), np.array(gold["var_of_mean"]), rel_floor=2e-6)
+    ok, zc = sidak_ok(z)
+    assert ok and np.all(np.abs(z) <= 4.5), f"{name}: |z| max {np.abs(z).max():.2f}\n gpu {mean}\n cpu {gold['mean']}"
+    # this kernel walks with the single global majorant, as the reference does: same trip counts as the oracle
+    k_gpu = (st["trips_main"] + st["trips_nee"]) / st["n_paths"]
+    k_cpu = gold["trips_main_per_path"] + gold["trips_nee_per_path"]
+    assert 0.55 * k_cpu - 3.0 <= k_gpu <= k_cpu + 0.05
+    assert np.isclose(st["n_scatter"] / st["n_paths"], gold["scatter_per_path"], rtol=0.05, atol=0.01)
+
+
+def test_register_kernel_is_really_selected(monkeypatch):
+    """Same seed, two kernels: the estimates differ in their noise (different consumption of the random streams),
+    so an identical film would mean the knob is ignored."""
+    sc = mi_load_dict(battery()["afgl_rpv_pp"])
+    _, m_pool, _, _ = gpu_render(sc, 1 << 14, seed=5)
+    monkeypatch.setenv("ERTB_KERNEL", "legacy")
+    _, m_reg, v_reg, _ = gpu_render(sc, 1 << 14, seed=5)
+    assert not np.array_equal(m_pool, m_reg)
+    assert np.all(np.abs(m_pool - m_reg) < 6.0 * np.sqrt(2.0 * v_reg))
+
+
 @pytest.mark.parametrize("name", ["c3_afgl_aerosol_tab_hdistant", "aerosol_hg_blend_pp", "polarized_aerosol_tab_pp"])
 def test_banded_and_global_majorant_agree(name, monkeypatch):
     """Profiles with a thin dense layer are walked with a banded majorant (ertb_kernel_pool.cuh): same
