@@ -995,9 +995,9 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
             delete S;
             return set_error("Invalid angular diameter specified! (must be in ]0, 180[)");
         }
-        if (D->n_instances > 0 || D->has_patch || D->integrator == ERTB_INTEGRATOR_VOLPATHMIS) {
+        if (D->n_instances > 0 || D->has_patch) {
             delete S;
-            return set_error("astroobject: 1D scenes with the volpath / piecewise_volpath integrators only");
+            return set_error("astroobject: 1D scenes only (no canopy, no central patch)");
         }
         S->astro_diameter = D->emitter_angular_diameter;
     }

@@ -248,7 +248,7 @@ typedef struct ertb_scene_desc {
     int32_t _pad5;
     /* ERP/emitters/astroobject.cpp:54-242: the light source is a uniform disc of this angular diameter (degrees,
      * in ]0, 180[) centred on -emitter_direction, radiating `irradiance` / solid angle; 0 = the delta
-     * `directional` emitter.  1D scenes, volpath / piecewise_volpath. */
+     * `directional` emitter.  1D scenes (no canopy / camera / central patch). */
     double emitter_angular_diameter;
 } ertb_scene_desc;
 

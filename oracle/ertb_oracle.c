@@ -346,8 +346,8 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
     S->astro = d->emitter_angular_diameter > 0.0;
     if (S->astro) { /* astroobject.cpp:75-80 */
         if (!(d->emitter_angular_diameter < 180.0)) return fail("Invalid angular diameter specified! (must be in ]0, 180[)");
-        if (d->n_instances > 0 || d->has_patch || d->integrator == ERTB_INTEGRATOR_VOLPATHMIS)
-            return fail("astroobject: 1D scenes with the volpath / piecewise_volpath integrators only");
+        if (d->n_instances > 0 || d->has_patch)
+            return fail("astroobject: 1D scenes only (no canopy, no central patch)");
         S->astro_cos = cos(0.5 * d->emitter_angular_diameter * PI / 180.0);
         S->astro_omega = 2.0 * PI * (1.0 - S->astro_cos);
     }
@@ -1310,9 +1310,12 @@ static frame_t surface_frame(const scene_t *S, const si_t *si) {
 
 static int target_medium(v3 n, v3 d) { return vdot(d, n) > 0.0 ? 0 : 1; } /* interaction.h:318-332 */
 
-/* volpath.cpp:567-572 */
+/* volpath.cpp:567-572 (power heuristic); volpathmis.cpp:657-669 combines the two full-path densities as
+ * 1 / (p_a / f + p_b / f), i.e. the balance heuristic (`balance` != 0) */
+static int g_mis_balance = 0;
+#pragma omp threadprivate(g_mis_balance)
 static double mis_weight(double pdf_a, double pdf_b) {
-    pdf_a *= pdf_a; pdf_b *= pdf_b;
+    if (!g_mis_balance) { pdf_a *= pdf_a; pdf_b *= pdf_b; }
     double w = pdf_a / (pdf_a + pdf_b);
     return w == w ? w : 0.0; /* detach(select(isfinite(w), w, 0)) */
 }
@@ -1494,6 +1497,7 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
     int needs_intersection = 1, last_event_was_null = 0;
     int specular_chain = 1;  /* volpath.cpp:113 (hide_emitters = false) */
     double last_pdf = 0.0;   /* last_scatter_direction_pdf */
+    g_mis_balance = mis;
 
     for (;;) {
         /* ---- termination, volpath.cpp:189-202 ---- */

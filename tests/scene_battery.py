@@ -152,6 +152,10 @@ def battery() -> dict:
                                             surface={"type": "ocean_grasp", "wavelength": 550.0, "wind_speed": 3.0,
                                                      "water_body_reflectance": 0.01},
                                             sensor={"type": "mdistant", "vza": [-45.0, -30.0, -15.0, 30.0], "vaa": 0.0}),
+        "astro_volpathmis_thick_hg_pp": S(geometry="plane_parallel", atmosphere="homogeneous", integrator="volpathmis",
+                                          homogeneous_sigma_t=2.0 / scenes.TOA, homogeneous_albedo=0.95,
+                                          phase={"type": "hg", "g": 0.6}, angular_diameter=8.0, sensor=VZA5,
+                                          surface={"type": "diffuse", "reflectance": 0.3}),
         "astro_direct_beam_from_ground_spherical": S(
             n_layers=100, sza=40.0, saa=0.0, angular_diameter=0.5358, surface={"type": "diffuse", "reflectance": 0.2},
             sensor={"type": "mradiancemeter", "medium": {"type": "ref", "id": "medium_atmosphere"},

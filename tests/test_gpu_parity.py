@@ -400,6 +400,33 @@ def test_canopy_leaf_optics_update_equals_fresh_scene():
     assert np.allclose(b, c, rtol=1e-9) and np.all(b < 0.8 * a)
 
 
+@pytest.mark.parametrize("surface,changes", [
+    # the parameters each plugin's traverse() publishes (ocean_mishchenko.cpp:118-123, ocean_grasp.cpp:147-153,
+    # maignan.cpp:103-109); `wavelength` of ocean_grasp is what Eradiate updates per spectral context
+    ({"type": "ocean_mishchenko", "wind_speed": 2.0, "eta": 1.33}, {"wind_speed": 9.0, "eta.value": 1.36}),
+    ({"type": "ocean_grasp", "wavelength": 550.0, "wind_speed": 12.0, "water_body_reflectance": 0.02},
+     {"wavelength": 865.0, "wind_speed.value": 14.0, "water_body_reflectance.value": 0.005, "eta.value": 1.329}),
+    ({"type": "maignan", "C": 5.0, "ndvi": 0.4}, {"C.value": 6.5, "ndvi.value": 0.2, "refr_re.value": 1.45}),
+])
+def test_glint_family_update_equals_fresh_scene(surface, changes):
+    """Updating the BSDF through the parameter table == loading a scene built with the new values (same seed:
+    identical films), and the update is not a no-op."""
+    mk = lambda srf: mi_load_dict(scenes.atmosphere_scene(  # noqa: E731
+        geometry="plane_parallel", n_layers=40, sza=35.0, surface=srf,
+        sensor={"type": "mdistant", "vza": [-45.0, -35.0, -20.0, 30.0], "vaa": 0.0}))
+    sc = mk(surface)
+    w = mi_traverse(sc)
+    keys = {k.split(".bsdf.")[-1]: k for k in w.parameters.keys() if ".bsdf." in k}
+    spp = 1 << 14
+    a = render(sc, seed=4, spp=spp).raw["sum_l"].copy()
+    w.parameters.update({keys[k]: v for k, v in changes.items()})
+    b = render(sc, seed=4, spp=spp).raw["sum_l"].copy()
+    fresh = dict(surface)
+    fresh.update({k.replace(".value", ""): v for k, v in changes.items()})
+    c = render(mk(fresh), seed=4, spp=spp).raw["sum_l"]
+    assert np.allclose(b, c, rtol=1e-9) and not np.allclose(a, b, rtol=1e-3)
+
+
 def test_central_patch_surface_on_device():
     """CentralPatchSurface in the 3D kernel: same closed form the oracle is pinned on, and the patch BSDF is an
     updatable scene parameter (`<shape>.bsdf.bsdf_1.*`, _central_patch.py:228-243)."""
