@@ -1264,17 +1264,22 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
         if (c3d) return set_error("astroobject: not supported with a perspective camera or a canopy");
         use_pool = true;
     }
-    // general primary rays: the GEN instances of the pool kernel (compiled with statistics on)
-    const bool gen = !c3d && (hs.desc.type == ERTB_SENSOR_MPDISTANT || hs.desc.type == ERTB_SENSOR_MRADIANCEMETER);
-    if (gen) use_pool = true;
+    // general primary rays and the finite solar disc exist in the GEN instances of the pool kernel only
+    // (compiled with statistics on)
+    const bool gen_needed = !c3d && (hs.desc.type == ERTB_SENSOR_MPDISTANT || hs.desc.type == ERTB_SENSOR_MRADIANCEMETER ||
+                                     S->astro_diameter > 0.0);
+    if (gen_needed) use_pool = true;
     const int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK);
     const bool bands = S->base.n_bands > 1;
     size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol, bands && !pw) : (size_t) S->base.blob_bytes;
     if (use_pool && smem > (size_t) S->max_smem_optin) { // huge tables: fall back to the register kernel
-        if (pol || pw || S->astro_diameter > 0.0) return set_error("scene tables leave no shared memory for the path pools");
+        if (pol || pw || gen_needed) return set_error("scene tables leave no shared memory for the path pools");
         use_pool = false;
         smem = (size_t) S->base.blob_bytes;
     }
+    // ... and so do the plugins added after SURVEY 8a (glint family, mqdiffuse): the lean instances keep the
+    // instruction stream of the headline configurations free of them (the register and 3D kernels are general)
+    const bool gen = gen_needed || (use_pool && !c3d && S->bsdf_type >= ERTB_BSDF_OCEAN_MISHCHENKO);
     // (attribute + occupancy are queried once per kernel instantiation and table size, then cached)
 #define ERTB_OCC(KERNEL)                                                                              \
     do {                                                                                              \

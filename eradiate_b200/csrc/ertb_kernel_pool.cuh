@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                     acc_pix = pix_old; // (a lane holding another pixel's sums was flushed just above)
                     float r = FLD(PF_RES, slot);
                     float wr = FLD(PF_WRAY, slot);
-                    if (P.astro_radiance > 0.f && (FLDU(PF_FLAGS, slot) >> PFL_DEPTH_SHIFT) == 0u) {
+                    if (GEN && P.astro_radiance > 0.f && (FLDU(PF_FLAGS, slot) >> PFL_DEPTH_SHIFT) == 0u) {
                         // astroobject: a primary ray that left the scene without any event looks at the sky and
                         // sees the disc if it points into it (volpath.cpp:328-346, count_direct; throughput 1)
                         f3 dd = mk3(FLD(PF_DX, slot), FLD(PF_DY, slot), FLD(PF_DZ, slot));
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
             // emitter hit for scattered rays -- the same expectation as the reference's MIS pair (volpath.cpp:
             // 286-290, :336-343), whose second technique carries (pdf_scatter x solid angle)^2 of the weight.
             f3 sun_e = sun;
-            if (P.astro_omc > 0.f) {
+            if (GEN && P.astro_omc > 0.f) { // (astroobject scenes run in the GEN instances)
                 float ox, oy;
                 disk_concentric(pcg_float(rng), pcg_float(rng), ox, oy);
                 float pn = fmaf(ox, ox, oy * oy);
@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                     depth++; // absorbed by the ground: not an escape (the astroobject direct view tests depth == 0)
                 } else {
                     float f_sun, weight;
-                    if (POL && bsdf_is_mueller(P.bsdf_type)) {
+                    if (POL && bsdf_is_mueller_t<GEN>(P.bsdf_type)) {
                         // Mueller-valued BSDF (polarized Fresnel matrix): ocean_legacy.cpp:561-661,
                         // ocean_mishchenko.cpp:228-296, ocean_grasp.cpp:354-455, maignan.cpp:105-166
                         f3 fs, ft;
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                         if (depth + 1u < P.max_depth) {
                             f3 ws = mk3(dot3(sun_e, fs), dot3(sun_e, ft), dot3(sun_e, n0));
                             if (ws.z > 0.f) {
-                                lf_eval_mueller(P, false, wi, ws, fs, ft, n0, Mb);
+                                lf_eval_mueller<GEN>(P, false, wi, ws, fs, ft, n0, Mb);
 #pragma unroll
                                 for (int r = 0; r < 4; ++r)
                                     v[r] = fmaf(T[4 * r], Mb[0], fmaf(T[4 * r + 1], Mb[4], fmaf(T[4 * r + 2], Mb[8], T[4 * r + 3] * Mb[12])));
@@ -657,11 +657,11 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                         for (int k = 0; k < 3; ++k) qn[k] = v[k + 1] * inv;
                         float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
                         f3 wo;
-                        if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) oc_sample(P, wi, s1, u1, u2, wo);
+                        if (!GEN || P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) oc_sample(P, wi, s1, u1, u2, wo);
                         else wo = gl_sample_dir(P, wi, s1, u1, u2);
                         float Tn[16];
                         if (wo.z > 0.f) { // the weight BSDF::sample returns, as a matrix
-                            lf_eval_mueller(P, true, wi, wo, fs, ft, n0, Mb);
+                            lf_eval_mueller<GEN>(P, true, wi, wo, fs, ft, n0, Mb);
                             mueller_mul(T, Mb, Tn);
                         } else {
 #pragma unroll
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                         weight = thr != 0.f ? __fdividef(T[0], thr) : 0.f; // so that thr * weight = T00 below
                         if (!(weight > 0.f)) weight = 0.f;
                     } else {
-                    surface_interact<SPH>(P, n0, sun_e, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
+                    surface_interact<SPH, POL, GEN>(P, n0, sun_e, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
                     wnee = thr * f_sun * P.irradiance;
                     if (POL) {
                         // depolarizer(f): the NEE Stokes vector is T[:,0] * f * E; then T <- T * depolarizer(w)

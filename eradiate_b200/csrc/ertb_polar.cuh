@@ -158,12 +158,13 @@ __device__ __forceinline__ void stokes_output_rotation(const ErtbParams &P, f3 d
 // `weight`: return the weight BSDF::sample gives for the sampled `wo` instead (eval / pdf for the two-lobe
 // oceans, F G / G1 for ocean_mishchenko, C F for maignan).
 // `wi`, `wo` local (wi = si.wi, wo = towards the light / sampled), (fs, ft, n) = shading frame.
+template <bool GENERAL = true>
 __device__ __forceinline__ void lf_eval_mueller(const ErtbParams &P, bool weight, f3 wi, f3 wo, f3 fs, f3 ft, f3 n, float *M) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) M[i] = 0.f;
     if (!(wi.z > 0.f && wo.z > 0.f)) return;
     float g, dep;
-    if (P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
+    if (!GENERAL || P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) {
         const float *tdn = P.ocean_tables, *tup = P.ocean_tables + ERTB_OC_RES * ERTB_OC_RES;
         float wc = P.bsdf[OC_WHITECAP], ul = 0.f;
         if (P.bsdf[OC_UNDERLIGHT_ON] != 0.f)
