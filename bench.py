@@ -81,7 +81,7 @@ def ncu_issue(kernel_ms, sm_mhz, n_sm):
         peak = n_sm * 4 * float(sm_mhz) * 1e6 / 1e9
         return {"achieved": achieved, "peak": peak, "unit": "G warp-inst/s", "frac": achieved / peak,
                 "active_lanes_per_inst": lanes,
-                "note": "instruction count of one C2 launch from profiles/r01k (ncu), time measured live"}
+                "note": "instruction count of one C2 launch from profiles/r01x (ncu), time measured live"}
     except Exception:
         return None
 
