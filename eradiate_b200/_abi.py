@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -169,7 +169,7 @@ class SceneDesc(C.Structure):
         ("patch_rect", C.c_double * 4),
         ("bsdf_table", c_float_p),
         ("bsdf_table_res", C.c_int32 * 3),
-        ("_pad5", C.c_int32),
+        ("phase_mis", C.c_int32),
         ("emitter_angular_diameter", C.c_double),
     ]
 

@@ -259,7 +259,7 @@ struct ertb_scene {
     float irradiance = 1.f;
     int integrator = 0, rr_depth = 5;
     long long max_depth = -1;
-    int polarized = 0, meridian_align = 0;
+    int polarized = 0, meridian_align = 0, phase_mis = 0;
     std::vector<HostSensor> sensors;
 
     // derived / device state
@@ -729,6 +729,7 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
         P.astro_radiance = (float) ((double) S->irradiance / (2.0 * M_PI * omc));
     }
     P.polarized = S->polarized;
+    P.phase_mis = S->phase_mis;
     P.meridian_align = S->meridian_align;
     P.mis = S->integrator == ERTB_INTEGRATOR_VOLPATHMIS;
     P.rr_depth = (unsigned) S->rr_depth;
@@ -1024,6 +1025,7 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
     S->rr_depth = D->rr_depth;
     S->max_depth = D->max_depth;
     S->polarized = D->polarized != 0;
+    S->phase_mis = D->phase_mis != 0 && D->has_medium && D->n_phase > 1;
     S->meridian_align = D->meridian_align != 0;
     if (S->polarized && D->integrator == ERTB_INTEGRATOR_VOLPATHMIS) {
         delete S;
@@ -1264,10 +1266,11 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
         if (c3d) return set_error("astroobject: not supported with a perspective camera or a canopy");
         use_pool = true;
     }
+    if (S->phase_mis && c3d) return set_error("multiphase with use_mis: not supported with a perspective camera or a canopy");
     // general primary rays and the finite solar disc exist in the GEN instances of the pool kernel only
     // (compiled with statistics on)
     const bool gen_needed = !c3d && (hs.desc.type == ERTB_SENSOR_MPDISTANT || hs.desc.type == ERTB_SENSOR_MRADIANCEMETER ||
-                                     S->astro_diameter > 0.0);
+                                     S->astro_diameter > 0.0 || S->phase_mis);
     if (gen_needed) use_pool = true;
     const int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK);
     const bool bands = S->base.n_bands > 1;

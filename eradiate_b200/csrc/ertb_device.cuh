@@ -124,6 +124,7 @@ struct ErtbParams {
     float astro_omc, astro_sin2, astro_radiance; // 1 - cos a, sin^2 a, irradiance / solid angle
     // integrator
     int polarized;    // Mueller/Stokes transport (scalar_mono_polarized variant)
+    int phase_mis;    // multiphase.cpp:176-200: mixture weight of a sampled direction (GEN instances of the pool kernel)
     int meridian_align; // stokes.cpp: output basis in the meridian plane
     float sensor_up[3]; // else: sensor world_transform * (0, 1, 0)
     int mis;          // volpathmis Russian-roulette placement
@@ -338,6 +339,12 @@ __device__ __forceinline__ float leaf_eval(const float *tb, const ErtbPhaseLeaf 
         case ERTB_PHASE_HG: return hg_eval(L.p0, ct);                // hg.cpp:92-99
         default: return tab_eval(tb, L, ct) * ERTB_INV_TWO_PI;       // tabphase.cpp:107-118
     }
+}
+
+// pdf of one leaf at the physics-convention cosine: the value, except for (depolarized) Rayleigh (rayleigh.cpp:97-107)
+__device__ __forceinline__ float leaf_pdf(const float *tb, const ErtbPhaseLeaf &L, float ct) {
+    if (L.type == ERTB_PHASE_RAYLEIGH || L.type == ERTB_PHASE_RAYLEIGH_POLARIZED) return rayleigh_pdf(ct);
+    return leaf_eval(tb, L, ct);
 }
 
 // sample one leaf: returns ct (physics convention), weight = value/pdf, pdf

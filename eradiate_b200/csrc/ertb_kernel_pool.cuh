@@ -780,7 +780,28 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                             if (POL) {
                                 // weight = Mueller value / pdf (rayleigh_polarized.cpp:155-157), T <- T * W
                                 float W[16], pp, Tn[16];
-                                leaf_mueller(tb, P.leaf[leaf], wi_w, d, W, pp);
+                                if (GEN && P.phase_mis) {
+                                    // multiphase.cpp:176-200: mixture value / mixture pdf over all leaves
+#pragma unroll
+                                    for (int k = 0; k < 16; ++k) W[k] = 0.f;
+                                    pp = 0.f;
+                                    float prev = 0.f;
+                                    for (int i = 0; i < P.n_phase; ++i) {
+                                        float cum = (i < P.n_phase - 1) ? tb[P.off_cumw + i * P.n_layers + l] : 1.f;
+                                        float w = cum - prev;
+                                        prev = cum;
+                                        if (w > 0.f) {
+                                            float Mi[16], pi_;
+                                            leaf_mueller(tb, P.leaf[i], wi_w, d, Mi, pi_);
+#pragma unroll
+                                            for (int k = 0; k < 16; ++k) W[k] = fmaf(w, Mi[k], W[k]);
+                                            pp = fmaf(w, pi_, pp);
+                                        }
+                                    }
+                                    if (!(pp > 1e-8f)) pp = 0.f;
+                                } else {
+                                    leaf_mueller(tb, P.leaf[leaf], wi_w, d, W, pp);
+                                }
                                 float ip = pp > 0.f ? __fdividef(1.f, pp) : 0.f;
 #pragma unroll
                                 for (int k = 0; k < 16; ++k) W[k] *= ip;
@@ -789,6 +810,19 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                                 for (int k = 0; k < 16; ++k) T[k] = Tn[k];
                                 thr = T[0];
                             } else {
+                                if (GEN && P.phase_mis) { // multiphase.cpp:176-200: mixture value / mixture pdf
+                                    float num = 0.f, den = 0.f, prev = 0.f;
+                                    for (int i = 0; i < P.n_phase; ++i) {
+                                        float cum = (i < P.n_phase - 1) ? tb[P.off_cumw + i * P.n_layers + l] : 1.f;
+                                        float w = cum - prev;
+                                        prev = cum;
+                                        if (w > 0.f) {
+                                            num = fmaf(w, leaf_eval(tb, P.leaf[i], ct), num);
+                                            den = fmaf(w, leaf_pdf(tb, P.leaf[i], ct), den);
+                                        }
+                                    }
+                                    pw = den > 1e-8f ? __fdividef(num, den) : 0.f;
+                                }
                                 thr *= pw;
                             }
                         }

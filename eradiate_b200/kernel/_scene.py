@@ -1072,6 +1072,7 @@ class FlatScene:
     def phase_leaves(self, n: int):
         """Flatten the blendphase tree: list of (leaf node, probability[n])."""
         leaves: list[tuple[PhaseFunction, np.ndarray]] = []
+        self._phase_mis = False
 
         def walk(ph: PhaseFunction, prob: np.ndarray):
             if ph.type == "blendphase":
@@ -1096,9 +1097,16 @@ class FlatScene:
                             else float(leaf.children["depolarization"].layer_values().flat[0])
                         if leaf.type in ("rayleigh_polarized", "tabphase_polarized") or \
                                 (leaf.type == "rayleigh" and dep != 0.0):
-                            raise RuntimeError(
-                                "multiphase: use_mis=True is only supported for components whose value equals their "
-                                f"pdf (got '{leaf.type}'); pass use_mis=False")
+                            # the mixture weight differs from the leaf's own: carried by the kernels (`phase_mis`)
+                            # when the multiphase node is the medium's phase function and its components are leaves
+                            flat_children = all(ph.children[f"phase{i}"].type not in ("blendphase", "multiphase")
+                                                for i in range(k))
+                            if ph is not self.medium.children["phase_function"] or not flat_children:
+                                raise RuntimeError(
+                                    "multiphase: use_mis=True over components whose value differs from their pdf "
+                                    f"(got '{leaf.type}') is only supported for a non-nested multiphase node; "
+                                    "pass use_mis=False")
+                            self._phase_mis = True
                 for i in range(k):
                     walk(ph.children[f"phase{i}"], prob * (ws[i] / total))
             else:
@@ -1197,6 +1205,7 @@ class FlatScene:
             d.homogeneous = int(self.homogeneous)
             leaves = self.phase_leaves(n)
             d.n_phase = len(leaves)
+            d.phase_mis = int(getattr(self, "_phase_mis", False))
             w = np.ascontiguousarray(np.stack([p for _, p in leaves]).astype(np.float32))
             keep.append(w)
             d.phase_weight = w.ctypes.data_as(_abi.c_float_p)

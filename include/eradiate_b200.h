@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 14
+#define ERTB_ABI_VERSION 15
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -245,7 +245,10 @@ typedef struct ertb_scene_desc {
      * (mqdiffuse.cpp:80-86); copied at scene creation, not updatable (the plugin exposes no parameter) */
     const float *bsdf_table;
     int32_t bsdf_table_res[3];      /* x, y, z */
-    int32_t _pad5;
+    /* ERP/phase/multiphase.cpp:176-200 (`use_mis`, root node only): the weight of a sampled direction is the mixture
+     * sum_j w_j value_j / sum_j w_j pdf_j over all leaves instead of the drawn leaf's own weight.  Only set when
+     * that differs (a leaf whose value is not its pdf: depolarized Rayleigh, Mueller-valued phase functions). */
+    int32_t phase_mis;
     /* ERP/emitters/astroobject.cpp:54-242: the light source is a uniform disc of this angular diameter (degrees,
      * in ]0, 180[) centred on -emitter_direction, radiating `irradiance` / solid angle; 0 = the delta
      * `directional` emitter.  1D scenes (no canopy / camera / central patch). */

@@ -812,6 +812,14 @@ static void phase_sample(const scene_t *S, int layer, v3 wi, double s1, double u
     leaf_sample(S, leaf, u1, u2, &wl, weight, pdf);
     frame_t f = make_frame(wi); /* medium.cpp:51 sh_frame = Frame3f(wi) */
     *wo = to_world(&f, wl);
+    if (S->desc->phase_mis && n > 1) {
+        /* multiphase.cpp:176-200: value and pdf of every component at the sampled direction;
+         * weight = sum_j w_j value_j / sum_j w_j pdf_j, pdf = the mixture pdf */
+        double v, p;
+        phase_eval_pdf(S, layer, wi, *wo, &v, &p);
+        *weight = p > 1e-8 ? v / p : 0.0;
+        *pdf = p;
+    }
 }
 
 
@@ -951,6 +959,12 @@ static void phase_sample_mueller(const scene_t *S, int layer, v3 wi, double s1, 
     } else {
         *pdf = p_scalar;
         *W = mu_identity(w_scalar);
+    }
+    if (S->desc->phase_mis && n > 1) { /* multiphase.cpp:176-200 with Spectrum = Mueller matrix */
+        mueller_t M; double pm;
+        phase_eval_mueller_pdf(S, layer, wi, *wo, &M, &pm);
+        *W = pm > 1e-8 ? mu_scale(&M, 1.0 / pm) : mu_zero();
+        *pdf = pm;
     }
 }
 

@@ -131,6 +131,15 @@ def battery() -> dict:
                         surface={"type": "maignan", "C": 5.0, "ndvi": 0.4, "refr_re": 1.5, "refr_im": 0.0},
                         sensor={"type": "mdistant", "vza": [-60.0, -40.0, 0.0, 30.0, 60.0], "vaa": 10.0}),
         "multiphase_three_components_pp": multiphase_scene(),
+        # multiphase with use_mis over components whose value is not their pdf: the mixture weight is carried by the
+        # kernels (phase_mis)
+        "multiphase_mis_depolarized_rayleigh_pp": S(
+            geometry="plane_parallel", atmosphere="homogeneous", homogeneous_sigma_t=1.5 / scenes.TOA,
+            homogeneous_albedo=0.97, sensor=VZA5, sza=40.0, surface={"type": "diffuse", "reflectance": 0.1},
+            phase={"type": "multiphase", "use_mis": True,
+                   "phase0": {"type": "rayleigh", "depolarization": 0.25}, "weight0": 2.0,
+                   "phase1": {"type": "hg", "g": 0.75}, "weight1": 1.0,
+                   "phase2": {"type": "isotropic"}, "weight2": 0.5}),
         "mqdiffuse_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=25.0,
                           surface={"type": "mqdiffuse", "grid": mq_table()},
                           sensor={"type": "mdistant", "vza": [-60.0, -30.0, 0.0, 30.0, 60.0], "vaa": 70.0}),
@@ -202,6 +211,13 @@ def battery() -> dict:
                                            phase={"type": "rayleigh_polarized"}, angular_diameter=3.0,
                                            surface={"type": "ocean_mishchenko", "wind_speed": 2.0, "eta": 1.33},
                                            sensor={"type": "mdistant", "vza": [-50.0, -40.0, -30.0, 20.0], "vaa": 0.0}),
+        "polarized_multiphase_mis_pp": S(
+            geometry="plane_parallel", atmosphere="homogeneous", homogeneous_sigma_t=1.0 / scenes.TOA,
+            homogeneous_albedo=0.95, stokes=True, sza=45.0, saa=20.0, surface={"type": "diffuse", "reflectance": 0.05},
+            sensor={"type": "mdistant", "vza": [-60.0, -25.0, 10.0, 50.0], "vaa": 60.0},
+            phase={"type": "multiphase", "use_mis": True,
+                   "phase0": {"type": "rayleigh_polarized", "depolarization": 0.03}, "weight0": 1.0,
+                   "phase1": {"type": "hg", "g": 0.6}, "weight1": 1.0}),
         # BASELINE C5 at reduced size: polarized ocean + molecular + polarized aerosol, one band of the sweep
         "c5_polarized_ocean_aerosol_reduced": scenes.config_c5(spp=16, n_vza=4, w_nm=865.0, n_layers=120),
         # integrator options

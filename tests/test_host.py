@@ -151,12 +151,24 @@ def test_multiphase_flattens_like_the_equivalent_blend_tree():
 @pytest.mark.parametrize("phase,match", [
     ({"type": "multiphase", "phase0": {"type": "isotropic"}, "weight0": 1.0}, "At least 2 child phase functions"),
     ({"type": "multiphase", "phase0": {"type": "isotropic"}, "weight0": 1.0, "phase1": {"type": "hg"}}, "weight1"),
-    ({"type": "multiphase", "phase0": {"type": "isotropic"}, "weight0": 1.0,
-      "phase1": {"type": "rayleigh", "depolarization": 0.03}, "weight1": 1.0}, "use_mis=False"),
+    # the mixture weight is only carried for a non-nested multiphase node
+    ({"type": "blendphase", "weight": 0.5, "phase_0": {"type": "isotropic"},
+      "phase_1": {"type": "multiphase", "phase0": {"type": "isotropic"}, "weight0": 1.0,
+                  "phase1": {"type": "rayleigh", "depolarization": 0.03}, "weight1": 1.0}}, "use_mis=False"),
 ])
 def test_multiphase_load_errors(phase, match):
     with pytest.raises(RuntimeError, match=match):
         mi_load_dict(scenes.atmosphere_scene(phase=phase, geometry="plane_parallel", n_layers=4)).flat.build_desc()
+
+
+def test_multiphase_mis_flag():
+    """`phase_mis` is set only when the mixture weight differs from the drawn component's own weight."""
+    mk = lambda ph: mi_load_dict(scenes.atmosphere_scene(  # noqa: E731
+        phase=ph, geometry="plane_parallel", n_layers=4)).flat.build_desc()
+    base = {"type": "multiphase", "phase0": {"type": "hg", "g": 0.3}, "weight0": 1.0}
+    assert mk({**base, "phase1": {"type": "rayleigh"}, "weight1": 1.0}).phase_mis == 0
+    assert mk({**base, "phase1": {"type": "rayleigh", "depolarization": 0.03}, "weight1": 1.0}).phase_mis == 1
+    assert mk({**base, "use_mis": False, "phase1": {"type": "rayleigh", "depolarization": 0.03}, "weight1": 1.0}).phase_mis == 0
 
 
 def test_multiphase_without_mis_accepts_any_component():

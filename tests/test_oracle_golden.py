@@ -703,3 +703,4 @@ def test_multiphase_mixture_eval(oracle, weight, g):
     assert np.isclose(vals[0], inv_four_pi) and np.isclose(vals[1], inv_four_pi * (1 - g) / (1 + g) ** 2)
     expected = weight * inv_four_pi + (1 - weight) * inv_four_pi * (1.0 - g) / (1.0 + g) ** 2
     assert np.isclose(w[0] * vals[0] + w[1] * vals[1], expected, rtol=1e-6)
+

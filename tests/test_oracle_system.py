@@ -243,3 +243,24 @@ def test_astroobject_small_disc_matches_directional(oracle):
     _, m1, v1, _ = run(oracle, scenes.atmosphere_scene(angular_diameter=0.5358, **kw), spp, seed=9)
     z = (m1 - m0) / np.sqrt(v0 + v1)
     assert np.all(np.abs(z) < 4.0), z
+
+
+def test_multiphase_mis_same_expectation(oracle):
+    """multiphase.cpp:176-200: with use_mis the weight of a sampled direction is the mixture ratio
+    sum_j w_j value_j / sum_j w_j pdf_j instead of the drawn component's own weight.  Both are unbiased: a thick
+    medium whose components include a strongly depolarized Rayleigh lobe (value != pdf) renders to the same
+    radiance either way, and the two estimators really differ (different noise for the same seed)."""
+    def scene(use_mis):
+        return scenes.atmosphere_scene(
+            geometry="plane_parallel", atmosphere="homogeneous", homogeneous_sigma_t=2.0 / scenes.TOA,
+            homogeneous_albedo=0.98, sza=40.0, surface={"type": "diffuse", "reflectance": 0.1},
+            sensor={"type": "mdistant", "vza": [-60.0, 0.0, 45.0], "vaa": 0.0},
+            phase={"type": "multiphase", "use_mis": use_mis,
+                   "phase0": {"type": "rayleigh", "depolarization": 0.4}, "weight0": 2.0,
+                   "phase1": {"type": "hg", "g": 0.7}, "weight1": 1.0})
+    spp = 150000
+    _, m0, v0, _ = run(oracle, scene(False), spp, seed=6)
+    _, m1, v1, _ = run(oracle, scene(True), spp, seed=6)
+    z = (m1 - m0) / np.sqrt(v0 + v1)
+    assert np.all(np.abs(z) < 4.0), z
+    assert not np.allclose(m0, m1, rtol=1e-9)
