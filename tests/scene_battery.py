@@ -251,6 +251,13 @@ def battery() -> dict:
                                        sensor={"type": "mdistant", "vza": [-60.0, -20.0, 0.0, 35.0, 70.0], "vaa": 40.0}),
         "canopy_volpath_afgl_rpv_pp": S(geometry="plane_parallel", n_layers=100, w_nm=670.0, sza=30.0, canopy=CANOPY,
                                         sensor=VZA5),
+        # the 3D kernel is general: late-plugin ground BSDFs under a canopy (table lookup / glint in the local frame)
+        "canopy_mqdiffuse_ground_pp": S(geometry="plane_parallel", n_layers=60, sza=35.0, saa=40.0, canopy=CANOPY,
+                                        surface={"type": "mqdiffuse", "grid": mq_table()}, sensor=VZA5),
+        "canopy_ocean_grasp_ground_pp": S(geometry="plane_parallel", n_layers=60, sza=30.0, canopy=dict(CANOPY, seed=5),
+                                          surface={"type": "ocean_grasp", "wavelength": 550.0, "wind_speed": 8.0,
+                                                   "water_body_reflectance": 0.03},
+                                          sensor={"type": "mdistant", "vza": [-45.0, -30.0, 0.0, 30.0], "vaa": 0.0}),
         "canopy_piecewise_aerosol_pp": S(geometry="plane_parallel", n_layers=120, integrator="piecewise_volpath",
                                          aerosol=True, aerosol_phase="hg", sza=50.0, saa=120.0,
                                          canopy=dict(CANOPY, orientation="planophile", seed=9), sensor=VZA5),
