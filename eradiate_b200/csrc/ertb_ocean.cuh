@@ -1,4 +1,5 @@
-// ertb_ocean.cuh -- ocean_legacy BSDF (6SV ocean model) for the sm_100a path tracer.
+// ertb_ocean.cuh -- the local-frame BSDFs of the sm_100a path tracer: ocean_legacy (6SV ocean model) first, then
+// (end of the file) the isotropic-Beckmann glint family -- ocean_mishchenko, ocean_grasp, maignan -- and mqdiffuse.
 //
 // Reference: ERP/bsdfs/ocean_legacy.cpp (update :313-372, glint :405-447, underlight
 // :449-491, sample :494-559, eval :561-661, pdf :663-713),

@@ -1,5 +1,6 @@
 /*
- * ertb_oracle_ocean.c -- CPU oracle: ocean_legacy BSDF (6SV ocean model).
+ * ertb_oracle_ocean.c -- CPU oracle: ocean_legacy BSDF (6SV ocean model); second half of the file: the
+ * isotropic-Beckmann glint family (ocean_mishchenko, ocean_grasp, maignan).
  * TEST INFRASTRUCTURE (see ertb_oracle.c).  Restates, in scalar double C:
  *   ERP/bsdfs/ocean_legacy.cpp:137-243  eval_ocean_transmittance (64x64 Gauss-Legendre)
  *   ERP/bsdfs/ocean_legacy.cpp:313-372  update(); :384-393 whitecaps; :405-447 glint;
