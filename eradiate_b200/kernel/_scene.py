@@ -808,6 +808,7 @@ class _Loader:
         it.kernel_type = inner["type"]
         it.max_depth = int(inner.get("max_depth", -1))
         it.rr_depth = int(inner.get("rr_depth", 5))
+        it.hide_emitters = bool(inner.get("hide_emitters", False))  # MI/src/render/integrator.cpp:29
         if it.max_depth < 0 and it.max_depth != -1:
             raise RuntimeError(
                 '"max_depth" must be set to -1 (infinite) or a value >= 0'
@@ -869,6 +870,10 @@ class FlatScene:
             raise RuntimeError(f"exactly one directional emitter is supported, got {len(emitters)}")
         self.emitter = emitters[0]
         self.integrator = sc.integrator()
+        if getattr(self.emitter, "angular_diameter", 0.0) > 0.0 and getattr(self.integrator, "hide_emitters", False):
+            # volpath.cpp:114, :333: hiding the emitter switches off the direct view of the disc AND the
+            # specular-chain rule; the kernels implement the default (hide_emitters = false) only
+            raise RuntimeError("astroobject: 'hide_emitters=True' is not supported")
 
         canopy = [s for s in shapes if s.type in ("shapegroup", "instance", "disk")]
         shapes = [s for s in shapes if s.type not in ("shapegroup", "instance", "disk")]

@@ -199,6 +199,14 @@ def test_astroobject_emitter_conventions():
     d["illumination"] = {"type": "astroobject", "direction": list(sun), "to_world": np.eye(4)}
     with pytest.raises(RuntimeError, match="Only one of the parameters"):
         mi_load_dict(d)
+    # the direct view of the disc follows the integrators' default hide_emitters = false (volpath.cpp:114, :333)
+    d = scenes.atmosphere_scene(n_layers=4, angular_diameter=1.0, moment=False)
+    d["integrator"]["hide_emitters"] = True
+    with pytest.raises(RuntimeError, match="hide_emitters"):
+        mi_load_dict(d)
+    d["illumination"]["type"] = "directional"  # irrelevant for a delta emitter (never hit)
+    del d["illumination"]["angular_diameter"]
+    mi_load_dict(d)
 
 
 def test_piecewise_volpath_needs_a_piecewise_medium():
