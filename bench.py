@@ -166,11 +166,12 @@ def run_reference(args):
         return  # other ranks exit 0 without work
     cores = os.cpu_count() or 1
     spp = 1 << 18  # bounded sample: 32 x 2^18 = 8.4 M paths per step (~1 s on 16 cores)
+    # n_threads is passed explicitly: torchrun exports OMP_NUM_THREADS=1 to every rank
     for _ in range(args.warmup):
-        time_cpu_oracle(1 << 12)
+        time_cpu_oracle(1 << 12, n_threads=cores)
     times = []
     for _ in range(args.steps):
-        mp, sec, _ = time_cpu_oracle(spp)
+        mp, sec, _ = time_cpu_oracle(spp, n_threads=cores)
         times.append(sec)
     ms = 1e3 * float(np.mean(times))
     value = N_VZA * spp / (ms * 1e-3) / 1e6
@@ -210,10 +211,19 @@ def run_cuda(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, in front of the one JSON line of the contract
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        # NCCL prints its version banner on stdout when it initialises (the GPU boxes export NCCL_DEBUG=VERSION),
+        # in front of the one JSON line of the contract: point fd 1 at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            warm = torch.zeros(1, device=f"cuda:{local_rank}")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     if rank == 0:
         g.build_cuda()
     if world > 1:
@@ -367,7 +377,7 @@ def run_cuda(args):
         if world == 1 and args.config == "c2":
             cores = os.cpu_count() or 1
             cpu_spp = 1 << 19  # 16.8 M paths: ~15-30 core-seconds of the same workload
-            cpu_val, cpu_s, cpu_k = time_cpu_oracle(cpu_spp, repeats=2)
+            cpu_val, cpu_s, cpu_k = time_cpu_oracle(cpu_spp, repeats=2, n_threads=cores)
             line["cpu_baseline"] = {
                 "value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"C2 scene, 32 pixels x spp=2^19 = {N_VZA * cpu_spp} paths, best of 2, "
