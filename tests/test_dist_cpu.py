@@ -140,3 +140,27 @@ def test_two_rank_gloo_sharded_mi_render_equals_single(tmp_path, oracle, shard):
     want = np.stack([res[c.si.as_hashable][s].raw["sum_l"] for c in ctxs for s in ("measure", "measure_2")])
     assert got.shape == want.shape and np.allclose(got, want, rtol=1e-12)
     assert not np.allclose(want[0], want[1])  # the two sensors of a context got different seeds
+
+
+def test_reference_arm_under_torchrun_prints_one_line_and_uses_all_cores():
+    """bench.py --impl reference launched as the driver launches it for N > 1: rank 0 alone works and prints the
+    one JSON line, the other rank exits 0 silently, and the oracle runs on every host core although torchrun
+    exports OMP_NUM_THREADS=1 to its workers."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(root, "bench.py"),
+           "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["gpu_launches"] == 0
+    cores = os.cpu_count() or 1
+    assert d["cpu_baseline"]["cores"] == cores and d["cpu_baseline"]["kind"] == "port"
+    if cores >= 4:  # one thread manages ~0.7 Mpaths/s on this workload
+        assert d["value"] > 1.2, d["value"]
