@@ -111,7 +111,8 @@ def context_shard(n_items: int, rank: int, world: int) -> list[int]:
 
 def _render_items_gpu(mi_scene, plan, mine, seeds, spps, offsets=None):
     """This rank's items through the pipelined batch entry points (one device per rank)."""
-    dev = _device_scene(mi_scene.obj)
+    # the device of THIS rank (torchrun: set_device(LOCAL_RANK)), not device 0 of the box
+    dev = _device_scene(mi_scene.obj, torch.cuda.current_device())
     dev.batch_begin([plan[k][1] for k in mine])
     last_ctx = None
     for k in mine:

@@ -74,6 +74,8 @@ class DeviceScene:
         handle = C.c_void_p()
         _lib.check(self.lib.ertb_scene_create(C.byref(self.desc), device, C.byref(handle)))
         self.handle = handle
+        self._batch = None
+        self._batch_open = False
         self._mark_clean()
 
     def _nodes(self):
@@ -89,10 +91,47 @@ class DeviceScene:
     def _mark_clean(self):
         for n in self._nodes():
             n.dirty = False
+            n.dirty_names.clear()
+
+    # (plugin kind, value name) pairs ``ertb_scene_update`` can refresh in place; everything else the
+    # parameter table publishes (medium ``scale``, the ``nodes`` of irregular / polarized tabulated phase
+    # functions, sensor and emitter geometry ...) is honoured by re-creating the device scene from the
+    # updated graph -- slower, never silently stale (Mitsuba's ``parameters_changed`` accepts all of them).
+    _IN_PLACE = {
+        ("volume", "data"), ("volume", "value"), ("texture", "value"),
+        ("phase", "values"), ("phase", "g"), ("phase", "depolarization"),
+        ("phase", "m11"), ("phase", "m12"), ("phase", "m22"), ("phase", "m33"), ("phase", "m34"), ("phase", "m44"),
+    }
+
+    def _needs_rebuild(self) -> bool:
+        for n in self._nodes():
+            for name in n.dirty_names:
+                if n.plugin_kind == "bsdf":  # every BSDF value is re-read by bsdf_params()
+                    continue
+                if (n.plugin_kind, name) not in self._IN_PLACE:
+                    return True
+        return False
+
+    def _rebuild(self) -> None:
+        """Re-create the device scene from the (updated) host graph."""
+        if getattr(self, "_batch", None) is not None and self._batch_open:
+            raise RuntimeError("a parameter that needs a scene rebuild was updated inside a pipelined batch")
+        self.scene._flat = None
+        self.flat = self.scene.flat
+        self.desc = self.flat.build_desc()
+        handle = C.c_void_p()
+        _lib.check(self.lib.ertb_scene_create(C.byref(self.desc), self.device, C.byref(handle)))
+        self.lib.ertb_scene_destroy(self.handle)
+        self.handle = handle
+        self.rebuilds = getattr(self, "rebuilds", 0) + 1
+        self._mark_clean()
 
     def sync(self) -> None:
         """Push updated parameters (``parameters_changed`` equivalent)."""
         if not any(n.dirty for n in self._nodes()):
+            return
+        if self._needs_rebuild():
+            self._rebuild()
             return
         flat, lib, h = self.flat, self.lib, self.handle
 
@@ -173,8 +212,10 @@ class DeviceScene:
     # -- pipelined contexts x sensors loop (ertb_batch_*) -------------------
     def batch_begin(self, sensors: list[int], with_stats: bool = False) -> None:
         arr = (C.c_int * len(sensors))(*sensors)
+        self.sync()  # (a pending rebuild must not happen inside the batch)
         _lib.check(self.lib.ertb_batch_begin(self.handle, len(sensors), arr, int(with_stats)))
         self._batch = (list(sensors), with_stats)
+        self._batch_open = True
 
     def batch_push(self, sensor: int, seed: int, spp: int, sample_offset: int = 0) -> None:
         """Snapshot the current parameters and queue one render; does not wait for it."""
@@ -184,6 +225,7 @@ class DeviceScene:
     def batch_end(self):
         """Wait for the queued renders. Returns ([accumulators[rows, npix] per item], [stats], ms)."""
         sensors, with_stats = self._batch
+        self._batch_open = False
         rows = 7 if self.flat.polarized else 3
         npix = [self.lib.ertb_sensor_pixel_count(self.handle, i) for i in sensors]
         out = np.zeros(rows * sum(npix), dtype=np.float64)
@@ -212,9 +254,20 @@ class DeviceScene:
             pass
 
 
+def _default_device() -> int:
+    """Device of a scene created without an explicit one: the calling process's current CUDA device when
+    torch is in use (one process per GPU: ``torch.cuda.set_device(LOCAL_RANK)``), else device 0."""
+    import sys
+
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+        return int(torch.cuda.current_device())
+    return 0
+
+
 def _device_scene(scene: _scene.Scene, device: int | None = None) -> DeviceScene:
     dev = getattr(scene, "_device_scene", None)
-    want = 0 if device is None else device
+    want = _default_device() if device is None else device
     if dev is None or (device is not None and dev.device != want):
         if dev is not None:
             dev.close()

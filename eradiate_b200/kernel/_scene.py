@@ -100,6 +100,7 @@ class Object:
         self.children: dict[str, Object] = {}
         self.values: dict[str, t.Any] = {}
         self.dirty = True
+        self.dirty_names: set[str] = set()  # values changed since the device scene last synchronised
 
     def id(self) -> str:
         return self._id
@@ -122,6 +123,7 @@ class Object:
         else:
             self.values[name] = type(cur)(np.asarray(value).reshape(-1)[0])
         self.dirty = True
+        self.dirty_names.add(name)
 
     def __repr__(self):
         return f"{type(self).__name__}[type={self.type}, id={self._id!r}]"

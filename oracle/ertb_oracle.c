@@ -1302,7 +1302,17 @@ static double sensor_sample_ray(const scene_t *S, const ertb_sensor_desc *sd, do
 }
 
 /* ----------------------------------------------------------- integrator */
-typedef struct { uint64_t trips_main, trips_nee, n_scatter, n_surface; } counters_t;
+static uint64_t g_last_flights[2];
+/* trips_*: iterations of the reference's loops (volpath.cpp:170-393, :454-551), stencil crossings included.
+ * flights_*: free flights actually sampled (Medium::sample_interaction calls) -- the quantity a kernel that
+ * has no stencil-crossing iterations counts as its loop trips.  flights_nee counts only shadow rays that can
+ * contribute: a ray that ends on an opaque surface, or whose scattering value is zero, is walked by the
+ * reference for nothing (a kernel may cull it without changing any estimate). */
+typedef struct {
+    uint64_t trips_main, trips_nee, n_scatter, n_surface;
+    uint64_t flights_main, flights_nee;
+    uint64_t ray_flights; int ray_opaque; /* scratch: the shadow ray being walked */
+} counters_t;
 
 /* Shading frame of a surface hit: SurfaceInteraction::initialize_sh_frame
  * (MI/include/mitsuba/render/interaction.h:278-288) with the sphere's dp_du = (-y, x, 0) 2 pi
@@ -1374,6 +1384,7 @@ static double sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n, i
     double max_dist = ray.maxt, total_dist = 0.0, transmittance = 1.0;
     si_t si; si.t = INFINITY; si.shape = -1;
     int needs_intersection = 1, active = 1;
+    C->ray_flights = 0; C->ray_opaque = 0;
     while (active) {
         double remaining = max_dist - total_dist;
         ray.maxt = remaining;
@@ -1381,6 +1392,7 @@ static double sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n, i
         C->trips_nee++;
         int escaped = 0, active_medium = medium, active_surface = !medium;
         if (active_medium) {
+            C->ray_flights++;
             mei_t mei = sample_interaction(S, &ray, next_1d(rng));
             if (D->homogeneous && mei.t < INFINITY) ray.maxt = fmin(mei.t, remaining);
             if (needs_intersection) si = scene_intersect(S, &ray);
@@ -1411,6 +1423,7 @@ static double sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n, i
         if (active_surface) {
             /* eval_null_transmission: null.cpp -> 1, every other BSDF -> 0 */
             transmittance *= si.shape == SHAPE_TOA ? 1.0 : 0.0;
+            if (si.shape != SHAPE_TOA) C->ray_opaque = 1;
             ray = spawn_ray(si.p, si.n, ray.d);
             needs_intersection = 1;
         }
@@ -1439,6 +1452,7 @@ static double pw_sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n
     ray_t ray = spawn_ray_to(ref_p, ref_n, ds_p);
     double max_dist = ray.maxt, total_dist = 0.0, transmittance = 1.0;
     int active = 1;
+    C->ray_flights = 0; C->ray_opaque = 0;
     while (active) {
         double remaining = max_dist - total_dist;
         ray.maxt = remaining;
@@ -1453,10 +1467,12 @@ static double pw_sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n
             int hit = medium_aabb(S, &ray, &mint, &maxt);
             escaped = pw_eval_transmittance_pdf_real(S, &ray, si.t, hit, mint, maxt, &tr, &pdf);
             transmittance *= tr; /* "exact estimation" */
+            C->ray_flights++;
             active_medium = !escaped;
         }
         if (active_surface) {
             transmittance *= si.shape == SHAPE_TOA ? 1.0 : 0.0; /* eval_null_transmission */
+            if (si.shape != SHAPE_TOA) C->ray_opaque = 1;
             ray = spawn_ray(si.p, si.n, ray.d);
         }
         ray.maxt = remaining;
@@ -1532,11 +1548,13 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
         mei_t mei; memset(&mei, 0, sizeof mei);
 
         if (active_medium && pw) {
+            C->flights_main++;
             throughput *= pw_medium_step(S, rng, &ray, &si, &needs_intersection, &mei);
             escaped = !(mei.t < INFINITY);
             active_medium = mei.t < INFINITY;
             if (active_medium) { medium_scatter = 1; depth++; }
         } else if (active_medium) { /* :218-259 */
+            C->flights_main++;
             mei = sample_interaction(S, &ray, next_1d(rng));
             if (D->homogeneous && mei.t < INFINITY) ray.maxt = mei.t;
             if (needs_intersection) si = scene_intersect(S, &ray);
@@ -1572,6 +1590,7 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
             phase_eval_pdf(S, mei.layer, mei.wi, ds_d, &pv, &ppdf);
             /* mis_weight(ds.pdf, select(ds.delta, 0, phase_pdf)): 1 for a delta emitter */
             result += throughput * pv * emitted * (ds_pdf > 0.0 ? mis_weight(ds_pdf, ppdf) : 1.0);
+            if (!C->ray_opaque && throughput * pv > 0.0) C->flights_nee += C->ray_flights;
             specular_chain = 0; /* :276-277 */
             v3 wo; double pw, pp;
             double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
@@ -1604,8 +1623,9 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
                     double ds_pdf;
                     double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, si.p, si.n, medium, C, &ds_d, &ds_pdf);
                     v3 wo = to_local(&fr, ds_d);
-                    result += throughput * surf_eval(S, &si, wi, wo) * emitted *
-                              (ds_pdf > 0.0 ? mis_weight(ds_pdf, surf_pdf(S, wi, wo)) : 1.0);
+                    const double fv = surf_eval(S, &si, wi, wo);
+                    result += throughput * fv * emitted * (ds_pdf > 0.0 ? mis_weight(ds_pdf, surf_pdf(S, wi, wo)) : 1.0);
+                    if (!C->ray_opaque && throughput * fv > 0.0) C->flights_nee += C->ray_flights;
                 }
                 double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
                 v3 wo;
@@ -1716,12 +1736,14 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, int medi
         int escaped = 0, null_scatter = 0, medium_scatter = 0;
         mei_t mei; memset(&mei, 0, sizeof mei);
         if (active_medium && pw) {
+            C->flights_main++;
             T = mu_scale(&T, pw_medium_step(S, rng, &ray, &si, &needs_intersection, &mei));
             escaped = !(mei.t < INFINITY);
             active_medium = mei.t < INFINITY;
             if (active_medium) { medium_scatter = 1; depth++; }
         } else if (active_medium) {
-            mei = sample_interaction(S, &ray, next_1d(rng));
+C->flights_main++;
+                        mei = sample_interaction(S, &ray, next_1d(rng));
             if (D->homogeneous && mei.t < INFINITY) ray.maxt = mei.t;
             if (needs_intersection) si = scene_intersect(S, &ray);
             needs_intersection = 0;
@@ -1756,6 +1778,7 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, int medi
             mueller_t TP = mu_mul(&T, &P);
             const double wm = ds_pdf > 0.0 ? mis_weight(ds_pdf, ppdf) : 1.0;
             for (int i = 0; i < 4; ++i) result[i] += TP.m[4 * i] * emitted * wm; /* * depolarizer(E): column 0 */
+            if (!C->ray_opaque && TP.m[0] > 0.0) C->flights_nee += C->ray_flights;
             specular_chain = 0;
             v3 wo; mueller_t W; double pp;
             double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
@@ -1793,6 +1816,7 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, int medi
                     TB = mu_mul(&T, &B);
                     const double wm = ds_pdf > 0.0 ? mis_weight(ds_pdf, surf_pdf(S, wi, wo)) : 1.0;
                     for (int i = 0; i < 4; ++i) result[i] += TB.m[4 * i] * emitted * wm;
+                    if (!C->ray_opaque && TB.m[0] > 0.0) C->flights_nee += C->ray_flights;
                 }
                 double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
                 v3 wo;
@@ -1863,11 +1887,11 @@ int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, 
     v3 sensor_up;
     mat_apply_vec(sd->to_world, V(0, 1, 0), &sensor_up);
     if (sd->type == ERTB_SENSOR_MDISTANT || sd->type == ERTB_SENSOR_MRADIANCEMETER) sensor_up = V(0, 1, 0);
-    counters_t total = { 0, 0, 0, 0 };
+    counters_t total; memset(&total, 0, sizeof total);
 
 #pragma omp parallel
     {
-        counters_t C = { 0, 0, 0, 0 };
+        counters_t C; memset(&C, 0, sizeof C);
 #pragma omp for schedule(dynamic, 1)
         for (int64_t item = 0; item < n_items; ++item) {
             int64_t pix = item / (int64_t) chunks_per_pixel;
@@ -1906,6 +1930,7 @@ int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, 
         {
             total.trips_main += C.trips_main; total.trips_nee += C.trips_nee;
             total.n_scatter += C.n_scatter; total.n_surface += C.n_surface;
+            total.flights_main += C.flights_main; total.flights_nee += C.flights_nee;
         }
     }
     for (int64_t i = 0; i < npix; ++i) {
@@ -1921,9 +1946,13 @@ int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, 
         stats->trips_main = total.trips_main; stats->trips_nee = total.trips_nee;
         stats->n_scatter = total.n_scatter; stats->n_surface = total.n_surface;
     }
+    g_last_flights[0] = total.flights_main; g_last_flights[1] = total.flights_nee;
     scene_free(&S);
     return 0;
 }
+
+/* free flights sampled by the last ertbo_render* call: {main walk, contributing shadow rays} */
+void ertbo_last_flights(uint64_t out[2]) { out[0] = g_last_flights[0]; out[1] = g_last_flights[1]; }
 
 /* ------------------------------------------------------------ KAT entries */
 int ertbo_bsdf_eval(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo, double *out) {

@@ -29,6 +29,10 @@ int ertbo_render(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_
 int ertbo_render_stokes(const ertb_scene_desc *desc, int sensor, uint64_t seed, uint64_t spp,
                         uint64_t sample_offset, double *sum_wl, double *sum_l, double *sum_l2,
                         double *sum_stokes, ertb_render_stats *stats, int n_threads);
+/* Free flights sampled by the last ertbo_render / ertbo_render_stokes call: out[0] = main walk
+ * (Medium::sample_interaction calls of volpath.cpp:220), out[1] = shadow rays that can contribute
+ * (volpath.cpp:479; rays ending on an opaque surface or carrying a zero weight excluded). */
+void ertbo_last_flights(uint64_t out[2]);
 int ertbo_piecewise_sample(const ertb_scene_desc *desc, double half_width, size_t n, const double *o,
                            const double *d, const double *sample, const double *si_t, double *t,
                            double *tr, double *pdf);

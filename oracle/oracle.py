@@ -71,7 +71,16 @@ def render(desc: _abi.SceneDesc, sensor: int = 0, seed: int = 0, spp: int = 1024
             C.c_int(n_threads),
         )
     )
-    return out[0], out[1], out[2], stats.as_dict()
+    return out[0], out[1], out[2], _with_flights(stats.as_dict())
+
+
+def _with_flights(st: dict) -> dict:
+    """Adds the free-flight counts of the last render (what a kernel without stencil-crossing
+    iterations and with culled zero-weight shadow rays counts as its loop trips)."""
+    f = (C.c_uint64 * 2)()
+    load().ertbo_last_flights(f)
+    st["flights_main"], st["flights_nee"] = int(f[0]), int(f[1])
+    return st
 
 
 def render_stokes(desc: _abi.SceneDesc, sensor: int = 0, seed: int = 0, spp: int = 1024,
@@ -90,7 +99,7 @@ def render_stokes(desc: _abi.SceneDesc, sensor: int = 0, seed: int = 0, spp: int
             C.byref(stats), C.c_int(n_threads),
         )
     )
-    return out[0], out[1], out[2], st, stats.as_dict()
+    return out[0], out[1], out[2], st, _with_flights(stats.as_dict())
 
 
 def phase_mueller(desc, leaf, wi, wo):

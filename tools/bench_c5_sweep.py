@@ -33,8 +33,6 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     sc = mi_load_dict(scenes.config_c5(spp=args.spp))
-    from eradiate_b200.kernel._render import _device_scene
-    _device_scene(sc, local)
     mi_scene = mi_traverse(sc, scenes.spectral_update_map_c5(1200, True))
     ctxs = [KernelContext(w=w) for w in np.linspace(400.0, 1000.0, args.bands)]
     mi_render_sharded(mi_scene, ctxs[: 2 * world], spp=1 << 12, seed_state=SeedState(1))  # warm-up

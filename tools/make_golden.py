@@ -2,9 +2,9 @@
 Generates tests/golden/oracle_renders.json: per-pixel mean / variance-of-the-mean /
 loop-trip counters of the CPU oracle for the scene battery at a fixed seed.
 
-The reference itself cannot be imported or built in this environment,
-so these fixtures are outputs of the oracle restatement -- pinned separately against the
-reference's golden vectors by tests/test_oracle_golden.py and test_oracle_system.py.
+These fixtures are outputs of the oracle restatement -- pinned against the reference's golden
+vectors by tests/test_oracle_golden.py / test_oracle_system.py and against renders of the reference
+itself (oracle/_ref, tests/golden/reference_renders.json) by tests/test_oracle_vs_reference.py.
 Run:  python tools/make_golden.py [--only-missing]
 """
 import json
@@ -52,6 +52,10 @@ def main():
             "trips_nee_per_path": st["trips_nee"] / st["n_paths"],
             "scatter_per_path": st["n_scatter"] / st["n_paths"],
             "surface_per_path": st["n_surface"] / st["n_paths"],
+            # free flights actually sampled (no stencil-crossing iterations, no zero-weight shadow rays):
+            # what the CUDA kernels count as loop trips
+            "flights_main_per_path": st["flights_main"] / st["n_paths"],
+            "flights_nee_per_path": st["flights_nee"] / st["n_paths"],
         }
         if stokes is not None:
             out["scenes"][name]["stokes"] = (stokes / spp).tolist()
