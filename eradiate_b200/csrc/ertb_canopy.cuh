@@ -623,9 +623,9 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 // ---- next-event estimation (volpath.cpp:400-554): leaves and the ground are opaque to the
                 //      shadow ray, the medium attenuates it. The occlusion test is the second BVH walk. ----
                 phase = LP_SEGMENT;
-                if (STATS && nee > 0.f && !(in_medium && medium)) st_nee++; // a vacuum shadow ray is one loop trip
+                if (STATS && nee != 0.f && !(in_medium && medium)) st_nee++; // a vacuum shadow ray is one loop trip
                 if (!(sun.z > 0.f)) nee = 0.f; // the ground plane is in the way
-                if (nee > 0.f) {
+                if (nee != 0.f) { // (either sign: a BSDF such as RTLS may be negative at grazing angles)
                     double t1;
                     shadow = true;
                     T.H.inst = -1;

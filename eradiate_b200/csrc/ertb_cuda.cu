@@ -395,12 +395,39 @@ static int build_canopy(ertb_scene *S) {
 static size_t align4(size_t n) { return (n + 3) & ~size_t(3); }
 
 // Banded majorant (ertb_kernel_pool.cuh): cut the layer stack into <= ERTB_MAX_BANDS contiguous bands
-// minimising the expected number of loop trips of a vertical traverse,
+// minimising the expected cost of a vertical traverse in units of one loop trip,
 //     sum over bands (band majorant x band thickness)  +  ERTB_BAND_PENALTY x (number of bands),
-// i.e. tentative collisions plus one boundary stop per band. O(n^2 x bands) dynamic programme.
+// i.e. tentative collisions plus one boundary crossing per band (a crossing is handled inside the trip
+// that reaches it: one boundary distance, a fraction of a trip). O(n^2 x bands) dynamic programme.
+// Bands are used when the predicted cost of a traverse, 1 (the trip that ends the segment) + the sum
+// above, is below ERTB_BAND_MIN_GAIN x the same figure for the single global majorant.
 #define ERTB_MAX_BANDS 8
-#define ERTB_BAND_PENALTY 1.0
+#ifndef ERTB_BAND_PENALTY
+#define ERTB_BAND_PENALTY 0.1
+#endif
+#ifndef ERTB_BAND_MIN_GAIN
 #define ERTB_BAND_MIN_GAIN 0.5
+#endif
+// (developer knobs for A/B runs, read once: ERTB_BAND_PENALTY / ERTB_BAND_MIN_GAIN in the environment)
+static double env_double(const char *name, double dflt, double lo, double hi) {
+    const char *e = getenv(name);
+    if (!e) return dflt;
+    char *end = nullptr;
+    double v = strtod(e, &end);
+    return (end == e || !(v >= lo) || !(v <= hi)) ? dflt : v;
+}
+// developer tuning knobs (integers), clamped: a zero threshold would stall the persistent scheduler loop
+static int env_int_clamped(const char *name, int dflt, int lo, int hi) {
+    const char *e = getenv(name);
+    if (!e) return dflt;
+    char *end = nullptr;
+    long v = strtol(e, &end, 10);
+    if (end == e) return dflt;
+    return (int) (v < lo ? lo : (v > hi ? hi : v));
+}
+static double band_penalty() { static const double v = env_double("ERTB_BAND_PENALTY", ERTB_BAND_PENALTY, 0.0, 100.0); return v; }
+static double band_min_gain() { static const double v = env_double("ERTB_BAND_MIN_GAIN", ERTB_BAND_MIN_GAIN, 0.0, 10.0); return v; }
+
 static std::vector<int> choose_bands(const std::vector<double> &sigma, double dz) {
     const int n = (int) sigma.size();
     // candidate cut points: the layer edges with the largest jumps of log(sigma_t) plus a uniform
@@ -435,15 +462,13 @@ static std::vector<int> choose_bands(const std::vector<double> &sigma, double dz
             for (int i = j - 1; i >= 0; --i) { // band = layers [cand[i], cand[j])
                 mx = fmax(mx, segmax[i]);
                 if (cost[k - 1][i] >= INF) continue;
-                double c = cost[k - 1][i] + mx * dz * (cand[j] - cand[i]) + ERTB_BAND_PENALTY;
+                double c = cost[k - 1][i] + mx * dz * (cand[j] - cand[i]) + band_penalty();
                 if (c < cost[k][j]) { cost[k][j] = c; from[k][j] = i; }
             }
         }
     int best = 1;
     for (int k = 2; k <= ERTB_MAX_BANDS; ++k) if (cost[k][m - 1] < cost[best][m - 1] - 1e-12) best = k;
-    // a trip of the banded walk costs ~1.6x a trip of the plain one (measured on C2, where the programme
-    // finds 8.5 trips per path against 10.2 and the kernel is 30 % slower): bands must halve the trips
-    if (cost[best][m - 1] > ERTB_BAND_MIN_GAIN * cost[1][m - 1]) best = 1;
+    if (1.0 + cost[best][m - 1] > band_min_gain() * (1.0 + cost[1][m - 1])) best = 1;
     std::vector<int> starts(best);
     for (int k = best, j = m - 1; k >= 1; --k) { j = from[k][j]; starts[k - 1] = cand[j]; }
     return starts; // first layer of every band (starts[0] = 0)
@@ -577,9 +602,9 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
                 // (2) keep the previous cut while it still does (its majorants are re-derived below anyway).
                 double tau = 0.0, mxg = 0.0;
                 for (int i = 0; i < n; ++i) { tau += sg[i] * dz; mxg = fmax(mxg, sg[i]); }
-                const double cost_global = mxg * dz * n + ERTB_BAND_PENALTY;
+                const double cost_global = 1.0 + mxg * dz * n + band_penalty();
                 std::vector<int> starts(1, 0);
-                if (tau + 2.0 * ERTB_BAND_PENALTY < ERTB_BAND_MIN_GAIN * cost_global) {
+                if (1.0 + tau + 2.0 * band_penalty() < band_min_gain() * cost_global) {
                     bool reuse = false;
                     if (S->band_starts.size() > 1 && S->band_starts.back() < n) {
                         double c = 0.0;
@@ -587,9 +612,9 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
                             const int a = S->band_starts[k], b = k + 1 < S->band_starts.size() ? S->band_starts[k + 1] : n;
                             double mx = 0.0;
                             for (int i = a; i < b; ++i) mx = fmax(mx, sg[i]);
-                            c += mx * dz * (b - a) + ERTB_BAND_PENALTY;
+                            c += mx * dz * (b - a) + band_penalty();
                         }
-                        reuse = c < ERTB_BAND_MIN_GAIN * cost_global;
+                        reuse = 1.0 + c < band_min_gain() * cost_global;
                     }
                     starts = reuse ? S->band_starts : choose_bands(sg, dz);
                 }
@@ -609,6 +634,9 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
                         // (a band of vacuum gets a token majorant: its flights overshoot the band at once)
                         blob.push_back((float) (majorant / fmax(mx, 1e-6 * majorant)));
                     }
+                    blob.resize(align4(blob.size()), 0.f);
+                    P.off_band_iratio = (int) blob.size();
+                    for (int k = 0; k < nb; ++k) blob.push_back(1.f / blob[(size_t) P.off_band_ratio + k]);
                     blob.resize(align4(blob.size()), 0.f);
                 }
             }
@@ -1248,7 +1276,7 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     P.sample_offset = sample_offset;
     P.n_pixels = (unsigned) (hs.desc.width * hs.desc.height);
     P.tw = ERTB_TW;
-    if (const char *e = getenv("ERTB_TW")) P.tw = atoi(e); // tuning knob
+    P.tw = env_int_clamped("ERTB_TW", P.tw, 1, 32); // tuning knob
 
     // persistent grid: as many CTAs as can be resident (queried, not assumed)
     const bool sph = P.spherical;
@@ -1329,8 +1357,8 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     if (blocks_per_sm < 1) return set_error("render kernel cannot be resident on this device");
     if (use_pool) {
         P.tw = 32; P.twi = bands ? 8 : 16; // (banded walks lose lanes at band boundaries: keep stepping longer; C3 +4 %)
-        if (const char *e = getenv("ERTB_POOL_TW")) P.tw = atoi(e);
-        if (const char *e = getenv("ERTB_POOL_TWI")) P.twi = atoi(e);
+        P.tw = env_int_clamped("ERTB_POOL_TW", P.tw, 1, ERTB_POOL_NS);
+        P.twi = env_int_clamped("ERTB_POOL_TWI", P.twi, 1, 32);
     }
     // chunk: a few thousand paths, so that the queue hands out >> n_warps chunks
     const unsigned long long total = (unsigned long long) P.n_pixels * spp;
@@ -1362,7 +1390,7 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
 
     // small renders: do not spread the paths over more warps than can keep their pools busy
     unsigned long long warp_paths = use_pool ? ERTB_MIN_WARP_PATHS : 32ULL;
-    if (const char *e = getenv("ERTB_MIN_WARP_PATHS")) warp_paths = (unsigned long long) atoll(e);
+    warp_paths = (unsigned long long) env_int_clamped("ERTB_MIN_WARP_PATHS", (int) warp_paths, 32, 1 << 30);
     if (warp_paths < 32) warp_paths = 32;
     unsigned long long want_warps = (total + warp_paths - 1) / warp_paths;
     unsigned long long want_blocks = (want_warps * 32ULL + block - 1) / block;
@@ -1371,7 +1399,7 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
         // batch items share the device: with a fraction of the resident CTAs each, consecutive
         // items run side by side and the drain of one overlaps the bulk of the next
         int div = ERTB_BATCH_GRID_DIV;
-        if (const char *e = getenv("ERTB_BATCH_GRID_DIV")) div = atoi(e);
+        div = env_int_clamped("ERTB_BATCH_GRID_DIV", div, 1, 64);
         if (div > 1 && blocks_per_sm / div >= 1) grid = (unsigned long long) S->sm_count * (blocks_per_sm / div);
     }
     if (want_blocks < grid) grid = want_blocks ? want_blocks : 1;

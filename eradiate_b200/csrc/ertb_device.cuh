@@ -104,9 +104,9 @@ struct ErtbParams {
     int off_cumw;     // (n_phase-1) x n_layers cumulative leaf probabilities
     // banded majorant (pool kernel, BANDS instances): the layer stack is cut into n_bands altitude bands,
     // each with its own majorant. Blob: band_lo[n_bands + 1] (altitudes above the ground of the band
-    // boundaries), band_ratio[n_bands] (global majorant / band majorant)
+    // boundaries), band_ratio[n_bands] (global majorant / band majorant), band_iratio[n_bands] (its inverse)
     int n_bands;
-    int off_band_lo, off_band_ratio;
+    int off_band_lo, off_band_ratio, off_band_iratio;
     // piecewise medium (ertb_piecewise.cuh): sigma_t per layer, vertical optical depth above each of
     // the n_layers + 1 layer boundaries, layer thickness, optical depth above the ground level
     int piecewise;

@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(ERTB_BLOCK, ERTB_MINB) ertb_render_kernel(cons
                         d = normalize3(nd);
                         thr *= pw;
                     }
-                    mode = wnee > 0.f ? MODE_SETUP_NEE : MODE_SETUP_MAIN;
+                    mode = wnee != 0.f ? MODE_SETUP_NEE : MODE_SETUP_MAIN; // (a BSDF may be negative: rtls.cpp)
                 }
             } else if (phase == PHASE_SURFACE && mode == MODE_EV_SURFACE) {
                 // ---- volpath.cpp:344-389 ----
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(ERTB_BLOCK, ERTB_MINB) ertb_render_kernel(cons
                     thr *= weight;
                     depth++;
                     last_null = false;
-                    mode = wnee > 0.f ? MODE_SETUP_NEE : MODE_SETUP_MAIN;
+                    mode = wnee != 0.f ? MODE_SETUP_NEE : MODE_SETUP_MAIN; // (a BSDF may be negative: rtls.cpp)
                 }
             }
         }

@@ -101,29 +101,33 @@ __device__ __forceinline__ int band_of(const ErtbParams &P, const float *tb, flo
     return bi;
 }
 
+// Distance along the segment (h0, b) at which a record in band `bi` leaves it. `down`: the record is
+// descending; cleared when a spherical ray passes its perigee inside the band (it then leaves through the
+// band's top). Spherical shell: the boundary at altitude hk is met where s (s + 2 b) = c,
+// c = (hk - h0)(hk + h0 + 2 R) -- the cancellation-free roots of segment_setup.
 template <bool SPH>
 __device__ __forceinline__ float band_exit(const ErtbParams &P, const float *tb, float h0, float b, int bi, bool &down,
                                            float smax) {
     const float *lo = tb + P.off_band_lo;
     if (down) {
-        const float hk = bi > 0 ? lo[bi] : 0.f; // band 0 ends at the ground
+        const float hk = lo[bi]; // (lo[0] = 0: band 0 ends at the ground)
         if (SPH) {
-            float c = (h0 - hk) * (2.f * P.R + h0 + hk);
-            float disc = fmaf(b, b, -c);
-            if (disc >= 0.f) return bi > 0 ? fminf(fmaxf(__fdividef(c, fast_sqrt(disc) - b), 0.f), smax) : smax;
-            down = false; // perigee inside this band: it is left through its top
+            const float c = (hk - h0) * (hk + h0 + 2.f * P.R); // <= 0
+            const float disc = fmaf(b, b, c);
+            if (disc >= 0.f) return bi > 0 ? fminf(__fdividef(-c, fast_sqrt(disc) - b), smax) : smax;
+            down = false; // perigee inside this band
         } else {
-            return bi > 0 ? fminf(fmaxf(__fdividef(h0 - hk, -b), 0.f), smax) : smax;
+            return bi > 0 ? fminf(__fdividef(hk - h0, b), smax) : smax;
         }
     }
     if (bi >= P.n_bands - 1) return smax;
     const float hk = lo[bi + 1];
     if (SPH) {
-        float c = fmaxf((hk - h0) * (2.f * P.R + hk + h0), 0.f);
-        float sq = fast_sqrt(fmaf(b, b, c));
+        const float c = fmaxf((hk - h0) * (hk + h0 + 2.f * P.R), 0.f);
+        const float sq = fast_sqrt(fmaf(b, b, c));
         return fminf(b > 0.f ? __fdividef(c, b + sq) : sq - b, smax);
     }
-    return fminf(fmaxf(__fdividef(hk - h0, b), 0.f), smax);
+    return fminf(__fdividef(hk - h0, b), smax);
 }
 
 #ifndef ERTB_FLUSH_COLLECTIVE_MIN
@@ -314,29 +318,39 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                     }
                     if (alive) {
                         if (STATS) { if (is_main) st_main++; else st_nee++; }
-                        float inv_maj = P.inv_majorant, bratio = 1.f;
-                        if (BANDS) {
-                            if (s == 0.f) { // a new segment (every event starts one with s = 0): band of its origin
-                                int bi = band_of(P, tb, h0);
+                        float bratio = 1.f;
+                        const float E = -__logf(1.f - pcg_float(rng)); // majorant optical depth of this flight
+                        bool nee_over = false;
+                        if (!BANDS) {
+                            s = fmaf(E, P.inv_majorant, s);
+                        } else {
+                            if (s == 0.f) { // a new segment (every event starts one with s = 0) in the event's band
+                                const int bi = (int) ((band >> 16) & 255u);
                                 bool down = b < 0.f;
                                 sb = band_exit<SPH>(P, tb, h0, b, bi, down, smax);
-                                band = (unsigned) bi | (down ? 256u : 0u);
+                                band = (band & 0xff0000u) | (unsigned) bi | (down ? 256u : 0u);
                             }
-                            bratio = tb[P.off_band_ratio + (band & 255u)];
-                            inv_maj *= bratio;
+                            // Spend E band by band: a flight that outlives the band it is in pays that band's
+                            // share (majorant x remaining length) and carries on in the next band with its
+                            // majorant -- the tentative collision falls where the piecewise-constant majorant
+                            // optical depth along the segment reaches E (no event and no random number at a
+                            // boundary; a crossing costs one boundary distance).
+                            float Er = E * P.inv_majorant; // remaining depth, in metres at the global majorant
+#pragma unroll 1
+                            for (int it = 2 * P.n_bands + 2; it > 0; --it) {
+                                const unsigned bi = band & 255u;
+                                bratio = tb[P.off_band_ratio + bi];
+                                const float sn = fmaf(Er, bratio, s);
+                                if (sn < sb || !(sb < smax)) { s = sn; break; }
+                                Er = fmaxf(fmaf(s - sb, tb[P.off_band_iratio + bi], Er), 0.f);
+                                s = sb;
+                                bool down = (band & 256u) != 0u;
+                                const int nb = (int) bi + (down ? -1 : 1);
+                                sb = band_exit<SPH>(P, tb, h0, b, nb, down, smax);
+                                band = (band & 0xff0000u) | (unsigned) nb | (down ? 256u : 0u);
+                            }
                         }
-                        float u = pcg_float(rng);
-                        s += -__logf(1.f - u) * inv_maj;
-                        bool nee_over = false;
-                        if (BANDS && !(s < sb) && sb < smax) {
-                            // the flight leaves the band: stop at the boundary, carry on with the next band's
-                            // majorant (no event; free flights are memoryless)
-                            bool down = (band & 256u) != 0u;
-                            int bi = (int) (band & 255u) + (down ? -1 : 1);
-                            s = sb > 0.f ? sb : 1e-30f; // (s = 0 marks a new segment)
-                            sb = band_exit<SPH>(P, tb, h0, b, bi, down, smax);
-                            band = (unsigned) bi | (down ? 256u : 0u);
-                        } else if (!(s < smax)) {
+                        if (!(s < smax)) {
                             if (is_main) {
                                 mode = (flags & PFL_KIND) ? PM_SURF : PM_IDLE; // ground hit / left through the TOA
                             } else {
@@ -563,6 +577,8 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                 FLD(PF_N0X, slot) = n0.x; FLD(PF_N0Y, slot) = n0.y; FLD(PF_N0Z, slot) = n0.z;
                 FLD(PF_DX, slot) = d.x; FLD(PF_DY, slot) = d.y; FLD(PF_DZ, slot) = d.z;
                 FLDU(PF_PIX, slot) = pix; FLD(PF_WRAY, slot) = wray;
+                // band of the segment's origin (bits 16-23): the top band for rays entering at the TOA
+                if (BANDS) FLDU(PF_BAND, slot) = (unsigned) (GEN ? band_of(P, tb, h0) : P.n_bands - 1) << 16;
                 if (POL) {
                     // throughput starts as the rotation to the output Stokes basis (stokes.cpp:111-151):
                     // the accumulated vector is then directly expressed in that basis
@@ -651,8 +667,8 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                                     v[r] = fmaf(T[4 * r], Mb[0], fmaf(T[4 * r + 1], Mb[4], fmaf(T[4 * r + 2], Mb[8], T[4 * r + 3] * Mb[12])));
                             }
                         }
-                        wnee = v[0] > 0.f ? v[0] * P.irradiance : 0.f;
-                        float inv = v[0] > 0.f ? __fdividef(1.f, v[0]) : 0.f;
+                        wnee = v[0] * P.irradiance;
+                        float inv = v[0] != 0.f ? __fdividef(1.f, v[0]) : 0.f;
 #pragma unroll
                         for (int k = 0; k < 3; ++k) qn[k] = v[k + 1] * inv;
                         float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
@@ -760,10 +776,10 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                             for (int r = 0; r < 4; ++r)
                                 v[r] = fmaf(T[4 * r], Pm[0], fmaf(T[4 * r + 1], Pm[4], fmaf(T[4 * r + 2], Pm[8], T[4 * r + 3] * Pm[12])));
                             wnee = v[0] * P.irradiance;
-                            float inv = v[0] > 0.f ? __fdividef(1.f, v[0]) : 0.f;
+                            float inv = v[0] != 0.f ? __fdividef(1.f, v[0]) : 0.f;
 #pragma unroll
                             for (int k = 0; k < 3; ++k) qn[k] = v[k + 1] * inv;
-                            if (!(wnee > 0.f)) wnee = 0.f;
+                            if (!(wnee == wnee)) wnee = 0.f; // (NaN guard; the sign is the estimator's business)
                         } else {
                             wnee = thr * pv * P.irradiance;
                         }
@@ -835,12 +851,15 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                 float q = fminf(thr, 0.95f);
                 if (pcg_float(rng) >= q) thr = 0.f; else thr = __fdividef(thr, q);
             }
-            if (POL && !(thr > 0.f)) thr = 0.f; // unpolarized(throughput) == 0 ends the path (volpath.cpp:191)
+            // A BSDF may be negative (RTLS at grazing angles, rtls.cpp:231-243 does not clamp): throughput and
+            // next-event terms keep their sign as in the reference, where only unpolarized(throughput) == 0 ends
+            // the path (volpath.cpp:191) and Russian roulette removes a negative throughput once depth > rr_depth
+            if (POL && !(thr == thr)) thr = 0.f;
             if (thr == 0.f || depth >= P.max_depth) dead = true; // the NEE walk (if any) still runs
             if (PW) {
                 // ---- exact shadow-ray transmittance (piecewise_volpath.cpp:404-527), then the free
                 //      flight to the next event ----
-                if (wnee > 0.f) {
+                if (wnee != 0.f) {
                     if (STATS) st_nee++;
                     float c = sun_e.z > 0.f ? wnee * pw_transmittance_up(P, tb, h0, sun_e.z) : 0.f;
                     res += c;
@@ -861,7 +880,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                 FLDU(PF_RNG0, slot) = (unsigned) rng.state; FLDU(PF_RNG1, slot) = (unsigned) (rng.state >> 32);
                 FLD(PF_DX, slot) = d.x; FLD(PF_DY, slot) = d.y; FLD(PF_DZ, slot) = d.z;
                 if (POL) {
-                    float inv = thr > 0.f ? __fdividef(1.f, T[0]) : 0.f;
+                    float inv = thr != 0.f ? __fdividef(1.f, T[0]) : 0.f;
 #pragma unroll
                     for (int k = 0; k < 16; ++k) FLD(PF_T0 + k, slot) = T[k] * inv;
 #pragma unroll
@@ -872,12 +891,12 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
             float b = 0.f, smax = 0.f, b2 = 0.f, smax2 = 0.f;
             int kind = KIND_TOA, kind2 = KIND_TOA;
             if (!dead) segment_setup<SPH>(P, n0, h0, d, b2, smax2, kind2);
-            if (wnee > 0.f) {
+            if (wnee != 0.f) {
                 segment_setup<SPH>(P, n0, h0, sun_e, b, smax, kind);
                 if (kind == KIND_GROUND) wnee = 0.f; // sun below the local horizon
             }
             unsigned mode;
-            if (wnee > 0.f) {
+            if (wnee != 0.f) {
                 mode = PM_WALK_NEE;
                 kind = KIND_TOA;
             } else if (dead) {
@@ -896,8 +915,10 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
             FLD(PF_B2, slot) = b2; FLD(PF_SMAX2, slot) = smax2;
             FLD(PF_N0X, slot) = n0.x; FLD(PF_N0Y, slot) = n0.y; FLD(PF_N0Z, slot) = n0.z;
             FLD(PF_DX, slot) = d.x; FLD(PF_DY, slot) = d.y; FLD(PF_DZ, slot) = d.z;
+            // both segments of this event start in its band: the ground's, or the one the collision fell in
+            if (BANDS) FLDU(PF_BAND, slot) = phase == PM_SURF ? 0u : (FLDU(PF_BAND, slot) & 255u) << 16;
             if (POL) {
-                float inv = thr > 0.f ? __fdividef(1.f, T[0]) : 0.f;
+                float inv = thr != 0.f ? __fdividef(1.f, T[0]) : 0.f;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) FLD(PF_T0 + k, slot) = T[k] * inv;
 #pragma unroll

@@ -138,8 +138,8 @@ class Volume(Object):
 
     def layer_values(self) -> np.ndarray:
         """1D profile carried by the volume (float32)."""
-        if self.type == "constvolume":
-            return np.array([self.values["value"]], dtype=np.float32)
+        if self.type == "constvolume":  # volumes/const.cpp:89: a texture child named `value`
+            return np.array([self.children["value"].values["value"]], dtype=np.float32)
         if self.type == "sphericalcoordsvolume":
             return self.children["volume"].layer_values()
         data = self.values["data"]
@@ -308,12 +308,12 @@ class _Loader:
     def make_volume(self, d, oid) -> Volume:
         if not isinstance(d, dict):  # bare float -> constvolume (Properties::get_volume)
             vol = Volume("constvolume", oid)
-            vol.values["value"] = float(d)
+            vol.children["value"] = self.make_texture(float(d), "constvolume.value")
             return vol
         ty = d["type"]
         vol = Volume(ty, oid)
         if ty == "constvolume":
-            vol.values["value"] = _scalar_spectrum(d.get("value", 1.0), "constvolume.value")
+            vol.children["value"] = self.make_texture(d.get("value", 1.0), "constvolume.value")
         elif ty == "gridvolume":
             if d.get("filter_type", "trilinear") != "nearest":
                 raise RuntimeError("gridvolume: only filter_type='nearest' is supported")
@@ -371,15 +371,12 @@ class _Loader:
                         "same size as 'cos_theta_str'!")
                 ph.values[name] = arr
         elif ty in ("rayleigh", "rayleigh_polarized"):
-            dep = d.get("depolarization", 0.0)
-            if isinstance(dep, dict):
-                vol = self.make_volume(dep, None)
-                vals = vol.layer_values()
-                if not np.all(vals == vals.flat[0]):
-                    raise RuntimeError("rayleigh: layer-dependent depolarization is unsupported")
-                ph.children["depolarization"] = vol
-            else:
-                ph.values["depolarization"] = float(dep)
+            dep = d.get("depolarization", 0.0)  # rayleigh.cpp:48 / rayleigh_polarized.cpp: a volume (get_volume)
+            vol = self.make_volume(dep, None)
+            vals = vol.layer_values()
+            if not np.all(vals == vals.flat[0]):
+                raise RuntimeError("rayleigh: layer-dependent depolarization is unsupported")
+            ph.children["depolarization"] = vol
         elif ty == "tabphase":
             ph.values["values"] = _parse_floats(d["values"], "tabphase.values").astype(np.float32)
         elif ty == "tabphase_irregular":
@@ -424,8 +421,9 @@ class _Loader:
             b.children["rho_0"] = tex("rho_0", 0.1)
             b.children["g"] = tex("g", 0.0)
             b.children["k"] = tex("k", 0.1)
-            b.children["rho_c"] = tex("rho_c", d.get("rho_0", 0.1))
-            b.rho_c_tied = "rho_c" not in d
+            b.rho_c_tied = "rho_c" not in d  # rpv.cpp:84-87: rho_c follows rho_0 unless given
+            if not b.rho_c_tied:
+                b.children["rho_c"] = tex("rho_c", d["rho_c"])
         elif ty == "rtls":  # rtls.cpp:63-78
             b.children["f_iso"] = tex("f_iso", 0.209741)
             b.children["f_vol"] = tex("f_vol", 0.081384)
@@ -468,6 +466,9 @@ class _Loader:
             b.values["chlorinity"] = float(d.get("chlorinity", 19.0))
             b.values["pigmentation"] = float(d.get("pigmentation", 0.3))
             b.values["shadowing"] = bool(d.get("shadowing", True))
+            # ocean_legacy.cpp:299, :360-361: the derived whitecap coverage is published too (read-only: the
+            # kernel re-derives it from the wind speed at every parameter update)
+            b.values["coverage"] = float(min(max(2.95e-06 * b.values["wind_speed"] ** 3.52, 0.0), 1.0))
             b.component = int(d.get("component", 0))
             if b.component != 0:
                 raise RuntimeError("ocean_legacy: only component=0 (full BRDF) is supported")
@@ -834,8 +835,7 @@ class _Loader:
             obj = self.make(value, value.get("id", key))
             if obj._id == "":
                 obj._id = key
-            if obj.plugin_kind in ("integrator", "emitter", "shape", "sensor"):
-                scene.children[obj.id() or key] = obj
+            scene.children[obj.id() or key] = obj  # every top-level object is a child (scene.cpp:510-522)
             if obj.plugin_kind == "integrator":
                 scene._integrator_key = obj.id() or key
             elif obj.plugin_kind == "sensor":
@@ -1100,8 +1100,8 @@ class FlatScene:
                     raise RuntimeError("multiphase: the weights must have a positive sum in every layer")
                 if getattr(ph, "use_mis", True):
                     for leaf in _phase_leaf_nodes(ph):
-                        dep = leaf.values.get("depolarization", 0.0) if "depolarization" not in leaf.children \
-                            else float(leaf.children["depolarization"].layer_values().flat[0])
+                        dep = float(leaf.children["depolarization"].layer_values().flat[0]) \
+                            if "depolarization" in leaf.children else 0.0
                         if leaf.type in ("rayleigh_polarized", "tabphase_polarized") or \
                                 (leaf.type == "rayleigh" and dep != 0.0):
                             # the mixture weight differs from the leaf's own: carried by the kernels (`phase_mis`)
@@ -1339,10 +1339,7 @@ def _phase_leaf_desc(ph: PhaseFunction):
     if ph.type == "tabphase_polarized":
         return _abi.PHASE_TABULATED_POLARIZED, params, ph.values["m11"], ph.values["nodes"]
     if ph.type in ("rayleigh", "rayleigh_polarized"):
-        if "depolarization" in ph.children:
-            params[0] = float(ph.children["depolarization"].layer_values().flat[0])
-        else:
-            params[0] = ph.values.get("depolarization", 0.0)
+        params[0] = float(ph.children["depolarization"].layer_values().flat[0])
         if params[0] >= 1.0:
             raise RuntimeError("Depolarization factor must be in [0, 1[")
         ty = _abi.PHASE_RAYLEIGH_POLARIZED if ph.type == "rayleigh_polarized" else _abi.PHASE_RAYLEIGH

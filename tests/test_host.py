@@ -110,7 +110,7 @@ def test_glint_family_bsdfs_load_with_reference_defaults_and_keys():
     def bsdf_of(surface):
         d = scenes.atmosphere_scene(surface=surface, geometry="plane_parallel", n_layers=4)
         sc = mi_load_dict(d)
-        keys = {k.split(".bsdf.")[-1] for k in mi_traverse(sc).parameters.keys() if ".bsdf." in k}
+        keys = {k.split("surface_bsdf.")[-1] for k in mi_traverse(sc).parameters.keys() if k.startswith("surface_bsdf.")}
         desc = sc.flat.build_desc()
         return desc.bsdf_type, np.array(desc.bsdf_params[:8]), keys
 
@@ -143,8 +143,8 @@ def test_multiphase_flattens_like_the_equivalent_blend_tree():
     wb = np.ctypeslib.as_array(b.phase_weight, shape=(3, b.n_layers))
     assert np.allclose(wa, wb, atol=2e-7) and np.allclose(wa.sum(axis=0), 1.0, atol=1e-6)
     # traverse() publishes phase<i> / weight<i> (multiphase.cpp:114-119)
-    keys = {k.split("phase_function.")[-1] for k in mi_traverse(mi_load_dict(multiphase_scene())).parameters.keys()
-            if "phase_function." in k}
+    keys = {k.split("phase_atmosphere.")[-1] for k in mi_traverse(mi_load_dict(multiphase_scene())).parameters.keys()
+            if k.startswith("phase_atmosphere.")}
     assert {"weight0.data", "weight1.data", "weight2.data", "phase1.g"} <= keys, keys
 
 
@@ -221,24 +221,23 @@ def test_piecewise_volpath_needs_a_piecewise_medium():
 def test_traverse_parameter_keys_and_search():
     sc = mi_load_dict(scenes.config_c2(spp=4))
     umap = scenes.spectral_update_map(1200, spherical=True)
-    umap["surface.rho_0"] = SceneParameter(lambda ctx: 0.2, parameter_id="surface_shape.bsdf.rho_0.value")
+    umap["surface.rho_0"] = SceneParameter(lambda ctx: 0.2, parameter_id="surface_bsdf.rho_0.value")
     w = mi_traverse(sc, umap)
     keys = set(w.parameters.keys())
     # same dotted paths Mitsuba's traversal publishes
     for k in (
-        "shape_atmosphere.interior_medium.sigma_t.volume.data",
-        "shape_atmosphere.interior_medium.albedo.volume.data",
-        "shape_atmosphere.interior_medium.scale",
+        "medium_atmosphere.sigma_t.volume.data",
+        "medium_atmosphere.albedo.volume.data",
+        "medium_atmosphere.scale",
         "illumination.irradiance.value",
-        "surface_shape.bsdf.rho_0.value",
-        "surface_shape.bsdf.k.value",
-        "surface_shape.bsdf.g.value",
-        "surface_shape.bsdf.rho_c.value",
+        "surface_bsdf.rho_0.value",
+        "surface_bsdf.k.value",
+        "surface_bsdf.g.value",
     ):
         assert k in keys, k
     # SearchSceneParameter lookups were resolved (kernel/_render.py:314-321)
     assert w.umap_template["medium_atmosphere.sigma_t"].parameter_id == \
-        "shape_atmosphere.interior_medium.sigma_t.volume.data"
+        "medium_atmosphere.sigma_t.volume.data"
     assert w.umap_template["illumination.irradiance.value"].parameter_id == "illumination.irradiance.value"
     # drop_parameters keeps only what the update map touches (kernel/_render.py:122-140)
     w.drop_parameters()
@@ -266,7 +265,7 @@ def test_update_size_mismatch_raises():
     sc = mi_load_dict(scenes.config_c2(spp=4))
     w = mi_traverse(sc)
     with pytest.raises(RuntimeError, match="size mismatch"):
-        w.parameters.update({"shape_atmosphere.interior_medium.sigma_t.volume.data": np.zeros(7)})
+        w.parameters.update({"medium_atmosphere.sigma_t.volume.data": np.zeros(7)})
     with pytest.raises(KeyError):
         w.parameters.update({"nope.value": 1.0})
 
@@ -334,7 +333,7 @@ def test_flatten_canopy_groups_instances_and_leaf_optics():
     assert d.sensors[0].target_type == _abi.TARGET_RECTANGLE
     # leaf optics are scene parameters; the leaves themselves are not exposed one by one
     keys = list(mi_traverse(sc).parameters.keys())
-    assert "leaf_cloud.bsdf.reflectance.value" in keys and "leaf_cloud.bsdf.transmittance.value" in keys
+    assert "bsdf_leaf_cloud.reflectance.value" in keys and "bsdf_leaf_cloud.transmittance.value" in keys
     assert not any("leaf_cloud_leaf_" in k for k in keys)
 
 

@@ -487,7 +487,7 @@ def test_ocean_mishchenko_update_equals_fresh_scene(oracle):
     from eradiate_b200.kernel import mi_traverse
     sc, _ = make_desc(surface=MISHCHENKO, stokes=True)
     w = mi_traverse(sc)
-    keys = {k.split("bsdf.")[-1]: k for k in w.parameters.keys() if ".bsdf." in k}
+    keys = {k.split("surface_bsdf.")[-1]: k for k in w.parameters.keys() if k.startswith("surface_bsdf.")}
     assert set(keys) == {"wind_speed", "eta.value", "k.value", "ext_ior.value"}  # ocean_mishchenko.cpp:118-123
     w.parameters.update({keys["wind_speed"]: 10.0, keys["eta.value"]: 1.39})
     M = oracle.bsdf_mueller(sc.flat.build_desc(), _deg_dir(60.0, 0.0), _deg_dir(40.0, 180.0))[0]
