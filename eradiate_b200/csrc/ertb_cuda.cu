@@ -14,9 +14,18 @@
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 #include "ertb_kernel.cuh"
 #include "ertb_kernel_pool.cuh"
 #include "ertb_canopy.cuh"
+
+// Host-side NVTX ranges (the B200 counterpart of the reference's MI_PROFILER_NVTX scopes):
+// table commit, kernel launch and film read-back show up as named ranges in an nsys / ncu timeline.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ----------------------------------------------------------------------------
 // error handling
@@ -248,6 +257,8 @@ struct ertb_scene {
     float scale = 1.f;
     std::vector<float> sigma_t, albedo, phase_weight;
     std::vector<int> band_starts; // banded majorant: first layer of every band chosen at the last commit
+    cudaStream_t last_stream = nullptr; // stream of the last render through the main slot
+    bool last_stream_valid = false;
     int n_phase = 0;
     HostPhase phase[ERTB_MAX_PHASE];
     int bsdf_type = 0;
@@ -544,6 +555,7 @@ static int validate_tab(const HostPhase &hp) {
 
 // Rebuild derived tables + base kernel parameters and upload them.
 static int scene_commit(ertb_scene *S, TableSlot &T) {
+    NvtxRange nvtx("ertb:scene_commit");
     CUDA_TRY(cudaSetDevice(S->device));
     ErtbParams &P = S->base;
     memset(&P, 0, sizeof P);
@@ -735,6 +747,9 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
         if (T.ocean_key[0] != n_real || T.ocean_key[1] != n_imag || T.ocean_key[2] != ws) {
             ertb_ocean_tables_kernel<<<(2 * ERTB_OC_RES * ERTB_OC_RES + 127) / 128, 128, 0, T.stream>>>(n_real, n_imag, ws, S->d_gl, T.d_ocean);
             CUDA_TRY(cudaGetLastError());
+            // the main slot builds its tables on the legacy stream, which does not order against a caller's
+            // non-blocking stream: finish them before any render can be queued behind this commit
+            if (!T.async) CUDA_TRY(cudaStreamSynchronize(T.stream));
             T.ocean_key[0] = n_real; T.ocean_key[1] = n_imag; T.ocean_key[2] = ws;
         }
         P.ocean_tables = T.d_ocean;
@@ -1262,9 +1277,21 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     if (spp == 0) return set_error("spp must be > 0");
     if (sample_offset + spp >= (1ULL << 40)) return set_error("sample index exceeds 2^40");
     CUDA_TRY(cudaSetDevice(S->device));
+    NvtxRange nvtx("ertb:launch_render");
     if (slot) {
         if (scene_commit(S, *slot)) return 1;
-    } else if (S->dirty && scene_commit(S, S->main)) return 1;
+    } else {
+        // Outside the batch entry points a scene has ONE table slot and ONE work counter: renders of a scene are
+        // serialised. A render queued on another stream than the previous one waits for it, and a commit (a
+        // synchronous upload into the tables the previous render may still be reading) waits for the caller's stream.
+        if (S->last_stream_valid && S->last_stream != stream) CUDA_TRY(cudaStreamSynchronize(S->last_stream));
+        if (S->dirty) {
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (scene_commit(S, S->main)) return 1;
+        }
+        S->last_stream = stream;
+        S->last_stream_valid = true;
+    }
     ErtbParams P = S->base;
     if (!counter_dev) counter_dev = S->d_counter;
     const HostSensor &hs = S->sensors[sensor];
@@ -1300,7 +1327,7 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     const bool gen_needed = !c3d && (hs.desc.type == ERTB_SENSOR_MPDISTANT || hs.desc.type == ERTB_SENSOR_MRADIANCEMETER ||
                                      S->astro_diameter > 0.0 || S->phase_mis);
     if (gen_needed) use_pool = true;
-    const int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? ERTB_POOL_BLOCK : ERTB_BLOCK);
+    const int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? (pol ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK) : ERTB_BLOCK);
     const bool bands = S->base.n_bands > 1;
     size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol, bands && !pw) : (size_t) S->base.blob_bytes;
     if (use_pool && smem > (size_t) S->max_smem_optin) { // huge tables: fall back to the register kernel
@@ -1356,7 +1383,9 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     ERTB_DISPATCH(ERTB_OCC);
     if (blocks_per_sm < 1) return set_error("render kernel cannot be resident on this device");
     if (use_pool) {
-        P.tw = 32; P.twi = bands ? 8 : 16; // (banded walks lose lanes at band boundaries: keep stepping longer; C3 +4 %)
+        // (banded walks lose lanes at band boundaries: keep stepping longer, C3 +4 %; polarized records are
+        // expensive to move: stay in the walk until few are left, C5 +2 %)
+        P.tw = 32; P.twi = pol ? 4 : (bands ? 8 : 16);
         P.tw = env_int_clamped("ERTB_POOL_TW", P.tw, 1, ERTB_POOL_NS);
         P.twi = env_int_clamped("ERTB_POOL_TWI", P.twi, 1, 32);
     }
@@ -1439,7 +1468,10 @@ int ertb_render_stokes(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, u
     if (launch_render(S, sensor, seed, spp, sample_offset, S->d_accum, d_stats, 0, stats != nullptr)) return 1;
     CUDA_TRY(cudaEventRecord(S->ev1, 0));
     std::vector<double> host((size_t) rows * npix);
-    CUDA_TRY(cudaMemcpy(host.data(), S->d_accum, bytes, cudaMemcpyDeviceToHost));
+    {
+        NvtxRange nvtx("ertb:film_readback");
+        CUDA_TRY(cudaMemcpy(host.data(), S->d_accum, bytes, cudaMemcpyDeviceToHost));
+    }
     if (sum_stokes) {
         if (S->polarized) memcpy(sum_stokes, host.data() + 3 * (size_t) npix, 4 * (size_t) npix * sizeof(double));
         else memset(sum_stokes, 0, 4 * (size_t) npix * sizeof(double));

@@ -23,6 +23,8 @@
 // is therefore always in one of the three event modes and each trip of a lane is one real event.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "ertb_kernel.cuh"
 #include "ertb_polar.cuh"
 #include "ertb_piecewise.cuh"
@@ -36,10 +38,24 @@
 #ifndef ERTB_POOL_MINB
 #define ERTB_POOL_MINB 6
 #endif
-#ifndef ERTB_POOL_MINB_POL
-#define ERTB_POOL_MINB_POL 3 // polarized instances: Mueller-matrix events need > 128 registers
+// Polarized instances: the table blob is replicated per CTA, so a few big CTAs leave more shared memory to the
+// pools than many small ones (warps never synchronise with each other after the tables are staged)
+#ifndef ERTB_POOL_BLOCK_POL
+#define ERTB_POOL_BLOCK_POL 640 // one CTA of 20 warps per SM (<= 102 registers): C5 +7 % over 4 CTAs of 4 warps
 #endif
-#define ERTB_POOL_K (ERTB_POOL_NS / 32)
+#ifndef ERTB_POOL_MINB_POL
+#define ERTB_POOL_MINB_POL 1 // polarized instances: CTAs per SM at ERTB_POOL_BLOCK_POL threads
+#endif
+#ifndef ERTB_POOL_NS_POL
+#define ERTB_POOL_NS_POL 64 // records per warp of the polarized instances
+#endif
+// Polarized records keep the normalised Mueller throughput and the Q/I, U/I, V/I ratios of the pending
+// next-event term as fp16 pairs (entries are O(1) by construction; storage rounding is unbiased and 5e-4
+// relative, far below the Monte Carlo noise of Q, U, V): 13 extra words per record instead of 22, which is
+// what lets a fourth CTA fit into an SM's shared memory.  The intensity path (thr, wnee, res) stays fp32.
+#ifndef ERTB_POL_PACK16
+#define ERTB_POL_PACK16 1
+#endif
 
 enum : int {
     PF_FLAGS = 0, PF_H0, PF_B, PF_S, PF_SMAX, PF_THR, PF_WNEE, PF_RES, PF_RNG0, PF_RNG1,
@@ -50,7 +66,11 @@ enum : int {
     // polarized records only: throughput Mueller matrix normalised by its (0,0) entry (PF_THR holds
     // that entry, so the walk phase is identical in both modes), Q/I U/I V/I of the pending NEE
     // Stokes vector, and the Q, U, V components of the result (PF_RES holds I)
+#if ERTB_POL_PACK16
+    PF_T0 = PF_COUNT, PF_QN0 = PF_T0 + 8, PF_RQ = PF_QN0 + 2, PF_COUNT_POL = PF_RQ + 3
+#else
     PF_T0 = PF_COUNT, PF_QN0 = PF_T0 + 16, PF_RQ = PF_QN0 + 3, PF_COUNT_POL = PF_RQ + 3
+#endif
 };
 enum : unsigned {
     PM_DEAD = 0, PM_IDLE = 1, PM_WALK_MAIN = 2, PM_WALK_NEE = 3, PM_SURF = 4, PM_SCAT = 5,
@@ -63,8 +83,8 @@ enum : unsigned {
 // segment, and (band index | descending << 8)
 __host__ __device__ inline size_t ertb_pool_smem_bytes(size_t blob_bytes, bool pol = false, bool bands = false) {
     size_t blob = (blob_bytes + 15) & ~size_t(15);
-    size_t warps = ERTB_POOL_BLOCK / 32;
-    return blob + warps * (size_t) ((pol ? PF_COUNT_POL : PF_COUNT) + (bands ? 2 : 0)) * ERTB_POOL_NS * 4 + warps * 32 * 4;
+    size_t warps = (pol ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK) / 32;
+    return blob + warps * (size_t) ((pol ? PF_COUNT_POL : PF_COUNT) + (bands ? 2 : 0)) * (pol ? ERTB_POOL_NS_POL : ERTB_POOL_NS) * 4 + warps * 32 * 4;
 }
 
 // free flight that follows a regeneration or an event of the piecewise integrator
@@ -130,6 +150,53 @@ __device__ __forceinline__ float band_exit(const ErtbParams &P, const float *tb,
     return fminf(__fdividef(hk - h0, b), smax);
 }
 
+// polarized record fields (field-major pool `wp` of NS slots): normalised throughput and NEE ratios
+template <int NS>
+__device__ __forceinline__ void pol_load_T(const float *wp, int slot, float scale, float *T) {
+#if ERTB_POL_PACK16
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float2 v = __half22float2(*reinterpret_cast<const __half2 *>(&wp[(PF_T0 + k) * NS + slot]));
+        T[2 * k] = scale * v.x; T[2 * k + 1] = scale * v.y;
+    }
+#else
+#pragma unroll
+    for (int k = 0; k < 16; ++k) T[k] = scale * wp[(PF_T0 + k) * NS + slot];
+#endif
+}
+template <int NS>
+__device__ __forceinline__ void pol_store_T(float *wp, int slot, const float *T, float scale) {
+#if ERTB_POL_PACK16
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<__half2 *>(&wp[(PF_T0 + k) * NS + slot]) = __floats2half2_rn(T[2 * k] * scale, T[2 * k + 1] * scale);
+#else
+#pragma unroll
+    for (int k = 0; k < 16; ++k) wp[(PF_T0 + k) * NS + slot] = T[k] * scale;
+#endif
+}
+template <int NS>
+__device__ __forceinline__ void pol_load_qn(const float *wp, int slot, float *qn) {
+#if ERTB_POL_PACK16
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&wp[PF_QN0 * NS + slot]));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&wp[(PF_QN0 + 1) * NS + slot]));
+    qn[0] = a.x; qn[1] = a.y; qn[2] = b.x;
+#else
+#pragma unroll
+    for (int k = 0; k < 3; ++k) qn[k] = wp[(PF_QN0 + k) * NS + slot];
+#endif
+}
+template <int NS>
+__device__ __forceinline__ void pol_store_qn(float *wp, int slot, const float *qn) {
+#if ERTB_POL_PACK16
+    *reinterpret_cast<__half2 *>(&wp[PF_QN0 * NS + slot]) = __floats2half2_rn(qn[0], qn[1]);
+    *reinterpret_cast<__half2 *>(&wp[(PF_QN0 + 1) * NS + slot]) = __floats2half2_rn(qn[2], 0.f);
+#else
+#pragma unroll
+    for (int k = 0; k < 3; ++k) wp[(PF_QN0 + k) * NS + slot] = qn[k];
+#endif
+}
+
 #ifndef ERTB_FLUSH_COLLECTIVE_MIN
 #define ERTB_FLUSH_COLLECTIVE_MIN 6
 #endif
@@ -186,9 +253,11 @@ __device__ __noinline__ void film_flush_warp(const ErtbParams &P, unsigned lane,
 // class 3 of the per-pixel table carries the start altitude) and `mpdistant` (the film sample picks the
 // target point). A template parameter for the same reason as COLL: the C2 instance must not change.
 template <bool SPH, bool STATS, bool POL, bool PW = false, bool COLL = false, bool BANDS = false, bool GEN = false>
-__global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
+__global__ void __launch_bounds__(POL ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
     static_assert(!(PW && BANDS), "the piecewise integrator has no null collisions");
     static_assert(!(PW && SPH), "the piecewise medium is a plane-parallel layer stack");
+    constexpr int NS = POL ? ERTB_POOL_NS_POL : ERTB_POOL_NS; // records per warp
+    constexpr int NK = NS / 32;
     constexpr int NF = (POL ? PF_COUNT_POL : PF_COUNT) + (BANDS ? 2 : 0);
     constexpr int PF_SB = NF - 2, PF_BAND = NF - 1; // (BANDS only)
     extern __shared__ __align__(16) float smem[];
@@ -197,9 +266,10 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
     const unsigned blob_words = ((unsigned) P.blob_bytes + 15u) / 16u * 4u;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    float *wp = smem + blob_words + warp * (NF * ERTB_POOL_NS);
+    float *wp = smem + blob_words + warp * (NF * NS);
     unsigned *wpu = reinterpret_cast<unsigned *>(wp);
-    int *list = reinterpret_cast<int *>(smem + blob_words + (ERTB_POOL_BLOCK / 32) * (NF * ERTB_POOL_NS)) + warp * 32;
+    constexpr int NW = (POL ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK) / 32; // warps per CTA
+    int *list = reinterpret_cast<int *>(smem + blob_words + NW * (NF * NS)) + warp * 32;
 
     if (P.blob_bytes > 0) tma_stage(tb, P.blob, (unsigned) P.blob_bytes, &mbar);
 
@@ -207,11 +277,11 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
 
     // every record starts "finished with nothing to accumulate"
 #pragma unroll
-    for (int j = 0; j < ERTB_POOL_K; ++j) {
-        wpu[PF_FLAGS * ERTB_POOL_NS + j * 32 + lane] = PM_IDLE;
-        wpu[PF_PIX * ERTB_POOL_NS + j * 32 + lane] = 0xffffffffu;
-        wp[PF_RES * ERTB_POOL_NS + j * 32 + lane] = 0.f;
-        wp[PF_WRAY * ERTB_POOL_NS + j * 32 + lane] = 0.f;
+    for (int j = 0; j < NK; ++j) {
+        wpu[PF_FLAGS * NS + j * 32 + lane] = PM_IDLE;
+        wpu[PF_PIX * NS + j * 32 + lane] = 0xffffffffu;
+        wp[PF_RES * NS + j * 32 + lane] = 0.f;
+        wp[PF_WRAY * NS + j * 32 + lane] = 0.f;
     }
     __syncwarp();
 
@@ -225,16 +295,16 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
     bool exhausted = false;
     unsigned st_main = 0, st_nee = 0, st_scatter = 0, st_surface = 0, st_paths = 0;
 
-#define FLD(f, slot) wp[(f) * ERTB_POOL_NS + (slot)]
-#define FLDU(f, slot) wpu[(f) * ERTB_POOL_NS + (slot)]
+#define FLD(f, slot) wp[(f) * NS + (slot)]
+#define FLDU(f, slot) wpu[(f) * NS + (slot)]
 
     for (;;) {
         // ---- 1. membership masks -------------------------------------------------
-        unsigned md[ERTB_POOL_K];
-        unsigned sel[ERTB_POOL_K];
+        unsigned md[NK];
+        unsigned sel[NK];
         int n_walk = 0;
 #pragma unroll
-        for (int j = 0; j < ERTB_POOL_K; ++j) {
+        for (int j = 0; j < NK; ++j) {
             md[j] = FLDU(PF_FLAGS, j * 32 + lane) & PFL_MODE_MASK;
             sel[j] = __ballot_sync(0xffffffffu, md[j] == PM_WALK_MAIN || md[j] == PM_WALK_NEE);
             n_walk += __popc(sel[j]);
@@ -243,10 +313,10 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
         unsigned phase = PM_WALK_MAIN; // walk
         int n_sel = n_walk;
         if (PW || n_walk < P.tw) {
-            unsigned ms[ERTB_POOL_K], mc[ERTB_POOL_K], mi[ERTB_POOL_K];
+            unsigned ms[NK], mc[NK], mi[NK];
             int ns = 0, nc = 0, ni = 0;
 #pragma unroll
-            for (int j = 0; j < ERTB_POOL_K; ++j) {
+            for (int j = 0; j < NK; ++j) {
                 ms[j] = __ballot_sync(0xffffffffu, md[j] == PM_SURF);
                 mc[j] = __ballot_sync(0xffffffffu, md[j] == PM_SCAT);
                 mi[j] = __ballot_sync(0xffffffffu, md[j] == PM_IDLE);
@@ -260,7 +330,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
             if (phase != PM_WALK_MAIN) {
                 n_sel = best;
 #pragma unroll
-                for (int j = 0; j < ERTB_POOL_K; ++j)
+                for (int j = 0; j < NK; ++j)
                     sel[j] = phase == PM_IDLE ? mi[j] : (phase == PM_SURF ? ms[j] : mc[j]);
             }
         }
@@ -268,7 +338,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
         {
             int base = 0;
 #pragma unroll
-            for (int j = 0; j < ERTB_POOL_K; ++j) {
+            for (int j = 0; j < NK; ++j) {
                 int pos = base + __popc(sel[j] & lt_mask);
                 if (((sel[j] >> lane) & 1u) && pos < 32) list[pos] = j * 32 + (int) lane;
                 base += __popc(sel[j]);
@@ -435,10 +505,11 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                     if (POL) {
                         float rq = FLD(PF_RQ, slot), ru = FLD(PF_RQ + 1, slot), rv = FLD(PF_RQ + 2, slot);
                         if (FLDU(PF_FLAGS, slot) & PFL_NEE_QUV) {
-                            float wn = FLD(PF_WNEE, slot);
-                            rq = fmaf(wn, FLD(PF_QN0, slot), rq);
-                            ru = fmaf(wn, FLD(PF_QN0 + 1, slot), ru);
-                            rv = fmaf(wn, FLD(PF_QN0 + 2, slot), rv);
+                            float wn = FLD(PF_WNEE, slot), q3[3];
+                            pol_load_qn<NS>(wp, slot, q3);
+                            rq = fmaf(wn, q3[0], rq);
+                            ru = fmaf(wn, q3[1], ru);
+                            rv = fmaf(wn, q3[2], rv);
                         }
                         acc_q += (double) (wr * rq); acc_u += (double) (wr * ru); acc_v += (double) (wr * rv);
                     }
@@ -584,8 +655,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                     // the accumulated vector is then directly expressed in that basis
                     float R[16];
                     stokes_output_rotation(P, d, R);
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) FLD(PF_T0 + k, slot) = R[k];
+                    pol_store_T<NS>(wp, slot, R, 1.f);
                     FLD(PF_RQ, slot) = 0.f; FLD(PF_RQ + 1, slot) = 0.f; FLD(PF_RQ + 2, slot) = 0.f;
                 }
             }
@@ -629,14 +699,14 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
             // polarized state: T = thr * That (actual Mueller throughput), result (Q, U, V), NEE ratios
             float T[POL ? 16 : 1], rquv[3] = { 0.f, 0.f, 0.f }, qn[3] = { 0.f, 0.f, 0.f };
             if (POL) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) T[k] = thr * FLD(PF_T0 + k, slot);
+                pol_load_T<NS>(wp, slot, thr, T);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) rquv[k] = FLD(PF_RQ + k, slot);
                 if (flags & PFL_NEE_QUV) { // finish the previous NEE term
-                    float wn = FLD(PF_WNEE, slot);
+                    float wn = FLD(PF_WNEE, slot), q3[3];
+                    pol_load_qn<NS>(wp, slot, q3);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) rquv[k] = fmaf(wn, FLD(PF_QN0 + k, slot), rquv[k]);
+                    for (int k = 0; k < 3; ++k) rquv[k] = fmaf(wn, q3[k], rquv[k]);
                 }
             }
 
@@ -881,8 +951,7 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
                 FLD(PF_DX, slot) = d.x; FLD(PF_DY, slot) = d.y; FLD(PF_DZ, slot) = d.z;
                 if (POL) {
                     float inv = thr != 0.f ? __fdividef(1.f, T[0]) : 0.f;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) FLD(PF_T0 + k, slot) = T[k] * inv;
+                    pol_store_T<NS>(wp, slot, T, inv);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) FLD(PF_RQ + k, slot) = rquv[k];
                 }
@@ -919,10 +988,10 @@ __global__ void __launch_bounds__(ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ER
             if (BANDS) FLDU(PF_BAND, slot) = phase == PM_SURF ? 0u : (FLDU(PF_BAND, slot) & 255u) << 16;
             if (POL) {
                 float inv = thr != 0.f ? __fdividef(1.f, T[0]) : 0.f;
+                pol_store_T<NS>(wp, slot, T, inv);
+                pol_store_qn<NS>(wp, slot, qn);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) FLD(PF_T0 + k, slot) = T[k] * inv;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { FLD(PF_QN0 + k, slot) = qn[k]; FLD(PF_RQ + k, slot) = rquv[k]; }
+                for (int k = 0; k < 3; ++k) FLD(PF_RQ + k, slot) = rquv[k];
             }
             } // !PW
         }

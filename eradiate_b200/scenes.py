@@ -120,6 +120,7 @@ def atmosphere_scene(
     extra_sensors: list | None = None,
     central_patch: dict | None = None,
     angular_diameter: float | None = None,
+    width: float = 1.0e9,
 ) -> dict:
     """Build the nested scene dict an ``AtmosphereExperiment`` would emit (with ``canopy``: a
     ``CanopyAtmosphereExperiment``, see :func:`disc_canopy`).
@@ -166,7 +167,7 @@ def atmosphere_scene(
         raise ValueError(f"unknown geometry '{geometry}'")
 
     scene["surface_bsdf"] = surface
-    width = 1.0e9  # PlaneParallelGeometry.width default 1e6 km (geometry.py:182-189)
+    # `width`: PlaneParallelGeometry.width, default 1e6 km (geometry.py:182-189)
     if spherical:
         scene["surface_shape"] = {
             "type": "sphere",
@@ -423,7 +424,7 @@ def _sensor_dict(sensor: dict, target, spp: int) -> dict:
     out: dict = {"type": ty, "id": sensor.pop("id", "measure")}
     if ty == "mdistant":
         vza = np.atleast_1d(np.asarray(sensor.pop("vza"), dtype=np.float64))
-        vaa = float(sensor.pop("vaa", 0.0))
+        vaa = np.broadcast_to(np.asarray(sensor.pop("vaa", 0.0), dtype=np.float64), vza.shape)
         # hplane layout: negative zeniths point to azimuth + 180 deg
         az = np.where(vza < 0, vaa + 180.0, vaa)
         view = angles_to_direction(np.abs(vza), az)

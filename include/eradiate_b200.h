@@ -313,7 +313,11 @@ int ertb_render(ertb_scene *scene, int sensor, uint64_t seed, uint64_t spp,
  * ([sum_wl | sum_l | sum_l2], zeroed by the caller) on `stream` (a cudaStream_t,
  * NULL = default stream) and does not synchronise: used for the HBM-resident
  * throughput number and for the NCCL all-reduce of the accumulators.
- * `stats_dev` (optional) is a device buffer of 8 uint64 counters. */
+ * `stats_dev` (optional) is a device buffer of 8 uint64 counters.
+ * Ordering: outside the ertb_batch_* entry points a scene owns ONE table slot and ONE work counter, so its
+ * renders are serialised by the library -- a launch on another stream than the previous one first waits for it,
+ * and a launch that has to commit updated parameters first waits for `stream` (the upload is synchronous).
+ * Any stream is therefore safe, including non-blocking ones; overlap of renders comes from ertb_batch_push. */
 int ertb_render_device(ertb_scene *scene, int sensor, uint64_t seed, uint64_t spp,
                        uint64_t sample_offset, void *accum_dev, void *stats_dev,
                        void *stream);

@@ -21,7 +21,7 @@ from eradiate_b200.kernel import (
     KernelContext, mi_load_dict, mi_render, mi_traverse, render, SeedState,
 )
 from tests.scene_battery import POMMEROL, battery
-from tests.util import sidak_ok, stats_from_sums, z_scores
+from tests.util import REFERENCE_GROUND_LEAK, leak_bounded, sidak_ok, stats_from_sums, z_scores
 
 pytestmark = pytest.mark.gpu
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_renders.json")))
@@ -356,8 +356,8 @@ def test_tree_trunk_ray_caster_and_radiance(oracle):
     mean = render(sc, seed=1, spp=256).raw["sum_l"].ravel() / 256
     want = rho * 1.8 * np.maximum(nrm @ s_dir, 0.0) / np.pi
     assert np.allclose(mean, want, rtol=2e-4, atol=1e-7), (mean, want)
-    # the bark is a scene parameter (`<group>.trunk_bsdf.reflectance.value`)
-    mi_traverse(sc).parameters.update({"tree.trunk_bsdf.reflectance.value": 0.8})
+    # the bark is a scene parameter (`bsdf_tree.reflectance.value`: the top-level BSDF the trunk shapes reference)
+    mi_traverse(sc).parameters.update({"bsdf_tree.reflectance.value": 0.8})
     mean2 = render(sc, seed=1, spp=256).raw["sum_l"].ravel() / 256
     assert np.allclose(mean2, 2.0 * mean, rtol=1e-5, atol=1e-7)
 
@@ -394,7 +394,7 @@ def test_canopy_leaf_optics_update_equals_fresh_scene():
     w = mi_traverse(sc)
     spp = 1 << 14
     a = render(sc, seed=4, spp=spp).raw["sum_l"].copy()
-    w.parameters.update({"leaf_cloud.bsdf.reflectance.value": 0.1, "leaf_cloud.bsdf.transmittance.value": 0.05})
+    w.parameters.update({"bsdf_leaf_cloud.reflectance.value": 0.1, "bsdf_leaf_cloud.transmittance.value": 0.05})
     b = render(sc, seed=4, spp=spp).raw["sum_l"].copy()
     c = render(mk(0.1, 0.05), seed=4, spp=spp).raw["sum_l"]
     assert np.allclose(b, c, rtol=1e-9) and np.all(b < 0.8 * a)
@@ -416,7 +416,7 @@ def test_glint_family_update_equals_fresh_scene(surface, changes):
         sensor={"type": "mdistant", "vza": [-45.0, -35.0, -20.0, 30.0], "vaa": 0.0}))
     sc = mk(surface)
     w = mi_traverse(sc)
-    keys = {k.split(".bsdf.")[-1]: k for k in w.parameters.keys() if ".bsdf." in k}
+    keys = {k.split("surface_bsdf.")[-1]: k for k in w.parameters.keys() if k.startswith("surface_bsdf.")}
     spp = 1 << 14
     a = render(sc, seed=4, spp=spp).raw["sum_l"].copy()
     w.parameters.update({keys[k]: v for k, v in changes.items()})
@@ -661,6 +661,39 @@ def test_render_matches_oracle_fixture(name):
         assert np.isclose(st["n_surface"] / st["n_paths"], gold["surface_per_path"], rtol=0.05, atol=0.01)
 
 
+@pytest.mark.parametrize("name", [
+    "c2_afgl_rpv_spherical", "afgl_rpv_pp", "thick_isotropic_pp", "rtls_rb_spherical", "ocean_pp", "hdistant_pp",
+    "aerosol_hg_blend_pp", "c3_afgl_aerosol_tab_hdistant", "volpathmis_thick", "max_depth_3_rr_2",
+    "polarized_rayleigh_pp", "piecewise_afgl_rpv_pp", "astro_wide_disc_afgl_rpv_pp",
+])
+def test_loop_trips_equal_the_oracles_free_flights(oracle, name, monkeypatch):
+    """K-bar of the kernel and of the CPU restatement "must agree within MC error -- this is itself a
+    parity check".  The kernel's loop trips are free flights: it has no stencil-crossing iterations and does not
+    walk shadow rays whose weight is zero (sun below the horizon, ray ending on the ground).  The oracle counts
+    exactly those flights next to the reference's loop iterations (ertbo_last_flights), so with the reference's
+    single global majorant the two counts are estimates of the same expectation: equal to 1.5 % (> 5 sigma of
+    the oracle's 2.6e5-path sample), main walk and shadow rays separately, plus events per path."""
+    monkeypatch.setenv("ERTB_MAJORANT", "global")
+    sc = mi_load_dict(battery()[name])
+    desc = sc.flat.build_desc()
+    npix = desc.sensors[0].width * desc.sensors[0].height
+    heavy = GOLDEN["scenes"][name]["trips_main_per_path"] + GOLDEN["scenes"][name]["trips_nee_per_path"] > 100
+    o_spp = max(256, (1 << (15 if heavy else 18)) // npix)
+    if desc.polarized:
+        st_o = oracle.render_stokes(desc, 0, 3, o_spp)[4]
+    else:
+        st_o = oracle.render(desc, 0, 3, o_spp)[3]
+    _, _, _, st = gpu_render(sc, max(1024, (1 << (18 if heavy else 21)) // npix), seed=13)
+    assert st["n_bands"] == 1
+    n_o, n_g = st_o["n_paths"], st["n_paths"]
+    for key_g, key_o in (("trips_main", "flights_main"), ("trips_nee", "flights_nee"),
+                         ("n_scatter", "n_scatter"), ("n_surface", "n_surface")):
+        a, b = st[key_g] / n_g, st_o[key_o] / n_o
+        assert np.isclose(a, b, rtol=0.015, atol=0.004), (name, key_g, a, b)
+    # and the reference's own loop-iteration count is never below the flights (stencil crossings come on top)
+    assert st_o["trips_main"] >= st_o["flights_main"] and st_o["trips_nee"] >= st_o["flights_nee"]
+
+
 REFERENCE = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_renders.json")))
 
 
@@ -685,6 +718,10 @@ def test_render_matches_reference_fixture(name):
         var = np.maximum(m2 - mean**2, 0.0) / spp
     else:
         _, mean, var, _ = gpu_render(sc, spp, seed=47)
+    if name in REFERENCE_GROUND_LEAK:  # the reference loses rays through the ground here (tests/util.py)
+        ok, msg = leak_bounded(mean, var, rm, rv, REFERENCE_GROUND_LEAK[name])
+        assert ok, f"{name}: {msg}"
+        return
     z = z_scores(mean, var, rm, rv, rel_floor=2e-6)
     ok, zc = sidak_ok(z)
     assert ok and np.all(np.abs(z) <= 4.5), (
@@ -1033,3 +1070,38 @@ def test_error_paths_through_the_abi():
     from eradiate_b200.kernel._render import _device_scene
     with pytest.raises(RuntimeError, match="spp must be > 0"):
         _device_scene(sc).render(0, 0, 0)
+
+
+# ------------------------------------------------------------------ the reference's sampler (PCG32 build)
+@pytest.mark.parametrize("name", ["c2_afgl_rpv_spherical", "aerosol_hg_blend_pp", "polarized_rayleigh_pp"])
+def test_pcg32_build_matches_reference_fixture(name):
+    """The default build draws from xoroshiro64** with 23-bit uniforms (SURVEY section 7 "RNG semantics" allows any
+    generator with independent per-path streams); -DERTB_RNG_PCG32 compiles the reference's PCG32
+    (MI/ext/drjit/include/drjit/random.h:108-195) into the same kernels.  That build, loaded through ERTB_LIB in a
+    fresh process, must pass the same high-precision reference fixtures."""
+    import shutil
+    import subprocess
+    import sys
+
+    import __graft_entry__ as g
+
+    if shutil.which(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) is None:
+        pytest.skip("nvcc not available to build the PCG32 variant")
+    lib = g.build_variant("pcg32", ["-DERTB_RNG_PCG32"])
+    ref = REFERENCE["scenes"][name]
+    npix = len(ref["mean"])
+    spp = (1 << 26) // npix
+    code = (
+        "import json, sys; sys.path.insert(0, %r)\n"
+        "from eradiate_b200.kernel import mi_load_dict, render\n"
+        "from tests.scene_battery import battery\n"
+        "raw = render(mi_load_dict(battery()[%r]), sensor=0, seed=5, spp=%d).raw\n"
+        "print(json.dumps({'l': raw['sum_l'].ravel().tolist(), 'l2': raw['sum_l2'].ravel().tolist()}))\n"
+    ) % (g.ROOT, name, spp)
+    env = dict(os.environ, ERTB_LIB=lib)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+    d = json.loads(out.strip().splitlines()[-1])
+    mean, var = stats_from_sums(np.array(d["l"]), np.array(d["l2"]), spp)
+    z = z_scores(mean, var, np.array(ref["mean"]), np.array(ref["var_of_mean"]), rel_floor=2e-6)
+    ok, zc = sidak_ok(z)
+    assert ok and np.all(np.abs(z) <= 4.5), f"{name} (PCG32 build): |z| max {np.abs(z).max():.2f} > {zc:.2f}"

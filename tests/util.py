@@ -26,3 +26,29 @@ def sidak_ok(z, alpha=0.001):
     a0 = 1.0 - (1.0 - alpha) ** (1.0 / n)
     zc = stats.norm.ppf(1.0 - a0 / 2.0)
     return bool(np.all(np.abs(z) <= zc)), zc
+
+
+# Scenes on which the REFERENCE ITSELF loses camera rays through the ground: with Eradiate's default
+# plane-parallel width (1e6 km) the flat `rectangle` is missed by a direction-dependent fraction of the rays
+# (0.56 % of hdistant's uniform-hemisphere directions, none of the principal-plane mdistant sets), which then
+# leave through the bottom of the atmosphere cube and return nothing.  Measured on the compiled reference by
+# tests/test_oracle_vs_reference.py::test_reference_loses_rays_through_the_ground (0.4 % at 1e5 km, 0.05 % at
+# 1e4 km: a precision artefact of its ray/shape search at planetary scale, not part of the estimator).  The
+# analytic slab of the oracle and of the CUDA kernels cannot leak, so on these scenes the comparison with the
+# reference fixture is one-sided: not darker than the reference, and brighter by no more than the leak allows.
+REFERENCE_GROUND_LEAK = {
+    "hdistant_pp": 0.0056,
+    "piecewise_ocean_hdistant_pp": 0.0056,
+    "piecewise_distantflux_coarse_pp": 0.0056,
+    "canopy_hdistant_maxdepth_pp": 0.0056,
+}
+
+
+def leak_bounded(mean, var, ref_mean, ref_var, leak, nsig=4.5):
+    """One-sided acceptance for REFERENCE_GROUND_LEAK scenes. Returns (ok, message)."""
+    mean, ref_mean = np.asarray(mean, float), np.asarray(ref_mean, float)
+    sig = np.sqrt(np.asarray(var, float) + np.asarray(ref_var, float))
+    lo = ref_mean - nsig * sig
+    hi = ref_mean * (1.0 + 2.5 * leak) + nsig * sig
+    ok = bool(np.all(mean >= lo) and np.all(mean <= hi))
+    return ok, f"rel. diff {np.round(mean / ref_mean - 1.0, 5)} (allowed: -{nsig} sigma ... +{2.5 * leak:.4f})"
