@@ -19,6 +19,13 @@
 //     main loop advances all walking lanes by at most ERTB_TRACE_STEPS nodes, then runs the other
 //     stages for the lanes that are ready. Rays that need 10 node visits therefore do not wait
 //     for the one that needs 300 (lock-step walks ran with 4 of 32 lanes active, ncu r01e).
+//
+// Tried in round 2 and withdrawn (bit-identical films, profiles/r02g_canopy_scheduler_experiment.md): a warp
+// scheduler that runs ONE kind of work per trip -- BVH slices while at least half of the tracing lanes still
+// trace, else steps of resumable medium walks, else the short stages.  It executed 25 % more warp
+// instructions at the same 10 active lanes (box tests fell from 21 to 16 lanes): 131 against 167 Mpaths/s on
+// C4.  The lanes are lost INSIDE the traversal step (leaf tests at 1.2 lanes, stack and instance
+// bookkeeping at 3-5), not between the stages.
 #pragma once
 
 #include "ertb_kernel.cuh"

@@ -708,9 +708,14 @@ class _Loader:
                 fov = np.degrees(2.0 * np.arctan(0.5 * diag * aspect / np.sqrt(1.0 + aspect * aspect)))
             elif axis != "x":
                 raise RuntimeError(f"perspective: invalid fov_axis '{axis}'")
-            s.x_fov = float(fov)
-            s.near_clip = float(d.get("near_clip", 1e-2))
-            s.far_clip = float(d.get("far_clip", 1e4))
+            # perspective.cpp:186-194 publishes these (an update re-creates the device scene)
+            s.values["x_fov"] = float(fov)
+            s.values["near_clip"] = float(d.get("near_clip", 1e-2))
+            s.values["far_clip"] = float(d.get("far_clip", 1e4))
+            s.values["principal_point_offset_x"] = float(d.get("principal_point_offset_x", 0.0))
+            s.values["principal_point_offset_y"] = float(d.get("principal_point_offset_y", 0.0))
+            if s.values["principal_point_offset_x"] != 0.0 or s.values["principal_point_offset_y"] != 0.0:
+                raise RuntimeError("perspective: a principal point offset is not supported")
             a = s.to_world[:3, :3]
             if not np.allclose(a.T @ a, np.eye(3), atol=1e-6):
                 raise RuntimeError("Scale factors in the camera-to-world transformation are not allowed!")
@@ -1275,7 +1280,7 @@ class FlatScene:
                 sd.origins = org.ctypes.data_as(_abi.c_double_p)
                 sd.in_medium = int(s.in_medium)
             if s.type == "perspective":
-                sd.x_fov_deg, sd.near_clip, sd.far_clip = s.x_fov, s.near_clip, s.far_clip
+                sd.x_fov_deg, sd.near_clip, sd.far_clip = s.values["x_fov"], s.values["near_clip"], s.values["far_clip"]
                 sd.in_medium = int(s.in_medium)
             sd.width, sd.height = s.film().width, s.film().height
             if s.type in ("mdistant", "mradiancemeter"):

@@ -161,6 +161,9 @@ def test_reference_arm_under_torchrun_prints_one_line_and_uses_all_cores():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["gpu_launches"] == 0
     cores = os.cpu_count() or 1
-    assert d["cpu_baseline"]["cores"] == cores and d["cpu_baseline"]["kind"] == "port"
-    if cores >= 4:  # one thread manages ~0.7 Mpaths/s on this workload
-        assert d["value"] > 1.2, d["value"]
+    from oracle import ref
+
+    kind = "reference" if ref.available() else "port"  # the reference itself when oracle/_ref was built
+    assert d["cpu_baseline"]["cores"] == cores and d["cpu_baseline"]["kind"] == kind
+    if cores >= 4:  # one thread manages ~0.09 Mpaths/s (reference, scalar_mono) / ~0.7 Mpaths/s (C port)
+        assert d["value"] > (0.2 if kind == "reference" else 1.2), d["value"]

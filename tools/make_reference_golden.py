@@ -56,7 +56,9 @@ def spp_for(name: str, npix: int, k_oracle: float) -> int:
 def render_scene(name: str, d: dict, spp: int) -> dict:
     polarized = ref.is_polarized(d)
     mi = ref.mitsuba("scalar_mono_polarized_double" if polarized else "scalar_mono_double")
-    scene = mi.load_dict(ref.to_mitsuba(mi, d))
+    # optimize=False as eradiate.kernel.mi_load_dict does (_render.py:186): no merging of identical objects,
+    # so the published parameter keys do not depend on two textures happening to hold the same value
+    scene = mi.load_dict(ref.to_mitsuba(mi, d), optimize=False)
     keys = sorted(mi.traverse(scene).keys())
     t0 = time.perf_counter()
     mi.render(scene, sensor=0, seed=SEED, spp=spp)
@@ -82,6 +84,7 @@ def main():
     ap.add_argument("--only", nargs="*", default=None)
     ap.add_argument("--spp-log2", type=int, default=None, help="override the per-scene sample count")
     ap.add_argument("--list", action="store_true")
+    ap.add_argument("--keys-only", action="store_true", help="refresh only the traverse key lists (no rendering)")
     args = ap.parse_args()
     path = os.path.join(ROOT, "tests", "golden", "reference_renders.json")
     out = {"seed": SEED, "generator": "tools/make_reference_golden.py", "reference": ref.describe(), "scenes": {}}
@@ -91,6 +94,15 @@ def main():
     bat = battery()
     if args.list:
         print("\n".join(bat.keys()))
+        return
+    if args.keys_only:
+        for name, rec in out["scenes"].items():
+            polarized = ref.is_polarized(bat[name])
+            mi = ref.mitsuba("scalar_mono_polarized_double" if polarized else "scalar_mono_double")
+            rec["traverse_keys"] = sorted(mi.traverse(mi.load_dict(ref.to_mitsuba(mi, bat[name]), optimize=False)).keys())
+        with open(path, "w") as f:
+            json.dump(out, f, indent=1)
+        print("refreshed the key lists of", len(out["scenes"]), "scenes")
         return
     oracle_gold = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_renders.json")))["scenes"]
     out.setdefault("refused", {})
