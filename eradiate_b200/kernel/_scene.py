@@ -231,7 +231,7 @@ _SUPPORTED = {
     "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance", "cylinder"},
     "medium": {"heterogeneous", "homogeneous", "piecewise"},
     "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "ocean_mishchenko", "ocean_grasp", "maignan",
-             "mqdiffuse", "null", "bilambertian", "blendbsdf"},
+             "mqdiffuse", "null", "bilambertian", "blendbsdf", "selectbsdf"},
     "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
               "rayleigh_polarized", "tabphase_polarized", "multiphase"},
     "sensor": {"mdistant", "hdistant", "distantflux", "perspective", "mpdistant", "mradiancemeter"},
@@ -244,7 +244,6 @@ _KNOWN_UNSUPPORTED = {
     "obj": "mesh canopy elements are not implemented",
     # the reference's remaining plugins for this slot
     "measured_mono": "only the quasi-diffuse measured BSDF ('mqdiffuse') is implemented",
-    "selectbsdf": "this BSDF adapter is not implemented",
 }
 
 
@@ -434,6 +433,25 @@ class _Loader:
                 if name not in d:
                     raise RuntimeError(f"hapke: missing required parameter '{name}'")
                 b.children[name] = tex(name, 0.0)
+        elif ty == "selectbsdf":
+            # ERP/bsdfs/selectbsdf.cpp:62-96: an index texture picks one of >= 2 nested BSDFs; traverse() publishes
+            # `indices` and `bsdf_<i>` in order of appearance.  A 1D scene has no surface position, so the index
+            # texture must be uniform: the selected BSDF is then THE surface BSDF (resolved by the flattener; an
+            # update of `indices.value` re-creates the device scene).
+            nested = [v for k, v in d.items() if isinstance(v, dict) and k != "indices"
+                      and (_KIND_OF.get(v.get("type")) == "bsdf" or v.get("type") == "ref")]
+            if len(nested) < 2:
+                raise RuntimeError("SelectBSDF: At least two child BSDFs must be specified!")
+            idx = d.get("indices")
+            if isinstance(idx, dict) and idx.get("type") != "uniform":
+                raise RuntimeError(f"selectbsdf: only a uniform 'indices' texture is supported, got '{idx.get('type')}' "
+                                   "(the analytic 1D surfaces carry no texture coordinates)")
+            if idx is None:
+                raise RuntimeError("selectbsdf: missing required parameter 'indices'")
+            b.children["indices"] = tex("indices", 0.0)
+            b.children["indices"].rebuild_on_change = True
+            for i, child in enumerate(nested):
+                b.children[f"bsdf_{i}"] = self.resolve(child)
         elif ty == "blendbsdf":
             # MI/src/bsdfs/blendbsdf.cpp as emitted by CentralPatchSurface (scenes/surface/_central_patch.py:
             # 185-215): weight = the 3x3 central-patch mask (nearest filter, clamped), so the blend is a switch:
@@ -893,6 +911,14 @@ class FlatScene:
         self.surface_shape = srf[0]
         self.atm_shape = atm[0] if atm else None
         self.bsdf: BSDF = self.surface_shape.children["bsdf"]
+        if self.bsdf.type == "selectbsdf":  # selectbsdf.cpp:98-110: UInt32(indices->eval_1(si)) picks the BSDF
+            n_sel = sum(1 for k in self.bsdf.children if k.startswith("bsdf_"))
+            i_sel = int(np.uint32(self.bsdf.children["indices"].values["value"]))
+            if not 0 <= i_sel < n_sel:
+                raise RuntimeError(f"selectbsdf: index {i_sel} out of range (the plugin holds {n_sel} BSDFs)")
+            self.bsdf = self.bsdf.children[f"bsdf_{i_sel}"]
+            if self.bsdf.type in ("selectbsdf", "blendbsdf"):
+                raise RuntimeError("selectbsdf: nested BSDF adapters are not supported")
         self.patch_bsdf: BSDF | None = None
         if self.bsdf.type == "blendbsdf":  # CentralPatchSurface: background + patch
             self.patch_blend = self.bsdf
@@ -1344,7 +1370,10 @@ def _phase_leaf_desc(ph: PhaseFunction):
     if ph.type == "tabphase_polarized":
         return _abi.PHASE_TABULATED_POLARIZED, params, ph.values["m11"], ph.values["nodes"]
     if ph.type in ("rayleigh", "rayleigh_polarized"):
-        params[0] = float(ph.children["depolarization"].layer_values().flat[0])
+        dep = ph.children["depolarization"].layer_values()
+        if not np.all(dep == dep.flat[0]):  # (also reached by parameter updates: never silently use layer 0)
+            raise RuntimeError("rayleigh: layer-dependent depolarization is unsupported")
+        params[0] = float(dep.flat[0])
         if params[0] >= 1.0:
             raise RuntimeError("Depolarization factor must be in [0, 1[")
         ty = _abi.PHASE_RAYLEIGH_POLARIZED if ph.type == "rayleigh_polarized" else _abi.PHASE_RAYLEIGH

@@ -91,6 +91,9 @@ def to_mitsuba(mi, value):
     from eradiate_b200.kernel._types import ScalarTransform4f, VolumeGrid
 
     if isinstance(value, dict):
+        if value.get("type") == "bitmap" and str(value.get("filename", "")).endswith("central_patch_surface_mask.bmp"):
+            # Eradiate ships this 3x3 mask (white centre) with its data; an equivalent file lives next to the fixtures
+            value = dict(value, filename=os.path.join(_HERE, "..", "tests", "golden", "central_patch_surface_mask.bmp"))
         return {k: to_mitsuba(mi, v) for k, v in value.items()}
     if isinstance(value, ScalarTransform4f):
         return mi.ScalarTransform4f(np.asarray(value.matrix, dtype=np.float64))

@@ -227,6 +227,12 @@ def battery() -> dict:
         "max_depth_3_rr_2": S(geometry="plane_parallel", atmosphere="homogeneous", max_depth=3, rr_depth=2,
                               homogeneous_sigma_t=2.0 / scenes.TOA, sensor=VZA5),
         "no_atmosphere_rpv_spherical": S(atmosphere=None, sensor=VZA5),
+        # ERP/bsdfs/selectbsdf.cpp with a uniform index texture: the selected BSDF (here the second one) is the surface
+        "selectbsdf_uniform_index_pp": S(geometry="plane_parallel", n_layers=50, sensor=VZA5, surface={
+            "type": "selectbsdf", "indices": {"type": "uniform", "value": 1.0},
+            "bsdf_0": {"type": "diffuse", "reflectance": {"type": "uniform", "value": 0.05}},
+            "bsdf_1": {"type": "rtls", "f_iso": {"type": "uniform", "value": 0.25},
+                       "f_vol": {"type": "uniform", "value": 0.1}, "f_geo": {"type": "uniform", "value": 0.02}}}),
         # piecewise medium + piecewise_volpath (the default Eradiate picks for plane-parallel atmospheres,
         # experiments/_atmosphere.py:165-184): analytic free flights, exact shadow-ray transmittance
         "piecewise_afgl_rpv_pp": S(geometry="plane_parallel", integrator="piecewise_volpath", sensor=VZA5,

@@ -1105,3 +1105,66 @@ def test_pcg32_build_matches_reference_fixture(name):
     z = z_scores(mean, var, np.array(ref["mean"]), np.array(ref["var_of_mean"]), rel_floor=2e-6)
     ok, zc = sidak_ok(z)
     assert ok and np.all(np.abs(z) <= 4.5), f"{name} (PCG32 build): |z| max {np.abs(z).max():.2f} > {zc:.2f}"
+
+
+# ------------------------------------------------------------------ one process per GPU
+def test_sharded_render_uses_the_device_of_each_rank():
+    """`dist.mi_render_sharded` under torchrun: every rank renders on ITS device (torch.cuda.set_device(LOCAL_RANK)),
+    not on device 0 of the box, and the sample-sharded film equals the single-GPU one (same seeds, disjoint sample
+    ranges, one all-reduce).  Needs two GPUs; skipped on a one-GPU box."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import os, sys, json; sys.path.insert(0, %r)\n"
+        "import numpy as np, torch, torch.distributed as dist\n"
+        "torch.cuda.set_device(int(os.environ['LOCAL_RANK']))\n"
+        "dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))\n"
+        "from eradiate_b200 import scenes\n"
+        "from eradiate_b200.dist import mi_render_sharded\n"
+        "from eradiate_b200.kernel import KernelContext, SeedState, mi_load_dict, mi_traverse\n"
+        "from eradiate_b200.kernel._render import _device_scene\n"
+        "sc = mi_load_dict(scenes.config_c2(spp=1 << 12, n_vza=8))\n"
+        "ms = mi_traverse(sc, scenes.spectral_update_map(1200, True))\n"
+        "ctxs = [KernelContext(w=550.0), KernelContext(w=600.0)]\n"
+        "out = {}\n"
+        "for shard in ('samples', 'contexts'):\n"
+        "    res = mi_render_sharded(ms, ctxs, spp=1 << 12, seed_state=SeedState(3), shard=shard)\n"
+        "    out[shard] = [float(np.array(res[c.si.as_hashable]['measure'])[..., 0].sum()) for c in ctxs]\n"
+        "out['device'] = _device_scene(sc).device\n"
+        "out['rank'] = dist.get_rank()\n"
+        "print('RESULT ' + json.dumps(out), flush=True)\n"
+        "dist.destroy_process_group()\n"
+    ) % root
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", "-c", code]
+    # torchrun has no -c: write the script to a temporary file
+    import tempfile
+
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(code)
+        script = f.name
+    cmd = cmd[:-2] + [script]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    os.unlink(script)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rows = [json.loads(ln.split("RESULT ", 1)[1]) for ln in r.stdout.splitlines() if "RESULT " in ln]
+    assert len(rows) == 2
+    for row in rows:
+        assert row["device"] == row["rank"], row  # LOCAL_RANK == RANK on one node
+    # every rank holds the complete, identical result
+    assert rows[0]["samples"] == rows[1]["samples"] and rows[0]["contexts"] == rows[1]["contexts"]
+    # single-GPU reference in this process: same seeds -> the context-sharded films are identical, the
+    # sample-sharded ones equal to the order of the float64 sums
+    sc = mi_load_dict(scenes.config_c2(spp=1 << 12, n_vza=8))
+    ms = mi_traverse(sc, scenes.spectral_update_map(1200, True))
+    ctxs = [KernelContext(w=550.0), KernelContext(w=600.0)]
+    res = mi_render(ms, ctxs, spp=1 << 12, seed_state=SeedState(3))
+    one = [float(np.array(res[c.si.as_hashable]["measure"])[..., 0].sum()) for c in ctxs]
+    assert np.allclose(rows[0]["contexts"], one, rtol=1e-6)
+    assert np.allclose(rows[0]["samples"], one, rtol=1e-5)

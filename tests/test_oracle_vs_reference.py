@@ -138,7 +138,9 @@ def test_reference_loses_rays_through_the_ground():
 _PASSIVE = ("to_world", "silhouette_sampling_weight", "sampling_weight", "film.size", "film.crop_size",
             "film.crop_offset", "shutter_open", "shutter_open_time", "allow_thread_reordering",
             # the 12-triangle mesh of the `cube` stencil (an analytic slab here)
-            "faces", "vertex_normals", "vertex_positions", "vertex_texcoords")
+            "faces", "vertex_normals", "vertex_positions", "vertex_texcoords",
+            # the 3x3 mask bitmap of a CentralPatchSurface and its placement
+            "weight.data", "weight.to_uv")
 
 
 def _is_passive(key: str) -> bool:

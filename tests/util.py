@@ -41,6 +41,10 @@ REFERENCE_GROUND_LEAK = {
     "piecewise_ocean_hdistant_pp": 0.0056,
     "piecewise_distantflux_coarse_pp": 0.0056,
     "canopy_hdistant_maxdepth_pp": 0.0056,
+    # principal-plane mdistant camera rays do not leak, but rays scattered back down by leaves and trunks reach the
+    # (bright, rho = 0.5) ground from every direction: the oracle at 5e6 paths and the CUDA path agree with each other
+    # and sit 0.1-0.3 % above the reference, as a 0.56 % loss of the ground's multiple-scattering share predicts
+    "canopy_abstract_trees_pp": 0.0056,
 }
 
 

@@ -74,4 +74,26 @@ with open(out + ".md", "w") as f:
     for (fl, ln), (s, ie, tie) in top:
         f.write(f"| {fl}:{ln} | {100*ie/tot:.1f}% | {tie/max(ie,1):.1f} | `{s.replace('|', '/')}` |\n")
 json.dump({"report": rep, "kernels": [{k: v[0] for k, v in kk.items()} for kk in kernels]}, open(out + ".json", "w"), indent=1)
+if "--bench-json" in sys.argv:
+    # profiles/render_kernel_profile.json: what bench.py's issue roofline reads (instruction count of one launch of the
+    # headline workload), tied to the build it was captured from by the hash of the CUDA sources
+    import hashlib, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha256()
+    d = os.path.join(root, "eradiate_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    h.update(open(os.path.join(root, "include", "eradiate_b200.h"), "rb").read())
+    k0 = kernels[0]
+    json.dump({
+        "capture": out + ".md", "kernel": k0["Kernel Name"][0], "csrc_sha16": h.hexdigest()[:16],
+        "warp_inst_per_launch": float(k0["smsp__inst_executed.sum"][0]),
+        "thread_inst_per_warp_inst": float(k0["smsp__thread_inst_executed_per_inst_executed.ratio"][0]),
+        "dram_bytes_per_launch": float(k0["dram__bytes_read.sum"][0]) * {"Kbyte": 1e3, "Mbyte": 1e6, "byte": 1.0, "Gbyte": 1e9}[k0["dram__bytes_read.sum"][1]]
+                                 + float(k0["dram__bytes_write.sum"][0]) * {"Kbyte": 1e3, "Mbyte": 1e6, "byte": 1.0, "Gbyte": 1e9}[k0["dram__bytes_write.sum"][1]],
+        "issue_active_pct": float(k0["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+        "ncu_duration_ms": float(k0["gpu__time_duration.sum"][0]),
+    }, open(os.path.join(root, "profiles", "render_kernel_profile.json"), "w"), indent=1)
+    print("wrote profiles/render_kernel_profile.json")
 print("wrote", out + ".md")
