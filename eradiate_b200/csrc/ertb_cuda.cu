@@ -404,6 +404,7 @@ static int build_canopy(ertb_scene *S) {
 }
 
 static size_t align4(size_t n) { return (n + 3) & ~size_t(3); }
+static double wall_ms();
 
 // Banded majorant (ertb_kernel_pool.cuh): cut the layer stack into <= ERTB_MAX_BANDS contiguous bands
 // minimising the expected cost of a vertical traverse in units of one loop trip,
@@ -1397,10 +1398,20 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     if (chunk < 32) chunk = 32;
     if (chunk > spp) chunk = spp;
     P.chunk = (unsigned) chunk;
-    // Lanes switch pixel once or twice per chunk. The per-lane flush atomics of one render (about
-    // n_chunks x 64 lanes x 3) drain at ~0.3 ns each in the L2 atomic unit: hidden behind the walk
-    // for chunks of >= 512 paths (C2: 590), the bottleneck below that -> collective flushes.
-    coll = chunk < 512;
+    // Film flush. Lanes switch pixel once or twice per chunk, and a per-lane flush is three float64 atomics on one of
+    // 3 x n_pixels addresses: ~10^7 atomics per C2 launch. Round 1 used per-lane flushes for chunks of >= 512 paths
+    // ("hidden behind the walk") and the warp-collective flush (lanes grouped by pixel, shuffle reduction, one lane
+    // issues the atomics) below that. Measured in round 2 (profiles/r02k_film_flush.md): the per-lane variant's time
+    // depends on WHERE the accumulators were allocated -- 3.49 ms with bench.py's torch buffer, 4.05 ms with the
+    // library's own cudaMalloc'ed film behind ertb_render / mi_render, same kernel, same parameters -- while the
+    // collective variant runs in 3.60 ms wherever they are. The pool kernel therefore always flushes collectively;
+    // ERTB_FLUSH=lane keeps the other variant reachable for A/B runs.
+    coll = use_pool;
+    {
+        static const char *e = getenv("ERTB_FLUSH"); // developer knob (lane | coll)
+        if (e && strcmp(e, "coll") == 0) coll = true;
+        if (e && strcmp(e, "lane") == 0) coll = chunk < 512;
+    }
     if (coll && use_pool && !with_stats) { // same resources, but the attribute is per instantiation
         int bps = 0;
         std::swap(bps, blocks_per_sm);
@@ -1432,6 +1443,19 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
         if (div > 1 && blocks_per_sm / div >= 1) grid = (unsigned long long) S->sm_count * (blocks_per_sm / div);
     }
     if (want_blocks < grid) grid = want_blocks ? want_blocks : 1;
+    {
+        static const bool dump = getenv("ERTB_DUMP_PARAMS") != nullptr; // developer aid
+        if (dump) {
+            unsigned long long h = 1469598103934665603ULL;
+            const unsigned char *pb = (const unsigned char *) &P;
+            for (size_t i = 0; i < sizeof P; ++i) { h ^= pb[i]; h *= 1099511628211ULL; }
+            fprintf(stderr, "ertb launch: grid %llu block %d smem %zu tw %d twi %d chunk %u n_chunks %llu spp %llu off %llu seed %llu "
+                            "npix %u stats %p with_stats %d coll %d bands %d use_table %d sensor_type %d params_hash %016llx\n",
+                    grid, block, smem, P.tw, P.twi, P.chunk, P.n_chunks, (unsigned long long) P.spp,
+                    (unsigned long long) P.sample_offset, (unsigned long long) P.seed, P.n_pixels, (void *) P.stats,
+                    (int) with_stats, (int) coll, P.n_bands, P.sensor.use_table, P.sensor.type, h);
+        }
+    }
 #define ERTB_LAUNCH(KERNEL) KERNEL<<<(unsigned) grid, block, smem, stream>>>(P)
     ERTB_DISPATCH(ERTB_LAUNCH);
 #undef ERTB_LAUNCH
@@ -1461,16 +1485,26 @@ int ertb_render_stokes(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp, u
         CUDA_TRY(cudaMalloc(&S->d_accum, bytes));
         S->d_accum_capacity = bytes;
     }
+    static const bool timing = getenv("ERTB_TIMING") != nullptr; // developer aid: host time of each step of the call
+    const double t0 = timing ? wall_ms() : 0.0;
     CUDA_TRY(cudaMemsetAsync(S->d_accum, 0, bytes, 0));
     unsigned long long *d_stats = S->d_counter + 8;
     CUDA_TRY(cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), 0));
     CUDA_TRY(cudaEventRecord(S->ev0, 0));
+    const double t1 = timing ? wall_ms() : 0.0;
     if (launch_render(S, sensor, seed, spp, sample_offset, S->d_accum, d_stats, 0, stats != nullptr)) return 1;
+    const double t2 = timing ? wall_ms() : 0.0;
     CUDA_TRY(cudaEventRecord(S->ev1, 0));
     std::vector<double> host((size_t) rows * npix);
     {
         NvtxRange nvtx("ertb:film_readback");
         CUDA_TRY(cudaMemcpy(host.data(), S->d_accum, bytes, cudaMemcpyDeviceToHost));
+    }
+    if (timing) {
+        float kms = 0.f;
+        cudaEventElapsedTime(&kms, S->ev0, S->ev1);
+        fprintf(stderr, "ertb_render: memsets %.3f ms, commit + launch %.3f ms, wait + read-back %.3f ms, kernel (events) %.3f ms\n",
+                t1 - t0, t2 - t1, wall_ms() - t2, kms);
     }
     if (sum_stokes) {
         if (S->polarized) memcpy(sum_stokes, host.data() + 3 * (size_t) npix, 4 * (size_t) npix * sizeof(double));

@@ -46,6 +46,9 @@
 #ifndef ERTB_POOL_MINB_POL
 #define ERTB_POOL_MINB_POL 1 // polarized instances: CTAs per SM at ERTB_POOL_BLOCK_POL threads
 #endif
+#ifndef ERTB_WALK_UNROLL
+#define ERTB_WALK_UNROLL 2 // free flights per loop-control vote in the walk phase
+#endif
 #ifndef ERTB_POOL_NS_POL
 #define ERTB_POOL_NS_POL 64 // records per warp of the polarized instances
 #endif
@@ -258,6 +261,11 @@ __global__ void __launch_bounds__(POL ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK, P
     static_assert(!(PW && SPH), "the piecewise medium is a plane-parallel layer stack");
     constexpr int NS = POL ? ERTB_POOL_NS_POL : ERTB_POOL_NS; // records per warp
     constexpr int NK = NS / 32;
+#ifdef ERTB_WALK_UNROLL_ALL
+    constexpr int WALK_UNROLL = ERTB_WALK_UNROLL;
+#else
+    constexpr int WALK_UNROLL = BANDS ? 1 : ERTB_WALK_UNROLL; // (see the walk phase)
+#endif
     constexpr int NF = (POL ? PF_COUNT_POL : PF_COUNT) + (BANDS ? 2 : 0);
     constexpr int PF_SB = NF - 2, PF_BAND = NF - 1; // (BANDS only)
     extern __shared__ __align__(16) float smem[];
@@ -375,10 +383,18 @@ __global__ void __launch_bounds__(POL ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK, P
             // depth is constant during a walk: hoist the Russian-roulette / max-depth predicates
             const bool rr_on = !P.mis && (flags >> PFL_DEPTH_SHIFT) > P.rr_depth;
             const bool depth_done = (flags >> PFL_DEPTH_SHIFT) >= P.max_depth;
+            // shared-memory address of the p_real table, formed once: indexed with a per-lane layer the generic
+            // pointer made the compiler rebuild the window base (S2UR + 3 uniform ops) on every trip
+            const unsigned preal_s = smem_u32(tb + P.off_preal);
             for (;;) {
-                const bool walking = mode == PM_WALK_MAIN || mode == PM_WALK_NEE;
-                if (__popc(__ballot_sync(0xffffffffu, walking)) < keep) break;
-                if (walking) {
+                if (__popc(__ballot_sync(0xffffffffu, mode == PM_WALK_MAIN || mode == PM_WALK_NEE)) < keep) break;
+                // ERTB_WALK_UNROLL free flights per vote: the vote + count + compare + branch of the loop control
+                // are a fifth of a trip's instructions; a lane that stops walking idles for at most one extra trip
+                // (C2 +4.8 % at 2, nothing more at 3, -5 % at 4; the banded walk, whose trip holds the band loop, loses
+                // 5-18 % when unrolled: it keeps one flight per vote)
+#pragma unroll
+                for (int rep = 0; rep < WALK_UNROLL; ++rep)
+                if (mode == PM_WALK_MAIN || mode == PM_WALK_NEE) {
                     const bool is_main = mode == PM_WALK_MAIN;
                     bool alive = true;
                     if (is_main && rr_on) { // volpath.cpp:194-198: every main loop trip
@@ -431,7 +447,8 @@ __global__ void __launch_bounds__(POL ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK, P
                             }
                         } else {
                             float h = altitude_at<SPH>(P, h0, b, s);
-                            float preal = tb[P.off_preal + layer_of(P, h)];
+                            float preal;
+                            asm("ld.shared.f32 %0, [%1];" : "=f"(preal) : "r"(preal_s + 4u * (unsigned) layer_of(P, h)));
                             if (BANDS) preal = fminf(preal * bratio, 1.f); // relative to the band's majorant
                             if (is_main) {
                                 if (pcg_float(rng) >= 1.f - preal) mode = PM_SCAT; // real collision
