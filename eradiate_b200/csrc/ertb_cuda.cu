@@ -1440,6 +1440,8 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
         // items run side by side and the drain of one overlaps the bulk of the next
         int div = ERTB_BATCH_GRID_DIV;
         div = env_int_clamped("ERTB_BATCH_GRID_DIV", div, 1, 64);
+        const int n_items = (int) S->batch.sensors.size(); // a batch of one or two items has nothing to share with
+        if (n_items < div) div = n_items > 0 ? n_items : 1;
         if (div > 1 && blocks_per_sm / div >= 1) grid = (unsigned long long) S->sm_count * (blocks_per_sm / div);
     }
     if (want_blocks < grid) grid = want_blocks ? want_blocks : 1;
