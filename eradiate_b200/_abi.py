@@ -30,6 +30,7 @@ BSDF_OCEAN_MISHCHENKO = 6
 BSDF_OCEAN_GRASP = 7
 BSDF_MAIGNAN = 8
 BSDF_MQDIFFUSE = 9
+BSDF_MEASURED_MONO = 10
 
 # enum ertb_phase_type
 PHASE_ISOTROPIC = 0

@@ -757,6 +757,8 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
     } else if (S->bsdf_type == ERTB_BSDF_MQDIFFUSE) {
         for (int i = 0; i < 3; ++i) P.bsdf[i] = (float) S->bsdf_table_res[i];
         P.ocean_tables = S->d_bsdf_table;
+    } else if (S->bsdf_type == ERTB_BSDF_MEASURED_MONO) {
+        P.ocean_tables = S->d_bsdf_table; // self-describing: sizes and offsets in its header
     } else if (S->bsdf_type >= ERTB_BSDF_OCEAN_MISHCHENKO) {
         ertb_ocean_host::derive_glint(S->bsdf_type, S->bsdf_params, P.bsdf);
     }
@@ -964,6 +966,34 @@ void ertb_scene_destroy(ertb_scene *S) {
     delete S;
 }
 
+// measured_mono: the device indexes the table through the sizes / offsets of its header (ertb_measured.cuh), so
+// every one of them is checked against the array length here; nullptr when the table is well formed
+static const char *measured_table_error(const float *T, int n_floats) {
+    const long n = n_floats;
+    if (n < 32 || n >= (1 << 24)) return "measured_mono: invalid table size";
+    auto whole = [&](int k, long &v) { v = (long) T[k]; return T[k] >= 0.f && T[k] < 16777216.f && (float) v == T[k]; };
+    long h[28];
+    for (int k = 0; k < 28; ++k)
+        if (!whole(k, h[k])) return "measured_mono: malformed table header";
+    const long n_phi = h[0], n_theta = h[1], slices = n_phi * n_theta;
+    if (n_phi < 1 || n_theta < 1 || h[2] > 1 || h[3] > 1 || (h[4] != 0 && h[4] != 1 && h[4] != 2 && h[4] != 4))
+        return "measured_mono: malformed table header";
+    if (h[26] != (n_phi > 1 ? n_theta : 0) || h[27] != (n_theta > 1 ? 1 : 0)) return "measured_mono: malformed slice strides";
+    auto fits = [&](long off, long count) { return off >= 32 && count >= 0 && off + count <= n; };
+    auto grid = [&](int k) { return h[k] >= 2 && h[k + 1] >= 2; }; // w, h
+    if (!grid(5) || !grid(8) || !grid(11) || !grid(16) || !grid(21)) return "Distribution2D(): input array resolution must be >= 2!";
+    if (!fits(h[7], h[5] * h[6]) || !fits(h[10], h[8] * h[9]) || !fits(h[23], slices * h[21] * h[22]) ||
+        !fits(h[24], n_phi) || !fits(h[25], n_theta))
+        return "measured_mono: table offsets out of range";
+    for (int k : { 11, 16 })
+        if (!fits(h[k + 2], slices * h[k] * h[k + 1]) || !fits(h[k + 3], slices * (h[k + 1] - 1)) ||
+            !fits(h[k + 4], slices * h[k + 1] * (h[k] - 1)))
+            return "measured_mono: table offsets out of range";
+    for (long k = 0; k < n; ++k)
+        if (!std::isfinite(T[k])) return "measured_mono: non-finite table entry";
+    return nullptr;
+}
+
 int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
     if (!D || !out) return set_error("null argument");
     *out = nullptr;
@@ -973,7 +1003,11 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
     if (device < 0 || device >= ndev) return set_error("invalid CUDA device index");
     if (D->geometry != ERTB_GEOM_PLANE_PARALLEL && D->geometry != ERTB_GEOM_SPHERICAL_SHELL)
         return set_error("unsupported geometry");
-    if (D->bsdf_type < 0 || D->bsdf_type > ERTB_BSDF_MQDIFFUSE) return set_error("unsupported BSDF type");
+    if (D->bsdf_type < 0 || D->bsdf_type > ERTB_BSDF_MEASURED_MONO) return set_error("unsupported BSDF type");
+    if (D->bsdf_type == ERTB_BSDF_MEASURED_MONO) {
+        if (!D->bsdf_table) return set_error("measured_mono: missing table");
+        if (const char *why = measured_table_error(D->bsdf_table, D->bsdf_table_res[0])) return set_error(why);
+    }
     if (D->bsdf_type == ERTB_BSDF_MQDIFFUSE) {
         if (!D->bsdf_table) return set_error("mqdiffuse: missing table");
         for (int i = 0; i < 3; ++i)
@@ -1139,13 +1173,14 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
         ertb_scene_destroy(S);
         return set_error("device allocation failed");
     }
-    if (D->bsdf_type == ERTB_BSDF_MQDIFFUSE) { // the measured table lives in global memory (L2-resident)
+    if (D->bsdf_type == ERTB_BSDF_MQDIFFUSE || D->bsdf_type == ERTB_BSDF_MEASURED_MONO) { // the measured table lives in global memory (L2-resident)
         size_t n = 1;
         for (int i = 0; i < 3; ++i) { S->bsdf_table_res[i] = D->bsdf_table_res[i]; n *= (size_t) D->bsdf_table_res[i]; }
+        if (D->bsdf_type == ERTB_BSDF_MEASURED_MONO) n = (size_t) D->bsdf_table_res[0];
         if (cudaMalloc(&S->d_bsdf_table, n * sizeof(float)) != cudaSuccess ||
             cudaMemcpy(S->d_bsdf_table, D->bsdf_table, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
             ertb_scene_destroy(S);
-            return set_error("mqdiffuse: table upload failed");
+            return set_error("measured BSDF: table upload failed");
         }
     }
     for (int i = 0; i < D->n_sensors; ++i) {

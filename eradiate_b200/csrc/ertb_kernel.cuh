@@ -188,24 +188,24 @@ __device__ __forceinline__ void surface_frame(f3 n, f3 &s, f3 &t) {
 // estimation (`f_sun` = f * cos, 0 when not wanted) and BSDF sampling (new direction `d`,
 // weight = f * cos / pdf).  `ci` = cos of the incident direction with the normal (> 0).
 // `SCALAR_ONLY`: the caller handles the Mueller-valued BSDFs itself (polarized instances of the pool kernel), so
-// their scalar code is not compiled into it; the only local-frame BSDF left here is mqdiffuse.
+// their scalar code is not compiled into it; the local-frame BSDFs left here are the table-driven ones.
 // `GENERAL` = false: only the plugin set of SURVEY 8a (see bsdf_is_local_t).
 template <bool SPH, bool SCALAR_ONLY = false, bool GENERAL = true>
 __device__ __forceinline__ void surface_interact(const ErtbParams &P, f3 n0, f3 sun, float ci, bool want_nee,
                                                  Pcg32 &rng, f3 &d, float &f_sun, float &weight) {
     f_sun = 0.f;
     weight = 0.f;
-    if (SCALAR_ONLY ? (GENERAL && P.bsdf_type == ERTB_BSDF_MQDIFFUSE) : bsdf_is_local_t<GENERAL>(P.bsdf_type)) { // 6SV ocean, glint family, mqdiffuse
+    if (SCALAR_ONLY ? (GENERAL && bsdf_is_table(P.bsdf_type)) : bsdf_is_local_t<GENERAL>(P.bsdf_type)) { // 6SV ocean, glint family, mqdiffuse, measured_mono
         f3 fs, ft;
         surface_frame<SPH>(n0, fs, ft);
         f3 wi = mk3(-dot3(d, fs), -dot3(d, ft), ci);
         if (want_nee) {
             f3 ws = mk3(dot3(sun, fs), dot3(sun, ft), dot3(sun, n0));
-            if (ws.z > 0.f) f_sun = SCALAR_ONLY ? mq_eval(P, wi, ws) : lf_eval<GENERAL>(P, wi, ws);
+            if (ws.z > 0.f) f_sun = SCALAR_ONLY ? tb_eval(P, wi, ws) : lf_eval<GENERAL>(P, wi, ws);
         }
         float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
         f3 wo;
-        weight = SCALAR_ONLY ? mq_sample(P, wi, u1, u2, wo) : lf_sample<GENERAL>(P, wi, s1, u1, u2, wo);
+        weight = SCALAR_ONLY ? tb_sample(P, wi, u1, u2, wo) : lf_sample<GENERAL>(P, wi, s1, u1, u2, wo);
         if (!(wo.z > 0.f)) weight = 0.f;
         d = normalize3(fma3(fs, wo.x, fma3(ft, wo.y, scale3(n0, wo.z))));
         return;

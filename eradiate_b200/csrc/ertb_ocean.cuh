@@ -13,6 +13,7 @@
 #pragma once
 
 #include "ertb_device.cuh"
+#include "ertb_measured.cuh"
 
 #define ERTB_OC_RES 64
 
@@ -648,16 +649,26 @@ __device__ __forceinline__ float mq_sample(const ErtbParams &P, f3 wi, float u1,
     return mq_tex(P, wo.z, mq_phi_d(wi, wo), wi.z) * ERTB_PI; // value * cos / pdf
 }
 
-// dispatch over the local-frame BSDFs (6SV ocean, glint family, mqdiffuse)
+// the table-driven scalar BSDFs (mqdiffuse, measured_mono): depolarizers in polarized scenes
+__device__ __forceinline__ bool bsdf_is_table(int t) { return t >= ERTB_BSDF_MQDIFFUSE; }
+__device__ __forceinline__ float tb_eval(const ErtbParams &P, f3 wi, f3 wo) {
+    return P.bsdf_type == ERTB_BSDF_MEASURED_MONO ? mm_eval(P, wi, wo) : mq_eval(P, wi, wo);
+}
+__device__ __forceinline__ float tb_sample(const ErtbParams &P, f3 wi, float u1, float u2, f3 &wo) {
+    float pdf;
+    return P.bsdf_type == ERTB_BSDF_MEASURED_MONO ? mm_sample(P, wi, u1, u2, wo, pdf) : mq_sample(P, wi, u1, u2, wo);
+}
+
+// dispatch over the local-frame BSDFs (6SV ocean, glint family, mqdiffuse, measured_mono)
 template <bool GENERAL = true>
 __device__ __forceinline__ float lf_eval(const ErtbParams &P, f3 wi, f3 wo) {
     if (!GENERAL || P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) return oc_eval(P, wi, wo);
-    if (P.bsdf_type == ERTB_BSDF_MQDIFFUSE) return mq_eval(P, wi, wo);
+    if (bsdf_is_table(P.bsdf_type)) return tb_eval(P, wi, wo);
     return gl_eval(P, wi, wo);
 }
 template <bool GENERAL = true>
 __device__ __forceinline__ float lf_sample(const ErtbParams &P, f3 wi, float s1, float u1, float u2, f3 &wo) {
     if (!GENERAL || P.bsdf_type == ERTB_BSDF_OCEAN_LEGACY) return oc_sample(P, wi, s1, u1, u2, wo);
-    if (P.bsdf_type == ERTB_BSDF_MQDIFFUSE) return mq_sample(P, wi, u1, u2, wo);
+    if (bsdf_is_table(P.bsdf_type)) return tb_sample(P, wi, u1, u2, wo);
     return gl_sample(P, wi, s1, u1, u2, wo);
 }

@@ -231,7 +231,7 @@ _SUPPORTED = {
     "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance", "cylinder"},
     "medium": {"heterogeneous", "homogeneous", "piecewise"},
     "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "ocean_mishchenko", "ocean_grasp", "maignan",
-             "mqdiffuse", "null", "bilambertian", "blendbsdf", "selectbsdf"},
+             "mqdiffuse", "measured_mono", "null", "bilambertian", "blendbsdf", "selectbsdf"},
     "phase": {"isotropic", "rayleigh", "hg", "tabphase", "tabphase_irregular", "blendphase",
               "rayleigh_polarized", "tabphase_polarized", "multiphase"},
     "sensor": {"mdistant", "hdistant", "distantflux", "perspective", "mpdistant", "mradiancemeter"},
@@ -242,8 +242,6 @@ _KIND_OF = {ty: kind for kind, types in _SUPPORTED.items() for ty in types}
 _KNOWN_UNSUPPORTED = {
     "ply": "mesh canopy elements are not implemented",
     "obj": "mesh canopy elements are not implemented",
-    # the reference's remaining plugins for this slot
-    "measured_mono": "only the quasi-diffuse measured BSDF ('mqdiffuse') is implemented",
 }
 
 
@@ -516,6 +514,14 @@ class _Loader:
             if data.shape[-1] != 1:
                 raise RuntimeError("mqdiffuse: only 1-channel grids are supported")
             b.table = np.ascontiguousarray(data[..., 0], dtype=np.float32)  # [z, y, x] = [cos_theta_i, phi_d, cos_theta_o]
+        elif ty == "measured_mono":  # measured_mono.cpp:47-54, :224-226
+            from ._measured import MeasuredData
+
+            if "filename" not in d:
+                raise RuntimeError('Property "filename" has not been specified!')
+            b.measured = MeasuredData(str(d["filename"]))
+            b.values["wavelength"] = float(d.get("wavelength", 550.0))
+            b.rebuild_on_change = True  # the table is re-blended at the new wavelength and uploaded again
         elif ty == "maignan":  # maignan.cpp:92-101 (constructor defaults, not the documented ones)
             b.children["C"] = tex("C", 0.1)
             b.children["ndvi"] = tex("ndvi", 0.0)
@@ -1209,6 +1215,7 @@ class FlatScene:
             "ocean_grasp": _abi.BSDF_OCEAN_GRASP,
             "maignan": _abi.BSDF_MAIGNAN,
             "mqdiffuse": _abi.BSDF_MQDIFFUSE,
+            "measured_mono": _abi.BSDF_MEASURED_MONO,
         }[(self.bsdf if b is None else b).type]
 
     # -- ctypes descriptor -----------------------------------------------------------------
@@ -1276,6 +1283,11 @@ class FlatScene:
             keep.append(tab)
             d.bsdf_table = tab.ctypes.data_as(_abi.c_float_p)
             d.bsdf_table_res[:] = [tab.shape[2], tab.shape[1], tab.shape[0]]
+        elif self.bsdf.type == "measured_mono":
+            tab = self.bsdf.measured.table(self.bsdf.values["wavelength"])
+            keep.append(tab)
+            d.bsdf_table = tab.ctypes.data_as(_abi.c_float_p)
+            d.bsdf_table_res[:] = [tab.size, 1, 1]
         d.emitter_direction[:] = list(self.emitter.direction)
         d.irradiance = self.emitter.children["irradiance"].values["value"]
         d.emitter_angular_diameter = getattr(self.emitter, "angular_diameter", 0.0)

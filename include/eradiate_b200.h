@@ -69,7 +69,13 @@ enum ertb_bsdf_type {
     /* ERP/bsdfs/mqdiffuse.cpp:56-210 (measured quasi-diffuse: trilinear, clamped lookup of a
      * (cos_theta_o, phi_d, cos_theta_i) table, cosine-hemisphere sampling); no params, table in
      * `bsdf_table` / `bsdf_table_res` */
-    ERTB_BSDF_MQDIFFUSE = 9
+    ERTB_BSDF_MQDIFFUSE = 9,
+    /* ERP/bsdfs/measured_mono.cpp:40-512 (RGL measured material, Dupuy & Jakob 2018, at one wavelength): five
+     * Marginal2D<.., Continuous> interpolants (MI/include/mitsuba/core/distr_2d.h:868-1480) flattened by the host
+     * into one float table, `bsdf_table` with `bsdf_table_res` = { number of floats, 1, 1 }; the layout (a 32-float
+     * header of sizes / offsets, then the tables; `spectra` already blended at the scene wavelength) is the one
+     * eradiate_b200/kernel/_measured.py documents and ertb_scene_create() validates; no params */
+    ERTB_BSDF_MEASURED_MONO = 10
 };
 
 enum ertb_phase_type {
@@ -244,7 +250,7 @@ typedef struct ertb_scene_desc {
     /* mqdiffuse: the plugin's VolumeGrid, data[z][y][x] with x = cos_theta_o, y = phi_d / 2 pi, z = cos_theta_i
      * (mqdiffuse.cpp:80-86); copied at scene creation, not updatable (the plugin exposes no parameter) */
     const float *bsdf_table;
-    int32_t bsdf_table_res[3];      /* x, y, z */
+    int32_t bsdf_table_res[3];      /* x, y, z; measured_mono: { number of floats, 1, 1 } */
     /* ERP/phase/multiphase.cpp:176-200 (`use_mis`, root node only): the weight of a sampled direction is the mixture
      * sum_j w_j value_j / sum_j w_j pdf_j over all leaves instead of the drawn leaf's own weight.  Only set when
      * that differs (a leaf whose value is not its pdf: depolarized Rayleigh, Mueller-valued phase functions). */

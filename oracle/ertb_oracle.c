@@ -31,6 +31,7 @@
 
 #include "ertb_oracle_ocean.h"
 #include "ertb_oracle_canopy.h"
+#include "ertb_oracle_measured.h"
 
 #define PI 3.14159265358979323846
 #define INV_PI (1.0 / PI)
@@ -351,6 +352,8 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
         S->astro_cos = cos(0.5 * d->emitter_angular_diameter * PI / 180.0);
         S->astro_omega = 2.0 * PI * (1.0 - S->astro_cos);
     }
+    if (d->bsdf_type == ERTB_BSDF_MEASURED_MONO && (!d->bsdf_table || d->bsdf_table_res[0] < 32))
+        return fail("measured_mono: missing table");
     if (d->bsdf_type == ERTB_BSDF_MQDIFFUSE &&
         (!d->bsdf_table || d->bsdf_table_res[0] < 1 || d->bsdf_table_res[1] < 1 || d->bsdf_table_res[2] < 1))
         return fail("mqdiffuse: missing table");
@@ -1126,6 +1129,10 @@ static double bsdf_eval_tp(const scene_t *S, int type, const float *P, v3 wi, v3
             if (phi_d < 0.0) phi_d += 2.0 * PI;
             return mq_texture(S->desc, cto, phi_d, cti) * cto;
         }
+        case ERTB_BSDF_MEASURED_MONO: { /* measured_mono.cpp:339-393: the tables already hold f * cos */
+            double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
+            return mm_oracle_eval(S->desc->bsdf_table, a, b);
+        }
         default: return 0.0;
     }
 }
@@ -1143,6 +1150,11 @@ static double bsdf_sample_tp(const scene_t *S, int type, const float *P, v3 wi, 
     }
     if (is_glint_family(type)) {
         double a[3] = { wi.x, wi.y, wi.z }, o[3], w = glint_sample(&S->glint, a, s1, u1, u2, o);
+        *wo = V(o[0], o[1], o[2]);
+        return w;
+    }
+    if (type == ERTB_BSDF_MEASURED_MONO) { /* measured_mono.cpp:234-337 */
+        double a[3] = { wi.x, wi.y, wi.z }, o[3], w = mm_oracle_sample(S->desc->bsdf_table, a, u1, u2, o, NULL);
         *wo = V(o[0], o[1], o[2]);
         return w;
     }
@@ -1504,6 +1516,10 @@ static double surf_pdf(const scene_t *S, v3 wi, v3 wo) {
     if (type == ERTB_BSDF_OCEAN_MISHCHENKO || type == ERTB_BSDF_OCEAN_GRASP) {
         double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
         return glint_pdf(&S->glint, a, b);
+    }
+    if (type == ERTB_BSDF_MEASURED_MONO) {
+        double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
+        return mm_oracle_pdf(S->desc->bsdf_table, a, b);
     }
     return INV_PI * wo.z; /* warp::square_to_cosine_hemisphere_pdf */
 }
@@ -1960,6 +1976,14 @@ int ertbo_bsdf_eval(const ertb_scene_desc *desc, size_t n, const double *wi, con
     if (scene_init(&S, desc)) return 1;
     for (size_t i = 0; i < n; ++i)
         out[i] = bsdf_eval(&S, V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
+    scene_free(&S);
+    return 0;
+}
+int ertbo_bsdf_pdf(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo, double *out) {
+    scene_t S;
+    if (scene_init(&S, desc)) return 1;
+    for (size_t i = 0; i < n; ++i)
+        out[i] = surf_pdf(&S, V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
     scene_free(&S);
     return 0;
 }

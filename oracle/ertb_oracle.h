@@ -46,6 +46,8 @@ int ertbo_phase_mueller(const ertb_scene_desc *desc, int leaf, size_t n, const d
 int ertbo_bsdf_mueller(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo, double *mueller);
 
 /* Point-wise plugin evaluations (double). Same conventions as ertb_kat_*. */
+/* BSDF::pdf of the ground BSDF (solid-angle density of BSDF::sample) */
+int ertbo_bsdf_pdf(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo, double *out);
 int ertbo_bsdf_eval(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo,
                     double *out);
 int ertbo_bsdf_sample(const ertb_scene_desc *desc, size_t n, const double *wi, const double *u,

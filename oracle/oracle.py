@@ -155,6 +155,14 @@ def bsdf_eval(desc, wi, wo):
     return out
 
 
+def bsdf_pdf(desc, wi, wo):
+    wi, wo = _d(wi).reshape(-1, 3), _d(wo).reshape(-1, 3)
+    out = np.zeros(wi.shape[0])
+    _check(load().ertbo_bsdf_pdf(C.byref(desc), C.c_size_t(wi.shape[0]), wi.ctypes.data_as(dp),
+                                 wo.ctypes.data_as(dp), out.ctypes.data_as(dp)))
+    return out
+
+
 def bsdf_sample(desc, wi, u):
     wi, u = _d(wi).reshape(-1, 3), _d(u).reshape(-1, 3)
     wo, w = np.zeros_like(wi), np.zeros(wi.shape[0])

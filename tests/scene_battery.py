@@ -1,7 +1,17 @@
 """Scene battery shared by the golden-fixture generator and the GPU parity tests."""
+import os
+
 import numpy as np
 
 from eradiate_b200 import scenes
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def measured(fname: str, wavelength: float) -> dict:
+    """`measured_mono` on one of the synthetic RGL tensor files of tests/golden (tools/make_measured_fixture.py)."""
+    return {"type": "measured_mono", "filename": os.path.join(GOLDEN, fname), "wavelength": wavelength}
+
 
 POMMEROL = dict(w=0.526, theta=13.3, b=0.187, c=(1.0 + 0.273) / 2.0, h=0.083, B_0=1.0)
 VZA5 = {"type": "mdistant", "vza": [-70.0, -35.0, 0.0, 35.0, 70.0], "vaa": 0.0}
@@ -149,6 +159,20 @@ def battery() -> dict:
                                        surface={"type": "mqdiffuse", "grid": mq_table(9, 13, 7)},
                                        sensor={"type": "mdistant", "vza": [-50.0, -20.0, 20.0, 50.0], "vaa": 140.0,
                                                "target": [2.0e5, 3.0e5, 6.3679007e6]}),
+        # measured_mono (measured_mono.cpp): isotropic and anisotropic (reduction = 2) tensor files, between two
+        # wavelength nodes; the thin atmosphere keeps the surface term dominant
+        "measured_iso_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=25.0,
+                             surface=measured("measured_iso.bsdf", 600.0),
+                             sensor={"type": "mdistant", "vza": [-60.0, -30.0, 0.0, 30.0, 60.0], "vaa": 70.0}),
+        "measured_aniso_spherical_thick": S(geometry="spherical_shell", atmosphere="homogeneous",
+                                            homogeneous_sigma_t=1.0 / scenes.TOA, homogeneous_albedo=0.95,
+                                            phase={"type": "hg", "g": 0.5}, sza=30.0, saa=200.0,
+                                            surface=measured("measured_aniso.bsdf", 520.0),
+                                            sensor={"type": "mdistant", "vza": [-50.0, -20.0, 20.0, 50.0], "vaa": 140.0,
+                                                    "target": [2.0e5, 3.0e5, 6.3679007e6]}),
+        "astro_measured_aniso_pp": S(geometry="plane_parallel", n_layers=40, sza=55.0, saa=120.0, angular_diameter=4.0,
+                                     surface=measured("measured_aniso.bsdf", 725.0),
+                                     sensor={"type": "mdistant", "vza": [-70.0, -40.0, -10.0, 20.0, 50.0], "vaa": 20.0}),
         # astroobject: a solar disc instead of the delta directional emitter (next-event directions in a cone, the
         # disc seen directly by unscattered primary rays)
         "astro_wide_disc_afgl_rpv_pp": S(geometry="plane_parallel", n_layers=100, sza=50.0, saa=30.0,
@@ -207,6 +231,10 @@ def battery() -> dict:
                                     phase={"type": "rayleigh_polarized"},
                                     surface={"type": "mqdiffuse", "grid": mq_table()},
                                     sensor={"type": "mdistant", "vza": [-55.0, -25.0, 15.0, 45.0], "vaa": 100.0}),
+        "polarized_measured_iso_pp": S(geometry="plane_parallel", n_layers=60, sza=50.0, saa=10.0, stokes=True,
+                                       phase={"type": "rayleigh_polarized"},
+                                       surface=measured("measured_iso.bsdf", 450.0),
+                                       sensor={"type": "mdistant", "vza": [-55.0, -25.0, 15.0, 45.0], "vaa": 100.0}),
         "polarized_astro_mishchenko_pp": S(geometry="plane_parallel", n_layers=60, sza=40.0, saa=0.0, stokes=True,
                                            phase={"type": "rayleigh_polarized"}, angular_diameter=3.0,
                                            surface={"type": "ocean_mishchenko", "wind_speed": 2.0, "eta": 1.33},
