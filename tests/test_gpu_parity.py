@@ -224,7 +224,8 @@ def test_measured_mono_on_device(oracle, fname, wavelength):
 
 def test_measured_mono_wavelength_update_on_device():
     """`wavelength` is the plugin's one parameter (:224-226): an update re-blends the table and re-creates the device
-    scene; the render then equals that of a scene loaded at the new wavelength (same seed: identical)."""
+    scene; the render then equals that of a scene loaded at the new wavelength (same seed: the same paths, summed by
+    atomics in a different order)."""
     from tests.scene_battery import measured
 
     kw = dict(geometry="plane_parallel", n_layers=20, sza=30.0,
@@ -235,7 +236,7 @@ def test_measured_mono_wavelength_update_on_device():
     mi_traverse(a).parameters.update({"surface_bsdf.wavelength": 725.0})
     ra1 = render(a, sensor=0, seed=3, spp=1 << 16).raw["sum_l"]
     rb = render(b, sensor=0, seed=3, spp=1 << 16).raw["sum_l"]
-    assert np.array_equal(ra1, rb) and not np.array_equal(ra0, ra1)
+    assert np.allclose(ra1, rb, rtol=1e-10) and not np.allclose(ra0, ra1, rtol=1e-3)
 
 
 def test_hapke_golden_on_device():
