@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 MAX_PHASE = 4
 MAX_BSDF_PARAMS = 16
 MAX_LAYERS = 4096
@@ -72,6 +72,7 @@ PARAM_PHASE_MUELLER = 7
 PARAM_LEAF_BSDF = 8
 PARAM_PATCH_BSDF_PARAMS = 9
 PARAM_TRUNK_BSDF = 10
+PARAM_MESH_BSDF = 11
 
 c_float_p = C.POINTER(C.c_float)
 c_double_p = C.POINTER(C.c_double)
@@ -122,7 +123,12 @@ class LeafGroupDesc(C.Structure):
         ("cylinders", c_float_p),
         ("trunk_disks", c_float_p),
         ("trunk_reflectance", C.c_float),
+        ("n_triangles", C.c_int32),
+        ("n_mesh_bsdfs", C.c_int32),
         ("_pad2", C.c_int32),
+        ("triangles", c_float_p),
+        ("triangle_bsdf", C.POINTER(C.c_int32)),
+        ("mesh_bsdfs", c_float_p),
     ]
 
 

@@ -97,8 +97,22 @@ __device__ __forceinline__ float cylinder_hit(float4 c, float4 ax, f3 o, f3 d, f
     return INFINITY;
 }
 
-__device__ __forceinline__ float prim_hit(float4 a, float4 b, f3 o, f3 d, float tmax) {
-    return __float_as_int(b.w) == 2 ? cylinder_hit(a, b, o, d, tmax) : disk_hit(a, b, o, d, tmax);
+// mesh.h:481-504 (Moeller-Trumbore): a = (v0, .), b = (e1, .), e2 from the triangle table
+__device__ __forceinline__ float triangle_hit(float4 a, float4 b, float4 c, f3 o, f3 d, float tmax) {
+    const f3 e1 = mk3(b.x, b.y, b.z), e2 = mk3(c.x, c.y, c.z);
+    const f3 pvec = cross3(d, e2);
+    const float inv_det = 1.f / dot3(e1, pvec);
+    const f3 tvec = mk3(o.x - a.x, o.y - a.y, o.z - a.z);
+    const float u = dot3(tvec, pvec) * inv_det;
+    const f3 qvec = cross3(tvec, e1);
+    const float v = dot3(d, qvec) * inv_det, t = dot3(e2, qvec) * inv_det;
+    return (u >= 0.f && u <= 1.f && v >= 0.f && u + v <= 1.f && t >= 0.f && t <= tmax) ? t : INFINITY;
+}
+
+__device__ __forceinline__ float prim_hit(const ErtbCanopy &C, float4 a, float4 b, f3 o, f3 d, float tmax) {
+    const int kind = __float_as_int(b.w);
+    if (kind == 3) return triangle_hit(a, b, __ldg(C.tris + 4 * __float_as_int(a.w)), o, d, tmax);
+    return kind == 2 ? cylinder_hit(a, b, o, d, tmax) : disk_hit(a, b, o, d, tmax);
 }
 
 struct TraceState {
@@ -143,7 +157,7 @@ __device__ __forceinline__ bool trace_run(const ErtbCanopy &C, TraceState &T, in
             } else { // disks: intersected on the spot
                 for (int k = c[s]; k < c[s] + n[s]; ++k) {
                     if (k == T.skip_disk && ii == T.skip_inst) continue;
-                    float t = prim_hit(__ldg(C.disks + 2 * k), __ldg(C.disks + 2 * k + 1), ol, d, fminf(T.tmax, T.H.t));
+                    float t = prim_hit(C, __ldg(C.disks + 2 * k), __ldg(C.disks + 2 * k + 1), ol, d, fminf(T.tmax, T.H.t));
                     if (t < T.H.t) { T.H.t = t; T.H.inst = ii; T.H.disk = k; }
                 }
             }
@@ -203,14 +217,28 @@ __device__ __forceinline__ f3 canopy_local(const ErtbCanopy &C, const double p[3
                (float) (p[2] + t0 * (double) d.z - C.origin[2]));
 }
 
-// surface normal and kind (0 leaf, 1 trunk cap, 2 trunk tube) of the primitive hit at world point q
-__device__ __forceinline__ f3 canopy_normal(const ErtbCanopy &C, const double q[3], const CanopyHit &H, int &kind) {
+// surface (shading) normal and kind (0 leaf, 1 trunk cap, 2 trunk tube, 3 mesh triangle) of the primitive hit at
+// world point q; `mat`: row of a triangle's BSDF in the mesh table
+__device__ __forceinline__ f3 canopy_normal(const ErtbCanopy &C, const double q[3], const CanopyHit &H, int &kind, int &mat) {
     const float4 a = __ldg(C.disks + 2 * H.disk), b = __ldg(C.disks + 2 * H.disk + 1);
     kind = __float_as_int(b.w);
-    if (kind != 2) return mk3(b.x, b.y, b.z);
+    mat = 0;
+    if (kind < 2) return mk3(b.x, b.y, b.z);
     const float4 in = __ldg(C.inst + H.inst);
     const f3 w = mk3((float) (q[0] - C.origin[0]) - in.x - a.x, (float) (q[1] - C.origin[1]) - in.y - a.y,
                      (float) (q[2] - C.origin[2]) - in.z - a.z);
+    if (kind == 3) { // mesh.cpp:1500-1535: barycentric interpolation of the vertex normals, renormalised
+        const float4 *t = C.tris + 4 * __float_as_int(a.w);
+        const float4 c = __ldg(t), n0 = __ldg(t + 1), n1 = __ldg(t + 2), n2 = __ldg(t + 3);
+        mat = __float_as_int(c.w);
+        const f3 e1 = mk3(b.x, b.y, b.z), e2 = mk3(c.x, c.y, c.z);
+        const float d11 = dot3(e1, e1), d12 = dot3(e1, e2), d22 = dot3(e2, e2), w1 = dot3(w, e1), w2 = dot3(w, e2);
+        const float inv = 1.f / (d11 * d22 - d12 * d12);
+        const float b1 = fminf(fmaxf((d22 * w1 - d12 * w2) * inv, 0.f), 1.f), b2 = fminf(fmaxf((d11 * w2 - d12 * w1) * inv, 0.f), 1.f);
+        const float b0 = 1.f - b1 - b2;
+        return normalize3(mk3(fmaf(n2.x, b2, fmaf(n1.x, b1, n0.x * b0)), fmaf(n2.y, b2, fmaf(n1.y, b1, n0.y * b0)),
+                              fmaf(n2.z, b2, fmaf(n1.z, b1, n0.z * b0))));
+    }
     const float iL = rsqrtf(b.x * b.x + b.y * b.y + b.z * b.z);
     const f3 u = mk3(b.x * iL, b.y * iL, b.z * iL);
     return normalize3(fma3(u, -dot3(w, u), w)); // radial, pointing outwards
@@ -609,13 +637,15 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 if (STATS) st_surface++;
                 float4 in = __ldg(C.inst + T.H.inst);
                 const float *lb = tb + C.off_leaf_bsdf + 4 * __float_as_int(in.w);
-                int kind;
-                f3 n = canopy_normal(C, p, T.H, kind);
+                int kind, mat;
+                f3 n = canopy_normal(C, p, T.H, kind, mat);
                 float ci = -dot3(n, d);
                 on_inst = T.H.inst; on_disk = T.H.disk;
-                // leaves: bilambertian (r, t); trunk parts: one-sided Lambertian = (rho, 0) seen from the front only
+                // leaves: bilambertian (r, t); trunk parts: one-sided Lambertian = (rho, 0) seen from the front only;
+                // mesh triangles: the bilambertian of their element, about the interpolated shading normal
                 float r_ = lb[0], t_ = lb[1];
-                if (kind != 0) { r_ = ci > 0.f ? lb[2] : 0.f; t_ = 0.f; }
+                if (kind == 3) { r_ = tb[C.off_mesh_bsdf + 2 * mat]; t_ = tb[C.off_mesh_bsdf + 2 * mat + 1]; }
+                else if (kind != 0) { r_ = ci > 0.f ? lb[2] : 0.f; t_ = 0.f; }
                 if (depth + 1u < P.max_depth) nee = thr * bilambertian_eval(r_, t_, ci, dot3(n, sun)) * P.irradiance;
                 float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
                 f3 wl;

@@ -106,6 +106,9 @@ struct HostLeafGroup {
     std::vector<float> trunk_disks; // trunk caps (diffuse)
     std::vector<float> cylinders;   // n x 7: p0, p1, radius (diffuse)
     float reflectance = 0.f, transmittance = 0.f, trunk_reflectance = 0.f;
+    std::vector<float> triangles;   // n x 18: v0, v1, v2, shading normals n0, n1, n2 (mesh elements)
+    std::vector<int> triangle_bsdf; // n: index into mesh_bsdfs
+    std::vector<float> mesh_bsdfs;  // m x 2: bilambertian reflectance, transmittance
 };
 
 struct BvhBox {
@@ -296,7 +299,8 @@ struct ertb_scene {
     std::vector<int> instance_group;
     std::vector<double> instance_offset;
     ErtbCanopy canopy;          // device pointers (zero-initialised: no canopy)
-    void *d_canopy[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    void *d_canopy[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    std::vector<int> mesh_bsdf_base; // per group: first row of its mesh BSDFs in the table blob
     bool needs_3d = false;      // canopy or perspective sensor: rendered by ertb_canopy_kernel
 };
 
@@ -310,8 +314,35 @@ static int build_canopy(ertb_scene *S) {
     std::vector<std::vector<BvhBox>> dboxes(ng);
     // primitives of a group, in this order: leaf disks (kind 0), trunk cap disks (kind 1), cylinders (kind 2)
     std::vector<std::vector<float>> prims(ng); // 8 floats each: device record, kind in the last slot
+    std::vector<float> tris; // 16 floats per triangle (ErtbCanopy::tris), in input order; the record points here
+    S->mesh_bsdf_base.assign(ng, 0);
+    int n_mesh_bsdfs = 0;
     for (int g = 0; g < ng; ++g) {
         const HostLeafGroup &hg = S->leaf_groups[g];
+        S->mesh_bsdf_base[g] = n_mesh_bsdfs;
+        n_mesh_bsdfs += (int) hg.mesh_bsdfs.size() / 2;
+        for (size_t i = 0; i < hg.triangles.size() / 18; ++i) {
+            const float *q = &hg.triangles[18 * i];
+            BvhBox b;
+            for (int k = 0; k < 3; ++k) {
+                b.lo[k] = fminf(q[k], fminf(q[3 + k], q[6 + k]));
+                b.hi[k] = fmaxf(q[k], fmaxf(q[3 + k], q[6 + k]));
+                const float pad = 1e-6f * fmaxf(1.f, fmaxf(fabsf(b.lo[k]), fabsf(b.hi[k]))); // axis-aligned faces: no empty box
+                b.lo[k] -= pad; b.hi[k] += pad;
+            }
+            dboxes[g].push_back(b);
+            gbox[g].grow(b);
+            const int kind = 3, tri = (int) tris.size() / 16, mat = S->mesh_bsdf_base[g] + hg.triangle_bsdf[i];
+            // record: (v0, triangle index) (e1 = v1 - v0, kind); tris: (e2 = v2 - v0, mesh BSDF row) n0 n1 n2
+            float row[8] = { q[0], q[1], q[2], 0.f, q[3] - q[0], q[4] - q[1], q[5] - q[2], 0.f };
+            memcpy(&row[3], &tri, sizeof(float));
+            memcpy(&row[7], &kind, sizeof(float));
+            prims[g].insert(prims[g].end(), row, row + 8);
+            float ext[16] = { q[6] - q[0], q[7] - q[1], q[8] - q[2], 0.f, q[9], q[10], q[11], 0.f,
+                              q[12], q[13], q[14], 0.f, q[15], q[16], q[17], 0.f };
+            memcpy(&ext[3], &mat, sizeof(float));
+            tris.insert(tris.end(), ext, ext + 16);
+        }
         for (int pass = 0; pass < 2; ++pass) {
             const std::vector<float> &dk = pass == 0 ? hg.disks : hg.trunk_disks;
             for (size_t i = 0; i < dk.size() / 7; ++i) {
@@ -386,11 +417,12 @@ static int build_canopy(ertb_scene *S) {
         int g = S->instance_group[i];
         memcpy(&inst[4 * j + 3], &g, sizeof(float));
     }
-    const void *src[5] = { tlas.data(), inst.data(), blas.data(), blas_root.data(), disks.data() };
-    const size_t bytes[5] = { tlas.size() * sizeof(ErtbBvhNode), inst.size() * sizeof(float),
+    const void *src[6] = { tlas.data(), inst.data(), blas.data(), blas_root.data(), disks.data(), tris.data() };
+    const size_t bytes[6] = { tlas.size() * sizeof(ErtbBvhNode), inst.size() * sizeof(float),
                               blas.size() * sizeof(ErtbBvhNode), blas_root.size() * sizeof(int),
-                              disks.size() * sizeof(float) };
-    for (int k = 0; k < 5; ++k) {
+                              disks.size() * sizeof(float), tris.size() * sizeof(float) };
+    for (int k = 0; k < 6; ++k) {
+        if (bytes[k] == 0) continue;
         CUDA_TRY(cudaMalloc(&S->d_canopy[k], bytes[k]));
         CUDA_TRY(cudaMemcpy(S->d_canopy[k], src[k], bytes[k], cudaMemcpyHostToDevice));
     }
@@ -400,6 +432,7 @@ static int build_canopy(ertb_scene *S) {
     C.blas = (const ErtbBvhNode *) S->d_canopy[2];
     C.blas_root = (const int *) S->d_canopy[3];
     C.disks = (const float4 *) S->d_canopy[4];
+    C.tris = (const float4 *) S->d_canopy[5];
     return 0;
 }
 
@@ -694,6 +727,9 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
     for (const HostLeafGroup &g : S->leaf_groups) { // 4 floats per group: leaf r, leaf t, trunk rho, -
         blob.push_back(g.reflectance); blob.push_back(g.transmittance); blob.push_back(g.trunk_reflectance); blob.push_back(0.f);
     }
+    blob.resize(align4(blob.size()), 0.f);
+    P.canopy.off_mesh_bsdf = (int) blob.size(); // 2 floats per mesh BSDF, groups concatenated (mesh_bsdf_base)
+    for (const HostLeafGroup &g : S->leaf_groups) blob.insert(blob.end(), g.mesh_bsdfs.begin(), g.mesh_bsdfs.end());
     blob.resize(align4(blob.size()), 0.f);
     P.canopy.patch_type = -1;
     if (S->has_patch) { // the patch BSDF travels with the tables (spectral updates, batch slots)
@@ -1133,9 +1169,22 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
         }
         for (int g = 0; g < D->n_leaf_groups; ++g) {
             const ertb_leaf_group_desc &gd = D->leaf_groups[g];
-            if (gd.n_disks < 1 || !gd.disks) { delete S; return set_error("leaf group without disks"); }
+            if (gd.n_disks < 0 || gd.n_triangles < 0 || (gd.n_disks > 0 && !gd.disks) ||
+                gd.n_disks + gd.n_triangles + gd.n_cylinders + gd.n_trunk_disks < 1) { delete S; return set_error("leaf group without primitives"); }
             HostLeafGroup hg;
-            hg.disks.assign(gd.disks, gd.disks + 7 * (size_t) gd.n_disks);
+            if (gd.n_disks) hg.disks.assign(gd.disks, gd.disks + 7 * (size_t) gd.n_disks);
+            if (gd.n_triangles) {
+                if (!gd.triangles || !gd.triangle_bsdf || !gd.mesh_bsdfs || gd.n_mesh_bsdfs < 1 || gd.n_mesh_bsdfs > 65535) {
+                    delete S; return set_error("mesh arrays missing");
+                }
+                hg.triangles.assign(gd.triangles, gd.triangles + 18 * (size_t) gd.n_triangles);
+                hg.triangle_bsdf.assign(gd.triangle_bsdf, gd.triangle_bsdf + gd.n_triangles);
+                hg.mesh_bsdfs.assign(gd.mesh_bsdfs, gd.mesh_bsdfs + 2 * (size_t) gd.n_mesh_bsdfs);
+                for (float v : hg.triangles)
+                    if (!std::isfinite(v)) { delete S; return set_error("mesh contains invalid vertex data"); }
+                for (int m : hg.triangle_bsdf)
+                    if (m < 0 || m >= gd.n_mesh_bsdfs) { delete S; return set_error("triangle refers to an unknown mesh BSDF"); }
+            }
             hg.reflectance = gd.reflectance;
             hg.transmittance = gd.transmittance;
             if ((gd.n_trunk_disks > 0 && !gd.trunk_disks) || (gd.n_cylinders > 0 && !gd.cylinders) ||
@@ -1280,6 +1329,15 @@ int ertb_scene_update(ertb_scene *S, int param, int index, const float *data, si
             if (need(1)) return 1;
             S->leaf_groups[index].trunk_reflectance = data[0];
             break;
+        case ERTB_PARAM_MESH_BSDF: {
+            const int g = index >> 16, m = index & 0xffff;
+            if (index < 0 || g >= (int) S->leaf_groups.size() || 2 * (size_t) m + 1 >= S->leaf_groups[g].mesh_bsdfs.size())
+                return set_error("invalid mesh BSDF index");
+            if (need(2)) return 1;
+            S->leaf_groups[g].mesh_bsdfs[2 * m] = data[0];
+            S->leaf_groups[g].mesh_bsdfs[2 * m + 1] = data[1];
+            break;
+        }
         case ERTB_PARAM_PATCH_BSDF_PARAMS:
             if (!S->has_patch) return set_error("scene has no central patch");
             if (need(ERTB_MAX_BSDF_PARAMS)) return 1;
@@ -2007,8 +2065,8 @@ __global__ void kat_canopy_intersect_kernel(ErtbParams P, size_t n, const double
         float4 in = __ldg(P.canopy.inst + H.inst);
         group[i] = __float_as_int(in.w);
         double q[3] = { p[0] + th * (double) d.x, p[1] + th * (double) d.y, p[2] + th * (double) d.z };
-        int kind;
-        f3 n = canopy_normal(P.canopy, q, H, kind);
+        int kind, mat;
+        f3 n = canopy_normal(P.canopy, q, H, kind, mat);
         normal[3 * i] = n.x; normal[3 * i + 1] = n.y; normal[3 * i + 2] = n.z;
     }
 }

@@ -73,7 +73,10 @@ struct ErtbCanopy {
     const int *blas_root;     // per group: root node index in `blas`
     const float4 *disks;      // 2 per primitive, in BVH leaf order: disk (centre, radius) (normal, kind 0 leaf / 1 trunk
                               // cap); cylinder (p0, radius) (axis vector p1 - p0, kind 2)
+                              // triangle (v0, index into `tris` as int bits) (e1 = v1 - v0, kind 3)
+    const float4 *tris;       // 4 per triangle: (e2 = v2 - v0, row of its BSDF in the mesh table as int bits), n0, n1, n2
     int off_leaf_bsdf;        // table blob: per group (leaf reflectance, leaf transmittance, trunk reflectance, -)
+    int off_mesh_bsdf;        // table blob: per mesh BSDF (reflectance, transmittance)
     double origin[3];
     double lo[3], hi[3];      // world-space bounding box of all instances
     // CentralPatchSurface: a second ground BSDF (type, 16 params in the table blob) inside a rectangle

@@ -190,6 +190,8 @@ class DeviceScene:
                 push(_abi.PARAM_LEAF_BSDF, i, flat.leaf_bsdf_params(i))
                 if "trunk_bsdf" in g.children:
                     push(_abi.PARAM_TRUNK_BSDF, i, [flat.trunk_reflectance(i)])
+                for k, rt in enumerate(flat.mesh_bsdf_params(i)):
+                    push(_abi.PARAM_MESH_BSDF, (i << 16) | k, rt)
         if flat.patch_bsdf is not None and dirty(flat.patch_bsdf):
             push(_abi.PARAM_PATCH_BSDF_PARAMS, 0, flat.bsdf_params(flat.patch_bsdf))
         if dirty(flat.bsdf):

@@ -228,7 +228,7 @@ class Scene(Object):
 _SUPPORTED = {
     "integrator": {"volpath", "volpathmis", "piecewise_volpath", "path", "moment", "stokes"},
     "emitter": {"directional", "astroobject"},
-    "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance", "cylinder"},
+    "shape": {"sphere", "cube", "rectangle", "arectangle", "disk", "shapegroup", "instance", "cylinder", "ply", "obj"},
     "medium": {"heterogeneous", "homogeneous", "piecewise"},
     "bsdf": {"diffuse", "rpv", "rtls", "hapke", "ocean_legacy", "ocean_mishchenko", "ocean_grasp", "maignan",
              "mqdiffuse", "measured_mono", "null", "bilambertian", "blendbsdf", "selectbsdf"},
@@ -240,8 +240,6 @@ _SUPPORTED = {
 _KIND_OF = {ty: kind for kind, types in _SUPPORTED.items() for ty in types}
 # plugins the reference ships for this slot but that this kernel does not (yet) implement
 _KNOWN_UNSUPPORTED = {
-    "ply": "mesh canopy elements are not implemented",
-    "obj": "mesh canopy elements are not implemented",
 }
 
 
@@ -599,14 +597,33 @@ class _Loader:
             # src/eradiate/scenes/biosphere/_core.py:266-275: a group of `disk` leaves. The disks are
             # kept as one [n, 7] array, not as one node each (a RAMI canopy has > 10^5 of them).
             rows, trunk_rows, cyl_rows, bsdf, trunk_bsdf = [], [], [], None, None
+            tri_rows, tri_bsdf, mesh_bsdfs = [], [], []
             for key, v in d.items():
                 if not isinstance(v, dict) or "type" not in v:
                     continue
                 if v["type"] in _KNOWN_UNSUPPORTED:
                     raise RuntimeError(f"unsupported plugin '{v['type']}': {_KNOWN_UNSUPPORTED[v['type']]}")
-                if v["type"] not in ("disk", "cylinder"):
-                    raise RuntimeError(f"shapegroup: unsupported child shape '{v['type']}' (only 'disk' and 'cylinder')")
+                if v["type"] not in ("disk", "cylinder", "ply", "obj"):
+                    raise RuntimeError(f"shapegroup: unsupported child shape '{v['type']}' "
+                                       "(only 'disk', 'cylinder', 'ply' and 'obj')")
                 b = self._child_bsdf(v)
+                if v["type"] in ("ply", "obj"):
+                    # MeshTreeElement (_tree.py:440-478): a triangle mesh with its own bilambertian BSDF and a
+                    # scaling to_world (mesh units -> kernel length unit)
+                    from ._mesh import load_triangles
+
+                    if b.type != "bilambertian":
+                        raise RuntimeError(f"mesh canopy elements must carry a bilambertian BSDF, got '{b.type}'")
+                    if "filename" not in v:
+                        raise RuntimeError('Property "filename" has not been specified!')
+                    tri, _ = load_triangles(v["type"], str(v["filename"]), to_matrix(v.get("to_world")),
+                                            face_normals=bool(v.get("face_normals", False)),
+                                            flip_normals=bool(v.get("flip_normals", False)))
+                    if not any(b is m for m in mesh_bsdfs):
+                        mesh_bsdfs.append(b)
+                    tri_rows.append(tri)
+                    tri_bsdf.append(np.full(tri.shape[0], next(i for i, m in enumerate(mesh_bsdfs) if m is b), dtype=np.int32))
+                    continue
                 if b.type == "bilambertian" and v["type"] == "disk":  # a leaf
                     if bsdf is not None and b is not bsdf:
                         raise RuntimeError("shapegroup: all leaves of a group must share one BSDF")
@@ -629,15 +646,23 @@ class _Loader:
                 else:
                     raise RuntimeError(f"canopy leaves must carry a bilambertian BSDF and trunks a diffuse one, "
                                        f"got '{b.type}' on a {v['type']}")
-            if not rows:
-                raise RuntimeError("shapegroup: no leaf (bilambertian disk) among the child shapes")
-            s.disks = np.asarray(rows, dtype=np.float64)
+            if not rows and not tri_rows:
+                raise RuntimeError("shapegroup: no leaf (bilambertian disk or mesh) among the child shapes")
+            s.triangles = np.concatenate(tri_rows) if tri_rows else np.zeros((0, 18), dtype=np.float32)
+            s.triangle_bsdf = np.concatenate(tri_bsdf) if tri_bsdf else np.zeros(0, dtype=np.int32)
+            s.mesh_bsdfs = mesh_bsdfs
+            for i, m in enumerate(mesh_bsdfs):
+                s.children[f"mesh_bsdf_{i}"] = m
+            s.disks = np.asarray(rows, dtype=np.float64).reshape(-1, 7)
             s.trunk_disks = np.asarray(trunk_rows, dtype=np.float64).reshape(-1, 7)
             s.cylinders = np.asarray(cyl_rows, dtype=np.float64).reshape(-1, 7)
-            s.children["bsdf"] = bsdf
+            if bsdf is not None:
+                s.children["bsdf"] = bsdf
             if trunk_bsdf is not None:
                 s.children["trunk_bsdf"] = trunk_bsdf
             return s
+        if ty in ("ply", "obj"):
+            raise RuntimeError(f"'{ty}': triangle meshes are supported as canopy elements inside a shapegroup only")
         if ty == "instance":
             # _core.py:277-296: `group` reference + translation
             g = d.get("group") or next((v for v in d.values() if isinstance(v, dict) and v.get("type") in ("ref", "shapegroup")), None)
@@ -660,6 +685,7 @@ class _Loader:
             s.disks = np.asarray([self._disk_row(s.to_world)], dtype=np.float64)
             s.trunk_disks = np.zeros((0, 7))
             s.cylinders = np.zeros((0, 7))
+            s.triangles, s.triangle_bsdf, s.mesh_bsdfs = np.zeros((0, 18), dtype=np.float32), np.zeros(0, dtype=np.int32), []
             s.children["bsdf"] = bsdf
             return s
         if ty == "sphere":
@@ -997,13 +1023,20 @@ class FlatScene:
                 g = self.leaf_groups[gi]
                 dk = np.vstack([g.disks, g.trunk_disks])
                 ext = dk[:, 6:7] * np.sqrt(np.maximum(1.0 - dk[:, 3:6] ** 2, 0.0))
-                lo, hi = (dk[:, :3] - ext).min(axis=0) + off, (dk[:, :3] + ext).max(axis=0) + off
+                lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+                if dk.shape[0]:
+                    lo, hi = (dk[:, :3] - ext).min(axis=0) + off, (dk[:, :3] + ext).max(axis=0) + off
                 for c in g.cylinders:
                     lo = np.minimum(lo, np.minimum(c[:3], c[3:6]) - c[6] + off)
                     hi = np.maximum(hi, np.maximum(c[:3], c[3:6]) + c[6] + off)
+                if g.triangles.shape[0]:
+                    v = g.triangles[:, :9].reshape(-1, 3).astype(np.float64)
+                    lo, hi = np.minimum(lo, v.min(axis=0) + off), np.maximum(hi, v.max(axis=0) + off)
+                    if v[:, 2].min() + off[2] < self.surface_z - 1e-6:
+                        raise RuntimeError("canopy meshes must lie above the ground surface")
                 dk = g.disks
                 bbox_lo, bbox_hi = np.minimum(bbox_lo, lo), np.maximum(bbox_hi, hi)
-                if (dk[:, 2] + off[2]).min() < self.surface_z:
+                if dk.shape[0] and (dk[:, 2] + off[2]).min() < self.surface_z:
                     raise RuntimeError("canopy leaf centres must lie above the ground surface")
                 if self.atm_shape is not None and hi[2] > self.medium_top:
                     raise RuntimeError("canopy leaves must lie below the top of the atmosphere")
@@ -1200,9 +1233,16 @@ class FlatScene:
         return 0.0 if b is None else float(b.children["reflectance"].values["value"])
 
     def leaf_bsdf_params(self, group: int) -> tuple[float, float]:
-        b = self.leaf_groups[group].children["bsdf"]
+        b = self.leaf_groups[group].children.get("bsdf")
+        if b is None:  # a group of meshes only
+            return 0.0, 0.0
         return (float(b.children["reflectance"].values["value"]),
                 float(b.children["transmittance"].values["value"]))
+
+    def mesh_bsdf_params(self, group: int) -> np.ndarray:
+        """[n_mesh_bsdfs, 2]: bilambertian (reflectance, transmittance) of the group's mesh elements."""
+        return np.array([[float(b.children["reflectance"].values["value"]), float(b.children["transmittance"].values["value"])]
+                         for b in self.leaf_groups[group].mesh_bsdfs], dtype=np.float32).reshape(-1, 2)
 
     def bsdf_type(self, b: BSDF | None = None) -> int:
         return {
@@ -1347,6 +1387,15 @@ class FlatScene:
                 groups[i].n_disks = disks.shape[0]
                 groups[i].disks = disks.ctypes.data_as(_abi.c_float_p)
                 groups[i].reflectance, groups[i].transmittance = self.leaf_bsdf_params(i)
+                if g.triangles.shape[0]:
+                    tri = np.ascontiguousarray(g.triangles, dtype=np.float32)
+                    tid = np.ascontiguousarray(g.triangle_bsdf, dtype=np.int32)
+                    mb = np.ascontiguousarray(self.mesh_bsdf_params(i), dtype=np.float32)
+                    keep += [tri, tid, mb]
+                    groups[i].n_triangles, groups[i].n_mesh_bsdfs = tri.shape[0], mb.shape[0]
+                    groups[i].triangles = tri.ctypes.data_as(_abi.c_float_p)
+                    groups[i].triangle_bsdf = tid.ctypes.data_as(C.POINTER(C.c_int32))
+                    groups[i].mesh_bsdfs = mb.ctypes.data_as(_abi.c_float_p)
                 cyl = np.ascontiguousarray(g.cylinders, dtype=np.float32)
                 tdk = np.ascontiguousarray(g.trunk_disks, dtype=np.float32)
                 keep += [cyl, tdk]

@@ -294,6 +294,8 @@ def atmosphere_scene(
             raise ValueError("canopies need the plane-parallel geometry")
         if "trees" in canopy:  # {"trees": {...abstract_tree_canopy arguments...}, "size": (lx, ly, lz)}
             scene.update(abstract_tree_canopy(**canopy["trees"]))
+        elif "mesh_trees" in canopy:  # {"mesh_trees": {...mesh_tree_canopy arguments...}, "size": (lx, ly, lz)}
+            scene.update(mesh_tree_canopy(**canopy["mesh_trees"]))
         else:
             scene.update(disc_canopy(**canopy))
         # experiments/_canopy_atmosphere.py:200-210: distant measures target the top of the unit cell
@@ -560,6 +562,53 @@ def abstract_tree_canopy(
     for k, (x, y) in enumerate(positions):
         out[f"tree_instance_{k}"] = {"type": "instance", "group": {"type": "ref", "id": "tree"},
                                      "to_world": ScalarTransform4f().translate([float(x), float(y), 0.0])}
+    return out
+
+
+def mesh_tree_canopy(
+    elements,
+    positions=((0.0, 0.0), (3.0, 1.0), (-2.0, 2.5)),
+    leaves: dict | None = None,
+) -> dict:
+    """
+    Instanced `MeshTree`s (``scenes/biosphere/_tree.py:285-478, :600-700``): a shape group of triangle meshes,
+    each a `ply` / `obj` file with its own `bilambertian` BSDF and a scaling `to_world` (mesh units -> metres),
+    placed by translated `instance`s.  `elements`: [{"id", "filename", "scale", "reflectance", "transmittance",
+    optional "face_normals"}]; `leaves`: optional disc leaves in the same group ({"n", "radius", "centre", "extent",
+    "reflectance", "transmittance", "seed"}).
+    """
+    out: dict = {}
+    group: dict = {"type": "shapegroup"}
+    for e in elements:
+        ext = str(e["filename"]).rsplit(".", 1)[-1].lower()
+        if ext not in ("ply", "obj"):
+            raise ValueError(f"unsupported file extension '.{ext}'")
+        out[f"bsdf_{e['id']}"] = {"type": "bilambertian",
+                                  "reflectance": {"type": "uniform", "value": float(e["reflectance"])},
+                                  "transmittance": {"type": "uniform", "value": float(e["transmittance"])}}
+        shape = {"type": ext, "bsdf": {"type": "ref", "id": f"bsdf_{e['id']}"}, "filename": str(e["filename"]),
+                 "to_world": ScalarTransform4f().scale(float(e.get("scale", 1.0)))}
+        if "face_normals" in e:
+            shape["face_normals"] = bool(e["face_normals"])
+        group[e["id"]] = shape
+    if leaves:
+        rng = np.random.default_rng(leaves.get("seed", 3))
+        n = int(leaves["n"])
+        pos = np.asarray(leaves["centre"]) + (rng.uniform(-1.0, 1.0, (n, 3)) * np.asarray(leaves["extent"]))
+        nrm = leaf_normals(n, "uniform", rng)
+        out["bsdf_leaf_cloud"] = {"type": "bilambertian",
+                                  "reflectance": {"type": "uniform", "value": float(leaves["reflectance"])},
+                                  "transmittance": {"type": "uniform", "value": float(leaves["transmittance"])}}
+        for i in range(n):
+            up = np.array([1.0, 0.0, 0.0]) if abs(nrm[i][2]) > 0.9 else np.array([0.0, 0.0, 1.0])
+            group[f"leaf_cloud_leaf_{i}"] = {
+                "type": "disk", "bsdf": {"type": "ref", "id": "bsdf_leaf_cloud"},
+                "to_world": ScalarTransform4f().look_at(origin=pos[i], target=pos[i] + nrm[i], up=up).scale(float(leaves["radius"])),
+            }
+    out["mesh_tree"] = group
+    for k, (x, y) in enumerate(positions):
+        out[f"mesh_tree_instance_{k}"] = {"type": "instance", "group": {"type": "ref", "id": "mesh_tree"},
+                                          "to_world": ScalarTransform4f().translate([float(x), float(y), 0.0])}
     return out
 
 

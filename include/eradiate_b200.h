@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERTB_ABI_VERSION 15
+#define ERTB_ABI_VERSION 16
 #define ERTB_MAX_PHASE 4       /* leaves of the flattened blendphase tree */
 #define ERTB_MAX_BSDF_PARAMS 16
 #define ERTB_MAX_LAYERS 4096   /* sigma_t + albedo + weights must fit one SM's shared memory */
@@ -157,7 +157,8 @@ typedef struct ertb_sensor_desc {
  * whose to_world is a pure translation.  Plane-parallel scenes only; the leaves sit inside the atmosphere and do
  * not change the medium of a path (no medium interface).
  * disks: n_disks x 7 floats = centre xyz, unit normal xyz, radius (MI/src/shapes/disk.cpp:
- * to_world = look_at x uniform scale). */
+ * to_world = look_at x uniform scale).  A group holds at least one primitive (n_disks may be 0 when it has
+ * triangles). */
 typedef struct ertb_leaf_group_desc {
     int32_t n_disks;
     float reflectance;     /* bilambertian `reflectance` (uniform) */
@@ -172,7 +173,18 @@ typedef struct ertb_leaf_group_desc {
     const float *cylinders;     /* n_cylinders x 7: p0 xyz, p1 xyz, radius */
     const float *trunk_disks;   /* n_trunk_disks x 7, same layout as `disks` */
     float trunk_reflectance;
+    /* MeshTreeElement (src/eradiate/scenes/biosphere/_tree.py:285-470): `ply` / `obj` triangle meshes
+     * (MI/src/shapes/ply.cpp, obj.cpp, MI/src/render/mesh.cpp), each with its own `bilambertian` BSDF.  The host
+     * reads the files, applies `to_world` and computes the vertex normals (eradiate_b200/kernel/_mesh.py); here
+     * they are plain triangles: 18 floats = v0, v1, v2, then the unit shading normals at the three vertices
+     * (mesh.cpp:1500-1560: interpolated and renormalised at the hit; all three equal to the face normal when the
+     * shape was loaded with `face_normals`).  Hit test: Moeller-Trumbore, MI/include/mitsuba/render/mesh.h:481-504. */
+    int32_t n_triangles;
+    int32_t n_mesh_bsdfs;
     int32_t _pad2;
+    const float *triangles;        /* n_triangles x 18 */
+    const int32_t *triangle_bsdf;  /* n_triangles: index into mesh_bsdfs */
+    const float *mesh_bsdfs;       /* n_mesh_bsdfs x 2: bilambertian reflectance, transmittance */
 } ertb_leaf_group_desc;
 
 typedef struct ertb_scene_desc {
@@ -275,7 +287,8 @@ enum ertb_param {
     ERTB_PARAM_PHASE_MUELLER = 7, /* index = leaf * 5 + k (k: m12, m22, m33, m34, m44); float[n_nodes] */
     ERTB_PARAM_LEAF_BSDF = 8,    /* index = leaf group; float[2]: reflectance, transmittance */
     ERTB_PARAM_PATCH_BSDF_PARAMS = 9, /* float[ERTB_MAX_BSDF_PARAMS]: the central patch's BSDF */
-    ERTB_PARAM_TRUNK_BSDF = 10        /* index = leaf group; float[1]: trunk reflectance */
+    ERTB_PARAM_TRUNK_BSDF = 10,       /* index = leaf group; float[1]: trunk reflectance */
+    ERTB_PARAM_MESH_BSDF = 11         /* index = (leaf group << 16) | mesh BSDF; float[2]: reflectance, transmittance */
 };
 
 typedef struct ertb_render_stats {

@@ -372,7 +372,8 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
 /* ------------------------------------------------------------- geometry */
 typedef struct { v3 o, d; double maxt; } ray_t;
 enum { SHAPE_GROUND = 0, SHAPE_TOA = 1, SHAPE_LEAF = 2 };
-typedef struct { double t; v3 p, n; int shape; int group; int trunk; } si_t; /* t = INFINITY when invalid */
+typedef struct { double t; v3 p, n; int shape; int group; int trunk; /* t = INFINITY when invalid */
+                 int mesh; v3 sh_n; double mesh_r, mesh_t; /* mesh triangle: shading normal and its bilambertian */ } si_t;
 
 static inline v3 ray_at(const ray_t *r, double t) { return vfma(r->d, t, r->o); }
 
@@ -400,7 +401,7 @@ static double sphere_intersect(const ray_t *ray, double radius) {
  * `cube` top face; horizontal extent treated as unbounded: default width 1e6 km) */
 static si_t scene_intersect(const scene_t *S, const ray_t *ray) {
     const ertb_scene_desc *d = S->desc;
-    si_t best; best.t = INFINITY; best.shape = -1; best.group = -1; best.trunk = 0; best.p = best.n = V(0, 0, 0);
+    si_t best; memset(&best, 0, sizeof best); best.t = INFINITY; best.shape = -1; best.group = -1;
     double tg = INFINITY, tt = INFINITY;
     if (S->spherical) {
         tg = sphere_intersect(ray, d->surface_z);
@@ -438,6 +439,9 @@ static si_t scene_intersect(const scene_t *S, const ray_t *ray) {
             best.t = h.t; best.shape = SHAPE_LEAF; best.group = h.group; best.trunk = h.kind == CANOPY_TRUNK;
             best.p = V(h.p[0], h.p[1], h.p[2]);
             best.n = V(h.n[0], h.n[1], h.n[2]);
+            best.mesh = h.kind == CANOPY_MESH;
+            best.sh_n = V(h.sh_n[0], h.sh_n[1], h.sh_n[2]);
+            best.mesh_r = h.mesh_r; best.mesh_t = h.mesh_t;
         }
     }
     return best;
@@ -1191,6 +1195,7 @@ static double surf_eval(const scene_t *S, const si_t *si, v3 wi, v3 wo) {
         double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
         if (si->trunk) /* diffuse.cpp:127-143: one-sided Lambertian */
             return wi.z > 0.0 && wo.z > 0.0 ? G->trunk_reflectance * INV_PI * wo.z : 0.0;
+        if (si->mesh) return bilambertian_eval(si->mesh_r, si->mesh_t, a, b);
         return bilambertian_eval(G->reflectance, G->transmittance, a, b);
     }
     if (on_patch(S, si->p)) return bsdf_eval_tp(S, S->desc->patch_bsdf_type, S->desc->patch_bsdf_params, wi, wo);
@@ -1206,7 +1211,8 @@ static double surf_sample(const scene_t *S, const si_t *si, v3 wi, double s1, do
     if (si->shape == SHAPE_LEAF) {
         const canopy_group_t *G = &S->canopy.groups[si->group];
         double a[3] = { wi.x, wi.y, wi.z }, o[3];
-        double w = bilambertian_sample(G->reflectance, G->transmittance, a, s1, u1, u2, o);
+        double w = si->mesh ? bilambertian_sample(si->mesh_r, si->mesh_t, a, s1, u1, u2, o)
+                            : bilambertian_sample(G->reflectance, G->transmittance, a, s1, u1, u2, o);
         *wo = V(o[0], o[1], o[2]);
         return w;
     }
@@ -1394,7 +1400,7 @@ static double sample_emitter(const scene_t *S, pcg32 *rng, v3 ref_p, v3 ref_n, i
 
     ray_t ray = spawn_ray_to(ref_p, ref_n, ds_p);
     double max_dist = ray.maxt, total_dist = 0.0, transmittance = 1.0;
-    si_t si; si.t = INFINITY; si.shape = -1;
+    si_t si; memset(&si, 0, sizeof si); si.t = INFINITY; si.shape = -1;
     int needs_intersection = 1, active = 1;
     C->ray_flights = 0; C->ray_opaque = 0;
     while (active) {
@@ -1539,7 +1545,7 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
     double throughput = 1.0, result = 0.0, eta = 1.0;
     int medium = medium0; /* distant sensors sit outside the atmosphere; a camera may be inside */
     uint64_t depth = 0;
-    si_t si; si.t = INFINITY; si.shape = -1; si.group = -1; si.p = si.n = V(0, 0, 0);
+    si_t si; memset(&si, 0, sizeof si); si.t = INFINITY; si.shape = -1; si.group = -1;
     int needs_intersection = 1, last_event_was_null = 0;
     int specular_chain = 1;  /* volpath.cpp:113 (hide_emitters = false) */
     double last_pdf = 0.0;   /* last_scatter_direction_pdf */
@@ -1626,7 +1632,7 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
             result += throughput * astro_hit(S, ray.d, depth, specular_chain, last_pdf);
         active_surface = active_surface && si.t < INFINITY;
         if (active_surface) {
-            frame_t fr = si.shape == SHAPE_LEAF ? make_frame(si.n) : surface_frame(S, &si);
+            frame_t fr = si.shape == SHAPE_LEAF ? make_frame(si.mesh ? si.sh_n : si.n) : surface_frame(S, &si);
             v3 wi = to_local(&fr, vneg(ray.d));
             v3 wo_world;
             if (si.shape == SHAPE_TOA) { /* null.cpp:41-87 */
@@ -1726,7 +1732,7 @@ static void volpath_sample_pol(const scene_t *S, pcg32 *rng, ray_t ray, int medi
     double result[4] = { 0, 0, 0, 0 }, eta = 1.0;
     int medium = medium0;
     uint64_t depth = 0;
-    si_t si; si.t = INFINITY; si.shape = -1; si.group = -1; si.p = si.n = V(0, 0, 0);
+    si_t si; memset(&si, 0, sizeof si); si.t = INFINITY; si.shape = -1; si.group = -1;
     int needs_intersection = 1, last_event_was_null = 0;
     int specular_chain = 1;
     double last_pdf = 0.0;
@@ -2121,7 +2127,7 @@ int ertbo_canopy_intersect(const ertb_scene_desc *desc, size_t n, const double *
         canopy_hit_t h = canopy_intersect(&S.canopy, o + 3 * i, dv, tmax ? tmax[i] : INFINITY);
         t[i] = h.t;
         group[i] = h.group;
-        for (int k = 0; k < 3; ++k) normal[3 * i + k] = h.t < INFINITY ? h.n[k] : 0.0;
+        for (int k = 0; k < 3; ++k) normal[3 * i + k] = h.t < INFINITY ? h.sh_n[k] : 0.0; /* (the shading normal) */
     }
     scene_free(&S);
     return 0;

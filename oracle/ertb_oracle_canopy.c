@@ -29,31 +29,45 @@ static void cyl_bounds(const float *c, double lo[3], double hi[3]) {
     }
 }
 
-/* bounds of primitive i of a group: disks [0, n_disks), then cylinders */
+static void tri_bounds(const float *q, double lo[3], double hi[3]) {
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = fmin(q[k], fmin(q[3 + k], q[6 + k]));
+        hi[k] = fmax(q[k], fmax(q[3 + k], q[6 + k]));
+    }
+}
+
+/* bounds of primitive i of a group: disks [0, n_disks), then cylinders, then triangles */
 static void prim_bounds(const canopy_group_t *G, int i, double lo[3], double hi[3]) {
     if (i < G->n_disks) disk_bounds(G->disks + 7 * i, lo, hi);
-    else cyl_bounds(G->cylinders + 7 * (i - G->n_disks), lo, hi);
+    else if (i < G->n_disks + G->n_cylinders) cyl_bounds(G->cylinders + 7 * (i - G->n_disks), lo, hi);
+    else tri_bounds(G->triangles + 18 * (size_t) (i - G->n_disks - G->n_cylinders), lo, hi);
 }
 
 static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 static int group_init(canopy_group_t *G, const ertb_leaf_group_desc *gd) {
     memset(G, 0, sizeof *G);
-    if (gd->n_disks < 1 || !gd->disks) return 1;
+    if (gd->n_disks < 0 || (gd->n_disks > 0 && !gd->disks)) return 1;
     if ((gd->n_trunk_disks > 0 && !gd->trunk_disks) || (gd->n_cylinders > 0 && !gd->cylinders)) return 1;
+    if (gd->n_triangles > 0 && (!gd->triangles || !gd->triangle_bsdf || !gd->mesh_bsdfs)) return 1;
+    if (gd->n_disks + gd->n_trunk_disks + gd->n_cylinders + gd->n_triangles < 1) return 1;
+    G->n_triangles = gd->n_triangles;
+    G->triangles = gd->triangles;
+    G->triangle_bsdf = gd->triangle_bsdf;
+    G->mesh_bsdfs = gd->mesh_bsdfs;
     G->n_leaf_disks = gd->n_disks;
     G->n_disks = gd->n_disks + gd->n_trunk_disks;
     G->n_cylinders = gd->n_cylinders;
-    G->disks = malloc(sizeof(float) * 7 * (size_t) G->n_disks);
+    G->disks = malloc(sizeof(float) * 7 * (size_t) (G->n_disks > 0 ? G->n_disks : 1));
     if (!G->disks) return 1;
-    memcpy(G->disks, gd->disks, sizeof(float) * 7 * (size_t) gd->n_disks);
+    if (gd->n_disks) memcpy(G->disks, gd->disks, sizeof(float) * 7 * (size_t) gd->n_disks);
     if (gd->n_trunk_disks)
         memcpy(G->disks + 7 * (size_t) gd->n_disks, gd->trunk_disks, sizeof(float) * 7 * (size_t) gd->n_trunk_disks);
     G->cylinders = gd->cylinders;
     G->reflectance = gd->reflectance;
     G->transmittance = gd->transmittance;
     G->trunk_reflectance = gd->trunk_reflectance;
-    const int n_prims = G->n_disks + G->n_cylinders;
+    const int n_prims = G->n_disks + G->n_cylinders + G->n_triangles;
     for (int k = 0; k < 3; ++k) { G->lo[k] = INFINITY; G->hi[k] = -INFINITY; }
     for (int i = 0; i < n_prims; ++i) {
         double lo[3], hi[3];
@@ -166,8 +180,27 @@ static double cyl_hit(const float *c, const double o[3], const double d[3], doub
     return INFINITY;
 }
 
+/* MI/include/mitsuba/render/mesh.h:481-504 (Moeller & Trumbore); `uv`: the barycentric coordinates of v1, v2 */
+static double tri_hit(const float *q, const double o[3], const double d[3], double maxt, double uv[2]) {
+    double e1[3], e2[3], tv[3];
+    for (int k = 0; k < 3; ++k) { e1[k] = (double) q[3 + k] - q[k]; e2[k] = (double) q[6 + k] - q[k]; tv[k] = o[k] - q[k]; }
+    double pv[3] = { d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0] };
+    double inv_det = 1.0 / (e1[0] * pv[0] + e1[1] * pv[1] + e1[2] * pv[2]);
+    double u = (tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2]) * inv_det;
+    if (!(u >= 0.0 && u <= 1.0)) return INFINITY;
+    double qv[3] = { tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2], tv[0] * e1[1] - tv[1] * e1[0] };
+    double v = (d[0] * qv[0] + d[1] * qv[1] + d[2] * qv[2]) * inv_det;
+    if (!(v >= 0.0 && u + v <= 1.0)) return INFINITY;
+    double t = (e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2]) * inv_det;
+    if (!(t >= 0.0 && t <= maxt)) return INFINITY;
+    if (uv) { uv[0] = u; uv[1] = v; }
+    return t;
+}
+
 static double prim_hit(const canopy_group_t *G, int i, const double o[3], const double d[3], double maxt) {
-    return i < G->n_disks ? disk_hit(G->disks + 7 * i, o, d, maxt) : cyl_hit(G->cylinders + 7 * (i - G->n_disks), o, d, maxt);
+    if (i < G->n_disks) return disk_hit(G->disks + 7 * i, o, d, maxt);
+    if (i < G->n_disks + G->n_cylinders) return cyl_hit(G->cylinders + 7 * (i - G->n_disks), o, d, maxt);
+    return tri_hit(G->triangles + 18 * (size_t) (i - G->n_disks - G->n_cylinders), o, d, maxt, NULL);
 }
 
 /* nearest primitive of one group (ray in the group's local coordinates); returns the primitive index */
@@ -228,6 +261,27 @@ canopy_hit_t canopy_intersect(const canopy_t *C, const double o[3], const double
             H.t = t; H.group = C->instance_group[i];
             H.kind = k < G->n_leaf_disks ? CANOPY_LEAF : CANOPY_TRUNK;
             double p[3] = { o[0] + t * d[0], o[1] + t * d[1], o[2] + t * d[2] };
+            if (k >= G->n_disks + G->n_cylinders) { /* mesh.cpp:1393-1560 */
+                const int ti = k - G->n_disks - G->n_cylinders;
+                const float *q = G->triangles + 18 * (size_t) ti;
+                double uv[2];
+                tri_hit(q, ol, d, fmin(maxt, H.t), uv);
+                const double b1 = uv[0], b2 = uv[1], b0 = 1.0 - b1 - b2;
+                double e1[3], e2[3], sn[3], gl = 0.0, sl = 0.0;
+                for (int a = 0; a < 3; ++a) {
+                    H.p[a] = q[a] * b0 + q[3 + a] * b1 + q[6 + a] * b2 + off[a]; /* re-interpolated hit point */
+                    e1[a] = (double) q[3 + a] - q[a]; e2[a] = (double) q[6 + a] - q[a];
+                    sn[a] = q[9 + a] * b0 + q[12 + a] * b1 + q[15 + a] * b2;
+                    sl += sn[a] * sn[a];
+                }
+                double gn[3] = { e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0] };
+                for (int a = 0; a < 3; ++a) gl += gn[a] * gn[a];
+                for (int a = 0; a < 3; ++a) { H.n[a] = gn[a] / sqrt(gl); H.sh_n[a] = sn[a] / sqrt(sl); }
+                H.kind = CANOPY_MESH;
+                H.mesh_r = G->mesh_bsdfs[2 * G->triangle_bsdf[ti]];
+                H.mesh_t = G->mesh_bsdfs[2 * G->triangle_bsdf[ti] + 1];
+                continue;
+            }
             if (k < G->n_disks) {
                 const float *dk = G->disks + 7 * k;
                 double c[3] = { dk[0] + off[0], dk[1] + off[1], dk[2] + off[2] };
@@ -246,6 +300,8 @@ canopy_hit_t canopy_intersect(const canopy_t *C, const double o[3], const double
             }
         }
     }
+    if (H.kind != CANOPY_MESH)
+        for (int a = 0; a < 3; ++a) H.sh_n[a] = H.n[a];
     return H;
 }
 

@@ -13,7 +13,7 @@
 #include "../include/eradiate_b200.h"
 
 /* primitive kinds of a group: leaf disks first, then the trunk's cap disks, then its cylinders */
-enum { CANOPY_LEAF = 0, CANOPY_TRUNK = 1 };
+enum { CANOPY_LEAF = 0, CANOPY_TRUNK = 1, CANOPY_MESH = 2 };
 
 typedef struct {
     int n_disks;         /* leaves + trunk disks */
@@ -21,6 +21,10 @@ typedef struct {
     int n_cylinders;
     float *disks;        /* n_disks x 7 (owned copy: leaves, then trunk disks) */
     const float *cylinders; /* n_cylinders x 7: p0, p1, radius (borrowed) */
+    int n_triangles;        /* mesh elements (MI/src/render/mesh.cpp): primitives after the cylinders */
+    const float *triangles; /* n_triangles x 18: v0, v1, v2, shading normals n0, n1, n2 (borrowed) */
+    const int *triangle_bsdf;
+    const float *mesh_bsdfs; /* n x 2: bilambertian reflectance, transmittance */
     double trunk_reflectance;
     double lo[3], hi[3]; /* bounding box of the group (local coordinates) */
     int res[3];
@@ -40,9 +44,11 @@ typedef struct {
 typedef struct {
     double t;        /* INFINITY: no hit */
     double p[3];     /* hit point re-projected onto the disk (disk.cpp:482-485) */
-    double n[3];     /* disk normal (m_frame.n) / outward normal of the cylinder */
+    double n[3];     /* disk normal (m_frame.n) / outward normal of the cylinder / face normal of the triangle */
+    double sh_n[3];  /* shading normal: n, except on a mesh with vertex normals (interpolated, mesh.cpp:1500-1535) */
     int group;
-    int kind;        /* CANOPY_LEAF (bilambertian) or CANOPY_TRUNK (one-sided diffuse) */
+    int kind;        /* CANOPY_LEAF (bilambertian), CANOPY_TRUNK (one-sided diffuse), CANOPY_MESH (bilambertian r, t below) */
+    double mesh_r, mesh_t;
 } canopy_hit_t;
 
 int canopy_init(canopy_t *C, const ertb_scene_desc *d);

@@ -27,6 +27,12 @@ def polarized_aerosol_scene() -> dict:
     return d
 
 
+MESH_TREE = [
+    {"id": "crown", "filename": os.path.join(GOLDEN, "mesh_crown.ply"), "scale": 0.01, "reflectance": 0.45, "transmittance": 0.4},
+    {"id": "trunk", "filename": os.path.join(GOLDEN, "mesh_trunk.obj"), "scale": 0.01, "reflectance": 0.3, "transmittance": 0.0},
+]
+MESH_LEAF = {"id": "curled_leaf", "filename": os.path.join(GOLDEN, "mesh_leaf_normals_ascii.ply"), "scale": 1.0,
+             "reflectance": 0.5, "transmittance": 0.3}
 CANOPY = {"lai": 2.5, "radius": 0.1, "size": (4.0, 4.0, 1.0), "padding": 1, "seed": 6}
 
 
@@ -89,6 +95,9 @@ def battery() -> dict:
         "c1_homogeneous_lambertian_pp": scenes.config_c1(spp=16),
         "c2_afgl_rpv_spherical": scenes.config_c2(spp=16, n_vza=8),
         "c3_afgl_aerosol_tab_hdistant": scenes.config_c3(spp=16, res=4),
+        # the same two at the film sizes BASELINE.json quotes (32 view angles; the 32x32 hemispherical film)
+        "c2_full_size_32vza": scenes.config_c2(spp=16),
+        "c3_full_film_32x32": scenes.config_c3(spp=16),
         # geometry x medium
         "afgl_rpv_pp": S(geometry="plane_parallel", sensor=VZA5, sza=50.0, saa=30.0),
         "homogeneous_spherical_hg": S(geometry="spherical_shell", atmosphere="homogeneous",
@@ -349,6 +358,24 @@ def battery() -> dict:
                                       canopy={"trees": {}, "size": (8.0, 8.0, 4.1)},
                                       surface={"type": "diffuse", "reflectance": 0.2},
                                       sensor={"type": "mdistant", "vza": [-55.0, -20.0, 0.0, 30.0, 65.0], "vaa": 30.0}),
+        # MeshTree instances (_tree.py:285-478): a smooth-shaded ellipsoidal crown (binary ply, centimetres) on a
+        # hexagonal-prism trunk (obj with quads and hexagons), each element with its own bilambertian BSDF
+        "canopy_mesh_trees_pp": S(geometry="plane_parallel", n_layers=60, sza=40.0, saa=30.0,
+                                  canopy={"mesh_trees": {"elements": MESH_TREE}, "size": (8.0, 8.0, 4.6)},
+                                  surface={"type": "diffuse", "reflectance": 0.2},
+                                  sensor={"type": "mdistant", "vza": [-55.0, -20.0, 0.0, 30.0, 65.0], "vaa": 30.0}),
+        # the same trees without an atmosphere, flat-shaded, plus disc leaves and a mesh leaf with its own vertex
+        # normals in the group; seen by a camera
+        "canopy_mesh_faceted_path_perspective": S(
+            geometry="plane_parallel", atmosphere=None, integrator="path", sza=25.0, saa=200.0,
+            canopy={"mesh_trees": {"elements": [dict(e, face_normals=True) for e in MESH_TREE] + [MESH_LEAF],
+                                   "positions": ((0.0, 0.0), (2.5, 1.5)),
+                                   "leaves": {"n": 60, "radius": 0.08, "centre": (0.0, 0.0, 3.3), "extent": (1.4, 1.2, 1.0),
+                                              "reflectance": 0.4, "transmittance": 0.5}},
+                    "size": (6.0, 6.0, 4.6)},
+            surface={"type": "rpv", "rho_0": 0.1, "k": 0.8, "g": -0.1},
+            sensor={"type": "perspective", "origin": [1.0, -9.0, 6.0], "look_at": [1.0, 0.5, 2.5], "fov": 35.0,
+                    "film_resolution": (4, 3)}),
         "mpdistant_canopy_image_pp": S(geometry="plane_parallel", n_layers=60, sza=30.0, canopy=CANOPY,
                                        sensor={"type": "mpdistant", "vza": 25.0, "vaa": 60.0, "film_resolution": (3, 2)}),
         "mpdistant_spherical": S(n_layers=100, sza=60.0, sensor={"type": "mpdistant", "vza": 40.0, "vaa": 0.0,

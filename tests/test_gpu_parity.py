@@ -375,6 +375,67 @@ def test_canopy_ray_caster_matches_oracle(oracle):
     assert np.allclose(n_g[same], n_o[same], atol=1e-6) and np.all(g_g[same] == g_o[same])
 
 
+def test_mesh_ray_caster_and_bsdf_update(oracle):
+    """Mesh canopy elements (triangles in the bottom-level BVH, Moeller-Trumbore as mesh.h:481-504, interpolated
+    shading normals as mesh.cpp:1500-1535): (1) the rays the compiled reference cast at the fixture meshes
+    (tests/golden/mesh_reference.json), (2) the device against the oracle's grid on a group mixing smooth and
+    faceted meshes with disc leaves, (3) an in-place update of one element's bilambertian."""
+    from tests.scene_battery import MESH_LEAF, MESH_TREE
+    from tests.test_mesh import REF, element, mesh_scene
+
+    for c in REF["cases"]:
+        sc = mesh_scene([element(c)])
+        o = np.array([r["o"] for r in c["rays"]])
+        d = np.array([r["d"] for r in c["rays"]], dtype=np.float32)
+        t_g, n_g, _ = kat.canopy_intersect(sc, o, d)
+        up = (o[:, 2] + np.array([r["t"] for r in c["rays"]]) * d[:, 2]) > 1e-3  # the device clips the canopy at the ground
+        assert np.allclose(t_g[up], np.array([r["t"] for r in c["rays"]])[up], rtol=2e-5, atol=2e-5)
+        assert np.allclose(n_g[up], np.array([r["sh_n"] for r in c["rays"]])[up], atol=2e-4)
+
+    elements = [MESH_TREE[0], dict(MESH_TREE[1], face_normals=True), MESH_LEAF]
+    leaves = {"n": 80, "radius": 0.08, "centre": (0.0, 0.0, 3.3), "extent": (1.4, 1.2, 1.0), "reflectance": 0.4, "transmittance": 0.5}
+    sc = mi_load_dict(scenes.atmosphere_scene(
+        geometry="plane_parallel", atmosphere=None, integrator="path", sza=30.0,
+        canopy={"mesh_trees": {"elements": elements, "positions": ((0.0, 0.0), (2.5, 1.5), (-2.0, 2.0)), "leaves": leaves},
+                "size": (6.0, 6.0, 4.6)},
+        sensor={"type": "mdistant", "vza": [0.0, 40.0], "vaa": 0.0}))
+    desc = sc.flat.build_desc()
+    rng = np.random.default_rng(8)
+    n = 40000
+    o = np.stack([rng.uniform(-4, 5, n), rng.uniform(-3, 5, n), rng.uniform(0.01, 5.0, n)], axis=1)
+    tgt = np.stack([rng.uniform(-3, 3.5, n), rng.uniform(-1, 3.5, n), rng.uniform(0.2, 4.5, n)], axis=1)
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    inside = rng.random(n) < 0.1  # origins inside a crown
+    o[inside] = np.array([0.0, 0.0, 3.3]) + rng.uniform(-0.4, 0.4, (inside.sum(), 3))
+    t_g, n_g, g_g = kat.canopy_intersect(sc, o, d)
+    t_o, n_o, g_o = oracle.canopy_intersect(desc, o, d.astype(np.float32).astype(np.float64))
+    z_hit = o[:, 2] + np.where(np.isfinite(t_o), t_o, 0.0) * d[:, 2]
+    ok = ~(np.isfinite(t_o) & (z_hit < 1e-3))
+    assert (np.isfinite(t_g[ok]) != np.isfinite(t_o[ok])).sum() <= 4  # (edge-on hits in float32)
+    both = ok & np.isfinite(t_g) & np.isfinite(t_o)
+    assert both.sum() > 12000 and (both & inside).sum() > 2000
+    assert np.sum(np.abs(t_g[both] - t_o[both]) > 3e-5 + 3e-5 * t_o[both]) <= 4
+    with np.errstate(invalid="ignore"):
+        same = both & (np.abs(t_g - t_o) < 1e-4)
+    # shading normals: the barycentric coordinates are recovered from the float32 hit point on the device
+    assert np.quantile(np.linalg.norm(n_g[same] - n_o[same], axis=1), 0.999) < 2e-3
+
+    spp = 1 << 18
+    before = render(sc, sensor=0, seed=2, spp=spp).raw["sum_l"].copy()
+    mi_traverse(sc).parameters.update({"bsdf_crown.reflectance.value": 0.1, "bsdf_crown.transmittance.value": 0.7})
+    after = render(sc, sensor=0, seed=2, spp=spp).raw["sum_l"]
+    from eradiate_b200.kernel._render import _device_scene
+    assert getattr(_device_scene(sc), "rebuilds", 0) == 0  # pushed in place (ERTB_PARAM_MESH_BSDF)
+    fresh = mi_load_dict(scenes.atmosphere_scene(
+        geometry="plane_parallel", atmosphere=None, integrator="path", sza=30.0,
+        canopy={"mesh_trees": {"elements": [dict(elements[0], reflectance=0.1, transmittance=0.7)] + elements[1:],
+                               "positions": ((0.0, 0.0), (2.5, 1.5), (-2.0, 2.0)), "leaves": leaves}, "size": (6.0, 6.0, 4.6)},
+        sensor={"type": "mdistant", "vza": [0.0, 40.0], "vaa": 0.0}))
+    assert np.allclose(after, render(fresh, sensor=0, seed=2, spp=spp).raw["sum_l"], rtol=1e-10)
+    assert not np.allclose(before, after, rtol=1e-2)
+
+
 def test_tree_trunk_ray_caster_and_radiance(oracle):
     """AbstractTree trunks (cylinder + cap disk, one-sided diffuse): the BVH ray caster against the oracle's
     grid, including origins inside the tube, and the closed-form radiance of the lit wall and cap."""

@@ -90,7 +90,7 @@ def _set_integrator(ty):
     (_set_integrator("path"), "ignores participating media"),
     (lambda d: d["surface_bsdf"].update({"type": "dielectric"}), "unsupported plugin type 'dielectric'"),
     (lambda d: d["measure"].update({"type": "perspective"}), "field of view"),
-    (lambda d: d.update({"mesh": {"type": "ply"}}), "mesh canopy elements"),
+    (lambda d: d.update({"mesh": {"type": "ply"}}), "inside a shapegroup only"),
     (lambda d: d["measure"]["film"].update({"width": 5}), "Film size"),
     (lambda d: d["measure"]["sampler"].update({"type": "stratified"}), "sampler"),
     (lambda d: d["illumination"].update({"type": "constant"}), "unsupported"),
@@ -300,7 +300,7 @@ def test_desc_struct_layout_is_stable():
     assert C.sizeof(_abi.PhaseDesc) == 80
     assert C.sizeof(_abi.RenderStats) == 56
     assert C.sizeof(_abi.SensorDesc) == 360
-    assert C.sizeof(_abi.LeafGroupDesc) == 56
+    assert C.sizeof(_abi.LeafGroupDesc) == 88
     assert C.sizeof(_abi.SceneDesc) == 744
     assert _abi.SceneDesc.patch_rect.offset + 32 == _abi.SceneDesc.bsdf_table.offset == 712
     assert _abi.SceneDesc.bsdf_table_res.offset == 720

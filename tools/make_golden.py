@@ -36,6 +36,8 @@ def main():
         desc = sc.flat.build_desc()
         npix = desc.sensors[0].width * desc.sensors[0].height
         spp = SPP if npix <= 8 else SPP // 2
+        if npix > 256:  # full-size films (C3 32x32 at ~475 loop trips per path): 2^23 paths in total
+            spp = max(1 << 10, (1 << 23) // npix)
         stokes = None
         if desc.polarized:
             wl, l, l2, stokes, st = oracle.render_stokes(desc, 0, SEED, spp)

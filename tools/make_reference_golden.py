@@ -39,6 +39,8 @@ OVERRIDE = {  # log2(total paths) for the BASELINE configurations
     "c1_homogeneous_lambertian_pp": 23,
     "c2_afgl_rpv_spherical": 26,
     "c3_afgl_aerosol_tab_hdistant": 24,
+    "c2_full_size_32vza": 26,
+    "c3_full_film_32x32": 24,
     "c5_polarized_ocean_aerosol_reduced": 24,
 }
 
