@@ -178,6 +178,8 @@ class SceneDesc(C.Structure):
         ("bsdf_table_res", C.c_int32 * 3),
         ("phase_mis", C.c_int32),
         ("emitter_angular_diameter", C.c_double),
+        ("hide_emitters", C.c_int32),
+        ("_pad_tail", C.c_int32),
     ]
 
 

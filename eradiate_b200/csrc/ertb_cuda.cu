@@ -292,6 +292,7 @@ struct ertb_scene {
     int max_smem_optin = 0;
     double *d_gl = nullptr;     // Gauss-Legendre nodes/weights of the ocean transmittance quadrature
     double astro_diameter = 0.0;   // astroobject: angular diameter in degrees (0 = directional emitter)
+    int hide_emitters = 0;         // integrator.cpp:29: primary rays do not see the disc
     float *d_bsdf_table = nullptr; // mqdiffuse: the measured table, [z][y][x] (static)
     int bsdf_table_res[3] = { 0, 0, 0 };
     // canopy (plane-parallel scenes): host description and the device BVH
@@ -808,7 +809,8 @@ static int scene_commit(ertb_scene *S, TableSlot &T) {
         const double omc = 2.0 * sin(0.5 * a) * sin(0.5 * a); // 1 - cos a without cancellation
         P.astro_omc = (float) omc;
         P.astro_sin2 = (float) (sin(a) * sin(a));
-        P.astro_radiance = (float) ((double) S->irradiance / (2.0 * M_PI * omc));
+        // the direct view of the disc by unscattered primary rays (volpath.cpp:329-330 switches it off)
+        P.astro_radiance = S->hide_emitters ? 0.f : (float) ((double) S->irradiance / (2.0 * M_PI * omc));
     }
     P.polarized = S->polarized;
     P.phase_mis = S->phase_mis;
@@ -1115,6 +1117,7 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
             return set_error("astroobject: 1D scenes only (no canopy, no central patch)");
         }
         S->astro_diameter = D->emitter_angular_diameter;
+        S->hide_emitters = D->hide_emitters != 0;
     }
     memset(S->patch_bsdf_params, 0, sizeof S->patch_bsdf_params);
     if (D->has_patch) {

@@ -927,10 +927,6 @@ class FlatScene:
             raise RuntimeError(f"exactly one directional emitter is supported, got {len(emitters)}")
         self.emitter = emitters[0]
         self.integrator = sc.integrator()
-        if getattr(self.emitter, "angular_diameter", 0.0) > 0.0 and getattr(self.integrator, "hide_emitters", False):
-            # volpath.cpp:114, :333: hiding the emitter switches off the direct view of the disc AND the
-            # specular-chain rule; the kernels implement the default (hide_emitters = false) only
-            raise RuntimeError("astroobject: 'hide_emitters=True' is not supported")
 
         canopy = [s for s in shapes if s.type in ("shapegroup", "instance", "disk")]
         shapes = [s for s in shapes if s.type not in ("shapegroup", "instance", "disk")]
@@ -1331,6 +1327,7 @@ class FlatScene:
         d.emitter_direction[:] = list(self.emitter.direction)
         d.irradiance = self.emitter.children["irradiance"].values["value"]
         d.emitter_angular_diameter = getattr(self.emitter, "angular_diameter", 0.0)
+        d.hide_emitters = int(bool(getattr(self.integrator, "hide_emitters", False)))
         it = self.integrator
         d.integrator = (
             {"volpathmis": _abi.INTEGRATOR_VOLPATHMIS,

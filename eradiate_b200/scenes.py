@@ -121,6 +121,7 @@ def atmosphere_scene(
     central_patch: dict | None = None,
     angular_diameter: float | None = None,
     width: float = 1.0e9,
+    hide_emitters: bool = False,
 ) -> dict:
     """Build the nested scene dict an ``AtmosphereExperiment`` would emit (with ``canopy``: a
     ``CanopyAtmosphereExperiment``, see :func:`disc_canopy`).
@@ -142,6 +143,8 @@ def atmosphere_scene(
         integ["max_depth"] = max_depth
     if rr_depth is not None:
         integ["rr_depth"] = rr_depth
+    if hide_emitters:  # MI/src/render/integrator.cpp:29
+        integ["hide_emitters"] = True
     scene["integrator"] = {"type": "moment", "nested": integ} if moment else integ
     if stokes:  # integrators/_path_tracers.py:70-78: the stokes wrapper comes last
         scene["integrator"] = {"type": "stokes", "integrator": scene["integrator"],

@@ -271,6 +271,11 @@ typedef struct ertb_scene_desc {
      * in ]0, 180[) centred on -emitter_direction, radiating `irradiance` / solid angle; 0 = the delta
      * `directional` emitter.  1D scenes (no canopy / camera / central patch). */
     double emitter_angular_diameter;
+    /* MI/src/render/integrator.cpp:29 `hide_emitters`: camera rays do not see the emitter directly (volpath.cpp:103,
+     * :114, :329-330: no emitter hit at depth 0, and hits of rays that have not scattered yet are no longer counted
+     * in full).  Only the astroobject disc can be seen at all, so the flag matters with it alone. */
+    int32_t hide_emitters;
+    int32_t _pad_tail;
 } ertb_scene_desc;
 
 /* Named updatable parameters (KernelSceneParameterMap keys resolve to these;

@@ -1534,6 +1534,10 @@ static double surf_pdf(const scene_t *S, v3 wi, v3 wo) {
 static double astro_hit(const scene_t *S, v3 d, uint64_t depth, int specular_chain, double last_pdf) {
     double em = astro_eval(S, d);
     if (em == 0.0) return 0.0;
+    if (S->desc->hide_emitters) { /* volpath.cpp:114, :329-330: no hit at depth 0, no specular chain from the camera */
+        if (depth == 0) return 0.0;
+        specular_chain = 0;
+    }
     return (depth == 0 || specular_chain) ? em : em * mis_weight(last_pdf, 1.0 / S->astro_omega);
 }
 

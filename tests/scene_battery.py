@@ -206,6 +206,15 @@ def battery() -> dict:
                     "origins": [[0.0, 0.0, scenes.EARTH_RADIUS + 1.0]] * 4,
                     "directions": [list(scenes.angles_to_direction(40.0, 0.0)), list(scenes.angles_to_direction(40.2, 0.0)),
                                    list(scenes.angles_to_direction(40.4, 0.0)), [0.0, 0.0, 1.0]]}),
+        # the same photometer with `hide_emitters` (integrator.cpp:29, volpath.cpp:329-330): the disc itself is not
+        # seen, only the light scattered into the line of sight
+        "astro_hide_emitters_from_ground_spherical": S(
+            n_layers=100, sza=40.0, saa=0.0, angular_diameter=0.5358, surface={"type": "diffuse", "reflectance": 0.2},
+            hide_emitters=True,
+            sensor={"type": "mradiancemeter", "medium": {"type": "ref", "id": "medium_atmosphere"},
+                    "origins": [[0.0, 0.0, scenes.EARTH_RADIUS + 1.0]] * 4,
+                    "directions": [list(scenes.angles_to_direction(40.0, 0.0)), list(scenes.angles_to_direction(40.2, 0.0)),
+                                   list(scenes.angles_to_direction(40.4, 0.0)), [0.0, 0.0, 1.0]]}),
         # polarized (Stokes) transport: rayleigh_polarized / tabphase_polarized + stokes integrator
         "polarized_rayleigh_pp": S(geometry="plane_parallel", n_layers=100, sza=40.0, saa=30.0, stokes=True,
                                    phase={"type": "rayleigh_polarized", "depolarization": 0.0279},

@@ -199,11 +199,12 @@ def test_astroobject_emitter_conventions():
     d["illumination"] = {"type": "astroobject", "direction": list(sun), "to_world": np.eye(4)}
     with pytest.raises(RuntimeError, match="Only one of the parameters"):
         mi_load_dict(d)
-    # the direct view of the disc follows the integrators' default hide_emitters = false (volpath.cpp:114, :333)
+    # `hide_emitters` (integrator.cpp:29; volpath.cpp:103, :329-330) travels in the descriptor, also under `moment`
     d = scenes.atmosphere_scene(n_layers=4, angular_diameter=1.0, moment=False)
+    assert mi_load_dict(d).flat.build_desc().hide_emitters == 0
     d["integrator"]["hide_emitters"] = True
-    with pytest.raises(RuntimeError, match="hide_emitters"):
-        mi_load_dict(d)
+    assert mi_load_dict(d).flat.build_desc().hide_emitters == 1
+    assert mi_load_dict(scenes.atmosphere_scene(n_layers=4, angular_diameter=1.0, hide_emitters=True)).flat.build_desc().hide_emitters == 1
     d["illumination"]["type"] = "directional"  # irrelevant for a delta emitter (never hit)
     del d["illumination"]["angular_diameter"]
     mi_load_dict(d)
@@ -301,7 +302,7 @@ def test_desc_struct_layout_is_stable():
     assert C.sizeof(_abi.RenderStats) == 56
     assert C.sizeof(_abi.SensorDesc) == 360
     assert C.sizeof(_abi.LeafGroupDesc) == 88
-    assert C.sizeof(_abi.SceneDesc) == 744
+    assert C.sizeof(_abi.SceneDesc) == 752
     assert _abi.SceneDesc.patch_rect.offset + 32 == _abi.SceneDesc.bsdf_table.offset == 712
     assert _abi.SceneDesc.bsdf_table_res.offset == 720
 

@@ -230,6 +230,14 @@ def test_astroobject_direct_beam_seen_from_the_ground(oracle, integrator):
         tol = 5.0 * np.sqrt(var[k]) + 1e-6 * expected  # delta tracking through an absorber: binary estimator
         assert abs(mean[k] - expected) < tol, (k, mean[k], expected)
     assert mean[2] == 0.0
+    # `hide_emitters` (integrator.cpp:29, volpath.cpp:329-330): the disc is not seen by camera rays; nothing
+    # scatters in this atmosphere, so the radiometer reads zero everywhere
+    d["integrator"]["nested"]["hide_emitters"] = True
+    sc = mi_load_dict(d)
+    sc.flat.medium.children["sigma_t"].values["data"][:] = prof.reshape(-1, 1, 1, 1)
+    sc.flat.medium.children["albedo"].values["data"][:] = 0.0
+    _, l, _, _ = oracle.render(sc.flat.build_desc(), 0, 11, 2000)
+    assert np.all(l == 0.0)
 
 
 def test_astroobject_small_disc_matches_directional(oracle):
