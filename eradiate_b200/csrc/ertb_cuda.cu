@@ -303,6 +303,7 @@ struct ertb_scene {
     void *d_canopy[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     std::vector<int> mesh_bsdf_base; // per group: first row of its mesh BSDFs in the table blob
     bool needs_3d = false;      // canopy or perspective sensor: rendered by ertb_canopy_kernel
+    bool has_mesh = false;      // some group holds triangles: the MESH instances of that kernel
 };
 
 static int build_canopy(ertb_scene *S) {
@@ -1180,6 +1181,7 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
                 if (!gd.triangles || !gd.triangle_bsdf || !gd.mesh_bsdfs || gd.n_mesh_bsdfs < 1 || gd.n_mesh_bsdfs > 65535) {
                     delete S; return set_error("mesh arrays missing");
                 }
+                S->has_mesh = true;
                 hg.triangles.assign(gd.triangles, gd.triangles + 18 * (size_t) gd.n_triangles);
                 hg.triangle_bsdf.assign(gd.triangle_bsdf, gd.triangle_bsdf + gd.n_triangles);
                 hg.mesh_bsdfs.assign(gd.mesh_bsdfs, gd.mesh_bsdfs + 2 * (size_t) gd.n_mesh_bsdfs);
@@ -1460,7 +1462,10 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
 #define ERTB_DISPATCH(MACRO)                                                                          \
     do {                                                                                              \
         if (c3d) {                                                                                    \
-            if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true>)); else MACRO((ertb_canopy_kernel<false, true>)); } \
+            if (S->has_mesh) {                                                                        \
+                if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true, true>)); else MACRO((ertb_canopy_kernel<false, true, true>)); } \
+                else    { if (with_stats) MACRO((ertb_canopy_kernel<true, false, true>)); else MACRO((ertb_canopy_kernel<false, false, true>)); } \
+            } else if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true>)); else MACRO((ertb_canopy_kernel<false, true>)); } \
             else    { if (with_stats) MACRO((ertb_canopy_kernel<true, false>)); else MACRO((ertb_canopy_kernel<false, false>)); } \
         } else if (pw && pol) ERTB_POOL_VARIANT(MACRO, false, true, true);                            \
         else if (pw) ERTB_POOL_VARIANT(MACRO, false, false, true);                                    \
