@@ -198,8 +198,11 @@ __device__ __forceinline__ bool trace_run(const ErtbCanopy &C, TraceState &T, in
 #define ERTB_TRACE_POSTPONE 0 // (experiment: see trace_run_postponed)
 #endif
 static_assert(ERTB_BVH_LEAF == 1, "the parking area of trace_run_postponed holds the two leaves of one step");
-#define ERTB_TRACE_PEND 4       // parked primitives per lane (2 new ones per step at most, flush at >= 3)
+#ifndef ERTB_TRACE_VOTE_EVERY
+#define ERTB_TRACE_VOTE_EVERY 4 // steps between two warp votes (power of two)
+#endif
 #define ERTB_TRACE_PEND_FLUSH 3
+#define ERTB_TRACE_PEND (ERTB_TRACE_PEND_FLUSH - 1 + 2 * ERTB_TRACE_VOTE_EVERY) // at most 2 new ones per step
 
 // The same walk with POSTPONED leaf tests.  In trace_run() a lane meets a leaf in roughly one step out of ten, so the
 // intersection code that follows the two box tests runs with 1-3 active lanes (profiles/r01e, r02g).  Here a lane
@@ -254,6 +257,7 @@ __device__ __forceinline__ bool trace_run_postponed(const ErtbCanopy &C, TraceSt
             node = next;
         }
         // ---- the postponed tests, warp-wide ----
+        if ((step & (ERTB_TRACE_VOTE_EVERY - 1)) != ERTB_TRACE_VOTE_EVERY - 1) continue;
         if (__any_sync(mask, npend >= ERTB_TRACE_PEND_FLUSH) || __all_sync(mask, walked)) {
             while (__any_sync(mask, npend > 0)) {
                 if (npend > 0) {
