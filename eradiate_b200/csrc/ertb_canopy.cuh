@@ -109,8 +109,9 @@ __device__ __forceinline__ float triangle_hit(float4 a, float4 b, float4 c, f3 o
     return (u >= 0.f && u <= 1.f && v >= 0.f && u + v <= 1.f && t >= 0.f && t <= tmax) ? t : INFINITY;
 }
 
-// `MESH` = false: the instances the host launches for canopies without triangles (disc / cylinder scenes such as C4
-// keep the instruction stream they had before meshes existed: -17 % on C4 otherwise)
+// `MESH` = false: the instances the host launches for canopies without triangles over a ground BSDF of SURVEY 8a
+// (disc / cylinder scenes such as C4 keep the instruction stream they had before meshes and the later BSDF plugins
+// existed: C4 lost 17 % with the triangle code and another 5 % with the measured BSDFs compiled in)
 template <bool MESH>
 __device__ __forceinline__ float prim_hit(const ErtbCanopy &C, float4 a, float4 b, f3 o, f3 d, float tmax) {
     const int kind = __float_as_int(b.w);
@@ -123,15 +124,12 @@ struct TraceState {
     float tmax;
     int node, ii, sp; // current node, its instance (< 0: top level), stack height
     int skip_inst, skip_disk; // the leaf the ray starts on
-    int npend;   // postponed leaf tests (ERTB_TRACE_POSTPONE): entries parked at the top end of the stack array
-    bool walked; // the descent is over (only postponed tests may be left)
     CanopyHit H;
 };
 
 __device__ __forceinline__ void trace_begin(TraceState &T, f3 o, float tmax, int skip_inst, int skip_disk) {
     T.o = o; T.tmax = tmax; T.node = 0; T.ii = -1; T.sp = 0;
     T.skip_inst = skip_inst; T.skip_disk = skip_disk;
-    T.npend = 0; T.walked = false;
     T.H.t = INFINITY; T.H.inst = -1; T.H.disk = -1;
 }
 
@@ -194,100 +192,12 @@ __device__ __forceinline__ bool trace_run(const ErtbCanopy &C, TraceState &T, in
     return done;
 }
 
-#ifndef ERTB_TRACE_POSTPONE
-#define ERTB_TRACE_POSTPONE 0 // (experiment: see trace_run_postponed)
-#endif
-static_assert(ERTB_BVH_LEAF == 1, "the parking area of trace_run_postponed holds the two leaves of one step");
-#ifndef ERTB_TRACE_VOTE_EVERY
-#define ERTB_TRACE_VOTE_EVERY 4 // steps between two warp votes (power of two)
-#endif
-#define ERTB_TRACE_PEND_FLUSH 3
-#define ERTB_TRACE_PEND (ERTB_TRACE_PEND_FLUSH - 1 + 2 * ERTB_TRACE_VOTE_EVERY) // at most 2 new ones per step
-
-// The same walk with POSTPONED leaf tests.  In trace_run() a lane meets a leaf in roughly one step out of ten, so the
-// intersection code that follows the two box tests runs with 1-3 active lanes (profiles/r01e, r02g).  Here a lane
-// only PARKS the primitive (index, instance) and goes on descending; when some lane of the warp holds
-// ERTB_TRACE_PEND_FLUSH of them -- or every lane has finished descending -- all lanes test what they hold, together.
-// Tests done later cull later (T.H.t shrinks later), so a few more nodes are visited; the hits are the same.
-// `mask`: the lanes of the warp that call this function together (they vote, and stay in the loop until all are done).
-template <bool MESH>
-__device__ __forceinline__ bool trace_run_postponed(const ErtbCanopy &C, TraceState &T, int2 *stack, f3 d, bool any, int steps,
-                                                    unsigned mask) {
-    const float big = 1e30f;
-    const f3 inv = mk3(fabsf(d.x) > 1e-30f ? 1.f / d.x : copysignf(big, d.x), fabsf(d.y) > 1e-30f ? 1.f / d.y : copysignf(big, d.y),
-                       fabsf(d.z) > 1e-30f ? 1.f / d.z : copysignf(big, d.z));
-    const int cap = ERTB_TRACE_STACK - ERTB_TRACE_PEND; // the stack proper ends where the parked entries begin
-    int node = T.node, ii = T.ii, sp = T.sp, npend = T.npend;
-    bool walked = T.walked;
-    f3 ol = T.o;
-    if (ii >= 0) { const float4 in = __ldg(C.inst + ii); ol = mk3(T.o.x - in.x, T.o.y - in.y, T.o.z - in.z); }
-    for (int step = 0; step < steps; ++step) {
-        if (!walked) {
-            const float4 *q = reinterpret_cast<const float4 *>((ii < 0 ? C.tlas : C.blas) + node);
-            const float4 l0 = __ldg(q), h0 = __ldg(q + 1), l1 = __ldg(q + 2), h1 = __ldg(q + 3);
-            const float lim = fminf(T.tmax, T.H.t);
-            float e[2] = { aabb_entry(l0, h0, ol, inv, lim), aabb_entry(l1, h1, ol, inv, lim) };
-            const int c[2] = { __float_as_int(l0.w), __float_as_int(l1.w) }, n[2] = { __float_as_int(h0.w), __float_as_int(h1.w) };
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (!(e[s] < INFINITY) || n[s] == 0) continue;
-                for (int k = c[s]; k < c[s] + n[s]; ++k) {
-                    if (ii < 0) { // an instance: its group's root goes on the stack
-                        if (sp < cap) stack[sp++] = make_int2(__ldg(C.blas_root + __float_as_int(__ldg(C.inst + k).w)), k);
-                    } else if (!(k == T.skip_disk && ii == T.skip_inst) && npend < ERTB_TRACE_PEND) {
-                        stack[ERTB_TRACE_STACK - 1 - npend] = make_int2(k, ii); // a primitive: parked
-                        ++npend;
-                    }
-                }
-                e[s] = INFINITY;
-            }
-            // inner children: the nearer one next, the other on the stack; nothing left: pop
-            const bool in0 = e[0] < INFINITY, in1 = e[1] < INFINITY, first0 = e[0] <= e[1];
-            int next = (in0 && (!in1 || first0)) ? c[0] : c[1], next_ii = ii;
-            if (in0 && in1 && sp < cap) stack[sp++] = make_int2(first0 ? c[1] : c[0], ii);
-            if (!in0 && !in1) {
-                if (sp == 0) walked = true;
-                else { const int2 top = stack[--sp]; next = top.x; next_ii = top.y; }
-            }
-            if (next_ii != ii) {
-                ii = next_ii;
-                if (ii < 0) ol = T.o;
-                else { const float4 in = __ldg(C.inst + ii); ol = mk3(T.o.x - in.x, T.o.y - in.y, T.o.z - in.z); }
-            }
-            node = next;
-        }
-        // ---- the postponed tests, warp-wide ----
-        if ((step & (ERTB_TRACE_VOTE_EVERY - 1)) != ERTB_TRACE_VOTE_EVERY - 1) continue;
-        if (__any_sync(mask, npend >= ERTB_TRACE_PEND_FLUSH) || __all_sync(mask, walked)) {
-            while (__any_sync(mask, npend > 0)) {
-                if (npend > 0) {
-                    const int2 pk = stack[ERTB_TRACE_STACK - npend];
-                    --npend;
-                    const float4 in = __ldg(C.inst + pk.y);
-                    const f3 op = mk3(T.o.x - in.x, T.o.y - in.y, T.o.z - in.z);
-                    const float t = prim_hit<MESH>(C, __ldg(C.disks + 2 * pk.x), __ldg(C.disks + 2 * pk.x + 1), op, d, fminf(T.tmax, T.H.t));
-                    if (t < T.H.t) { T.H.t = t; T.H.inst = pk.y; T.H.disk = pk.x; }
-                }
-            }
-            if (any && T.H.inst >= 0) walked = true; // a shadow ray needs one hit only
-        }
-        if (__all_sync(mask, walked && npend == 0)) break;
-    }
-    T.node = node; T.ii = ii; T.sp = sp; T.npend = npend; T.walked = walked;
-    return walked && npend == 0;
-}
-
 // whole walk in one call (KAT entry point)
 __device__ __noinline__ CanopyHit canopy_trace(const ErtbCanopy &C, f3 o, f3 d, float tmax, bool any, int skip_inst, int skip_disk) {
     TraceState T;
     int2 stack[ERTB_TRACE_STACK];
     trace_begin(T, o, tmax, skip_inst, skip_disk);
-#if ERTB_TRACE_POSTPONE
-    const unsigned mask = __activemask(); // the lanes that arrived here together walk (and vote) together
-    while (!__all_sync(mask, trace_run_postponed<true>(C, T, stack, d, any, ERTB_TRACE_STEPS, mask))) { }
-#else
     while (!trace_run<true>(C, T, stack, d, any, ERTB_TRACE_STEPS)) { }
-#endif
     return T.H;
 }
 
@@ -623,15 +533,9 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
         }
 
         // ================= BVH walk, one slice (nearest leaf of a path segment, or any leaf on a shadow ray) =================
-        {
-            const unsigned tracing = __ballot_sync(0xffffffffu, phase == LP_TRACE);
-#if ERTB_TRACE_POSTPONE
-            if (phase == LP_TRACE && trace_run_postponed<MESH>(C, T, stack, shadow ? sun : d, shadow, ERTB_TRACE_STEPS, tracing))
+        if (__any_sync(0xffffffffu, phase == LP_TRACE)) {
+            if (phase == LP_TRACE && trace_run<MESH>(C, T, stack, shadow ? sun : d, shadow, ERTB_TRACE_STEPS))
                 phase = shadow ? LP_SHADE : LP_FLIGHT;
-#else
-            if (tracing && phase == LP_TRACE && trace_run<MESH>(C, T, stack, shadow ? sun : d, shadow, ERTB_TRACE_STEPS))
-                phase = shadow ? LP_SHADE : LP_FLIGHT;
-#endif
         }
 
         // ================= free flight to the next event, the event, the sun sample it generates =================
@@ -729,7 +633,7 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 } else {
                     float f_sun, weight;
                     const f3 up = mk3(0.f, 0.f, 1.f);
-                    surface_interact<false>(P, up, sun, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
+                    surface_interact<false, false, MESH>(P, up, sun, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
                     nee = thr * f_sun * P.irradiance;
                     thr *= weight;
                     depth++;

@@ -1462,7 +1462,7 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
 #define ERTB_DISPATCH(MACRO)                                                                          \
     do {                                                                                              \
         if (c3d) {                                                                                    \
-            if (S->has_mesh) {                                                                        \
+            if (S->has_mesh || S->bsdf_type >= ERTB_BSDF_OCEAN_MISHCHENKO) { /* the general instances */  \
                 if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true, true>)); else MACRO((ertb_canopy_kernel<false, true, true>)); } \
                 else    { if (with_stats) MACRO((ertb_canopy_kernel<true, false, true>)); else MACRO((ertb_canopy_kernel<false, false, true>)); } \
             } else if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true>)); else MACRO((ertb_canopy_kernel<false, true>)); } \

@@ -160,7 +160,9 @@ __device__ __forceinline__ float mm_theta2u(float t) { return sqrtf(t * (2.f * E
 __device__ __forceinline__ float mm_phi2u(float p) { return (p + ERTB_PI) * (0.5f * ERTB_INV_PI); }
 
 // BSDF::eval (:339-393).  The tables hold f * cos(theta_o): no cosine factor is applied.
-__device__ __forceinline__ float mm_eval(const ErtbParams &P, f3 wi, f3 wo) {
+// (not inlined: a rarely used BSDF whose loops would otherwise weigh on the register allocation of every kernel that
+// can meet it -- the 3D canopy kernel lost 10 % on C4 with it inline)
+__device__ __noinline__ float mm_eval(const ErtbParams &P, f3 wi, f3 wo) {
     if (!(wi.z > 0.f && wo.z > 0.f)) return 0.f;
     const float *T = P.ocean_tables;
     const int reduction = mm_i(T, 4);
@@ -185,7 +187,7 @@ __device__ __forceinline__ float mm_eval(const ErtbParams &P, f3 wi, f3 wo) {
 }
 
 // BSDF::sample (:234-337): returns the weight spec / pdf; `pdf` is set for callers that want it
-__device__ __forceinline__ float mm_sample(const ErtbParams &P, f3 wi, float u1, float u2, f3 &wo, float &pdf) {
+__device__ __noinline__ float mm_sample(const ErtbParams &P, f3 wi, float u1, float u2, f3 &wo, float &pdf) {
     wo = mk3(0.f, 0.f, 1.f);
     pdf = 0.f;
     if (!(wi.z > 0.f)) return 0.f;
