@@ -70,7 +70,8 @@ class Bitmap:
         return self._data if dtype is None else self._data.astype(dtype)
 
     def split(self) -> list[tuple[str, "Bitmap"]]:
-        """Group channels by prefix (``Bitmap::split``): ``<root>`` first, then AOV layers."""
+        """Group channels by prefix (``Bitmap::split``, MI/src/core/bitmap.cpp:589-698): the layers come back SORTED
+        by name (byte order, :692-696: ``<root>``, ``S0`` .. ``S3``, ``m2_nested``, ``nested``)."""
         groups: dict[str, list[int]] = {}
         for i, name in enumerate(self._channel_names):
             prefix = name.rsplit(".", 1)[0] if "." in name else "<root>"
@@ -85,6 +86,7 @@ class Bitmap:
             else:
                 fmt = PixelFormat.MultiChannel
             out.append((prefix, Bitmap(self._data[:, :, idx], fmt, names)))
+        out.sort(key=lambda kv: kv[0].encode())
         return out
 
     def __repr__(self):

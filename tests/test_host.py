@@ -278,7 +278,9 @@ def test_bitmap_split_matches_experiment_process_protocol():
     s1 = np.arange(5, dtype=float)
     bmp = develop(sc, 0, s1 * 2, s1, s1 * s1, spp)
     splits = dict(bmp.split())
-    assert set(splits) == {"<root>", "nested", "m2_nested"}
+    # sorted by name as Bitmap::split does (bitmap.cpp:692-696; order recorded from the reference in
+    # tests/golden/reference_boundary.json)
+    assert [k for k, _ in bmp.split()] == ["<root>", "m2_nested", "nested"]
     assert splits["<root>"].pixel_format() == Bitmap.PixelFormat.Y
     assert splits["m2_nested"].pixel_format() == Bitmap.PixelFormat.XYZ
     assert np.array(bmp).shape == (1, 5, 7)
