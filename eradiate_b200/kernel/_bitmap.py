@@ -18,6 +18,7 @@ import numpy as np
 class PixelFormat(enum.Enum):
     Y = "Y"
     XYZ = "XYZ"
+    RGB = "RGB"
     MultiChannel = "MultiChannel"
 
 
@@ -83,6 +84,8 @@ class Bitmap:
                 fmt = PixelFormat.Y
             elif names == ["X", "Y", "Z"]:
                 fmt = PixelFormat.XYZ
+            elif names == ["R", "G", "B"]:  # the S0 .. S3 layers of the stokes integrator (stokes.cpp:190-196)
+                fmt = PixelFormat.RGB
             else:
                 fmt = PixelFormat.MultiChannel
             out.append((prefix, Bitmap(self._data[:, :, idx], fmt, names)))

@@ -29,7 +29,8 @@ def test_traverse_resolves_the_update_map_as_the_reference_does(name):
     # _render.py:333-371: every SearchSceneParameter look-up ends in the same parameter id
     assert {k: p.parameter_id for k, p in w.umap_template.items()} == ref["resolved_parameter_ids"]
     # and the parameter table holds the reference's keys (minus the passive ones this kernel has no use for)
-    want = {k for k in ref["parameters"] if not _is_passive(k)}
+    used = set(ref["resolved_parameter_ids"].values())  # (a blendphase `weight.data` is no mask bitmap)
+    want = {k for k in ref["parameters"] if k in used or not _is_passive(k)}
     assert set(w.parameters.keys()) == want
     # rendering the template for a context gives updates for exactly the resolved ids (_kernel_dict.py:276-314)
     upd = w.umap_template.render(KernelContext(w=550.0))
@@ -69,8 +70,13 @@ def test_mi_render_loop_matches_the_reference_loop(name):
                 assert str(sub.pixel_format()).split(".")[-1] == rc["pixel_format"] and list(a.shape) == rc["shape"]
                 vals[cname] = a[..., 0].ravel()
             assert np.array_equal(vals["<root>"], vals["nested"])  # box filter: the two are the same estimator
+            stokes = [k for k in vals if k.startswith("S")]
+            assert stokes == ([] if ref.get("variant") != "scalar_mono_polarized_double" else ["S0", "S1", "S2", "S3"])
             m_g, m_r = vals["nested"], np.array(rf[sid]["channels"]["nested"]["first"])
             v_g = np.maximum(vals["m2_nested"] - m_g**2, 0.0) / spp
             v_r = np.maximum(np.array(rf[sid]["channels"]["m2_nested"]["first"]) - m_r**2, 0.0) / spp
             ok, zc = sidak_ok(z_scores(m_g, v_g, m_r, v_r), alpha=0.001 / 6)  # six (context, sensor) films per case
             assert ok, (name, siah, sid, m_g, m_r)
+            for k in stokes:  # Stokes components: |S_k| <= I, compared on the scale of the noise of I
+                s_r = np.array(rf[sid]["channels"][k]["first"])
+                assert np.all(np.abs(vals[k] - s_r) <= 5.0 * np.sqrt(v_g + v_r) + 1e-12), (name, siah, k, vals[k], s_r)

@@ -38,6 +38,9 @@ def cases():
                                     sensor={"type": "mdistant", "vza": [-40.0, 0.0, 40.0], "vaa": 20.0},
                                     extra_sensors=[{"type": "hdistant", "film_resolution": (2, 2)}]),
             scenes.spectral_update_map(n, spherical=False), 1 << 18),
+        # polarized variant: the `stokes` wrapper around `moment`-less volpath (AOV layers S0 .. S3), C5-like
+        "c5_reduced_polarized_loop": (scenes.config_c5(spp=4, n_vza=3, n_layers=n, geometry="plane_parallel"),
+                                      scenes.spectral_update_map_c5(n, spherical=False), 1 << 17),
     }
 
 
@@ -53,12 +56,13 @@ def film_stats(mi, bmp, spp):
 
 
 def main():
-    rd, kd, mi = ref_eradiate.kernel("scalar_mono_double")
     out = {"generator": "tools/make_boundary_fixture.py", "reference": ref.describe(), "wavelengths": WAVELENGTHS,
            "seed": SEED, "cases": {}}
     for name, (kdict, umap, spp) in cases().items():
+        variant = "scalar_mono_polarized_double" if ref.is_polarized(kdict) else "scalar_mono_double"
+        rd, kd, mi = ref_eradiate.kernel(variant)
         mi_obj = rd.mi_load_dict(ref.to_mitsuba(mi, kdict))
-        wrapper = rd.mi_traverse(mi_obj, ref_eradiate.translate_umap(umap))
+        wrapper = rd.mi_traverse(mi_obj, ref_eradiate.translate_umap(umap, variant))
         resolved = {k: p.parameter_id for k, p in wrapper.umap_template.items()}
         kept = sorted(wrapper.parameters.keys())
         ctxs = [KernelContext(w=w) for w in WAVELENGTHS]
@@ -66,11 +70,12 @@ def main():
         films = {}
         for siah, per_sensor in results.items():
             films[repr(float(siah))] = {sid: film_stats(mi, bmp, spp) for sid, bmp in per_sensor.items()}
-        out["cases"][name] = {"spp": spp, "resolved_parameter_ids": resolved, "parameters": kept,
+        out["cases"][name] = {"spp": spp, "variant": variant, "resolved_parameter_ids": resolved, "parameters": kept,
                               "result_keys": [float(k) for k in results.keys()],
                               "sensor_ids": [list(v.keys()) for v in results.values()][0], "films": films}
         print(name, resolved, len(kept), list(films.keys()))
     # the seed sequence of the loop (rng.py): one SeedState.next() per (context, sensor)
+    rd, _, _ = ref_eradiate.kernel("scalar_mono_double")
     ss = rd.SeedState(SEED)
     out["seed_sequence_first6"] = [int(ss.next().squeeze()) for _ in range(6)]
     ours = SeedState(SEED)
