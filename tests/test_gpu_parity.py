@@ -1258,16 +1258,21 @@ def test_sharded_render_uses_the_device_of_each_rank():
         "print('RESULT ' + json.dumps(out), flush=True)\n"
         "dist.destroy_process_group()\n"
     ) % root
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29611", "-c", code]
-    # torchrun has no -c: write the script to a temporary file
+    import socket
     import tempfile
 
     with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
         f.write(code)
         script = f.name
-    cmd = cmd[:-2] + [script]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    for attempt in range(2):  # (a rendezvous that fails to come up is the launcher's business, not the renderer's: once more)
+        with socket.socket() as sk:  # a free port: a fixed one may still be in TIME_WAIT from an earlier launch
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), script]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+        if r.returncode == 0:
+            break
     os.unlink(script)
     assert r.returncode == 0, r.stderr[-3000:]
     rows = [json.loads(ln.split("RESULT ", 1)[1]) for ln in r.stdout.splitlines() if "RESULT " in ln]
