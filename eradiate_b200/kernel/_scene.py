@@ -367,11 +367,8 @@ class _Loader:
                 ph.values[name] = arr
         elif ty in ("rayleigh", "rayleigh_polarized"):
             dep = d.get("depolarization", 0.0)  # rayleigh.cpp:48 / rayleigh_polarized.cpp: a volume (get_volume)
-            vol = self.make_volume(dep, None)
-            vals = vol.layer_values()
-            if not np.all(vals == vals.flat[0]):
-                raise RuntimeError("rayleigh: layer-dependent depolarization is unsupported")
-            ph.children["depolarization"] = vol
+            # a per-layer profile is carried as a blend of two constant-depolarization leaves (phase_leaves)
+            ph.children["depolarization"] = self.make_volume(dep, None)
         elif ty == "tabphase":
             ph.values["values"] = _parse_floats(d["values"], "tabphase.values").astype(np.float32)
         elif ty == "tabphase_irregular":
@@ -1166,10 +1163,10 @@ class FlatScene:
                     raise RuntimeError("multiphase: the weights must have a positive sum in every layer")
                 if getattr(ph, "use_mis", True):
                     for leaf in _phase_leaf_nodes(ph):
-                        dep = float(leaf.children["depolarization"].layer_values().flat[0]) \
-                            if "depolarization" in leaf.children else 0.0
+                        dep = bool(np.any(leaf.children["depolarization"].layer_values() != 0.0)) \
+                            if "depolarization" in leaf.children else False
                         if leaf.type in ("rayleigh_polarized", "tabphase_polarized") or \
-                                (leaf.type == "rayleigh" and dep != 0.0):
+                                (leaf.type == "rayleigh" and dep):
                             # the mixture weight differs from the leaf's own: carried by the kernels (`phase_mis`)
                             # when the multiphase node is the medium's phase function and its components are leaves
                             flat_children = all(ph.children[f"phase{i}"].type not in ("blendphase", "multiphase")
@@ -1182,6 +1179,23 @@ class FlatScene:
                             self._phase_mis = True
                 for i in range(k):
                     walk(ph.children[f"phase{i}"], prob * (ws[i] / total))
+            elif ph.type in ("rayleigh", "rayleigh_polarized") and \
+                    ph.children["depolarization"].layer_values().size > 1:
+                # rayleigh.cpp:48,79 / rayleigh_polarized.cpp: `depolarization` is a volume evaluated at the
+                # interaction.  Every entry of the (Mueller) value is affine in (1, rho) / (2 + rho) -- r1 r2 =
+                # 2 (1 + rho) / (2 + rho), r1 = 2 (1 - rho) / (2 + rho), r1 r3 = 2 (1 - 2 rho) / (2 + rho) -- and the
+                # sampling density (1 + cos^2) does not depend on rho, so the layer's phase function IS the blend
+                # of the two constant-rho leaves at the profile's extremes with the per-layer weight
+                # w_hi = [b(rho) - b(lo)] / [b(hi) - b(lo)], b(rho) = rho / (2 + rho): same value, same pdf.
+                # (Always two leaves for a gridded profile, so that an update cannot change the leaf count.)
+                rho = self._profile(ph.children["depolarization"], n, "rayleigh.depolarization").astype(np.float64)
+                lo, hi = float(rho.min()), float(rho.max())
+                if hi >= 1.0:
+                    raise RuntimeError("Depolarization factor must be in [0, 1[")
+                b = lambda r: r / (2.0 + r)  # noqa: E731
+                w_hi = (b(rho) - b(lo)) / (b(hi) - b(lo)) if hi > lo else np.zeros(n)
+                leaves.append((_RayleighLeaf(ph.type, lo), (prob * (1.0 - w_hi)).astype(np.float32)))
+                leaves.append((_RayleighLeaf(ph.type, hi), (prob * w_hi).astype(np.float32)))
             else:
                 leaves.append((ph, prob.astype(np.float32)))
 
@@ -1414,6 +1428,13 @@ class FlatScene:
         return d
 
 
+class _RayleighLeaf:
+    """One constant-depolarization half of a Rayleigh leaf whose depolarization is a per-layer profile."""
+
+    def __init__(self, type_: str, rho: float):
+        self.type, self.rho = type_, rho
+
+
 def _phase_leaf_mueller(ph: PhaseFunction):
     """m12, m22, m33, m34, m44 arrays of a tabphase_polarized leaf (else None)."""
     if ph.type != "tabphase_polarized":
@@ -1428,10 +1449,12 @@ def _phase_leaf_desc(ph: PhaseFunction):
     if ph.type == "tabphase_polarized":
         return _abi.PHASE_TABULATED_POLARIZED, params, ph.values["m11"], ph.values["nodes"]
     if ph.type in ("rayleigh", "rayleigh_polarized"):
-        dep = ph.children["depolarization"].layer_values()
-        if not np.all(dep == dep.flat[0]):  # (also reached by parameter updates: never silently use layer 0)
-            raise RuntimeError("rayleigh: layer-dependent depolarization is unsupported")
-        params[0] = float(dep.flat[0])
+        if isinstance(ph, _RayleighLeaf):
+            params[0] = ph.rho
+        else:
+            dep = ph.children["depolarization"].layer_values()
+            assert dep.size == 1  # (gridded profiles were split by phase_leaves)
+            params[0] = float(dep.flat[0])
         if params[0] >= 1.0:
             raise RuntimeError("Depolarization factor must be in [0, 1[")
         ty = _abi.PHASE_RAYLEIGH_POLARIZED if ph.type == "rayleigh_polarized" else _abi.PHASE_RAYLEIGH

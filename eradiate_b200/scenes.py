@@ -232,6 +232,11 @@ def atmosphere_scene(
 
         if phase is None:
             phase = {"type": "rayleigh"}
+        if isinstance(phase.get("depolarization"), (list, tuple, np.ndarray)):
+            # scenes/phase/_rayleigh.py:98-131: a per-layer depolarization factor is a volume on the medium's grid
+            phase = dict(phase)
+            phase["depolarization"] = _volume(np.asarray(phase["depolarization"], dtype=np.float64), spherical,
+                                              planet_radius, toa, width)
         if aerosol and weight is not None:
             if aerosol_phase == "tabphase":
                 _, p = hg_table()

@@ -119,6 +119,14 @@ def battery() -> dict:
         "aerosol_tab_irregular_spherical": S(aerosol=True, aerosol_phase="tabphase_irregular", sensor=VZA5),
         "rayleigh_depolarized_pp": S(geometry="plane_parallel", n_layers=100, sensor=VZA5,
                                      phase={"type": "rayleigh", "depolarization": 0.0279}),
+        # depolarization factor as a per-layer volume (rayleigh.cpp:48,79; scenes/phase/_rayleigh.py:98-131),
+        # alone and below a blendphase node
+        "rayleigh_depolarization_profile_pp": S(geometry="plane_parallel", n_layers=60, sensor=VZA5, sza=40.0,
+                                                phase={"type": "rayleigh",
+                                                       "depolarization": np.linspace(0.0, 0.45, 60) ** 2 / 0.45}),
+        "aerosol_blend_depolarization_profile_spherical": S(
+            aerosol=True, aerosol_phase="hg", n_layers=60, sensor=VZA5, sza=55.0, saa=40.0,
+            phase={"type": "rayleigh", "depolarization": 0.4 - np.linspace(0.0, 0.6, 60) ** 2}),
         # sensors
         "hdistant_pp": S(geometry="plane_parallel", n_layers=100,
                          sensor={"type": "hdistant", "film_resolution": (3, 3)}),
@@ -225,6 +233,11 @@ def battery() -> dict:
                                                 phase={"type": "rayleigh_polarized"}, stokes=True, sza=50.0,
                                                 surface={"type": "rpv", "rho_0": 0.1, "k": 0.9, "g": -0.1},
                                                 sensor={"type": "mdistant", "vza": [-70.0, -20.0, 20.0, 70.0], "vaa": 45.0}),
+        "polarized_rayleigh_depolarization_profile_spherical": S(
+            n_layers=60, sza=45.0, saa=20.0, stokes=True,
+            phase={"type": "rayleigh_polarized", "depolarization": np.linspace(0.0, 0.45, 60) ** 2 / 0.45},
+            surface={"type": "diffuse", "reflectance": 0.05},
+            sensor={"type": "mdistant", "vza": [-65.0, -35.0, 0.0, 30.0, 60.0], "vaa": 60.0}),
         "polarized_aerosol_tab_pp": polarized_aerosol_scene(),
         # C5-like: polarized ocean glint (complex Fresnel Mueller matrix) under a Rayleigh atmosphere
         "polarized_ocean_pp": S(geometry="plane_parallel", n_layers=60, sza=40.0, saa=0.0, stokes=True,

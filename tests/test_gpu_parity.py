@@ -517,6 +517,29 @@ def test_canopy_leaf_optics_update_equals_fresh_scene():
     assert np.allclose(b, c, rtol=1e-9) and np.all(b < 0.8 * a)
 
 
+@pytest.mark.parametrize("phase,stokes", [("rayleigh", False), ("rayleigh_polarized", True)])
+def test_depolarization_profile_update_equals_fresh_scene(phase, stokes):
+    """`depolarization` is a volume (rayleigh.cpp:48,79): a gridded profile is updated through the parameter table
+    like sigma_t (scenes/phase/_rayleigh.py:137-165); the device receives new leaf parameters and blend weights."""
+    n = 30
+    mk = lambda rho: mi_load_dict(scenes.atmosphere_scene(  # noqa: E731
+        n_layers=n, phase={"type": phase, "depolarization": rho}, stokes=stokes, aerosol=True, aerosol_phase="hg",
+        sensor={"type": "mdistant", "vza": [-50.0, 0.0, 35.0], "vaa": 20.0}))
+    rho_a, rho_b = np.linspace(0.0, 0.2, n), np.linspace(0.5, 0.05, n) ** 2
+    sc = mk(rho_a)
+    params = mi_traverse(sc).parameters
+    key = [k for k in params.keys() if "depolarization" in k and k.endswith("data")]
+    assert len(key) == 1
+    spp = 1 << 14
+    a = render(sc, seed=4, spp=spp).raw["sum_l"].copy()
+    params.update({key[0]: rho_b.astype(np.float32).reshape(params[key[0]].shape)})
+    b = render(sc, seed=4, spp=spp).raw["sum_l"].copy()
+    c = render(mk(rho_b), seed=4, spp=spp).raw["sum_l"]
+    assert np.allclose(b, c, rtol=1e-9) and not np.allclose(a, b, rtol=1e-4)
+    from eradiate_b200.kernel._render import _device_scene
+    assert getattr(_device_scene(sc), "rebuilds", 0) == 0  # pushed in place (PHASE_PARAMS + PHASE_WEIGHT)
+
+
 @pytest.mark.parametrize("surface,changes", [
     # the parameters each plugin's traverse() publishes (ocean_mishchenko.cpp:118-123, ocean_grasp.cpp:147-153,
     # maignan.cpp:103-109); `wavelength` of ocean_grasp is what Eradiate updates per spectral context
