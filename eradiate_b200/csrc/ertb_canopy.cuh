@@ -389,7 +389,23 @@ __device__ __forceinline__ float sun_medium_transmittance(const ErtbParams &P, c
     return tr;
 }
 
-enum : int { CEV_NONE = 0, CEV_COLLISION = 1, CEV_GROUND = 2, CEV_LEAF = 3, CEV_END = 4 };
+// astroobject.cpp:141-175: a direction uniform in the cone of the solar disc about `sun` (weight: the irradiance)
+__device__ __forceinline__ f3 astro_sample(const ErtbParams &P, f3 sun, Pcg32 &rng) {
+    float ox, oy;
+    disk_concentric(pcg_float(rng), pcg_float(rng), ox, oy);
+    const float t = P.astro_omc * fmaf(ox, ox, oy * oy); // 1 - cos(theta) of the sample
+    const float sc = sqrtf(P.astro_omc * (2.f - t));     // sin(theta) / sqrt(ox^2 + oy^2)
+    f3 fs, ft;
+    onb(sun, fs, ft);
+    return normalize3(fma3(fs, ox * sc, fma3(ft, oy * sc, scale3(sun, 1.f - t))));
+}
+// astroobject.cpp:111-124: radiance of the disc seen along `d` (0 for a directional emitter or with hide_emitters)
+__device__ __forceinline__ float astro_direct(const ErtbParams &P, f3 d, f3 sun) {
+    const f3 cx = cross3(d, sun);
+    return (P.astro_radiance > 0.f && dot3(d, sun) > 0.f && dot3(cx, cx) < P.astro_sin2) ? P.astro_radiance : 0.f;
+}
+
+enum : int { CEV_NONE = 0, CEV_COLLISION = 1, CEV_GROUND = 2, CEV_LEAF = 3, CEV_END = 4, CEV_CLIP = 5 };
 // lane state machine
 enum : int { LP_NEW = 0, LP_SEGMENT = 1, LP_TRACE = 2, LP_FLIGHT = 3, LP_SHADE = 4 };
 
@@ -412,6 +428,10 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
     double p[3] = { 0.0, 0.0, 0.0 };
     f3 d = mk3(0.f, 0.f, -1.f);
     float thr = 0.f, res = 0.f, wray = 1.f, maxt = INFINITY, nee = 0.f;
+    // next-event direction of the last event: the sun, or (general instances, astroobject.cpp:141-175) a point of the
+    // solar disc drawn at the event -- it has to outlive the shadow-ray walk
+    f3 sun_e = sun;
+#define SUN_E (MESH ? sun_e : sun)
     unsigned depth = 0, pix = 0;
     int on_inst = -1, on_disk = -1; // the leaf the current ray starts on
     // the segment being resolved: distance / kind of the next analytic surface, start of the BVH walk
@@ -503,7 +523,10 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
             }
             // a ray above the atmosphere travels through vacuum down to its top
             if (!dead && !in_medium && medium && (float) (p[2] - z_ground) >= P.H) {
-                if (!(d.z < 0.f)) dead = true; // leaves the scene
+                if (!(d.z < 0.f)) { // leaves the scene
+                    dead = true;
+                    if (MESH && depth == 0u) res += astro_direct(P, d, sun);
+                }
                 else {
                     double t_in = ((double) P.H - (p[2] - z_ground)) / (double) d.z;
                     p[0] += t_in * (double) d.x; p[1] += t_in * (double) d.y; p[2] = z_ground + (double) P.H;
@@ -519,7 +542,13 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                              : (in_medium && d.z > 0.f ? fmax((double) P.H - (p[2] - z_ground), 0.0) / (double) d.z : 1e30);
                 ev_geo = down ? CEV_GROUND : CEV_END; // upward: leaves through the top (or to infinity)
                 if (t_geo > 1e9) { t_geo = 1e9; ev_geo = CEV_END; } // grazing rays: the reference's slab is 1e9 m wide
-                if (first_segment && (double) maxt < t_geo) { t_geo = (double) maxt; ev_geo = CEV_END; } // far clip
+                // far clip. (General instances: a ray clipped INSIDE the medium carries no throughput in the reference --
+                // transmittance_eval_pdf over an infinite distance, volpath.cpp:229-233 -- so it does not see the solar
+                // disc of an astroobject either; a ray clipped in vacuum does)
+                if (first_segment && (double) maxt < t_geo) {
+                    t_geo = (double) maxt;
+                    ev_geo = (MESH && in_medium && medium) ? CEV_CLIP : CEV_END;
+                }
                 // ---- nearest leaf: walk the BVH over the part of the segment inside the canopy's box ----
                 double t1;
                 shadow = false;
@@ -534,7 +563,7 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
 
         // ================= BVH walk, one slice (nearest leaf of a path segment, or any leaf on a shadow ray) =================
         if (__any_sync(0xffffffffu, phase == LP_TRACE)) {
-            if (phase == LP_TRACE && trace_run<MESH>(C, T, stack, shadow ? sun : d, shadow, ERTB_TRACE_STEPS))
+            if (phase == LP_TRACE && trace_run<MESH>(C, T, stack, shadow ? SUN_E : d, shadow, ERTB_TRACE_STEPS))
                 phase = shadow ? LP_SHADE : LP_FLIGHT;
         }
 
@@ -567,6 +596,9 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 }
             }
             first_segment = false;
+            const bool escaped = ev == CEV_END; // no event on this segment: the ray leaves the scene
+            if (MESH && ev == CEV_CLIP) ev = CEV_END;
+            if (MESH && P.astro_omc > 0.f && !escaped) sun_e = astro_sample(P, sun, rng);
             if (ev != CEV_END) {
                 p[0] += t_ev * (double) d.x; p[1] += t_ev * (double) d.y; p[2] += t_ev * (double) d.z;
                 if (ev == CEV_GROUND) p[2] = z_ground;
@@ -581,7 +613,7 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 if (STATS) st_scatter++;
                 if (depth >= P.max_depth || thr == 0.f) ev = CEV_END;
                 else {
-                    float ct_sun = dot3(d, sun);
+                    float ct_sun = dot3(d, SUN_E);
                     float pv = 0.f;
                     int leaf = 0;
                     if (P.n_phase == 1) pv = leaf_eval(tb, P.leaf[0], ct_sun);
@@ -607,6 +639,19 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                         f3 fs, ft;
                         onb(d, fs, ft);
                         d = normalize3(fma3(fs, st * cp, fma3(ft, st * sp, scale3(d, ct))));
+                        if (MESH && P.phase_mis) { // multiphase.cpp:176-200: mixture value / mixture pdf
+                            float num = 0.f, den = 0.f, prev = 0.f;
+                            for (int i = 0; i < P.n_phase; ++i) {
+                                float cum = (i < P.n_phase - 1) ? tb[P.off_cumw + i * P.n_layers + l] : 1.f;
+                                float w = cum - prev;
+                                prev = cum;
+                                if (w > 0.f) {
+                                    num = fmaf(w, leaf_eval(tb, P.leaf[i], ct), num);
+                                    den = fmaf(w, leaf_pdf(tb, P.leaf[i], ct), den);
+                                }
+                            }
+                            pw = den > 1e-8f ? __fdividef(num, den) : 0.f;
+                        }
                         thr *= pw;
                     }
                 }
@@ -620,8 +665,8 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                          fabs(p[1] - C.patch_rect[1]) <= C.patch_rect[3]) {
                     // CentralPatchSurface (blendbsdf.cpp:108-165 with a 0/1 mask): the patch's own land BSDF
                     const float *pp = tb + C.off_patch_bsdf;
-                    if (depth + 1u < P.max_depth && sun.z > 0.f)
-                        nee = thr * land_bsdf(C.patch_type, pp, ci, sun.z, cos_dphi(ci, sun.z, -dot3(d, sun))) * sun.z * P.irradiance;
+                    if (depth + 1u < P.max_depth && SUN_E.z > 0.f)
+                        nee = thr * land_bsdf(C.patch_type, pp, ci, SUN_E.z, cos_dphi(ci, SUN_E.z, -dot3(d, SUN_E))) * SUN_E.z * P.irradiance;
                     float u1 = pcg_float(rng), u2 = pcg_float(rng);
                     f3 wl = cosine_hemisphere(u1, u2);
                     float weight = 0.f;
@@ -633,7 +678,7 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 } else {
                     float f_sun, weight;
                     const f3 up = mk3(0.f, 0.f, 1.f);
-                    surface_interact<false, false, MESH>(P, up, sun, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
+                    surface_interact<false, false, MESH>(P, up, SUN_E, ci, depth + 1u < P.max_depth, rng, d, f_sun, weight);
                     nee = thr * f_sun * P.irradiance;
                     thr *= weight;
                     depth++;
@@ -652,7 +697,7 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 float r_ = lb[0], t_ = lb[1];
                 if (MESH && kind == 3) { r_ = tb[C.off_mesh_bsdf + 2 * mat]; t_ = tb[C.off_mesh_bsdf + 2 * mat + 1]; }
                 else if (kind != 0) { r_ = ci > 0.f ? lb[2] : 0.f; t_ = 0.f; }
-                if (depth + 1u < P.max_depth) nee = thr * bilambertian_eval(r_, t_, ci, dot3(n, sun)) * P.irradiance;
+                if (depth + 1u < P.max_depth) nee = thr * bilambertian_eval(r_, t_, ci, dot3(n, SUN_E)) * P.irradiance;
                 float s1 = pcg_float(rng), u1 = pcg_float(rng), u2 = pcg_float(rng);
                 f3 wl;
                 thr *= bilambertian_sample(r_, t_, ci, s1, u1, u2, wl);
@@ -661,20 +706,24 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
                 d = normalize3(fma3(fs, wl.x, fma3(ft, wl.y, scale3(n, wl.z))));
                 depth++;
             }
-            if (ev == CEV_END) CANOPY_FINISH();
-            else {
+            if (ev == CEV_END) {
+                // astroobject: a primary ray that met nothing looks at the sky and sees the disc if it points into it
+                // (volpath.cpp:328-346, throughput 1; scattered rays reach the disc by next-event estimation only)
+                if (MESH && escaped && depth == 0u) res += astro_direct(P, d, sun);
+                CANOPY_FINISH();
+            } else {
                 // ---- next-event estimation (volpath.cpp:400-554): leaves and the ground are opaque to the
                 //      shadow ray, the medium attenuates it. The occlusion test is the second BVH walk. ----
                 phase = LP_SEGMENT;
                 if (STATS && nee != 0.f && !(in_medium && medium)) st_nee++; // a vacuum shadow ray is one loop trip
-                if (!(sun.z > 0.f)) nee = 0.f; // the ground plane is in the way
+                if (!(SUN_E.z > 0.f)) nee = 0.f; // the ground plane is in the way
                 if (nee != 0.f) { // (either sign: a BSDF such as RTLS may be negative at grazing angles)
                     double t1;
                     shadow = true;
                     T.H.inst = -1;
                     phase = LP_SHADE;
-                    if (C.n_instances && canopy_clip(C, p, sun, 1e30, t_clip0, t1)) {
-                        trace_begin(T, canopy_local(C, p, sun, t_clip0), (float) (t1 - t_clip0), on_inst, on_disk);
+                    if (C.n_instances && canopy_clip(C, p, SUN_E, 1e30, t_clip0, t1)) {
+                        trace_begin(T, canopy_local(C, p, SUN_E, t_clip0), (float) (t1 - t_clip0), on_inst, on_disk);
                         phase = LP_TRACE;
                     }
                 }
@@ -686,13 +735,14 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
             if (T.H.inst < 0) {
                 float tr = 1.f;
                 if (in_medium && medium)
-                    tr = sun_medium_transmittance<PW, STATS>(P, tb, fmaxf((float) (p[2] - z_ground), 0.f), sun, rng, st_nee);
+                    tr = sun_medium_transmittance<PW, STATS>(P, tb, fmaxf((float) (p[2] - z_ground), 0.f), SUN_E, rng, st_nee);
                 res = fmaf(nee, tr, res);
             }
             phase = LP_SEGMENT;
         }
     }
 #undef CANOPY_FINISH
+#undef SUN_E
 
     film_flush_warp<false>(P, lane, true, acc_pix, acc_wl, acc_l, acc_l2, 0.0, 0.0, 0.0);
     if (STATS && P.stats) {

@@ -1113,10 +1113,6 @@ int ertb_scene_create(const ertb_scene_desc *D, int device, ertb_scene **out) {
             delete S;
             return set_error("Invalid angular diameter specified! (must be in ]0, 180[)");
         }
-        if (D->n_instances > 0 || D->has_patch) {
-            delete S;
-            return set_error("astroobject: 1D scenes only (no canopy, no central patch)");
-        }
         S->astro_diameter = D->emitter_angular_diameter;
         S->hide_emitters = D->hide_emitters != 0;
     }
@@ -1416,13 +1412,8 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     const bool c3d = S->needs_3d; // canopy / perspective camera: the 3D kernel (ertb_canopy.cuh)
     if (pol || pw) use_pool = true; // the polarized and the piecewise paths exist in the pool kernel only
     if (c3d) use_pool = false;
-    if (S->astro_diameter > 0.0) { // the finite solar disc exists in the pool kernel only
-        if (c3d) return set_error("astroobject: not supported with a perspective camera or a canopy");
-        use_pool = true;
-    }
-    if (S->phase_mis && c3d) return set_error("multiphase with use_mis: not supported with a perspective camera or a canopy");
-    // general primary rays and the finite solar disc exist in the GEN instances of the pool kernel only
-    // (compiled with statistics on)
+    // general primary rays, the finite solar disc (astroobject) and the mixture weight of multiphase exist in the GEN
+    // instances of the pool kernel (compiled with statistics on) and in the general instances of the 3D kernel
     const bool gen_needed = !c3d && (hs.desc.type == ERTB_SENSOR_MPDISTANT || hs.desc.type == ERTB_SENSOR_MRADIANCEMETER ||
                                      S->astro_diameter > 0.0 || S->phase_mis);
     if (gen_needed) use_pool = true;
@@ -1462,7 +1453,7 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
 #define ERTB_DISPATCH(MACRO)                                                                          \
     do {                                                                                              \
         if (c3d) {                                                                                    \
-            if (S->has_mesh || S->bsdf_type >= ERTB_BSDF_OCEAN_MISHCHENKO) { /* the general instances */  \
+            if (S->has_mesh || S->bsdf_type >= ERTB_BSDF_OCEAN_MISHCHENKO || S->astro_diameter > 0.0 || S->phase_mis) { /* the general instances */ \
                 if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true, true>)); else MACRO((ertb_canopy_kernel<false, true, true>)); } \
                 else    { if (with_stats) MACRO((ertb_canopy_kernel<true, false, true>)); else MACRO((ertb_canopy_kernel<false, false, true>)); } \
             } else if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true>)); else MACRO((ertb_canopy_kernel<false, true>)); } \

@@ -347,8 +347,6 @@ static int scene_init(scene_t *S, const ertb_scene_desc *d) {
     S->astro = d->emitter_angular_diameter > 0.0;
     if (S->astro) { /* astroobject.cpp:75-80 */
         if (!(d->emitter_angular_diameter < 180.0)) return fail("Invalid angular diameter specified! (must be in ]0, 180[)");
-        if (d->n_instances > 0 || d->has_patch)
-            return fail("astroobject: 1D scenes only (no canopy, no central patch)");
         S->astro_cos = cos(0.5 * d->emitter_angular_diameter * PI / 180.0);
         S->astro_omega = 2.0 * PI * (1.0 - S->astro_cos);
     }
@@ -1514,9 +1512,15 @@ static double pw_medium_step(const scene_t *S, pcg32 *rng, const ray_t *ray, si_
 
 /* volpath.cpp:93-396 (mono, unpolarized).  mis != 0 selects the volpathmis.cpp
  * Russian-roulette placement (:227-231), the only difference left in mono. */
-/* BSDF::pdf of the ground (only needed for MIS against a non-delta emitter: astroobject scenes, no canopy) */
-static double surf_pdf(const scene_t *S, v3 wi, v3 wo) {
+/* BSDF::pdf of the shape that was hit (only needed for MIS against a non-delta emitter: astroobject scenes) */
+static double surf_pdf(const scene_t *S, const si_t *si, v3 wi, v3 wo) {
+    if (si->shape == SHAPE_LEAF && !si->trunk) { /* bilambertian.cpp:161-204 */
+        const canopy_group_t *G = &S->canopy.groups[si->group];
+        double a[3] = { wi.x, wi.y, wi.z }, b[3] = { wo.x, wo.y, wo.z };
+        return si->mesh ? bilambertian_pdf(si->mesh_r, si->mesh_t, a, b) : bilambertian_pdf(G->reflectance, G->transmittance, a, b);
+    }
     if (!(wi.z > 0.0 && wo.z > 0.0)) return 0.0;
+    if (si->shape == SHAPE_LEAF || on_patch(S, si->p)) return INV_PI * wo.z; /* trunk (diffuse.cpp:145-160), patch land BSDF */
     const int type = S->desc->bsdf_type;
     if (type == ERTB_BSDF_OCEAN_LEGACY) return ocean_pdf(&S->ocean, wi.x, wi.y, wi.z, wo.x, wo.y, wo.z);
     if (type == ERTB_BSDF_OCEAN_MISHCHENKO || type == ERTB_BSDF_OCEAN_GRASP) {
@@ -1650,13 +1654,13 @@ static double volpath_sample(const scene_t *S, pcg32 *rng, ray_t ray, int medium
                     double emitted = (pw ? pw_sample_emitter : sample_emitter)(S, rng, si.p, si.n, medium, C, &ds_d, &ds_pdf);
                     v3 wo = to_local(&fr, ds_d);
                     const double fv = surf_eval(S, &si, wi, wo);
-                    result += throughput * fv * emitted * (ds_pdf > 0.0 ? mis_weight(ds_pdf, surf_pdf(S, wi, wo)) : 1.0);
+                    result += throughput * fv * emitted * (ds_pdf > 0.0 ? mis_weight(ds_pdf, surf_pdf(S, &si, wi, wo)) : 1.0);
                     if (!C->ray_opaque && throughput * fv > 0.0) C->flights_nee += C->ray_flights;
                 }
                 double s1 = next_1d(rng), u1 = next_1d(rng), u2 = next_1d(rng);
                 v3 wo;
                 throughput *= surf_sample(S, &si, wi, s1, u1, u2, &wo);
-                if (S->astro) last_pdf = surf_pdf(S, wi, wo); /* bs.pdf, :383 */
+                if (S->astro) last_pdf = surf_pdf(S, &si, wi, wo); /* bs.pdf, :383 */
                 specular_chain = 0; /* every ground BSDF here is smooth, :387 */
                 wo_world = to_world(&fr, wo);
                 depth++;
@@ -1840,7 +1844,7 @@ C->flights_main++;
                     mueller_t B, TB;
                     bsdf_eval_mueller(S, &fr, wi, wo, &B);
                     TB = mu_mul(&T, &B);
-                    const double wm = ds_pdf > 0.0 ? mis_weight(ds_pdf, surf_pdf(S, wi, wo)) : 1.0;
+                    const double wm = ds_pdf > 0.0 ? mis_weight(ds_pdf, surf_pdf(S, &si, wi, wo)) : 1.0;
                     for (int i = 0; i < 4; ++i) result[i] += TB.m[4 * i] * emitted * wm;
                     if (!C->ray_opaque && TB.m[0] > 0.0) C->flights_nee += C->ray_flights;
                 }
@@ -1855,7 +1859,7 @@ C->flights_main++;
                     Dw.m[0] = w; /* depolarizer(w) */
                 }
                 T = mu_mul(&T, &Dw);
-                if (S->astro) last_pdf = surf_pdf(S, wi, wo);
+                if (S->astro) last_pdf = surf_pdf(S, &si, wi, wo);
                 specular_chain = 0;
                 wo_world = to_world(&fr, wo);
                 depth++;
@@ -1992,8 +1996,12 @@ int ertbo_bsdf_eval(const ertb_scene_desc *desc, size_t n, const double *wi, con
 int ertbo_bsdf_pdf(const ertb_scene_desc *desc, size_t n, const double *wi, const double *wo, double *out) {
     scene_t S;
     if (scene_init(&S, desc)) return 1;
+    si_t ground;
+    memset(&ground, 0, sizeof ground);
+    ground.shape = SHAPE_GROUND;
+    ground.p = V(1e30, 1e30, 0.0); /* (never on a central patch) */
     for (size_t i = 0; i < n; ++i)
-        out[i] = surf_pdf(&S, V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
+        out[i] = surf_pdf(&S, &ground, V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
     scene_free(&S);
     return 0;
 }

@@ -398,6 +398,43 @@ def battery() -> dict:
             surface={"type": "rpv", "rho_0": 0.1, "k": 0.8, "g": -0.1},
             sensor={"type": "perspective", "origin": [1.0, -9.0, 6.0], "look_at": [1.0, 0.5, 2.5], "fov": 35.0,
                     "film_resolution": (4, 3)}),
+        # astroobject / multiphase-MIS in the 3D kernel's general instances: penumbrae of the leaves under a wide disc;
+        # a camera under the canopy looking at the disc through the gaps (direct view, volpath.cpp:328-346); a
+        # central patch under the disc; the multiphase mixture weight above a canopy
+        "astro_canopy_wide_disc_pp": S(geometry="plane_parallel", n_layers=60, sza=35.0, saa=40.0, angular_diameter=8.0,
+                                       canopy=dict(CANOPY, reflectance=0.5, transmittance=0.4),
+                                       surface={"type": "diffuse", "reflectance": 0.3}, sensor=VZA5),
+        "astro_canopy_camera_at_the_disc_pp": S(
+            geometry="plane_parallel", n_layers=60, sza=30.0, saa=0.0, angular_diameter=12.0,
+            canopy=dict(CANOPY, lai=1.5), surface={"type": "diffuse", "reflectance": 0.2},
+            sensor={"type": "perspective", "origin": [0.9, -0.7, 0.02],
+                    "look_at": [float(v) for v in np.array([0.9, -0.7, 0.02]) + scenes.angles_to_direction(30.0, 0.0)],
+                    "fov": 16.0, "far_clip": 1e7, "film_resolution": (2, 2),
+                    "medium": {"type": "ref", "id": "medium_atmosphere"}}),
+        # ... and with the default far clip of 10 km: the clipped ray ends inside the medium, where the reference gives
+        # it no throughput (transmittance_eval_pdf over an infinite distance, volpath.cpp:229-233): no disc
+        # (homogeneous medium: under a heterogeneous one the reference measures the clip distance from the last NULL
+        # collision instead of the camera -- ray.maxt is not shortened at :255-258 -- which the kernel does not imitate)
+        "astro_camera_far_clip_in_medium_pp": S(
+            geometry="plane_parallel", atmosphere="homogeneous", homogeneous_sigma_t=2e-5, homogeneous_albedo=0.95,
+            sza=30.0, saa=0.0, angular_diameter=12.0,
+            surface={"type": "diffuse", "reflectance": 0.2},
+            sensor={"type": "perspective", "origin": [0.0, 0.0, 0.05],
+                    "look_at": [float(v) for v in np.array([0.0, 0.0, 0.05]) + scenes.angles_to_direction(30.0, 0.0)],
+                    "fov": 16.0, "film_resolution": (2, 2), "medium": {"type": "ref", "id": "medium_atmosphere"}}),
+        "astro_central_patch_pp": S(
+            geometry="plane_parallel", n_layers=60, sza=50.0, saa=10.0, angular_diameter=5.0,
+            surface={"type": "diffuse", "reflectance": 0.05},
+            central_patch={"edges": (4.0, 4.0), "bsdf": {"type": "rpv", "rho_0": 0.25, "k": 0.8, "g": -0.1}},
+            sensor={"type": "mpdistant", "vza": 20.0, "vaa": 45.0, "film_resolution": (3, 3),
+                    "target": {"type": "rectangle", "to_world": scenes.ScalarTransform4f().scale([6.0, 6.0, 1.0])}}),
+        "canopy_multiphase_mis_pp": S(
+            geometry="plane_parallel", atmosphere="homogeneous", homogeneous_sigma_t=0.8 / scenes.TOA,
+            homogeneous_albedo=0.97, sensor=VZA5, sza=40.0, surface={"type": "diffuse", "reflectance": 0.1},
+            canopy=dict(CANOPY, lai=1.0),
+            phase={"type": "multiphase", "use_mis": True,
+                   "phase0": {"type": "rayleigh", "depolarization": 0.25}, "weight0": 2.0,
+                   "phase1": {"type": "hg", "g": 0.75}, "weight1": 1.0}),
         "mpdistant_canopy_image_pp": S(geometry="plane_parallel", n_layers=60, sza=30.0, canopy=CANOPY,
                                        sensor={"type": "mpdistant", "vza": 25.0, "vaa": 60.0, "film_resolution": (3, 2)}),
         "mpdistant_spherical": S(n_layers=100, sza=60.0, sensor={"type": "mpdistant", "vza": 40.0, "vaa": 0.0,
