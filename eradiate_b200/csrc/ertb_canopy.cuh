@@ -71,7 +71,17 @@ __device__ __forceinline__ float disk_hit(float4 c, float4 n, f3 o, f3 d, float 
 }
 
 #ifndef ERTB_TRACE_STEPS
-#define ERTB_TRACE_STEPS 32
+#define ERTB_TRACE_STEPS 32 // node visits per sub-slice of the BVH walk
+#endif
+#ifndef ERTB_TRACE_SUBS
+#define ERTB_TRACE_SUBS 2 // VOTE form: sub-slices per trip of the main loop, at most
+#endif
+#ifndef ERTB_TRACE_KEEP_NUM
+#define ERTB_TRACE_KEEP_NUM 1 // VOTE form: the next sub-slice runs while NUM / DEN of the lanes that entered still walk
+#define ERTB_TRACE_KEEP_DEN 2
+#endif
+#ifndef ERTB_VOTE_MAX_PRIMS
+#define ERTB_VOTE_MAX_PRIMS 8192 // largest group (primitives) for which the host picks the VOTE form
 #endif
 #define ERTB_TRACE_STACK 40
 
@@ -137,16 +147,23 @@ __device__ __forceinline__ void trace_begin(TraceState &T, f3 o, float tmax, int
 // or, with `any`, the first leaf found). ONE loop walks both levels: a stack entry is (node, instance),
 // instance < 0 meaning a node of the top-level tree, so the lanes of a warp always execute the same
 // few instructions (fetch a node, test its two child boxes, push) whichever level each of them is in.
-template <bool MESH>
-__device__ __forceinline__ bool trace_run(const ErtbCanopy &C, TraceState &T, int2 *stack, f3 d, bool any, int steps) {
+// VOTE: every lane of the warp calls (`active`: the lanes that walk); sub-slices of `steps` visits follow one another
+// while enough of the lanes that entered still walk (see the kernel's BVH stage).
+template <bool MESH, bool VOTE = false>
+__device__ __forceinline__ bool trace_run(const ErtbCanopy &C, TraceState &T, int2 *stack, f3 d, bool any, int steps,
+                                          bool active = true) {
     const float big = 1e30f;
     const f3 inv = mk3(fabsf(d.x) > 1e-30f ? 1.f / d.x : copysignf(big, d.x), fabsf(d.y) > 1e-30f ? 1.f / d.y : copysignf(big, d.y),
                        fabsf(d.z) > 1e-30f ? 1.f / d.z : copysignf(big, d.z));
     int node = T.node, ii = T.ii, sp = T.sp;
     f3 ol = T.o;
     if (ii >= 0) { const float4 in = __ldg(C.inst + ii); ol = mk3(T.o.x - in.x, T.o.y - in.y, T.o.z - in.z); }
-    bool done = false;
-    for (int step = 0; step < steps; ++step) {
+    bool done = !active;
+    const int n_enter = VOTE ? __popc(__ballot_sync(0xffffffffu, active)) : 0;
+    for (int step = 0; step < (VOTE ? steps * ERTB_TRACE_SUBS : steps); ++step) {
+        if (VOTE && step > 0 && step % steps == 0 &&
+            __popc(__ballot_sync(0xffffffffu, !done)) * ERTB_TRACE_KEEP_DEN < n_enter * ERTB_TRACE_KEEP_NUM) break;
+        if (VOTE && done) continue;
         const float4 *q = reinterpret_cast<const float4 *>((ii < 0 ? C.tlas : C.blas) + node);
         const float4 l0 = __ldg(q), h0 = __ldg(q + 1), l1 = __ldg(q + 2), h1 = __ldg(q + 3);
         const float lim = fminf(T.tmax, T.H.t);
@@ -168,7 +185,7 @@ __device__ __forceinline__ bool trace_run(const ErtbCanopy &C, TraceState &T, in
             }
             e[s] = INFINITY;
         }
-        if (any && T.H.inst >= 0) { done = true; break; }
+        if (any && T.H.inst >= 0) { done = true; if (VOTE) continue; else break; }
         // inner children: the nearer one next, the other on the stack
         if (e[0] < INFINITY && e[1] < INFINITY) {
             const bool first0 = e[0] <= e[1];
@@ -177,7 +194,7 @@ __device__ __forceinline__ bool trace_run(const ErtbCanopy &C, TraceState &T, in
         } else if (e[0] < INFINITY) next = c[0];
         else if (e[1] < INFINITY) next = c[1];
         else {
-            if (sp == 0) { done = true; break; }
+            if (sp == 0) { done = true; if (VOTE) continue; else break; }
             const int2 top = stack[--sp];
             next = top.x; next_ii = top.y;
         }
@@ -189,7 +206,7 @@ __device__ __forceinline__ bool trace_run(const ErtbCanopy &C, TraceState &T, in
         node = next;
     }
     T.node = node; T.ii = ii; T.sp = sp;
-    return done;
+    return done && active;
 }
 
 // whole walk in one call (KAT entry point)
@@ -409,7 +426,8 @@ enum : int { CEV_NONE = 0, CEV_COLLISION = 1, CEV_GROUND = 2, CEV_LEAF = 3, CEV_
 // lane state machine
 enum : int { LP_NEW = 0, LP_SEGMENT = 1, LP_TRACE = 2, LP_FLIGHT = 3, LP_SHADE = 4 };
 
-template <bool STATS, bool PW, bool MESH = false>
+// VOTE: the form of the BVH stage for canopies of small groups (see there).
+template <bool STATS, bool PW, bool MESH = false, bool VOTE = false>
 __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_canopy_kernel(const ErtbParams P) {
     extern __shared__ __align__(16) float tb[]; // table blob
     __shared__ __align__(8) unsigned long long mbar;
@@ -562,8 +580,19 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
         }
 
         // ================= BVH walk, one slice (nearest leaf of a path segment, or any leaf on a shadow ray) =================
+        // Two forms.  Fixed slices (VOTE = false): the lanes that walk advance by ERTB_TRACE_STEPS node visits.  Every
+        // trip of the main loop costs the other stages' votes and divergent code -- and the set-up of the walk itself --
+        // whatever the number of lanes that need them (C4: 112 / 158 / 168 / 160 Mpaths/s at slices of 8 / 32 / 64 /
+        // 128 visits): short slices pay it too often, long ones keep finished lanes waiting.  VOTE = true: EVERY lane
+        // enters the walk's loop (idle ones skip the body), whose trip count is then warp-uniform, and a second
+        // sub-slice follows while at least half of the lanes that entered still walk.  Canopies of small groups
+        // (abstract / mesh trees, a few hundred primitives: walks of a dozen visits) gain 13-20 % from it, the 60 k-leaf
+        // groups of C4 lose 0-4 % (profiles/r02t_canopy_slices.md): the host picks the form from the group sizes.
         if (__any_sync(0xffffffffu, phase == LP_TRACE)) {
-            if (phase == LP_TRACE && trace_run<MESH>(C, T, stack, shadow ? SUN_E : d, shadow, ERTB_TRACE_STEPS))
+            if (VOTE) {
+                if (trace_run<MESH, true>(C, T, stack, shadow ? SUN_E : d, shadow, ERTB_TRACE_STEPS, phase == LP_TRACE))
+                    phase = shadow ? LP_SHADE : LP_FLIGHT;
+            } else if (phase == LP_TRACE && trace_run<MESH>(C, T, stack, shadow ? SUN_E : d, shadow, ERTB_TRACE_STEPS))
                 phase = shadow ? LP_SHADE : LP_FLIGHT;
         }
 

@@ -304,6 +304,7 @@ struct ertb_scene {
     std::vector<int> mesh_bsdf_base; // per group: first row of its mesh BSDFs in the table blob
     bool needs_3d = false;      // canopy or perspective sensor: rendered by ertb_canopy_kernel
     bool has_mesh = false;      // some group holds triangles: the MESH instances of that kernel
+    bool small_groups = false;  // every group holds <= ERTB_VOTE_MAX_PRIMS primitives: the VOTE form of its BVH stage
 };
 
 static int build_canopy(ertb_scene *S) {
@@ -395,12 +396,15 @@ static int build_canopy(ertb_scene *S) {
     // bottom level: one tree per group, disks reordered into leaf order
     std::vector<ErtbBvhNode> blas;
     std::vector<int> blas_root(ng);
+    S->small_groups = ng > 0;
     std::vector<float> disks;
     for (int g = 0; g < ng; ++g) {
         std::vector<int> order;
+        if (dboxes[g].size() > (size_t) ERTB_VOTE_MAX_PRIMS) S->small_groups = false;
         blas_root[g] = build_bvh(dboxes[g], blas, order, (int) disks.size() / 8);
         for (int i : order) disks.insert(disks.end(), &prims[g][8 * (size_t) i], &prims[g][8 * (size_t) i] + 8);
     }
+    if (const char *e = getenv("ERTB_CANOPY_VOTE")) S->small_groups = atoi(e) != 0; // developer knob (A/B runs)
     // top level over the instances (float coordinates relative to the canopy origin)
     std::vector<BvhBox> iboxes(ninst);
     for (int i = 0; i < ninst; ++i)
@@ -1450,14 +1454,22 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
         if (!PW_ && bands) ERTB_POOL_VARIANT_B(MACRO, SPH_, POL_, false, true);                       \
         else ERTB_POOL_VARIANT_B(MACRO, SPH_, POL_, PW_, false);                                      \
     } while (0)
+#define ERTB_CANOPY_VARIANT_V(MACRO, MESH_, VOTE_)                                                    \
+    do {                                                                                              \
+        if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true, MESH_, VOTE_>)); else MACRO((ertb_canopy_kernel<false, true, MESH_, VOTE_>)); } \
+        else    { if (with_stats) MACRO((ertb_canopy_kernel<true, false, MESH_, VOTE_>)); else MACRO((ertb_canopy_kernel<false, false, MESH_, VOTE_>)); } \
+    } while (0)
+#define ERTB_CANOPY_VARIANT(MACRO, MESH_)                                                             \
+    do {                                                                                              \
+        if (S->small_groups) ERTB_CANOPY_VARIANT_V(MACRO, MESH_, true);                               \
+        else ERTB_CANOPY_VARIANT_V(MACRO, MESH_, false);                                              \
+    } while (0)
 #define ERTB_DISPATCH(MACRO)                                                                          \
     do {                                                                                              \
         if (c3d) {                                                                                    \
             if (S->has_mesh || S->bsdf_type >= ERTB_BSDF_OCEAN_MISHCHENKO || S->astro_diameter > 0.0 || S->phase_mis) { /* the general instances */ \
-                if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true, true>)); else MACRO((ertb_canopy_kernel<false, true, true>)); } \
-                else    { if (with_stats) MACRO((ertb_canopy_kernel<true, false, true>)); else MACRO((ertb_canopy_kernel<false, false, true>)); } \
-            } else if (pw) { if (with_stats) MACRO((ertb_canopy_kernel<true, true>)); else MACRO((ertb_canopy_kernel<false, true>)); } \
-            else    { if (with_stats) MACRO((ertb_canopy_kernel<true, false>)); else MACRO((ertb_canopy_kernel<false, false>)); } \
+                ERTB_CANOPY_VARIANT(MACRO, true);                                                     \
+            } else ERTB_CANOPY_VARIANT(MACRO, false);                                                 \
         } else if (pw && pol) ERTB_POOL_VARIANT(MACRO, false, true, true);                            \
         else if (pw) ERTB_POOL_VARIANT(MACRO, false, false, true);                                    \
         else if (use_pool && pol) {                                                                   \
