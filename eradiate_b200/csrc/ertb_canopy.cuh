@@ -32,9 +32,17 @@
 #include "ertb_kernel_pool.cuh" // film_flush_warp
 #include "ertb_piecewise.cuh"
 
-#define ERTB_CANOPY_BLOCK 128
+// 4 CTAs of 256 threads per SM = 64 registers, 32 resident warps.  The walk waits on dependent node fetches (35 % of the
+// stall samples are long-scoreboard, profiles/r02t): resident warps are what hides them, and the state the register
+// cap pushes into local memory belongs to the event code, not to the traversal loop.  Measured (C4 mdistant /
+// C4 perspective / abstract trees, Mpaths/s): 128 x 4 (128 reg.) 150 / 192 / 696; 128 x 5 (96) 157 / 210 / 662;
+// 128 x 6 (80) 161 / 217 / 722; 128 x 7 (72) 173 / 235 / 730; 128 x 8 (64) 172 / 237 / 751; 256 x 4 (64) 173 / 240 / 753;
+// 128 x 10 (48) 168 / 232 / 740; 256 x 5 (48) 168 / 231 / 748; 256 x 6 (40) 160 / 204 / 711.
+#ifndef ERTB_CANOPY_BLOCK
+#define ERTB_CANOPY_BLOCK 256
+#endif
 #ifndef ERTB_CANOPY_MINB
-#define ERTB_CANOPY_MINB 5 // 96 registers: 20 warps / SM hide the dependent node fetches (B200: +14 % over 4)
+#define ERTB_CANOPY_MINB 4
 #endif
 #ifndef ERTB_BVH_LEAF
 #define ERTB_BVH_LEAF 1 // primitives per BVH leaf: disk tests run with ~1.5 active lanes, box tests with many
@@ -71,8 +79,11 @@ __device__ __forceinline__ float disk_hit(float4 c, float4 n, f3 o, f3 d, float 
 }
 
 #ifndef ERTB_TRACE_STEPS
-#define ERTB_TRACE_STEPS 32 // node visits per sub-slice of the BVH walk
+#define ERTB_TRACE_STEPS 32 // VOTE form: node visits per sub-slice of the BVH walk
 #endif
+#ifndef ERTB_TRACE_STEPS_FIXED
+#define ERTB_TRACE_STEPS_FIXED 48 // fixed form (large groups): node visits per slice; at 64 registers 24 / 32 / 48 / 64
+#endif                            // visits give C4 160 / 173 / 187 / 187 (mdistant), 224 / 240 / 253 / 246 (camera)
 #ifndef ERTB_TRACE_SUBS
 #define ERTB_TRACE_SUBS 2 // VOTE form: sub-slices per trip of the main loop, at most
 #endif
@@ -580,7 +591,7 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
         }
 
         // ================= BVH walk, one slice (nearest leaf of a path segment, or any leaf on a shadow ray) =================
-        // Two forms.  Fixed slices (VOTE = false): the lanes that walk advance by ERTB_TRACE_STEPS node visits.  Every
+        // Two forms.  Fixed slices (VOTE = false): the lanes that walk advance by ERTB_TRACE_STEPS_FIXED node visits.  Every
         // trip of the main loop costs the other stages' votes and divergent code -- and the set-up of the walk itself --
         // whatever the number of lanes that need them (C4: 112 / 158 / 168 / 160 Mpaths/s at slices of 8 / 32 / 64 /
         // 128 visits): short slices pay it too often, long ones keep finished lanes waiting.  VOTE = true: EVERY lane
@@ -592,7 +603,7 @@ __global__ void __launch_bounds__(ERTB_CANOPY_BLOCK, ERTB_CANOPY_MINB) ertb_cano
             if (VOTE) {
                 if (trace_run<MESH, true>(C, T, stack, shadow ? SUN_E : d, shadow, ERTB_TRACE_STEPS, phase == LP_TRACE))
                     phase = shadow ? LP_SHADE : LP_FLIGHT;
-            } else if (phase == LP_TRACE && trace_run<MESH>(C, T, stack, shadow ? SUN_E : d, shadow, ERTB_TRACE_STEPS))
+            } else if (phase == LP_TRACE && trace_run<MESH>(C, T, stack, shadow ? SUN_E : d, shadow, ERTB_TRACE_STEPS_FIXED))
                 phase = shadow ? LP_SHADE : LP_FLIGHT;
         }
 
