@@ -1421,13 +1421,14 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     const bool gen_needed = !c3d && (hs.desc.type == ERTB_SENSOR_MPDISTANT || hs.desc.type == ERTB_SENSOR_MRADIANCEMETER ||
                                      S->astro_diameter > 0.0 || S->phase_mis);
     if (gen_needed) use_pool = true;
-    const int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? (pol ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK) : ERTB_BLOCK);
     const bool bands = S->base.n_bands > 1;
+    int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? ertb_pool_block(pol, bands && !pw) : ERTB_BLOCK);
     size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol, bands && !pw) : (size_t) S->base.blob_bytes;
     if (use_pool && smem > (size_t) S->max_smem_optin) { // huge tables: fall back to the register kernel
         if (pol || pw || gen_needed) return set_error("scene tables leave no shared memory for the path pools");
         use_pool = false;
         smem = (size_t) S->base.blob_bytes;
+        block = ERTB_BLOCK;
     }
     // ... and so do the plugins added after SURVEY 8a (glint family, mqdiffuse): the lean instances keep the
     // instruction stream of the headline configurations free of them (the register and 3D kernels are general)

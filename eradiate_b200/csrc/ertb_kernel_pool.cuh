@@ -32,11 +32,18 @@
 #ifndef ERTB_POOL_NS
 #define ERTB_POOL_NS 64 // records per warp (multiple of 32)
 #endif
+// Launch shape of the scalar instances: 2 CTAs of 448 threads = 28 resident warps at 72 registers.  Round 1 ran 6 CTAs
+// of 128 threads (24 warps, 80 registers; registers and shared memory both allowed exactly 6).  A third of the stall
+// samples of the C2 launch are fixed-latency waits (profiles/r02u), which more warps hide; warps cost pool space, and
+// big CTAs pay for it by staging two copies of the table blob instead of six.  Measured (STATS instances, Mpaths/s;
+// C2 / C3 banded / plane-parallel AFGL + RPV): 128 x 6: 9214 / 3535 / 7488; 128 x 7: 9622 / - / 7433; 256 x 4: 9476 /
+// 3599 / 6822; 448 x 2: 9613 / 4042 / 7448; 512 x 2: 9470 / 3973 / 6864; 896 x 1: 9677 / - / 7394; 1024 x 1: 9616 / - /
+// 6772; banded 256 x 3: 3855, 384 x 2: 3872, 320 x 3: 3898, 192 x 4: 3862.
 #ifndef ERTB_POOL_BLOCK
-#define ERTB_POOL_BLOCK 128
+#define ERTB_POOL_BLOCK 448
 #endif
 #ifndef ERTB_POOL_MINB
-#define ERTB_POOL_MINB 6
+#define ERTB_POOL_MINB 2
 #endif
 // Polarized instances: the table blob is replicated per CTA, so a few big CTAs leave more shared memory to the
 // pools than many small ones (warps never synchronise with each other after the tables are staged)
@@ -46,6 +53,21 @@
 #ifndef ERTB_POOL_MINB_POL
 #define ERTB_POOL_MINB_POL 1 // polarized instances: CTAs per SM at ERTB_POOL_BLOCK_POL threads
 #endif
+// Banded instances (the record is two fields longer and the table blob holds the aerosol tables as well): fewer, bigger
+// CTAs stage fewer copies of the blob and leave room for more warps
+#ifndef ERTB_POOL_BLOCK_BANDS
+#define ERTB_POOL_BLOCK_BANDS ERTB_POOL_BLOCK
+#endif
+#ifndef ERTB_POOL_MINB_BANDS
+#define ERTB_POOL_MINB_BANDS ERTB_POOL_MINB
+#endif
+// launch shape of an instance
+__host__ __device__ constexpr int ertb_pool_block(bool pol, bool bands) {
+    return pol ? ERTB_POOL_BLOCK_POL : (bands ? ERTB_POOL_BLOCK_BANDS : ERTB_POOL_BLOCK);
+}
+__host__ __device__ constexpr int ertb_pool_minb(bool pol, bool bands) {
+    return pol ? ERTB_POOL_MINB_POL : (bands ? ERTB_POOL_MINB_BANDS : ERTB_POOL_MINB);
+}
 #ifndef ERTB_WALK_UNROLL
 #define ERTB_WALK_UNROLL 2 // free flights per loop-control vote in the walk phase
 #endif
@@ -86,7 +108,7 @@ enum : unsigned {
 // segment, and (band index | descending << 8)
 __host__ __device__ inline size_t ertb_pool_smem_bytes(size_t blob_bytes, bool pol = false, bool bands = false) {
     size_t blob = (blob_bytes + 15) & ~size_t(15);
-    size_t warps = (pol ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK) / 32;
+    size_t warps = (size_t) ertb_pool_block(pol, bands) / 32;
     return blob + warps * (size_t) ((pol ? PF_COUNT_POL : PF_COUNT) + (bands ? 2 : 0)) * (pol ? ERTB_POOL_NS_POL : ERTB_POOL_NS) * 4 + warps * 32 * 4;
 }
 
@@ -256,7 +278,7 @@ __device__ __noinline__ void film_flush_warp(const ErtbParams &P, unsigned lane,
 // class 3 of the per-pixel table carries the start altitude) and `mpdistant` (the film sample picks the
 // target point). A template parameter for the same reason as COLL: the C2 instance must not change.
 template <bool SPH, bool STATS, bool POL, bool PW = false, bool COLL = false, bool BANDS = false, bool GEN = false>
-__global__ void __launch_bounds__(POL ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK, POL ? ERTB_POOL_MINB_POL : ERTB_POOL_MINB) ertb_render_pool_kernel(const ErtbParams P) {
+__global__ void __launch_bounds__(ertb_pool_block(POL, BANDS), ertb_pool_minb(POL, BANDS)) ertb_render_pool_kernel(const ErtbParams P) {
     static_assert(!(PW && BANDS), "the piecewise integrator has no null collisions");
     static_assert(!(PW && SPH), "the piecewise medium is a plane-parallel layer stack");
     constexpr int NS = POL ? ERTB_POOL_NS_POL : ERTB_POOL_NS; // records per warp
@@ -276,7 +298,7 @@ __global__ void __launch_bounds__(POL ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK, P
     const unsigned lt_mask = (1u << lane) - 1u;
     float *wp = smem + blob_words + warp * (NF * NS);
     unsigned *wpu = reinterpret_cast<unsigned *>(wp);
-    constexpr int NW = (POL ? ERTB_POOL_BLOCK_POL : ERTB_POOL_BLOCK) / 32; // warps per CTA
+    constexpr int NW = ertb_pool_block(POL, BANDS) / 32; // warps per CTA
     int *list = reinterpret_cast<int *>(smem + blob_words + NW * (NF * NS)) + warp * 32;
 
     if (P.blob_bytes > 0) tma_stage(tb, P.blob, (unsigned) P.blob_bytes, &mbar);
