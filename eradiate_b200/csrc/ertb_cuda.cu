@@ -10,6 +10,7 @@
 #include <ctime>
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -249,6 +250,10 @@ static int build_bvh(const std::vector<BvhBox> &boxes, std::vector<ErtbBvhNode> 
         }
     return root;
 }
+
+// largest dynamic shared-memory size requested so far, per (device, kernel function): see ERTB_OCC
+static std::map<std::pair<int, const void *>, size_t> g_smem_attr;
+static std::mutex g_smem_attr_mutex;
 
 struct ertb_scene {
     int device = 0;
@@ -1434,12 +1439,23 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     // instruction stream of the headline configurations free of them (the register and 3D kernels are general)
     const bool gen = gen_needed || (use_pool && !c3d && S->bsdf_type >= ERTB_BSDF_OCEAN_MISHCHENKO);
     // (attribute + occupancy are queried once per kernel instantiation and table size, then cached)
+    // The dynamic shared-memory limit is an attribute of the FUNCTION (per device), shared by every scene and table
+    // size in the process: it is only ever raised.  (A spectral loop whose contexts alternate between two blob sizes
+    // used to lower it again on the second size and fail with "invalid argument" on the third launch, once the 448-thread
+    // CTAs needed more than the 48 KB every function has by default.)
 #define ERTB_OCC(KERNEL)                                                                              \
     do {                                                                                              \
+        {                                                                                             \
+            std::lock_guard<std::mutex> lock(g_smem_attr_mutex);                                      \
+            size_t &cur = g_smem_attr[std::make_pair(S->device, (const void *) KERNEL)];              \
+            if (smem > cur) {                                                                         \
+                CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+                cur = smem;                                                                           \
+            }                                                                                         \
+        }                                                                                             \
         auto key = std::make_pair((const void *) KERNEL, smem);                                       \
         auto it = S->occupancy.find(key);                                                             \
         if (it != S->occupancy.end()) { blocks_per_sm = it->second; break; }                          \
-        CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, KERNEL, block, smem)); \
         S->occupancy[key] = blocks_per_sm;                                                            \
     } while (0)

@@ -1141,6 +1141,23 @@ def test_mi_render_pipelined_equals_sequential():
     assert np.allclose(again.raw["sum_l"], ref.raw["sum_l"], rtol=1e-10)
 
 
+def test_spectral_sweep_with_changing_table_sizes():
+    """A spectral loop over 96 contexts of one scene: the number of majorant bands -- hence the size of the table
+    blob and the dynamic shared memory of a launch -- changes from context to context and comes back.  The limit is an
+    attribute of the kernel FUNCTION: it must only ever be raised (regression: the third size used to fail with
+    "invalid argument" once a CTA needed more than the default 48 KB).  Sequential and pipelined loops agree."""
+    kdict = scenes.atmosphere_scene(geometry="spherical_shell", atmosphere="afgl",
+                                    sensor={"type": "mdistant", "vza": [0.0], "vaa": 0.0}, spp=1 << 10)
+    mi_scene = mi_traverse(mi_load_dict(kdict), scenes.spectral_update_map(1200, spherical=True))
+    ctxs = [KernelContext(w=w) for w in np.linspace(400.0, 1000.0, 96)]
+    seq = mi_render(mi_scene, ctxs, spp=1 << 10, seed_state=SeedState(0), pipelined=False)
+    pip = mi_render(mi_scene, ctxs, spp=1 << 10, seed_state=SeedState(0), pipelined=True)
+    assert len(seq) == len(pip) == 96
+    a = np.array([np.array(list(v.values())[0])[0, 0, 0] for v in seq.values()])
+    b = np.array([np.array(list(v.values())[0])[0, 0, 0] for v in pip.values()])
+    assert np.all(np.isfinite(a)) and np.all(a > 0) and np.allclose(a, b, rtol=1e-6)
+
+
 def test_band_sharded_mi_render_single_rank_equals_mi_render():
     from eradiate_b200.dist import mi_render_sharded
     spp = 1 << 12
