@@ -1429,6 +1429,12 @@ static int launch_render(ertb_scene *S, int sensor, uint64_t seed, uint64_t spp,
     const bool bands = S->base.n_bands > 1;
     int block = c3d ? ERTB_CANOPY_BLOCK : (use_pool ? ertb_pool_block(pol, bands && !pw) : ERTB_BLOCK);
     size_t smem = use_pool ? ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol, bands && !pw) : (size_t) S->base.blob_bytes;
+    // large tables: the pools of a full-size CTA do not fit next to them -- launch smaller CTAs of the same instance
+    // (every warp owns its pool; the kernel takes the number of warps from blockDim)
+    while (use_pool && smem > (size_t) S->max_smem_optin && block > 128) {
+        block -= 64;
+        smem = ertb_pool_smem_bytes((size_t) S->base.blob_bytes, pol, bands && !pw, block);
+    }
     if (use_pool && smem > (size_t) S->max_smem_optin) { // huge tables: fall back to the register kernel
         if (pol || pw || gen_needed) return set_error("scene tables leave no shared memory for the path pools");
         use_pool = false;

@@ -106,9 +106,10 @@ enum : unsigned {
 
 // BANDS instances append two fields to the record: the distance of the next band boundary along the
 // segment, and (band index | descending << 8)
-__host__ __device__ inline size_t ertb_pool_smem_bytes(size_t blob_bytes, bool pol = false, bool bands = false) {
+// (`threads`: CTA size of the launch, 0 = the instance's own; the host launches smaller CTAs when the tables are large)
+__host__ __device__ inline size_t ertb_pool_smem_bytes(size_t blob_bytes, bool pol = false, bool bands = false, int threads = 0) {
     size_t blob = (blob_bytes + 15) & ~size_t(15);
-    size_t warps = (size_t) ertb_pool_block(pol, bands) / 32;
+    size_t warps = (size_t) (threads > 0 ? threads : ertb_pool_block(pol, bands)) / 32;
     return blob + warps * (size_t) ((pol ? PF_COUNT_POL : PF_COUNT) + (bands ? 2 : 0)) * (pol ? ERTB_POOL_NS_POL : ERTB_POOL_NS) * 4 + warps * 32 * 4;
 }
 
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(ertb_pool_block(POL, BANDS), ertb_pool_minb(PO
     const unsigned lt_mask = (1u << lane) - 1u;
     float *wp = smem + blob_words + warp * (NF * NS);
     unsigned *wpu = reinterpret_cast<unsigned *>(wp);
-    constexpr int NW = ertb_pool_block(POL, BANDS) / 32; // warps per CTA
+    const int NW = (int) (blockDim.x >> 5); // warps per CTA (<= the instance's launch bound: large tables get smaller CTAs)
     int *list = reinterpret_cast<int *>(smem + blob_words + NW * (NF * NS)) + warp * 32;
 
     if (P.blob_bytes > 0) tma_stage(tb, P.blob, (unsigned) P.blob_bytes, &mbar);

@@ -1141,6 +1141,36 @@ def test_mi_render_pipelined_equals_sequential():
     assert np.allclose(again.raw["sum_l"], ref.raw["sum_l"], rtol=1e-10)
 
 
+def large_table_scene(integrator):
+    """4 096 layers under a four-component phase mixture with three 2 000-node irregular tables: ~150 KB of tables."""
+    n = 4096
+    zn = (np.arange(n) + 0.5) / n
+    vol = lambda v: scenes._volume(v, False, scenes.EARTH_RADIUS, scenes.TOA, 1.0e9)  # noqa: E731
+    mu = np.concatenate([np.linspace(-1.0, 0.5, 600), np.linspace(0.5, 1.0, 1401)[1:]])
+    phase = {"type": "multiphase", "use_mis": False, "phase0": {"type": "rayleigh"}, "weight0": vol(np.full(n, 1.0))}
+    for i, g in enumerate((0.5, 0.65, 0.8)):
+        p = (1.0 - g * g) / (4.0 * np.pi * (1.0 + g * g - 2.0 * g * mu) ** 1.5)
+        phase[f"phase{i + 1}"] = {"type": "tabphase_irregular", "values": ",".join(map(str, p)), "nodes": ",".join(map(str, mu))}
+        phase[f"weight{i + 1}"] = vol((0.3 + i) * np.exp(-(4.0 + 2.0 * i) * zn))
+    return scenes.atmosphere_scene(geometry="plane_parallel", n_layers=n, phase=phase, integrator=integrator, sza=30.0,
+                                   surface={"type": "diffuse", "reflectance": 0.2},
+                                   sensor={"type": "mdistant", "vza": [-40.0, 0.0, 50.0], "vaa": 0.0})
+
+
+@pytest.mark.parametrize("integrator", ["piecewise_volpath", "volpath"])
+def test_large_tables_get_smaller_ctas(oracle, integrator):
+    """Tables that leave no room in shared memory for the pools of a full-size CTA: the host launches smaller CTAs of
+    the same pool-kernel instance (the piecewise integrator has no other kernel to fall back to).  Same film as the
+    oracle's."""
+    sc = mi_load_dict(large_table_scene(integrator))
+    spp = 1 << 16
+    _, mean, var, st = gpu_render(sc, spp)
+    out = oracle.render(sc.flat.build_desc(), 0, 5, 1 << 14)
+    om, ov = stats_from_sums(out[1], out[2], 1 << 14)
+    z = z_scores(mean, var, om, ov, rel_floor=2e-6)
+    assert np.all(np.abs(z) < 4.5), (z, mean, om)
+
+
 def test_spectral_sweep_with_changing_table_sizes():
     """A spectral loop over 96 contexts of one scene: the number of majorant bands -- hence the size of the table
     blob and the dynamic shared memory of a launch -- changes from context to context and comes back.  The limit is an
