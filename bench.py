@@ -441,6 +441,14 @@ def run_cuda(args):
             run_cfg("C4: same scene, perspective 64x64 inside the atmosphere, spp 2^11", c4, 1 << 11, sensor=1),
             run_cfg("C5 band @550 nm: polarized ocean + AFGL + polarized aerosol, spherical, mdistant 1, spp 2^26",
                     scenes.config_c5(), 1 << 26),
+            # a canopy of small groups (3 abstract trees: 300 disc leaves + a trunk each): the VOTE form of the 3D
+            # kernel's BVH stage, as opposed to C4's 60 k-leaf groups
+            run_cfg("abstract-tree canopy (3 trees x 300 leaves + trunks) + AFGL + Lambertian, mdistant 5, spp 2^20",
+                    scenes.atmosphere_scene(geometry="plane_parallel", n_layers=60, sza=40.0, saa=30.0,
+                                            canopy={"trees": {}, "size": (8.0, 8.0, 4.1)},
+                                            surface={"type": "diffuse", "reflectance": 0.2},
+                                            sensor={"type": "mdistant", "vza": [-55.0, -20.0, 0.0, 30.0, 65.0], "vaa": 30.0}),
+                    1 << 20),
         ]
 
     if rank == 0:
