@@ -100,3 +100,29 @@ def test_renders_are_sensitive_to_the_profile(oracle, name):
     gm, gv = np.array(gold["mean"]), np.array(gold["var_of_mean"])
     z = np.abs(mean - gm) / np.sqrt(var + gv)
     assert (z ** 2).sum() > 50.0, z  # chi^2 over the 5 pixels (P < 1e-8 under "no difference")
+
+
+def test_profile_below_a_multiphase_node_with_mis():
+    """multiphase.cpp:176-200 (use_mis): the mixture weight sum_j w_j value_j / sum_j w_j pdf_j over the split leaves
+    is the reference's own weight for the layer's depolarization, because the two halves share the sampling density."""
+    n = 10
+    rho = np.linspace(0.05, 0.4, n)
+    vol = lambda v: scenes._volume(np.asarray(v, float), False, scenes.EARTH_RADIUS, scenes.TOA, 1.0e9)  # noqa: E731
+    phase = {"type": "multiphase", "use_mis": True,
+             "phase0": {"type": "rayleigh", "depolarization": vol(rho)}, "weight0": vol(np.full(n, 2.0)),
+             "phase1": {"type": "hg", "g": 0.7}, "weight1": vol(np.linspace(0.5, 1.5, n))}
+    sc = mi_load_dict(scenes.atmosphere_scene(geometry="plane_parallel", n_layers=n, phase=phase))
+    leaves = sc.flat.phase_leaves(n)
+    assert [ph.type for ph, _ in leaves] == ["rayleigh", "rayleigh", "hg"] and sc.flat._phase_mis
+    w = np.stack([p for _, p in leaves]).astype(np.float64)
+    assert np.allclose(w.sum(axis=0), 1.0, atol=1e-6)
+    ct = np.linspace(-1.0, 1.0, 11)[:, None]
+    pdf_ray = 3.0 / (16.0 * np.pi) * (1.0 + ct * ct)
+    g = 0.7
+    hg = (1.0 - g * g) / (4.0 * np.pi * (1.0 + g * g + 2.0 * g * ct) ** 1.5)  # value == pdf; either cosine convention
+    num = w[0] * rayleigh_value(ct, leaves[0][0].rho) + w[1] * rayleigh_value(ct, leaves[1][0].rho) + w[2] * hg
+    den = (w[0] + w[1]) * pdf_ray + w[2] * hg
+    w_mol = 2.0 / (2.0 + np.linspace(0.5, 1.5, n))
+    ref = (w_mol * rayleigh_value(ct, rho.astype(np.float32)) + (1.0 - w_mol) * hg) / (w_mol * pdf_ray + (1.0 - w_mol) * hg)
+    assert np.allclose(num / den, ref, rtol=5e-6)
+    assert sc.flat.build_desc().phase_mis == 1
